@@ -1,0 +1,663 @@
+// C ABI + host orchestration of the REPPO update step (see include/reppo_b200.h).
+//
+// The host side only sequences kernels on the caller's stream; all device memory belongs to the
+// caller.  One minibatch step = critic forward/backward/clip/Adam followed by actor
+// forward/backward/clip/Adam (src/jaxrl/reppo.py:466-643; src/torchrl/reppo.py:622-629), the
+// whole update = epochs x minibatches of those, optionally captured once into a CUDA graph.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/reppo_b200.h"
+#include "kernels.h"
+
+using namespace reppo;
+
+namespace {
+
+struct Linear {
+  int64_t w = -1, b = -1, g = -1, beta = -1;  // offsets into the flat arena (floats)
+  int in = 0, out = 0;
+};
+struct Mlp {
+  std::vector<Linear> layers;
+  int norm = NORM_NONE;  // applied after every layer but the last
+};
+struct TensorInfo {
+  std::string name;
+  int64_t off;
+  int rows, cols;  // cols == 0: vector of `rows`; rows == 0: scalar
+};
+struct Acts {  // saved activations of one MLP evaluation
+  std::vector<float*> z, x, rstd, mean;
+  float* out = nullptr;
+};
+struct Sem {
+  float norm_eps, bias_scale, action_clip;
+  int clip_policy_sample, old_logp_at_clipped, reward_head, aux_mask_done, torch_opt;
+  float force_min_std;  // < 0: use hp.actor_min_std
+};
+
+// minimal NCCL surface (resolved with dlsym from libnccl.so.2)
+typedef struct ncclComm* ncclComm_t;
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+struct GraphKey {
+  reppo_state state;
+  reppo_batch batch;
+  reppo_plan plan;
+  reppo_hyper hp;
+};
+
+std::string g_create_error;
+
+}  // namespace
+
+struct reppo_ctx {
+  reppo_shape shape;
+  Sem sem;
+  Mlp feature, head, pred, actor;
+  int64_t zero_dist_off = 0, critic_count = 0, actor_count = 0;
+  int pred_out = 0, K0 = 0;
+  std::vector<TensorInfo> critic_tensors, actor_tensors;
+  std::vector<float> edges_h, support_h;
+  HLConsts hl{};
+  // workspace
+  char* ws = nullptr;
+  size_t ws_bytes = 0, ws_need = 0;
+  float *edges_d = nullptr, *support_d = nullptr, *partials = nullptr;
+  float *x0 = nullptr, *xs = nullptr, *xa0 = nullptr;
+  Acts fa, ha, pa, aa, oa;
+  float *tmpA = nullptr, *tmpB = nullptr, *dxs = nullptr, *dfeat = nullptr, *dlogits = nullptr, *dpred = nullptr,
+        *dout = nullptr, *dx0 = nullptr;
+  float *logp = nullptr, *kl = nullptr, *q = nullptr, *gmu = nullptr, *gsig = nullptr, *scratch_metrics = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  // graph cache
+  cudaGraphExec_t graph_exec = nullptr;
+  GraphKey graph_key{};
+  bool graph_valid = false;
+  int64_t graph_launches = 0;
+  // nccl
+  NcclApi nccl;
+  ncclComm_t comm = nullptr;
+  int world = 1, rank = 0;
+};
+
+namespace {
+
+int fail(reppo_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    ++c->launches;                                                                                 \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(c, REPPO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));         \
+  } while (0)
+#define RET(expr)                       \
+  do {                                  \
+    int r__ = (expr);                   \
+    if (r__ != REPPO_OK) return r__;    \
+  } while (0)
+
+void add_fcnn(std::vector<TensorInfo>& ts, int64_t& off, Mlp& mlp, const std::string& prefix, int in_f, int hidden,
+              int out_f, int layers, bool input_activation, int norm) {
+  // Sequential indices of torch_models.FCNN (:97-139): an input activation occupies slot 0.
+  const int shift = input_activation ? 1 : 0;
+  mlp.norm = norm;
+  for (int i = 0; i < layers; ++i) {
+    Linear L;
+    L.in = (i == 0) ? in_f : hidden;
+    L.out = (i == layers - 1) ? out_f : hidden;
+    const std::string blk = prefix + ".net." + std::to_string(shift + i);
+    L.w = off; ts.push_back({blk + ".0.weight", off, L.out, L.in}); off += static_cast<int64_t>(L.out) * L.in;
+    L.b = off; ts.push_back({blk + ".0.bias", off, L.out, 0}); off += L.out;
+    if (norm != NORM_NONE && i < layers - 1) {
+      L.g = off; ts.push_back({blk + ".1.weight", off, L.out, 0}); off += L.out;
+      if (norm == NORM_LAYER) { L.beta = off; ts.push_back({blk + ".1.bias", off, L.out, 0}); off += L.out; }
+    }
+    mlp.layers.push_back(L);
+  }
+}
+
+// torch.linspace(start, end, steps, dtype=float32) on the CPU (symmetric two-sided evaluation)
+std::vector<float> linspace_f32(double start_d, double end_d, int steps) {
+  const float start = static_cast<float>(start_d), end = static_cast<float>(end_d);
+  std::vector<float> v(steps);
+  if (steps == 1) { v[0] = start; return v; }
+  const float step = (end - start) / static_cast<float>(steps - 1);
+  const int half = steps / 2;
+  for (int i = 0; i < steps; ++i)
+    v[i] = (i < half) ? start + step * static_cast<float>(i) : end - step * static_cast<float>(steps - i - 1);
+  return v;
+}
+
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes) { const size_t o = off; off += (bytes + 255) & ~static_cast<size_t>(255); return o; }
+};
+
+// lays the workspace out; when base == nullptr only sizes it
+size_t layout_workspace(reppo_ctx* c, char* base) {
+  const reppo_shape& s = c->shape;
+  const size_t R = s.max_rows, H = s.critic_hidden, Ha = s.actor_hidden, B = s.num_bins, A = s.action_dim;
+  const size_t P = c->pred_out, K0 = c->K0, D = s.obs_dim;
+  Bump bp;
+  auto F = [&](size_t n) -> float* {
+    const size_t o = bp.take(n * sizeof(float));
+    return base ? reinterpret_cast<float*>(base + o) : nullptr;
+  };
+  auto acts = [&](Acts& a, const Mlp& m, size_t out_dim) {
+    a.z.clear(); a.x.clear(); a.rstd.clear(); a.mean.clear();
+    for (size_t i = 0; i + 1 < m.layers.size(); ++i) {
+      const size_t h = m.layers[i].out;
+      a.z.push_back(F(R * h)); a.x.push_back(F(R * h)); a.rstd.push_back(F(R)); a.mean.push_back(F(R));
+    }
+    a.out = F(R * out_dim);
+  };
+  c->edges_d = F(B + 1); c->support_d = F(B); c->partials = F(kMaxPartials); c->scratch_metrics = F(M_NUM);
+  c->x0 = F(R * K0); c->xs = F(R * H); c->xa0 = F(R * D);
+  acts(c->fa, c->feature, H); acts(c->ha, c->head, B); acts(c->pa, c->pred, P);
+  acts(c->aa, c->actor, 2 * A); acts(c->oa, c->actor, 2 * A);
+  const size_t maxdim = std::max(std::max(H, Ha), std::max(std::max(B, P), std::max(K0, D)));
+  c->tmpA = F(R * maxdim); c->tmpB = F(R * maxdim);
+  c->dxs = F(R * H); c->dfeat = F(R * H); c->dlogits = F(R * B); c->dpred = F(R * P); c->dout = F(R * 2 * A);
+  c->dx0 = F(R * K0);
+  c->logp = F(R); c->kl = F(R); c->q = F(R); c->gmu = F(R * A); c->gsig = F(R * A);
+  return bp.off;
+}
+
+int gemm(reppo_ctx* c, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+         int ldc, const float* bias, int mode, int split_k, cudaStream_t st) {
+  // REPPO_GEMM_BF16 routes the aligned H x H layers to the tcgen05 kernel (gemm_bf16_tc.cu) once
+  // enabled; every other shape and the fp32 mode run the FFMA kernel.
+  CK(launch_gemm_f32(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, mode, split_k, st));
+  return REPPO_OK;
+}
+
+int mlp_forward(reppo_ctx* c, const Mlp& m, const float* params, const float* in, int rows, Acts& a, cudaStream_t st) {
+  const float* cur = in;
+  const int n = static_cast<int>(m.layers.size());
+  for (int i = 0; i < n; ++i) {
+    const Linear& L = m.layers[i];
+    const bool last = (i == n - 1);
+    float* dst = last ? a.out : a.z[i];
+    RET(gemm(c, false, true, rows, L.out, L.in, cur, L.in, params + L.w, L.in, dst, L.out, params + L.b, GEMM_STORE, 1, st));
+    if (!last) {
+      CK(launch_norm_act_fwd(m.norm, a.z[i], L.g >= 0 ? params + L.g : nullptr, L.beta >= 0 ? params + L.beta : nullptr,
+                             rows, L.out, c->sem.norm_eps, a.x[i], a.rstd[i], a.mean[i], st));
+      cur = a.x[i];
+    }
+  }
+  return REPPO_OK;
+}
+
+int wgrad_split(int out, int in, int rows) {
+  const int tiles = ((out + 63) / 64) * ((in + 63) / 64);
+  int split = std::max(1, 296 / std::max(1, tiles));
+  split = std::min(split, std::max(1, rows / 64));
+  return split;
+}
+
+// d: gradient w.r.t. the MLP output [rows, out_last] (read only).  grads == nullptr: frozen network (dgrad only).
+// dx_in != nullptr: also produce the gradient w.r.t. the MLP input (mode GEMM_STORE / GEMM_ACCUM).
+int mlp_backward(reppo_ctx* c, const Mlp& m, const float* params, float* grads, const float* in, int rows, const Acts& a,
+                 const float* d_out, float* dx_in, int dx_mode, float* bias2, float scale2, cudaStream_t st) {
+  const int n = static_cast<int>(m.layers.size());
+  const float* d = d_out;
+  for (int i = n - 1; i >= 0; --i) {
+    const Linear& L = m.layers[i];
+    const float* xin = (i == 0) ? in : a.x[i - 1];
+    if (grads != nullptr) {
+      RET(gemm(c, true, false, L.out, L.in, rows, d, L.out, xin, L.in, grads + L.w, L.in, nullptr, GEMM_ATOMIC,
+               wgrad_split(L.out, L.in, rows), st));
+      CK(launch_colsum(d, rows, L.out, L.out, grads + L.b, (i == n - 1) ? bias2 : nullptr, scale2, st));
+    }
+    if (i > 0) {
+      const Linear& Lp = m.layers[i - 1];
+      RET(gemm(c, false, false, rows, L.in, L.out, d, L.out, params + L.w, L.in, c->tmpA, L.in, nullptr, GEMM_STORE, 1, st));
+      CK(launch_norm_act_bwd(m.norm, c->tmpA, a.z[i - 1], Lp.g >= 0 ? params + Lp.g : nullptr,
+                             Lp.beta >= 0 ? params + Lp.beta : nullptr, a.rstd[i - 1], a.mean[i - 1], rows, L.in, c->tmpB,
+                             (grads && Lp.g >= 0) ? grads + Lp.g : nullptr, (grads && Lp.beta >= 0) ? grads + Lp.beta : nullptr,
+                             st));
+      d = c->tmpB;
+    } else if (dx_in != nullptr) {
+      RET(gemm(c, false, false, rows, L.in, L.out, d, L.out, params + L.w, L.in, dx_in, L.in, nullptr, dx_mode, 1, st));
+    }
+  }
+  return REPPO_OK;
+}
+
+int check_rows(reppo_ctx* c, int rows) {
+  if (c->ws == nullptr) return fail(c, REPPO_ERR_WORKSPACE, "workspace not set (reppo_set_workspace)");
+  if (rows <= 0 || rows > c->shape.max_rows) return fail(c, REPPO_ERR_INVALID, "rows outside (0, shape.max_rows]");
+  return REPPO_OK;
+}
+
+int critic_trunk(reppo_ctx* c, const float* cp, int rows, bool with_pred, cudaStream_t st) {
+  RET(mlp_forward(c, c->feature, cp, c->x0, rows, c->fa, st));
+  CK(launch_norm_act_fwd(NORM_NONE, c->fa.out, nullptr, nullptr, rows, c->shape.critic_hidden, 0.f, c->xs, nullptr, nullptr, st));
+  RET(mlp_forward(c, c->head, cp, c->xs, rows, c->ha, st));
+  if (with_pred) RET(mlp_forward(c, c->pred, cp, c->xs, rows, c->pa, st));
+  return REPPO_OK;
+}
+
+int allreduce_grads(reppo_ctx* c, float* g, int64_t n, cudaStream_t st) {
+  if (c->comm == nullptr) return REPPO_OK;
+  const int r = c->nccl.AllReduce(g, g, static_cast<size_t>(n), /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, st);
+  ++c->launches;
+  if (r != 0) return fail(c, REPPO_ERR_NCCL, std::string("ncclAllReduce: ") + c->nccl.GetErrorString(r));
+  return REPPO_OK;
+}
+
+float inv_rows(const reppo_hyper* hp, int mb) {
+  const int w = hp->world_size > 0 ? hp->world_size : 1;
+  return 1.f / (static_cast<float>(mb) * static_cast<float>(w));
+}
+
+int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb,
+                     const reppo_hyper* hp, float* metrics, cudaStream_t st) {
+  RET(check_rows(c, mb));
+  const reppo_shape& sh = c->shape;
+  const float* cp = s->critic.params;
+  float* cg = s->critic.grads;
+  const float inv = inv_rows(hp, mb);
+  const int no_mask = (sh.semantics == REPPO_SEM_TORCH && hp->partial_reset) ? 1 : 0;
+  if (c->sem.reward_head && b->reward == nullptr) return fail(c, REPPO_ERR_INVALID, "batch.reward is required in JAX semantics");
+  CK(launch_metrics_init(metrics, kCriticMetricMask, st));
+  CK(cudaMemsetAsync(cg, 0, static_cast<size_t>(c->critic_count) * sizeof(float), st));
+  CK(launch_gather_concat(b->critic_obs, sh.critic_obs_dim, b->action, sh.action_dim, idx, 0, mb, c->x0, c->K0, st));
+  RET(critic_trunk(c, cp, mb, true, st));
+  CK(launch_critic_ce(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, b->target, b->truncated, idx, mb, inv, no_mask,
+                      c->dlogits, metrics, st));
+  CK(launch_critic_aux(c->pa.out, c->pred_out, sh.critic_hidden, c->sem.reward_head, c->sem.aux_mask_done, b->next_emb,
+                       b->reward, b->done, b->truncated, idx, mb, inv, no_mask, hp->aux_loss_mult, c->dpred, metrics, st));
+  RET(mlp_backward(c, c->head, cp, cg, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, cg + c->zero_dist_off,
+                   c->sem.bias_scale, st));
+  RET(mlp_backward(c, c->pred, cp, cg, c->xs, mb, c->pa, c->dpred, c->dxs, GEMM_ACCUM, nullptr, 0.f, st));
+  CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden, c->dfeat,
+                         nullptr, nullptr, st));
+  RET(mlp_backward(c, c->feature, cp, cg, c->x0, mb, c->fa, c->dfeat, nullptr, GEMM_STORE, nullptr, 0.f, st));
+  return REPPO_OK;
+}
+
+ActorConsts actor_consts(const reppo_ctx* c, const reppo_hyper* hp) {
+  ActorConsts ac{};
+  ac.min_std = c->sem.force_min_std >= 0.f ? c->sem.force_min_std : hp->actor_min_std;
+  ac.action_clip = c->sem.action_clip;
+  ac.kl_bound = hp->kl_bound;
+  ac.target_entropy = static_cast<float>(c->shape.action_dim) * hp->ent_target_mult;
+  const bool torch_sem = c->shape.semantics == REPPO_SEM_TORCH;
+  ac.reduce_kl = (torch_sem || hp->reduce_kl) ? 1.f : 0.f;
+  ac.clip_policy_sample = c->sem.clip_policy_sample;
+  ac.old_logp_at_clipped = c->sem.old_logp_at_clipped;
+  ac.kl_mode = hp->kl_clip_mode;
+  ac.update_entropy = (torch_sem || hp->update_entropy_lagrangian) ? 1 : 0;
+  ac.update_kl = (torch_sem || hp->update_kl_lagrangian) ? 1 : 0;
+  return ac;
+}
+
+int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb,
+                    const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, cudaStream_t st) {
+  RET(check_rows(c, mb));
+  if (hp->kl_clip_mode < 0 || hp->kl_clip_mode > 2) return fail(c, REPPO_ERR_INVALID, "unknown actor_kl_clip_mode");
+  const reppo_shape& sh = c->shape;
+  const int A = sh.action_dim, Dc = sh.critic_obs_dim;
+  const float* cp = s->critic.params;
+  const float* ap = s->actor.params;
+  float* ag = s->actor.grads;
+  const float inv = inv_rows(hp, mb);
+  const ActorConsts ac = actor_consts(c, hp);
+  CK(launch_metrics_init(metrics, kActorMetricMask, st));
+  CK(cudaMemsetAsync(ag, 0, static_cast<size_t>(c->actor_count) * sizeof(float), st));
+  CK(launch_gather_concat(b->obs, sh.obs_dim, nullptr, 0, idx, 0, mb, c->xa0, sh.obs_dim, st));
+  RET(mlp_forward(c, c->actor, ap, c->xa0, mb, c->aa, st));
+  RET(mlp_forward(c, c->actor, s->actor_old, c->xa0, mb, c->oa, st));
+  CK(launch_gather_concat(b->critic_obs, Dc, nullptr, 0, idx, 0, mb, c->x0, c->K0, st));
+  CK(launch_actor_sample(c->aa.out, c->oa.out, eps_pi, eps_kl, mb, A, sh.kl_samples, ac, c->x0 + Dc, c->K0, c->logp, c->kl,
+                         c->gmu, c->gsig, st));
+  RET(critic_trunk(c, cp, mb, false, st));
+  CK(launch_actor_q(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, c->kl, mb, inv, ac.kl_mode, ac.kl_bound, c->q,
+                    c->dlogits, st));
+  RET(mlp_backward(c, c->head, cp, nullptr, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, st));
+  CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden, c->dfeat,
+                         nullptr, nullptr, st));
+  RET(mlp_backward(c, c->feature, cp, nullptr, c->x0, mb, c->fa, c->dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, st));
+  CK(launch_actor_grad(c->aa.out, eps_pi, c->x0 + Dc, c->K0, c->dx0 + Dc, c->K0, c->logp, c->kl, c->q, c->gmu, c->gsig, ap,
+                       mb, A, inv, ac, c->dout, ag, metrics, st));
+  RET(mlp_backward(c, c->actor, ap, ag, c->xa0, mb, c->aa, c->dout, nullptr, GEMM_STORE, nullptr, 0.f, st));
+  return REPPO_OK;
+}
+
+int clip_adam_impl(reppo_ctx* c, const reppo_net_state* net, int64_t n, const reppo_hyper* hp, float* gn_out, cudaStream_t st) {
+  if (c->ws == nullptr) return fail(c, REPPO_ERR_WORKSPACE, "workspace not set (reppo_set_workspace)");
+  AdamConsts a{};
+  a.lr = hp->lr; a.b1 = 0.9f; a.b2 = 0.999f; a.eps = 1e-8f;
+  a.weight_decay = c->sem.torch_opt ? 0.01f : 0.f;  // torch.optim.AdamW default (src/torchrl/reppo.py:527-534)
+  a.max_grad_norm = hp->max_grad_norm;
+  a.torch_clip = c->sem.torch_opt;
+  CK(launch_clip_adam(net->params, net->grads, net->adam_m, net->adam_v, n, net->step, c->partials, a, gn_out, st));
+  ++c->launches;  // two kernels
+  return REPPO_OK;
+}
+
+int critic_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb,
+                     const reppo_hyper* hp, float* metrics, cudaStream_t st) {
+  RET(critic_grad_impl(c, s, b, idx, mb, hp, metrics, st));
+  RET(allreduce_grads(c, s->critic.grads, c->critic_count, st));
+  return clip_adam_impl(c, &s->critic, c->critic_count, hp, metrics + M_CRITIC_GRAD_NORM, st);
+}
+
+int actor_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb, const float* eps_pi,
+                    const float* eps_kl, const reppo_hyper* hp, float* metrics, cudaStream_t st) {
+  RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, st));
+  RET(allreduce_grads(c, s->actor.grads, c->actor_count, st));
+  return clip_adam_impl(c, &s->actor, c->actor_count, hp, metrics + M_ACTOR_GRAD_NORM, st);
+}
+
+int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const reppo_plan* p, const reppo_hyper* hp,
+              cudaStream_t st) {
+  const int A = c->shape.action_dim, mb = p->minibatch, ks = c->shape.kl_samples;
+  const int64_t per_epoch = static_cast<int64_t>(p->num_mini_batches) * mb;
+  for (int e = 0; e < p->num_epochs; ++e) {
+    const float* eps_pi = p->eps_pi + static_cast<int64_t>(e) * mb * A;
+    const float* eps_kl = p->eps_kl + static_cast<int64_t>(e) * ks * mb * A;
+    for (int j = 0; j < p->num_mini_batches; ++j) {
+      const int32_t* idx = p->perms + e * per_epoch + static_cast<int64_t>(j) * mb;
+      const int64_t step = static_cast<int64_t>(e) * p->num_mini_batches + j;
+      float* m = p->step_metrics ? p->step_metrics + step * M_NUM : c->scratch_metrics;
+      RET(critic_step_impl(c, s, b, idx, mb, hp, m, st));
+      RET(actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, st));
+    }
+  }
+  if (p->metrics != nullptr && p->step_metrics != nullptr)
+    CK(launch_metrics_mean(p->step_metrics, (p->num_epochs - 1) * p->num_mini_batches, p->num_mini_batches, M_NUM, p->metrics, st));
+  return REPPO_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int reppo_version(void) { return 1; }
+
+const char* reppo_last_error(const reppo_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
+  if (shape == nullptr || out == nullptr) return fail(nullptr, REPPO_ERR_INVALID, "null argument");
+  const reppo_shape& s = *shape;
+  if (s.obs_dim <= 0 || s.critic_obs_dim <= 0 || s.action_dim <= 0 || s.critic_hidden <= 0 || s.actor_hidden <= 0 ||
+      s.num_bins < 2 || s.max_rows <= 0 || s.kl_samples <= 0)
+    return fail(nullptr, REPPO_ERR_INVALID, "non-positive dimension in reppo_shape");
+  if (s.enc_layers < 2 || s.head_layers < 2 || s.pred_layers < 2 || s.actor_layers < 2)
+    return fail(nullptr, REPPO_ERR_UNSUPPORTED,
+                "layers == 1 has divergent JAX / Torch semantics (jax_models.py:81-89 vs torch_models.py:98-107)");
+  if (s.num_bins > 256) return fail(nullptr, REPPO_ERR_UNSUPPORTED, "num_bins > 256");
+  if (s.critic_hidden > 2048 || s.actor_hidden > 2048) return fail(nullptr, REPPO_ERR_UNSUPPORTED, "hidden_dim > 2048");
+  if (s.semantics != REPPO_SEM_JAX && s.semantics != REPPO_SEM_TORCH) return fail(nullptr, REPPO_ERR_INVALID, "semantics");
+  if (s.critic_norm < 0 || s.critic_norm > 2 || s.actor_norm < 0 || s.actor_norm > 2) return fail(nullptr, REPPO_ERR_INVALID, "norm type");
+  if (s.gemm_mode != REPPO_GEMM_FP32 && s.gemm_mode != REPPO_GEMM_BF16) return fail(nullptr, REPPO_ERR_INVALID, "gemm_mode");
+  if (!(s.vmax > s.vmin)) return fail(nullptr, REPPO_ERR_INVALID, "vmax <= vmin");
+
+  reppo_ctx* c = new reppo_ctx();
+  c->shape = s;
+  if (s.semantics == REPPO_SEM_JAX) {
+    // flax RMSNorm/LayerNorm eps 1e-6; logits + 40.0 * zero_dist (jax_models.py:298); clip 1-1e-4
+    // (jaxrl/reppo.py:558); min_std 0.1 because the constructor ignores cfg (jax_models.py:336);
+    // reward head + (1-done) aux mask (jaxrl/reppo.py:493-502); optax clip + adam.
+    c->sem = Sem{1e-6f, 40.0f, 1.0f - 1e-4f, 0, 0, 1, 1, 0, 0.1f};
+  } else {
+    // nn.RMSNorm(eps=None) -> finfo(float32).eps; 40.9 (torch_models.py:282); clip 1-1e-6
+    // (torchrl/reppo.py:301,308); AdamW(wd=0.01) + clip_grad_norm_ (:270-273,527-534).
+    c->sem = Sem{1.1920928955078125e-07f, 40.9f, 1.0f - 1e-6f, 1, 1, 0, 0, 1, -1.f};
+  }
+  if (s.critic_norm == REPPO_NORM_LAYER || s.actor_norm == REPPO_NORM_LAYER) c->sem.norm_eps = 1e-6f;  // reppo_mj_playground.py:65-72
+  c->K0 = s.critic_obs_dim + s.action_dim;
+  c->pred_out = s.critic_hidden + (c->sem.reward_head ? 1 : 0);
+
+  int64_t off = 0;
+  c->zero_dist_off = 0;
+  c->critic_tensors.push_back({"zero_dist", 0, s.num_bins, 0});
+  off += s.num_bins;
+  add_fcnn(c->critic_tensors, off, c->feature, "feature_module", c->K0, s.critic_hidden, s.critic_hidden, s.enc_layers, false, s.critic_norm);
+  add_fcnn(c->critic_tensors, off, c->head, "critic_module", s.critic_hidden, s.critic_hidden, s.num_bins, s.head_layers, true, s.critic_norm);
+  add_fcnn(c->critic_tensors, off, c->pred, "pred_module", s.critic_hidden, s.critic_hidden, c->pred_out, s.pred_layers, true, s.critic_norm);
+  c->critic_count = off;
+  off = 0;
+  c->actor_tensors.push_back({"log_temp", 0, 0, 0});
+  c->actor_tensors.push_back({"log_lagrange", 1, 0, 0});
+  off = 2;
+  add_fcnn(c->actor_tensors, off, c->actor, "model", s.obs_dim, s.actor_hidden, 2 * s.action_dim, s.actor_layers, false, s.actor_norm);
+  c->actor_count = off;
+
+  const double bw = (static_cast<double>(s.vmax) - static_cast<double>(s.vmin)) / (s.num_bins - 1);
+  const double sigma = bw * 0.75;
+  c->edges_h = linspace_f32(s.vmin - bw / 2, s.vmax + bw / 2, s.num_bins + 1);
+  c->support_h = linspace_f32(s.vmin, s.vmax, s.num_bins);
+  c->hl.vmin = s.vmin; c->hl.vmax = s.vmax; c->hl.num_bins = s.num_bins; c->hl.bias_scale = c->sem.bias_scale;
+  if (s.semantics == REPPO_SEM_JAX) {
+    c->hl.den = static_cast<float>(static_cast<double>(sqrtf(2.f)) * sigma);  // utils.py:52
+    c->hl.z_eps = 0.f;
+  } else {
+    c->hl.den = sqrtf(2.f) * static_cast<float>(sigma) + 1e-6f;               // reppo_util.py:767-769
+    c->hl.z_eps = 1e-6f;                                                      // :773
+  }
+  c->ws_need = layout_workspace(c, nullptr);
+  *out = c;
+  return REPPO_OK;
+}
+
+void reppo_ctx_destroy(reppo_ctx* c) {
+  if (c == nullptr) return;
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
+  delete c;
+}
+
+int64_t reppo_param_count(const reppo_ctx* c, int net) { return net == REPPO_NET_CRITIC ? c->critic_count : c->actor_count; }
+int32_t reppo_param_num_tensors(const reppo_ctx* c, int net) {
+  return static_cast<int32_t>(net == REPPO_NET_CRITIC ? c->critic_tensors.size() : c->actor_tensors.size());
+}
+int reppo_param_tensor(const reppo_ctx* c, int net, int32_t index, char* name, int32_t name_cap, int64_t* offset,
+                       int32_t* rows, int32_t* cols) {
+  const auto& ts = net == REPPO_NET_CRITIC ? c->critic_tensors : c->actor_tensors;
+  if (index < 0 || index >= static_cast<int32_t>(ts.size())) return REPPO_ERR_INVALID;
+  const TensorInfo& t = ts[index];
+  if (name && name_cap > 0) snprintf(name, name_cap, "%s", t.name.c_str());
+  if (offset) *offset = t.off;
+  if (rows) *rows = t.rows;
+  if (cols) *cols = t.cols;
+  return REPPO_OK;
+}
+
+size_t reppo_workspace_bytes(const reppo_ctx* c) { return c->ws_need; }
+
+int reppo_set_bins(reppo_ctx* c, const float* edges_host, const float* support_host) {
+  // optional: host-computed torch.linspace arrays (bit-identical to the reference's own support / bin edges)
+  if (edges_host) c->edges_h.assign(edges_host, edges_host + c->shape.num_bins + 1);
+  if (support_host) c->support_h.assign(support_host, support_host + c->shape.num_bins);
+  if (c->ws) {
+    if (cudaMemcpy(c->edges_d, c->edges_h.data(), c->edges_h.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->support_d, c->support_h.data(), c->support_h.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+      return fail(c, REPPO_ERR_CUDA, "uploading bin edges failed");
+  }
+  return REPPO_OK;
+}
+
+int reppo_set_workspace(reppo_ctx* c, void* workspace, size_t bytes) {
+  if (workspace == nullptr || bytes < c->ws_need) return fail(c, REPPO_ERR_WORKSPACE, "workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255u) return fail(c, REPPO_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  c->ws = static_cast<char*>(workspace);
+  c->ws_bytes = bytes;
+  layout_workspace(c, c->ws);
+  c->hl.edges = c->edges_d;
+  c->hl.support = c->support_d;
+  c->graph_valid = false;
+  return reppo_set_bins(c, nullptr, nullptr);
+}
+
+int reppo_td_lambda(const float* soft_reward, const float* value, const float* done, float* truncated,
+                    const float* importance_weight, float* target, int32_t T, int64_t N, double gamma, double lmbda,
+                    int32_t convention, int32_t mutate_truncated, reppo_stream stream) {
+  if (!soft_reward || !value || !done || !truncated || !target || T <= 0 || N <= 0) return REPPO_ERR_INVALID;
+  if (convention != REPPO_SEM_JAX && convention != REPPO_SEM_TORCH) return REPPO_ERR_INVALID;
+  const cudaError_t e = launch_td_lambda(soft_reward, value, done, truncated, importance_weight, target, T, N, gamma, lmbda,
+                                         convention, mutate_truncated, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) { g_create_error = std::string("td_lambda: ") + cudaGetErrorString(e); return REPPO_ERR_CUDA; }
+  return REPPO_OK;
+}
+
+int reppo_critic_forward(reppo_ctx* c, const float* cp, const float* critic_obs, const float* action, int32_t rows,
+                         float* value, float* logits, float* pred, float* features, reppo_stream stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RET(check_rows(c, rows));
+  c->launches = 0;
+  const reppo_shape& sh = c->shape;
+  CK(launch_gather_concat(critic_obs, sh.critic_obs_dim, action, sh.action_dim, nullptr, 0, rows, c->x0, c->K0, st));
+  RET(critic_trunk(c, cp, rows, pred != nullptr, st));
+  if (value || logits) CK(launch_value_head(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, rows, value, logits, st));
+  if (pred) CK(cudaMemcpyAsync(pred, c->pa.out, sizeof(float) * rows * c->pred_out, cudaMemcpyDeviceToDevice, st));
+  if (features) CK(cudaMemcpyAsync(features, c->fa.out, sizeof(float) * rows * sh.critic_hidden, cudaMemcpyDeviceToDevice, st));
+  return REPPO_OK;
+}
+
+int reppo_actor_forward(reppo_ctx* c, const float* ap, const float* obs, int32_t rows, float min_std, float* mean, float* std,
+                        reppo_stream stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RET(check_rows(c, rows));
+  c->launches = 0;
+  RET(mlp_forward(c, c->actor, ap, obs, rows, c->aa, st));
+  const float ms = c->sem.force_min_std >= 0.f ? c->sem.force_min_std : min_std;
+  CK(launch_mean_std(c->aa.out, rows, c->shape.action_dim, ms, mean, std, st));
+  return REPPO_OK;
+}
+
+int reppo_critic_grad(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int32_t mb,
+                      const reppo_hyper* hp, float* metrics, reppo_stream stream) {
+  c->launches = 0;
+  return critic_grad_impl(c, s, b, idx, mb, hp, metrics, static_cast<cudaStream_t>(stream));
+}
+int reppo_actor_grad(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int32_t mb,
+                     const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, reppo_stream stream) {
+  c->launches = 0;
+  return actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, static_cast<cudaStream_t>(stream));
+}
+int reppo_critic_step(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int32_t mb,
+                      const reppo_hyper* hp, float* metrics, reppo_stream stream) {
+  c->launches = 0;
+  return critic_step_impl(c, s, b, idx, mb, hp, metrics, static_cast<cudaStream_t>(stream));
+}
+int reppo_actor_step(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int32_t mb,
+                     const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, reppo_stream stream) {
+  c->launches = 0;
+  return actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, static_cast<cudaStream_t>(stream));
+}
+int reppo_clip_adam(reppo_ctx* c, const reppo_net_state* net, int64_t n, const reppo_hyper* hp, float* gn, reppo_stream stream) {
+  c->launches = 0;
+  return clip_adam_impl(c, net, n, hp, gn, static_cast<cudaStream_t>(stream));
+}
+
+int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const reppo_plan* p, const reppo_hyper* hp,
+                 reppo_stream stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!s || !b || !p || !hp) return fail(c, REPPO_ERR_INVALID, "null argument");
+  if (p->num_epochs <= 0 || p->num_mini_batches <= 0 || !p->perms || !p->eps_pi || !p->eps_kl)
+    return fail(c, REPPO_ERR_INVALID, "incomplete reppo_plan");
+  RET(check_rows(c, p->minibatch));
+  if (!p->use_graph) {
+    c->launches = 0;
+    return run_steps(c, s, b, p, hp, st);
+  }
+  GraphKey key{};
+  key.state = *s; key.batch = *b; key.plan = *p; key.hp = *hp;
+  if (!c->graph_valid || memcmp(&key, &c->graph_key, sizeof(GraphKey)) != 0) {
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    c->graph_valid = false;
+    c->launches = 0;
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
+    const int r = run_steps(c, s, b, p, hp, st);
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(st, &graph);
+    if (r != REPPO_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+    if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    memcpy(&c->graph_key, &key, sizeof(GraphKey));
+    c->graph_valid = true;
+    c->graph_launches = c->launches;
+  }
+  const cudaError_t e = cudaGraphLaunch(c->graph_exec, st);
+  if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
+  c->launches = c->graph_launches;
+  return REPPO_OK;
+}
+
+int64_t reppo_launch_count(const reppo_ctx* c) { return c->launches; }
+
+static int nccl_load(reppo_ctx* c) {
+  if (c->nccl.lib) return REPPO_OK;
+  const char* names[] = {getenv("REPPO_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    if (n == nullptr) continue;
+    c->nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (c->nccl.lib) break;
+  }
+  if (!c->nccl.lib) return fail(c, REPPO_ERR_NCCL, "cannot dlopen libnccl.so.2 (set REPPO_NCCL_LIB)");
+  c->nccl.GetUniqueId = reinterpret_cast<int (*)(NcclId*)>(dlsym(c->nccl.lib, "ncclGetUniqueId"));
+  c->nccl.CommInitRank = reinterpret_cast<int (*)(ncclComm_t*, int, NcclId, int)>(dlsym(c->nccl.lib, "ncclCommInitRank"));
+  c->nccl.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t)>(dlsym(c->nccl.lib, "ncclAllReduce"));
+  c->nccl.CommDestroy = reinterpret_cast<int (*)(ncclComm_t)>(dlsym(c->nccl.lib, "ncclCommDestroy"));
+  c->nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(c->nccl.lib, "ncclGetErrorString"));
+  if (!c->nccl.GetUniqueId || !c->nccl.CommInitRank || !c->nccl.AllReduce || !c->nccl.CommDestroy || !c->nccl.GetErrorString)
+    return fail(c, REPPO_ERR_NCCL, "libnccl is missing required symbols");
+  return REPPO_OK;
+}
+
+int reppo_nccl_unique_id(reppo_ctx* c, void* id_out_128) {
+  RET(nccl_load(c));
+  NcclId id;
+  const int r = c->nccl.GetUniqueId(&id);
+  if (r != 0) return fail(c, REPPO_ERR_NCCL, std::string("ncclGetUniqueId: ") + c->nccl.GetErrorString(r));
+  memcpy(id_out_128, &id, sizeof(id));
+  return REPPO_OK;
+}
+
+int reppo_nccl_init(reppo_ctx* c, const void* id_128, int32_t rank, int32_t world_size) {
+  RET(nccl_load(c));
+  NcclId id;
+  memcpy(&id, id_128, sizeof(id));
+  const int r = c->nccl.CommInitRank(&c->comm, world_size, id, rank);
+  if (r != 0) { c->comm = nullptr; return fail(c, REPPO_ERR_NCCL, std::string("ncclCommInitRank: ") + c->nccl.GetErrorString(r)); }
+  c->world = world_size; c->rank = rank;
+  c->graph_valid = false;
+  return REPPO_OK;
+}
+
+int reppo_nccl_finalize(reppo_ctx* c) {
+  if (c->comm) { c->nccl.CommDestroy(c->comm); c->comm = nullptr; }
+  c->graph_valid = false;
+  return REPPO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// Internal launcher interface between api.cu (host orchestration / C ABI) and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace reppo {
+
+enum { GEMM_STORE = 0, GEMM_ACCUM = 1, GEMM_ATOMIC = 2 };
+enum { NORM_NONE = 0, NORM_RMS = 1, NORM_LAYER = 2 };
+enum { KL_CLIPPED = 0, KL_FULL = 1, KL_VALUE = 2 };
+constexpr int kMaxPartials = 512;
+
+// metric slots: must mirror include/reppo_b200.h
+enum {
+  M_CRITIC_LOSS = 0, M_CE_MEAN, M_AUX_MEAN, M_VALUE_LOSS, M_Q_MEAN, M_TARGET_MEAN, M_TARGET_MAX, M_TARGET_MIN,
+  M_CRITIC_GRAD_NORM, M_ACTOR_LOSS, M_POLICY_LOSS, M_KL, M_ENTROPY, M_TEMPERATURE, M_LAGRANGIAN, M_ENTROPY_LOSS,
+  M_LAGRANGIAN_LOSS, M_ACTOR_Q_MEAN, M_ABS_PRED_ACTION, M_ACTOR_GRAD_NORM, M_REWARD_MEAN, M_ABS_BATCH_ACTION,
+  M_NUM = 24
+};
+constexpr uint32_t kCriticMetricMask = 0x1FFu | (1u << M_REWARD_MEAN) | (1u << M_ABS_BATCH_ACTION);
+constexpr uint32_t kActorMetricMask = ((1u << (M_ACTOR_GRAD_NORM + 1)) - 1u) & ~0x1FFu;
+
+struct HLConsts {           // categorical head + HL-Gauss constants
+  const float* edges;       // [B+1] fp32 linspace(vmin - bw/2, vmax + bw/2)
+  const float* support;     // [B]   fp32 linspace(vmin, vmax)
+  float vmin, vmax;
+  float den;                // sqrt(2) * sigma (+1e-6 torch)
+  float z_eps;              // 0 (jax) | 1e-6 (torch)
+  float bias_scale;         // 40.0 (jax_models.py:298) | 40.9 (torch_models.py:282)
+  int num_bins;
+};
+
+struct ActorConsts {
+  float min_std, action_clip, kl_bound, target_entropy, reduce_kl;
+  int clip_policy_sample, old_logp_at_clipped, kl_mode, update_entropy, update_kl;
+};
+
+struct AdamConsts {
+  float lr, b1, b2, eps, weight_decay, max_grad_norm;
+  int torch_clip;
+};
+
+cudaError_t launch_td_lambda(const float* sr, const float* val, const float* done, float* trunc, const float* iw,
+                             float* out, int T, long long N, double gamma, double lmbda, int convention, int mutate,
+                             cudaStream_t st);
+
+cudaError_t launch_gemm_f32(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                            float* C, int ldc, const float* bias, int mode, int split_k, cudaStream_t st);
+cudaError_t launch_colsum(const float* X, int M, int N, int ld, float* out, float* out2, float scale2, cudaStream_t st);
+
+cudaError_t launch_gather_concat(const float* a, int da, const float* b, int db, const int* idx, int b_is_local,
+                                 int rows, float* out, int out_ld, cudaStream_t st);
+cudaError_t launch_norm_act_fwd(int norm, const float* z, const float* gamma, const float* beta, int rows, int H,
+                                float eps, float* x, float* rstd, float* mean, cudaStream_t st);
+cudaError_t launch_norm_act_bwd(int norm, const float* dx, const float* z, const float* gamma, const float* beta,
+                                const float* rstd, const float* mean, int rows, int H, float* dz, float* dgamma,
+                                float* dbeta, cudaStream_t st);
+
+cudaError_t launch_critic_ce(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, const float* target,
+                             const float* truncated, const int* idx, int rows, float inv_rows, int no_mask, float* dlogits,
+                             float* metrics, cudaStream_t st);
+cudaError_t launch_critic_aux(const float* pred, int P, int H, int reward_head, int mask_done, const float* next_emb,
+                              const float* reward, const float* done, const float* truncated, const int* idx, int rows,
+                              float inv_rows, int no_mask, float aux_mult, float* dpred, float* metrics, cudaStream_t st);
+cudaError_t launch_actor_sample(const float* out, const float* out_old, const float* eps_pi, const float* eps_kl, int rows,
+                                int A, int kl_samples, const ActorConsts& ac, float* act_out, int act_ld, float* logp,
+                                float* kl, float* gmu, float* gsig, cudaStream_t st);
+cudaError_t launch_actor_q(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, const float* kl, int rows,
+                           float inv_rows, int kl_mode, float kl_bound, float* q_out, float* dlogits, cudaStream_t st);
+cudaError_t launch_actor_grad(const float* out, const float* eps_pi, const float* act, int act_ld, const float* dact,
+                              int dact_ld, const float* logp, const float* kl, const float* q, const float* gmu,
+                              const float* gsig, const float* actor_params, int rows, int A, float inv_rows,
+                              const ActorConsts& ac, float* dout, float* actor_grads, float* metrics, cudaStream_t st);
+cudaError_t launch_value_head(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, int rows,
+                              float* value, float* logits, cudaStream_t st);
+cudaError_t launch_mean_std(const float* out, int rows, int A, float min_std, float* mean, float* std, cudaStream_t st);
+
+cudaError_t launch_clip_adam(float* p, const float* g, float* m, float* v, long long n, int* step, float* partials,
+                             const AdamConsts& c, float* grad_norm_out, cudaStream_t st);
+cudaError_t launch_metrics_mean(const float* step_metrics, int first, int count, int nm, float* out, cudaStream_t st);
+cudaError_t launch_metrics_init(float* m, uint32_t mask, cudaStream_t st);
+
+}  // namespace reppo

@@ -1,0 +1,418 @@
+// Fused loss kernels of the REPPO update (K6-K11).
+//
+//  critic_ce_kernel  : categorical value head + HL-Gauss target + cross-entropy, forward AND
+//                      d logits, one warp per row (src/jaxrl/reppo.py:474-485,505-513,
+//                      src/jaxrl/utils.py:43-59; src/torchrl/reppo.py:243-254,
+//                      src/torchrl/reppo_util.py:756-777; value head jax_models.py:297-310).
+//  critic_aux_kernel : next-embedding (+ reward) prediction loss and d pred (reppo.py:492-502;
+//                      torchrl/reppo.py:255-262).
+//  actor_sample_kernel / actor_q_kernel / actor_grad_kernel : tanh-Gaussian reparameterised
+//                      sample + log-prob, 16-sample forward KL to the behaviour policy, the
+//                      KL-clipped pathwise loss with temperature / Lagrange terms, and their
+//                      hand-derived gradients (reppo.py:526-622; torchrl/reppo.py:291-338;
+//                      distrax Tanh fldj = 2 (log 2 - x - softplus(-2x)), torch_models.py:52-55).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace reppo {
+
+constexpr int kMaxBinsPerLane = 8;  // num_bins <= 256
+constexpr float kLog2 = 0.6931471805599453f;
+constexpr float kHalfLog2Pi = 0.9189385332046727f;
+
+struct RowSoftmax {
+  float p[kMaxBinsPerLane];
+  float lg[kMaxBinsPerLane];
+  float lse, value;
+};
+
+// logits = head + bias_scale * zero_dist; softmax; value = p . support
+REPPO_DEVINL void row_softmax(const float* __restrict__ head_row, const float* __restrict__ zero_dist,
+                              const float* __restrict__ support, float bias_scale, int B, int lane, RowSoftmax& o) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kMaxBinsPerLane; ++j) {
+    const int c = lane + 32 * j;
+    o.lg[j] = (c < B) ? head_row[c] + bias_scale * zero_dist[c] : -INFINITY;
+    m = fmaxf(m, o.lg[j]);
+  }
+  m = warp_max(m);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxBinsPerLane; ++j) {
+    const int c = lane + 32 * j;
+    o.p[j] = (c < B) ? expf(o.lg[j] - m) : 0.f;
+    s += o.p[j];
+  }
+  s = warp_sum(s);
+  const float inv = 1.f / s;
+  float v = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxBinsPerLane; ++j) {
+    const int c = lane + 32 * j;
+    o.p[j] *= inv;
+    if (c < B) v += o.p[j] * support[c];
+  }
+  o.value = warp_sum(v);
+  o.lse = m + logf(s);
+}
+
+// block-level accumulation of per-warp metric partials -> one atomicAdd per metric per block
+template <int NM>
+REPPO_DEVINL void block_metric_add(float (&vals)[NM], float* sm /* [8][NM] */, float* const* dst) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < NM; ++k) sm[warp * NM + k] = vals[k];
+  __syncthreads();
+  if (threadIdx.x < NM) {
+    float s = 0.f;
+    for (int w = 0; w < nwarp; ++w) s += sm[w * NM + threadIdx.x];
+    if (dst[threadIdx.x] != nullptr) atomicAdd(dst[threadIdx.x], s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __restrict__ zero_dist, HLConsts hl,
+                 const float* __restrict__ target, const float* __restrict__ truncated, const int* __restrict__ idx,
+                 int rows, float inv_rows, int no_mask, float* __restrict__ dlogits, float* __restrict__ metrics) {
+  __shared__ float sm[8 * 5];
+  __shared__ float smax[8], smin[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 8 + warp;
+  const int B = hl.num_bins;
+  float vals[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float tmax = -INFINITY, tmin = INFINITY;
+  if (row < rows) {
+    const long long src = idx ? idx[row] : row;
+    const float tgt = target[src];
+    const float mask = no_mask ? 1.f : 1.f - truncated[src];
+    RowSoftmax sx;
+    row_softmax(head_out + static_cast<size_t>(row) * ld, zero_dist, hl.support, hl.bias_scale, B, lane, sx);
+    // HL-Gauss histogram of the clipped target
+    const float x = fminf(fmaxf(tgt, hl.vmin), hl.vmax);
+    const float z = erff((hl.edges[B] - x) / hl.den) - erff((hl.edges[0] - x) / hl.den) + hl.z_eps;
+    float ce = 0.f, sum_tp = 0.f, tp[kMaxBinsPerLane];
+#pragma unroll
+    for (int j = 0; j < kMaxBinsPerLane; ++j) {
+      const int c = lane + 32 * j;
+      tp[j] = 0.f;
+      if (c < B) {
+        const float lo = erff((hl.edges[c] - x) / hl.den), hi = erff((hl.edges[c + 1] - x) / hl.den);
+        tp[j] = (hi - lo) / z;
+        ce -= tp[j] * (sx.lg[j] - sx.lse);
+        sum_tp += tp[j];
+      }
+    }
+    ce = warp_sum(ce);
+    sum_tp = warp_sum(sum_tp);
+    const float coef = mask * inv_rows;
+    float* drow = dlogits + static_cast<size_t>(row) * ld;
+#pragma unroll
+    for (int j = 0; j < kMaxBinsPerLane; ++j) {
+      const int c = lane + 32 * j;
+      if (c < B) drow[c] = coef * (sum_tp * sx.p[j] - tp[j]);
+    }
+    vals[0] = mask * ce * inv_rows;                         // REPPO_M_CRITIC_LOSS (CE part)
+    vals[1] = ce * inv_rows;                                // REPPO_M_CE_MEAN
+    vals[2] = (sx.value - tgt) * (sx.value - tgt) * inv_rows;  // REPPO_M_VALUE_LOSS
+    vals[3] = sx.value * inv_rows;                          // REPPO_M_Q_MEAN
+    vals[4] = tgt * inv_rows;                               // REPPO_M_TARGET_MEAN
+    tmax = tgt; tmin = tgt;
+  }
+  float* dst[5] = {metrics + M_CRITIC_LOSS, metrics + M_CE_MEAN, metrics + M_VALUE_LOSS, metrics + M_Q_MEAN,
+                   metrics + M_TARGET_MEAN};
+  if (lane == 0) { smax[warp] = tmax; smin[warp] = tmin; }
+  block_metric_add<5>(vals, sm, dst);
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { tmax = fmaxf(tmax, smax[w]); tmin = fminf(tmin, smin[w]); }
+    if (tmax > -INFINITY) { atomic_max_float(metrics + M_TARGET_MAX, tmax); atomic_min_float(metrics + M_TARGET_MIN, tmin); }
+  }
+}
+
+// pred [rows, P]: JAX P = H + 1 (slot 0 = reward), Torch P = H
+__global__ void __launch_bounds__(256)
+critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head, int mask_done,
+                  const float* __restrict__ next_emb, const float* __restrict__ reward, const float* __restrict__ done,
+                  const float* __restrict__ truncated, const int* __restrict__ idx, int rows, float inv_rows, int no_mask,
+                  float aux_mult, float* __restrict__ dpred, float* __restrict__ metrics) {
+  __shared__ float sm[8 * 3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 8 + warp;
+  float vals[3] = {0.f, 0.f, 0.f};
+  if (row < rows) {
+    const long long src = idx ? idx[row] : row;
+    const float mask = no_mask ? 1.f : 1.f - truncated[src];
+    const float nd = mask_done ? 1.f - done[src] : 1.f;
+    const float* pr = pred + static_cast<size_t>(row) * P;
+    const float* ne = next_emb + static_cast<size_t>(src) * H;
+    float* dr = dpred + static_cast<size_t>(row) * P;
+    const int off = reward_head ? 1 : 0;
+    const float g = 2.f * mask * nd * aux_mult * inv_rows / static_cast<float>(P);
+    float sq = 0.f;
+    for (int c = lane; c < H; c += 32) {
+      const float d = pr[off + c] - ne[c];
+      sq += d * d;
+      dr[off + c] = g * d;
+    }
+    float r = 0.f;
+    if (reward_head) {
+      r = reward[src];
+      if (lane == 0) {
+        const float d = pr[0] - r;
+        sq += d * d;
+        dr[0] = g * d;
+      }
+    }
+    sq = warp_sum(sq);
+    const float aux = nd * sq / static_cast<float>(P);
+    vals[0] = mask * aux_mult * aux * inv_rows;                    // joins REPPO_M_CRITIC_LOSS
+    vals[1] = (reward_head ? aux : mask * aux) * inv_rows;         // REPPO_M_AUX_MEAN (jax: mean aux; torch: embedding_loss)
+    vals[2] = r * inv_rows;                                        // REPPO_M_REWARD_MEAN
+  }
+  float* dst[3] = {metrics + M_CRITIC_LOSS, metrics + M_AUX_MEAN, metrics + M_REWARD_MEAN};
+  block_metric_add<3>(vals, sm, dst);
+}
+
+// -------------------------------------------------------------------------------------------------
+// actor: sample + log-prob + KL estimate (thread per row)
+// -------------------------------------------------------------------------------------------------
+REPPO_DEVINL float fldj_(float x) { return 2.f * (kLog2 - x - softplusf_(-2.f * x)); }
+
+__global__ void __launch_bounds__(128)
+actor_sample_kernel(const float* __restrict__ out, const float* __restrict__ out_old, const float* __restrict__ eps_pi,
+                    const float* __restrict__ eps_kl, int rows, int A, int kl_samples, ActorConsts ac,
+                    float* __restrict__ act_out, int act_ld, float* __restrict__ logp_out, float* __restrict__ kl_out,
+                    float* __restrict__ gmu_kl, float* __restrict__ gsig_kl) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const float* o = out + static_cast<size_t>(row) * 2 * A;
+  const float* oo = out_old + static_cast<size_t>(row) * 2 * A;
+  float logp = 0.f, lp_old = 0.f, lp_new = 0.f;
+  for (int k = 0; k < A; ++k) {
+    const float mu = o[k], sig = expf(o[A + k]) + ac.min_std;
+    const float e = eps_pi[static_cast<size_t>(row) * A + k];
+    const float x = mu + sig * e;
+    const float a = tanhf(x);
+    act_out[static_cast<size_t>(row) * act_ld + k] = a;
+    if (ac.clip_policy_sample) {
+      // torchrl/reppo.py:301: log_prob(actions.clip(+-c)) -> base.log_prob(atanh(.)) - fldj(atanh(.))
+      const float xc = atanhf(fminf(fmaxf(a, -ac.action_clip), ac.action_clip));
+      const float zz = (xc - mu) / sig;
+      logp += -0.5f * zz * zz - logf(sig) - kHalfLog2Pi - fldj_(xc);
+    } else {
+      // distrax sample_and_log_prob: base log-prob at the pre-tanh sample minus fldj
+      logp += -0.5f * e * e - logf(sig) - kHalfLog2Pi - fldj_(x);
+    }
+    // forward KL samples from the behaviour policy
+    const float mu_o = oo[k], sig_o = expf(oo[A + k]) + ac.min_std;
+    const float log_sig = logf(sig), log_sig_o = logf(sig_o);
+    const float inv_sig = 1.f / sig;
+    float gm = 0.f, gs = 0.f;
+    for (int s = 0; s < kl_samples; ++s) {
+      const float eo = eps_kl[(static_cast<size_t>(s) * rows + row) * A + k];
+      const float xo = mu_o + sig_o * eo;
+      const float u = atanhf(fminf(fmaxf(tanhf(xo), -ac.action_clip), ac.action_clip));
+      const float fu = fldj_(u);
+      if (ac.old_logp_at_clipped) {
+        const float zo = (u - mu_o) / sig_o;
+        lp_old += -0.5f * zo * zo - log_sig_o - kHalfLog2Pi - fu;
+      } else {
+        lp_old += -0.5f * eo * eo - log_sig_o - kHalfLog2Pi - fldj_(xo);
+      }
+      const float zn = (u - mu) * inv_sig;
+      lp_new += -0.5f * zn * zn - log_sig - kHalfLog2Pi - fu;
+      gm += zn * inv_sig;                   // d lp_new / d mu
+      gs += (zn * zn - 1.f) * inv_sig;      // d lp_new / d sigma
+    }
+    const float inv_s = 1.f / static_cast<float>(kl_samples);
+    gmu_kl[static_cast<size_t>(row) * A + k] = gm * inv_s;
+    gsig_kl[static_cast<size_t>(row) * A + k] = gs * inv_s;
+  }
+  logp_out[row] = logp;
+  kl_out[row] = (lp_old - lp_new) / static_cast<float>(kl_samples);
+}
+
+// Q_i = softmax(logits_i) . support  and  d loss / d logits = -(w_path_i / rows) * p (s - Q)
+__global__ void __launch_bounds__(256)
+actor_q_kernel(const float* __restrict__ head_out, int ld, const float* __restrict__ zero_dist, HLConsts hl,
+               const float* __restrict__ kl, int rows, float inv_rows, int kl_mode, float kl_bound,
+               float* __restrict__ q_out, float* __restrict__ dlogits) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const int B = hl.num_bins;
+  RowSoftmax sx;
+  row_softmax(head_out + static_cast<size_t>(row) * ld, zero_dist, hl.support, hl.bias_scale, B, lane, sx);
+  const float w_path = (kl_mode == KL_CLIPPED) ? (kl[row] < kl_bound ? 1.f : 0.f) : 1.f;
+  const float coef = -w_path * inv_rows;
+  float* drow = dlogits + static_cast<size_t>(row) * ld;
+#pragma unroll
+  for (int j = 0; j < kMaxBinsPerLane; ++j) {
+    const int c = lane + 32 * j;
+    if (c < B) drow[c] = coef * sx.p[j] * (hl.support[c] - sx.value);
+  }
+  if (lane == 0) q_out[row] = sx.value;
+}
+
+// d loss / d (mu, log_std) per row, scalar gradients for log_temp / log_lagrange, metrics
+__global__ void __launch_bounds__(128)
+actor_grad_kernel(const float* __restrict__ out, const float* __restrict__ eps_pi, const float* __restrict__ act, int act_ld,
+                  const float* __restrict__ dact, int dact_ld, const float* __restrict__ logp_in,
+                  const float* __restrict__ kl_in, const float* __restrict__ q_in, const float* __restrict__ gmu_kl,
+                  const float* __restrict__ gsig_kl, const float* __restrict__ actor_params, int rows, int A, float inv_rows,
+                  ActorConsts ac, float* __restrict__ dout, float* __restrict__ actor_grads, float* __restrict__ metrics) {
+  __shared__ float red[32];
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const float alpha = expf(actor_params[0]), beta = expf(actor_params[1]);
+  float v_path = 0.f, v_kl = 0.f, v_ent = 0.f, v_q = 0.f, v_abs = 0.f, v_ent_t = 0.f;
+  if (row < rows) {
+    const float logp = logp_in[row], kl = kl_in[row], q = q_in[row];
+    float w_path, w_kl;
+    if (ac.kl_mode == KL_CLIPPED) { w_path = kl < ac.kl_bound ? 1.f : 0.f; w_kl = 1.f - w_path; }
+    else if (ac.kl_mode == KL_FULL) { w_path = 1.f; w_kl = 1.f; }
+    else { w_path = 1.f; w_kl = 0.f; }
+    const float g_logp = inv_rows * w_path * alpha;           // d L / d logp   (alpha is stop-gradient here)
+    const float g_lpnew = -inv_rows * w_kl * beta * ac.reduce_kl;  // d L / d lp_new = - d L / d kl
+    const float* o = out + static_cast<size_t>(row) * 2 * A;
+    float* d = dout + static_cast<size_t>(row) * 2 * A;
+    float abs_a = 0.f;
+    for (int k = 0; k < A; ++k) {
+      const float mu = o[k], ex = expf(o[A + k]), sig = ex + ac.min_std;
+      const float e = eps_pi[static_cast<size_t>(row) * A + k];
+      const float a = act[static_cast<size_t>(row) * act_ld + k];
+      const float da = dact[static_cast<size_t>(row) * dact_ld + k] * (1.f - a * a);  // through a = tanh(x)
+      float dlp_mu, dlp_sig;
+      const bool clamped = ac.clip_policy_sample && !(a >= -ac.action_clip && a <= ac.action_clip);
+      if (!clamped) {
+        dlp_mu = 2.f * a;
+        dlp_sig = -1.f / sig + 2.f * a * e;
+      } else {
+        const float xc = atanhf(fminf(fmaxf(a, -ac.action_clip), ac.action_clip));
+        const float zz = (xc - mu) / sig;
+        dlp_mu = zz / sig;
+        dlp_sig = (zz * zz - 1.f) / sig;
+      }
+      const float dmu = da + g_logp * dlp_mu + g_lpnew * gmu_kl[static_cast<size_t>(row) * A + k];
+      const float dsig = da * e + g_logp * dlp_sig + g_lpnew * gsig_kl[static_cast<size_t>(row) * A + k];
+      d[k] = dmu;
+      d[A + k] = dsig * ex;
+      abs_a += fabsf(a);
+    }
+    v_path = w_path * (alpha * logp - q) + w_kl * beta * ac.reduce_kl * kl;
+    v_kl = kl;
+    v_ent = -logp;
+    v_q = q;
+    v_abs = abs_a / static_cast<float>(A);
+    v_ent_t = ac.target_entropy - logp;
+  }
+  const float s_path = block_sum(v_path, red) * inv_rows;
+  const float s_kl = block_sum(v_kl, red) * inv_rows;
+  const float s_ent = block_sum(v_ent, red) * inv_rows;
+  const float s_q = block_sum(v_q, red) * inv_rows;
+  const float s_abs = block_sum(v_abs, red) * inv_rows;
+  const float s_ent_t = block_sum(v_ent_t, red) * inv_rows;
+  if (threadIdx.x == 0) {
+    // entropy_loss = alpha * mean(sg(target_entropy - logp)); lagrangian_loss = -beta * mean(sg(kl - bound))
+    const float frac = static_cast<float>(min(rows - static_cast<int>(blockIdx.x * blockDim.x), static_cast<int>(blockDim.x))) * inv_rows;
+    const float ent_loss = alpha * s_ent_t;
+    const float lag_loss = -beta * (s_kl - ac.kl_bound * frac);
+    float total = s_path;
+    if (ac.update_entropy) { total += ent_loss; atomicAdd(actor_grads + 0, ent_loss); }   // d/d log_temp = alpha * c
+    if (ac.update_kl) { total += lag_loss; atomicAdd(actor_grads + 1, lag_loss); }        // d/d log_lagrange = -beta * c
+    atomicAdd(metrics + M_ACTOR_LOSS, total);
+    atomicAdd(metrics + M_POLICY_LOSS, s_path);
+    atomicAdd(metrics + M_KL, s_kl);
+    atomicAdd(metrics + M_ENTROPY, s_ent);
+    atomicAdd(metrics + M_ENTROPY_LOSS, ent_loss);
+    atomicAdd(metrics + M_LAGRANGIAN_LOSS, lag_loss);
+    atomicAdd(metrics + M_ACTOR_Q_MEAN, s_q);
+    atomicAdd(metrics + M_ABS_PRED_ACTION, s_abs);
+    if (blockIdx.x == 0) { metrics[M_TEMPERATURE] = alpha; metrics[M_LAGRANGIAN] = beta; }
+  }
+}
+
+// ---- launchers -----------------------------------------------------------------------------------
+cudaError_t launch_critic_ce(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, const float* target,
+                             const float* truncated, const int* idx, int rows, float inv_rows, int no_mask, float* dlogits,
+                             float* metrics, cudaStream_t st) {
+  if (hl.num_bins > 32 * kMaxBinsPerLane) return cudaErrorInvalidValue;
+  critic_ce_kernel<<<(rows + 7) / 8, 256, 0, st>>>(head_out, ld, zero_dist, hl, target, truncated, idx, rows, inv_rows,
+                                                     no_mask, dlogits, metrics);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_critic_aux(const float* pred, int P, int H, int reward_head, int mask_done, const float* next_emb,
+                              const float* reward, const float* done, const float* truncated, const int* idx, int rows,
+                              float inv_rows, int no_mask, float aux_mult, float* dpred, float* metrics, cudaStream_t st) {
+  critic_aux_kernel<<<(rows + 7) / 8, 256, 0, st>>>(pred, P, H, reward_head, mask_done, next_emb, reward, done, truncated,
+                                                      idx, rows, inv_rows, no_mask, aux_mult, dpred, metrics);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_actor_sample(const float* out, const float* out_old, const float* eps_pi, const float* eps_kl, int rows,
+                                int A, int kl_samples, const ActorConsts& ac, float* act_out, int act_ld, float* logp,
+                                float* kl, float* gmu, float* gsig, cudaStream_t st) {
+  actor_sample_kernel<<<(rows + 127) / 128, 128, 0, st>>>(out, out_old, eps_pi, eps_kl, rows, A, kl_samples, ac, act_out,
+                                                            act_ld, logp, kl, gmu, gsig);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_actor_q(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, const float* kl, int rows,
+                           float inv_rows, int kl_mode, float kl_bound, float* q_out, float* dlogits, cudaStream_t st) {
+  if (hl.num_bins > 32 * kMaxBinsPerLane) return cudaErrorInvalidValue;
+  actor_q_kernel<<<(rows + 7) / 8, 256, 0, st>>>(head_out, ld, zero_dist, hl, kl, rows, inv_rows, kl_mode, kl_bound, q_out,
+                                                   dlogits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_actor_grad(const float* out, const float* eps_pi, const float* act, int act_ld, const float* dact,
+                              int dact_ld, const float* logp, const float* kl, const float* q, const float* gmu,
+                              const float* gsig, const float* actor_params, int rows, int A, float inv_rows,
+                              const ActorConsts& ac, float* dout, float* actor_grads, float* metrics, cudaStream_t st) {
+  actor_grad_kernel<<<(rows + 127) / 128, 128, 0, st>>>(out, eps_pi, act, act_ld, dact, dact_ld, logp, kl, q, gmu, gsig,
+                                                          actor_params, rows, A, inv_rows, ac, dout, actor_grads, metrics);
+  return cudaGetLastError();
+}
+
+// Critic.forward outputs (torch_models.py:278-285): logits = head + scale * zero_dist, value = softmax . support
+__global__ void __launch_bounds__(256)
+value_head_kernel(const float* __restrict__ head_out, int ld, const float* __restrict__ zero_dist, HLConsts hl, int rows,
+                  float* __restrict__ value, float* __restrict__ logits) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  RowSoftmax sx;
+  row_softmax(head_out + static_cast<size_t>(row) * ld, zero_dist, hl.support, hl.bias_scale, hl.num_bins, lane, sx);
+  if (logits != nullptr) {
+#pragma unroll
+    for (int j = 0; j < kMaxBinsPerLane; ++j) {
+      const int c = lane + 32 * j;
+      if (c < hl.num_bins) logits[static_cast<size_t>(row) * hl.num_bins + c] = sx.lg[j];
+    }
+  }
+  if (value != nullptr && lane == 0) value[row] = sx.value;
+}
+
+__global__ void mean_std_kernel(const float* __restrict__ out, int rows, int A, float min_std, float* __restrict__ mean,
+                                float* __restrict__ std) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * A) return;
+  const int r = i / A, k = i % A;
+  if (mean != nullptr) mean[i] = out[static_cast<size_t>(r) * 2 * A + k];
+  if (std != nullptr) std[i] = expf(out[static_cast<size_t>(r) * 2 * A + A + k]) + min_std;
+}
+
+cudaError_t launch_value_head(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, int rows,
+                              float* value, float* logits, cudaStream_t st) {
+  if (hl.num_bins > 32 * kMaxBinsPerLane) return cudaErrorInvalidValue;
+  value_head_kernel<<<(rows + 7) / 8, 256, 0, st>>>(head_out, ld, zero_dist, hl, rows, value, logits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mean_std(const float* out, int rows, int A, float min_std, float* mean, float* std, cudaStream_t st) {
+  mean_std_kernel<<<(rows * A + 255) / 256, 256, 0, st>>>(out, rows, A, min_std, mean, std);
+  return cudaGetLastError();
+}
+
+}  // namespace reppo

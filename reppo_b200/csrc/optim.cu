@@ -1,0 +1,115 @@
+// K12 -- global-norm clip + Adam / AdamW on one flat fp32 arena.
+//   JAX  : optax.chain(clip_by_global_norm(max_grad_norm), adam(lr))  src/jaxrl/reppo.py:246-257
+//   Torch: clip_grad_norm_ (+1e-6) -> AdamW(weight_decay=0.01)         src/torchrl/reppo.py:270-273,527-534
+// Two launches: (1) per-block partial sums of squares (deterministic, no atomics) + step counter
+// increment; (2) every block re-reduces the <= kMaxPartials partials, derives the clip scale and
+// the bias corrections, and streams its slice: 28 B per parameter (read g,p,m,v; write p,m,v).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace reppo {
+
+__global__ void __launch_bounds__(256)
+sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partials, int* __restrict__ step) {
+  __shared__ float red[32];
+  float s = 0.f;
+  const long long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = g4[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = g[(n4 << 2) + threadIdx.x]; s += v * v; }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = s;
+    if (blockIdx.x == 0 && step != nullptr) *step = *step + 1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+            const float* __restrict__ partials, int num_partials, const int* __restrict__ step, AdamConsts c,
+            float* __restrict__ grad_norm_out) {
+  __shared__ float red[32];
+  __shared__ float s_scale, s_bc1, s_bc2;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < num_partials; i += blockDim.x) s += partials[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const float gn = sqrtf(s);
+    float scale = 1.f;
+    if (c.max_grad_norm > 0.f) {
+      if (c.torch_clip) scale = fminf(c.max_grad_norm / (gn + 1e-6f), 1.f);   // clip_grad_norm_
+      else scale = (gn < c.max_grad_norm) ? 1.f : c.max_grad_norm / gn;       // optax.clip_by_global_norm
+    }
+    const int t = *step;
+    s_scale = scale;
+    s_bc1 = static_cast<float>(1.0 - pow(static_cast<double>(c.b1), static_cast<double>(t)));
+    s_bc2 = static_cast<float>(1.0 - pow(static_cast<double>(c.b2), static_cast<double>(t)));
+    if (blockIdx.x == 0 && grad_norm_out != nullptr) *grad_norm_out = gn;
+  }
+  __syncthreads();
+  const float scale = s_scale, bc1 = s_bc1, bc2 = s_bc2;
+  const float decay = 1.f - c.lr * c.weight_decay;
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    gg *= scale;
+    mm = c.b1 * mm + (1.f - c.b1) * gg;
+    vv = c.b2 * vv + (1.f - c.b2) * gg * gg;
+    pp = pp * decay - c.lr * (mm / bc1) / (sqrtf(vv / bc2) + c.eps);
+  };
+  const long long n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = g4[i];
+    upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    upd(p[i], g[i], m[i], v[i]);
+  }
+}
+
+cudaError_t launch_clip_adam(float* p, const float* g, float* m, float* v, long long n, int* step, float* partials,
+                             const AdamConsts& c, float* grad_norm_out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const long long want = (n / 4 + 255) / 256;
+  int blocks = static_cast<int>(want < kMaxPartials ? want : kMaxPartials);
+  if (blocks < 1) blocks = 1;
+  sumsq_partial_kernel<<<blocks, 256, 0, st>>>(g, n, partials, step);
+  adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, partials, blocks, step, c, grad_norm_out);
+  return cudaGetLastError();
+}
+
+// mean of the step metrics of the last epoch (src/jaxrl/reppo.py:660,671)
+__global__ void metrics_mean_kernel(const float* __restrict__ step_metrics, int first, int count, int nm, float* __restrict__ out) {
+  const int k = threadIdx.x;
+  if (k >= nm) return;
+  float s = 0.f;
+  for (int i = 0; i < count; ++i) s += step_metrics[static_cast<size_t>(first + i) * nm + k];
+  out[k] = s / static_cast<float>(count);
+}
+
+cudaError_t launch_metrics_mean(const float* step_metrics, int first, int count, int nm, float* out, cudaStream_t st) {
+  metrics_mean_kernel<<<1, 32, 0, st>>>(step_metrics, first, count, nm, out);
+  return cudaGetLastError();
+}
+
+// metric vector prologue: zero the sums, seed the min / max slots
+__global__ void metrics_init_kernel(float* __restrict__ m, uint32_t mask) {
+  const int k = threadIdx.x;
+  if (k < M_NUM && ((mask >> k) & 1u)) m[k] = (k == M_TARGET_MAX) ? -INFINITY : (k == M_TARGET_MIN ? INFINITY : 0.f);
+}
+cudaError_t launch_metrics_init(float* m, uint32_t mask, cudaStream_t st) {
+  metrics_init_kernel<<<1, 32, 0, st>>>(m, mask);
+  return cudaGetLastError();
+}
+
+}  // namespace reppo
