@@ -1,0 +1,452 @@
+#!/usr/bin/env python
+"""bench.py -- REPPO update samples/s on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C2]
+
+A "step" is ONE full REPPO update of one rollout batch: the TD(lambda) scan plus
+num_epochs x num_mini_batches critic+actor minibatch steps (src/jaxrl/reppo.py:417-673).  The
+workload at N=1 is C2 = CheetahRun-shaped mjx_dmc_large_data (T=128, N=1024 envs, S=131072
+samples, 64 minibatches x 8 epochs, mb=2048, obs 17 / act 6, H=512, 151 bins).  Under torchrun
+every rank owns its own 1024 env columns (weak scaling over environments); gradients are
+all-reduced with NCCL each minibatch step.  Rank 0 prints ONE JSON line.
+
+value     : samples/s with the rollout already resident in HBM (CUDA events around K updates).
+e2e       : the same through the public API (reppo_b200.torch_api.reppo_update) with HOST pinned
+            buffers: H2D of the rollout and D2H of the metrics inside the timed region.
+roofline  : the dominant kernel family (the MLP GEMMs): algorithmic FLOPs / measured kernel time.
+cpu_baseline / --impl reference : the oracle port of the reference update timed on the host cores
+            (a bounded sample of minibatch steps, extrapolated to the full update).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (env group, experiment override, obs_dim, action_dim, terminate, reward_scaling, extra hyper overrides)
+    "C1": ("mjx_dmc", "mjx_dmc_small_data", 5, 1, False, 1.0, {}),
+    "C2": ("mjx_dmc", "mjx_dmc_large_data", 17, 6, False, 1.0, {}),
+    "C3": ("brax", "default", 27, 8, True, 0.1, {}),
+    "C4": ("humanoid_brax", "default", 244, 17, True, 0.1, {}),
+    "C5": ("mjx_dmc", "mjx_dmc_large_data", 17, 6, False, 1.0,
+           {"critic_hidden_dim": 1024, "actor_hidden_dim": 1024, "num_envs": 2048, "num_mini_batches": 16}),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def make_cfg(name, semantics):
+    from reppo_b200.config import compose
+    env, ov, D, A, term, rs, extra = CONFIGS[name]
+    overrides = [f"env={env}", f"experiment_overrides={ov}", f"b200.semantics={semantics}"]
+    overrides += [f"hyperparameters.{k}={v}" for k, v in extra.items()]
+    cfg = compose(overrides)
+    return cfg, D, A, term, rs
+
+
+def oracle_hyper(cfg, D, A):
+    from oracle import reppo_oracle as O
+    h = cfg.hyperparameters
+    return O.Hyper(num_steps=h.num_steps, num_envs=h.num_envs, num_mini_batches=h.num_mini_batches, num_epochs=h.num_epochs,
+                   gamma=h.gamma, lmbda=h.lmbda, lr=h.lr, max_grad_norm=h.max_grad_norm, critic_hidden_dim=h.critic_hidden_dim,
+                   actor_hidden_dim=h.actor_hidden_dim, vmin=float(h.vmin), vmax=float(h.vmax), num_bins=h.num_bins,
+                   kl_bound=h.kl_bound, obs_dim=D, critic_obs_dim=D, action_dim=A, actor_min_std=h.actor_min_std)
+
+
+def gemm_flops_per_update(hp):
+    """Algorithmic FLOPs of the Linear layers: critic step 6(f+h+p), actor step
+    2(3a + a + 2(f+h)) per sample visit."""
+    H, Ha, B, D, A = hp.critic_hidden_dim, hp.actor_hidden_dim, hp.num_bins, hp.obs_dim, hp.action_dim
+    f = (hp.critic_obs_dim + A) * H + H * H
+    h = H * H + H * B
+    p = H * H + H * (H + 1)
+    a = D * Ha + Ha * Ha + 2 * A * Ha
+    per_visit = 6 * (f + h + p) + 2 * (3 * a + a + 2 * (f + h))
+    return per_visit * hp.batch_size * hp.num_epochs
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = next((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(hp, sem_name, seconds=12.0, min_steps=2):
+    """Oracle port timed on the host cores: scan + a bounded number of minibatch steps, extrapolated."""
+    import torch
+    from oracle import reppo_oracle as O
+    sem = O.JAX if sem_name == "jax" else O.TORCH
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cp, ap = O.init_params(hp, sem, seed=0)
+    batch = O.synthetic_rollout(hp, seed=0)
+    eps_pi, eps_kl = O.synthetic_noise(hp)
+    perms = O.synthetic_perms(hp)
+    t0 = time.perf_counter()
+    target = O.compute_targets({k: v.clone() for k, v in batch.items()}, hp, sem)
+    t_scan = time.perf_counter() - t0
+    flat = O.flatten_batch(batch, target)
+    ts = O.TrainState.create(cp, ap)
+    mbs = hp.minibatch_size
+    times = []
+    j = 0
+    t_begin = time.perf_counter()
+    while True:
+        idx = perms[0, (j % hp.num_mini_batches) * mbs:(j % hp.num_mini_batches + 1) * mbs]
+        t0 = time.perf_counter()
+        mb = O.take(flat, idx)
+        ts, _, _ = O.critic_step(ts, mb, hp, sem)
+        ts, _, _ = O.actor_step(ts, mb, eps_pi[0], eps_kl[0], hp, sem)
+        dt = time.perf_counter() - t0
+        if j > 0:
+            times.append(dt)  # first step is warm-up
+        j += 1
+        if len(times) >= min_steps and time.perf_counter() - t_begin > seconds:
+            break
+        if len(times) >= 64:
+            break
+    step = sorted(times)[len(times) // 2]
+    n_steps = hp.num_epochs * hp.num_mini_batches
+    total = t_scan + n_steps * step
+    return {"value": hp.batch_size / total, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"TD(lambda) scan ({t_scan * 1e3:.1f} ms) + median of {len(times)} critic+actor minibatch steps "
+                      f"({step * 1e3:.1f} ms each, mb={mbs}) of oracle/reppo_oracle.py ({sem_name} semantics, fp32, torch CPU), "
+                      f"extrapolated to {n_steps} steps"}, total
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path.  JAX is not installable here and /root/reference is absent on the
+    GPU box, so the arm times the oracle port (a line-by-line restatement pinned to the reference's Torch closures)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, D, A, term, rs = make_cfg(args.config, args.semantics)
+    hp = oracle_hyper(cfg, D, A)
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        base, total = cpu_sample(hp, args.semantics, seconds=6.0)
+        if i >= args.warmup:
+            vals.append(total)
+        last = base
+    ms = 1e3 * sum(vals) / len(vals)
+    value = hp.batch_size / (ms / 1e3)
+    last["value"] = value
+    line = {
+        "impl": "reference", "metric": "reppo_update_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.config, cfg, D, A, 1), "cpu_baseline": last,
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "jax/flax/optax are not installable in this image and /root/reference does not exist on the GPU box: "
+                "this arm times oracle/reppo_oracle.py (CPU restatement of the reference update) on all host cores",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(name, cfg, D, A, world):
+    h = cfg.hyperparameters
+    S = h.num_steps * h.num_envs
+    return {"workload": f"{name}: REPPO update, {CONFIGS[name][0]} / {CONFIGS[name][1]}-shaped synthetic rollout, "
+                        f"T={h.num_steps} x N={h.num_envs} envs per GPU (S={S}), {h.num_mini_batches} minibatches x "
+                        f"{h.num_epochs} epochs (mb={S // h.num_mini_batches}/GPU), obs {D} / act {A}, H={h.critic_hidden_dim}, "
+                        f"{h.num_bins} bins",
+            "samples_per_gpu": S, "minibatch_per_gpu": S // h.num_mini_batches, "optimizer_steps": h.num_epochs * h.num_mini_batches,
+            "parallelism": f"dp{world} over environments" if world > 1 else "single GPU",
+            "l2": "rollout batch (292 MB at C2) exceeds the 126 MB L2; weights/Adam state are L2-resident by design"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--semantics", default="jax", choices=["jax", "torch"])
+    ap.add_argument("--gemm", default=os.environ.get("REPPO_GEMM", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="warm-up + one update, no timing legs (for ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from oracle import reppo_oracle as O  # synthetic inputs + cpu_baseline leg only
+    from reppo_b200 import torch_api as T
+    from reppo_b200.engine import HyperParams
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    peaks = load_peaks()
+
+    cfg, D, A, term, rs = make_cfg(args.config, args.semantics)
+    if args.gemm == "bf16":
+        cfg.platform.amp_dtype = "bf16"
+    h = cfg.hyperparameters
+    hp = oracle_hyper(cfg, D, A)
+    S, n_mb, E = hp.batch_size, hp.num_mini_batches, hp.num_epochs
+    mb = S // n_mb
+    sem = O.JAX if args.semantics == "jax" else O.TORCH
+
+    # ---- synthetic rollout (host, seeded per rank), networks -------------------------------------------
+    batch = O.synthetic_rollout(hp, seed=rank, terminate=term, reward_scaling=rs)
+    cp, ap_ = O.init_params(hp, sem, seed=0)
+    ts = T.make_train_state(cfg, D, D, A, device=dev)
+    eng = ts.engine
+    eng.load_params(cp, ap_)
+    if world > 1:
+        import ctypes as C
+        from reppo_b200 import _lib as L
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = C.create_string_buffer(128)
+            L.check(eng.lib.reppo_nccl_unique_id(eng.ctx, raw), eng.ctx, "nccl id")
+            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        idbuf = idbuf.to(dev)
+        dist.broadcast(idbuf, 0)
+        raw = bytes(idbuf.cpu().tolist())
+        L.check(eng.lib.reppo_nccl_init(eng.ctx, raw, rank, world), eng.ctx, "nccl init")
+    hyp = HyperParams(gamma=h.gamma, lmbda=h.lmbda, lr=h.lr, max_grad_norm=h.max_grad_norm, kl_bound=h.kl_bound,
+                      ent_target_mult=h.ent_target_mult, aux_loss_mult=h.aux_loss_mult, actor_min_std=h.actor_min_std,
+                      actor_kl_clip_mode=h.actor_kl_clip_mode, world_size=world)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    devb = {k: v.to(dev) for k, v in batch.items()}
+    perms = torch.stack([torch.randperm(S, device=dev, generator=g) for _ in range(E)]).to(torch.int32)
+    eps_pi = torch.randn(E, mb, A, device=dev, generator=g)
+    eps_kl = torch.randn(E, 16, mb, A, device=dev, generator=g)
+    target = torch.empty(hp.num_steps, hp.num_envs, device=dev)
+    flat = {k: v.reshape(-1, *v.shape[2:]) for k, v in devb.items()}
+    flat["target"] = target.reshape(-1)
+    cb = eng.make_batch(flat)
+    step_metrics = torch.empty(E * n_mb, 24, device=dev)
+    use_graph = not args.no_graph
+
+    def one_update():
+        eng.td_lambda(devb["soft_reward"], devb["value"], devb["done"], devb["truncated"], devb["importance_weight"],
+                      h.gamma, h.lmbda, out=target)
+        eng.sync_actor_old()
+        eng.update(cb, perms, eps_pi, eps_kl, hyp, n_mb, use_graph=use_graph, step_metrics=step_metrics)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_update()
+    barrier()
+    if args.profile_only:
+        one_update()
+        torch.cuda.synchronize()
+        return
+    launches_per_update = eng.launch_count() + 2  # + scan + actor_old copy
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        one_update()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    final_metrics = eng.metrics_dict(eng.metrics)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = S * world / (ms / 1e3)
+
+    # ---- e2e: public API, host pinned buffers, H2D + D2H inside the timed region ---------------------------
+    host = {"observations": batch["obs"], "critic_observations": batch["critic_obs"], "actions": batch["action"],
+            "rewards": batch["soft_reward"].unsqueeze(-1), "raw_rewards": batch["reward"].unsqueeze(-1),
+            "next_embeddings": batch["next_emb"], "next_values": batch["value"].unsqueeze(-1),
+            "dones": batch["done"].unsqueeze(-1), "truncations": batch["truncated"].unsqueeze(-1),
+            "importance_weight": batch["importance_weight"].unsqueeze(-1)}
+    host = {k: v.contiguous().pin_memory() for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    for _ in range(2):
+        T.reppo_update(ts, host, cfg, generator=g, use_graph=use_graph, world_size=world)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        logs = T.reppo_update(ts, host, cfg, generator=g, use_graph=use_graph, world_size=world)  # floats: D2H read inside
+    ev1.record()
+    barrier()
+    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = t.item()
+    e2e = {"value": S * world / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 24 * 4,
+           "ms_per_step": e2e_ms}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline legs (rank 0, N=1 semantics) ----------------------------------------------------------------
+    def time_fn(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    # GEMM family: every distinct Linear GEMM of one critic+actor step, timed in isolation with CUDA events
+    Hc, Ha, B, K0 = hp.critic_hidden_dim, hp.actor_hidden_dim, hp.num_bins, hp.critic_obs_dim + A
+    P = Hc + (1 if args.semantics == "jax" else 0)
+    crit_layers = [(K0, Hc), (Hc, Hc), (Hc, Hc), (Hc, B), (Hc, Hc), (Hc, P)]   # feature x2, head x2, pred x2
+    act_layers = [(D, Ha), (Ha, Ha), (Ha, 2 * A)]
+    # (op, in, out, count per critic+actor step): critic step fwd+dgrad+wgrad; actor step: actor fwd/old fwd/bwd, critic fwd+dgrad
+    plan = {}
+    def add(op, i, o, n=1):
+        plan[(op, i, o)] = plan.get((op, i, o), 0) + n
+    for i, o in crit_layers:
+        add(0, i, o); add(2, i, o)
+    for i, o in crit_layers[1:]:
+        add(1, i, o)
+    for i, o in crit_layers[:4]:
+        add(0, i, o); add(1, i, o)
+    for i, o in act_layers:
+        add(0, i, o, 2); add(2, i, o)
+    for i, o in act_layers[1:]:
+        add(1, i, o)
+    gemm_ms, gemm_flops = 0.0, 0.0
+    top = None
+    for (op, i, o), n in plan.items():
+        if op == 0:
+            a_, b_ = torch.randn(mb, i, device=dev), torch.randn(o, i, device=dev)
+        elif op == 1:
+            a_, b_ = torch.randn(mb, o, device=dev), torch.randn(o, i, device=dev)
+        else:
+            a_, b_ = torch.randn(mb, o, device=dev), torch.randn(mb, i, device=dev)
+        out = eng.linear(op, a_, b_)
+        if op == 2:
+            t_ms = time_fn(lambda: eng.lib.reppo_linear(eng.ctx, op, mb, i, o, a_.data_ptr(), b_.data_ptr(), out.data_ptr(), None,
+                                                         eng._stream()), 50)
+        else:
+            t_ms = time_fn(lambda: eng.linear(op, a_, b_, out=out), 50)
+        fl = 2.0 * mb * i * o
+        gemm_ms += n * t_ms
+        gemm_flops += n * fl
+        if top is None or n * t_ms > top[0]:
+            top = (n * t_ms, op, i, o, t_ms, fl)
+    n_steps = E * n_mb
+    peak_tf = peaks["bf16_tflops_sustained"]
+    achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_f32_kernel (fp32 FFMA)" if args.gemm == "fp32" else "gemm_bf16_tc_kernel (tcgen05)",
+        "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+        "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+        "method": "every distinct Linear GEMM of one critic+actor minibatch step timed alone with CUDA events (50 reps), "
+                  "weighted by its launches per step",
+        "gemm_ms_per_update": gemm_ms * n_steps, "gemm_share_of_update": gemm_ms * n_steps / ms,
+        "top_gemm": {"op": ["fwd", "dgrad", "wgrad"][top[1]], "in": top[2], "out": top[3], "rows": mb, "ms": top[4],
+                     "tflops": top[5] / (top[4] * 1e-3) / 1e12},
+        "in_update_tflops": gemm_flops_per_update(hp) / (ms * 1e-3) / 1e12,
+    }
+
+    # TD(lambda) scan bandwidth on a batch far larger than L2 (the named shape moves 3 MB: launch-latency bound)
+    Tn, Nn = 128, 1 << 20
+    big = [torch.rand(Tn, Nn, device=dev) for _ in range(2)] + [-torch.rand(Tn, Nn, device=dev)] + \
+          [torch.zeros(Tn, Nn, device=dev), torch.zeros(Tn, Nn, device=dev)]
+    outb = torch.empty(Tn, Nn, device=dev)
+    scan_ms = time_fn(lambda: eng.td_lambda(big[0], big[1], big[3], big[4], big[2], 0.99, 0.95, convention="jax", out=outb), 10)
+    scan_bytes = 24.0 * Tn * Nn
+    scan = {"kernel": "td_lambda_kernel<4,4,jax,iw>", "bound": "hbm", "achieved": scan_bytes / (scan_ms * 1e-3) / 1e9,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": scan_bytes / (scan_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "shape": [Tn, Nn], "ms": scan_ms, "algorithmic_bytes": scan_bytes,
+            "named_shape_latency_ms": time_fn(lambda: eng.td_lambda(devb["soft_reward"], devb["value"], devb["done"],
+                                                                    devb["truncated"], devb["importance_weight"], h.gamma,
+                                                                    h.lmbda, out=target), 50)}
+    del big, outb
+
+    # clip+Adam bandwidth (28 B / parameter)
+    import ctypes as C
+    ns, hs = eng.critic.c_state(), hyp.c_struct()
+    adam_ms = time_fn(lambda: eng.lib.reppo_clip_adam(eng.ctx, C.byref(ns), eng.critic.count, C.byref(hs), None, eng._stream()), 50)
+    adam = {"kernel": "sumsq_partial_kernel + adam_kernel", "bound": "hbm (L2-resident at this size)",
+            "achieved": 28.0 * eng.critic.count / (adam_ms * 1e-3) / 1e9, "unit": "GB/s", "ms": adam_ms, "params": eng.critic.count}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu, _ = cpu_sample(hp, args.semantics, seconds=12.0)
+
+    line = {
+        "metric": "reppo_update_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.gemm == "fp32" else "bf16 operands / f32 accumulate", "data": "synthetic",
+        "config": workload_config(args.config, cfg, D, A, world),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_update * args.steps),
+        "launches_per_update": int(launches_per_update), "cuda_graph": use_graph, "semantics": args.semantics,
+        "sample_visits_per_s": value * E, "roofline": roofline, "scan": scan, "adam": adam, "cpu_baseline": cpu,
+        "final_metrics": {k: final_metrics[k] for k in ("critic_loss", "actor_loss", "kl", "entropy")},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

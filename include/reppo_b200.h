@@ -126,6 +126,9 @@ typedef struct reppo_plan {
   float* step_metrics;    /* [num_epochs * num_mini_batches, REPPO_NUM_METRICS] or NULL */
   float* metrics;         /* [REPPO_NUM_METRICS] mean over the minibatches of the LAST epoch (:660,671) */
   int32_t use_graph;      /* capture the step sequence in a CUDA graph and replay it */
+  int32_t noise_per_minibatch; /* 0: eps_* indexed by epoch only (JAX, above); 1: eps_pi [E, n_mb, mb, A] and
+                                  eps_kl [E, n_mb, kl_samples, mb, A] -- fresh draws for every step like
+                                  src/torchrl/reppo.py:300,308 */
 } reppo_plan;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -171,6 +174,15 @@ int reppo_critic_forward(reppo_ctx* ctx, const float* critic_params, const float
 /* Actor.forward, src/networks/torch_models.py:321-335: mean, std = exp(log_std) + min_std. */
 int reppo_actor_forward(reppo_ctx* ctx, const float* actor_params, const float* obs, int32_t rows, float min_std,
                         float* mean, float* std, reppo_stream stream);
+
+/* One Linear layer of FCNN (src/networks/torch_models.py:71-79, jax_models.py:35-49) in isolation -- the
+ * GEMM family the MLP forward / backward is built from; used by the kernel tests and bench.py's roofline leg.
+ *   op 0  forward : y[rows,out]  = x[rows,in] w[out,in]^T + bias   (bias may be NULL)
+ *   op 1  dgrad   : dx[rows,in]  = dy[rows,out] w[out,in]
+ *   op 2  wgrad   : dw[out,in]   = dy[rows,out]^T x[rows,in]       (dw must be zeroed by the caller)
+ * a / b / c are (x, w, y), (dy, w, dx), (dy, x, dw) respectively. */
+int reppo_linear(reppo_ctx* ctx, int32_t op, int32_t rows, int32_t in_features, int32_t out_features, const float* a,
+                 const float* b, float* c, const float* bias, reppo_stream stream);
 
 /* ---- one minibatch step ---------------------------------------------------------------------
  * update_critic, src/torchrl/reppo.py:227-283  == critic_loss_fn + apply_gradients,

@@ -61,7 +61,8 @@ class Batch(C.Structure):
 class Plan(C.Structure):
     _fields_ = [("num_epochs", C.c_int32), ("num_mini_batches", C.c_int32), ("minibatch", C.c_int32),
                 ("perms", C.c_void_p), ("eps_pi", C.c_void_p), ("eps_kl", C.c_void_p),
-                ("step_metrics", C.c_void_p), ("metrics", C.c_void_p), ("use_graph", C.c_int32)]
+                ("step_metrics", C.c_void_p), ("metrics", C.c_void_p), ("use_graph", C.c_int32),
+                ("noise_per_minibatch", C.c_int32)]
 
 
 # every symbol include/reppo_b200.h declares: name -> (restype, argtypes)
@@ -80,6 +81,7 @@ SYMBOLS = {
     "reppo_td_lambda": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _d, _d, _i32, _i32, _vp]),
     "reppo_critic_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "reppo_actor_forward": (C.c_int, [_vp, _vp, _vp, _i32, _f, _vp, _vp, _vp]),
+    "reppo_linear": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "reppo_critic_step": (C.c_int, [_vp, C.POINTER(State), C.POINTER(Batch), _vp, _i32, C.POINTER(Hyper), _vp, _vp]),
     "reppo_actor_step": (C.c_int, [_vp, C.POINTER(State), C.POINTER(Batch), _vp, _i32, _vp, _vp, C.POINTER(Hyper), _vp, _vp]),
     "reppo_critic_grad": (C.c_int, [_vp, C.POINTER(State), C.POINTER(Batch), _vp, _i32, C.POINTER(Hyper), _vp, _vp]),

@@ -89,6 +89,7 @@ struct reppo_ctx {
   int64_t launches = 0;
   // graph cache
   cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t cap_stream = nullptr;  // capture happens here: the caller's stream may be the legacy default stream
   GraphKey graph_key{};
   bool graph_valid = false;
   int64_t graph_launches = 0;
@@ -378,9 +379,10 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
   const int A = c->shape.action_dim, mb = p->minibatch, ks = c->shape.kl_samples;
   const int64_t per_epoch = static_cast<int64_t>(p->num_mini_batches) * mb;
   for (int e = 0; e < p->num_epochs; ++e) {
-    const float* eps_pi = p->eps_pi + static_cast<int64_t>(e) * mb * A;
-    const float* eps_kl = p->eps_kl + static_cast<int64_t>(e) * ks * mb * A;
     for (int j = 0; j < p->num_mini_batches; ++j) {
+      const int64_t slot = p->noise_per_minibatch ? static_cast<int64_t>(e) * p->num_mini_batches + j : e;
+      const float* eps_pi = p->eps_pi + slot * mb * A;
+      const float* eps_kl = p->eps_kl + slot * ks * mb * A;
       const int32_t* idx = p->perms + e * per_epoch + static_cast<int64_t>(j) * mb;
       const int64_t step = static_cast<int64_t>(e) * p->num_mini_batches + j;
       float* m = p->step_metrics ? p->step_metrics + step * M_NUM : c->scratch_metrics;
@@ -469,6 +471,7 @@ int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
 void reppo_ctx_destroy(reppo_ctx* c) {
   if (c == nullptr) return;
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
   delete c;
 }
@@ -551,6 +554,18 @@ int reppo_actor_forward(reppo_ctx* c, const float* ap, const float* obs, int32_t
   return REPPO_OK;
 }
 
+int reppo_linear(reppo_ctx* c, int32_t op, int32_t rows, int32_t in_f, int32_t out_f, const float* a, const float* b,
+                 float* out, const float* bias, reppo_stream stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!a || !b || !out || rows <= 0 || in_f <= 0 || out_f <= 0) return fail(c, REPPO_ERR_INVALID, "reppo_linear: bad argument");
+  c->launches = 0;
+  if (op == 0) return gemm(c, false, true, rows, out_f, in_f, a, in_f, b, in_f, out, out_f, bias, GEMM_STORE, 1, st);
+  if (op == 1) return gemm(c, false, false, rows, in_f, out_f, a, out_f, b, in_f, out, in_f, nullptr, GEMM_STORE, 1, st);
+  if (op == 2) return gemm(c, true, false, out_f, in_f, rows, a, out_f, b, in_f, out, in_f, nullptr, GEMM_ATOMIC,
+                           wgrad_split(out_f, in_f, rows), st);
+  return fail(c, REPPO_ERR_INVALID, "reppo_linear: unknown op");
+}
+
 int reppo_critic_grad(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int32_t mb,
                       const reppo_hyper* hp, float* metrics, reppo_stream stream) {
   c->launches = 0;
@@ -593,11 +608,16 @@ int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
     c->graph_valid = false;
     c->launches = 0;
-    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    cudaError_t e = cudaSuccess;
+    if (c->cap_stream == nullptr) {
+      e = cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking);
+      if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    e = cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal);
     if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
-    const int r = run_steps(c, s, b, p, hp, st);
+    const int r = run_steps(c, s, b, p, hp, c->cap_stream);
     cudaGraph_t graph = nullptr;
-    e = cudaStreamEndCapture(st, &graph);
+    e = cudaStreamEndCapture(c->cap_stream, &graph);
     if (r != REPPO_OK) { if (graph) cudaGraphDestroy(graph); return r; }
     if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
     e = cudaGraphInstantiate(&c->graph_exec, graph, 0);

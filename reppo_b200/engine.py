@@ -237,26 +237,46 @@ class ReppoEngine:
                                              std.data_ptr(), self._stream()), self.ctx, "reppo_actor_forward")
         return mean, std
 
+    def linear(self, op: int, a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One Linear layer's GEMM in isolation (op 0 forward y = x w^T + b, 1 dgrad, 2 wgrad); see reppo_linear."""
+        if op == 0:
+            rows, in_f = a.shape; out_f = b.shape[0]; shp = (rows, out_f)
+        elif op == 1:
+            rows, out_f = a.shape; in_f = b.shape[1]; shp = (rows, in_f)
+        else:
+            rows, out_f = a.shape; in_f = b.shape[1]; shp = (out_f, in_f)
+        if out is None:
+            out = torch.zeros(shp, device=self.device, dtype=torch.float32)
+        elif op == 2:
+            out.zero_()
+        L.check(self.lib.reppo_linear(self.ctx, op, rows, in_f, out_f, a.data_ptr(), b.data_ptr(), out.data_ptr(),
+                                      bias.data_ptr() if bias is not None else None, self._stream()), self.ctx, "reppo_linear")
+        return out
+
     # ---- steps ------------------------------------------------------------------------------
-    def _idx(self, idx: torch.Tensor) -> torch.Tensor:
-        return idx.to(device=self.device, dtype=torch.int32).contiguous()
+    def _idx(self, idx):
+        if isinstance(idx, int):  # identity gather over the first `idx` rows of the batch
+            return None, idx
+        t = idx.to(device=self.device, dtype=torch.int32).contiguous()
+        return t, t.numel()
 
     def critic_grad(self, batch: L.Batch, idx, hp: HyperParams, step: bool = False, metrics=None):
-        idx = self._idx(idx)
+        idx, rows = self._idx(idx)
         m = self.metrics if metrics is None else metrics
         st, h = self.c_state(), hp.c_struct()
         fn = self.lib.reppo_critic_step if step else self.lib.reppo_critic_grad
-        L.check(fn(self.ctx, C.byref(st), C.byref(batch), idx.data_ptr(), idx.numel(), C.byref(h), m.data_ptr(),
+        L.check(fn(self.ctx, C.byref(st), C.byref(batch), idx.data_ptr() if idx is not None else None, rows, C.byref(h), m.data_ptr(),
                    self._stream()), self.ctx, "reppo_critic_step" if step else "reppo_critic_grad")
         return m
 
     def actor_grad(self, batch: L.Batch, idx, eps_pi, eps_kl, hp: HyperParams, step: bool = False, metrics=None):
-        idx = self._idx(idx)
+        idx, rows = self._idx(idx)
         e1, e2 = self._f32(eps_pi), self._f32(eps_kl)
         m = self.metrics if metrics is None else metrics
         st, h = self.c_state(), hp.c_struct()
         fn = self.lib.reppo_actor_step if step else self.lib.reppo_actor_grad
-        L.check(fn(self.ctx, C.byref(st), C.byref(batch), idx.data_ptr(), idx.numel(), e1.data_ptr(), e2.data_ptr(),
+        L.check(fn(self.ctx, C.byref(st), C.byref(batch), idx.data_ptr() if idx is not None else None, rows, e1.data_ptr(), e2.data_ptr(),
                    C.byref(h), m.data_ptr(), self._stream()), self.ctx, "reppo_actor_step" if step else "reppo_actor_grad")
         return m
 
@@ -273,14 +293,21 @@ class ReppoEngine:
         eps_kl [E, 16, mb, A] device tensors (kept alive by the caller while the stream work runs)."""
         E = perms.shape[0]
         mb = perms.shape[1] // num_mini_batches
+        A, ks = self.cfg.action_dim, self.cfg.kl_samples
         assert perms.dtype == torch.int32 and perms.is_cuda and perms.is_contiguous()
-        assert tuple(eps_pi.shape) == (E, mb, self.cfg.action_dim), eps_pi.shape
-        assert tuple(eps_kl.shape) == (E, self.cfg.kl_samples, mb, self.cfg.action_dim), eps_kl.shape
+        assert eps_pi.is_cuda and eps_kl.is_cuda and eps_pi.is_contiguous() and eps_kl.is_contiguous()
+        per_mb = eps_pi.dim() == 4  # [E, n_mb, mb, A]: fresh noise for every step (Torch semantics)
+        if per_mb:
+            assert tuple(eps_pi.shape) == (E, num_mini_batches, mb, A), eps_pi.shape
+            assert tuple(eps_kl.shape) == (E, num_mini_batches, ks, mb, A), eps_kl.shape
+        else:
+            assert tuple(eps_pi.shape) == (E, mb, A), eps_pi.shape
+            assert tuple(eps_kl.shape) == (E, ks, mb, A), eps_kl.shape
         if step_metrics is None:
             step_metrics = torch.empty(E * num_mini_batches, L.NUM_METRICS, device=self.device)
         m = self.metrics if metrics is None else metrics
         plan = L.Plan(E, num_mini_batches, mb, perms.data_ptr(), eps_pi.data_ptr(), eps_kl.data_ptr(),
-                      step_metrics.data_ptr(), m.data_ptr(), int(use_graph))
+                      step_metrics.data_ptr(), m.data_ptr(), int(use_graph), int(per_mb))
         st, h = self.c_state(), hp.c_struct()
         L.check(self.lib.reppo_update(self.ctx, C.byref(st), C.byref(batch), C.byref(plan), C.byref(h), self._stream()),
                 self.ctx, "reppo_update")

@@ -1,0 +1,455 @@
+"""Torch-facing façade: the reference's entry points for the update path, backed by the B200 engine.
+
+Mirrors (same names, argument meaning, return keys, error behaviour):
+
+* ``Actor`` / ``Critic``            -- src/networks/torch_models.py:209-335 (constructor arguments, forward
+                                      tuple order, ``state_dict`` keys)
+* ``TrainState``                    -- src/torchrl/reppo.py:46-58
+* ``make_postprocess_fn``           -- src/torchrl/reppo.py:173-221 (TD(lambda) scan + flatten)
+* ``make_critic_update_fn``         -- src/torchrl/reppo.py:224-285
+* ``make_actor_update_fn``          -- src/torchrl/reppo.py:288-360
+* ``reppo_update``                  -- the whole per-rollout update: src/jaxrl/reppo.py:417-673 (learn_step) /
+                                      the loop body src/torchrl/reppo.py:614-632
+
+The modules' parameters are views into the engine's flat arenas; forward and update run the
+hand-written CUDA kernels through the C ABI.  ``TensorDict`` is not installed here, so batches are
+``TensorBatch`` (a dict of tensors sharing leading batch dimensions) or any mapping of tensors.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Any, Dict, Mapping, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .engine import EngineConfig, HyperParams, ReppoEngine
+
+
+# -------------------------------------------------------------------------------------------------
+# minimal TensorDict stand-in
+# -------------------------------------------------------------------------------------------------
+class TensorBatch(dict):
+    """Mapping of tensors with common leading dims: supports the operations the reference loop uses
+    (``data[indices]``, slicing, ``.contiguous()``, ``.float()``, ``.flatten(0, 1)``, ``.detach()``, ``.to``)."""
+
+    def __init__(self, data: Mapping[str, torch.Tensor], batch_size=None, device=None):
+        super().__init__(data)
+        self.batch_size = tuple(batch_size) if batch_size is not None else None
+
+    def _map(self, fn):
+        return TensorBatch({k: fn(v) for k, v in self.items()})
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return dict.__getitem__(self, key)
+        return self._map(lambda v: v[key])
+
+    def contiguous(self):
+        return self._map(lambda v: v.contiguous())
+
+    def float(self):
+        return self._map(lambda v: v.float())
+
+    def detach(self):
+        return self._map(lambda v: v.detach())
+
+    def flatten(self, a=0, b=1):
+        return self._map(lambda v: v.flatten(a, b))
+
+    def to(self, *args, **kw):
+        return self._map(lambda v: v.to(*args, **kw))
+
+
+# -------------------------------------------------------------------------------------------------
+# modules
+# -------------------------------------------------------------------------------------------------
+def _attach(root: nn.Module, dotted: str, param: nn.Parameter):
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, nn.Module())
+        mod = mod._modules[p]
+    mod.register_parameter(parts[-1], param)
+
+
+class _ArenaModule(nn.Module):
+    """nn.Module whose parameters are views into one flat fp32 tensor (the engine arena once bound)."""
+
+    def _build(self, layout: Dict[str, tuple], device):
+        n = sum(int(math.prod(s)) if s else 1 for s in layout.values())
+        self._layout = {}
+        off = 0
+        flat = torch.zeros((n + 3) // 4 * 4, dtype=torch.float32, device=device)
+        for k, shp in layout.items():
+            cnt = int(math.prod(shp)) if shp else 1
+            self._layout[k] = (off, tuple(shp))
+            _attach(self, k, nn.Parameter(flat[off:off + cnt].view(shp), requires_grad=True))
+            off += cnt
+        self._flat = flat
+        self._engine: Optional[ReppoEngine] = None
+
+    def _rebind(self, flat: torch.Tensor, grads: Optional[torch.Tensor] = None):
+        """Point every parameter at `flat` (same layout), keeping the current values."""
+        flat[: self._flat.numel()].copy_(self._flat.to(flat.device))
+        named = dict(self.named_parameters())
+        for k, (off, shp) in self._layout.items():
+            cnt = int(math.prod(shp)) if shp else 1
+            named[k].data = flat[off:off + cnt].view(shp)
+            if grads is not None:
+                named[k].grad = grads[off:off + cnt].view(shp)
+        self._flat = flat
+
+    def flat_parameters(self) -> torch.Tensor:
+        return self._flat
+
+
+def _fcnn_layout(prefix, in_f, hidden, out_f, layers, input_activation, use_norm, out=None):
+    out = {} if out is None else out
+    shift = 1 if input_activation else 0
+    for i in range(layers):
+        fi = in_f if i == 0 else hidden
+        fo = out_f if i == layers - 1 else hidden
+        out[f"{prefix}.net.{shift + i}.0.weight"] = (fo, fi)
+        out[f"{prefix}.net.{shift + i}.0.bias"] = (fo,)
+        if use_norm and i < layers - 1:
+            out[f"{prefix}.net.{shift + i}.1.weight"] = (fo,)
+    return out
+
+
+def _init_linear_(module: _ArenaModule, gen=None):
+    """nn.Linear's default init (kaiming_uniform(a=sqrt(5)) == U(+-1/sqrt(fan_in)) for weight and bias),
+    RMSNorm scale 1 -- what the reference modules get from torch (torch_models.py:71-79)."""
+    named = dict(module.named_parameters())
+    for k, p in named.items():
+        if k.endswith(".0.weight"):
+            bound = 1.0 / math.sqrt(p.shape[1])
+            with torch.no_grad():
+                p.uniform_(-bound, bound, generator=gen)
+                named[k[:-6] + "bias"].uniform_(-bound, bound, generator=gen)
+        elif k.endswith(".1.weight"):
+            with torch.no_grad():
+                p.fill_(1.0)
+
+
+class Critic(_ArenaModule):
+    """Categorical HL-Gauss critic (src/networks/torch_models.py:209-285)."""
+
+    def __init__(self, n_obs, n_act, num_atoms: int, vmin: float, vmax: float, hidden_dim=256, use_norm=True,
+                 use_encoder_norm=False, encoder_layers=1, head_layers=1, pred_layers=1, device=None,
+                 semantics: str = "torch"):
+        super().__init__()
+        if use_encoder_norm:
+            raise NotImplementedError("use_encoder_norm=True is never set by the reference (src/torchrl/reppo.py:510-523)")
+        if min(encoder_layers, head_layers, pred_layers) < 2:
+            raise NotImplementedError("layers == 1 has divergent JAX/Torch semantics (SURVEY.md App. B)")
+        self.n_obs, self.n_act, self.num_atoms, self.vmin, self.vmax = n_obs, n_act, num_atoms, float(vmin), float(vmax)
+        self.hidden_dim, self.use_norm = hidden_dim, use_norm
+        self.encoder_layers, self.head_layers, self.pred_layers = encoder_layers, head_layers, pred_layers
+        self.semantics = semantics
+        pred_out = hidden_dim + (1 if semantics == "jax" else 0)
+        layout = {"zero_dist": (num_atoms,)}
+        _fcnn_layout("feature_module", n_obs + n_act, hidden_dim, hidden_dim, encoder_layers, False, use_norm, layout)
+        _fcnn_layout("critic_module", hidden_dim, hidden_dim, num_atoms, head_layers, True, use_norm, layout)
+        _fcnn_layout("pred_module", hidden_dim, hidden_dim, pred_out, pred_layers, True, use_norm, layout)
+        self._build(layout, device)
+        _init_linear_(self)
+        self.values = torch.linspace(vmin, vmax, num_atoms, device=device, dtype=torch.float32)
+        with torch.no_grad():
+            self.zero_dist.copy_(hl_gauss(torch.zeros(1, 1), vmin, vmax, num_atoms, torch_variant=(semantics == "torch")).reshape(-1))
+
+    def forward(self, obs, action):
+        eng = _engine_of(self)
+        return eng.critic_forward(obs, action, params=self._flat)
+
+
+class Actor(_ArenaModule):
+    """Tanh-Gaussian policy with temperature / Lagrange multipliers (src/networks/torch_models.py:288-335)."""
+
+    def __init__(self, n_obs, n_act, ent_start: float, kl_start: float, hidden_dim=256, use_norm=True, layers=2,
+                 min_std=0.1, device=None):
+        super().__init__()
+        if layers < 2:
+            raise NotImplementedError("layers == 1 has divergent JAX/Torch semantics (SURVEY.md App. B)")
+        self.n_obs, self.n_act, self.hidden_dim, self.use_norm, self.layers = n_obs, n_act, hidden_dim, use_norm, layers
+        self.min_std = float(min_std)
+        layout = {"log_temp": (), "log_lagrange": ()}
+        _fcnn_layout("model", n_obs, hidden_dim, 2 * n_act, layers, False, use_norm, layout)
+        self._build(layout, device)
+        _init_linear_(self)
+        with torch.no_grad():
+            self.log_temp.fill_(math.log(ent_start))
+            self.log_lagrange.fill_(math.log(kl_start))
+
+    def forward(self, obs):
+        eng = _engine_of(self)
+        mean, std = eng.actor_forward(obs, min_std=self.min_std, params=self._flat)
+        pi = torch.distributions.TransformedDistribution(
+            torch.distributions.Normal(mean, std, validate_args=False), [torch.distributions.TanhTransform()])
+        return pi, torch.tanh(mean), torch.exp(self.log_temp.detach()), torch.exp(self.log_lagrange.detach())
+
+
+def hl_gauss(inp, vmin, vmax, num_atoms, torch_variant=True):
+    """Host helper used only to INITIALISE ``zero_dist`` (torch_models.py:268-276 / jax_models.py:288-290);
+    the training-time histogram is computed inside the fused CUDA loss kernel."""
+    x = torch.clip(inp, vmin, vmax)
+    bw = (vmax - vmin) / (num_atoms - 1)
+    support = torch.linspace(vmin - bw / 2, vmax + bw / 2, num_atoms + 1)
+    sigma = bw * 0.75
+    e1, e2 = (1e-6, 1e-6) if torch_variant else (0.0, 0.0)
+    cdf = torch.erf((support.unsqueeze(0) - x) / (math.sqrt(2.0) * sigma + e1))
+    z = cdf[..., -1] - cdf[..., 0]
+    return (cdf[..., 1:] - cdf[..., :-1]) / (z.unsqueeze(-1) + e2)
+
+
+class ArenaOptimizer:
+    """Stands where the reference keeps ``optim.AdamW`` (src/torchrl/reppo.py:527-534): the Adam moments live in
+    the engine arenas and the step is the fused CUDA kernel; this object only carries ``lr``."""
+
+    def __init__(self, lr: float):
+        self.param_groups = [{"lr": float(lr)}]
+
+    def zero_grad(self, set_to_none: bool = True):
+        pass
+
+
+@dataclass
+class TrainState:
+    """Field-compatible with src/torchrl/reppo.py:46-58."""
+    device: Any = None
+    obs: Any = None
+    critic_obs: Any = None
+    actor: Optional[Actor] = None
+    old_actor: Optional[Actor] = None
+    critic: Optional[Critic] = None
+    normalizer: Any = None
+    critic_normalizer: Any = None
+    actor_optimizer: Any = None
+    critic_optimizer: Any = None
+    scaler: Any = None
+    engine: Optional[ReppoEngine] = None
+
+    def compile(self):  # the reference compiles modules with torch.compile; nothing to do here
+        pass
+
+
+def _engine_of(module: _ArenaModule) -> ReppoEngine:
+    if module._engine is None:
+        raise RuntimeError("module is not bound to a ReppoEngine: build it with make_train_state(...) or bind_engine(...)")
+    return module._engine
+
+
+def bind_engine(actor: Actor, critic: Critic, old_actor: Optional[Actor] = None, *, max_rows: int = 2048,
+                semantics: Optional[str] = None, norm_type: str = "rms", gemm_mode: str = "fp32",
+                device=None) -> ReppoEngine:
+    """Create the engine for (actor, critic) and move their parameters into its arenas."""
+    semantics = semantics or critic.semantics
+    ecfg = EngineConfig(
+        obs_dim=actor.n_obs, action_dim=actor.n_act, critic_obs_dim=critic.n_obs, critic_hidden_dim=critic.hidden_dim,
+        actor_hidden_dim=actor.hidden_dim, num_bins=critic.num_atoms, vmin=critic.vmin, vmax=critic.vmax,
+        num_critic_encoder_layers=critic.encoder_layers, num_critic_head_layers=critic.head_layers,
+        num_critic_pred_layers=critic.pred_layers, num_actor_layers=actor.layers, use_critic_norm=critic.use_norm,
+        use_actor_norm=actor.use_norm, norm_type=norm_type, semantics=semantics, gemm_mode=gemm_mode, max_rows=max_rows)
+    eng = ReppoEngine(ecfg, device=device)
+    for mod, net in ((critic, eng.critic), (actor, eng.actor)):
+        assert {k: v[1] for k, v in mod._layout.items()} == {k: tuple(v[1]) for k, v in net.layout.items()}, "layout mismatch"
+        mod._rebind(net.params, net.grads)
+        mod._engine = eng
+    if old_actor is not None:
+        old_actor._rebind(eng.actor_old)
+        old_actor._engine = eng
+    else:
+        eng.sync_actor_old()
+    return eng
+
+
+def make_train_state(cfg, n_obs: int, n_critic_obs: int, n_act: int, device=None, max_rows: Optional[int] = None) -> TrainState:
+    """Networks + optimizers exactly as ``main`` builds them (src/torchrl/reppo.py:500-555), bound to one engine."""
+    h = cfg.hyperparameters
+    b200 = cfg.get("b200", {}) if hasattr(cfg, "get") else {}
+    semantics = b200.get("semantics", "torch")
+    device = torch.device(device if device is not None else f"cuda:{cfg.platform.get('device_rank', 0)}")
+    actor = Actor(n_obs=n_obs, n_act=n_act, ent_start=h.ent_start, kl_start=h.kl_start, hidden_dim=h.actor_hidden_dim,
+                  use_norm=h.use_actor_norm, layers=h.num_actor_layers, min_std=h.actor_min_std)
+    critic = Critic(n_obs=n_critic_obs, n_act=n_act, num_atoms=h.num_bins, vmin=h.vmin, vmax=h.vmax,
+                    hidden_dim=h.critic_hidden_dim, use_norm=h.use_critic_norm, use_encoder_norm=False,
+                    encoder_layers=h.num_critic_encoder_layers, head_layers=h.num_critic_head_layers,
+                    pred_layers=h.num_critic_pred_layers, semantics=semantics)
+    old_actor = Actor(n_obs=n_obs, n_act=n_act, ent_start=h.ent_start, kl_start=h.kl_start, hidden_dim=h.actor_hidden_dim,
+                      use_norm=h.use_actor_norm, layers=h.num_actor_layers, min_std=h.actor_min_std)
+    old_actor.load_state_dict(actor.state_dict())
+    mb = (int(h.num_steps) * int(h.num_envs)) // int(h.num_mini_batches)
+    gemm_mode = "bf16" if cfg.platform.get("amp_dtype", "f32") == "bf16" else "fp32"
+    eng = bind_engine(actor, critic, old_actor, max_rows=max_rows or mb, semantics=semantics,
+                      norm_type=b200.get("norm_type", "rms"), gemm_mode=gemm_mode, device=device)
+    return TrainState(device=device, actor=actor, old_actor=old_actor, critic=critic, normalizer=nn.Identity(),
+                      critic_normalizer=nn.Identity(), actor_optimizer=ArenaOptimizer(h.lr),
+                      critic_optimizer=ArenaOptimizer(h.lr), scaler=None, engine=eng)
+
+
+def _hyper(cfg, train_state: TrainState, which: str = "critic") -> HyperParams:
+    h = cfg.hyperparameters
+    opt = train_state.critic_optimizer if which == "critic" else train_state.actor_optimizer
+    lr = float(opt.param_groups[0]["lr"]) if opt is not None and hasattr(opt, "param_groups") else float(h.lr)
+    return HyperParams(
+        gamma=float(h.gamma), lmbda=float(h.lmbda), lr=lr, max_grad_norm=float(h.max_grad_norm), kl_bound=float(h.kl_bound),
+        ent_target_mult=float(h.ent_target_mult), aux_loss_mult=float(h.aux_loss_mult),
+        actor_min_std=float(train_state.actor.min_std), actor_kl_clip_mode=str(h.actor_kl_clip_mode),
+        reduce_kl=bool(h.get("reduce_kl", True)), update_entropy_lagrangian=bool(h.get("update_entropy_lagrangian", True)),
+        update_kl_lagrangian=bool(h.get("update_kl_lagrangian", True)),
+        partial_reset=bool(cfg.env.get("partial_reset", False)))
+
+
+def _engine_for(cfg, train_state: TrainState) -> ReppoEngine:
+    if train_state.engine is None:
+        h = cfg.hyperparameters
+        mb = (int(h.num_steps) * int(h.num_envs)) // int(h.num_mini_batches)
+        train_state.engine = bind_engine(train_state.actor, train_state.critic, train_state.old_actor, max_rows=mb,
+                                         device=train_state.device)
+    return train_state.engine
+
+
+# -------------------------------------------------------------------------------------------------
+# the three factory closures
+# -------------------------------------------------------------------------------------------------
+def make_postprocess_fn(cfg, env=None):
+    """TD(lambda) targets + flatten (src/torchrl/reppo.py:173-221).  Like the reference's ``compute_gve`` the Torch
+    convention writes ``truncations[-1] = 1`` into the transition."""
+
+    def postprocess(train_state: TrainState, transition: Mapping[str, torch.Tensor]):
+        eng = _engine_for(cfg, train_state)
+        h = cfg.hyperparameters
+        T, N = int(h.num_steps), int(h.num_envs)
+        dev = eng.device
+
+        def tn(x):  # [T, N, 1] or [T, N] -> contiguous fp32 [T, N] on the device (a view when already so)
+            x = x.to(dev)
+            x = x.reshape(T, N)
+            return x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+
+        trunc_in = transition["truncations"]
+        trunc = tn(trunc_in)
+        conv = eng.cfg.semantics
+        iw = transition.get("importance_weight") if hasattr(transition, "get") else None
+        gve = eng.td_lambda(tn(transition["rewards"]), tn(transition["next_values"]), tn(transition["dones"]), trunc,
+                            tn(iw) if iw is not None else None, float(h.gamma), float(h.lmbda), convention=conv)
+        if conv == "torch" and trunc.data_ptr() != trunc_in.data_ptr():
+            trunc_in[-1] = 1.0  # the kernel wrote into a converted copy: reproduce the in-place mutation (:178)
+        data = TensorBatch({k: transition[k] for k in (
+            "observations", "critic_observations", "actions", "rewards", "next_embeddings", "next_values", "dones",
+            "truncations") if k in transition})
+        data["truncations"] = trunc.reshape(T, N, 1)
+        data["gve"] = gve.reshape(T, N, 1)
+        if "raw_rewards" in transition:
+            data["raw_rewards"] = transition["raw_rewards"]
+        return data.to(dev).float().flatten(0, 1).detach()
+
+    return postprocess
+
+
+def _mini_batch(eng: ReppoEngine, data: Mapping[str, torch.Tensor]) -> L.Batch:
+    flat = {
+        "obs": data["observations"], "critic_obs": data["critic_observations"], "action": data["actions"],
+        "done": data["dones"].reshape(-1), "truncated": data["truncations"].reshape(-1),
+        "next_emb": data["next_embeddings"], "target": data["gve"].reshape(-1),
+        "reward": data["raw_rewards"].reshape(-1) if "raw_rewards" in data else
+        (data["rewards"].reshape(-1) if eng.cfg.semantics == "jax" else None),
+    }
+    return eng.make_batch(flat)
+
+
+def make_critic_update_fn(cfg, train_state: TrainState):
+    """``update(data) -> logs`` with the reference's keys (src/torchrl/reppo.py:224-285)."""
+    eng = _engine_for(cfg, train_state)
+
+    def update(data: Mapping[str, torch.Tensor]):
+        rows = data["gve"].shape[0]
+        m = eng.critic_step(_mini_batch(eng, data), rows, _hyper(cfg, train_state, "critic")).clone()
+        i = L.METRIC_NAMES.index
+        return {"critic_grad_norm": m[i("critic_grad_norm")], "qf_loss": m[i("critic_loss")], "qf_max": m[i("target_max")],
+                "qf_min": m[i("target_min")], "qf_mean": m[i("target_mean")], "embedding_loss": m[i("aux_mean")]}
+
+    return update
+
+
+def make_actor_update_fn(cfg, train_state: TrainState, generator: Optional[torch.Generator] = None):
+    """``update(data) -> logs`` (src/torchrl/reppo.py:288-360).  Fresh standard-normal noise per call from torch's
+    device generator (the reference draws it inside ``rsample`` / ``sample((16,))``)."""
+    eng = _engine_for(cfg, train_state)
+    A, ks = eng.cfg.action_dim, eng.cfg.kl_samples
+
+    def update(data: Mapping[str, torch.Tensor], eps_pi: Optional[torch.Tensor] = None, eps_kl: Optional[torch.Tensor] = None):
+        rows = data["gve"].shape[0]
+        if eps_pi is None:
+            eps_pi = torch.randn(rows, A, device=eng.device, generator=generator)
+        if eps_kl is None:
+            eps_kl = torch.randn(ks, rows, A, device=eng.device, generator=generator)
+        m = eng.actor_step(_mini_batch(eng, data), rows, eps_pi, eps_kl, _hyper(cfg, train_state, "actor")).clone()
+        i = L.METRIC_NAMES.index
+        return {"actor_grad_norm": m[i("actor_grad_norm")], "actor_loss": m[i("actor_loss")], "kl": m[i("kl")],
+                "entropy": m[i("entropy")], "temperature": m[i("temperature")], "lagrangian": m[i("lagrangian")],
+                "entropy_loss": m[i("entropy_loss")], "lagrangian_loss": m[i("lagrangian_loss")]}
+
+    return update
+
+
+# -------------------------------------------------------------------------------------------------
+# the whole update in one call
+# -------------------------------------------------------------------------------------------------
+def reppo_update(train_state: TrainState, transition: Mapping[str, torch.Tensor], cfg, *,
+                 perms: Optional[torch.Tensor] = None, eps_pi: Optional[torch.Tensor] = None,
+                 eps_kl: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None,
+                 use_graph: Optional[bool] = None, return_device_metrics: bool = False, world_size: int = 1):
+    """One full REPPO update over a rollout batch = ``learn_step`` (src/jaxrl/reppo.py:417-673) /
+    lines 614-632 of src/torchrl/reppo.py: TD(lambda) scan, ``num_epochs`` x ``num_mini_batches`` critic+actor
+    steps on shuffled minibatches, then ``old_actor <- actor``.
+
+    ``transition``: ``[T, N, ...]`` tensors (host or device) with the reference's keys.  ``perms [E, S]``,
+    ``eps_pi`` and ``eps_kl`` may be injected (parity tests); by default they are drawn on the device:
+    JAX semantics reuses one noise draw per epoch, Torch semantics draws per minibatch.
+    Returns the metrics of the last epoch averaged over its minibatches, as a dict of Python floats.
+    """
+    eng = _engine_for(cfg, train_state)
+    h = cfg.hyperparameters
+    T, N, n_mb, E = int(h.num_steps), int(h.num_envs), int(h.num_mini_batches), int(h.num_epochs)
+    S = T * N
+    mb = S // n_mb
+    dev = eng.device
+    A, ks = eng.cfg.action_dim, eng.cfg.kl_samples
+    data = make_postprocess_fn(cfg)(train_state, transition)
+    if eng.cfg.semantics == "jax":
+        eng.sync_actor_old()  # actor_target <- actor at the START of learn_step (src/jaxrl/reppo.py:457-464)
+    if perms is None:
+        perms = torch.stack([torch.randperm(S, device=dev, generator=generator) for _ in range(E)])
+    perms = perms.to(device=dev, dtype=torch.int32).contiguous()
+    per_mb = eng.cfg.semantics == "torch"
+    if eps_pi is None:
+        eps_pi = torch.randn((E, n_mb, mb, A) if per_mb else (E, mb, A), device=dev, generator=generator)
+    if eps_kl is None:
+        eps_kl = torch.randn((E, n_mb, ks, mb, A) if per_mb else (E, ks, mb, A), device=dev, generator=generator)
+    b200 = cfg.get("b200", {}) if hasattr(cfg, "get") else {}
+    graph = bool(b200.get("use_graph", True)) if use_graph is None else use_graph
+    batch = _mini_batch(eng, data)
+    hyp = _hyper(cfg, train_state)
+    hyp.world_size = world_size  # data-parallel ranks sharing every minibatch (gradients all-reduced by the engine)
+    m, sm = eng.update(batch, perms, eps_pi.to(dev).float().contiguous(), eps_kl.to(dev).float().contiguous(),
+                       hyp, n_mb, use_graph=graph)
+    eng.sync_actor_old()  # src/torchrl/reppo.py:631-632 (same state as the JAX ordering at the next call)
+    if return_device_metrics:
+        return m, sm
+    md = eng.metrics_dict(m)  # one device->host read per update
+    logs = {  # Torch keys (src/torchrl/reppo.py:275-283,348-358)
+        "critic_grad_norm": md["critic_grad_norm"], "qf_loss": md["critic_loss"], "qf_max": md["target_max"],
+        "qf_min": md["target_min"], "qf_mean": md["target_mean"], "embedding_loss": md["aux_mean"],
+        "actor_grad_norm": md["actor_grad_norm"], "actor_loss": md["actor_loss"], "kl": md["kl"], "entropy": md["entropy"],
+        "temperature": md["temperature"], "lagrangian": md["lagrangian"], "entropy_loss": md["entropy_loss"],
+        "lagrangian_loss": md["lagrangian_loss"],
+        # JAX keys (src/jaxrl/reppo.py:514-524,609-622)
+        "value_loss": md["value_loss"], "loss": md["actor_loss"], "q": md["q_mean"], "temp": md["temperature"],
+        "abs_pred_action": md["abs_pred_action"], "reward_mean": md["reward_mean"], "target_values": md["target_mean"],
+        "aux_loss": md["aux_mean"],
+    }
+    return logs

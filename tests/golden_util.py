@@ -9,7 +9,10 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _digest_ok(t, d, tol=0.0):
+    # the sums are re-computed on another CPU (different SIMD width -> different summation order):
+    # compare them to 1e-10 relative, the 64-entry head exactly
     f = t.detach().double().reshape(-1)
+    tol = max(tol, 1e-10 * max(1.0, d["abs_sum"].item()))
     return (tuple(t.shape) == tuple(d["shape"]) and torch.equal(t.reshape(-1)[:64], d["head"])
             and abs(f.sum().item() - d["sum"].item()) <= tol and abs(f.abs().sum().item() - d["abs_sum"].item()) <= tol)
 
