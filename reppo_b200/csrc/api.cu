@@ -4,6 +4,13 @@
 // caller.  One minibatch step = critic forward/backward/clip/Adam followed by actor
 // forward/backward/clip/Adam (src/jaxrl/reppo.py:466-643; src/torchrl/reppo.py:622-629), the
 // whole update = epochs x minibatches of those, optionally captured once into a CUDA graph.
+//
+// GEMM modes.  REPPO_GEMM_FP32: every Linear runs the fp32 FFMA kernel (gemm_f32.cu).
+// REPPO_GEMM_BF16: every Linear runs the tcgen05 kernel (gemm_bf16_tc.cu).  Its bf16 operands
+// are never produced by separate cast passes inside a step: each elementwise kernel that
+// produces a GEMM operand (gather, norm+swish forward/backward, the loss kernels) writes a
+// bf16 "twin" next to its fp32 output, and the Adam step is followed by one pack kernel that
+// refreshes the bf16 shadows W and W^T of the network it updated.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
@@ -12,6 +19,7 @@
 
 #include <algorithm>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/reppo_b200.h"
@@ -22,8 +30,10 @@ using namespace reppo;
 namespace {
 
 struct Linear {
-  int64_t w = -1, b = -1, g = -1, beta = -1;  // offsets into the flat arena (floats)
+  int64_t w = -1, b = -1, g = -1, beta = -1;  // offsets into the flat fp32 arena (floats)
   int in = 0, out = 0;
+  int64_t sb = 0, st = 0;                     // offsets into the bf16 shadows W [out, ld_b] / W^T [in, ld_t] (elements)
+  int ld_b = 0, ld_t = 0;
 };
 struct Mlp {
   std::vector<Linear> layers;
@@ -43,6 +53,11 @@ struct Sem {
   int clip_policy_sample, old_logp_at_clipped, reward_head, aux_mask_done, torch_opt;
   float force_min_std;  // < 0: use hp.actor_min_std
 };
+struct Twin {  // bf16 copy of an fp32 activation buffer (REPPO_GEMM_BF16 only)
+  uint16_t* p = nullptr;
+  int ld = 0;
+};
+enum { SLOT_CRITIC = 0, SLOT_ACTOR = 1, SLOT_ACTOR_OLD = 2, NUM_SLOTS = 3 };
 
 // minimal NCCL surface (resolved with dlsym from libnccl.so.2)
 typedef struct ncclComm* ncclComm_t;
@@ -65,14 +80,18 @@ struct GraphKey {
 
 std::string g_create_error;
 
+inline int round8(int x) { return (x + 7) & ~7; }
+
 }  // namespace
 
 struct reppo_ctx {
   reppo_shape shape;
   Sem sem;
+  bool tc = false;  // REPPO_GEMM_BF16
   Mlp feature, head, pred, actor;
   int64_t zero_dist_off = 0, critic_count = 0, actor_count = 0;
-  int pred_out = 0, K0 = 0;
+  int64_t shadow_b_elems[2] = {0, 0}, shadow_t_elems[2] = {0, 0};  // per network (critic, actor)
+  int pred_out = 0, K0 = 0, maxdim = 0;
   std::vector<TensorInfo> critic_tensors, actor_tensors;
   std::vector<float> edges_h, support_h;
   HLConsts hl{};
@@ -85,6 +104,10 @@ struct reppo_ctx {
   float *tmpA = nullptr, *tmpB = nullptr, *dxs = nullptr, *dfeat = nullptr, *dlogits = nullptr, *dpred = nullptr,
         *dout = nullptr, *dx0 = nullptr;
   float *logp = nullptr, *kl = nullptr, *q = nullptr, *gmu = nullptr, *gsig = nullptr, *scratch_metrics = nullptr;
+  std::unordered_map<const float*, Twin> twins;
+  uint16_t* shadow_b[NUM_SLOTS] = {nullptr, nullptr, nullptr};
+  uint16_t* shadow_t[NUM_SLOTS] = {nullptr, nullptr, nullptr};
+  uint16_t *lin_a = nullptr, *lin_b = nullptr, *lin_c = nullptr;  // scratch operands of reppo_linear
   std::string err;
   int64_t launches = 0;
   // graph cache
@@ -97,6 +120,11 @@ struct reppo_ctx {
   NcclApi nccl;
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
+
+  Twin twin(const float* p) const {
+    auto it = twins.find(p);
+    return it == twins.end() ? Twin{} : it->second;
+  }
 };
 
 namespace {
@@ -119,8 +147,8 @@ int fail(reppo_ctx* c, int code, const std::string& msg) {
     if (r__ != REPPO_OK) return r__;    \
   } while (0)
 
-void add_fcnn(std::vector<TensorInfo>& ts, int64_t& off, Mlp& mlp, const std::string& prefix, int in_f, int hidden,
-              int out_f, int layers, bool input_activation, int norm) {
+void add_fcnn(std::vector<TensorInfo>& ts, int64_t& off, int64_t& sb, int64_t& st, Mlp& mlp, const std::string& prefix,
+              int in_f, int hidden, int out_f, int layers, bool input_activation, int norm) {
   // Sequential indices of torch_models.FCNN (:97-139): an input activation occupies slot 0.
   const int shift = input_activation ? 1 : 0;
   mlp.norm = norm;
@@ -135,6 +163,9 @@ void add_fcnn(std::vector<TensorInfo>& ts, int64_t& off, Mlp& mlp, const std::st
       L.g = off; ts.push_back({blk + ".1.weight", off, L.out, 0}); off += L.out;
       if (norm == NORM_LAYER) { L.beta = off; ts.push_back({blk + ".1.bias", off, L.out, 0}); off += L.out; }
     }
+    L.ld_b = round8(L.in); L.ld_t = round8(L.out);
+    L.sb = sb; sb += static_cast<int64_t>(L.out) * L.ld_b; sb = (sb + 63) & ~static_cast<int64_t>(63);
+    L.st = st; st += static_cast<int64_t>(L.in) * L.ld_t; st = (st + 63) & ~static_cast<int64_t>(63);
     mlp.layers.push_back(L);
   }
 }
@@ -159,89 +190,170 @@ struct Bump {
 // lays the workspace out; when base == nullptr only sizes it
 size_t layout_workspace(reppo_ctx* c, char* base) {
   const reppo_shape& s = c->shape;
-  const size_t R = s.max_rows, H = s.critic_hidden, Ha = s.actor_hidden, B = s.num_bins, A = s.action_dim;
+  const size_t R = s.max_rows, H = s.critic_hidden, B = s.num_bins, A = s.action_dim;
   const size_t P = c->pred_out, K0 = c->K0, D = s.obs_dim;
   Bump bp;
+  c->twins.clear();
   auto F = [&](size_t n) -> float* {
     const size_t o = bp.take(n * sizeof(float));
     return base ? reinterpret_cast<float*>(base + o) : nullptr;
+  };
+  auto Hf = [&](size_t n) -> uint16_t* {
+    const size_t o = bp.take(n * sizeof(uint16_t));
+    return base ? reinterpret_cast<uint16_t*>(base + o) : nullptr;
+  };
+  // fp32 buffer [R, cols] that is also a GEMM operand: give it a bf16 twin in tensor-core mode
+  auto FT = [&](size_t cols) -> float* {
+    float* p = F(R * cols);
+    if (c->tc) {
+      Twin t;
+      t.ld = round8(static_cast<int>(cols));
+      t.p = Hf(R * t.ld);
+      if (base) c->twins[p] = t;
+    }
+    return p;
   };
   auto acts = [&](Acts& a, const Mlp& m, size_t out_dim) {
     a.z.clear(); a.x.clear(); a.rstd.clear(); a.mean.clear();
     for (size_t i = 0; i + 1 < m.layers.size(); ++i) {
       const size_t h = m.layers[i].out;
-      a.z.push_back(F(R * h)); a.x.push_back(F(R * h)); a.rstd.push_back(F(R)); a.mean.push_back(F(R));
+      a.z.push_back(F(R * h)); a.x.push_back(FT(h)); a.rstd.push_back(F(R)); a.mean.push_back(F(R));
     }
     a.out = F(R * out_dim);
   };
   c->edges_d = F(B + 1); c->support_d = F(B); c->partials = F(kMaxPartials); c->scratch_metrics = F(M_NUM);
-  c->x0 = F(R * K0); c->xs = F(R * H); c->xa0 = F(R * D);
+  c->x0 = FT(K0); c->xs = FT(H); c->xa0 = FT(D);
   acts(c->fa, c->feature, H); acts(c->ha, c->head, B); acts(c->pa, c->pred, P);
   acts(c->aa, c->actor, 2 * A); acts(c->oa, c->actor, 2 * A);
-  const size_t maxdim = std::max(std::max(H, Ha), std::max(std::max(B, P), std::max(K0, D)));
-  c->tmpA = F(R * maxdim); c->tmpB = F(R * maxdim);
-  c->dxs = F(R * H); c->dfeat = F(R * H); c->dlogits = F(R * B); c->dpred = F(R * P); c->dout = F(R * 2 * A);
+  const size_t maxdim = c->maxdim;
+  c->tmpA = F(R * maxdim); c->tmpB = FT(maxdim);
+  c->dxs = F(R * H); c->dfeat = FT(H); c->dlogits = FT(B); c->dpred = FT(P); c->dout = FT(2 * A);
   c->dx0 = F(R * K0);
   c->logp = F(R); c->kl = F(R); c->q = F(R); c->gmu = F(R * A); c->gsig = F(R * A);
+  if (c->tc) {
+    c->shadow_b[SLOT_CRITIC] = Hf(c->shadow_b_elems[0]); c->shadow_t[SLOT_CRITIC] = Hf(c->shadow_t_elems[0]);
+    c->shadow_b[SLOT_ACTOR] = Hf(c->shadow_b_elems[1]); c->shadow_t[SLOT_ACTOR] = Hf(c->shadow_t_elems[1]);
+    c->shadow_b[SLOT_ACTOR_OLD] = Hf(c->shadow_b_elems[1]); c->shadow_t[SLOT_ACTOR_OLD] = nullptr;
+    const size_t md8 = round8(static_cast<int>(maxdim));
+    c->lin_a = Hf(R * md8); c->lin_c = Hf(R * md8); c->lin_b = Hf(maxdim * md8);
+  }
   return bp.off;
 }
 
-int gemm(reppo_ctx* c, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
-         int ldc, const float* bias, int mode, int split_k, cudaStream_t st) {
-  // REPPO_GEMM_BF16 routes the aligned H x H layers to the tcgen05 kernel (gemm_bf16_tc.cu) once
-  // enabled; every other shape and the fp32 mode run the FFMA kernel.
-  CK(launch_gemm_f32(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, mode, split_k, st));
+int wgrad_split(int out, int in, int rows, bool tc) {
+  if (tc) {
+    const int tiles = ((out + 127) / 128) * ((in + 127) / 128);
+    int split = std::max(1, 128 / std::max(1, tiles));
+    return std::min(split, std::max(1, rows / 128));
+  }
+  const int tiles = ((out + 63) / 64) * ((in + 63) / 64);
+  int split = std::max(1, 296 / std::max(1, tiles));
+  return std::min(split, std::max(1, rows / 64));
+}
+
+// y[rows,out] = x[rows,in] W^T + b
+int linear_fwd(reppo_ctx* c, const Linear& L, const float* params, int slot, const float* x, int rows, float* y, cudaStream_t st) {
+  if (c->tc) {
+    const Twin tx = c->twin(x);
+    if (tx.p == nullptr) return fail(c, REPPO_ERR_INVALID, "internal: forward operand has no bf16 twin");
+    CK(launch_gemm_bf16_tc(false, rows, L.out, L.in, tx.p, tx.ld, c->shadow_b[slot] + L.sb, L.ld_b, y, L.out, params + L.b,
+                           GEMM_STORE, 1, st));
+  } else {
+    CK(launch_gemm_f32(false, true, rows, L.out, L.in, x, L.in, params + L.w, L.in, y, L.out, params + L.b, GEMM_STORE, 1, st));
+  }
+  return REPPO_OK;
+}
+// dx[rows,in] (=|+=) dy[rows,out] W
+int linear_dgrad(reppo_ctx* c, const Linear& L, const float* params, int slot, const float* dy, int rows, float* dx, int mode,
+                 cudaStream_t st) {
+  if (c->tc) {
+    const Twin td = c->twin(dy);
+    if (td.p == nullptr || c->shadow_t[slot] == nullptr) return fail(c, REPPO_ERR_INVALID, "internal: dgrad operand has no bf16 twin");
+    CK(launch_gemm_bf16_tc(false, rows, L.in, L.out, td.p, td.ld, c->shadow_t[slot] + L.st, L.ld_t, dx, L.in, nullptr, mode, 1, st));
+  } else {
+    CK(launch_gemm_f32(false, false, rows, L.in, L.out, dy, L.out, params + L.w, L.in, dx, L.in, nullptr, mode, 1, st));
+  }
+  return REPPO_OK;
+}
+// dW[out,in] += dy[rows,out]^T x[rows,in]   (dW zeroed at the start of the step)
+int linear_wgrad(reppo_ctx* c, const Linear& L, const float* dy, const float* x, int rows, float* dw, cudaStream_t st) {
+  const int split = wgrad_split(L.out, L.in, rows, c->tc);
+  if (c->tc) {
+    const Twin td = c->twin(dy), tx = c->twin(x);
+    if (td.p == nullptr || tx.p == nullptr) return fail(c, REPPO_ERR_INVALID, "internal: wgrad operand has no bf16 twin");
+    CK(launch_gemm_bf16_tc(true, L.out, L.in, rows, td.p, td.ld, tx.p, tx.ld, dw, L.in, nullptr, GEMM_ATOMIC, split, st));
+  } else {
+    CK(launch_gemm_f32(true, false, L.out, L.in, rows, dy, L.out, x, L.in, dw, L.in, nullptr, GEMM_ATOMIC, split, st));
+  }
   return REPPO_OK;
 }
 
-int mlp_forward(reppo_ctx* c, const Mlp& m, const float* params, const float* in, int rows, Acts& a, cudaStream_t st) {
+// refresh the bf16 shadows of one network's weights (no-op in fp32 mode)
+int pack_shadows(reppo_ctx* c, int slot, const float* params, cudaStream_t st) {
+  if (!c->tc) return REPPO_OK;
+  PackTable t{};
+  auto add = [&](const Mlp& m) {
+    for (const Linear& L : m.layers) {
+      PackEntry& e = t.e[t.n++];
+      e.w = params + L.w; e.wb = c->shadow_b[slot] + L.sb;
+      e.wtb = c->shadow_t[slot] ? c->shadow_t[slot] + L.st : nullptr;
+      e.out = L.out; e.in = L.in; e.ld_b = L.ld_b; e.ld_t = L.ld_t;
+    }
+  };
+  if (slot == SLOT_CRITIC) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
+  CK(launch_pack_weights(t, st));
+  return REPPO_OK;
+}
+
+int pack_all(reppo_ctx* c, const reppo_state* s, cudaStream_t st) {
+  RET(pack_shadows(c, SLOT_CRITIC, s->critic.params, st));
+  RET(pack_shadows(c, SLOT_ACTOR, s->actor.params, st));
+  if (s->actor_old) RET(pack_shadows(c, SLOT_ACTOR_OLD, s->actor_old, st));
+  return REPPO_OK;
+}
+
+int mlp_forward(reppo_ctx* c, const Mlp& m, const float* params, int slot, const float* in, int rows, Acts& a, cudaStream_t st) {
   const float* cur = in;
   const int n = static_cast<int>(m.layers.size());
   for (int i = 0; i < n; ++i) {
     const Linear& L = m.layers[i];
     const bool last = (i == n - 1);
     float* dst = last ? a.out : a.z[i];
-    RET(gemm(c, false, true, rows, L.out, L.in, cur, L.in, params + L.w, L.in, dst, L.out, params + L.b, GEMM_STORE, 1, st));
+    RET(linear_fwd(c, L, params, slot, cur, rows, dst, st));
     if (!last) {
+      const Twin tw = c->twin(a.x[i]);
       CK(launch_norm_act_fwd(m.norm, a.z[i], L.g >= 0 ? params + L.g : nullptr, L.beta >= 0 ? params + L.beta : nullptr,
-                             rows, L.out, c->sem.norm_eps, a.x[i], a.rstd[i], a.mean[i], st));
+                             rows, L.out, c->sem.norm_eps, a.x[i], a.rstd[i], a.mean[i], tw.p, tw.ld, st));
       cur = a.x[i];
     }
   }
   return REPPO_OK;
 }
 
-int wgrad_split(int out, int in, int rows) {
-  const int tiles = ((out + 63) / 64) * ((in + 63) / 64);
-  int split = std::max(1, 296 / std::max(1, tiles));
-  split = std::min(split, std::max(1, rows / 64));
-  return split;
-}
-
-// d: gradient w.r.t. the MLP output [rows, out_last] (read only).  grads == nullptr: frozen network (dgrad only).
+// d_out: gradient w.r.t. the MLP output [rows, out_last] (read only).  grads == nullptr: frozen network (dgrad only).
 // dx_in != nullptr: also produce the gradient w.r.t. the MLP input (mode GEMM_STORE / GEMM_ACCUM).
-int mlp_backward(reppo_ctx* c, const Mlp& m, const float* params, float* grads, const float* in, int rows, const Acts& a,
-                 const float* d_out, float* dx_in, int dx_mode, float* bias2, float scale2, cudaStream_t st) {
+int mlp_backward(reppo_ctx* c, const Mlp& m, const float* params, int slot, float* grads, const float* in, int rows,
+                 const Acts& a, const float* d_out, float* dx_in, int dx_mode, float* bias2, float scale2, cudaStream_t st) {
   const int n = static_cast<int>(m.layers.size());
   const float* d = d_out;
   for (int i = n - 1; i >= 0; --i) {
     const Linear& L = m.layers[i];
     const float* xin = (i == 0) ? in : a.x[i - 1];
     if (grads != nullptr) {
-      RET(gemm(c, true, false, L.out, L.in, rows, d, L.out, xin, L.in, grads + L.w, L.in, nullptr, GEMM_ATOMIC,
-               wgrad_split(L.out, L.in, rows), st));
+      RET(linear_wgrad(c, L, d, xin, rows, grads + L.w, st));
       CK(launch_colsum(d, rows, L.out, L.out, grads + L.b, (i == n - 1) ? bias2 : nullptr, scale2, st));
     }
     if (i > 0) {
       const Linear& Lp = m.layers[i - 1];
-      RET(gemm(c, false, false, rows, L.in, L.out, d, L.out, params + L.w, L.in, c->tmpA, L.in, nullptr, GEMM_STORE, 1, st));
+      RET(linear_dgrad(c, L, params, slot, d, rows, c->tmpA, GEMM_STORE, st));
+      const Twin tw = c->twin(c->tmpB);
       CK(launch_norm_act_bwd(m.norm, c->tmpA, a.z[i - 1], Lp.g >= 0 ? params + Lp.g : nullptr,
                              Lp.beta >= 0 ? params + Lp.beta : nullptr, a.rstd[i - 1], a.mean[i - 1], rows, L.in, c->tmpB,
                              (grads && Lp.g >= 0) ? grads + Lp.g : nullptr, (grads && Lp.beta >= 0) ? grads + Lp.beta : nullptr,
-                             st));
+                             tw.p, tw.ld, st));
       d = c->tmpB;
     } else if (dx_in != nullptr) {
-      RET(gemm(c, false, false, rows, L.in, L.out, d, L.out, params + L.w, L.in, dx_in, L.in, nullptr, dx_mode, 1, st));
+      RET(linear_dgrad(c, L, params, slot, d, rows, dx_in, dx_mode, st));
     }
   }
   return REPPO_OK;
@@ -254,10 +366,12 @@ int check_rows(reppo_ctx* c, int rows) {
 }
 
 int critic_trunk(reppo_ctx* c, const float* cp, int rows, bool with_pred, cudaStream_t st) {
-  RET(mlp_forward(c, c->feature, cp, c->x0, rows, c->fa, st));
-  CK(launch_norm_act_fwd(NORM_NONE, c->fa.out, nullptr, nullptr, rows, c->shape.critic_hidden, 0.f, c->xs, nullptr, nullptr, st));
-  RET(mlp_forward(c, c->head, cp, c->xs, rows, c->ha, st));
-  if (with_pred) RET(mlp_forward(c, c->pred, cp, c->xs, rows, c->pa, st));
+  RET(mlp_forward(c, c->feature, cp, SLOT_CRITIC, c->x0, rows, c->fa, st));
+  const Twin tw = c->twin(c->xs);
+  CK(launch_norm_act_fwd(NORM_NONE, c->fa.out, nullptr, nullptr, rows, c->shape.critic_hidden, 0.f, c->xs, nullptr, nullptr,
+                         tw.p, tw.ld, st));
+  RET(mlp_forward(c, c->head, cp, SLOT_CRITIC, c->xs, rows, c->ha, st));
+  if (with_pred) RET(mlp_forward(c, c->pred, cp, SLOT_CRITIC, c->xs, rows, c->pa, st));
   return REPPO_OK;
 }
 
@@ -285,18 +399,23 @@ int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
   if (c->sem.reward_head && b->reward == nullptr) return fail(c, REPPO_ERR_INVALID, "batch.reward is required in JAX semantics");
   CK(launch_metrics_init(metrics, kCriticMetricMask, st));
   CK(cudaMemsetAsync(cg, 0, static_cast<size_t>(c->critic_count) * sizeof(float), st));
-  CK(launch_gather_concat(b->critic_obs, sh.critic_obs_dim, b->action, sh.action_dim, idx, 0, mb, c->x0, c->K0, st));
+  Twin tw = c->twin(c->x0);
+  CK(launch_gather_concat(b->critic_obs, sh.critic_obs_dim, b->action, sh.action_dim, idx, 0, mb, c->x0, c->K0, tw.p, tw.ld, st));
   RET(critic_trunk(c, cp, mb, true, st));
+  tw = c->twin(c->dlogits);
   CK(launch_critic_ce(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, b->target, b->truncated, idx, mb, inv, no_mask,
-                      c->dlogits, metrics, st));
+                      c->dlogits, metrics, tw.p, tw.ld, st));
+  tw = c->twin(c->dpred);
   CK(launch_critic_aux(c->pa.out, c->pred_out, sh.critic_hidden, c->sem.reward_head, c->sem.aux_mask_done, b->next_emb,
-                       b->reward, b->done, b->truncated, idx, mb, inv, no_mask, hp->aux_loss_mult, c->dpred, metrics, st));
-  RET(mlp_backward(c, c->head, cp, cg, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, cg + c->zero_dist_off,
+                       b->reward, b->done, b->truncated, idx, mb, inv, no_mask, hp->aux_loss_mult, c->dpred, metrics, tw.p,
+                       tw.ld, st));
+  RET(mlp_backward(c, c->head, cp, SLOT_CRITIC, cg, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, cg + c->zero_dist_off,
                    c->sem.bias_scale, st));
-  RET(mlp_backward(c, c->pred, cp, cg, c->xs, mb, c->pa, c->dpred, c->dxs, GEMM_ACCUM, nullptr, 0.f, st));
+  RET(mlp_backward(c, c->pred, cp, SLOT_CRITIC, cg, c->xs, mb, c->pa, c->dpred, c->dxs, GEMM_ACCUM, nullptr, 0.f, st));
+  tw = c->twin(c->dfeat);
   CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden, c->dfeat,
-                         nullptr, nullptr, st));
-  RET(mlp_backward(c, c->feature, cp, cg, c->x0, mb, c->fa, c->dfeat, nullptr, GEMM_STORE, nullptr, 0.f, st));
+                         nullptr, nullptr, tw.p, tw.ld, st));
+  RET(mlp_backward(c, c->feature, cp, SLOT_CRITIC, cg, c->x0, mb, c->fa, c->dfeat, nullptr, GEMM_STORE, nullptr, 0.f, st));
   return REPPO_OK;
 }
 
@@ -329,22 +448,27 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
   const ActorConsts ac = actor_consts(c, hp);
   CK(launch_metrics_init(metrics, kActorMetricMask, st));
   CK(cudaMemsetAsync(ag, 0, static_cast<size_t>(c->actor_count) * sizeof(float), st));
-  CK(launch_gather_concat(b->obs, sh.obs_dim, nullptr, 0, idx, 0, mb, c->xa0, sh.obs_dim, st));
-  RET(mlp_forward(c, c->actor, ap, c->xa0, mb, c->aa, st));
-  RET(mlp_forward(c, c->actor, s->actor_old, c->xa0, mb, c->oa, st));
-  CK(launch_gather_concat(b->critic_obs, Dc, nullptr, 0, idx, 0, mb, c->x0, c->K0, st));
+  Twin tw = c->twin(c->xa0);
+  CK(launch_gather_concat(b->obs, sh.obs_dim, nullptr, 0, idx, 0, mb, c->xa0, sh.obs_dim, tw.p, tw.ld, st));
+  RET(mlp_forward(c, c->actor, ap, SLOT_ACTOR, c->xa0, mb, c->aa, st));
+  RET(mlp_forward(c, c->actor, s->actor_old, SLOT_ACTOR_OLD, c->xa0, mb, c->oa, st));
+  const Twin tx0 = c->twin(c->x0);
+  CK(launch_gather_concat(b->critic_obs, Dc, nullptr, 0, idx, 0, mb, c->x0, c->K0, tx0.p, tx0.ld, st));
   CK(launch_actor_sample(c->aa.out, c->oa.out, eps_pi, eps_kl, mb, A, sh.kl_samples, ac, c->x0 + Dc, c->K0, c->logp, c->kl,
-                         c->gmu, c->gsig, st));
+                         c->gmu, c->gsig, tx0.p ? tx0.p + Dc : nullptr, tx0.ld, st));
   RET(critic_trunk(c, cp, mb, false, st));
+  tw = c->twin(c->dlogits);
   CK(launch_actor_q(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, c->kl, mb, inv, ac.kl_mode, ac.kl_bound, c->q,
-                    c->dlogits, st));
-  RET(mlp_backward(c, c->head, cp, nullptr, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, st));
+                    c->dlogits, tw.p, tw.ld, st));
+  RET(mlp_backward(c, c->head, cp, SLOT_CRITIC, nullptr, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, st));
+  tw = c->twin(c->dfeat);
   CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden, c->dfeat,
-                         nullptr, nullptr, st));
-  RET(mlp_backward(c, c->feature, cp, nullptr, c->x0, mb, c->fa, c->dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, st));
+                         nullptr, nullptr, tw.p, tw.ld, st));
+  RET(mlp_backward(c, c->feature, cp, SLOT_CRITIC, nullptr, c->x0, mb, c->fa, c->dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, st));
+  tw = c->twin(c->dout);
   CK(launch_actor_grad(c->aa.out, eps_pi, c->x0 + Dc, c->K0, c->dx0 + Dc, c->K0, c->logp, c->kl, c->q, c->gmu, c->gsig, ap,
-                       mb, A, inv, ac, c->dout, ag, metrics, st));
-  RET(mlp_backward(c, c->actor, ap, ag, c->xa0, mb, c->aa, c->dout, nullptr, GEMM_STORE, nullptr, 0.f, st));
+                       mb, A, inv, ac, c->dout, ag, metrics, tw.p, tw.ld, st));
+  RET(mlp_backward(c, c->actor, ap, SLOT_ACTOR, ag, c->xa0, mb, c->aa, c->dout, nullptr, GEMM_STORE, nullptr, 0.f, st));
   return REPPO_OK;
 }
 
@@ -364,20 +488,23 @@ int critic_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
                      const reppo_hyper* hp, float* metrics, cudaStream_t st) {
   RET(critic_grad_impl(c, s, b, idx, mb, hp, metrics, st));
   RET(allreduce_grads(c, s->critic.grads, c->critic_count, st));
-  return clip_adam_impl(c, &s->critic, c->critic_count, hp, metrics + M_CRITIC_GRAD_NORM, st);
+  RET(clip_adam_impl(c, &s->critic, c->critic_count, hp, metrics + M_CRITIC_GRAD_NORM, st));
+  return pack_shadows(c, SLOT_CRITIC, s->critic.params, st);
 }
 
 int actor_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb, const float* eps_pi,
                     const float* eps_kl, const reppo_hyper* hp, float* metrics, cudaStream_t st) {
   RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, st));
   RET(allreduce_grads(c, s->actor.grads, c->actor_count, st));
-  return clip_adam_impl(c, &s->actor, c->actor_count, hp, metrics + M_ACTOR_GRAD_NORM, st);
+  RET(clip_adam_impl(c, &s->actor, c->actor_count, hp, metrics + M_ACTOR_GRAD_NORM, st));
+  return pack_shadows(c, SLOT_ACTOR, s->actor.params, st);
 }
 
 int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const reppo_plan* p, const reppo_hyper* hp,
               cudaStream_t st) {
   const int A = c->shape.action_dim, mb = p->minibatch, ks = c->shape.kl_samples;
   const int64_t per_epoch = static_cast<int64_t>(p->num_mini_batches) * mb;
+  RET(pack_all(c, s, st));
   for (int e = 0; e < p->num_epochs; ++e) {
     for (int j = 0; j < p->num_mini_batches; ++j) {
       const int64_t slot = p->noise_per_minibatch ? static_cast<int64_t>(e) * p->num_mini_batches + j : e;
@@ -400,7 +527,7 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
 // ================================================================================================
 extern "C" {
 
-int reppo_version(void) { return 1; }
+int reppo_version(void) { return 2; }
 
 const char* reppo_last_error(const reppo_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
@@ -413,6 +540,8 @@ int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
   if (s.enc_layers < 2 || s.head_layers < 2 || s.pred_layers < 2 || s.actor_layers < 2)
     return fail(nullptr, REPPO_ERR_UNSUPPORTED,
                 "layers == 1 has divergent JAX / Torch semantics (jax_models.py:81-89 vs torch_models.py:98-107)");
+  if (s.enc_layers + s.head_layers + s.pred_layers > kMaxPack || s.actor_layers > kMaxPack)
+    return fail(nullptr, REPPO_ERR_UNSUPPORTED, "more than 16 Linear layers in one network");
   if (s.num_bins > 256) return fail(nullptr, REPPO_ERR_UNSUPPORTED, "num_bins > 256");
   if (s.critic_hidden > 2048 || s.actor_hidden > 2048) return fail(nullptr, REPPO_ERR_UNSUPPORTED, "hidden_dim > 2048");
   if (s.semantics != REPPO_SEM_JAX && s.semantics != REPPO_SEM_TORCH) return fail(nullptr, REPPO_ERR_INVALID, "semantics");
@@ -422,6 +551,7 @@ int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
 
   reppo_ctx* c = new reppo_ctx();
   c->shape = s;
+  c->tc = (s.gemm_mode == REPPO_GEMM_BF16);
   if (s.semantics == REPPO_SEM_JAX) {
     // flax RMSNorm/LayerNorm eps 1e-6; logits + 40.0 * zero_dist (jax_models.py:298); clip 1-1e-4
     // (jaxrl/reppo.py:558); min_std 0.1 because the constructor ignores cfg (jax_models.py:336);
@@ -435,21 +565,22 @@ int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
   if (s.critic_norm == REPPO_NORM_LAYER || s.actor_norm == REPPO_NORM_LAYER) c->sem.norm_eps = 1e-6f;  // reppo_mj_playground.py:65-72
   c->K0 = s.critic_obs_dim + s.action_dim;
   c->pred_out = s.critic_hidden + (c->sem.reward_head ? 1 : 0);
+  c->maxdim = std::max(std::max(s.critic_hidden, s.actor_hidden),
+                       std::max(std::max(s.num_bins, c->pred_out), std::max(std::max(c->K0, s.obs_dim), 2 * s.action_dim)));
 
-  int64_t off = 0;
+  int64_t off = 0, sb = 0, st = 0;
   c->zero_dist_off = 0;
   c->critic_tensors.push_back({"zero_dist", 0, s.num_bins, 0});
   off += s.num_bins;
-  add_fcnn(c->critic_tensors, off, c->feature, "feature_module", c->K0, s.critic_hidden, s.critic_hidden, s.enc_layers, false, s.critic_norm);
-  add_fcnn(c->critic_tensors, off, c->head, "critic_module", s.critic_hidden, s.critic_hidden, s.num_bins, s.head_layers, true, s.critic_norm);
-  add_fcnn(c->critic_tensors, off, c->pred, "pred_module", s.critic_hidden, s.critic_hidden, c->pred_out, s.pred_layers, true, s.critic_norm);
-  c->critic_count = off;
-  off = 0;
+  add_fcnn(c->critic_tensors, off, sb, st, c->feature, "feature_module", c->K0, s.critic_hidden, s.critic_hidden, s.enc_layers, false, s.critic_norm);
+  add_fcnn(c->critic_tensors, off, sb, st, c->head, "critic_module", s.critic_hidden, s.critic_hidden, s.num_bins, s.head_layers, true, s.critic_norm);
+  add_fcnn(c->critic_tensors, off, sb, st, c->pred, "pred_module", s.critic_hidden, s.critic_hidden, c->pred_out, s.pred_layers, true, s.critic_norm);
+  c->critic_count = off; c->shadow_b_elems[0] = sb; c->shadow_t_elems[0] = st;
   c->actor_tensors.push_back({"log_temp", 0, 0, 0});
   c->actor_tensors.push_back({"log_lagrange", 1, 0, 0});
-  off = 2;
-  add_fcnn(c->actor_tensors, off, c->actor, "model", s.obs_dim, s.actor_hidden, 2 * s.action_dim, s.actor_layers, false, s.actor_norm);
-  c->actor_count = off;
+  off = 2; sb = 0; st = 0;
+  add_fcnn(c->actor_tensors, off, sb, st, c->actor, "model", s.obs_dim, s.actor_hidden, 2 * s.action_dim, s.actor_layers, false, s.actor_norm);
+  c->actor_count = off; c->shadow_b_elems[1] = sb; c->shadow_t_elems[1] = st;
 
   const double bw = (static_cast<double>(s.vmax) - static_cast<double>(s.vmin)) / (s.num_bins - 1);
   const double sigma = bw * 0.75;
@@ -515,6 +646,10 @@ int reppo_set_workspace(reppo_ctx* c, void* workspace, size_t bytes) {
   c->hl.edges = c->edges_d;
   c->hl.support = c->support_d;
   c->graph_valid = false;
+  if (c->tc) {
+    // bf16 twins / shadows are read through TMA with their padded leading dimension: clear the padding once
+    if (cudaMemset(workspace, 0, c->ws_need) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "clearing the workspace failed");
+  }
   return reppo_set_bins(c, nullptr, nullptr);
 }
 
@@ -535,7 +670,9 @@ int reppo_critic_forward(reppo_ctx* c, const float* cp, const float* critic_obs,
   RET(check_rows(c, rows));
   c->launches = 0;
   const reppo_shape& sh = c->shape;
-  CK(launch_gather_concat(critic_obs, sh.critic_obs_dim, action, sh.action_dim, nullptr, 0, rows, c->x0, c->K0, st));
+  RET(pack_shadows(c, SLOT_CRITIC, cp, st));
+  const Twin tw = c->twin(c->x0);
+  CK(launch_gather_concat(critic_obs, sh.critic_obs_dim, action, sh.action_dim, nullptr, 0, rows, c->x0, c->K0, tw.p, tw.ld, st));
   RET(critic_trunk(c, cp, rows, pred != nullptr, st));
   if (value || logits) CK(launch_value_head(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, rows, value, logits, st));
   if (pred) CK(cudaMemcpyAsync(pred, c->pa.out, sizeof(float) * rows * c->pred_out, cudaMemcpyDeviceToDevice, st));
@@ -548,7 +685,10 @@ int reppo_actor_forward(reppo_ctx* c, const float* ap, const float* obs, int32_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   RET(check_rows(c, rows));
   c->launches = 0;
-  RET(mlp_forward(c, c->actor, ap, obs, rows, c->aa, st));
+  RET(pack_shadows(c, SLOT_ACTOR, ap, st));
+  const Twin tw = c->twin(c->xa0);
+  CK(launch_gather_concat(obs, c->shape.obs_dim, nullptr, 0, nullptr, 0, rows, c->xa0, c->shape.obs_dim, tw.p, tw.ld, st));
+  RET(mlp_forward(c, c->actor, ap, SLOT_ACTOR, c->xa0, rows, c->aa, st));
   const float ms = c->sem.force_min_std >= 0.f ? c->sem.force_min_std : min_std;
   CK(launch_mean_std(c->aa.out, rows, c->shape.action_dim, ms, mean, std, st));
   return REPPO_OK;
@@ -557,33 +697,60 @@ int reppo_actor_forward(reppo_ctx* c, const float* ap, const float* obs, int32_t
 int reppo_linear(reppo_ctx* c, int32_t op, int32_t rows, int32_t in_f, int32_t out_f, const float* a, const float* b,
                  float* out, const float* bias, reppo_stream stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!a || !b || !out || rows <= 0 || in_f <= 0 || out_f <= 0) return fail(c, REPPO_ERR_INVALID, "reppo_linear: bad argument");
+  if (!a || !b || !out || rows <= 0 || in_f <= 0 || out_f <= 0 || op < 0 || op > 2)
+    return fail(c, REPPO_ERR_INVALID, "reppo_linear: bad argument");
   c->launches = 0;
-  if (op == 0) return gemm(c, false, true, rows, out_f, in_f, a, in_f, b, in_f, out, out_f, bias, GEMM_STORE, 1, st);
-  if (op == 1) return gemm(c, false, false, rows, in_f, out_f, a, out_f, b, in_f, out, in_f, nullptr, GEMM_STORE, 1, st);
-  if (op == 2) return gemm(c, true, false, out_f, in_f, rows, a, out_f, b, in_f, out, in_f, nullptr, GEMM_ATOMIC,
-                           wgrad_split(out_f, in_f, rows), st);
-  return fail(c, REPPO_ERR_INVALID, "reppo_linear: unknown op");
+  if (!c->tc) {
+    if (op == 0) CK(launch_gemm_f32(false, true, rows, out_f, in_f, a, in_f, b, in_f, out, out_f, bias, GEMM_STORE, 1, st));
+    else if (op == 1) CK(launch_gemm_f32(false, false, rows, in_f, out_f, a, out_f, b, in_f, out, in_f, nullptr, GEMM_STORE, 1, st));
+    else CK(launch_gemm_f32(true, false, out_f, in_f, rows, a, out_f, b, in_f, out, in_f, nullptr, GEMM_ATOMIC,
+                            wgrad_split(out_f, in_f, rows, false), st));
+    return REPPO_OK;
+  }
+  RET(check_rows(c, rows));
+  if (in_f > c->maxdim || out_f > c->maxdim) return fail(c, REPPO_ERR_INVALID, "reppo_linear (bf16): dimension exceeds the context's largest layer");
+  const int ldi = round8(in_f), ldo = round8(out_f);
+  if (op == 0) {
+    CK(launch_cast_bf16(a, rows, in_f, in_f, c->lin_a, ldi, st));
+    CK(launch_cast_bf16(b, out_f, in_f, in_f, c->lin_b, ldi, st));
+    CK(launch_gemm_bf16_tc(false, rows, out_f, in_f, c->lin_a, ldi, c->lin_b, ldi, out, out_f, bias, GEMM_STORE, 1, st));
+  } else if (op == 1) {
+    CK(launch_cast_bf16(a, rows, out_f, out_f, c->lin_a, ldo, st));
+    PackTable t{};
+    t.n = 1; t.e[0] = PackEntry{b, nullptr, c->lin_b, out_f, in_f, ldi, ldo};
+    CK(launch_pack_weights(t, st));
+    CK(launch_gemm_bf16_tc(false, rows, in_f, out_f, c->lin_a, ldo, c->lin_b, ldo, out, in_f, nullptr, GEMM_STORE, 1, st));
+  } else {
+    CK(launch_cast_bf16(a, rows, out_f, out_f, c->lin_a, ldo, st));
+    CK(launch_cast_bf16(b, rows, in_f, in_f, c->lin_c, ldi, st));
+    CK(launch_gemm_bf16_tc(true, out_f, in_f, rows, c->lin_a, ldo, c->lin_c, ldi, out, in_f, nullptr, GEMM_ATOMIC,
+                           wgrad_split(out_f, in_f, rows, true), st));
+  }
+  return REPPO_OK;
 }
 
 int reppo_critic_grad(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int32_t mb,
                       const reppo_hyper* hp, float* metrics, reppo_stream stream) {
   c->launches = 0;
+  RET(pack_all(c, s, static_cast<cudaStream_t>(stream)));
   return critic_grad_impl(c, s, b, idx, mb, hp, metrics, static_cast<cudaStream_t>(stream));
 }
 int reppo_actor_grad(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int32_t mb,
                      const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, reppo_stream stream) {
   c->launches = 0;
+  RET(pack_all(c, s, static_cast<cudaStream_t>(stream)));
   return actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, static_cast<cudaStream_t>(stream));
 }
 int reppo_critic_step(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int32_t mb,
                       const reppo_hyper* hp, float* metrics, reppo_stream stream) {
   c->launches = 0;
+  RET(pack_all(c, s, static_cast<cudaStream_t>(stream)));
   return critic_step_impl(c, s, b, idx, mb, hp, metrics, static_cast<cudaStream_t>(stream));
 }
 int reppo_actor_step(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int32_t mb,
                      const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, reppo_stream stream) {
   c->launches = 0;
+  RET(pack_all(c, s, static_cast<cudaStream_t>(stream)));
   return actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, static_cast<cudaStream_t>(stream));
 }
 int reppo_clip_adam(reppo_ctx* c, const reppo_net_state* net, int64_t n, const reppo_hyper* hp, float* gn, reppo_stream stream) {

@@ -1,0 +1,322 @@
+// tcgen05 / TMEM / TMA GEMM for the Linear layers of the REPPO MLPs (REPPO_GEMM_BF16 mode).
+//
+//   D[M,N] (fp32) = A · B  with bf16 operands staged in shared memory by TMA (128-byte swizzle),
+//   fp32 accumulators in tensor memory, issued by one elected thread with tcgen05.mma
+//   (cta_group::1, UMMA 128 x BLOCK_N x 16), read back with tcgen05.ld for the epilogue.
+//
+// Three operand arrangements cover forward, dgrad and wgrad of y = x W^T + b
+// (src/networks/jax_models.py:35-49, torch_models.py:71-79):
+//   KK : A[M,K] and B[N,K] both K-major (row-major, reduction dim contiguous)
+//          forward  y  = x  · W^T       A = x  [rows,in],  B = W   [out,in]
+//          dgrad    dx = dy · (W^T)^T   A = dy [rows,out], B = W^T [in,out]   (transposed bf16 shadow)
+//   MM : A and B both MN-major (reduction dim = rows is the OUTER dim of both operands)
+//          wgrad    dW[out,in] = dy^T · x     A = dy [rows,out],  B = x [rows,in]
+// Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer,
+// warps 2..5 = epilogue (each owns the 32 TMEM lanes  32*(warp%4) .. +32).
+// Pipeline: NUM_STAGES-deep smem ring with full/empty mbarriers (TMA -> MMA), one
+// tmem_full mbarrier (MMA -> epilogue).  One output tile per CTA; split-K over gridDim.z for
+// wgrad (fp32 atomics into the zeroed gradient arena).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace reppo {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
+constexpr int TC_UMMA_K = 16;
+constexpr int TC_THREADS = 192;
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+REPPO_DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+REPPO_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+REPPO_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+REPPO_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+REPPO_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+REPPO_DEVINL void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+REPPO_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+REPPO_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+REPPO_DEVINL void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+REPPO_DEVINL void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+REPPO_DEVINL void tc_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, sm_100 version bit
+REPPO_DEVINL uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;   // version = 1 (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;   // layout type SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(TC_BLOCK_M >> 4) << 24);
+}
+
+template <int BLOCK_N, int STAGES>
+struct TcSmem {
+  static constexpr int kABytes = TC_BLOCK_M * TC_BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * TC_BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+// MODE: GEMM_STORE / GEMM_ACCUM / GEMM_ATOMIC.  MN_MAJOR: false = KK arrangement, true = MM arrangement.
+template <int BLOCK_N, int STAGES, bool MN_MAJOR>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    float* __restrict__ C, int ldc, const float* __restrict__ bias, int M, int N, int K, int k_blocks_per_split,
+                    int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  using S = TcSmem<BLOCK_N, STAGES>;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+  const int total_k_blocks = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+  const int kb_begin = blockIdx.z * k_blocks_per_split;
+  const int kb_end = min(total_k_blocks, kb_begin + k_blocks_per_split);
+  const int num_kb = kb_end - kb_begin;
+
+  if (warp == 0) {
+    if (lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
+    // TMEM: BLOCK_N fp32 columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(BLOCK_N));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  } else if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* sa = smem + s * S::kStageBytes;
+      uint8_t* sb = sa + S::kABytes;
+      mbar_expect_tx(&full_bar[s], S::kStageBytes);
+      const int k0 = (kb_begin + i) * TC_BLOCK_K;
+      if (!MN_MAJOR) {
+        // A tile [128 rows][64 k], B tile [BLOCK_N rows][64 k]; coordinates {k, row}
+        tma_load_2d(&tmap_a, &full_bar[s], sa, k0, m0);
+        tma_load_2d(&tmap_b, &full_bar[s], sb, k0, n0);
+      } else {
+        // atoms of [64 k-rows][64 mn]: coordinates {mn, k-row}
+#pragma unroll
+        for (int a = 0; a < TC_BLOCK_M / 64; ++a) tma_load_2d(&tmap_a, &full_bar[s], sa + a * (TC_BLOCK_K * 128), m0 + a * 64, k0);
+#pragma unroll
+        for (int b = 0; b < BLOCK_N / 64; ++b) tma_load_2d(&tmap_b, &full_bar[s], sb + b * (TC_BLOCK_K * 128), n0 + b * 64, k0);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(BLOCK_N, MN_MAJOR, MN_MAJOR);
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+      const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+      for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+        uint64_t da, db;
+        if (!MN_MAJOR) {
+          // K-major SW128: 8-row groups 1024 B apart; advance 32 B per UMMA_K inside the swizzle row
+          da = make_smem_desc(sa + k * (TC_UMMA_K * 2), 16, 1024);
+          db = make_smem_desc(sb + k * (TC_UMMA_K * 2), 16, 1024);
+        } else {
+          // MN-major SW128: LBO = stride between 64-wide MN atoms, SBO = stride between 8-row K groups;
+          // advance 16 k-rows = 2048 B per UMMA_K
+          da = make_smem_desc(sa + k * (TC_UMMA_K * 128), TC_BLOCK_K * 128, 1024);
+          db = make_smem_desc(sb + k * (TC_UMMA_K * 128), TC_BLOCK_K * 128, 1024);
+        }
+        tc_mma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+      }
+      tc_commit(&empty_bar[s]);          // frees the smem slot when these MMAs retire
+    }
+    tc_commit(tmem_full_bar);            // accumulator complete
+  } else if (warp >= 2) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int lane_base = (warp & 3) * 32;
+    const int row = m0 + lane_base + lane;
+    const bool add_bias = (bias != nullptr) && (blockIdx.z == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      float v[32];
+      if (num_kb > 0) {
+        tc_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + c0, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (row < M) {
+        float* crow = C + static_cast<size_t>(row) * ldc;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + c0 + j;
+          if (col < N) {
+            float x = v[j];
+            if (add_bias) x += bias[col];
+            if (mode == GEMM_STORE) crow[col] = x;
+            else if (mode == GEMM_ACCUM) crow[col] += x;
+            else atomicAdd(crow + col, x);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BLOCK_N));
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major bf16 matrix [rows, cols] with leading dimension ld (elements); box = {box_cols, box_rows}
+static bool encode_2d(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BLOCK_N, int STAGES, bool MN_MAJOR>
+static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int ldc, const float* bias, int M, int N,
+                             int K, int split_k, int mode, cudaStream_t st) {
+  using S = TcSmem<BLOCK_N, STAGES>;
+  static bool configured = false;
+  auto kern = gemm_bf16_tc_kernel<BLOCK_N, STAGES, MN_MAJOR>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int total_kb = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+  if (split_k < 1) split_k = 1;
+  if (split_k > total_kb) split_k = total_kb;
+  const int per = (total_kb + split_k - 1) / split_k;
+  split_k = (total_kb + per - 1) / per;
+  if (split_k > 1) mode = GEMM_ATOMIC;
+  dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + TC_BLOCK_M - 1) / TC_BLOCK_M, split_k);
+  kern<<<grid, TC_THREADS, S::kTotal, st>>>(ta, tb, C, ldc, bias, M, N, K, per, mode);
+  return cudaGetLastError();
+}
+
+// A, B: bf16 device pointers.
+//  mn_major == false: A [M, K] ld lda, B [N, K] ld ldb               (forward / dgrad)
+//  mn_major == true : A [K, M] ld lda, B [K, N] ld ldb  (K = rows)   (wgrad)
+// Leading dimensions must be multiples of 8 elements (16 B) and the bases 16-byte aligned.
+cudaError_t launch_gemm_bf16_tc(bool mn_major, int M, int N, int K, const void* A, int lda, const void* B, int ldb, float* C,
+                                int ldc, const float* bias, int mode, int split_k, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
+  if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+    return cudaErrorInvalidValue;
+  CUtensorMap ta, tb;
+  const bool wide = N > 64;
+  const int block_n = wide ? 128 : 64;
+  bool ok;
+  if (!mn_major) {
+    ok = encode_2d(&ta, A, M, K, lda, TC_BLOCK_K, TC_BLOCK_M) && encode_2d(&tb, B, N, K, ldb, TC_BLOCK_K, block_n);
+  } else {
+    ok = encode_2d(&ta, A, K, M, lda, 64, TC_BLOCK_K) && encode_2d(&tb, B, K, N, ldb, 64, TC_BLOCK_K);
+  }
+  if (!ok) return cudaErrorInvalidValue;
+  if (!mn_major) {
+    return wide ? launch_tc<128, 4, false>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, st)
+                : launch_tc<64, 4, false>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, st);
+  }
+  return wide ? launch_tc<128, 4, true>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, st)
+              : launch_tc<64, 4, true>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, st);
+}
+
+}  // namespace reppo

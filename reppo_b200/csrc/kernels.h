@@ -46,31 +46,43 @@ cudaError_t launch_td_lambda(const float* sr, const float* val, const float* don
 
 cudaError_t launch_gemm_f32(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                             float* C, int ldc, const float* bias, int mode, int split_k, cudaStream_t st);
+// tcgen05 GEMM on bf16 operands (gemm_bf16_tc.cu); see the file header for the operand arrangements
+cudaError_t launch_gemm_bf16_tc(bool mn_major, int M, int N, int K, const void* A, int lda, const void* B, int ldb, float* C,
+                                int ldc, const float* bias, int mode, int split_k, cudaStream_t st);
+// fp32 -> bf16 copies: plain (row-padded) and, for weights, the [out,in] matrix plus its transpose
+struct PackEntry { const float* w; void* wb; void* wtb; int out, in, ld_b, ld_t; };
+constexpr int kMaxPack = 16;
+struct PackTable { int n; PackEntry e[kMaxPack]; };
+cudaError_t launch_pack_weights(const PackTable& t, cudaStream_t st);
+cudaError_t launch_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, cudaStream_t st);
 cudaError_t launch_colsum(const float* X, int M, int N, int ld, float* out, float* out2, float scale2, cudaStream_t st);
 
 cudaError_t launch_gather_concat(const float* a, int da, const float* b, int db, const int* idx, int b_is_local,
-                                 int rows, float* out, int out_ld, cudaStream_t st);
+                                 int rows, float* out, int out_ld, void* out_h, int out_ldh, cudaStream_t st);
 cudaError_t launch_norm_act_fwd(int norm, const float* z, const float* gamma, const float* beta, int rows, int H,
-                                float eps, float* x, float* rstd, float* mean, cudaStream_t st);
+                                float eps, float* x, float* rstd, float* mean, void* x_h, int ldh, cudaStream_t st);
 cudaError_t launch_norm_act_bwd(int norm, const float* dx, const float* z, const float* gamma, const float* beta,
                                 const float* rstd, const float* mean, int rows, int H, float* dz, float* dgamma,
-                                float* dbeta, cudaStream_t st);
+                                float* dbeta, void* dz_h, int ldh, cudaStream_t st);
 
 cudaError_t launch_critic_ce(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, const float* target,
                              const float* truncated, const int* idx, int rows, float inv_rows, int no_mask, float* dlogits,
-                             float* metrics, cudaStream_t st);
+                             float* metrics, void* dl_h, int ldh, cudaStream_t st);
 cudaError_t launch_critic_aux(const float* pred, int P, int H, int reward_head, int mask_done, const float* next_emb,
                               const float* reward, const float* done, const float* truncated, const int* idx, int rows,
-                              float inv_rows, int no_mask, float aux_mult, float* dpred, float* metrics, cudaStream_t st);
+                              float inv_rows, int no_mask, float aux_mult, float* dpred, float* metrics, void* dp_h, int ldh,
+                              cudaStream_t st);
 cudaError_t launch_actor_sample(const float* out, const float* out_old, const float* eps_pi, const float* eps_kl, int rows,
                                 int A, int kl_samples, const ActorConsts& ac, float* act_out, int act_ld, float* logp,
-                                float* kl, float* gmu, float* gsig, cudaStream_t st);
+                                float* kl, float* gmu, float* gsig, void* act_h, int act_ldh, cudaStream_t st);
 cudaError_t launch_actor_q(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, const float* kl, int rows,
-                           float inv_rows, int kl_mode, float kl_bound, float* q_out, float* dlogits, cudaStream_t st);
+                           float inv_rows, int kl_mode, float kl_bound, float* q_out, float* dlogits, void* dl_h, int ldh,
+                           cudaStream_t st);
 cudaError_t launch_actor_grad(const float* out, const float* eps_pi, const float* act, int act_ld, const float* dact,
                               int dact_ld, const float* logp, const float* kl, const float* q, const float* gmu,
                               const float* gsig, const float* actor_params, int rows, int A, float inv_rows,
-                              const ActorConsts& ac, float* dout, float* actor_grads, float* metrics, cudaStream_t st);
+                              const ActorConsts& ac, float* dout, float* actor_grads, float* metrics, void* dout_h, int ldh,
+                              cudaStream_t st);
 cudaError_t launch_value_head(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, int rows,
                               float* value, float* logits, cudaStream_t st);
 cudaError_t launch_mean_std(const float* out, int rows, int A, float min_std, float* mean, float* std, cudaStream_t st);

@@ -11,6 +11,8 @@
 //                      KL-clipped pathwise loss with temperature / Lagrange terms, and their
 //                      hand-derived gradients (reppo.py:526-622; torchrl/reppo.py:291-338;
 //                      distrax Tanh fldj = 2 (log 2 - x - softplus(-2x)), torch_models.py:52-55).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -75,7 +77,8 @@ REPPO_DEVINL void block_metric_add(float (&vals)[NM], float* sm /* [8][NM] */, f
 __global__ void __launch_bounds__(256)
 critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __restrict__ zero_dist, HLConsts hl,
                  const float* __restrict__ target, const float* __restrict__ truncated, const int* __restrict__ idx,
-                 int rows, float inv_rows, int no_mask, float* __restrict__ dlogits, float* __restrict__ metrics) {
+                 int rows, float inv_rows, int no_mask, float* __restrict__ dlogits, float* __restrict__ metrics,
+                 __nv_bfloat16* __restrict__ dl_h, int ldh) {
   __shared__ float sm[8 * 5];
   __shared__ float smax[8], smin[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -111,7 +114,11 @@ critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __rest
 #pragma unroll
     for (int j = 0; j < kMaxBinsPerLane; ++j) {
       const int c = lane + 32 * j;
-      if (c < B) drow[c] = coef * (sum_tp * sx.p[j] - tp[j]);
+      if (c < B) {
+        const float o = coef * (sum_tp * sx.p[j] - tp[j]);
+        drow[c] = o;
+        if (dl_h != nullptr) dl_h[static_cast<size_t>(row) * ldh + c] = __float2bfloat16_rn(o);
+      }
     }
     vals[0] = mask * ce * inv_rows;                         // REPPO_M_CRITIC_LOSS (CE part)
     vals[1] = ce * inv_rows;                                // REPPO_M_CE_MEAN
@@ -135,7 +142,8 @@ __global__ void __launch_bounds__(256)
 critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head, int mask_done,
                   const float* __restrict__ next_emb, const float* __restrict__ reward, const float* __restrict__ done,
                   const float* __restrict__ truncated, const int* __restrict__ idx, int rows, float inv_rows, int no_mask,
-                  float aux_mult, float* __restrict__ dpred, float* __restrict__ metrics) {
+                  float aux_mult, float* __restrict__ dpred, float* __restrict__ metrics, __nv_bfloat16* __restrict__ dp_h,
+                  int ldh) {
   __shared__ float sm[8 * 3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x * 8 + warp;
@@ -154,6 +162,7 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
       const float d = pr[off + c] - ne[c];
       sq += d * d;
       dr[off + c] = g * d;
+      if (dp_h != nullptr) dp_h[static_cast<size_t>(row) * ldh + off + c] = __float2bfloat16_rn(g * d);
     }
     float r = 0.f;
     if (reward_head) {
@@ -162,6 +171,7 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
         const float d = pr[0] - r;
         sq += d * d;
         dr[0] = g * d;
+        if (dp_h != nullptr) dp_h[static_cast<size_t>(row) * ldh] = __float2bfloat16_rn(g * d);
       }
     }
     sq = warp_sum(sq);
@@ -183,7 +193,7 @@ __global__ void __launch_bounds__(128)
 actor_sample_kernel(const float* __restrict__ out, const float* __restrict__ out_old, const float* __restrict__ eps_pi,
                     const float* __restrict__ eps_kl, int rows, int A, int kl_samples, ActorConsts ac,
                     float* __restrict__ act_out, int act_ld, float* __restrict__ logp_out, float* __restrict__ kl_out,
-                    float* __restrict__ gmu_kl, float* __restrict__ gsig_kl) {
+                    float* __restrict__ gmu_kl, float* __restrict__ gsig_kl, __nv_bfloat16* __restrict__ act_h, int act_ldh) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   const float* o = out + static_cast<size_t>(row) * 2 * A;
@@ -195,6 +205,7 @@ actor_sample_kernel(const float* __restrict__ out, const float* __restrict__ out
     const float x = mu + sig * e;
     const float a = tanhf(x);
     act_out[static_cast<size_t>(row) * act_ld + k] = a;
+    if (act_h != nullptr) act_h[static_cast<size_t>(row) * act_ldh + k] = __float2bfloat16_rn(a);
     if (ac.clip_policy_sample) {
       // torchrl/reppo.py:301: log_prob(actions.clip(+-c)) -> base.log_prob(atanh(.)) - fldj(atanh(.))
       const float xc = atanhf(fminf(fmaxf(a, -ac.action_clip), ac.action_clip));
@@ -237,7 +248,7 @@ actor_sample_kernel(const float* __restrict__ out, const float* __restrict__ out
 __global__ void __launch_bounds__(256)
 actor_q_kernel(const float* __restrict__ head_out, int ld, const float* __restrict__ zero_dist, HLConsts hl,
                const float* __restrict__ kl, int rows, float inv_rows, int kl_mode, float kl_bound,
-               float* __restrict__ q_out, float* __restrict__ dlogits) {
+               float* __restrict__ q_out, float* __restrict__ dlogits, __nv_bfloat16* __restrict__ dl_h, int ldh) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -250,7 +261,11 @@ actor_q_kernel(const float* __restrict__ head_out, int ld, const float* __restri
 #pragma unroll
   for (int j = 0; j < kMaxBinsPerLane; ++j) {
     const int c = lane + 32 * j;
-    if (c < B) drow[c] = coef * sx.p[j] * (hl.support[c] - sx.value);
+    if (c < B) {
+      const float o = coef * sx.p[j] * (hl.support[c] - sx.value);
+      drow[c] = o;
+      if (dl_h != nullptr) dl_h[static_cast<size_t>(row) * ldh + c] = __float2bfloat16_rn(o);
+    }
   }
   if (lane == 0) q_out[row] = sx.value;
 }
@@ -261,7 +276,8 @@ actor_grad_kernel(const float* __restrict__ out, const float* __restrict__ eps_p
                   const float* __restrict__ dact, int dact_ld, const float* __restrict__ logp_in,
                   const float* __restrict__ kl_in, const float* __restrict__ q_in, const float* __restrict__ gmu_kl,
                   const float* __restrict__ gsig_kl, const float* __restrict__ actor_params, int rows, int A, float inv_rows,
-                  ActorConsts ac, float* __restrict__ dout, float* __restrict__ actor_grads, float* __restrict__ metrics) {
+                  ActorConsts ac, float* __restrict__ dout, float* __restrict__ actor_grads, float* __restrict__ metrics,
+                  __nv_bfloat16* __restrict__ dout_h, int ldh) {
   __shared__ float red[32];
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   const float alpha = expf(actor_params[0]), beta = expf(actor_params[1]);
@@ -297,6 +313,10 @@ actor_grad_kernel(const float* __restrict__ out, const float* __restrict__ eps_p
       const float dsig = da * e + g_logp * dlp_sig + g_lpnew * gsig_kl[static_cast<size_t>(row) * A + k];
       d[k] = dmu;
       d[A + k] = dsig * ex;
+      if (dout_h != nullptr) {
+        dout_h[static_cast<size_t>(row) * ldh + k] = __float2bfloat16_rn(dmu);
+        dout_h[static_cast<size_t>(row) * ldh + A + k] = __float2bfloat16_rn(dsig * ex);
+      }
       abs_a += fabsf(a);
     }
     v_path = w_path * (alpha * logp - q) + w_kl * beta * ac.reduce_kl * kl;
@@ -335,43 +355,49 @@ actor_grad_kernel(const float* __restrict__ out, const float* __restrict__ eps_p
 // ---- launchers -----------------------------------------------------------------------------------
 cudaError_t launch_critic_ce(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, const float* target,
                              const float* truncated, const int* idx, int rows, float inv_rows, int no_mask, float* dlogits,
-                             float* metrics, cudaStream_t st) {
+                             float* metrics, void* dl_h, int ldh, cudaStream_t st) {
   if (hl.num_bins > 32 * kMaxBinsPerLane) return cudaErrorInvalidValue;
   critic_ce_kernel<<<(rows + 7) / 8, 256, 0, st>>>(head_out, ld, zero_dist, hl, target, truncated, idx, rows, inv_rows,
-                                                     no_mask, dlogits, metrics);
+                                                     no_mask, dlogits, metrics, static_cast<__nv_bfloat16*>(dl_h), ldh);
   return cudaGetLastError();
 }
 
 cudaError_t launch_critic_aux(const float* pred, int P, int H, int reward_head, int mask_done, const float* next_emb,
                               const float* reward, const float* done, const float* truncated, const int* idx, int rows,
-                              float inv_rows, int no_mask, float aux_mult, float* dpred, float* metrics, cudaStream_t st) {
+                              float inv_rows, int no_mask, float aux_mult, float* dpred, float* metrics, void* dp_h, int ldh,
+                              cudaStream_t st) {
   critic_aux_kernel<<<(rows + 7) / 8, 256, 0, st>>>(pred, P, H, reward_head, mask_done, next_emb, reward, done, truncated,
-                                                      idx, rows, inv_rows, no_mask, aux_mult, dpred, metrics);
+                                                      idx, rows, inv_rows, no_mask, aux_mult, dpred, metrics,
+                                                      static_cast<__nv_bfloat16*>(dp_h), ldh);
   return cudaGetLastError();
 }
 
 cudaError_t launch_actor_sample(const float* out, const float* out_old, const float* eps_pi, const float* eps_kl, int rows,
                                 int A, int kl_samples, const ActorConsts& ac, float* act_out, int act_ld, float* logp,
-                                float* kl, float* gmu, float* gsig, cudaStream_t st) {
+                                float* kl, float* gmu, float* gsig, void* act_h, int act_ldh, cudaStream_t st) {
   actor_sample_kernel<<<(rows + 127) / 128, 128, 0, st>>>(out, out_old, eps_pi, eps_kl, rows, A, kl_samples, ac, act_out,
-                                                            act_ld, logp, kl, gmu, gsig);
+                                                            act_ld, logp, kl, gmu, gsig, static_cast<__nv_bfloat16*>(act_h),
+                                                            act_ldh);
   return cudaGetLastError();
 }
 
 cudaError_t launch_actor_q(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, const float* kl, int rows,
-                           float inv_rows, int kl_mode, float kl_bound, float* q_out, float* dlogits, cudaStream_t st) {
+                           float inv_rows, int kl_mode, float kl_bound, float* q_out, float* dlogits, void* dl_h, int ldh,
+                           cudaStream_t st) {
   if (hl.num_bins > 32 * kMaxBinsPerLane) return cudaErrorInvalidValue;
   actor_q_kernel<<<(rows + 7) / 8, 256, 0, st>>>(head_out, ld, zero_dist, hl, kl, rows, inv_rows, kl_mode, kl_bound, q_out,
-                                                   dlogits);
+                                                   dlogits, static_cast<__nv_bfloat16*>(dl_h), ldh);
   return cudaGetLastError();
 }
 
 cudaError_t launch_actor_grad(const float* out, const float* eps_pi, const float* act, int act_ld, const float* dact,
                               int dact_ld, const float* logp, const float* kl, const float* q, const float* gmu,
                               const float* gsig, const float* actor_params, int rows, int A, float inv_rows,
-                              const ActorConsts& ac, float* dout, float* actor_grads, float* metrics, cudaStream_t st) {
+                              const ActorConsts& ac, float* dout, float* actor_grads, float* metrics, void* dout_h, int ldh,
+                              cudaStream_t st) {
   actor_grad_kernel<<<(rows + 127) / 128, 128, 0, st>>>(out, eps_pi, act, act_ld, dact, dact_ld, logp, kl, q, gmu, gsig,
-                                                          actor_params, rows, A, inv_rows, ac, dout, actor_grads, metrics);
+                                                          actor_params, rows, A, inv_rows, ac, dout, actor_grads, metrics,
+                                                          static_cast<__nv_bfloat16*>(dout_h), ldh);
   return cudaGetLastError();
 }
 

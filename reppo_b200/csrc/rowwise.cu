@@ -4,6 +4,8 @@
 //              normed_activation_layer src/networks/torch_models.py:71-79 (nn.RMSNorm eps=finfo.eps),
 //              LayerNorm variant src/reppo_mj_playground.py:63-74 (flax "fast variance", eps 1e-6).
 // One warp owns one row; lanes stride the feature dimension (coalesced 128 B per access).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -12,7 +14,7 @@ namespace reppo {
 // out[r, :] = [ a[idx[r], 0:da] | b[idx2 ? r : idx[r], 0:db] ]   (idx may be NULL = identity)
 __global__ void gather_concat_kernel(const float* __restrict__ a, int da, const float* __restrict__ b, int db,
                                      const int* __restrict__ idx, int b_is_local, int rows, float* __restrict__ out,
-                                     int out_ld) {
+                                     int out_ld, __nv_bfloat16* __restrict__ out_h, int out_ldh) {
   const int w = da + db;
   const long long total = static_cast<long long>(rows) * w;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -23,17 +25,19 @@ __global__ void gather_concat_kernel(const float* __restrict__ a, int da, const 
     if (c < da) v = a[src * da + c];
     else v = b[(b_is_local ? static_cast<long long>(r) : src) * db + (c - da)];
     out[static_cast<long long>(r) * out_ld + c] = v;
+    if (out_h != nullptr) out_h[static_cast<long long>(r) * out_ldh + c] = __float2bfloat16_rn(v);
   }
 }
 
 cudaError_t launch_gather_concat(const float* a, int da, const float* b, int db, const int* idx, int b_is_local,
-                                 int rows, float* out, int out_ld, cudaStream_t st) {
+                                 int rows, float* out, int out_ld, void* out_h, int out_ldh, cudaStream_t st) {
   const long long total = static_cast<long long>(rows) * (da + db);
   if (total <= 0) return cudaSuccess;
   const int block = 256;
   const long long want = (total + block - 1) / block;
   const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
-  gather_concat_kernel<<<grid, block, 0, st>>>(a, da, b, db, idx, b_is_local, rows, out, out_ld);
+  gather_concat_kernel<<<grid, block, 0, st>>>(a, da, b, db, idx, b_is_local, rows, out, out_ld,
+                                               static_cast<__nv_bfloat16*>(out_h), out_ldh);
   return cudaGetLastError();
 }
 
@@ -45,7 +49,7 @@ template <int NORM>
 __global__ void __launch_bounds__(256)
 norm_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
                     int rows, int H, float eps, float* __restrict__ x, float* __restrict__ rstd_out,
-                    float* __restrict__ mean_out) {
+                    float* __restrict__ mean_out, __nv_bfloat16* __restrict__ x_h, int ldh) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -69,18 +73,21 @@ norm_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma
     float y = zr[c];
     if (NORM == NORM_RMS) y = y * rstd * gamma[c];
     else if (NORM == NORM_LAYER) y = (y - mean) * rstd * gamma[c] + beta[c];
-    xr[c] = swishf_(y);
+    const float o = swishf_(y);
+    xr[c] = o;
+    if (x_h != nullptr) x_h[static_cast<size_t>(row) * ldh + c] = __float2bfloat16_rn(o);
   }
 }
 
 cudaError_t launch_norm_act_fwd(int norm, const float* z, const float* gamma, const float* beta, int rows, int H,
-                                float eps, float* x, float* rstd, float* mean, cudaStream_t st) {
+                                float eps, float* x, float* rstd, float* mean, void* x_h, int ldh, cudaStream_t st) {
+  __nv_bfloat16* xh = static_cast<__nv_bfloat16*>(x_h);
   if (rows <= 0) return cudaSuccess;
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
-  if (norm == NORM_NONE) norm_act_fwd_kernel<NORM_NONE><<<grid, wpb * 32, 0, st>>>(z, gamma, beta, rows, H, eps, x, rstd, mean);
-  else if (norm == NORM_RMS) norm_act_fwd_kernel<NORM_RMS><<<grid, wpb * 32, 0, st>>>(z, gamma, beta, rows, H, eps, x, rstd, mean);
-  else norm_act_fwd_kernel<NORM_LAYER><<<grid, wpb * 32, 0, st>>>(z, gamma, beta, rows, H, eps, x, rstd, mean);
+  if (norm == NORM_NONE) norm_act_fwd_kernel<NORM_NONE><<<grid, wpb * 32, 0, st>>>(z, gamma, beta, rows, H, eps, x, rstd, mean, xh, ldh);
+  else if (norm == NORM_RMS) norm_act_fwd_kernel<NORM_RMS><<<grid, wpb * 32, 0, st>>>(z, gamma, beta, rows, H, eps, x, rstd, mean, xh, ldh);
+  else norm_act_fwd_kernel<NORM_LAYER><<<grid, wpb * 32, 0, st>>>(z, gamma, beta, rows, H, eps, x, rstd, mean, xh, ldh);
   return cudaGetLastError();
 }
 
@@ -100,7 +107,7 @@ __global__ void __launch_bounds__(256)
 norm_act_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ z, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ rstd_in,
                     const float* __restrict__ mean_in, int rows, int H, int rows_per_block, float* __restrict__ dz,
-                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dz_h, int ldh) {
   extern __shared__ float sm[];  // [2][H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int r0 = blockIdx.x * rows_per_block;
@@ -122,7 +129,11 @@ norm_act_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ z, c
       float* dzr = dz + static_cast<size_t>(row) * H;
       if (NORM == NORM_NONE) {
         if (cbase == 0)
-          for (int c = lane; c < H; c += 32) dzr[c] = dxr[c] * swish_grad_(zr[c]);
+          for (int c = lane; c < H; c += 32) {
+            const float o = dxr[c] * swish_grad_(zr[c]);
+            dzr[c] = o;
+            if (dz_h != nullptr) dz_h[static_cast<size_t>(row) * ldh + c] = __float2bfloat16_rn(o);
+          }
         continue;
       }
       const float rstd = rstd_in[row];
@@ -147,7 +158,9 @@ norm_act_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ z, c
           const float y = (NORM == NORM_LAYER) ? zh * gamma[c] + beta[c] : zh * gamma[c];
           const float dy = dxr[c] * swish_grad_(y);
           const float dzh = dy * gamma[c];
-          dzr[c] = rstd * (dzh - s1 - zh * s2);
+          const float o = rstd * (dzh - s1 - zh * s2);
+          dzr[c] = o;
+          if (dz_h != nullptr) dz_h[static_cast<size_t>(row) * ldh + c] = __float2bfloat16_rn(o);
           pg[j] += dy * zh;
           pb[j] += dy;
         }
@@ -175,7 +188,8 @@ norm_act_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ z, c
 
 cudaError_t launch_norm_act_bwd(int norm, const float* dx, const float* z, const float* gamma, const float* beta,
                                 const float* rstd, const float* mean, int rows, int H, float* dz, float* dgamma,
-                                float* dbeta, cudaStream_t st) {
+                                float* dbeta, void* dz_h, int ldh, cudaStream_t st) {
+  __nv_bfloat16* dzh = static_cast<__nv_bfloat16*>(dz_h);
   if (rows <= 0) return cudaSuccess;
   if (H > 32 * kMaxColsPerLane) return cudaErrorInvalidValue;
   // enough blocks to fill the machine, few enough that the per-block atomics stay cheap
@@ -183,9 +197,9 @@ cudaError_t launch_norm_act_bwd(int norm, const float* dx, const float* z, const
   while ((rows + rows_per_block - 1) / rows_per_block > 148 * 4 && rows_per_block < 128) rows_per_block *= 2;
   const int grid = (rows + rows_per_block - 1) / rows_per_block;
   const size_t smem = (norm == NORM_NONE) ? 0 : 2 * static_cast<size_t>(H) * sizeof(float);
-  if (norm == NORM_NONE) norm_act_bwd_kernel<NORM_NONE><<<grid, 256, smem, st>>>(dx, z, gamma, beta, rstd, mean, rows, H, rows_per_block, dz, dgamma, dbeta);
-  else if (norm == NORM_RMS) norm_act_bwd_kernel<NORM_RMS><<<grid, 256, smem, st>>>(dx, z, gamma, beta, rstd, mean, rows, H, rows_per_block, dz, dgamma, dbeta);
-  else norm_act_bwd_kernel<NORM_LAYER><<<grid, 256, smem, st>>>(dx, z, gamma, beta, rstd, mean, rows, H, rows_per_block, dz, dgamma, dbeta);
+  if (norm == NORM_NONE) norm_act_bwd_kernel<NORM_NONE><<<grid, 256, smem, st>>>(dx, z, gamma, beta, rstd, mean, rows, H, rows_per_block, dz, dgamma, dbeta, dzh, ldh);
+  else if (norm == NORM_RMS) norm_act_bwd_kernel<NORM_RMS><<<grid, 256, smem, st>>>(dx, z, gamma, beta, rstd, mean, rows, H, rows_per_block, dz, dgamma, dbeta, dzh, ldh);
+  else norm_act_bwd_kernel<NORM_LAYER><<<grid, 256, smem, st>>>(dx, z, gamma, beta, rstd, mean, rows, H, rows_per_block, dz, dgamma, dbeta, dzh, ldh);
   return cudaGetLastError();
 }
 

@@ -383,3 +383,77 @@ def test_update_against_reference_golden(name):
         for net, e in (("critic", eng.critic), ("actor", eng.actor)):
             for k, dg in g["final_digest"][net].items():
                 _param_close(f"{net}.{k}", e.view(e.params, k).reshape(-1)[:64], dg["head"], hp.lr, len(logs))
+
+
+# ---------------------------------------------------------------------------------------------
+# REPPO_GEMM_BF16: tcgen05 GEMMs on bf16 operands, fp32 accumulation, fp32 everything else.
+# Tolerances (stated): forward activations 2e-2 of their max-abs; losses 1e-2 relative;
+# gradients: max-abs error <= 4e-2 of the tensor's max-abs gradient and cosine similarity >= 0.999;
+# after a full update: losses within 5 % of the fp32 oracle trace (Adam amplifies sign noise).
+# ---------------------------------------------------------------------------------------------
+def _cos(a, b):
+    a, b = a.detach().cpu().double().reshape(-1), b.detach().cpu().double().reshape(-1)
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("sem,kw", [(O.JAX, SMALL), (O.TORCH, RAGGED), (O.JAX, dict(RAGGED, norm_type="layer"))])
+def test_bf16_mode_gradients(sem, kw):
+    hp = O.Hyper(**kw)
+    cp, ap, ap_old, flat, eps_pi, eps_kl, perms = _setup(hp, sem)
+    eng = _engine(hp, sem, gemm_mode="bf16")
+    eng.load_params(cp, ap)
+    for k in eng.actor.layout:
+        eng.actor.view(eng.actor_old, k).copy_(ap_old[k])
+    hyp = _hyper(hp)
+    batch = eng.make_batch(flat)
+    idx = perms[0, :hp.minibatch_size]
+    mb = O.take(flat, idx)
+    m = eng.metrics_dict(eng.critic_grad(batch, idx, hyp))
+    loss, om, grads = O._value_and_grad(lambda p: O.critic_loss(p, mb, hp, sem), cp)
+    assert math.isclose(m["critic_loss"], loss.item(), rel_tol=1e-2)
+    assert math.isclose(m["q_mean"], om["q"].item(), rel_tol=2e-2, abs_tol=1e-3)
+    for k, gref in grads.items():
+        got = eng.critic.view(eng.critic.grads, k)
+        _grad_close(f"critic.{k}", got, gref, rel=4e-2)
+        if gref.numel() > 8:
+            assert _cos(got, gref) >= 0.999, k
+    m = eng.metrics_dict(eng.actor_grad(batch, idx, eps_pi[0], eps_kl[0], hyp))
+    loss, om, grads = O._value_and_grad(lambda p: O.actor_loss(p, ap_old, cp, mb, eps_pi[0], eps_kl[0], hp, sem), ap)
+    assert math.isclose(m["actor_loss"], loss.item(), rel_tol=2e-2, abs_tol=2e-3)
+    assert math.isclose(m["kl"], om["kl"].item(), rel_tol=5e-2, abs_tol=1e-4)
+    assert math.isclose(m["entropy"], om["entropy"].item(), rel_tol=1e-2, abs_tol=1e-3)
+    for k, gref in grads.items():
+        got = eng.actor.view(eng.actor.grads, k)
+        _grad_close(f"actor.{k}", got, gref, rel=6e-2)
+        if gref.numel() > 8:
+            assert _cos(got, gref) >= 0.998, k
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_bf16_mode_full_update(use_graph):
+    hp = O.Hyper(**SMALL)
+    sem = O.JAX
+    cp, ap = O.init_params(hp, sem, seed=0)
+    batch = O.synthetic_rollout(hp, seed=0, terminate=True)
+    perms = O.synthetic_perms(hp)
+    eps_pi, eps_kl = O.synthetic_noise(hp)
+    ts2, ometrics, target, traces = O.learn_step(O.TrainState.create(cp, ap), {k: v.clone() for k, v in batch.items()}, perms,
+                                                 eps_pi, eps_kl, hp, sem, trace=True)
+    eng = _engine(hp, sem, gemm_mode="bf16")
+    eng.load_params(cp, ap)
+    dev = {k: v.cuda() for k, v in batch.items()}
+    tgt = eng.td_lambda(dev["soft_reward"], dev["value"], dev["done"], dev["truncated"], dev["importance_weight"], hp.gamma, hp.lmbda)
+    flat = {k: v.reshape(-1, *v.shape[2:]) for k, v in dev.items()}
+    flat["target"] = tgt.reshape(-1)
+    m, sm = eng.update(eng.make_batch(flat), perms.to(torch.int32).cuda(), eps_pi.cuda(), eps_kl.cuda(), _hyper(hp),
+                       hp.num_mini_batches, use_graph=use_graph)
+    torch.cuda.synchronize()
+    sm = sm.cpu()
+    from reppo_b200 import _lib as L
+    col = {k: i for i, k in enumerate(L.METRIC_NAMES)}
+    for i, t in enumerate(traces):
+        assert math.isclose(sm[i, col["critic_loss"]].item(), t["critic/loss"].item(), rel_tol=5e-2), i
+        assert math.isclose(sm[i, col["entropy"]].item(), t["actor/entropy"].item(), rel_tol=5e-2, abs_tol=5e-3), i
+    for k in cp:
+        err = (eng.critic.view(eng.critic.params, k).cpu() - ts2.critic[k]).abs().max().item()
+        assert err <= 2 * hp.lr * len(traces) + 1e-6, (k, err)
