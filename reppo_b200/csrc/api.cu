@@ -231,9 +231,9 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
   c->dx0 = F(R * K0);
   c->logp = F(R); c->kl = F(R); c->q = F(R); c->gmu = F(R * A); c->gsig = F(R * A);
   if (c->tc) {
-    c->shadow_b[SLOT_CRITIC] = Hf(c->shadow_b_elems[0]); c->shadow_t[SLOT_CRITIC] = Hf(c->shadow_t_elems[0]);
-    c->shadow_b[SLOT_ACTOR] = Hf(c->shadow_b_elems[1]); c->shadow_t[SLOT_ACTOR] = Hf(c->shadow_t_elems[1]);
-    c->shadow_b[SLOT_ACTOR_OLD] = Hf(c->shadow_b_elems[1]); c->shadow_t[SLOT_ACTOR_OLD] = nullptr;
+    c->shadow_b[SLOT_CRITIC] = Hf(c->shadow_b_elems[0]);
+    c->shadow_b[SLOT_ACTOR] = Hf(c->shadow_b_elems[1]);
+    c->shadow_b[SLOT_ACTOR_OLD] = Hf(c->shadow_b_elems[1]);
     const size_t md8 = round8(static_cast<int>(maxdim));
     c->lin_a = Hf(R * md8); c->lin_c = Hf(R * md8); c->lin_b = Hf(maxdim * md8);
   }
@@ -256,8 +256,8 @@ int linear_fwd(reppo_ctx* c, const Linear& L, const float* params, int slot, con
   if (c->tc) {
     const Twin tx = c->twin(x);
     if (tx.p == nullptr) return fail(c, REPPO_ERR_INVALID, "internal: forward operand has no bf16 twin");
-    CK(launch_gemm_bf16_tc(false, rows, L.out, L.in, tx.p, tx.ld, c->shadow_b[slot] + L.sb, L.ld_b, y, L.out, params + L.b,
-                           GEMM_STORE, 1, st));
+    CK(launch_gemm_bf16_tc(false, false, rows, L.out, L.in, tx.p, tx.ld, c->shadow_b[slot] + L.sb, L.ld_b, y, L.out,
+                           params + L.b, GEMM_STORE, 1, st));
   } else {
     CK(launch_gemm_f32(false, true, rows, L.out, L.in, x, L.in, params + L.w, L.in, y, L.out, params + L.b, GEMM_STORE, 1, st));
   }
@@ -268,8 +268,10 @@ int linear_dgrad(reppo_ctx* c, const Linear& L, const float* params, int slot, c
                  cudaStream_t st) {
   if (c->tc) {
     const Twin td = c->twin(dy);
-    if (td.p == nullptr || c->shadow_t[slot] == nullptr) return fail(c, REPPO_ERR_INVALID, "internal: dgrad operand has no bf16 twin");
-    CK(launch_gemm_bf16_tc(false, rows, L.in, L.out, td.p, td.ld, c->shadow_t[slot] + L.st, L.ld_t, dx, L.in, nullptr, mode, 1, st));
+    if (td.p == nullptr) return fail(c, REPPO_ERR_INVALID, "internal: dgrad operand has no bf16 twin");
+    // B = W [out, in] read MN-major (reduction dim = out is the outer dim): no transposed shadow needed
+    CK(launch_gemm_bf16_tc(false, true, rows, L.in, L.out, td.p, td.ld, c->shadow_b[slot] + L.sb, L.ld_b, dx, L.in, nullptr, mode,
+                           1, st));
   } else {
     CK(launch_gemm_f32(false, false, rows, L.in, L.out, dy, L.out, params + L.w, L.in, dx, L.in, nullptr, mode, 1, st));
   }
@@ -281,7 +283,7 @@ int linear_wgrad(reppo_ctx* c, const Linear& L, const float* dy, const float* x,
   if (c->tc) {
     const Twin td = c->twin(dy), tx = c->twin(x);
     if (td.p == nullptr || tx.p == nullptr) return fail(c, REPPO_ERR_INVALID, "internal: wgrad operand has no bf16 twin");
-    CK(launch_gemm_bf16_tc(true, L.out, L.in, rows, td.p, td.ld, tx.p, tx.ld, dw, L.in, nullptr, GEMM_ATOMIC, split, st));
+    CK(launch_gemm_bf16_tc(true, true, L.out, L.in, rows, td.p, td.ld, tx.p, tx.ld, dw, L.in, nullptr, GEMM_ATOMIC, split, st));
   } else {
     CK(launch_gemm_f32(true, false, L.out, L.in, rows, dy, L.out, x, L.in, dw, L.in, nullptr, GEMM_ATOMIC, split, st));
   }
@@ -296,7 +298,7 @@ int pack_shadows(reppo_ctx* c, int slot, const float* params, cudaStream_t st) {
     for (const Linear& L : m.layers) {
       PackEntry& e = t.e[t.n++];
       e.w = params + L.w; e.wb = c->shadow_b[slot] + L.sb;
-      e.wtb = c->shadow_t[slot] ? c->shadow_t[slot] + L.st : nullptr;
+      e.wtb = nullptr;
       e.out = L.out; e.in = L.in; e.ld_b = L.ld_b; e.ld_t = L.ld_t;
     }
   };
@@ -323,7 +325,7 @@ int mlp_forward(reppo_ctx* c, const Mlp& m, const float* params, int slot, const
     if (!last) {
       const Twin tw = c->twin(a.x[i]);
       CK(launch_norm_act_fwd(m.norm, a.z[i], L.g >= 0 ? params + L.g : nullptr, L.beta >= 0 ? params + L.beta : nullptr,
-                             rows, L.out, c->sem.norm_eps, a.x[i], a.rstd[i], a.mean[i], tw.p, tw.ld, st));
+                             rows, L.out, c->sem.norm_eps, c->tc ? nullptr : a.x[i], a.rstd[i], a.mean[i], tw.p, tw.ld, st));
       cur = a.x[i];
     }
   }
@@ -332,8 +334,10 @@ int mlp_forward(reppo_ctx* c, const Mlp& m, const float* params, int slot, const
 
 // d_out: gradient w.r.t. the MLP output [rows, out_last] (read only).  grads == nullptr: frozen network (dgrad only).
 // dx_in != nullptr: also produce the gradient w.r.t. the MLP input (mode GEMM_STORE / GEMM_ACCUM).
+// last_bias_done: the producer of d_out already accumulated the last layer's bias gradient (column sums of d_out).
 int mlp_backward(reppo_ctx* c, const Mlp& m, const float* params, int slot, float* grads, const float* in, int rows,
-                 const Acts& a, const float* d_out, float* dx_in, int dx_mode, float* bias2, float scale2, cudaStream_t st) {
+                 const Acts& a, const float* d_out, float* dx_in, int dx_mode, float* bias2, float scale2, bool last_bias_done,
+                 cudaStream_t st) {
   const int n = static_cast<int>(m.layers.size());
   const float* d = d_out;
   for (int i = n - 1; i >= 0; --i) {
@@ -341,16 +345,17 @@ int mlp_backward(reppo_ctx* c, const Mlp& m, const float* params, int slot, floa
     const float* xin = (i == 0) ? in : a.x[i - 1];
     if (grads != nullptr) {
       RET(linear_wgrad(c, L, d, xin, rows, grads + L.w, st));
-      CK(launch_colsum(d, rows, L.out, L.out, grads + L.b, (i == n - 1) ? bias2 : nullptr, scale2, st));
+      // hidden layers: the norm backward that produced d accumulated its column sums already
+      if (i == n - 1 && !last_bias_done) CK(launch_colsum(d, rows, L.out, L.out, grads + L.b, bias2, scale2, st));
     }
     if (i > 0) {
       const Linear& Lp = m.layers[i - 1];
       RET(linear_dgrad(c, L, params, slot, d, rows, c->tmpA, GEMM_STORE, st));
       const Twin tw = c->twin(c->tmpB);
       CK(launch_norm_act_bwd(m.norm, c->tmpA, a.z[i - 1], Lp.g >= 0 ? params + Lp.g : nullptr,
-                             Lp.beta >= 0 ? params + Lp.beta : nullptr, a.rstd[i - 1], a.mean[i - 1], rows, L.in, c->tmpB,
-                             (grads && Lp.g >= 0) ? grads + Lp.g : nullptr, (grads && Lp.beta >= 0) ? grads + Lp.beta : nullptr,
-                             tw.p, tw.ld, st));
+                             Lp.beta >= 0 ? params + Lp.beta : nullptr, a.rstd[i - 1], a.mean[i - 1], rows, L.in,
+                             c->tc ? nullptr : c->tmpB, (grads && Lp.g >= 0) ? grads + Lp.g : nullptr,
+                             (grads && Lp.beta >= 0) ? grads + Lp.beta : nullptr, grads ? grads + Lp.b : nullptr, tw.p, tw.ld, st));
       d = c->tmpB;
     } else if (dx_in != nullptr) {
       RET(linear_dgrad(c, L, params, slot, d, rows, dx_in, dx_mode, st));
@@ -368,8 +373,8 @@ int check_rows(reppo_ctx* c, int rows) {
 int critic_trunk(reppo_ctx* c, const float* cp, int rows, bool with_pred, cudaStream_t st) {
   RET(mlp_forward(c, c->feature, cp, SLOT_CRITIC, c->x0, rows, c->fa, st));
   const Twin tw = c->twin(c->xs);
-  CK(launch_norm_act_fwd(NORM_NONE, c->fa.out, nullptr, nullptr, rows, c->shape.critic_hidden, 0.f, c->xs, nullptr, nullptr,
-                         tw.p, tw.ld, st));
+  CK(launch_norm_act_fwd(NORM_NONE, c->fa.out, nullptr, nullptr, rows, c->shape.critic_hidden, 0.f, c->tc ? nullptr : c->xs,
+                         nullptr, nullptr, tw.p, tw.ld, st));
   RET(mlp_forward(c, c->head, cp, SLOT_CRITIC, c->xs, rows, c->ha, st));
   if (with_pred) RET(mlp_forward(c, c->pred, cp, SLOT_CRITIC, c->xs, rows, c->pa, st));
   return REPPO_OK;
@@ -410,12 +415,13 @@ int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
                        b->reward, b->done, b->truncated, idx, mb, inv, no_mask, hp->aux_loss_mult, c->dpred, metrics, tw.p,
                        tw.ld, st));
   RET(mlp_backward(c, c->head, cp, SLOT_CRITIC, cg, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, cg + c->zero_dist_off,
-                   c->sem.bias_scale, st));
-  RET(mlp_backward(c, c->pred, cp, SLOT_CRITIC, cg, c->xs, mb, c->pa, c->dpred, c->dxs, GEMM_ACCUM, nullptr, 0.f, st));
+                   c->sem.bias_scale, false, st));
+  RET(mlp_backward(c, c->pred, cp, SLOT_CRITIC, cg, c->xs, mb, c->pa, c->dpred, c->dxs, GEMM_ACCUM, nullptr, 0.f, false, st));
   tw = c->twin(c->dfeat);
-  CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden, c->dfeat,
-                         nullptr, nullptr, tw.p, tw.ld, st));
-  RET(mlp_backward(c, c->feature, cp, SLOT_CRITIC, cg, c->x0, mb, c->fa, c->dfeat, nullptr, GEMM_STORE, nullptr, 0.f, st));
+  // d feat = d swish(feat) * swish'(feat); its column sums are the bias gradient of the encoder's last Linear
+  CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden,
+                         c->tc ? nullptr : c->dfeat, nullptr, nullptr, cg + c->feature.layers.back().b, tw.p, tw.ld, st));
+  RET(mlp_backward(c, c->feature, cp, SLOT_CRITIC, cg, c->x0, mb, c->fa, c->dfeat, nullptr, GEMM_STORE, nullptr, 0.f, true, st));
   return REPPO_OK;
 }
 
@@ -454,32 +460,45 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
   RET(mlp_forward(c, c->actor, s->actor_old, SLOT_ACTOR_OLD, c->xa0, mb, c->oa, st));
   const Twin tx0 = c->twin(c->x0);
   CK(launch_gather_concat(b->critic_obs, Dc, nullptr, 0, idx, 0, mb, c->x0, c->K0, tx0.p, tx0.ld, st));
-  CK(launch_actor_sample(c->aa.out, c->oa.out, eps_pi, eps_kl, mb, A, sh.kl_samples, ac, c->x0 + Dc, c->K0, c->logp, c->kl,
-                         c->gmu, c->gsig, tx0.p ? tx0.p + Dc : nullptr, tx0.ld, st));
+  CK(launch_actor_sample(c->aa.out, c->oa.out, nullptr, eps_pi, eps_kl, mb, A, sh.kl_samples, ac, c->x0 + Dc, c->K0, c->logp,
+                         c->kl, c->gmu, c->gsig, tx0.p ? tx0.p + Dc : nullptr, tx0.ld, st));
   RET(critic_trunk(c, cp, mb, false, st));
   tw = c->twin(c->dlogits);
   CK(launch_actor_q(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, c->kl, mb, inv, ac.kl_mode, ac.kl_bound, c->q,
                     c->dlogits, tw.p, tw.ld, st));
-  RET(mlp_backward(c, c->head, cp, SLOT_CRITIC, nullptr, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, st));
+  RET(mlp_backward(c, c->head, cp, SLOT_CRITIC, nullptr, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, false, st));
   tw = c->twin(c->dfeat);
-  CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden, c->dfeat,
-                         nullptr, nullptr, tw.p, tw.ld, st));
-  RET(mlp_backward(c, c->feature, cp, SLOT_CRITIC, nullptr, c->x0, mb, c->fa, c->dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, st));
+  CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden,
+                         c->tc ? nullptr : c->dfeat, nullptr, nullptr, nullptr, tw.p, tw.ld, st));
+  RET(mlp_backward(c, c->feature, cp, SLOT_CRITIC, nullptr, c->x0, mb, c->fa, c->dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, false, st));
   tw = c->twin(c->dout);
   CK(launch_actor_grad(c->aa.out, eps_pi, c->x0 + Dc, c->K0, c->dx0 + Dc, c->K0, c->logp, c->kl, c->q, c->gmu, c->gsig, ap,
                        mb, A, inv, ac, c->dout, ag, metrics, tw.p, tw.ld, st));
-  RET(mlp_backward(c, c->actor, ap, SLOT_ACTOR, ag, c->xa0, mb, c->aa, c->dout, nullptr, GEMM_STORE, nullptr, 0.f, st));
+  RET(mlp_backward(c, c->actor, ap, SLOT_ACTOR, ag, c->xa0, mb, c->aa, c->dout, nullptr, GEMM_STORE, nullptr, 0.f, false, st));
   return REPPO_OK;
 }
 
-int clip_adam_impl(reppo_ctx* c, const reppo_net_state* net, int64_t n, const reppo_hyper* hp, float* gn_out, cudaStream_t st) {
+// slot < 0: plain arena (no bf16 shadow to refresh)
+int clip_adam_impl(reppo_ctx* c, const reppo_net_state* net, int64_t n, const reppo_hyper* hp, float* gn_out, int slot,
+                   cudaStream_t st) {
   if (c->ws == nullptr) return fail(c, REPPO_ERR_WORKSPACE, "workspace not set (reppo_set_workspace)");
+  ShadowTable sh{};
+  if (c->tc && slot >= 0) {
+    auto add = [&](const Mlp& m) {
+      for (const Linear& L : m.layers) {
+        ShadowEntry& e = sh.e[sh.n++];
+        e.start = L.w; e.end = L.w + static_cast<int64_t>(L.out) * L.in; e.in = L.in; e.ld = L.ld_b;
+        e.dst = c->shadow_b[slot] + L.sb;
+      }
+    };
+    if (slot == SLOT_CRITIC) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
+  }
   AdamConsts a{};
   a.lr = hp->lr; a.b1 = 0.9f; a.b2 = 0.999f; a.eps = 1e-8f;
   a.weight_decay = c->sem.torch_opt ? 0.01f : 0.f;  // torch.optim.AdamW default (src/torchrl/reppo.py:527-534)
   a.max_grad_norm = hp->max_grad_norm;
   a.torch_clip = c->sem.torch_opt;
-  CK(launch_clip_adam(net->params, net->grads, net->adam_m, net->adam_v, n, net->step, c->partials, a, gn_out, st));
+  CK(launch_clip_adam(net->params, net->grads, net->adam_m, net->adam_v, n, net->step, c->partials, a, &sh, gn_out, st));
   ++c->launches;  // two kernels
   return REPPO_OK;
 }
@@ -488,16 +507,14 @@ int critic_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
                      const reppo_hyper* hp, float* metrics, cudaStream_t st) {
   RET(critic_grad_impl(c, s, b, idx, mb, hp, metrics, st));
   RET(allreduce_grads(c, s->critic.grads, c->critic_count, st));
-  RET(clip_adam_impl(c, &s->critic, c->critic_count, hp, metrics + M_CRITIC_GRAD_NORM, st));
-  return pack_shadows(c, SLOT_CRITIC, s->critic.params, st);
+  return clip_adam_impl(c, &s->critic, c->critic_count, hp, metrics + M_CRITIC_GRAD_NORM, SLOT_CRITIC, st);
 }
 
 int actor_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb, const float* eps_pi,
                     const float* eps_kl, const reppo_hyper* hp, float* metrics, cudaStream_t st) {
   RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, st));
   RET(allreduce_grads(c, s->actor.grads, c->actor_count, st));
-  RET(clip_adam_impl(c, &s->actor, c->actor_count, hp, metrics + M_ACTOR_GRAD_NORM, st));
-  return pack_shadows(c, SLOT_ACTOR, s->actor.params, st);
+  return clip_adam_impl(c, &s->actor, c->actor_count, hp, metrics + M_ACTOR_GRAD_NORM, SLOT_ACTOR, st);
 }
 
 int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const reppo_plan* p, const reppo_hyper* hp,
@@ -713,17 +730,15 @@ int reppo_linear(reppo_ctx* c, int32_t op, int32_t rows, int32_t in_f, int32_t o
   if (op == 0) {
     CK(launch_cast_bf16(a, rows, in_f, in_f, c->lin_a, ldi, st));
     CK(launch_cast_bf16(b, out_f, in_f, in_f, c->lin_b, ldi, st));
-    CK(launch_gemm_bf16_tc(false, rows, out_f, in_f, c->lin_a, ldi, c->lin_b, ldi, out, out_f, bias, GEMM_STORE, 1, st));
+    CK(launch_gemm_bf16_tc(false, false, rows, out_f, in_f, c->lin_a, ldi, c->lin_b, ldi, out, out_f, bias, GEMM_STORE, 1, st));
   } else if (op == 1) {
     CK(launch_cast_bf16(a, rows, out_f, out_f, c->lin_a, ldo, st));
-    PackTable t{};
-    t.n = 1; t.e[0] = PackEntry{b, nullptr, c->lin_b, out_f, in_f, ldi, ldo};
-    CK(launch_pack_weights(t, st));
-    CK(launch_gemm_bf16_tc(false, rows, in_f, out_f, c->lin_a, ldo, c->lin_b, ldo, out, in_f, nullptr, GEMM_STORE, 1, st));
+    CK(launch_cast_bf16(b, out_f, in_f, in_f, c->lin_b, ldi, st));
+    CK(launch_gemm_bf16_tc(false, true, rows, in_f, out_f, c->lin_a, ldo, c->lin_b, ldi, out, in_f, nullptr, GEMM_STORE, 1, st));
   } else {
     CK(launch_cast_bf16(a, rows, out_f, out_f, c->lin_a, ldo, st));
     CK(launch_cast_bf16(b, rows, in_f, in_f, c->lin_c, ldi, st));
-    CK(launch_gemm_bf16_tc(true, out_f, in_f, rows, c->lin_a, ldo, c->lin_c, ldi, out, in_f, nullptr, GEMM_ATOMIC,
+    CK(launch_gemm_bf16_tc(true, true, out_f, in_f, rows, c->lin_a, ldo, c->lin_c, ldi, out, in_f, nullptr, GEMM_ATOMIC,
                            wgrad_split(out_f, in_f, rows, true), st));
   }
   return REPPO_OK;
@@ -755,7 +770,7 @@ int reppo_actor_step(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
 }
 int reppo_clip_adam(reppo_ctx* c, const reppo_net_state* net, int64_t n, const reppo_hyper* hp, float* gn, reppo_stream stream) {
   c->launches = 0;
-  return clip_adam_impl(c, net, n, hp, gn, static_cast<cudaStream_t>(stream));
+  return clip_adam_impl(c, net, n, hp, gn, -1, static_cast<cudaStream_t>(stream));
 }
 
 int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const reppo_plan* p, const reppo_hyper* hp,

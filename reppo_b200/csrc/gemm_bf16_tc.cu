@@ -6,16 +6,16 @@
 //
 // Three operand arrangements cover forward, dgrad and wgrad of y = x W^T + b
 // (src/networks/jax_models.py:35-49, torch_models.py:71-79):
-//   KK : A[M,K] and B[N,K] both K-major (row-major, reduction dim contiguous)
-//          forward  y  = x  · W^T       A = x  [rows,in],  B = W   [out,in]
-//          dgrad    dx = dy · (W^T)^T   A = dy [rows,out], B = W^T [in,out]   (transposed bf16 shadow)
-//   MM : A and B both MN-major (reduction dim = rows is the OUTER dim of both operands)
-//          wgrad    dW[out,in] = dy^T · x     A = dy [rows,out],  B = x [rows,in]
+//   A K-major,  B K-major  : forward  y  = x  · W^T    A = x  [rows,in],  B = W [out,in]  (reduction dim contiguous)
+//   A K-major,  B MN-major : dgrad    dx = dy · W      A = dy [rows,out], B = W [out,in]  (same bf16 shadow, no W^T copy)
+//   A MN-major, B MN-major : wgrad    dW[out,in] = dy^T · x    A = dy [rows,out], B = x [rows,in]  (reduction dim = rows)
 // Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer,
 // warps 2..5 = epilogue (each owns the 32 TMEM lanes  32*(warp%4) .. +32).
 // Pipeline: NUM_STAGES-deep smem ring with full/empty mbarriers (TMA -> MMA), one
 // tmem_full mbarrier (MMA -> epilogue).  One output tile per CTA; split-K over gridDim.z for
-// wgrad (fp32 atomics into the zeroed gradient arena).
+// wgrad (fp32 atomics into the zeroed gradient arena).  Epilogue: tcgen05.ld gives every thread
+// one accumulator ROW, which is transposed through the (by then idle) pipeline shared memory so
+// that global stores are row-contiguous 128 B / 512 B segments.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -114,8 +114,8 @@ struct TcSmem {
   static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
 };
 
-// MODE: GEMM_STORE / GEMM_ACCUM / GEMM_ATOMIC.  MN_MAJOR: false = KK arrangement, true = MM arrangement.
-template <int BLOCK_N, int STAGES, bool MN_MAJOR>
+// mode: GEMM_STORE / GEMM_ACCUM / GEMM_ATOMIC.  A_MN / B_MN: operand is MN-major (reduction dim is the outer dim).
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     float* __restrict__ C, int ldc, const float* __restrict__ bias, int M, int N, int K, int k_blocks_per_split,
@@ -160,21 +160,23 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint8_t* sb = sa + S::kABytes;
       mbar_expect_tx(&full_bar[s], S::kStageBytes);
       const int k0 = (kb_begin + i) * TC_BLOCK_K;
-      if (!MN_MAJOR) {
-        // A tile [128 rows][64 k], B tile [BLOCK_N rows][64 k]; coordinates {k, row}
+      // K-major tile [rows][64 k]: coordinates {k, row}.  MN-major: atoms of [64 k-rows][64 mn], coordinates {mn, k-row}.
+      if (!A_MN) {
         tma_load_2d(&tmap_a, &full_bar[s], sa, k0, m0);
-        tma_load_2d(&tmap_b, &full_bar[s], sb, k0, n0);
       } else {
-        // atoms of [64 k-rows][64 mn]: coordinates {mn, k-row}
 #pragma unroll
         for (int a = 0; a < TC_BLOCK_M / 64; ++a) tma_load_2d(&tmap_a, &full_bar[s], sa + a * (TC_BLOCK_K * 128), m0 + a * 64, k0);
+      }
+      if (!B_MN) {
+        tma_load_2d(&tmap_b, &full_bar[s], sb, k0, n0);
+      } else {
 #pragma unroll
         for (int b = 0; b < BLOCK_N / 64; ++b) tma_load_2d(&tmap_b, &full_bar[s], sb + b * (TC_BLOCK_K * 128), n0 + b * 64, k0);
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc(BLOCK_N, MN_MAJOR, MN_MAJOR);
+    constexpr uint32_t idesc = make_idesc(BLOCK_N, A_MN, B_MN);
     for (int i = 0; i < num_kb; ++i) {
       const int s = i % STAGES;
       const uint32_t ph = (i / STAGES) & 1;
@@ -184,29 +186,27 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t sb = sa + S::kABytes;
 #pragma unroll
       for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-        uint64_t da, db;
-        if (!MN_MAJOR) {
-          // K-major SW128: 8-row groups 1024 B apart; advance 32 B per UMMA_K inside the swizzle row
-          da = make_smem_desc(sa + k * (TC_UMMA_K * 2), 16, 1024);
-          db = make_smem_desc(sb + k * (TC_UMMA_K * 2), 16, 1024);
-        } else {
-          // MN-major SW128: LBO = stride between 64-wide MN atoms, SBO = stride between 8-row K groups;
-          // advance 16 k-rows = 2048 B per UMMA_K
-          da = make_smem_desc(sa + k * (TC_UMMA_K * 128), TC_BLOCK_K * 128, 1024);
-          db = make_smem_desc(sb + k * (TC_UMMA_K * 128), TC_BLOCK_K * 128, 1024);
-        }
+        // K-major SW128: 8-row groups 1024 B apart; advance 32 B per UMMA_K inside the swizzle row.
+        // MN-major SW128: LBO = stride between 64-wide MN atoms, SBO = stride between 8-row K groups;
+        // advance 16 k-rows = 2048 B per UMMA_K.
+        const uint64_t da = A_MN ? make_smem_desc(sa + k * (TC_UMMA_K * 128), TC_BLOCK_K * 128, 1024)
+                                 : make_smem_desc(sa + k * (TC_UMMA_K * 2), 16, 1024);
+        const uint64_t db = B_MN ? make_smem_desc(sb + k * (TC_UMMA_K * 128), TC_BLOCK_K * 128, 1024)
+                                 : make_smem_desc(sb + k * (TC_UMMA_K * 2), 16, 1024);
         tc_mma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
       }
       tc_commit(&empty_bar[s]);          // frees the smem slot when these MMAs retire
     }
     tc_commit(tmem_full_bar);            // accumulator complete
   } else if (warp >= 2) {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    // all TMA loads were consumed by MMAs that have retired: the pipeline stages are free to reuse
+    constexpr int kStgLd = BLOCK_N + 4;
+    static_assert(4 * 32 * kStgLd * 4 <= STAGES * S::kStageBytes, "staging does not fit in the pipeline smem");
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * kStgLd;
     const int lane_base = (warp & 3) * 32;
-    const int row = m0 + lane_base + lane;
-    const bool add_bias = (bias != nullptr) && (blockIdx.z == 0);
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       float v[32];
@@ -216,13 +216,55 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      if (row < M) {
+      float4* dst = reinterpret_cast<float4*>(stg + lane * kStgLd + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    __syncwarp();
+    const bool add_bias = (bias != nullptr) && (blockIdx.z == 0);
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (mode != GEMM_ATOMIC);
+    if (vec_ok) {
+      constexpr int kLanesPerRow = BLOCK_N / 4;          // 32 (BLOCK_N = 128) or 16 (BLOCK_N = 64)
+      constexpr int kRowsPerIter = 32 / kLanesPerRow;    // 1 or 2
+      const int cl = (lane % kLanesPerRow) * 4;
+      const int col = n0 + cl;
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (add_bias) {
+        if (col + 0 < N) bv.x = bias[col + 0];
+        if (col + 1 < N) bv.y = bias[col + 1];
+        if (col + 2 < N) bv.z = bias[col + 2];
+        if (col + 3 < N) bv.w = bias[col + 3];
+      }
+#pragma unroll 4
+      for (int r = lane / kLanesPerRow; r < 32; r += kRowsPerIter) {
+        const int row = m0 + lane_base + r;
+        if (row >= M || col >= N) continue;
+        float4 x = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);
+        x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+        float* cp = C + static_cast<size_t>(row) * ldc + col;
+        if (col + 3 < N) {
+          if (mode == GEMM_ACCUM) {
+            const float4 o = *reinterpret_cast<const float4*>(cp);
+            x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+          }
+          *reinterpret_cast<float4*>(cp) = x;
+        } else {
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+          for (int j = 0; j < 4 && col + j < N; ++j) cp[j] = (mode == GEMM_ACCUM) ? cp[j] + xs[j] : xs[j];
+        }
+      }
+    } else {
+      // ragged leading dimension or atomics: scalar, lanes sweep consecutive columns (128 B per row per access)
+#pragma unroll 1
+      for (int r = 0; r < 32; ++r) {
+        const int row = m0 + lane_base + r;
+        if (row >= M) break;
         float* crow = C + static_cast<size_t>(row) * ldc;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = n0 + c0 + j;
+        for (int cc = 0; cc < BLOCK_N; cc += 32) {
+          const int col = n0 + cc + lane;
           if (col < N) {
-            float x = v[j];
+            float x = stg[r * kStgLd + cc + lane];
             if (add_bias) x += bias[col];
             if (mode == GEMM_STORE) crow[col] = x;
             else if (mode == GEMM_ACCUM) crow[col] += x;
@@ -270,12 +312,12 @@ static bool encode_2d(CUtensorMap* map, const void* base, int rows, int cols, in
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BLOCK_N, int STAGES, bool MN_MAJOR>
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
 static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int ldc, const float* bias, int M, int N,
                              int K, int split_k, int mode, cudaStream_t st) {
   using S = TcSmem<BLOCK_N, STAGES>;
   static bool configured = false;
-  auto kern = gemm_bf16_tc_kernel<BLOCK_N, STAGES, MN_MAJOR>;
+  auto kern = gemm_bf16_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) return e;
@@ -292,31 +334,30 @@ static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float
   return cudaGetLastError();
 }
 
-// A, B: bf16 device pointers.
-//  mn_major == false: A [M, K] ld lda, B [N, K] ld ldb               (forward / dgrad)
-//  mn_major == true : A [K, M] ld lda, B [K, N] ld ldb  (K = rows)   (wgrad)
-// Leading dimensions must be multiples of 8 elements (16 B) and the bases 16-byte aligned.
-cudaError_t launch_gemm_bf16_tc(bool mn_major, int M, int N, int K, const void* A, int lda, const void* B, int ldb, float* C,
-                                int ldc, const float* bias, int mode, int split_k, cudaStream_t st) {
+// A, B: bf16 device pointers, row-major with leading dimensions lda / ldb (elements, multiples of 8).
+//  a_mn == false: A stored [M, K]   | a_mn == true: A stored [K, M]
+//  b_mn == false: B stored [N, K]   | b_mn == true: B stored [K, N]
+cudaError_t launch_gemm_bf16_tc(bool a_mn, bool b_mn, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
+                                float* C, int ldc, const float* bias, int mode, int split_k, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
   if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
     return cudaErrorInvalidValue;
+  if (a_mn && !b_mn) return cudaErrorInvalidValue;  // arrangement not used by the MLP
   CUtensorMap ta, tb;
-  const bool wide = N > 64;
+  // narrow tiles when 128-wide ones would leave most of the 148 SMs idle
+  const int tiles128 = ((M + TC_BLOCK_M - 1) / TC_BLOCK_M) * ((N + 127) / 128) * (split_k > 0 ? split_k : 1);
+  const bool wide = (N > 64) && (tiles128 >= 120);
   const int block_n = wide ? 128 : 64;
-  bool ok;
-  if (!mn_major) {
-    ok = encode_2d(&ta, A, M, K, lda, TC_BLOCK_K, TC_BLOCK_M) && encode_2d(&tb, B, N, K, ldb, TC_BLOCK_K, block_n);
-  } else {
-    ok = encode_2d(&ta, A, K, M, lda, 64, TC_BLOCK_K) && encode_2d(&tb, B, K, N, ldb, 64, TC_BLOCK_K);
-  }
-  if (!ok) return cudaErrorInvalidValue;
-  if (!mn_major) {
-    return wide ? launch_tc<128, 4, false>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, st)
-                : launch_tc<64, 4, false>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, st);
-  }
-  return wide ? launch_tc<128, 4, true>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, st)
-              : launch_tc<64, 4, true>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, st);
+  const bool ok_a = a_mn ? encode_2d(&ta, A, K, M, lda, 64, TC_BLOCK_K) : encode_2d(&ta, A, M, K, lda, TC_BLOCK_K, TC_BLOCK_M);
+  const bool ok_b = b_mn ? encode_2d(&tb, B, K, N, ldb, 64, TC_BLOCK_K) : encode_2d(&tb, B, N, K, ldb, TC_BLOCK_K, block_n);
+  if (!ok_a || !ok_b) return cudaErrorInvalidValue;
+#define REPPO_TC_DISPATCH(AMN, BMN)                                                                           \
+  return wide ? launch_tc<128, 4, AMN, BMN>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, st)                 \
+              : launch_tc<64, 4, AMN, BMN>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, st)
+  if (!a_mn && !b_mn) { REPPO_TC_DISPATCH(false, false); }
+  if (!a_mn && b_mn) { REPPO_TC_DISPATCH(false, true); }
+  REPPO_TC_DISPATCH(true, true);
+#undef REPPO_TC_DISPATCH
 }
 
 }  // namespace reppo

@@ -47,8 +47,8 @@ cudaError_t launch_td_lambda(const float* sr, const float* val, const float* don
 cudaError_t launch_gemm_f32(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                             float* C, int ldc, const float* bias, int mode, int split_k, cudaStream_t st);
 // tcgen05 GEMM on bf16 operands (gemm_bf16_tc.cu); see the file header for the operand arrangements
-cudaError_t launch_gemm_bf16_tc(bool mn_major, int M, int N, int K, const void* A, int lda, const void* B, int ldb, float* C,
-                                int ldc, const float* bias, int mode, int split_k, cudaStream_t st);
+cudaError_t launch_gemm_bf16_tc(bool a_mn, bool b_mn, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
+                                float* C, int ldc, const float* bias, int mode, int split_k, cudaStream_t st);
 // fp32 -> bf16 copies: plain (row-padded) and, for weights, the [out,in] matrix plus its transpose
 struct PackEntry { const float* w; void* wb; void* wtb; int out, in, ld_b, ld_t; };
 constexpr int kMaxPack = 16;
@@ -63,7 +63,7 @@ cudaError_t launch_norm_act_fwd(int norm, const float* z, const float* gamma, co
                                 float eps, float* x, float* rstd, float* mean, void* x_h, int ldh, cudaStream_t st);
 cudaError_t launch_norm_act_bwd(int norm, const float* dx, const float* z, const float* gamma, const float* beta,
                                 const float* rstd, const float* mean, int rows, int H, float* dz, float* dgamma,
-                                float* dbeta, void* dz_h, int ldh, cudaStream_t st);
+                                float* dbeta, float* dbias, void* dz_h, int ldh, cudaStream_t st);
 
 cudaError_t launch_critic_ce(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, const float* target,
                              const float* truncated, const int* idx, int rows, float inv_rows, int no_mask, float* dlogits,
@@ -72,9 +72,10 @@ cudaError_t launch_critic_aux(const float* pred, int P, int H, int reward_head, 
                               const float* reward, const float* done, const float* truncated, const int* idx, int rows,
                               float inv_rows, int no_mask, float aux_mult, float* dpred, float* metrics, void* dp_h, int ldh,
                               cudaStream_t st);
-cudaError_t launch_actor_sample(const float* out, const float* out_old, const float* eps_pi, const float* eps_kl, int rows,
-                                int A, int kl_samples, const ActorConsts& ac, float* act_out, int act_ld, float* logp,
-                                float* kl, float* gmu, float* gsig, void* act_h, int act_ldh, cudaStream_t st);
+cudaError_t launch_actor_sample(const float* out, const float* out_old, const int* old_idx, const float* eps_pi,
+                                const float* eps_kl, int rows, int A, int kl_samples, const ActorConsts& ac, float* act_out,
+                                int act_ld, float* logp, float* kl, float* gmu, float* gsig, void* act_h, int act_ldh,
+                                cudaStream_t st);
 cudaError_t launch_actor_q(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, const float* kl, int rows,
                            float inv_rows, int kl_mode, float kl_bound, float* q_out, float* dlogits, void* dl_h, int ldh,
                            cudaStream_t st);
@@ -87,8 +88,11 @@ cudaError_t launch_value_head(const float* head_out, int ld, const float* zero_d
                               float* value, float* logits, cudaStream_t st);
 cudaError_t launch_mean_std(const float* out, int rows, int A, float min_std, float* mean, float* std, cudaStream_t st);
 
+// bf16 shadows of the weight matrices, refreshed by the Adam kernel itself (REPPO_GEMM_BF16)
+struct ShadowEntry { long long start, end; int in, ld; void* dst; };
+struct ShadowTable { int n; ShadowEntry e[kMaxPack]; };
 cudaError_t launch_clip_adam(float* p, const float* g, float* m, float* v, long long n, int* step, float* partials,
-                             const AdamConsts& c, float* grad_norm_out, cudaStream_t st);
+                             const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out, cudaStream_t st);
 cudaError_t launch_metrics_mean(const float* step_metrics, int first, int count, int nm, float* out, cudaStream_t st);
 cudaError_t launch_metrics_init(float* m, uint32_t mask, cudaStream_t st);
 

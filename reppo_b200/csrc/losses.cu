@@ -189,35 +189,42 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
 // -------------------------------------------------------------------------------------------------
 REPPO_DEVINL float fldj_(float x) { return 2.f * (kLog2 - x - softplusf_(-2.f * x)); }
 
-__global__ void __launch_bounds__(128)
-actor_sample_kernel(const float* __restrict__ out, const float* __restrict__ out_old, const float* __restrict__ eps_pi,
-                    const float* __restrict__ eps_kl, int rows, int A, int kl_samples, ActorConsts ac,
-                    float* __restrict__ act_out, int act_ld, float* __restrict__ logp_out, float* __restrict__ kl_out,
-                    float* __restrict__ gmu_kl, float* __restrict__ gsig_kl, __nv_bfloat16* __restrict__ act_h, int act_ldh) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= rows) return;
-  const float* o = out + static_cast<size_t>(row) * 2 * A;
-  const float* oo = out_old + static_cast<size_t>(row) * 2 * A;
+// one thread per (row, action dim); the A per-dimension partial sums of a row meet in shared memory
+__global__ void __launch_bounds__(256)
+actor_sample_kernel(const float* __restrict__ out, const float* __restrict__ out_old, const int* __restrict__ old_idx,
+                    const float* __restrict__ eps_pi, const float* __restrict__ eps_kl, int rows, int A, int kl_samples,
+                    ActorConsts ac, float* __restrict__ act_out, int act_ld, float* __restrict__ logp_out,
+                    float* __restrict__ kl_out, float* __restrict__ gmu_kl, float* __restrict__ gsig_kl,
+                    __nv_bfloat16* __restrict__ act_h, int act_ldh) {
+  __shared__ float s_logp[256], s_old[256], s_new[256];
+  const int rows_per_block = blockDim.x / A;
+  const int rl = threadIdx.x / A, k = threadIdx.x - rl * A;
+  const int row = blockIdx.x * rows_per_block + rl;
+  const bool active = (rl < rows_per_block) && (row < rows);
   float logp = 0.f, lp_old = 0.f, lp_new = 0.f;
-  for (int k = 0; k < A; ++k) {
+  if (active) {
+    const float* o = out + static_cast<size_t>(row) * 2 * A;
+    // behaviour-policy outputs: either this minibatch's rows, or rows of a whole-batch table gathered by old_idx
+    const float* oo = out_old + static_cast<size_t>(old_idx ? old_idx[row] : row) * 2 * A;
     const float mu = o[k], sig = expf(o[A + k]) + ac.min_std;
     const float e = eps_pi[static_cast<size_t>(row) * A + k];
     const float x = mu + sig * e;
     const float a = tanhf(x);
     act_out[static_cast<size_t>(row) * act_ld + k] = a;
     if (act_h != nullptr) act_h[static_cast<size_t>(row) * act_ldh + k] = __float2bfloat16_rn(a);
+    const float log_sig = logf(sig);
     if (ac.clip_policy_sample) {
       // torchrl/reppo.py:301: log_prob(actions.clip(+-c)) -> base.log_prob(atanh(.)) - fldj(atanh(.))
       const float xc = atanhf(fminf(fmaxf(a, -ac.action_clip), ac.action_clip));
       const float zz = (xc - mu) / sig;
-      logp += -0.5f * zz * zz - logf(sig) - kHalfLog2Pi - fldj_(xc);
+      logp = -0.5f * zz * zz - log_sig - kHalfLog2Pi - fldj_(xc);
     } else {
       // distrax sample_and_log_prob: base log-prob at the pre-tanh sample minus fldj
-      logp += -0.5f * e * e - logf(sig) - kHalfLog2Pi - fldj_(x);
+      logp = -0.5f * e * e - log_sig - kHalfLog2Pi - fldj_(x);
     }
     // forward KL samples from the behaviour policy
     const float mu_o = oo[k], sig_o = expf(oo[A + k]) + ac.min_std;
-    const float log_sig = logf(sig), log_sig_o = logf(sig_o);
+    const float log_sig_o = logf(sig_o);
     const float inv_sig = 1.f / sig;
     float gm = 0.f, gs = 0.f;
     for (int s = 0; s < kl_samples; ++s) {
@@ -240,8 +247,14 @@ actor_sample_kernel(const float* __restrict__ out, const float* __restrict__ out
     gmu_kl[static_cast<size_t>(row) * A + k] = gm * inv_s;
     gsig_kl[static_cast<size_t>(row) * A + k] = gs * inv_s;
   }
-  logp_out[row] = logp;
-  kl_out[row] = (lp_old - lp_new) / static_cast<float>(kl_samples);
+  s_logp[threadIdx.x] = logp; s_old[threadIdx.x] = lp_old; s_new[threadIdx.x] = lp_new;
+  __syncthreads();
+  if (active && k == 0) {
+    float l = 0.f, lo = 0.f, ln = 0.f;
+    for (int j = 0; j < A; ++j) { l += s_logp[threadIdx.x + j]; lo += s_old[threadIdx.x + j]; ln += s_new[threadIdx.x + j]; }
+    logp_out[row] = l;
+    kl_out[row] = (lo - ln) / static_cast<float>(kl_samples);
+  }
 }
 
 // Q_i = softmax(logits_i) . support  and  d loss / d logits = -(w_path_i / rows) * p (s - Q)
@@ -372,12 +385,15 @@ cudaError_t launch_critic_aux(const float* pred, int P, int H, int reward_head, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_actor_sample(const float* out, const float* out_old, const float* eps_pi, const float* eps_kl, int rows,
-                                int A, int kl_samples, const ActorConsts& ac, float* act_out, int act_ld, float* logp,
-                                float* kl, float* gmu, float* gsig, void* act_h, int act_ldh, cudaStream_t st) {
-  actor_sample_kernel<<<(rows + 127) / 128, 128, 0, st>>>(out, out_old, eps_pi, eps_kl, rows, A, kl_samples, ac, act_out,
-                                                            act_ld, logp, kl, gmu, gsig, static_cast<__nv_bfloat16*>(act_h),
-                                                            act_ldh);
+cudaError_t launch_actor_sample(const float* out, const float* out_old, const int* old_idx, const float* eps_pi,
+                                const float* eps_kl, int rows, int A, int kl_samples, const ActorConsts& ac, float* act_out,
+                                int act_ld, float* logp, float* kl, float* gmu, float* gsig, void* act_h, int act_ldh,
+                                cudaStream_t st) {
+  if (A > 256) return cudaErrorInvalidValue;
+  const int rows_per_block = 256 / A;
+  actor_sample_kernel<<<(rows + rows_per_block - 1) / rows_per_block, 256, 0, st>>>(
+      out, out_old, old_idx, eps_pi, eps_kl, rows, A, kl_samples, ac, act_out, act_ld, logp, kl, gmu, gsig,
+      static_cast<__nv_bfloat16*>(act_h), act_ldh);
   return cudaGetLastError();
 }
 

@@ -4,6 +4,8 @@
 // Two launches: (1) per-block partial sums of squares (deterministic, no atomics) + step counter
 // increment; (2) every block re-reduces the <= kMaxPartials partials, derives the clip scale and
 // the bias corrections, and streams its slice: 28 B per parameter (read g,p,m,v; write p,m,v).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -31,7 +33,7 @@ sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
             const float* __restrict__ partials, int num_partials, const int* __restrict__ step, AdamConsts c,
-            float* __restrict__ grad_norm_out) {
+            const ShadowTable sh, float* __restrict__ grad_norm_out) {
   __shared__ float red[32];
   __shared__ float s_scale, s_bc1, s_bc2;
   float s = 0.f;
@@ -53,11 +55,20 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   __syncthreads();
   const float scale = s_scale, bc1 = s_bc1, bc2 = s_bc2;
   const float decay = 1.f - c.lr * c.weight_decay;
-  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+  auto upd = [&](float& pp, float gg, float& mm, float& vv, long long idx) {
     gg *= scale;
     mm = c.b1 * mm + (1.f - c.b1) * gg;
     vv = c.b2 * vv + (1.f - c.b2) * gg * gg;
     pp = pp * decay - c.lr * (mm / bc1) / (sqrtf(vv / bc2) + c.eps);
+    // re-round the updated master weight into the bf16 operand shadow W[out, ld] of the tcgen05 GEMMs
+    for (int t = 0; t < sh.n; ++t) {
+      if (idx >= sh.e[t].start && idx < sh.e[t].end) {
+        const int off = static_cast<int>(idx - sh.e[t].start);
+        const int r = off / sh.e[t].in, col = off - r * sh.e[t].in;
+        static_cast<__nv_bfloat16*>(sh.e[t].dst)[static_cast<size_t>(r) * sh.e[t].ld + col] = __float2bfloat16_rn(pp);
+        break;
+      }
+    }
   };
   const long long n4 = n >> 2;
   float4* p4 = reinterpret_cast<float4*>(p);
@@ -68,23 +79,26 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float4 pp = p4[i], mm = m4[i], vv = v4[i];
     const float4 gg = g4[i];
-    upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+    upd(pp.x, gg.x, mm.x, vv.x, 4 * i); upd(pp.y, gg.y, mm.y, vv.y, 4 * i + 1); upd(pp.z, gg.z, mm.z, vv.z, 4 * i + 2);
+    upd(pp.w, gg.w, mm.w, vv.w, 4 * i + 3);
     p4[i] = pp; m4[i] = mm; v4[i] = vv;
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long long i = (n4 << 2) + threadIdx.x;
-    upd(p[i], g[i], m[i], v[i]);
+    upd(p[i], g[i], m[i], v[i], i);
   }
 }
 
 cudaError_t launch_clip_adam(float* p, const float* g, float* m, float* v, long long n, int* step, float* partials,
-                             const AdamConsts& c, float* grad_norm_out, cudaStream_t st) {
+                             const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   const long long want = (n / 4 + 255) / 256;
   int blocks = static_cast<int>(want < kMaxPartials ? want : kMaxPartials);
   if (blocks < 1) blocks = 1;
   sumsq_partial_kernel<<<blocks, 256, 0, st>>>(g, n, partials, step);
-  adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, partials, blocks, step, c, grad_norm_out);
+  ShadowTable sh{};
+  if (shadow != nullptr) sh = *shadow;
+  adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, partials, blocks, step, c, sh, grad_norm_out);
   return cudaGetLastError();
 }
 

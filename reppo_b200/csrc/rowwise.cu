@@ -3,15 +3,30 @@
 //   reference: FCNN.__call__ src/networks/jax_models.py:109-124 (nnx.RMSNorm eps 1e-6, swish),
 //              normed_activation_layer src/networks/torch_models.py:71-79 (nn.RMSNorm eps=finfo.eps),
 //              LayerNorm variant src/reppo_mj_playground.py:63-74 (flax "fast variance", eps 1e-6).
-// One warp owns one row; lanes stride the feature dimension (coalesced 128 B per access).
+// One warp owns one row.  Fast path (H a multiple of 128, H <= 1024): the whole row lives in
+// registers as VPL float4 per lane, every global access is a 512 B warp-contiguous segment and all
+// loads of a row are issued before the first use (HBM/L2-latency bound otherwise: these kernels
+// move 4-8 MB per launch).  Generic path: any H <= 2048, scalar strided loops.
+// The backward also produces the per-column reductions that autodiff needs from the same rows:
+// d gamma (/ d beta) of the norm and d bias of the Linear that feeds it (= column sum of dz), so no
+// separate column-sum pass runs over dz.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
 
 namespace reppo {
 
-// out[r, :] = [ a[idx[r], 0:da] | b[idx2 ? r : idx[r], 0:db] ]   (idx may be NULL = identity)
+REPPO_DEVINL void store_bf16x4(__nv_bfloat16* p, float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&lo);
+  u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// out[r, :] = [ a[idx[r], 0:da] | b[(b_is_local ? r : idx[r]), 0:db] ]   (idx may be NULL = identity)
 __global__ void gather_concat_kernel(const float* __restrict__ a, int da, const float* __restrict__ b, int db,
                                      const int* __restrict__ idx, int b_is_local, int rows, float* __restrict__ out,
                                      int out_ld, __nv_bfloat16* __restrict__ out_h, int out_ldh) {
@@ -43,7 +58,8 @@ cudaError_t launch_gather_concat(const float* a, int da, const float* b, int db,
 
 // ------------------------------------------------------------------------------------------------
 // forward: x = swish( norm(z) )      norm: none | rms (z * rsqrt(mean z^2 + eps) * g) | layer
-// saves rstd (and mean for layer norm) per row for the backward.
+// saves rstd (and mean for layer norm) per row for the backward.  x (fp32) and x_h (bf16) are both
+// optional outputs.
 // ------------------------------------------------------------------------------------------------
 template <int NORM>
 __global__ void __launch_bounds__(256)
@@ -54,7 +70,6 @@ norm_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float* zr = z + static_cast<size_t>(row) * H;
-  float* xr = x + static_cast<size_t>(row) * H;
   float rstd = 1.f, mean = 0.f;
   if (NORM != NORM_NONE) {
     float s1 = 0.f, s2 = 0.f;
@@ -74,31 +89,96 @@ norm_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma
     if (NORM == NORM_RMS) y = y * rstd * gamma[c];
     else if (NORM == NORM_LAYER) y = (y - mean) * rstd * gamma[c] + beta[c];
     const float o = swishf_(y);
-    xr[c] = o;
+    if (x != nullptr) x[static_cast<size_t>(row) * H + c] = o;
     if (x_h != nullptr) x_h[static_cast<size_t>(row) * ldh + c] = __float2bfloat16_rn(o);
   }
+}
+
+template <int NORM, int VPL>
+__global__ void __launch_bounds__(256)
+norm_act_fwd_vec_kernel(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        int rows, float eps, float* __restrict__ x, float* __restrict__ rstd_out,
+                        float* __restrict__ mean_out, __nv_bfloat16* __restrict__ x_h, int ldh) {
+  constexpr int H = 128 * VPL;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* zr = reinterpret_cast<const float4*>(z + static_cast<size_t>(row) * H);
+  float4 v[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) v[i] = zr[lane + 32 * i];
+  float rstd = 1.f, mean = 0.f;
+  if (NORM != NORM_NONE) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      s1 += v[i].x + v[i].y + v[i].z + v[i].w;
+      s2 += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (NORM == NORM_RMS) {
+      rstd = rsqrtf(s2 / H + eps);
+    } else {
+      mean = s1 / H;
+      rstd = rsqrtf(s2 / H - mean * mean + eps);
+    }
+    if (lane == 0) { rstd_out[row] = rstd; if (NORM == NORM_LAYER) mean_out[row] = mean; }
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    float y[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    if (NORM != NORM_NONE) {
+      // gamma / beta live in the flat parameter arena: only 4-byte aligned
+      const int cg = 4 * (lane + 32 * i);
+      const float gg[4] = {gamma[cg], gamma[cg + 1], gamma[cg + 2], gamma[cg + 3]};
+      float bb[4] = {0.f, 0.f, 0.f, 0.f};
+      if (NORM == NORM_LAYER) { bb[0] = beta[cg]; bb[1] = beta[cg + 1]; bb[2] = beta[cg + 2]; bb[3] = beta[cg + 3]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] = (NORM == NORM_RMS) ? y[j] * rstd * gg[j] : (y[j] - mean) * rstd * gg[j] + bb[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = swishf_(y[j]);
+    const int c = 4 * (lane + 32 * i);
+    if (x != nullptr) reinterpret_cast<float4*>(x + static_cast<size_t>(row) * H)[lane + 32 * i] = make_float4(y[0], y[1], y[2], y[3]);
+    if (x_h != nullptr) store_bf16x4(x_h + static_cast<size_t>(row) * ldh + c, y[0], y[1], y[2], y[3]);
+  }
+}
+
+template <int NORM>
+static void launch_fwd_norm(const float* z, const float* gamma, const float* beta, int rows, int H, float eps, float* x,
+                            float* rstd, float* mean, __nv_bfloat16* xh, int ldh, cudaStream_t st) {
+  const int wpb = 8, grid = (rows + wpb - 1) / wpb;
+  const bool vec = (H % 128 == 0) && H <= 1024 && (ldh % 4 == 0) && getenv("REPPO_NO_VEC") == nullptr;
+#define REPPO_FWD_VEC(V) norm_act_fwd_vec_kernel<NORM, V><<<grid, wpb * 32, 0, st>>>(z, gamma, beta, rows, eps, x, rstd, mean, xh, ldh)
+  if (vec && H == 128) REPPO_FWD_VEC(1);
+  else if (vec && H == 256) REPPO_FWD_VEC(2);
+  else if (vec && H == 384) REPPO_FWD_VEC(3);
+  else if (vec && H == 512) REPPO_FWD_VEC(4);
+  else if (vec && H == 768) REPPO_FWD_VEC(6);
+  else if (vec && H == 1024) REPPO_FWD_VEC(8);
+  else norm_act_fwd_kernel<NORM><<<grid, wpb * 32, 0, st>>>(z, gamma, beta, rows, H, eps, x, rstd, mean, xh, ldh);
+#undef REPPO_FWD_VEC
 }
 
 cudaError_t launch_norm_act_fwd(int norm, const float* z, const float* gamma, const float* beta, int rows, int H,
                                 float eps, float* x, float* rstd, float* mean, void* x_h, int ldh, cudaStream_t st) {
   __nv_bfloat16* xh = static_cast<__nv_bfloat16*>(x_h);
   if (rows <= 0) return cudaSuccess;
-  const int wpb = 8;
-  const int grid = (rows + wpb - 1) / wpb;
-  if (norm == NORM_NONE) norm_act_fwd_kernel<NORM_NONE><<<grid, wpb * 32, 0, st>>>(z, gamma, beta, rows, H, eps, x, rstd, mean, xh, ldh);
-  else if (norm == NORM_RMS) norm_act_fwd_kernel<NORM_RMS><<<grid, wpb * 32, 0, st>>>(z, gamma, beta, rows, H, eps, x, rstd, mean, xh, ldh);
-  else norm_act_fwd_kernel<NORM_LAYER><<<grid, wpb * 32, 0, st>>>(z, gamma, beta, rows, H, eps, x, rstd, mean, xh, ldh);
+  if (norm == NORM_NONE) launch_fwd_norm<NORM_NONE>(z, gamma, beta, rows, H, eps, x, rstd, mean, xh, ldh, st);
+  else if (norm == NORM_RMS) launch_fwd_norm<NORM_RMS>(z, gamma, beta, rows, H, eps, x, rstd, mean, xh, ldh, st);
+  else launch_fwd_norm<NORM_LAYER>(z, gamma, beta, rows, H, eps, x, rstd, mean, xh, ldh, st);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: given dx = dL/d swish(y), y = norm(z): dz, and dgamma / dbeta accumulated with atomics
-// (the gradient arena is zeroed at the start of a step).
+// backward: given dx = dL/d swish(y), y = norm(z): dz, plus (accumulated with atomics into the zeroed
+// gradient arena) d gamma / d beta of the norm and d bias = column sums of dz.
+//   none : dz = dx * swish'(z)
 //   rms  : zh = z*rstd;           dzh = dy*g;  dz = rstd * (dzh - zh * mean(dzh*zh))
 //   layer: zh = (z-mean)*rstd;    dz = rstd * (dzh - mean(dzh) - zh * mean(dzh*zh))
-// Each block walks ROWS_PER_BLOCK rows, 8 warps; per-column partial sums of dgamma/dbeta stay in
-// registers of the lane that owns the column, are combined across the block's warps in shared
-// memory and leave as one atomicAdd per column per block.
+// Each block walks rows_per_block rows with 8 warps; the per-column partial sums stay in registers
+// of the lane that owns the column, are combined across the block's warps in shared memory and
+// leave as one atomicAdd per column per block.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxColsPerLane = 64;  // H <= 2048
 
@@ -107,100 +187,212 @@ __global__ void __launch_bounds__(256)
 norm_act_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ z, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ rstd_in,
                     const float* __restrict__ mean_in, int rows, int H, int rows_per_block, float* __restrict__ dz,
-                    float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dz_h, int ldh) {
-  extern __shared__ float sm[];  // [2][H]
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                    __nv_bfloat16* __restrict__ dz_h, int ldh) {
+  extern __shared__ float sm[];  // [3][H]: dgamma, dbeta, dbias
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(rows, r0 + rows_per_block);
   const int cpl = (H + 31) / 32;
 
-  if (NORM != NORM_NONE) {
-    for (int c = threadIdx.x; c < 2 * H; c += blockDim.x) sm[c] = 0.f;
-    __syncthreads();
-  }
-  float pg[kMaxColsPerLane / 4], pb[kMaxColsPerLane / 4];  // flushed to smem every 16 columns-per-lane chunk
+  for (int c = threadIdx.x; c < 3 * H; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  float pg[16], pb[16], pd[16];
   // To keep register use bounded for large H the column range is processed in chunks of 16 per lane.
   for (int cbase = 0; cbase < cpl; cbase += 16) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { pg[j] = 0.f; pb[j] = 0.f; }
+    for (int j = 0; j < 16; ++j) { pg[j] = 0.f; pb[j] = 0.f; pd[j] = 0.f; }
     for (int row = r0 + warp; row < r1; row += nwarp) {
       const float* zr = z + static_cast<size_t>(row) * H;
       const float* dxr = dx + static_cast<size_t>(row) * H;
-      float* dzr = dz + static_cast<size_t>(row) * H;
-      if (NORM == NORM_NONE) {
-        if (cbase == 0)
-          for (int c = lane; c < H; c += 32) {
-            const float o = dxr[c] * swish_grad_(zr[c]);
-            dzr[c] = o;
-            if (dz_h != nullptr) dz_h[static_cast<size_t>(row) * ldh + c] = __float2bfloat16_rn(o);
-          }
-        continue;
-      }
-      const float rstd = rstd_in[row];
-      const float mean = (NORM == NORM_LAYER) ? mean_in[row] : 0.f;
-      // pass 1 (whole row): m1 = mean(dzh), m2 = mean(dzh*zh)
-      float s1 = 0.f, s2 = 0.f;
-      for (int c = lane; c < H; c += 32) {
-        const float zh = (zr[c] - mean) * rstd;
-        const float y = (NORM == NORM_LAYER) ? zh * gamma[c] + beta[c] : zh * gamma[c];
-        const float dy = dxr[c] * swish_grad_(y);
-        const float dzh = dy * gamma[c];
-        s1 += dzh; s2 += dzh * zh;
-      }
-      s1 = warp_sum(s1) / H; s2 = warp_sum(s2) / H;
-      if (NORM == NORM_RMS) s1 = 0.f;
-      // pass 2 (this column chunk): dz, dgamma, dbeta
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int c = lane + 32 * (cbase + j);
-        if (c < H) {
+      float rstd = 1.f, mean = 0.f, s1 = 0.f, s2 = 0.f;
+      if (NORM != NORM_NONE) {
+        rstd = rstd_in[row];
+        mean = (NORM == NORM_LAYER) ? mean_in[row] : 0.f;
+        // pass 1 (whole row): m1 = mean(dzh), m2 = mean(dzh*zh)
+        for (int c = lane; c < H; c += 32) {
           const float zh = (zr[c] - mean) * rstd;
           const float y = (NORM == NORM_LAYER) ? zh * gamma[c] + beta[c] : zh * gamma[c];
           const float dy = dxr[c] * swish_grad_(y);
           const float dzh = dy * gamma[c];
-          const float o = rstd * (dzh - s1 - zh * s2);
-          dzr[c] = o;
-          if (dz_h != nullptr) dz_h[static_cast<size_t>(row) * ldh + c] = __float2bfloat16_rn(o);
-          pg[j] += dy * zh;
-          pb[j] += dy;
+          s1 += dzh; s2 += dzh * zh;
         }
+        s1 = warp_sum(s1) / H; s2 = warp_sum(s2) / H;
+        if (NORM == NORM_RMS) s1 = 0.f;
       }
-    }
-    if (NORM != NORM_NONE) {
+      // pass 2 (this column chunk): dz and the column partial sums
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int c = lane + 32 * (cbase + j);
         if (c < H) {
-          atomicAdd(&sm[c], pg[j]);
-          if (NORM == NORM_LAYER) atomicAdd(&sm[H + c], pb[j]);
+          float o;
+          if (NORM == NORM_NONE) {
+            o = dxr[c] * swish_grad_(zr[c]);
+          } else {
+            const float zh = (zr[c] - mean) * rstd;
+            const float y = (NORM == NORM_LAYER) ? zh * gamma[c] + beta[c] : zh * gamma[c];
+            const float dy = dxr[c] * swish_grad_(y);
+            const float dzh = dy * gamma[c];
+            o = rstd * (dzh - s1 - zh * s2);
+            pg[j] += dy * zh;
+            pb[j] += dy;
+          }
+          pd[j] += o;
+          if (dz != nullptr) dz[static_cast<size_t>(row) * H + c] = o;
+          if (dz_h != nullptr) dz_h[static_cast<size_t>(row) * ldh + c] = __float2bfloat16_rn(o);
         }
       }
     }
-  }
-  if (NORM != NORM_NONE && dgamma != nullptr) {
-    __syncthreads();
-    for (int c = threadIdx.x; c < H; c += blockDim.x) {
-      atomicAdd(dgamma + c, sm[c]);
-      if (NORM == NORM_LAYER) atomicAdd(dbeta + c, sm[H + c]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = lane + 32 * (cbase + j);
+      if (c < H) {
+        if (NORM != NORM_NONE && dgamma != nullptr) atomicAdd(&sm[c], pg[j]);
+        if (NORM == NORM_LAYER && dbeta != nullptr) atomicAdd(&sm[H + c], pb[j]);
+        if (dbias != nullptr) atomicAdd(&sm[2 * H + c], pd[j]);
+      }
     }
   }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    if (NORM != NORM_NONE && dgamma != nullptr) atomicAdd(dgamma + c, sm[c]);
+    if (NORM == NORM_LAYER && dbeta != nullptr) atomicAdd(dbeta + c, sm[H + c]);
+    if (dbias != nullptr) atomicAdd(dbias + c, sm[2 * H + c]);
+  }
+}
+
+template <int NORM, int VPL>
+__global__ void __launch_bounds__(256)
+norm_act_bwd_vec_kernel(const float* __restrict__ dx, const float* __restrict__ z, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, const float* __restrict__ rstd_in,
+                        const float* __restrict__ mean_in, int rows, int rows_per_block, float* __restrict__ dz,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                        __nv_bfloat16* __restrict__ dz_h, int ldh) {
+  constexpr int H = 128 * VPL;
+  __shared__ float sm[3 * H];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  for (int c = threadIdx.x; c < 3 * H; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+
+  float g[VPL][4], b[VPL][4];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { g[i][j] = 1.f; b[i][j] = 0.f; }
+    const int cg = 4 * (lane + 32 * i);  // gamma / beta: flat parameter arena, only 4-byte aligned
+    if (NORM != NORM_NONE) { g[i][0] = gamma[cg]; g[i][1] = gamma[cg + 1]; g[i][2] = gamma[cg + 2]; g[i][3] = gamma[cg + 3]; }
+    if (NORM == NORM_LAYER) { b[i][0] = beta[cg]; b[i][1] = beta[cg + 1]; b[i][2] = beta[cg + 2]; b[i][3] = beta[cg + 3]; }
+  }
+  float pg[VPL][4], pb[VPL][4], pd[VPL][4];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { pg[i][j] = 0.f; pb[i][j] = 0.f; pd[i][j] = 0.f; }
+
+  for (int row = r0 + warp; row < r1; row += nwarp) {
+    const float4* zr = reinterpret_cast<const float4*>(z + static_cast<size_t>(row) * H);
+    const float4* dxr = reinterpret_cast<const float4*>(dx + static_cast<size_t>(row) * H);
+    float4 zv[VPL], dv[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) { zv[i] = zr[lane + 32 * i]; dv[i] = dxr[lane + 32 * i]; }
+    float rstd = 1.f, mean = 0.f;
+    if (NORM != NORM_NONE) { rstd = rstd_in[row]; if (NORM == NORM_LAYER) mean = mean_in[row]; }
+    float zh[VPL][4], dy[VPL][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float zz[4] = {zv[i].x, zv[i].y, zv[i].z, zv[i].w};
+      const float dd[4] = {dv[i].x, dv[i].y, dv[i].z, dv[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (NORM == NORM_NONE) {
+          zh[i][j] = zz[j];
+          dy[i][j] = dd[j] * swish_grad_(zz[j]);
+        } else {
+          zh[i][j] = (zz[j] - mean) * rstd;
+          const float y = zh[i][j] * g[i][j] + b[i][j];
+          dy[i][j] = dd[j] * swish_grad_(y);
+          const float dzh = dy[i][j] * g[i][j];
+          s1 += dzh; s2 += dzh * zh[i][j];
+        }
+      }
+    }
+    if (NORM != NORM_NONE) {
+      s1 = warp_sum(s1) / H; s2 = warp_sum(s2) / H;
+      if (NORM == NORM_RMS) s1 = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (NORM == NORM_NONE) {
+          o[j] = dy[i][j];
+        } else {
+          o[j] = rstd * (dy[i][j] * g[i][j] - s1 - zh[i][j] * s2);
+          pg[i][j] += dy[i][j] * zh[i][j];
+          pb[i][j] += dy[i][j];
+        }
+        pd[i][j] += o[j];
+      }
+      if (dz != nullptr) reinterpret_cast<float4*>(dz + static_cast<size_t>(row) * H)[lane + 32 * i] = make_float4(o[0], o[1], o[2], o[3]);
+      if (dz_h != nullptr) store_bf16x4(dz_h + static_cast<size_t>(row) * ldh + 4 * (lane + 32 * i), o[0], o[1], o[2], o[3]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 4 * (lane + 32 * i) + j;
+      if (NORM != NORM_NONE && dgamma != nullptr) atomicAdd(&sm[c], pg[i][j]);
+      if (NORM == NORM_LAYER && dbeta != nullptr) atomicAdd(&sm[H + c], pb[i][j]);
+      if (dbias != nullptr) atomicAdd(&sm[2 * H + c], pd[i][j]);
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    if (NORM != NORM_NONE && dgamma != nullptr) atomicAdd(dgamma + c, sm[c]);
+    if (NORM == NORM_LAYER && dbeta != nullptr) atomicAdd(dbeta + c, sm[H + c]);
+    if (dbias != nullptr) atomicAdd(dbias + c, sm[2 * H + c]);
+  }
+}
+
+template <int NORM>
+static cudaError_t launch_bwd_norm(const float* dx, const float* z, const float* gamma, const float* beta, const float* rstd,
+                                   const float* mean, int rows, int H, float* dz, float* dgamma, float* dbeta, float* dbias,
+                                   __nv_bfloat16* dzh, int ldh, cudaStream_t st) {
+  // one block per ~SM: enough parallelism, few enough blocks that the per-block column atomics stay cheap
+  int rows_per_block = 16;
+  while ((rows + rows_per_block - 1) / rows_per_block > 148 * 4 && rows_per_block < 128) rows_per_block *= 2;
+  const int grid = (rows + rows_per_block - 1) / rows_per_block;
+  const bool vec = (H % 128 == 0) && H <= 1024 && (ldh % 4 == 0) && getenv("REPPO_NO_VEC") == nullptr;
+#define REPPO_BWD_VEC(V) \
+  norm_act_bwd_vec_kernel<NORM, V><<<grid, 256, 0, st>>>(dx, z, gamma, beta, rstd, mean, rows, rows_per_block, dz, dgamma, dbeta, dbias, dzh, ldh)
+  if (vec && H == 128) REPPO_BWD_VEC(1);
+  else if (vec && H == 256) REPPO_BWD_VEC(2);
+  else if (vec && H == 384) REPPO_BWD_VEC(3);
+  else if (vec && H == 512) REPPO_BWD_VEC(4);
+  else if (vec && H == 768) REPPO_BWD_VEC(6);
+  else if (vec && H == 1024) REPPO_BWD_VEC(8);
+  else {
+    if (H > 32 * kMaxColsPerLane) return cudaErrorInvalidValue;
+    const size_t smem = 3 * static_cast<size_t>(H) * sizeof(float);
+    norm_act_bwd_kernel<NORM><<<grid, 256, smem, st>>>(dx, z, gamma, beta, rstd, mean, rows, H, rows_per_block, dz, dgamma, dbeta,
+                                                        dbias, dzh, ldh);
+  }
+#undef REPPO_BWD_VEC
+  return cudaGetLastError();
 }
 
 cudaError_t launch_norm_act_bwd(int norm, const float* dx, const float* z, const float* gamma, const float* beta,
                                 const float* rstd, const float* mean, int rows, int H, float* dz, float* dgamma,
-                                float* dbeta, void* dz_h, int ldh, cudaStream_t st) {
+                                float* dbeta, float* dbias, void* dz_h, int ldh, cudaStream_t st) {
   __nv_bfloat16* dzh = static_cast<__nv_bfloat16*>(dz_h);
   if (rows <= 0) return cudaSuccess;
-  if (H > 32 * kMaxColsPerLane) return cudaErrorInvalidValue;
-  // enough blocks to fill the machine, few enough that the per-block atomics stay cheap
-  int rows_per_block = 16;
-  while ((rows + rows_per_block - 1) / rows_per_block > 148 * 4 && rows_per_block < 128) rows_per_block *= 2;
-  const int grid = (rows + rows_per_block - 1) / rows_per_block;
-  const size_t smem = (norm == NORM_NONE) ? 0 : 2 * static_cast<size_t>(H) * sizeof(float);
-  if (norm == NORM_NONE) norm_act_bwd_kernel<NORM_NONE><<<grid, 256, smem, st>>>(dx, z, gamma, beta, rstd, mean, rows, H, rows_per_block, dz, dgamma, dbeta, dzh, ldh);
-  else if (norm == NORM_RMS) norm_act_bwd_kernel<NORM_RMS><<<grid, 256, smem, st>>>(dx, z, gamma, beta, rstd, mean, rows, H, rows_per_block, dz, dgamma, dbeta, dzh, ldh);
-  else norm_act_bwd_kernel<NORM_LAYER><<<grid, 256, smem, st>>>(dx, z, gamma, beta, rstd, mean, rows, H, rows_per_block, dz, dgamma, dbeta, dzh, ldh);
-  return cudaGetLastError();
+  if (norm == NORM_NONE) return launch_bwd_norm<NORM_NONE>(dx, z, gamma, beta, rstd, mean, rows, H, dz, dgamma, dbeta, dbias, dzh, ldh, st);
+  if (norm == NORM_RMS) return launch_bwd_norm<NORM_RMS>(dx, z, gamma, beta, rstd, mean, rows, H, dz, dgamma, dbeta, dbias, dzh, ldh, st);
+  return launch_bwd_norm<NORM_LAYER>(dx, z, gamma, beta, rstd, mean, rows, H, dz, dgamma, dbeta, dbias, dzh, ldh, st);
 }
 
 }  // namespace reppo
