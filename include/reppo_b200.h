@@ -129,6 +129,9 @@ typedef struct reppo_plan {
   int32_t noise_per_minibatch; /* 0: eps_* indexed by epoch only (JAX, above); 1: eps_pi [E, n_mb, mb, A] and
                                   eps_kl [E, n_mb, kl_samples, mb, A] -- fresh draws for every step like
                                   src/torchrl/reppo.py:300,308 */
+  float* old_policy_out;  /* optional scratch [batch.num_rows, 2A]: when given, the behaviour policy (actor_old) is
+                             evaluated ONCE per update on every row instead of once per minibatch step -- the same
+                             values, since actor_old is frozen during the update (src/jaxrl/reppo.py:457-464) */
 } reppo_plan;
 
 /* ---- context ------------------------------------------------------------------------------ */

@@ -62,7 +62,7 @@ class Plan(C.Structure):
     _fields_ = [("num_epochs", C.c_int32), ("num_mini_batches", C.c_int32), ("minibatch", C.c_int32),
                 ("perms", C.c_void_p), ("eps_pi", C.c_void_p), ("eps_kl", C.c_void_p),
                 ("step_metrics", C.c_void_p), ("metrics", C.c_void_p), ("use_graph", C.c_int32),
-                ("noise_per_minibatch", C.c_int32)]
+                ("noise_per_minibatch", C.c_int32), ("old_policy_out", C.c_void_p)]
 
 
 # every symbol include/reppo_b200.h declares: name -> (restype, argtypes)

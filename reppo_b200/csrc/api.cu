@@ -409,14 +409,14 @@ int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
   RET(critic_trunk(c, cp, mb, true, st));
   tw = c->twin(c->dlogits);
   CK(launch_critic_ce(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, b->target, b->truncated, idx, mb, inv, no_mask,
-                      c->dlogits, metrics, tw.p, tw.ld, st));
+                      c->dlogits, metrics, tw.p, tw.ld, cg + c->head.layers.back().b, cg + c->zero_dist_off, st));
   tw = c->twin(c->dpred);
   CK(launch_critic_aux(c->pa.out, c->pred_out, sh.critic_hidden, c->sem.reward_head, c->sem.aux_mask_done, b->next_emb,
                        b->reward, b->done, b->truncated, idx, mb, inv, no_mask, hp->aux_loss_mult, c->dpred, metrics, tw.p,
-                       tw.ld, st));
-  RET(mlp_backward(c, c->head, cp, SLOT_CRITIC, cg, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, cg + c->zero_dist_off,
-                   c->sem.bias_scale, false, st));
-  RET(mlp_backward(c, c->pred, cp, SLOT_CRITIC, cg, c->xs, mb, c->pa, c->dpred, c->dxs, GEMM_ACCUM, nullptr, 0.f, false, st));
+                       tw.ld, cg + c->pred.layers.back().b, st));
+  // the loss kernels already accumulated the bias / zero_dist gradients of the two last layers
+  RET(mlp_backward(c, c->head, cp, SLOT_CRITIC, cg, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, true, st));
+  RET(mlp_backward(c, c->pred, cp, SLOT_CRITIC, cg, c->xs, mb, c->pa, c->dpred, c->dxs, GEMM_ACCUM, nullptr, 0.f, true, st));
   tw = c->twin(c->dfeat);
   // d feat = d swish(feat) * swish'(feat); its column sums are the bias gradient of the encoder's last Linear
   CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden,
@@ -441,8 +441,10 @@ ActorConsts actor_consts(const reppo_ctx* c, const reppo_hyper* hp) {
   return ac;
 }
 
+// old_table: optional [S, 2A] behaviour-policy outputs for every batch row (precomputed once per update)
 int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb,
-                    const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, cudaStream_t st) {
+                    const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, const float* old_table,
+                    cudaStream_t st) {
   RET(check_rows(c, mb));
   if (hp->kl_clip_mode < 0 || hp->kl_clip_mode > 2) return fail(c, REPPO_ERR_INVALID, "unknown actor_kl_clip_mode");
   const reppo_shape& sh = c->shape;
@@ -457,11 +459,12 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
   Twin tw = c->twin(c->xa0);
   CK(launch_gather_concat(b->obs, sh.obs_dim, nullptr, 0, idx, 0, mb, c->xa0, sh.obs_dim, tw.p, tw.ld, st));
   RET(mlp_forward(c, c->actor, ap, SLOT_ACTOR, c->xa0, mb, c->aa, st));
-  RET(mlp_forward(c, c->actor, s->actor_old, SLOT_ACTOR_OLD, c->xa0, mb, c->oa, st));
+  if (old_table == nullptr) RET(mlp_forward(c, c->actor, s->actor_old, SLOT_ACTOR_OLD, c->xa0, mb, c->oa, st));
   const Twin tx0 = c->twin(c->x0);
   CK(launch_gather_concat(b->critic_obs, Dc, nullptr, 0, idx, 0, mb, c->x0, c->K0, tx0.p, tx0.ld, st));
-  CK(launch_actor_sample(c->aa.out, c->oa.out, nullptr, eps_pi, eps_kl, mb, A, sh.kl_samples, ac, c->x0 + Dc, c->K0, c->logp,
-                         c->kl, c->gmu, c->gsig, tx0.p ? tx0.p + Dc : nullptr, tx0.ld, st));
+  CK(launch_actor_sample(c->aa.out, old_table ? old_table : c->oa.out, old_table ? idx : nullptr, eps_pi, eps_kl, mb, A,
+                         sh.kl_samples, ac, c->x0 + Dc, c->K0, c->logp, c->kl, c->gmu, c->gsig, tx0.p ? tx0.p + Dc : nullptr,
+                         tx0.ld, st));
   RET(critic_trunk(c, cp, mb, false, st));
   tw = c->twin(c->dlogits);
   CK(launch_actor_q(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, c->kl, mb, inv, ac.kl_mode, ac.kl_bound, c->q,
@@ -473,8 +476,8 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
   RET(mlp_backward(c, c->feature, cp, SLOT_CRITIC, nullptr, c->x0, mb, c->fa, c->dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, false, st));
   tw = c->twin(c->dout);
   CK(launch_actor_grad(c->aa.out, eps_pi, c->x0 + Dc, c->K0, c->dx0 + Dc, c->K0, c->logp, c->kl, c->q, c->gmu, c->gsig, ap,
-                       mb, A, inv, ac, c->dout, ag, metrics, tw.p, tw.ld, st));
-  RET(mlp_backward(c, c->actor, ap, SLOT_ACTOR, ag, c->xa0, mb, c->aa, c->dout, nullptr, GEMM_STORE, nullptr, 0.f, false, st));
+                       mb, A, inv, ac, c->dout, ag, metrics, tw.p, tw.ld, ag + c->actor.layers.back().b, st));
+  RET(mlp_backward(c, c->actor, ap, SLOT_ACTOR, ag, c->xa0, mb, c->aa, c->dout, nullptr, GEMM_STORE, nullptr, 0.f, true, st));
   return REPPO_OK;
 }
 
@@ -511,8 +514,8 @@ int critic_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
 }
 
 int actor_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb, const float* eps_pi,
-                    const float* eps_kl, const reppo_hyper* hp, float* metrics, cudaStream_t st) {
-  RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, st));
+                    const float* eps_kl, const reppo_hyper* hp, float* metrics, const float* old_table, cudaStream_t st) {
+  RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, old_table, st));
   RET(allreduce_grads(c, s->actor.grads, c->actor_count, st));
   return clip_adam_impl(c, &s->actor, c->actor_count, hp, metrics + M_ACTOR_GRAD_NORM, SLOT_ACTOR, st);
 }
@@ -522,6 +525,17 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
   const int A = c->shape.action_dim, mb = p->minibatch, ks = c->shape.kl_samples;
   const int64_t per_epoch = static_cast<int64_t>(p->num_mini_batches) * mb;
   RET(pack_all(c, s, st));
+  if (p->old_policy_out != nullptr) {
+    // behaviour policy on every batch row, once: max_rows-sized chunks through the actor's forward buffers
+    const int D = c->shape.obs_dim, R = c->shape.max_rows;
+    const Twin tw = c->twin(c->xa0);
+    for (int64_t r0 = 0; r0 < b->num_rows; r0 += R) {
+      const int rows = static_cast<int>(std::min<int64_t>(R, b->num_rows - r0));
+      CK(launch_gather_concat(b->obs + r0 * D, D, nullptr, 0, nullptr, 0, rows, c->xa0, D, tw.p, tw.ld, st));
+      RET(mlp_forward(c, c->actor, s->actor_old, SLOT_ACTOR_OLD, c->xa0, rows, c->oa, st));
+      CK(cudaMemcpyAsync(p->old_policy_out + r0 * 2 * A, c->oa.out, sizeof(float) * rows * 2 * A, cudaMemcpyDeviceToDevice, st));
+    }
+  }
   for (int e = 0; e < p->num_epochs; ++e) {
     for (int j = 0; j < p->num_mini_batches; ++j) {
       const int64_t slot = p->noise_per_minibatch ? static_cast<int64_t>(e) * p->num_mini_batches + j : e;
@@ -531,7 +545,7 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
       const int64_t step = static_cast<int64_t>(e) * p->num_mini_batches + j;
       float* m = p->step_metrics ? p->step_metrics + step * M_NUM : c->scratch_metrics;
       RET(critic_step_impl(c, s, b, idx, mb, hp, m, st));
-      RET(actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, st));
+      RET(actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, p->old_policy_out, st));
     }
   }
   if (p->metrics != nullptr && p->step_metrics != nullptr)
@@ -754,7 +768,7 @@ int reppo_actor_grad(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
                      const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, reppo_stream stream) {
   c->launches = 0;
   RET(pack_all(c, s, static_cast<cudaStream_t>(stream)));
-  return actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, static_cast<cudaStream_t>(stream));
+  return actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, nullptr, static_cast<cudaStream_t>(stream));
 }
 int reppo_critic_step(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int32_t mb,
                       const reppo_hyper* hp, float* metrics, reppo_stream stream) {
@@ -766,7 +780,7 @@ int reppo_actor_step(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
                      const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, reppo_stream stream) {
   c->launches = 0;
   RET(pack_all(c, s, static_cast<cudaStream_t>(stream)));
-  return actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, static_cast<cudaStream_t>(stream));
+  return actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, nullptr, static_cast<cudaStream_t>(stream));
 }
 int reppo_clip_adam(reppo_ctx* c, const reppo_net_state* net, int64_t n, const reppo_hyper* hp, float* gn, reppo_stream stream) {
   c->launches = 0;

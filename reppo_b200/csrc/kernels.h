@@ -67,11 +67,11 @@ cudaError_t launch_norm_act_bwd(int norm, const float* dx, const float* z, const
 
 cudaError_t launch_critic_ce(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, const float* target,
                              const float* truncated, const int* idx, int rows, float inv_rows, int no_mask, float* dlogits,
-                             float* metrics, void* dl_h, int ldh, cudaStream_t st);
+                             float* metrics, void* dl_h, int ldh, float* dbias, float* dzero, cudaStream_t st);
 cudaError_t launch_critic_aux(const float* pred, int P, int H, int reward_head, int mask_done, const float* next_emb,
                               const float* reward, const float* done, const float* truncated, const int* idx, int rows,
                               float inv_rows, int no_mask, float aux_mult, float* dpred, float* metrics, void* dp_h, int ldh,
-                              cudaStream_t st);
+                              float* dbias, cudaStream_t st);
 cudaError_t launch_actor_sample(const float* out, const float* out_old, const int* old_idx, const float* eps_pi,
                                 const float* eps_kl, int rows, int A, int kl_samples, const ActorConsts& ac, float* act_out,
                                 int act_ld, float* logp, float* kl, float* gmu, float* gsig, void* act_h, int act_ldh,
@@ -83,7 +83,7 @@ cudaError_t launch_actor_grad(const float* out, const float* eps_pi, const float
                               int dact_ld, const float* logp, const float* kl, const float* q, const float* gmu,
                               const float* gsig, const float* actor_params, int rows, int A, float inv_rows,
                               const ActorConsts& ac, float* dout, float* actor_grads, float* metrics, void* dout_h, int ldh,
-                              cudaStream_t st);
+                              float* dbias, cudaStream_t st);
 cudaError_t launch_value_head(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, int rows,
                               float* value, float* logits, cudaStream_t st);
 cudaError_t launch_mean_std(const float* out, int rows, int A, float min_std, float* mean, float* std, cudaStream_t st);

@@ -74,19 +74,28 @@ REPPO_DEVINL void block_metric_add(float (&vals)[NM], float* sm /* [8][NM] */, f
   }
 }
 
+constexpr int kLossRowsPerBlock = 8;   // one row per warp: these kernels are latency-bound per row, parallelism wins
+
+// dbias (+)= column sums of dlogits (bias gradient of the head's last Linear); dzero (+)= bias_scale * the same
+// (gradient of zero_dist, which enters the logits as bias_scale * zero_dist).  Both nullable.
 __global__ void __launch_bounds__(256)
 critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __restrict__ zero_dist, HLConsts hl,
                  const float* __restrict__ target, const float* __restrict__ truncated, const int* __restrict__ idx,
                  int rows, float inv_rows, int no_mask, float* __restrict__ dlogits, float* __restrict__ metrics,
-                 __nv_bfloat16* __restrict__ dl_h, int ldh) {
+                 __nv_bfloat16* __restrict__ dl_h, int ldh, float* __restrict__ dbias, float* __restrict__ dzero) {
   __shared__ float sm[8 * 5];
   __shared__ float smax[8], smin[8];
+  __shared__ float scol[8][32 * kMaxBinsPerLane];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row = blockIdx.x * 8 + warp;
   const int B = hl.num_bins;
   float vals[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   float tmax = -INFINITY, tmin = INFINITY;
-  if (row < rows) {
+  float cs[kMaxBinsPerLane];
+#pragma unroll
+  for (int j = 0; j < kMaxBinsPerLane; ++j) cs[j] = 0.f;
+  for (int rr = 0; rr < kLossRowsPerBlock / 8; ++rr) {
+    const int row = blockIdx.x * kLossRowsPerBlock + rr * 8 + warp;
+    if (row >= rows) break;
     const long long src = idx ? idx[row] : row;
     const float tgt = target[src];
     const float mask = no_mask ? 1.f : 1.f - truncated[src];
@@ -117,23 +126,35 @@ critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __rest
       if (c < B) {
         const float o = coef * (sum_tp * sx.p[j] - tp[j]);
         drow[c] = o;
+        cs[j] += o;
         if (dl_h != nullptr) dl_h[static_cast<size_t>(row) * ldh + c] = __float2bfloat16_rn(o);
       }
     }
-    vals[0] = mask * ce * inv_rows;                         // REPPO_M_CRITIC_LOSS (CE part)
-    vals[1] = ce * inv_rows;                                // REPPO_M_CE_MEAN
-    vals[2] = (sx.value - tgt) * (sx.value - tgt) * inv_rows;  // REPPO_M_VALUE_LOSS
-    vals[3] = sx.value * inv_rows;                          // REPPO_M_Q_MEAN
-    vals[4] = tgt * inv_rows;                               // REPPO_M_TARGET_MEAN
-    tmax = tgt; tmin = tgt;
+    vals[0] += mask * ce * inv_rows;                         // REPPO_M_CRITIC_LOSS (CE part)
+    vals[1] += ce * inv_rows;                                // REPPO_M_CE_MEAN
+    vals[2] += (sx.value - tgt) * (sx.value - tgt) * inv_rows;  // REPPO_M_VALUE_LOSS
+    vals[3] += sx.value * inv_rows;                          // REPPO_M_Q_MEAN
+    vals[4] += tgt * inv_rows;                               // REPPO_M_TARGET_MEAN
+    tmax = fmaxf(tmax, tgt); tmin = fminf(tmin, tgt);
   }
   float* dst[5] = {metrics + M_CRITIC_LOSS, metrics + M_CE_MEAN, metrics + M_VALUE_LOSS, metrics + M_Q_MEAN,
                    metrics + M_TARGET_MEAN};
   if (lane == 0) { smax[warp] = tmax; smin[warp] = tmin; }
-  block_metric_add<5>(vals, sm, dst);
+#pragma unroll
+  for (int j = 0; j < kMaxBinsPerLane; ++j) scol[warp][lane + 32 * j] = cs[j];
+  block_metric_add<5>(vals, sm, dst);   // contains the __syncthreads that publishes smax / smin / scol
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; ++w) { tmax = fmaxf(tmax, smax[w]); tmin = fminf(tmin, smin[w]); }
     if (tmax > -INFINITY) { atomic_max_float(metrics + M_TARGET_MAX, tmax); atomic_min_float(metrics + M_TARGET_MIN, tmin); }
+  }
+  if (dbias != nullptr) {
+    for (int c = threadIdx.x; c < B; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += scol[w][c];
+      atomicAdd(dbias + c, t);
+      if (dzero != nullptr) atomicAdd(dzero + c, t * hl.bias_scale);
+    }
   }
 }
 
@@ -143,12 +164,18 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
                   const float* __restrict__ next_emb, const float* __restrict__ reward, const float* __restrict__ done,
                   const float* __restrict__ truncated, const int* __restrict__ idx, int rows, float inv_rows, int no_mask,
                   float aux_mult, float* __restrict__ dpred, float* __restrict__ metrics, __nv_bfloat16* __restrict__ dp_h,
-                  int ldh) {
+                  int ldh, float* __restrict__ dbias) {
   __shared__ float sm[8 * 3];
+  extern __shared__ float scol[];  // [P] column sums of dpred (only when dbias != nullptr)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row = blockIdx.x * 8 + warp;
   float vals[3] = {0.f, 0.f, 0.f};
-  if (row < rows) {
+  if (dbias != nullptr) {
+    for (int c = threadIdx.x; c < P; c += blockDim.x) scol[c] = 0.f;
+    __syncthreads();
+  }
+  for (int rr = 0; rr < kLossRowsPerBlock / 8; ++rr) {
+    const int row = blockIdx.x * kLossRowsPerBlock + rr * 8 + warp;
+    if (row >= rows) break;
     const long long src = idx ? idx[row] : row;
     const float mask = no_mask ? 1.f : 1.f - truncated[src];
     const float nd = mask_done ? 1.f - done[src] : 1.f;
@@ -158,10 +185,12 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
     const int off = reward_head ? 1 : 0;
     const float g = 2.f * mask * nd * aux_mult * inv_rows / static_cast<float>(P);
     float sq = 0.f;
+#pragma unroll 8
     for (int c = lane; c < H; c += 32) {
       const float d = pr[off + c] - ne[c];
       sq += d * d;
       dr[off + c] = g * d;
+      if (dbias != nullptr) atomicAdd(&scol[off + c], g * d);
       if (dp_h != nullptr) dp_h[static_cast<size_t>(row) * ldh + off + c] = __float2bfloat16_rn(g * d);
     }
     float r = 0.f;
@@ -171,17 +200,20 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
         const float d = pr[0] - r;
         sq += d * d;
         dr[0] = g * d;
+        if (dbias != nullptr) atomicAdd(&scol[0], g * d);
         if (dp_h != nullptr) dp_h[static_cast<size_t>(row) * ldh] = __float2bfloat16_rn(g * d);
       }
     }
     sq = warp_sum(sq);
     const float aux = nd * sq / static_cast<float>(P);
-    vals[0] = mask * aux_mult * aux * inv_rows;                    // joins REPPO_M_CRITIC_LOSS
-    vals[1] = (reward_head ? aux : mask * aux) * inv_rows;         // REPPO_M_AUX_MEAN (jax: mean aux; torch: embedding_loss)
-    vals[2] = r * inv_rows;                                        // REPPO_M_REWARD_MEAN
+    vals[0] += mask * aux_mult * aux * inv_rows;                    // joins REPPO_M_CRITIC_LOSS
+    vals[1] += (reward_head ? aux : mask * aux) * inv_rows;         // REPPO_M_AUX_MEAN (jax: mean aux; torch: embedding_loss)
+    vals[2] += r * inv_rows;                                        // REPPO_M_REWARD_MEAN
   }
   float* dst[3] = {metrics + M_CRITIC_LOSS, metrics + M_AUX_MEAN, metrics + M_REWARD_MEAN};
-  block_metric_add<3>(vals, sm, dst);
+  block_metric_add<3>(vals, sm, dst);   // contains a __syncthreads: scol is complete afterwards
+  if (dbias != nullptr)
+    for (int c = threadIdx.x; c < P; c += blockDim.x) atomicAdd(dbias + c, scol[c]);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -290,8 +322,11 @@ actor_grad_kernel(const float* __restrict__ out, const float* __restrict__ eps_p
                   const float* __restrict__ kl_in, const float* __restrict__ q_in, const float* __restrict__ gmu_kl,
                   const float* __restrict__ gsig_kl, const float* __restrict__ actor_params, int rows, int A, float inv_rows,
                   ActorConsts ac, float* __restrict__ dout, float* __restrict__ actor_grads, float* __restrict__ metrics,
-                  __nv_bfloat16* __restrict__ dout_h, int ldh) {
+                  __nv_bfloat16* __restrict__ dout_h, int ldh, float* __restrict__ dbias) {
   __shared__ float red[32];
+  __shared__ float scol[64];  // column sums of dout = bias gradient of the policy's last Linear (2A <= 64)
+  if (threadIdx.x < 64) scol[threadIdx.x] = 0.f;
+  __syncthreads();
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   const float alpha = expf(actor_params[0]), beta = expf(actor_params[1]);
   float v_path = 0.f, v_kl = 0.f, v_ent = 0.f, v_q = 0.f, v_abs = 0.f, v_ent_t = 0.f;
@@ -326,6 +361,7 @@ actor_grad_kernel(const float* __restrict__ out, const float* __restrict__ eps_p
       const float dsig = da * e + g_logp * dlp_sig + g_lpnew * gsig_kl[static_cast<size_t>(row) * A + k];
       d[k] = dmu;
       d[A + k] = dsig * ex;
+
       if (dout_h != nullptr) {
         dout_h[static_cast<size_t>(row) * ldh + k] = __float2bfloat16_rn(dmu);
         dout_h[static_cast<size_t>(row) * ldh + A + k] = __float2bfloat16_rn(dsig * ex);
@@ -363,25 +399,37 @@ actor_grad_kernel(const float* __restrict__ out, const float* __restrict__ eps_p
     atomicAdd(metrics + M_ABS_PRED_ACTION, s_abs);
     if (blockIdx.x == 0) { metrics[M_TEMPERATURE] = alpha; metrics[M_LAGRANGIAN] = beta; }
   }
+  if (dbias != nullptr) {
+    // column sums of dout: warp shuffle per column, one shared atomic per warp, one global atomic per block
+    float* d = dout + static_cast<size_t>(row) * 2 * A;
+    for (int j = 0; j < 2 * A; ++j) {
+      const float v = warp_sum(row < rows ? d[j] : 0.f);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&scol[j], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * A) atomicAdd(dbias + threadIdx.x, scol[threadIdx.x]);
+  }
 }
 
 // ---- launchers -----------------------------------------------------------------------------------
 cudaError_t launch_critic_ce(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, const float* target,
                              const float* truncated, const int* idx, int rows, float inv_rows, int no_mask, float* dlogits,
-                             float* metrics, void* dl_h, int ldh, cudaStream_t st) {
+                             float* metrics, void* dl_h, int ldh, float* dbias, float* dzero, cudaStream_t st) {
   if (hl.num_bins > 32 * kMaxBinsPerLane) return cudaErrorInvalidValue;
-  critic_ce_kernel<<<(rows + 7) / 8, 256, 0, st>>>(head_out, ld, zero_dist, hl, target, truncated, idx, rows, inv_rows,
-                                                     no_mask, dlogits, metrics, static_cast<__nv_bfloat16*>(dl_h), ldh);
+  critic_ce_kernel<<<(rows + kLossRowsPerBlock - 1) / kLossRowsPerBlock, 256, 0, st>>>(
+      head_out, ld, zero_dist, hl, target, truncated, idx, rows, inv_rows, no_mask, dlogits, metrics,
+      static_cast<__nv_bfloat16*>(dl_h), ldh, dbias, dzero);
   return cudaGetLastError();
 }
 
 cudaError_t launch_critic_aux(const float* pred, int P, int H, int reward_head, int mask_done, const float* next_emb,
                               const float* reward, const float* done, const float* truncated, const int* idx, int rows,
                               float inv_rows, int no_mask, float aux_mult, float* dpred, float* metrics, void* dp_h, int ldh,
-                              cudaStream_t st) {
-  critic_aux_kernel<<<(rows + 7) / 8, 256, 0, st>>>(pred, P, H, reward_head, mask_done, next_emb, reward, done, truncated,
-                                                      idx, rows, inv_rows, no_mask, aux_mult, dpred, metrics,
-                                                      static_cast<__nv_bfloat16*>(dp_h), ldh);
+                              float* dbias, cudaStream_t st) {
+  const size_t smem = dbias ? static_cast<size_t>(P) * sizeof(float) : 0;
+  critic_aux_kernel<<<(rows + kLossRowsPerBlock - 1) / kLossRowsPerBlock, 256, smem, st>>>(
+      pred, P, H, reward_head, mask_done, next_emb, reward, done, truncated, idx, rows, inv_rows, no_mask, aux_mult, dpred,
+      metrics, static_cast<__nv_bfloat16*>(dp_h), ldh, dbias);
   return cudaGetLastError();
 }
 
@@ -410,10 +458,11 @@ cudaError_t launch_actor_grad(const float* out, const float* eps_pi, const float
                               int dact_ld, const float* logp, const float* kl, const float* q, const float* gmu,
                               const float* gsig, const float* actor_params, int rows, int A, float inv_rows,
                               const ActorConsts& ac, float* dout, float* actor_grads, float* metrics, void* dout_h, int ldh,
-                              cudaStream_t st) {
+                              float* dbias, cudaStream_t st) {
+  if (dbias != nullptr && 2 * A > 64) return cudaErrorInvalidValue;
   actor_grad_kernel<<<(rows + 127) / 128, 128, 0, st>>>(out, eps_pi, act, act_ld, dact, dact_ld, logp, kl, q, gmu, gsig,
                                                           actor_params, rows, A, inv_rows, ac, dout, actor_grads, metrics,
-                                                          static_cast<__nv_bfloat16*>(dout_h), ldh);
+                                                          static_cast<__nv_bfloat16*>(dout_h), ldh, dbias);
   return cudaGetLastError();
 }
 

@@ -306,8 +306,11 @@ class ReppoEngine:
         if step_metrics is None:
             step_metrics = torch.empty(E * num_mini_batches, L.NUM_METRICS, device=self.device)
         m = self.metrics if metrics is None else metrics
+        S = int(batch.num_rows)
+        if getattr(self, "_old_out", None) is None or self._old_out.shape[0] != S:
+            self._old_out = torch.empty(S, 2 * A, device=self.device, dtype=torch.float32)
         plan = L.Plan(E, num_mini_batches, mb, perms.data_ptr(), eps_pi.data_ptr(), eps_kl.data_ptr(),
-                      step_metrics.data_ptr(), m.data_ptr(), int(use_graph), int(per_mb))
+                      step_metrics.data_ptr(), m.data_ptr(), int(use_graph), int(per_mb), self._old_out.data_ptr())
         st, h = self.c_state(), hp.c_struct()
         L.check(self.lib.reppo_update(self.ctx, C.byref(st), C.byref(batch), C.byref(plan), C.byref(h), self._stream()),
                 self.ctx, "reppo_update")

@@ -419,24 +419,68 @@ def reppo_update(train_state: TrainState, transition: Mapping[str, torch.Tensor]
     mb = S // n_mb
     dev = eng.device
     A, ks = eng.cfg.action_dim, eng.cfg.kl_samples
-    data = make_postprocess_fn(cfg)(train_state, transition)
-    if eng.cfg.semantics == "jax":
+    conv = eng.cfg.semantics
+
+    # Persistent device staging buffers: the rollout is copied INTO them (one async H2D per field from pinned host
+    # memory), so every pointer the engine sees is stable across calls and the captured CUDA graph is replayed
+    # instead of being re-captured.
+    stage = eng.__dict__.setdefault("_stage", {})
+
+    def buf(name, shape, dtype=torch.float32):
+        t = stage.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            stage[name] = t
+        return t
+
+    def put(name, src, shape):
+        dst = buf(name, shape)
+        dst.copy_(src.reshape(shape), non_blocking=True)
+        return dst
+
+    obs = put("obs", transition["observations"], (T, N, eng.cfg.obs_dim))
+    cobs = put("critic_obs", transition["critic_observations"], (T, N, eng._shape.critic_obs_dim))
+    act = put("action", transition["actions"], (T, N, A))
+    soft = put("soft_reward", transition["rewards"], (T, N))
+    nemb = put("next_emb", transition["next_embeddings"], (T, N, eng.cfg.critic_hidden_dim))
+    val = put("value", transition["next_values"], (T, N))
+    done = put("done", transition["dones"], (T, N))
+    trunc = put("truncated", transition["truncations"], (T, N))
+    has = (lambda k: k in transition)
+    raw = put("reward", transition["raw_rewards"], (T, N)) if has("raw_rewards") else (soft if conv == "jax" else None)
+    iw = put("iw", transition["importance_weight"], (T, N)) if (has("importance_weight") and conv == "jax") else None
+    target = buf("target", (T, N))
+    eng.td_lambda(soft, val, done, trunc, iw, float(h.gamma), float(h.lmbda), convention=conv, out=target)
+    if conv == "torch":
+        transition["truncations"][-1] = 1.0  # compute_gve writes this into the caller's batch (src/torchrl/reppo.py:178)
+    flat = {"obs": obs.view(S, -1), "critic_obs": cobs.view(S, -1), "action": act.view(S, -1), "done": done.view(S),
+            "truncated": trunc.view(S), "next_emb": nemb.view(S, -1), "target": target.view(S),
+            "reward": raw.view(S) if raw is not None else None}
+    batch = eng.make_batch(flat)
+    if conv == "jax":
         eng.sync_actor_old()  # actor_target <- actor at the START of learn_step (src/jaxrl/reppo.py:457-464)
+    per_mb = conv == "torch"
+    pbuf = buf("perms", (E, S), torch.int32)
     if perms is None:
-        perms = torch.stack([torch.randperm(S, device=dev, generator=generator) for _ in range(E)])
-    perms = perms.to(device=dev, dtype=torch.int32).contiguous()
-    per_mb = eng.cfg.semantics == "torch"
+        for e in range(E):
+            pbuf[e].copy_(torch.randperm(S, device=dev, generator=generator))
+    else:
+        pbuf.copy_(perms.to(torch.int32), non_blocking=True)
+    e1 = buf("eps_pi", (E, n_mb, mb, A) if per_mb else (E, mb, A))
+    e2 = buf("eps_kl", (E, n_mb, ks, mb, A) if per_mb else (E, ks, mb, A))
     if eps_pi is None:
-        eps_pi = torch.randn((E, n_mb, mb, A) if per_mb else (E, mb, A), device=dev, generator=generator)
+        e1.normal_(generator=generator)
+    else:
+        e1.copy_(eps_pi.reshape(e1.shape), non_blocking=True)
     if eps_kl is None:
-        eps_kl = torch.randn((E, n_mb, ks, mb, A) if per_mb else (E, ks, mb, A), device=dev, generator=generator)
+        e2.normal_(generator=generator)
+    else:
+        e2.copy_(eps_kl.reshape(e2.shape), non_blocking=True)
     b200 = cfg.get("b200", {}) if hasattr(cfg, "get") else {}
     graph = bool(b200.get("use_graph", True)) if use_graph is None else use_graph
-    batch = _mini_batch(eng, data)
     hyp = _hyper(cfg, train_state)
     hyp.world_size = world_size  # data-parallel ranks sharing every minibatch (gradients all-reduced by the engine)
-    m, sm = eng.update(batch, perms, eps_pi.to(dev).float().contiguous(), eps_kl.to(dev).float().contiguous(),
-                       hyp, n_mb, use_graph=graph)
+    m, sm = eng.update(batch, pbuf, e1, e2, hyp, n_mb, use_graph=graph, step_metrics=buf("step_metrics", (E * n_mb, L.NUM_METRICS)))
     eng.sync_actor_old()  # src/torchrl/reppo.py:631-632 (same state as the JAX ordering at the next call)
     if return_device_metrics:
         return m, sm
