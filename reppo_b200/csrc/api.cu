@@ -44,9 +44,11 @@ struct TensorInfo {
   int64_t off;
   int rows, cols;  // cols == 0: vector of `rows`; rows == 0: scalar
 };
-struct Acts {  // saved activations of one MLP evaluation
+struct Acts {  // saved activations of one MLP evaluation + its private backward scratch
   std::vector<float*> z, x, rstd, mean;
+  std::vector<float*> dz;   // gradient w.r.t. z of every hidden layer (own buffer: wgrad reads it concurrently with the chain)
   float* out = nullptr;
+  float* tmp = nullptr;     // dgrad output before the norm backward
 };
 struct Sem {
   float norm_eps, bias_scale, action_clip;
@@ -101,8 +103,9 @@ struct reppo_ctx {
   float *edges_d = nullptr, *support_d = nullptr, *partials = nullptr;
   float *x0 = nullptr, *xs = nullptr, *xa0 = nullptr;
   Acts fa, ha, pa, aa, oa;
-  float *tmpA = nullptr, *tmpB = nullptr, *dxs = nullptr, *dfeat = nullptr, *dlogits = nullptr, *dpred = nullptr,
-        *dout = nullptr, *dx0 = nullptr;
+  float *x0a = nullptr;  // critic input of the ACTOR step ([critic_obs | sampled action]); separate so that it can be
+                         // built while the critic step still reads x0
+  float *dxs = nullptr, *dxs2 = nullptr, *dfeat = nullptr, *dlogits = nullptr, *dpred = nullptr, *dout = nullptr, *dx0 = nullptr;
   float *logp = nullptr, *kl = nullptr, *q = nullptr, *gmu = nullptr, *gsig = nullptr, *scratch_metrics = nullptr;
   std::unordered_map<const float*, Twin> twins;
   uint16_t* shadow_b[NUM_SLOTS] = {nullptr, nullptr, nullptr};
@@ -116,6 +119,12 @@ struct reppo_ctx {
   GraphKey graph_key{};
   bool graph_valid = false;
   int64_t graph_launches = 0;
+  // concurrency: independent branches of a step run on context-owned side streams (captured into the graph as
+  // parallel branches): [0] pred-head branch, [1] weight-gradient GEMMs, [2] actor-only prefix of the actor step
+  bool concurrent = true;
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> events;
+  size_t ev_next = 0;
   // nccl
   NcclApi nccl;
   ncclComm_t comm = nullptr;
@@ -221,13 +230,20 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
     }
     a.out = F(R * out_dim);
   };
+  auto bwd_scratch = [&](Acts& a, const Mlp& m) {
+    a.dz.clear();
+    size_t hmax = 1;
+    for (size_t i = 0; i + 1 < m.layers.size(); ++i) { a.dz.push_back(FT(m.layers[i].out)); hmax = std::max<size_t>(hmax, m.layers[i].out); }
+    a.tmp = F(R * hmax);
+  };
   c->edges_d = F(B + 1); c->support_d = F(B); c->partials = F(kMaxPartials); c->scratch_metrics = F(M_NUM);
   c->x0 = FT(K0); c->xs = FT(H); c->xa0 = FT(D);
   acts(c->fa, c->feature, H); acts(c->ha, c->head, B); acts(c->pa, c->pred, P);
   acts(c->aa, c->actor, 2 * A); acts(c->oa, c->actor, 2 * A);
+  bwd_scratch(c->fa, c->feature); bwd_scratch(c->ha, c->head); bwd_scratch(c->pa, c->pred); bwd_scratch(c->aa, c->actor);
   const size_t maxdim = c->maxdim;
-  c->tmpA = F(R * maxdim); c->tmpB = FT(maxdim);
-  c->dxs = F(R * H); c->dfeat = FT(H); c->dlogits = FT(B); c->dpred = FT(P); c->dout = FT(2 * A);
+  c->x0a = FT(K0);
+  c->dxs = F(R * H); c->dxs2 = F(R * H); c->dfeat = FT(H); c->dlogits = FT(B); c->dpred = FT(P); c->dout = FT(2 * A);
   c->dx0 = F(R * K0);
   c->logp = F(R); c->kl = F(R); c->q = F(R); c->gmu = F(R * A); c->gsig = F(R * A);
   if (c->tc) {
@@ -334,29 +350,56 @@ int mlp_forward(reppo_ctx* c, const Mlp& m, const float* params, int slot, const
 
 // d_out: gradient w.r.t. the MLP output [rows, out_last] (read only).  grads == nullptr: frozen network (dgrad only).
 // dx_in != nullptr: also produce the gradient w.r.t. the MLP input (mode GEMM_STORE / GEMM_ACCUM).
+// `to` waits for everything enqueued so far on `from` (an edge of the step's DAG; captured as a graph dependency)
+int dep(reppo_ctx* c, cudaStream_t from, cudaStream_t to) {
+  if (from == to) return REPPO_OK;
+  cudaEvent_t e = c->events[c->ev_next++ % c->events.size()];
+  cudaError_t r = cudaEventRecord(e, from);
+  if (r == cudaSuccess) r = cudaStreamWaitEvent(to, e, 0);
+  if (r != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("stream dependency: ") + cudaGetErrorString(r));
+  return REPPO_OK;
+}
+
+int ensure_streams(reppo_ctx* c) {
+  if (!c->events.empty()) return REPPO_OK;
+  for (int i = 0; i < 3; ++i)
+    if (cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking) != cudaSuccess)
+      return fail(c, REPPO_ERR_CUDA, "cudaStreamCreate failed");
+  c->events.resize(64);
+  for (auto& e : c->events)
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaEventCreate failed");
+  return REPPO_OK;
+}
+
+// d_out: gradient w.r.t. the MLP output [rows, out_last] (read only).  grads == nullptr: frozen network (dgrad only).
+// dx_in != nullptr: also produce the gradient w.r.t. the MLP input (mode GEMM_STORE / GEMM_ACCUM).
 // last_bias_done: the producer of d_out already accumulated the last layer's bias gradient (column sums of d_out).
+// The dgrad / norm-backward chain runs on `st`; every weight-gradient GEMM only depends on one link of the chain and
+// runs on `wst` (the caller joins `wst` before the optimizer).
 int mlp_backward(reppo_ctx* c, const Mlp& m, const float* params, int slot, float* grads, const float* in, int rows,
                  const Acts& a, const float* d_out, float* dx_in, int dx_mode, float* bias2, float scale2, bool last_bias_done,
-                 cudaStream_t st) {
+                 cudaStream_t st, cudaStream_t wst) {
   const int n = static_cast<int>(m.layers.size());
   const float* d = d_out;
   for (int i = n - 1; i >= 0; --i) {
     const Linear& L = m.layers[i];
     const float* xin = (i == 0) ? in : a.x[i - 1];
     if (grads != nullptr) {
-      RET(linear_wgrad(c, L, d, xin, rows, grads + L.w, st));
+      RET(dep(c, st, wst));
+      RET(linear_wgrad(c, L, d, xin, rows, grads + L.w, wst));
       // hidden layers: the norm backward that produced d accumulated its column sums already
-      if (i == n - 1 && !last_bias_done) CK(launch_colsum(d, rows, L.out, L.out, grads + L.b, bias2, scale2, st));
+      if (i == n - 1 && !last_bias_done) CK(launch_colsum(d, rows, L.out, L.out, grads + L.b, bias2, scale2, wst));
     }
     if (i > 0) {
       const Linear& Lp = m.layers[i - 1];
-      RET(linear_dgrad(c, L, params, slot, d, rows, c->tmpA, GEMM_STORE, st));
-      const Twin tw = c->twin(c->tmpB);
-      CK(launch_norm_act_bwd(m.norm, c->tmpA, a.z[i - 1], Lp.g >= 0 ? params + Lp.g : nullptr,
+      RET(linear_dgrad(c, L, params, slot, d, rows, a.tmp, GEMM_STORE, st));
+      float* dz = a.dz[i - 1];
+      const Twin tw = c->twin(dz);
+      CK(launch_norm_act_bwd(m.norm, a.tmp, nullptr, a.z[i - 1], Lp.g >= 0 ? params + Lp.g : nullptr,
                              Lp.beta >= 0 ? params + Lp.beta : nullptr, a.rstd[i - 1], a.mean[i - 1], rows, L.in,
-                             c->tc ? nullptr : c->tmpB, (grads && Lp.g >= 0) ? grads + Lp.g : nullptr,
+                             c->tc ? nullptr : dz, (grads && Lp.g >= 0) ? grads + Lp.g : nullptr,
                              (grads && Lp.beta >= 0) ? grads + Lp.beta : nullptr, grads ? grads + Lp.b : nullptr, tw.p, tw.ld, st));
-      d = c->tmpB;
+      d = dz;
     } else if (dx_in != nullptr) {
       RET(linear_dgrad(c, L, params, slot, d, rows, dx_in, dx_mode, st));
     }
@@ -370,8 +413,8 @@ int check_rows(reppo_ctx* c, int rows) {
   return REPPO_OK;
 }
 
-int critic_trunk(reppo_ctx* c, const float* cp, int rows, bool with_pred, cudaStream_t st) {
-  RET(mlp_forward(c, c->feature, cp, SLOT_CRITIC, c->x0, rows, c->fa, st));
+int critic_trunk(reppo_ctx* c, const float* cp, const float* x0, int rows, bool with_pred, cudaStream_t st) {
+  RET(mlp_forward(c, c->feature, cp, SLOT_CRITIC, x0, rows, c->fa, st));
   const Twin tw = c->twin(c->xs);
   CK(launch_norm_act_fwd(NORM_NONE, c->fa.out, nullptr, nullptr, rows, c->shape.critic_hidden, 0.f, c->tc ? nullptr : c->xs,
                          nullptr, nullptr, tw.p, tw.ld, st));
@@ -402,26 +445,40 @@ int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
   const float inv = inv_rows(hp, mb);
   const int no_mask = (sh.semantics == REPPO_SEM_TORCH && hp->partial_reset) ? 1 : 0;
   if (c->sem.reward_head && b->reward == nullptr) return fail(c, REPPO_ERR_INVALID, "batch.reward is required in JAX semantics");
+  RET(ensure_streams(c));
+  cudaStream_t s1 = c->concurrent ? c->side[0] : st;   // pred-head branch
+  cudaStream_t sw = c->concurrent ? c->side[1] : st;   // weight gradients
+  const int Hc = sh.critic_hidden;
   CK(launch_metrics_init(metrics, kCriticMetricMask, st));
   CK(cudaMemsetAsync(cg, 0, static_cast<size_t>(c->critic_count) * sizeof(float), st));
   Twin tw = c->twin(c->x0);
   CK(launch_gather_concat(b->critic_obs, sh.critic_obs_dim, b->action, sh.action_dim, idx, 0, mb, c->x0, c->K0, tw.p, tw.ld, st));
-  RET(critic_trunk(c, cp, mb, true, st));
+  // encoder, then swish(features) feeds two independent heads
+  RET(mlp_forward(c, c->feature, cp, SLOT_CRITIC, c->x0, mb, c->fa, st));
+  tw = c->twin(c->xs);
+  CK(launch_norm_act_fwd(NORM_NONE, c->fa.out, nullptr, nullptr, mb, Hc, 0.f, c->tc ? nullptr : c->xs, nullptr, nullptr, tw.p, tw.ld, st));
+  RET(dep(c, st, s1));
+  // --- branch s1: prediction head forward, aux loss, backward down to d swish(features)
+  RET(mlp_forward(c, c->pred, cp, SLOT_CRITIC, c->xs, mb, c->pa, s1));
+  tw = c->twin(c->dpred);
+  CK(launch_critic_aux(c->pa.out, c->pred_out, Hc, c->sem.reward_head, c->sem.aux_mask_done, b->next_emb, b->reward, b->done,
+                       b->truncated, idx, mb, inv, no_mask, hp->aux_loss_mult, c->dpred, metrics, tw.p, tw.ld,
+                       cg + c->pred.layers.back().b, s1));
+  RET(mlp_backward(c, c->pred, cp, SLOT_CRITIC, cg, c->xs, mb, c->pa, c->dpred, c->dxs2, GEMM_STORE, nullptr, 0.f, true, s1, sw));
+  // --- main: categorical head forward, HL-Gauss cross-entropy, backward (the loss kernels also accumulate the
+  //     bias / zero_dist gradients of the two last layers)
+  RET(mlp_forward(c, c->head, cp, SLOT_CRITIC, c->xs, mb, c->ha, st));
   tw = c->twin(c->dlogits);
   CK(launch_critic_ce(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, b->target, b->truncated, idx, mb, inv, no_mask,
                       c->dlogits, metrics, tw.p, tw.ld, cg + c->head.layers.back().b, cg + c->zero_dist_off, st));
-  tw = c->twin(c->dpred);
-  CK(launch_critic_aux(c->pa.out, c->pred_out, sh.critic_hidden, c->sem.reward_head, c->sem.aux_mask_done, b->next_emb,
-                       b->reward, b->done, b->truncated, idx, mb, inv, no_mask, hp->aux_loss_mult, c->dpred, metrics, tw.p,
-                       tw.ld, cg + c->pred.layers.back().b, st));
-  // the loss kernels already accumulated the bias / zero_dist gradients of the two last layers
-  RET(mlp_backward(c, c->head, cp, SLOT_CRITIC, cg, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, true, st));
-  RET(mlp_backward(c, c->pred, cp, SLOT_CRITIC, cg, c->xs, mb, c->pa, c->dpred, c->dxs, GEMM_ACCUM, nullptr, 0.f, true, st));
+  RET(mlp_backward(c, c->head, cp, SLOT_CRITIC, cg, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, true, st, sw));
+  RET(dep(c, s1, st));
+  // d feat = (d swish(feat) from both heads) * swish'(feat); its column sums are the bias gradient of the encoder's last Linear
   tw = c->twin(c->dfeat);
-  // d feat = d swish(feat) * swish'(feat); its column sums are the bias gradient of the encoder's last Linear
-  CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden,
+  CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->dxs2, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, Hc,
                          c->tc ? nullptr : c->dfeat, nullptr, nullptr, cg + c->feature.layers.back().b, tw.p, tw.ld, st));
-  RET(mlp_backward(c, c->feature, cp, SLOT_CRITIC, cg, c->x0, mb, c->fa, c->dfeat, nullptr, GEMM_STORE, nullptr, 0.f, true, st));
+  RET(mlp_backward(c, c->feature, cp, SLOT_CRITIC, cg, c->x0, mb, c->fa, c->dfeat, nullptr, GEMM_STORE, nullptr, 0.f, true, st, sw));
+  RET(dep(c, sw, st));
   return REPPO_OK;
 }
 
@@ -444,7 +501,7 @@ ActorConsts actor_consts(const reppo_ctx* c, const reppo_hyper* hp) {
 // old_table: optional [S, 2A] behaviour-policy outputs for every batch row (precomputed once per update)
 int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb,
                     const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, const float* old_table,
-                    cudaStream_t st) {
+                    cudaStream_t prefix_stream, cudaStream_t st) {
   RET(check_rows(c, mb));
   if (hp->kl_clip_mode < 0 || hp->kl_clip_mode > 2) return fail(c, REPPO_ERR_INVALID, "unknown actor_kl_clip_mode");
   const reppo_shape& sh = c->shape;
@@ -454,30 +511,38 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
   float* ag = s->actor.grads;
   const float inv = inv_rows(hp, mb);
   const ActorConsts ac = actor_consts(c, hp);
-  CK(launch_metrics_init(metrics, kActorMetricMask, st));
-  CK(cudaMemsetAsync(ag, 0, static_cast<size_t>(c->actor_count) * sizeof(float), st));
+  RET(ensure_streams(c));
+  cudaStream_t sw = c->concurrent ? c->side[1] : st;
+  // The actor-only prefix (policy forward, sampling, KL statistics) does not depend on the critic update that precedes
+  // it on `st`: when `pre` is a different stream it overlaps the critic step (the caller forked it before that step).
+  cudaStream_t pre = prefix_stream ? prefix_stream : st;
+  CK(launch_metrics_init(metrics, kActorMetricMask, pre));
+  CK(cudaMemsetAsync(ag, 0, static_cast<size_t>(c->actor_count) * sizeof(float), pre));
   Twin tw = c->twin(c->xa0);
-  CK(launch_gather_concat(b->obs, sh.obs_dim, nullptr, 0, idx, 0, mb, c->xa0, sh.obs_dim, tw.p, tw.ld, st));
-  RET(mlp_forward(c, c->actor, ap, SLOT_ACTOR, c->xa0, mb, c->aa, st));
-  if (old_table == nullptr) RET(mlp_forward(c, c->actor, s->actor_old, SLOT_ACTOR_OLD, c->xa0, mb, c->oa, st));
-  const Twin tx0 = c->twin(c->x0);
-  CK(launch_gather_concat(b->critic_obs, Dc, nullptr, 0, idx, 0, mb, c->x0, c->K0, tx0.p, tx0.ld, st));
+  CK(launch_gather_concat(b->obs, sh.obs_dim, nullptr, 0, idx, 0, mb, c->xa0, sh.obs_dim, tw.p, tw.ld, pre));
+  RET(mlp_forward(c, c->actor, ap, SLOT_ACTOR, c->xa0, mb, c->aa, pre));
+  if (old_table == nullptr) RET(mlp_forward(c, c->actor, s->actor_old, SLOT_ACTOR_OLD, c->xa0, mb, c->oa, pre));
+  const Twin tx0 = c->twin(c->x0a);
+  CK(launch_gather_concat(b->critic_obs, Dc, nullptr, 0, idx, 0, mb, c->x0a, c->K0, tx0.p, tx0.ld, pre));
   CK(launch_actor_sample(c->aa.out, old_table ? old_table : c->oa.out, old_table ? idx : nullptr, eps_pi, eps_kl, mb, A,
-                         sh.kl_samples, ac, c->x0 + Dc, c->K0, c->logp, c->kl, c->gmu, c->gsig, tx0.p ? tx0.p + Dc : nullptr,
-                         tx0.ld, st));
-  RET(critic_trunk(c, cp, mb, false, st));
+                         sh.kl_samples, ac, c->x0a + Dc, c->K0, c->logp, c->kl, c->gmu, c->gsig, tx0.p ? tx0.p + Dc : nullptr,
+                         tx0.ld, pre));
+  RET(dep(c, pre, st));
+  // Q(s, a) through the (already updated, frozen) critic and dQ/da
+  RET(critic_trunk(c, cp, c->x0a, mb, false, st));
   tw = c->twin(c->dlogits);
   CK(launch_actor_q(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, c->kl, mb, inv, ac.kl_mode, ac.kl_bound, c->q,
                     c->dlogits, tw.p, tw.ld, st));
-  RET(mlp_backward(c, c->head, cp, SLOT_CRITIC, nullptr, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, false, st));
+  RET(mlp_backward(c, c->head, cp, SLOT_CRITIC, nullptr, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, false, st, st));
   tw = c->twin(c->dfeat);
-  CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden,
+  CK(launch_norm_act_bwd(NORM_NONE, c->dxs, nullptr, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden,
                          c->tc ? nullptr : c->dfeat, nullptr, nullptr, nullptr, tw.p, tw.ld, st));
-  RET(mlp_backward(c, c->feature, cp, SLOT_CRITIC, nullptr, c->x0, mb, c->fa, c->dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, false, st));
+  RET(mlp_backward(c, c->feature, cp, SLOT_CRITIC, nullptr, c->x0a, mb, c->fa, c->dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, false, st, st));
   tw = c->twin(c->dout);
-  CK(launch_actor_grad(c->aa.out, eps_pi, c->x0 + Dc, c->K0, c->dx0 + Dc, c->K0, c->logp, c->kl, c->q, c->gmu, c->gsig, ap,
+  CK(launch_actor_grad(c->aa.out, eps_pi, c->x0a + Dc, c->K0, c->dx0 + Dc, c->K0, c->logp, c->kl, c->q, c->gmu, c->gsig, ap,
                        mb, A, inv, ac, c->dout, ag, metrics, tw.p, tw.ld, ag + c->actor.layers.back().b, st));
-  RET(mlp_backward(c, c->actor, ap, SLOT_ACTOR, ag, c->xa0, mb, c->aa, c->dout, nullptr, GEMM_STORE, nullptr, 0.f, true, st));
+  RET(mlp_backward(c, c->actor, ap, SLOT_ACTOR, ag, c->xa0, mb, c->aa, c->dout, nullptr, GEMM_STORE, nullptr, 0.f, true, st, sw));
+  RET(dep(c, sw, st));
   return REPPO_OK;
 }
 
@@ -514,8 +579,9 @@ int critic_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
 }
 
 int actor_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb, const float* eps_pi,
-                    const float* eps_kl, const reppo_hyper* hp, float* metrics, const float* old_table, cudaStream_t st) {
-  RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, old_table, st));
+                    const float* eps_kl, const reppo_hyper* hp, float* metrics, const float* old_table,
+                    cudaStream_t prefix_stream, cudaStream_t st) {
+  RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, old_table, prefix_stream, st));
   RET(allreduce_grads(c, s->actor.grads, c->actor_count, st));
   return clip_adam_impl(c, &s->actor, c->actor_count, hp, metrics + M_ACTOR_GRAD_NORM, SLOT_ACTOR, st);
 }
@@ -544,8 +610,11 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
       const int32_t* idx = p->perms + e * per_epoch + static_cast<int64_t>(j) * mb;
       const int64_t step = static_cast<int64_t>(e) * p->num_mini_batches + j;
       float* m = p->step_metrics ? p->step_metrics + step * M_NUM : c->scratch_metrics;
+      // the actor-only prefix of this step's actor update is forked here and overlaps the critic update
+      cudaStream_t pre = nullptr;
+      if (c->concurrent) { RET(ensure_streams(c)); pre = c->side[2]; RET(dep(c, st, pre)); }
       RET(critic_step_impl(c, s, b, idx, mb, hp, m, st));
-      RET(actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, p->old_policy_out, st));
+      RET(actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, p->old_policy_out, pre, st));
     }
   }
   if (p->metrics != nullptr && p->step_metrics != nullptr)
@@ -583,6 +652,7 @@ int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
   reppo_ctx* c = new reppo_ctx();
   c->shape = s;
   c->tc = (s.gemm_mode == REPPO_GEMM_BF16);
+  c->concurrent = (getenv("REPPO_SERIAL") == nullptr);
   if (s.semantics == REPPO_SEM_JAX) {
     // flax RMSNorm/LayerNorm eps 1e-6; logits + 40.0 * zero_dist (jax_models.py:298); clip 1-1e-4
     // (jaxrl/reppo.py:558); min_std 0.1 because the constructor ignores cfg (jax_models.py:336);
@@ -634,6 +704,8 @@ void reppo_ctx_destroy(reppo_ctx* c) {
   if (c == nullptr) return;
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+  for (auto& e : c->events) cudaEventDestroy(e);
+  for (int i = 0; i < 3; ++i) if (c->side[i]) cudaStreamDestroy(c->side[i]);
   if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
   delete c;
 }
@@ -704,7 +776,7 @@ int reppo_critic_forward(reppo_ctx* c, const float* cp, const float* critic_obs,
   RET(pack_shadows(c, SLOT_CRITIC, cp, st));
   const Twin tw = c->twin(c->x0);
   CK(launch_gather_concat(critic_obs, sh.critic_obs_dim, action, sh.action_dim, nullptr, 0, rows, c->x0, c->K0, tw.p, tw.ld, st));
-  RET(critic_trunk(c, cp, rows, pred != nullptr, st));
+  RET(critic_trunk(c, cp, c->x0, rows, pred != nullptr, st));
   if (value || logits) CK(launch_value_head(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, rows, value, logits, st));
   if (pred) CK(cudaMemcpyAsync(pred, c->pa.out, sizeof(float) * rows * c->pred_out, cudaMemcpyDeviceToDevice, st));
   if (features) CK(cudaMemcpyAsync(features, c->fa.out, sizeof(float) * rows * sh.critic_hidden, cudaMemcpyDeviceToDevice, st));
@@ -768,7 +840,7 @@ int reppo_actor_grad(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
                      const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, reppo_stream stream) {
   c->launches = 0;
   RET(pack_all(c, s, static_cast<cudaStream_t>(stream)));
-  return actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, nullptr, static_cast<cudaStream_t>(stream));
+  return actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 int reppo_critic_step(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int32_t mb,
                       const reppo_hyper* hp, float* metrics, reppo_stream stream) {
@@ -780,7 +852,7 @@ int reppo_actor_step(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
                      const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, reppo_stream stream) {
   c->launches = 0;
   RET(pack_all(c, s, static_cast<cudaStream_t>(stream)));
-  return actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, nullptr, static_cast<cudaStream_t>(stream));
+  return actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 int reppo_clip_adam(reppo_ctx* c, const reppo_net_state* net, int64_t n, const reppo_hyper* hp, float* gn, reppo_stream stream) {
   c->launches = 0;

@@ -61,7 +61,7 @@ cudaError_t launch_gather_concat(const float* a, int da, const float* b, int db,
                                  int rows, float* out, int out_ld, void* out_h, int out_ldh, cudaStream_t st);
 cudaError_t launch_norm_act_fwd(int norm, const float* z, const float* gamma, const float* beta, int rows, int H,
                                 float eps, float* x, float* rstd, float* mean, void* x_h, int ldh, cudaStream_t st);
-cudaError_t launch_norm_act_bwd(int norm, const float* dx, const float* z, const float* gamma, const float* beta,
+cudaError_t launch_norm_act_bwd(int norm, const float* dx, const float* dx2, const float* z, const float* gamma, const float* beta,
                                 const float* rstd, const float* mean, int rows, int H, float* dz, float* dgamma,
                                 float* dbeta, float* dbias, void* dz_h, int ldh, cudaStream_t st);
 

@@ -184,7 +184,8 @@ constexpr int kMaxColsPerLane = 64;  // H <= 2048
 
 template <int NORM>
 __global__ void __launch_bounds__(256)
-norm_act_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ z, const float* __restrict__ gamma,
+norm_act_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ dx2, const float* __restrict__ z,
+                    const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ rstd_in,
                     const float* __restrict__ mean_in, int rows, int H, int rows_per_block, float* __restrict__ dz,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
@@ -205,6 +206,7 @@ norm_act_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ z, c
     for (int row = r0 + warp; row < r1; row += nwarp) {
       const float* zr = z + static_cast<size_t>(row) * H;
       const float* dxr = dx + static_cast<size_t>(row) * H;
+      const float* dx2r = dx2 ? dx2 + static_cast<size_t>(row) * H : nullptr;   // optional second upstream gradient (summed)
       float rstd = 1.f, mean = 0.f, s1 = 0.f, s2 = 0.f;
       if (NORM != NORM_NONE) {
         rstd = rstd_in[row];
@@ -213,7 +215,7 @@ norm_act_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ z, c
         for (int c = lane; c < H; c += 32) {
           const float zh = (zr[c] - mean) * rstd;
           const float y = (NORM == NORM_LAYER) ? zh * gamma[c] + beta[c] : zh * gamma[c];
-          const float dy = dxr[c] * swish_grad_(y);
+          const float dy = (dxr[c] + (dx2r ? dx2r[c] : 0.f)) * swish_grad_(y);
           const float dzh = dy * gamma[c];
           s1 += dzh; s2 += dzh * zh;
         }
@@ -226,12 +228,13 @@ norm_act_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ z, c
         const int c = lane + 32 * (cbase + j);
         if (c < H) {
           float o;
+          const float dxv = dxr[c] + (dx2r ? dx2r[c] : 0.f);
           if (NORM == NORM_NONE) {
-            o = dxr[c] * swish_grad_(zr[c]);
+            o = dxv * swish_grad_(zr[c]);
           } else {
             const float zh = (zr[c] - mean) * rstd;
             const float y = (NORM == NORM_LAYER) ? zh * gamma[c] + beta[c] : zh * gamma[c];
-            const float dy = dxr[c] * swish_grad_(y);
+            const float dy = dxv * swish_grad_(y);
             const float dzh = dy * gamma[c];
             o = rstd * (dzh - s1 - zh * s2);
             pg[j] += dy * zh;
@@ -263,7 +266,8 @@ norm_act_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ z, c
 
 template <int NORM, int VPL>
 __global__ void __launch_bounds__(256)
-norm_act_bwd_vec_kernel(const float* __restrict__ dx, const float* __restrict__ z, const float* __restrict__ gamma,
+norm_act_bwd_vec_kernel(const float* __restrict__ dx, const float* __restrict__ dx2, const float* __restrict__ z,
+                        const float* __restrict__ gamma,
                         const float* __restrict__ beta, const float* __restrict__ rstd_in,
                         const float* __restrict__ mean_in, int rows, int rows_per_block, float* __restrict__ dz,
                         float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
@@ -297,6 +301,14 @@ norm_act_bwd_vec_kernel(const float* __restrict__ dx, const float* __restrict__ 
     float4 zv[VPL], dv[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) { zv[i] = zr[lane + 32 * i]; dv[i] = dxr[lane + 32 * i]; }
+    if (dx2 != nullptr) {   // optional second upstream gradient (summed)
+      const float4* dx2r = reinterpret_cast<const float4*>(dx2 + static_cast<size_t>(row) * H);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const float4 t = dx2r[lane + 32 * i];
+        dv[i].x += t.x; dv[i].y += t.y; dv[i].z += t.z; dv[i].w += t.w;
+      }
+    }
     float rstd = 1.f, mean = 0.f;
     if (NORM != NORM_NONE) { rstd = rstd_in[row]; if (NORM == NORM_LAYER) mean = mean_in[row]; }
     float zh[VPL][4], dy[VPL][4];
@@ -359,7 +371,7 @@ norm_act_bwd_vec_kernel(const float* __restrict__ dx, const float* __restrict__ 
 }
 
 template <int NORM>
-static cudaError_t launch_bwd_norm(const float* dx, const float* z, const float* gamma, const float* beta, const float* rstd,
+static cudaError_t launch_bwd_norm(const float* dx, const float* dx2, const float* z, const float* gamma, const float* beta, const float* rstd,
                                    const float* mean, int rows, int H, float* dz, float* dgamma, float* dbeta, float* dbias,
                                    __nv_bfloat16* dzh, int ldh, cudaStream_t st) {
   // one block per ~SM: enough parallelism, few enough blocks that the per-block column atomics stay cheap
@@ -368,7 +380,7 @@ static cudaError_t launch_bwd_norm(const float* dx, const float* z, const float*
   const int grid = (rows + rows_per_block - 1) / rows_per_block;
   const bool vec = (H % 128 == 0) && H <= 1024 && (ldh % 4 == 0) && getenv("REPPO_NO_VEC") == nullptr;
 #define REPPO_BWD_VEC(V) \
-  norm_act_bwd_vec_kernel<NORM, V><<<grid, 256, 0, st>>>(dx, z, gamma, beta, rstd, mean, rows, rows_per_block, dz, dgamma, dbeta, dbias, dzh, ldh)
+  norm_act_bwd_vec_kernel<NORM, V><<<grid, 256, 0, st>>>(dx, dx2, z, gamma, beta, rstd, mean, rows, rows_per_block, dz, dgamma, dbeta, dbias, dzh, ldh)
   if (vec && H == 128) REPPO_BWD_VEC(1);
   else if (vec && H == 256) REPPO_BWD_VEC(2);
   else if (vec && H == 384) REPPO_BWD_VEC(3);
@@ -378,21 +390,21 @@ static cudaError_t launch_bwd_norm(const float* dx, const float* z, const float*
   else {
     if (H > 32 * kMaxColsPerLane) return cudaErrorInvalidValue;
     const size_t smem = 3 * static_cast<size_t>(H) * sizeof(float);
-    norm_act_bwd_kernel<NORM><<<grid, 256, smem, st>>>(dx, z, gamma, beta, rstd, mean, rows, H, rows_per_block, dz, dgamma, dbeta,
+    norm_act_bwd_kernel<NORM><<<grid, 256, smem, st>>>(dx, dx2, z, gamma, beta, rstd, mean, rows, H, rows_per_block, dz, dgamma, dbeta,
                                                         dbias, dzh, ldh);
   }
 #undef REPPO_BWD_VEC
   return cudaGetLastError();
 }
 
-cudaError_t launch_norm_act_bwd(int norm, const float* dx, const float* z, const float* gamma, const float* beta,
+cudaError_t launch_norm_act_bwd(int norm, const float* dx, const float* dx2, const float* z, const float* gamma, const float* beta,
                                 const float* rstd, const float* mean, int rows, int H, float* dz, float* dgamma,
                                 float* dbeta, float* dbias, void* dz_h, int ldh, cudaStream_t st) {
   __nv_bfloat16* dzh = static_cast<__nv_bfloat16*>(dz_h);
   if (rows <= 0) return cudaSuccess;
-  if (norm == NORM_NONE) return launch_bwd_norm<NORM_NONE>(dx, z, gamma, beta, rstd, mean, rows, H, dz, dgamma, dbeta, dbias, dzh, ldh, st);
-  if (norm == NORM_RMS) return launch_bwd_norm<NORM_RMS>(dx, z, gamma, beta, rstd, mean, rows, H, dz, dgamma, dbeta, dbias, dzh, ldh, st);
-  return launch_bwd_norm<NORM_LAYER>(dx, z, gamma, beta, rstd, mean, rows, H, dz, dgamma, dbeta, dbias, dzh, ldh, st);
+  if (norm == NORM_NONE) return launch_bwd_norm<NORM_NONE>(dx, dx2, z, gamma, beta, rstd, mean, rows, H, dz, dgamma, dbeta, dbias, dzh, ldh, st);
+  if (norm == NORM_RMS) return launch_bwd_norm<NORM_RMS>(dx, dx2, z, gamma, beta, rstd, mean, rows, H, dz, dgamma, dbeta, dbias, dzh, ldh, st);
+  return launch_bwd_norm<NORM_LAYER>(dx, dx2, z, gamma, beta, rstd, mean, rows, H, dz, dgamma, dbeta, dbias, dzh, ldh, st);
 }
 
 }  // namespace reppo
