@@ -7,11 +7,13 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace reppo {
 
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const PackTable t) {
+  REPPO_PDL_PROLOGUE();
   __shared__ float tile[32][33];
   // blockIdx.y = tensor, blockIdx.x = tile index inside the tensor (grid-strided)
   const PackEntry e = t.e[blockIdx.y];
@@ -46,12 +48,13 @@ pack_weights_kernel(const PackTable t) {
 cudaError_t launch_pack_weights(const PackTable& t, cudaStream_t st) {
   if (t.n <= 0) return cudaSuccess;
   dim3 grid(64, t.n);
-  pack_weights_kernel<<<grid, 256, 0, st>>>(t);
+  launch_k((pack_weights_kernel), dim3(grid), dim3(256), 0, st, t);
   return cudaGetLastError();
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int cols, int ld_src, __nv_bfloat16* __restrict__ dst,
                                  int ld_dst) {
+  REPPO_PDL_PROLOGUE();
   const long long total = static_cast<long long>(rows) * cols;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -64,8 +67,7 @@ cudaError_t launch_cast_bf16(const float* src, int rows, int cols, int ld_src, v
   const long long total = static_cast<long long>(rows) * cols;
   if (total <= 0) return cudaSuccess;
   const long long want = (total + 255) / 256;
-  cast_bf16_kernel<<<static_cast<int>(want < 148 * 8 ? want : 148 * 8), 256, 0, st>>>(src, rows, cols, ld_src,
-                                                                                      static_cast<__nv_bfloat16*>(dst), ld_dst);
+  launch_k((cast_bf16_kernel), dim3(static_cast<int>(want < 148 * 8 ? want : 148 * 8)), dim3(256), 0, st, src, rows, cols, ld_src, static_cast<__nv_bfloat16*>(dst), ld_dst);
   return cudaGetLastError();
 }
 

@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace reppo {
 
@@ -149,6 +150,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail
+  REPPO_PDL_PROLOGUE();
 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
@@ -330,7 +333,7 @@ static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float
   split_k = (total_kb + per - 1) / per;
   if (split_k > 1) mode = GEMM_ATOMIC;
   dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + TC_BLOCK_M - 1) / TC_BLOCK_M, split_k);
-  kern<<<grid, TC_THREADS, S::kTotal, st>>>(ta, tb, C, ldc, bias, M, N, K, per, mode);
+  launch_k((kern), dim3(grid), dim3(TC_THREADS), S::kTotal, st, ta, tb, C, ldc, bias, M, N, K, per, mode);
   return cudaGetLastError();
 }
 

@@ -9,6 +9,7 @@
 // shapes (K = obs+act, N = num_bins / 2*act).
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace reppo {
 
@@ -19,6 +20,7 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
                 const float* __restrict__ bias, int M, int N, int K, int lda, int ldb, int ldc, int k_chunk, int mode) {
+  REPPO_PDL_PROLOGUE();
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -95,10 +97,10 @@ cudaError_t launch_gemm_f32(bool ta, bool tb, int M, int N, int K, const float* 
   split_k = (K + k_chunk - 1) / k_chunk;
   if (split_k > 1) mode = GEMM_ATOMIC;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, split_k), block(256);
-  if (!ta && tb) gemm_f32_kernel<false, true><<<grid, block, 0, st>>>(A, B, C, bias, M, N, K, lda, ldb, ldc, k_chunk, mode);
-  else if (!ta && !tb) gemm_f32_kernel<false, false><<<grid, block, 0, st>>>(A, B, C, bias, M, N, K, lda, ldb, ldc, k_chunk, mode);
-  else if (ta && !tb) gemm_f32_kernel<true, false><<<grid, block, 0, st>>>(A, B, C, bias, M, N, K, lda, ldb, ldc, k_chunk, mode);
-  else gemm_f32_kernel<true, true><<<grid, block, 0, st>>>(A, B, C, bias, M, N, K, lda, ldb, ldc, k_chunk, mode);
+  if (!ta && tb) launch_k((gemm_f32_kernel<false, true>), dim3(grid), dim3(block), 0, st, A, B, C, bias, M, N, K, lda, ldb, ldc, k_chunk, mode);
+  else if (!ta && !tb) launch_k((gemm_f32_kernel<false, false>), dim3(grid), dim3(block), 0, st, A, B, C, bias, M, N, K, lda, ldb, ldc, k_chunk, mode);
+  else if (ta && !tb) launch_k((gemm_f32_kernel<true, false>), dim3(grid), dim3(block), 0, st, A, B, C, bias, M, N, K, lda, ldb, ldc, k_chunk, mode);
+  else launch_k((gemm_f32_kernel<true, true>), dim3(grid), dim3(block), 0, st, A, B, C, bias, M, N, K, lda, ldb, ldc, k_chunk, mode);
   return cudaGetLastError();
 }
 
@@ -106,6 +108,7 @@ cudaError_t launch_gemm_f32(bool ta, bool tb, int M, int N, int K, const float* 
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ X, int M, int N, int ld, int rows_per_block, float* __restrict__ out,
               float* __restrict__ out2, float scale2) {
+  REPPO_PDL_PROLOGUE();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
@@ -128,7 +131,7 @@ cudaError_t launch_colsum(const float* X, int M, int N, int ld, float* out, floa
   if (M <= 0 || N <= 0) return cudaSuccess;
   const int rows_per_block = 256;
   dim3 grid((N + 31) / 32, (M + rows_per_block - 1) / rows_per_block);
-  colsum_kernel<<<grid, 256, 0, st>>>(X, M, N, ld, rows_per_block, out, out2, scale2);
+  launch_k((colsum_kernel), dim3(grid), dim3(256), 0, st, X, M, N, ld, rows_per_block, out, out2, scale2);
   return cudaGetLastError();
 }
 

@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace reppo {
 
@@ -83,6 +84,7 @@ critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __rest
                  const float* __restrict__ target, const float* __restrict__ truncated, const int* __restrict__ idx,
                  int rows, float inv_rows, int no_mask, float* __restrict__ dlogits, float* __restrict__ metrics,
                  __nv_bfloat16* __restrict__ dl_h, int ldh, float* __restrict__ dbias, float* __restrict__ dzero) {
+  REPPO_PDL_PROLOGUE();
   __shared__ float sm[8 * 5];
   __shared__ float smax[8], smin[8];
   __shared__ float scol[8][32 * kMaxBinsPerLane];
@@ -165,6 +167,7 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
                   const float* __restrict__ truncated, const int* __restrict__ idx, int rows, float inv_rows, int no_mask,
                   float aux_mult, float* __restrict__ dpred, float* __restrict__ metrics, __nv_bfloat16* __restrict__ dp_h,
                   int ldh, float* __restrict__ dbias) {
+  REPPO_PDL_PROLOGUE();
   __shared__ float sm[8 * 3];
   extern __shared__ float scol[];  // [P] column sums of dpred (only when dbias != nullptr)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -228,6 +231,7 @@ actor_sample_kernel(const float* __restrict__ out, const float* __restrict__ out
                     ActorConsts ac, float* __restrict__ act_out, int act_ld, float* __restrict__ logp_out,
                     float* __restrict__ kl_out, float* __restrict__ gmu_kl, float* __restrict__ gsig_kl,
                     __nv_bfloat16* __restrict__ act_h, int act_ldh) {
+  REPPO_PDL_PROLOGUE();
   __shared__ float s_logp[256], s_old[256], s_new[256];
   const int rows_per_block = blockDim.x / A;
   const int rl = threadIdx.x / A, k = threadIdx.x - rl * A;
@@ -294,6 +298,7 @@ __global__ void __launch_bounds__(256)
 actor_q_kernel(const float* __restrict__ head_out, int ld, const float* __restrict__ zero_dist, HLConsts hl,
                const float* __restrict__ kl, int rows, float inv_rows, int kl_mode, float kl_bound,
                float* __restrict__ q_out, float* __restrict__ dlogits, __nv_bfloat16* __restrict__ dl_h, int ldh) {
+  REPPO_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -323,6 +328,7 @@ actor_grad_kernel(const float* __restrict__ out, const float* __restrict__ eps_p
                   const float* __restrict__ gsig_kl, const float* __restrict__ actor_params, int rows, int A, float inv_rows,
                   ActorConsts ac, float* __restrict__ dout, float* __restrict__ actor_grads, float* __restrict__ metrics,
                   __nv_bfloat16* __restrict__ dout_h, int ldh, float* __restrict__ dbias) {
+  REPPO_PDL_PROLOGUE();
   __shared__ float red[32];
   __shared__ float scol[64];  // column sums of dout = bias gradient of the policy's last Linear (2A <= 64)
   if (threadIdx.x < 64) scol[threadIdx.x] = 0.f;
@@ -416,9 +422,7 @@ cudaError_t launch_critic_ce(const float* head_out, int ld, const float* zero_di
                              const float* truncated, const int* idx, int rows, float inv_rows, int no_mask, float* dlogits,
                              float* metrics, void* dl_h, int ldh, float* dbias, float* dzero, cudaStream_t st) {
   if (hl.num_bins > 32 * kMaxBinsPerLane) return cudaErrorInvalidValue;
-  critic_ce_kernel<<<(rows + kLossRowsPerBlock - 1) / kLossRowsPerBlock, 256, 0, st>>>(
-      head_out, ld, zero_dist, hl, target, truncated, idx, rows, inv_rows, no_mask, dlogits, metrics,
-      static_cast<__nv_bfloat16*>(dl_h), ldh, dbias, dzero);
+  launch_k((critic_ce_kernel), dim3((rows + kLossRowsPerBlock - 1) / kLossRowsPerBlock), dim3(256), 0, st, head_out, ld, zero_dist, hl, target, truncated, idx, rows, inv_rows, no_mask, dlogits, metrics, static_cast<__nv_bfloat16*>(dl_h), ldh, dbias, dzero);
   return cudaGetLastError();
 }
 
@@ -427,9 +431,7 @@ cudaError_t launch_critic_aux(const float* pred, int P, int H, int reward_head, 
                               float inv_rows, int no_mask, float aux_mult, float* dpred, float* metrics, void* dp_h, int ldh,
                               float* dbias, cudaStream_t st) {
   const size_t smem = dbias ? static_cast<size_t>(P) * sizeof(float) : 0;
-  critic_aux_kernel<<<(rows + kLossRowsPerBlock - 1) / kLossRowsPerBlock, 256, smem, st>>>(
-      pred, P, H, reward_head, mask_done, next_emb, reward, done, truncated, idx, rows, inv_rows, no_mask, aux_mult, dpred,
-      metrics, static_cast<__nv_bfloat16*>(dp_h), ldh, dbias);
+  launch_k((critic_aux_kernel), dim3((rows + kLossRowsPerBlock - 1) / kLossRowsPerBlock), dim3(256), smem, st, pred, P, H, reward_head, mask_done, next_emb, reward, done, truncated, idx, rows, inv_rows, no_mask, aux_mult, dpred, metrics, static_cast<__nv_bfloat16*>(dp_h), ldh, dbias);
   return cudaGetLastError();
 }
 
@@ -439,9 +441,7 @@ cudaError_t launch_actor_sample(const float* out, const float* out_old, const in
                                 cudaStream_t st) {
   if (A > 256) return cudaErrorInvalidValue;
   const int rows_per_block = 256 / A;
-  actor_sample_kernel<<<(rows + rows_per_block - 1) / rows_per_block, 256, 0, st>>>(
-      out, out_old, old_idx, eps_pi, eps_kl, rows, A, kl_samples, ac, act_out, act_ld, logp, kl, gmu, gsig,
-      static_cast<__nv_bfloat16*>(act_h), act_ldh);
+  launch_k((actor_sample_kernel), dim3((rows + rows_per_block - 1) / rows_per_block), dim3(256), 0, st, out, out_old, old_idx, eps_pi, eps_kl, rows, A, kl_samples, ac, act_out, act_ld, logp, kl, gmu, gsig, static_cast<__nv_bfloat16*>(act_h), act_ldh);
   return cudaGetLastError();
 }
 
@@ -449,8 +449,7 @@ cudaError_t launch_actor_q(const float* head_out, int ld, const float* zero_dist
                            float inv_rows, int kl_mode, float kl_bound, float* q_out, float* dlogits, void* dl_h, int ldh,
                            cudaStream_t st) {
   if (hl.num_bins > 32 * kMaxBinsPerLane) return cudaErrorInvalidValue;
-  actor_q_kernel<<<(rows + 7) / 8, 256, 0, st>>>(head_out, ld, zero_dist, hl, kl, rows, inv_rows, kl_mode, kl_bound, q_out,
-                                                   dlogits, static_cast<__nv_bfloat16*>(dl_h), ldh);
+  launch_k((actor_q_kernel), dim3((rows + 7) / 8), dim3(256), 0, st, head_out, ld, zero_dist, hl, kl, rows, inv_rows, kl_mode, kl_bound, q_out, dlogits, static_cast<__nv_bfloat16*>(dl_h), ldh);
   return cudaGetLastError();
 }
 
@@ -460,9 +459,7 @@ cudaError_t launch_actor_grad(const float* out, const float* eps_pi, const float
                               const ActorConsts& ac, float* dout, float* actor_grads, float* metrics, void* dout_h, int ldh,
                               float* dbias, cudaStream_t st) {
   if (dbias != nullptr && 2 * A > 64) return cudaErrorInvalidValue;
-  actor_grad_kernel<<<(rows + 127) / 128, 128, 0, st>>>(out, eps_pi, act, act_ld, dact, dact_ld, logp, kl, q, gmu, gsig,
-                                                          actor_params, rows, A, inv_rows, ac, dout, actor_grads, metrics,
-                                                          static_cast<__nv_bfloat16*>(dout_h), ldh, dbias);
+  launch_k((actor_grad_kernel), dim3((rows + 127) / 128), dim3(128), 0, st, out, eps_pi, act, act_ld, dact, dact_ld, logp, kl, q, gmu, gsig, actor_params, rows, A, inv_rows, ac, dout, actor_grads, metrics, static_cast<__nv_bfloat16*>(dout_h), ldh, dbias);
   return cudaGetLastError();
 }
 
@@ -470,6 +467,7 @@ cudaError_t launch_actor_grad(const float* out, const float* eps_pi, const float
 __global__ void __launch_bounds__(256)
 value_head_kernel(const float* __restrict__ head_out, int ld, const float* __restrict__ zero_dist, HLConsts hl, int rows,
                   float* __restrict__ value, float* __restrict__ logits) {
+  REPPO_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -487,6 +485,7 @@ value_head_kernel(const float* __restrict__ head_out, int ld, const float* __res
 
 __global__ void mean_std_kernel(const float* __restrict__ out, int rows, int A, float min_std, float* __restrict__ mean,
                                 float* __restrict__ std) {
+  REPPO_PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * A) return;
   const int r = i / A, k = i % A;
@@ -497,12 +496,12 @@ __global__ void mean_std_kernel(const float* __restrict__ out, int rows, int A, 
 cudaError_t launch_value_head(const float* head_out, int ld, const float* zero_dist, const HLConsts& hl, int rows,
                               float* value, float* logits, cudaStream_t st) {
   if (hl.num_bins > 32 * kMaxBinsPerLane) return cudaErrorInvalidValue;
-  value_head_kernel<<<(rows + 7) / 8, 256, 0, st>>>(head_out, ld, zero_dist, hl, rows, value, logits);
+  launch_k((value_head_kernel), dim3((rows + 7) / 8), dim3(256), 0, st, head_out, ld, zero_dist, hl, rows, value, logits);
   return cudaGetLastError();
 }
 
 cudaError_t launch_mean_std(const float* out, int rows, int A, float min_std, float* mean, float* std, cudaStream_t st) {
-  mean_std_kernel<<<(rows * A + 255) / 256, 256, 0, st>>>(out, rows, A, min_std, mean, std);
+  launch_k((mean_std_kernel), dim3((rows * A + 255) / 256), dim3(256), 0, st, out, rows, A, min_std, mean, std);
   return cudaGetLastError();
 }
 

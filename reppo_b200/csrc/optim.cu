@@ -8,11 +8,13 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace reppo {
 
 __global__ void __launch_bounds__(256)
 sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partials, int* __restrict__ step) {
+  REPPO_PDL_PROLOGUE();
   __shared__ float red[32];
   float s = 0.f;
   const long long n4 = n >> 2;
@@ -34,6 +36,7 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
             const float* __restrict__ partials, int num_partials, const int* __restrict__ step, AdamConsts c,
             const ShadowTable sh, float* __restrict__ grad_norm_out) {
+  REPPO_PDL_PROLOGUE();
   __shared__ float red[32];
   __shared__ float s_scale, s_bc1, s_bc2;
   float s = 0.f;
@@ -95,15 +98,16 @@ cudaError_t launch_clip_adam(float* p, const float* g, float* m, float* v, long 
   const long long want = (n / 4 + 255) / 256;
   int blocks = static_cast<int>(want < kMaxPartials ? want : kMaxPartials);
   if (blocks < 1) blocks = 1;
-  sumsq_partial_kernel<<<blocks, 256, 0, st>>>(g, n, partials, step);
+  launch_k((sumsq_partial_kernel), dim3(blocks), dim3(256), 0, st, g, n, partials, step);
   ShadowTable sh{};
   if (shadow != nullptr) sh = *shadow;
-  adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, partials, blocks, step, c, sh, grad_norm_out);
+  launch_k((adam_kernel), dim3(blocks), dim3(256), 0, st, p, g, m, v, n, partials, blocks, step, c, sh, grad_norm_out);
   return cudaGetLastError();
 }
 
 // mean of the step metrics of the last epoch (src/jaxrl/reppo.py:660,671)
 __global__ void metrics_mean_kernel(const float* __restrict__ step_metrics, int first, int count, int nm, float* __restrict__ out) {
+  REPPO_PDL_PROLOGUE();
   const int k = threadIdx.x;
   if (k >= nm) return;
   float s = 0.f;
@@ -112,17 +116,18 @@ __global__ void metrics_mean_kernel(const float* __restrict__ step_metrics, int 
 }
 
 cudaError_t launch_metrics_mean(const float* step_metrics, int first, int count, int nm, float* out, cudaStream_t st) {
-  metrics_mean_kernel<<<1, 32, 0, st>>>(step_metrics, first, count, nm, out);
+  launch_k((metrics_mean_kernel), dim3(1), dim3(32), 0, st, step_metrics, first, count, nm, out);
   return cudaGetLastError();
 }
 
 // metric vector prologue: zero the sums, seed the min / max slots
 __global__ void metrics_init_kernel(float* __restrict__ m, uint32_t mask) {
+  REPPO_PDL_PROLOGUE();
   const int k = threadIdx.x;
   if (k < M_NUM && ((mask >> k) & 1u)) m[k] = (k == M_TARGET_MAX) ? -INFINITY : (k == M_TARGET_MIN ? INFINITY : 0.f);
 }
 cudaError_t launch_metrics_init(float* m, uint32_t mask, cudaStream_t st) {
-  metrics_init_kernel<<<1, 32, 0, st>>>(m, mask);
+  launch_k((metrics_init_kernel), dim3(1), dim3(32), 0, st, m, mask);
   return cudaGetLastError();
 }
 

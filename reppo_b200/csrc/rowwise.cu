@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace reppo {
 
@@ -30,6 +31,7 @@ REPPO_DEVINL void store_bf16x4(__nv_bfloat16* p, float a, float b, float c, floa
 __global__ void gather_concat_kernel(const float* __restrict__ a, int da, const float* __restrict__ b, int db,
                                      const int* __restrict__ idx, int b_is_local, int rows, float* __restrict__ out,
                                      int out_ld, __nv_bfloat16* __restrict__ out_h, int out_ldh) {
+  REPPO_PDL_PROLOGUE();
   const int w = da + db;
   const long long total = static_cast<long long>(rows) * w;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -51,8 +53,7 @@ cudaError_t launch_gather_concat(const float* a, int da, const float* b, int db,
   const int block = 256;
   const long long want = (total + block - 1) / block;
   const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
-  gather_concat_kernel<<<grid, block, 0, st>>>(a, da, b, db, idx, b_is_local, rows, out, out_ld,
-                                               static_cast<__nv_bfloat16*>(out_h), out_ldh);
+  launch_k((gather_concat_kernel), dim3(grid), dim3(block), 0, st, a, da, b, db, idx, b_is_local, rows, out, out_ld, static_cast<__nv_bfloat16*>(out_h), out_ldh);
   return cudaGetLastError();
 }
 
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(256)
 norm_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
                     int rows, int H, float eps, float* __restrict__ x, float* __restrict__ rstd_out,
                     float* __restrict__ mean_out, __nv_bfloat16* __restrict__ x_h, int ldh) {
+  REPPO_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(256)
 norm_act_fwd_vec_kernel(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
                         int rows, float eps, float* __restrict__ x, float* __restrict__ rstd_out,
                         float* __restrict__ mean_out, __nv_bfloat16* __restrict__ x_h, int ldh) {
+  REPPO_PDL_PROLOGUE();
   constexpr int H = 128 * VPL;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -149,14 +152,14 @@ static void launch_fwd_norm(const float* z, const float* gamma, const float* bet
                             float* rstd, float* mean, __nv_bfloat16* xh, int ldh, cudaStream_t st) {
   const int wpb = 8, grid = (rows + wpb - 1) / wpb;
   const bool vec = (H % 128 == 0) && H <= 1024 && (ldh % 4 == 0) && getenv("REPPO_NO_VEC") == nullptr;
-#define REPPO_FWD_VEC(V) norm_act_fwd_vec_kernel<NORM, V><<<grid, wpb * 32, 0, st>>>(z, gamma, beta, rows, eps, x, rstd, mean, xh, ldh)
+#define REPPO_FWD_VEC(V) launch_k((norm_act_fwd_vec_kernel<NORM, V>), dim3(grid), dim3(wpb * 32), 0, st, z, gamma, beta, rows, eps, x, rstd, mean, xh, ldh)
   if (vec && H == 128) REPPO_FWD_VEC(1);
   else if (vec && H == 256) REPPO_FWD_VEC(2);
   else if (vec && H == 384) REPPO_FWD_VEC(3);
   else if (vec && H == 512) REPPO_FWD_VEC(4);
   else if (vec && H == 768) REPPO_FWD_VEC(6);
   else if (vec && H == 1024) REPPO_FWD_VEC(8);
-  else norm_act_fwd_kernel<NORM><<<grid, wpb * 32, 0, st>>>(z, gamma, beta, rows, H, eps, x, rstd, mean, xh, ldh);
+  else launch_k((norm_act_fwd_kernel<NORM>), dim3(grid), dim3(wpb * 32), 0, st, z, gamma, beta, rows, H, eps, x, rstd, mean, xh, ldh);
 #undef REPPO_FWD_VEC
 }
 
@@ -190,6 +193,7 @@ norm_act_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ dx2,
                     const float* __restrict__ mean_in, int rows, int H, int rows_per_block, float* __restrict__ dz,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                     __nv_bfloat16* __restrict__ dz_h, int ldh) {
+  REPPO_PDL_PROLOGUE();
   extern __shared__ float sm[];  // [3][H]: dgamma, dbeta, dbias
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int r0 = blockIdx.x * rows_per_block;
@@ -272,6 +276,7 @@ norm_act_bwd_vec_kernel(const float* __restrict__ dx, const float* __restrict__ 
                         const float* __restrict__ mean_in, int rows, int rows_per_block, float* __restrict__ dz,
                         float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                         __nv_bfloat16* __restrict__ dz_h, int ldh) {
+  REPPO_PDL_PROLOGUE();
   constexpr int H = 128 * VPL;
   __shared__ float sm[3 * H];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -380,7 +385,7 @@ static cudaError_t launch_bwd_norm(const float* dx, const float* dx2, const floa
   const int grid = (rows + rows_per_block - 1) / rows_per_block;
   const bool vec = (H % 128 == 0) && H <= 1024 && (ldh % 4 == 0) && getenv("REPPO_NO_VEC") == nullptr;
 #define REPPO_BWD_VEC(V) \
-  norm_act_bwd_vec_kernel<NORM, V><<<grid, 256, 0, st>>>(dx, dx2, z, gamma, beta, rstd, mean, rows, rows_per_block, dz, dgamma, dbeta, dbias, dzh, ldh)
+  launch_k((norm_act_bwd_vec_kernel<NORM, V>), dim3(grid), dim3(256), 0, st, dx, dx2, z, gamma, beta, rstd, mean, rows, rows_per_block, dz, dgamma, dbeta, dbias, dzh, ldh)
   if (vec && H == 128) REPPO_BWD_VEC(1);
   else if (vec && H == 256) REPPO_BWD_VEC(2);
   else if (vec && H == 384) REPPO_BWD_VEC(3);
@@ -390,8 +395,7 @@ static cudaError_t launch_bwd_norm(const float* dx, const float* dx2, const floa
   else {
     if (H > 32 * kMaxColsPerLane) return cudaErrorInvalidValue;
     const size_t smem = 3 * static_cast<size_t>(H) * sizeof(float);
-    norm_act_bwd_kernel<NORM><<<grid, 256, smem, st>>>(dx, dx2, z, gamma, beta, rstd, mean, rows, H, rows_per_block, dz, dgamma, dbeta,
-                                                        dbias, dzh, ldh);
+    launch_k((norm_act_bwd_kernel<NORM>), dim3(grid), dim3(256), smem, st, dx, dx2, z, gamma, beta, rstd, mean, rows, H, rows_per_block, dz, dgamma, dbeta, dbias, dzh, ldh);
   }
 #undef REPPO_BWD_VEC
   return cudaGetLastError();
