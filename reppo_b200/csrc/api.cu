@@ -268,12 +268,14 @@ int wgrad_split(int out, int in, int rows, bool tc) {
 }
 
 // y[rows,out] = x[rows,in] W^T + b
-int linear_fwd(reppo_ctx* c, const Linear& L, const float* params, int slot, const float* x, int rows, float* y, cudaStream_t st) {
+// act: optional bf16 twin that receives swish(y) from the GEMM epilogue (tensor-core mode only)
+int linear_fwd(reppo_ctx* c, const Linear& L, const float* params, int slot, const float* x, int rows, float* y, Twin act,
+               cudaStream_t st) {
   if (c->tc) {
     const Twin tx = c->twin(x);
     if (tx.p == nullptr) return fail(c, REPPO_ERR_INVALID, "internal: forward operand has no bf16 twin");
     CK(launch_gemm_bf16_tc(false, false, rows, L.out, L.in, tx.p, tx.ld, c->shadow_b[slot] + L.sb, L.ld_b, y, L.out,
-                           params + L.b, GEMM_STORE, 1, st));
+                           params + L.b, GEMM_STORE, 1, act.p, act.ld, st));
   } else {
     CK(launch_gemm_f32(false, true, rows, L.out, L.in, x, L.in, params + L.w, L.in, y, L.out, params + L.b, GEMM_STORE, 1, st));
   }
@@ -287,7 +289,7 @@ int linear_dgrad(reppo_ctx* c, const Linear& L, const float* params, int slot, c
     if (td.p == nullptr) return fail(c, REPPO_ERR_INVALID, "internal: dgrad operand has no bf16 twin");
     // B = W [out, in] read MN-major (reduction dim = out is the outer dim): no transposed shadow needed
     CK(launch_gemm_bf16_tc(false, true, rows, L.in, L.out, td.p, td.ld, c->shadow_b[slot] + L.sb, L.ld_b, dx, L.in, nullptr, mode,
-                           1, st));
+                           1, nullptr, 0, st));
   } else {
     CK(launch_gemm_f32(false, false, rows, L.in, L.out, dy, L.out, params + L.w, L.in, dx, L.in, nullptr, mode, 1, st));
   }
@@ -299,7 +301,7 @@ int linear_wgrad(reppo_ctx* c, const Linear& L, const float* dy, const float* x,
   if (c->tc) {
     const Twin td = c->twin(dy), tx = c->twin(x);
     if (td.p == nullptr || tx.p == nullptr) return fail(c, REPPO_ERR_INVALID, "internal: wgrad operand has no bf16 twin");
-    CK(launch_gemm_bf16_tc(true, true, L.out, L.in, rows, td.p, td.ld, tx.p, tx.ld, dw, L.in, nullptr, GEMM_ATOMIC, split, st));
+    CK(launch_gemm_bf16_tc(true, true, L.out, L.in, rows, td.p, td.ld, tx.p, tx.ld, dw, L.in, nullptr, GEMM_ATOMIC, split, nullptr, 0, st));
   } else {
     CK(launch_gemm_f32(true, false, L.out, L.in, rows, dy, L.out, x, L.in, dw, L.in, nullptr, GEMM_ATOMIC, split, st));
   }
@@ -330,14 +332,16 @@ int pack_all(reppo_ctx* c, const reppo_state* s, cudaStream_t st) {
   return REPPO_OK;
 }
 
-int mlp_forward(reppo_ctx* c, const Mlp& m, const float* params, int slot, const float* in, int rows, Acts& a, cudaStream_t st) {
+// out_act: optional bf16 twin that receives swish(output) straight from the last GEMM's epilogue
+int mlp_forward(reppo_ctx* c, const Mlp& m, const float* params, int slot, const float* in, int rows, Acts& a, cudaStream_t st,
+                Twin out_act = Twin{}) {
   const float* cur = in;
   const int n = static_cast<int>(m.layers.size());
   for (int i = 0; i < n; ++i) {
     const Linear& L = m.layers[i];
     const bool last = (i == n - 1);
     float* dst = last ? a.out : a.z[i];
-    RET(linear_fwd(c, L, params, slot, cur, rows, dst, st));
+    RET(linear_fwd(c, L, params, slot, cur, rows, dst, last ? out_act : Twin{}, st));
     if (!last) {
       const Twin tw = c->twin(a.x[i]);
       CK(launch_norm_act_fwd(m.norm, a.z[i], L.g >= 0 ? params + L.g : nullptr, L.beta >= 0 ? params + L.beta : nullptr,
@@ -413,13 +417,25 @@ int check_rows(reppo_ctx* c, int rows) {
   return REPPO_OK;
 }
 
+int critic_trunk_encoder(reppo_ctx* c, const float* cp, const float* x0, int rows, cudaStream_t st);
 int critic_trunk(reppo_ctx* c, const float* cp, const float* x0, int rows, bool with_pred, cudaStream_t st) {
-  RET(mlp_forward(c, c->feature, cp, SLOT_CRITIC, x0, rows, c->fa, st));
-  const Twin tw = c->twin(c->xs);
-  CK(launch_norm_act_fwd(NORM_NONE, c->fa.out, nullptr, nullptr, rows, c->shape.critic_hidden, 0.f, c->tc ? nullptr : c->xs,
-                         nullptr, nullptr, tw.p, tw.ld, st));
+  RET(critic_trunk_encoder(c, cp, x0, rows, st));
   RET(mlp_forward(c, c->head, cp, SLOT_CRITIC, c->xs, rows, c->ha, st));
   if (with_pred) RET(mlp_forward(c, c->pred, cp, SLOT_CRITIC, c->xs, rows, c->pa, st));
+  return REPPO_OK;
+}
+
+// encoder + swish(features) -> xs
+int critic_trunk_encoder(reppo_ctx* c, const float* cp, const float* x0, int rows, cudaStream_t st) {
+  const Twin tw = c->twin(c->xs);
+  if (c->tc && getenv("REPPO_NO_FUSE_ACT") == nullptr) {
+    // swish(features), the input of both heads, leaves the encoder's last GEMM epilogue directly as bf16
+    RET(mlp_forward(c, c->feature, cp, SLOT_CRITIC, x0, rows, c->fa, st, tw));
+  } else {
+    RET(mlp_forward(c, c->feature, cp, SLOT_CRITIC, x0, rows, c->fa, st));
+    CK(launch_norm_act_fwd(NORM_NONE, c->fa.out, nullptr, nullptr, rows, c->shape.critic_hidden, 0.f, c->tc ? nullptr : c->xs,
+                           nullptr, nullptr, tw.p, tw.ld, st));
+  }
   return REPPO_OK;
 }
 
@@ -454,9 +470,7 @@ int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
   Twin tw = c->twin(c->x0);
   CK(launch_gather_concat(b->critic_obs, sh.critic_obs_dim, b->action, sh.action_dim, idx, 0, mb, c->x0, c->K0, tw.p, tw.ld, st));
   // encoder, then swish(features) feeds two independent heads
-  RET(mlp_forward(c, c->feature, cp, SLOT_CRITIC, c->x0, mb, c->fa, st));
-  tw = c->twin(c->xs);
-  CK(launch_norm_act_fwd(NORM_NONE, c->fa.out, nullptr, nullptr, mb, Hc, 0.f, c->tc ? nullptr : c->xs, nullptr, nullptr, tw.p, tw.ld, st));
+  RET(critic_trunk_encoder(c, cp, c->x0, mb, st));
   RET(dep(c, st, s1));
   // --- branch s1: prediction head forward, aux loss, backward down to d swish(features)
   RET(mlp_forward(c, c->pred, cp, SLOT_CRITIC, c->xs, mb, c->pa, s1));
@@ -816,16 +830,16 @@ int reppo_linear(reppo_ctx* c, int32_t op, int32_t rows, int32_t in_f, int32_t o
   if (op == 0) {
     CK(launch_cast_bf16(a, rows, in_f, in_f, c->lin_a, ldi, st));
     CK(launch_cast_bf16(b, out_f, in_f, in_f, c->lin_b, ldi, st));
-    CK(launch_gemm_bf16_tc(false, false, rows, out_f, in_f, c->lin_a, ldi, c->lin_b, ldi, out, out_f, bias, GEMM_STORE, 1, st));
+    CK(launch_gemm_bf16_tc(false, false, rows, out_f, in_f, c->lin_a, ldi, c->lin_b, ldi, out, out_f, bias, GEMM_STORE, 1, nullptr, 0, st));
   } else if (op == 1) {
     CK(launch_cast_bf16(a, rows, out_f, out_f, c->lin_a, ldo, st));
     CK(launch_cast_bf16(b, out_f, in_f, in_f, c->lin_b, ldi, st));
-    CK(launch_gemm_bf16_tc(false, true, rows, in_f, out_f, c->lin_a, ldo, c->lin_b, ldi, out, in_f, nullptr, GEMM_STORE, 1, st));
+    CK(launch_gemm_bf16_tc(false, true, rows, in_f, out_f, c->lin_a, ldo, c->lin_b, ldi, out, in_f, nullptr, GEMM_STORE, 1, nullptr, 0, st));
   } else {
     CK(launch_cast_bf16(a, rows, out_f, out_f, c->lin_a, ldo, st));
     CK(launch_cast_bf16(b, rows, in_f, in_f, c->lin_c, ldi, st));
     CK(launch_gemm_bf16_tc(true, true, out_f, in_f, rows, c->lin_a, ldo, c->lin_c, ldi, out, in_f, nullptr, GEMM_ATOMIC,
-                           wgrad_split(out_f, in_f, rows, true), st));
+                           wgrad_split(out_f, in_f, rows, true), nullptr, 0, st));
   }
   return REPPO_OK;
 }

@@ -9,8 +9,8 @@
 //   A K-major,  B K-major  : forward  y  = x  · W^T    A = x  [rows,in],  B = W [out,in]  (reduction dim contiguous)
 //   A K-major,  B MN-major : dgrad    dx = dy · W      A = dy [rows,out], B = W [out,in]  (same bf16 shadow, no W^T copy)
 //   A MN-major, B MN-major : wgrad    dW[out,in] = dy^T · x    A = dy [rows,out], B = x [rows,in]  (reduction dim = rows)
-// Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer,
-// warps 2..5 = epilogue (each owns the 32 TMEM lanes  32*(warp%4) .. +32).
+// Warp roles (320 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer,
+// warps 2..9 = epilogue (warp w owns TMEM lanes 32*(w%4)..+32; the two warps of a lane quarter split the columns).
 // Pipeline: NUM_STAGES-deep smem ring with full/empty mbarriers (TMA -> MMA), one
 // tmem_full mbarrier (MMA -> epilogue).  One output tile per CTA; split-K over gridDim.z for
 // wgrad (fp32 atomics into the zeroed gradient arena).  Epilogue: tcgen05.ld gives every thread
@@ -28,7 +28,7 @@ namespace reppo {
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int TC_UMMA_K = 16;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
 REPPO_DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -120,7 +120,7 @@ template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     float* __restrict__ C, int ldc, const float* __restrict__ bias, int M, int N, int K, int k_blocks_per_split,
-                    int mode) {
+                    int mode, __nv_bfloat16* __restrict__ act_out, int act_ld) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   using S = TcSmem<BLOCK_N, STAGES>;
@@ -203,18 +203,23 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tc_commit(tmem_full_bar);            // accumulator complete
   } else if (warp >= 2) {
     // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====
+    // 8 warps: warp w may only touch TMEM lanes 32*(w%4)..+32, so two warps share each lane quarter and split the
+    // tile's columns between them (the epilogue, not the MMA, bounds these short-K GEMMs).
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     // all TMA loads were consumed by MMAs that have retired: the pipeline stages are free to reuse
-    constexpr int kStgLd = BLOCK_N + 4;
-    static_assert(4 * 32 * kStgLd * 4 <= STAGES * S::kStageBytes, "staging does not fit in the pipeline smem");
-    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * kStgLd;
+    constexpr int kCols = BLOCK_N / 2;           // columns per epilogue warp
+    constexpr int kStgLd = kCols + 4;
+    static_assert(8 * 32 * kStgLd * 4 <= STAGES * S::kStageBytes, "staging does not fit in the pipeline smem");
+    const int ew = warp - 2;
+    float* stg = reinterpret_cast<float*>(smem) + ew * 32 * kStgLd;
     const int lane_base = (warp & 3) * 32;
+    const int cbase = (ew >> 2) * kCols;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = 0; c0 < kCols; c0 += 32) {
       float v[32];
       if (num_kb > 0) {
-        tc_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + c0, v);
+        tc_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + cbase + c0, v);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -225,12 +230,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     __syncwarp();
     const bool add_bias = (bias != nullptr) && (blockIdx.z == 0);
-    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (mode != GEMM_ATOMIC);
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (mode != GEMM_ATOMIC) &&
+                        (act_out == nullptr || (act_ld & 3) == 0);
     if (vec_ok) {
-      constexpr int kLanesPerRow = BLOCK_N / 4;          // 32 (BLOCK_N = 128) or 16 (BLOCK_N = 64)
-      constexpr int kRowsPerIter = 32 / kLanesPerRow;    // 1 or 2
+      constexpr int kLanesPerRow = kCols / 4;            // 16 (BLOCK_N = 128) or 8 (BLOCK_N = 64)
+      constexpr int kRowsPerIter = 32 / kLanesPerRow;    // 2 or 4
       const int cl = (lane % kLanesPerRow) * 4;
-      const int col = n0 + cl;
+      const int col = n0 + cbase + cl;
       float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
       if (add_bias) {
         if (col + 0 < N) bv.x = bias[col + 0];
@@ -251,9 +257,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
           }
           *reinterpret_cast<float4*>(cp) = x;
+          if (act_out != nullptr) {   // fused epilogue: swish(y) as the bf16 operand of the next GEMM
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(swishf_(x.x), swishf_(x.y)), hi = __floats2bfloat162_rn(swishf_(x.z), swishf_(x.w));
+            uint2 u;
+            u.x = *reinterpret_cast<const uint32_t*>(&lo);
+            u.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(act_out + static_cast<size_t>(row) * act_ld + col) = u;
+          }
         } else {
           const float xs[4] = {x.x, x.y, x.z, x.w};
-          for (int j = 0; j < 4 && col + j < N; ++j) cp[j] = (mode == GEMM_ACCUM) ? cp[j] + xs[j] : xs[j];
+          for (int j = 0; j < 4 && col + j < N; ++j) {
+            const float o = (mode == GEMM_ACCUM) ? cp[j] + xs[j] : xs[j];
+            cp[j] = o;
+            if (act_out != nullptr) act_out[static_cast<size_t>(row) * act_ld + col + j] = __float2bfloat16_rn(swishf_(o));
+          }
         }
       }
     } else {
@@ -264,14 +281,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (row >= M) break;
         float* crow = C + static_cast<size_t>(row) * ldc;
 #pragma unroll
-        for (int cc = 0; cc < BLOCK_N; cc += 32) {
-          const int col = n0 + cc + lane;
+        for (int cc = 0; cc < kCols; cc += 32) {
+          const int col = n0 + cbase + cc + lane;
           if (col < N) {
             float x = stg[r * kStgLd + cc + lane];
             if (add_bias) x += bias[col];
             if (mode == GEMM_STORE) crow[col] = x;
-            else if (mode == GEMM_ACCUM) crow[col] += x;
+            else if (mode == GEMM_ACCUM) { x += crow[col]; crow[col] = x; }
             else atomicAdd(crow + col, x);
+            if (act_out != nullptr && mode != GEMM_ATOMIC) act_out[static_cast<size_t>(row) * act_ld + col] = __float2bfloat16_rn(swishf_(x));
           }
         }
       }
@@ -317,7 +335,7 @@ static bool encode_2d(CUtensorMap* map, const void* base, int rows, int cols, in
 
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
 static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int ldc, const float* bias, int M, int N,
-                             int K, int split_k, int mode, cudaStream_t st) {
+                             int K, int split_k, int mode, __nv_bfloat16* act_out, int act_ld, cudaStream_t st) {
   using S = TcSmem<BLOCK_N, STAGES>;
   static bool configured = false;
   auto kern = gemm_bf16_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
@@ -333,7 +351,7 @@ static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float
   split_k = (total_kb + per - 1) / per;
   if (split_k > 1) mode = GEMM_ATOMIC;
   dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + TC_BLOCK_M - 1) / TC_BLOCK_M, split_k);
-  launch_k((kern), dim3(grid), dim3(TC_THREADS), S::kTotal, st, ta, tb, C, ldc, bias, M, N, K, per, mode);
+  launch_k((kern), dim3(grid), dim3(TC_THREADS), S::kTotal, st, ta, tb, C, ldc, bias, M, N, K, per, mode, act_out, act_ld);
   return cudaGetLastError();
 }
 
@@ -341,7 +359,9 @@ static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float
 //  a_mn == false: A stored [M, K]   | a_mn == true: A stored [K, M]
 //  b_mn == false: B stored [N, K]   | b_mn == true: B stored [K, N]
 cudaError_t launch_gemm_bf16_tc(bool a_mn, bool b_mn, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
-                                float* C, int ldc, const float* bias, int mode, int split_k, cudaStream_t st) {
+                                float* C, int ldc, const float* bias, int mode, int split_k, void* act_out_v, int act_ld,
+                                cudaStream_t st) {
+  __nv_bfloat16* act_out = static_cast<__nv_bfloat16*>(act_out_v);
   if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
   if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
     return cudaErrorInvalidValue;
@@ -355,8 +375,8 @@ cudaError_t launch_gemm_bf16_tc(bool a_mn, bool b_mn, int M, int N, int K, const
   const bool ok_b = b_mn ? encode_2d(&tb, B, K, N, ldb, 64, TC_BLOCK_K) : encode_2d(&tb, B, N, K, ldb, TC_BLOCK_K, block_n);
   if (!ok_a || !ok_b) return cudaErrorInvalidValue;
 #define REPPO_TC_DISPATCH(AMN, BMN)                                                                           \
-  return wide ? launch_tc<128, 4, AMN, BMN>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, st)                 \
-              : launch_tc<64, 4, AMN, BMN>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, st)
+  return wide ? launch_tc<128, 4, AMN, BMN>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, act_out, act_ld, st) \
+              : launch_tc<64, 4, AMN, BMN>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, act_out, act_ld, st)
   if (!a_mn && !b_mn) { REPPO_TC_DISPATCH(false, false); }
   if (!a_mn && b_mn) { REPPO_TC_DISPATCH(false, true); }
   REPPO_TC_DISPATCH(true, true);
