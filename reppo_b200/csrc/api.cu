@@ -122,6 +122,7 @@ struct reppo_ctx {
   // concurrency: independent branches of a step run on context-owned side streams (captured into the graph as
   // parallel branches): [0] pred-head branch, [1] weight-gradient GEMMs, [2] actor-only prefix of the actor step
   bool concurrent = true;
+  bool fuse_norm = true;   // REPPO_NO_FUSE_NORM=1: separate GEMM + norm/swish kernels
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> events;
   size_t ev_next = 0;
@@ -341,6 +342,16 @@ int mlp_forward(reppo_ctx* c, const Mlp& m, const float* params, int slot, const
     const Linear& L = m.layers[i];
     const bool last = (i == n - 1);
     float* dst = last ? a.out : a.z[i];
+    if (!last && c->tc && c->fuse_norm && m.norm != NORM_NONE) {
+      // Linear + bias + norm + swish in ONE tcgen05 kernel (cluster-wide row statistics); falls through when the
+      // shape does not fit the cluster scheme
+      const Twin tx = c->twin(cur), tw = c->twin(a.x[i]);
+      NormArgs na{L.g >= 0 ? params + L.g : nullptr, L.beta >= 0 ? params + L.beta : nullptr, c->sem.norm_eps, a.rstd[i], a.mean[i]};
+      const cudaError_t e = launch_gemm_bf16_tc_norm(m.norm, rows, L.out, L.in, tx.p, tx.ld, c->shadow_b[slot] + L.sb, L.ld_b,
+                                                     dst, L.out, params + L.b, tw.p, tw.ld, na, st);
+      if (e == cudaSuccess) { ++c->launches; cur = a.x[i]; continue; }
+      if (e != cudaErrorNotSupported) return fail(c, REPPO_ERR_CUDA, std::string("launch_gemm_bf16_tc_norm: ") + cudaGetErrorString(e));
+    }
     RET(linear_fwd(c, L, params, slot, cur, rows, dst, last ? out_act : Twin{}, st));
     if (!last) {
       const Twin tw = c->twin(a.x[i]);
@@ -667,6 +678,7 @@ int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
   c->shape = s;
   c->tc = (s.gemm_mode == REPPO_GEMM_BF16);
   c->concurrent = (getenv("REPPO_SERIAL") == nullptr);
+  c->fuse_norm = (getenv("REPPO_NO_FUSE_NORM") == nullptr);
   if (s.semantics == REPPO_SEM_JAX) {
     // flax RMSNorm/LayerNorm eps 1e-6; logits + 40.0 * zero_dist (jax_models.py:298); clip 1-1e-4
     // (jaxrl/reppo.py:558); min_std 0.1 because the constructor ignores cfg (jax_models.py:336);

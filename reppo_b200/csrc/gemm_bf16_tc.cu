@@ -112,15 +112,34 @@ struct TcSmem {
   static constexpr int kBBytes = BLOCK_N * TC_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int kStatOffset = kBarOffset + (2 * STAGES + 1) * 8 + 16;      // fused-norm row statistics
+  static constexpr int kStatBytes = (4 * 128 + 2 * 128 + 2 * 8 * 32) * 4;          // part[2][2][128], cta_stat[2][128], rs/mu[8][32]
+  static constexpr int kTotal = kStatOffset + kStatBytes + 1024;                   // + alignment slack
 };
 
+REPPO_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+REPPO_DEVINL float ld_dsmem_f32(const float* local_smem_ptr, uint32_t cta_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(cta_rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+
 // mode: GEMM_STORE / GEMM_ACCUM / GEMM_ATOMIC.  A_MN / B_MN: operand is MN-major (reduction dim is the outer dim).
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+// NORM != NORM_NONE: forward Linear with the whole FCNN block fused into the epilogue
+//   z = x W^T + b (stored fp32 for the backward), act_out = bf16( swish( norm(z) ) ), rstd / mean per row.
+// The N = H columns of a 128-row slab are spread over the CTAs of one thread-block CLUSTER (gridDim.x CTAs of
+// BLOCK_N columns); every CTA reduces its own columns and the per-row partial (sum, sum of squares) are exchanged
+// through distributed shared memory (mapa + ld.shared::cluster) between two cluster barriers.
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int NORM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     float* __restrict__ C, int ldc, const float* __restrict__ bias, int M, int N, int K, int k_blocks_per_split,
-                    int mode, __nv_bfloat16* __restrict__ act_out, int act_ld) {
+                    int mode, __nv_bfloat16* __restrict__ act_out, int act_ld, NormArgs na) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   using S = TcSmem<BLOCK_N, STAGES>;
@@ -215,6 +234,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     float* stg = reinterpret_cast<float*>(smem) + ew * 32 * kStgLd;
     const int lane_base = (warp & 3) * 32;
     const int cbase = (ew >> 2) * kCols;
+    float s1 = 0.f, s2 = 0.f;   // fused norm: this thread's row, this warp's columns
 #pragma unroll 1
     for (int c0 = 0; c0 < kCols; c0 += 32) {
       float v[32];
@@ -224,12 +244,34 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
+      if constexpr (NORM != NORM_NONE) {
+        // bias first: the statistics are those of z = x W^T + b
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] += bias[n0 + cbase + c0 + j];
+          s1 += v[j];
+          s2 += v[j] * v[j];
+        }
+      }
       float4* dst = reinterpret_cast<float4*>(stg + lane * kStgLd + c0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
+    if constexpr (NORM != NORM_NONE) {
+      float* part = reinterpret_cast<float*>(smem + S::kStatOffset);        // [2 stats][2 halves][128 rows]
+      float* cta_stat = part + 4 * 128;                                      // [2 stats][128 rows]
+      const int rrow = lane_base + lane, half = ew >> 2;
+      part[(0 * 2 + half) * 128 + rrow] = s1;
+      part[(1 * 2 + half) * 128 + rrow] = s2;
+      asm volatile("bar.sync 1, 256;" ::: "memory");                       // the 8 epilogue warps
+      if (half == 0) {
+        cta_stat[rrow] = part[0 * 128 + rrow] + part[1 * 128 + rrow];
+        cta_stat[128 + rrow] = part[2 * 128 + rrow] + part[3 * 128 + rrow];
+      }
+    }
     __syncwarp();
     const bool add_bias = (bias != nullptr) && (blockIdx.z == 0);
+    if constexpr (NORM == NORM_NONE) {
     const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (mode != GEMM_ATOMIC) &&
                         (act_out == nullptr || (act_ld & 3) == 0);
     if (vec_ok) {
@@ -294,7 +336,63 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
     }
+    }  // NORM == NORM_NONE
     tc_fence_before();
+  }
+  if constexpr (NORM != NORM_NONE) {
+    // ---- every thread of every CTA of the cluster: row statistics are published ----
+    cluster_sync_all();
+    if (warp >= 2) {
+      constexpr int kCols = BLOCK_N / 2;
+      constexpr int kStgLd = kCols + 4;
+      const int ew = warp - 2;
+      const float* stg = reinterpret_cast<const float*>(smem) + ew * 32 * kStgLd;
+      const int lane_base = (warp & 3) * 32, cbase = (ew >> 2) * kCols, rrow = lane_base + lane;
+      float* part = reinterpret_cast<float*>(smem + S::kStatOffset);
+      const float* cta_stat = part + 4 * 128;
+      float* rs = part + 6 * 128 + ew * 32;          // per-warp copies of the row statistics
+      float* mu = part + 6 * 128 + 8 * 32 + ew * 32;
+      float t1 = 0.f, t2 = 0.f;
+      const uint32_t ncta = gridDim.x;                // cluster spans the whole row
+      for (uint32_t r = 0; r < ncta; ++r) { t1 += ld_dsmem_f32(cta_stat + rrow, r); t2 += ld_dsmem_f32(cta_stat + 128 + rrow, r); }
+      const float inv_n = 1.f / static_cast<float>(N);
+      float mean = 0.f, rstd;
+      if (NORM == NORM_RMS) {
+        rstd = rsqrtf(t2 * inv_n + na.eps);
+      } else {
+        mean = t1 * inv_n;
+        rstd = rsqrtf(t2 * inv_n - mean * mean + na.eps);   // flax use_fast_variance
+      }
+      rs[lane] = rstd; mu[lane] = mean;
+      if (blockIdx.x == 0 && (ew >> 2) == 0 && m0 + rrow < M) {
+        na.rstd_out[m0 + rrow] = rstd;
+        if (NORM == NORM_LAYER) na.mean_out[m0 + rrow] = mean;
+      }
+      __syncwarp();
+      constexpr int kLanesPerRow = kCols / 4, kRowsPerIter = 32 / kLanesPerRow;
+      const int cl = (lane % kLanesPerRow) * 4;
+      const int col = n0 + cbase + cl;
+      float g[4], be[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { g[j] = na.gamma[col + j]; if (NORM == NORM_LAYER) be[j] = na.beta[col + j]; }
+#pragma unroll 4
+      for (int r = lane / kLanesPerRow; r < 32; r += kRowsPerIter) {
+        const int row = m0 + lane_base + r;
+        if (row >= M) continue;
+        const float4 x = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);   // z (bias included)
+        *reinterpret_cast<float4*>(C + static_cast<size_t>(row) * ldc + col) = x;
+        const float rr = rs[r], mm = mu[r];
+        const float y0 = swishf_((x.x - mm) * rr * g[0] + be[0]), y1 = swishf_((x.y - mm) * rr * g[1] + be[1]);
+        const float y2 = swishf_((x.z - mm) * rr * g[2] + be[2]), y3 = swishf_((x.w - mm) * rr * g[3] + be[3]);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(y0, y1), hi = __floats2bfloat162_rn(y2, y3);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&lo);
+        u.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(act_out + static_cast<size_t>(row) * act_ld + col) = u;
+      }
+    }
+    // ---- nobody leaves (and frees its shared memory) while a peer may still read it ----
+    cluster_sync_all();
   }
   __syncthreads();
   if (warp == 0) {
@@ -338,7 +436,7 @@ static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float
                              int K, int split_k, int mode, __nv_bfloat16* act_out, int act_ld, cudaStream_t st) {
   using S = TcSmem<BLOCK_N, STAGES>;
   static bool configured = false;
-  auto kern = gemm_bf16_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
+  auto kern = gemm_bf16_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN, NORM_NONE>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) return e;
@@ -351,8 +449,61 @@ static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float
   split_k = (total_kb + per - 1) / per;
   if (split_k > 1) mode = GEMM_ATOMIC;
   dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + TC_BLOCK_M - 1) / TC_BLOCK_M, split_k);
-  launch_k((kern), dim3(grid), dim3(TC_THREADS), S::kTotal, st, ta, tb, C, ldc, bias, M, N, K, per, mode, act_out, act_ld);
+  launch_k((kern), dim3(grid), dim3(TC_THREADS), S::kTotal, st, ta, tb, C, ldc, bias, M, N, K, per, mode, act_out, act_ld, NormArgs{});
   return cudaGetLastError();
+}
+
+// forward Linear + bias + RMS/LayerNorm + swish in one kernel; one cluster of N / BLOCK_N CTAs per 128-row slab
+template <int BLOCK_N, int NORM>
+static cudaError_t launch_tc_norm(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int ldc, const float* bias, int M,
+                                  int N, int K, __nv_bfloat16* act_out, int act_ld, const NormArgs& na, cudaStream_t st) {
+  using S = TcSmem<BLOCK_N, 4>;
+  static bool configured = false;
+  auto kern = gemm_bf16_tc_kernel<BLOCK_N, 4, false, false, NORM>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int total_kb = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(N / BLOCK_N, (M + TC_BLOCK_M - 1) / TC_BLOCK_M, 1);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = N / BLOCK_N; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, C, ldc, bias, M, N, K, total_kb, static_cast<int>(GEMM_STORE), act_out, act_ld, na);
+}
+
+// y = x W^T + b with norm + swish fused (see the kernel header).  Returns cudaErrorNotSupported when the shape does
+// not fit the cluster scheme (the caller then runs the unfused GEMM + row kernel).
+cudaError_t launch_gemm_bf16_tc_norm(int norm, int M, int N, int K, const void* A, int lda, const void* B, int ldb, float* C,
+                                     int ldc, const float* bias, void* act_out_v, int act_ld, const NormArgs& na,
+                                     cudaStream_t st) {
+  if (norm == NORM_NONE || bias == nullptr || act_out_v == nullptr) return cudaErrorNotSupported;
+  if ((lda & 7) || (ldb & 7) || (ldc & 3) || (act_ld & 3) || (reinterpret_cast<uintptr_t>(A) & 15) ||
+      (reinterpret_cast<uintptr_t>(B) & 15) || (reinterpret_cast<uintptr_t>(C) & 15))
+    return cudaErrorNotSupported;
+  int block_n = 0;
+  if (N % 64 == 0 && N / 64 <= 8) block_n = 64;            // portable cluster size <= 8
+  else if (N % 128 == 0 && N / 128 <= 8) block_n = 128;
+  if (block_n == 0) return cudaErrorNotSupported;
+  CUtensorMap ta, tb;
+  if (!encode_2d(&ta, A, M, K, lda, TC_BLOCK_K, TC_BLOCK_M) || !encode_2d(&tb, B, N, K, ldb, TC_BLOCK_K, block_n))
+    return cudaErrorInvalidValue;
+  __nv_bfloat16* act_out = static_cast<__nv_bfloat16*>(act_out_v);
+  if (block_n == 64) {
+    return norm == NORM_RMS ? launch_tc_norm<64, NORM_RMS>(ta, tb, C, ldc, bias, M, N, K, act_out, act_ld, na, st)
+                            : launch_tc_norm<64, NORM_LAYER>(ta, tb, C, ldc, bias, M, N, K, act_out, act_ld, na, st);
+  }
+  return norm == NORM_RMS ? launch_tc_norm<128, NORM_RMS>(ta, tb, C, ldc, bias, M, N, K, act_out, act_ld, na, st)
+                          : launch_tc_norm<128, NORM_LAYER>(ta, tb, C, ldc, bias, M, N, K, act_out, act_ld, na, st);
 }
 
 // A, B: bf16 device pointers, row-major with leading dimensions lda / ldb (elements, multiples of 8).

@@ -50,6 +50,10 @@ cudaError_t launch_gemm_f32(bool ta, bool tb, int M, int N, int K, const float* 
 cudaError_t launch_gemm_bf16_tc(bool a_mn, bool b_mn, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
                                 float* C, int ldc, const float* bias, int mode, int split_k, void* act_out, int act_ld,
                                 cudaStream_t st);
+// fused forward Linear + bias + norm + swish (cluster / DSMEM row statistics); cudaErrorNotSupported = shape not eligible
+struct NormArgs { const float* gamma; const float* beta; float eps; float* rstd_out; float* mean_out; };
+cudaError_t launch_gemm_bf16_tc_norm(int norm, int M, int N, int K, const void* A, int lda, const void* B, int ldb, float* C,
+                                     int ldc, const float* bias, void* act_out, int act_ld, const NormArgs& na, cudaStream_t st);
 // fp32 -> bf16 copies: plain (row-padded) and, for weights, the [out,in] matrix plus its transpose
 struct PackEntry { const float* w; void* wb; void* wtb; int out, in, ld_b, ld_t; };
 constexpr int kMaxPack = 16;

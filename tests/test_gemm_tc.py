@@ -67,3 +67,41 @@ def test_forward_is_deterministic_and_row_independent():
     assert torch.equal(y1, y2)
     y3 = eng.linear(0, x[:1000].contiguous(), w)
     assert torch.equal(y3, y1[:1000])
+
+
+@pytest.mark.parametrize("H,norm", [(512, "rms"), (256, "layer"), (1024, "rms"), (128, "rms")])
+def test_fused_norm_epilogue_matches_unfused(H, norm, monkeypatch):
+    """Linear + bias + norm + swish fused into the tcgen05 epilogue (cluster-wide row statistics over DSMEM) against
+    the unfused GEMM + row kernel on the same bf16 operands, and both against the fp32 oracle forward."""
+    from oracle import reppo_oracle as O
+    from reppo_b200.engine import EngineConfig, ReppoEngine
+    hp = O.Hyper(critic_hidden_dim=H, actor_hidden_dim=H, norm_type=norm, obs_dim=17, critic_obs_dim=17, action_dim=6,
+                 num_bins=151, vmin=0.0, vmax=150.0)
+    cp, ap = O.init_params(hp, O.JAX, seed=3)
+    g = torch.Generator().manual_seed(0)
+    for d in (cp, ap):
+        for k in d:
+            if k.endswith(".1.weight") or k.endswith(".1.bias") or k.endswith(".0.bias"):
+                d[k] = d[k] + 0.1 * torch.randn(d[k].shape, generator=g)
+    rows = 300
+    co, ob = torch.randn(rows, 17, generator=g), torch.randn(rows, 17, generator=g)
+    ac = torch.tanh(torch.randn(rows, 6, generator=g))
+    outs = []
+    for fuse in (True, False):
+        if fuse:
+            monkeypatch.delenv("REPPO_NO_FUSE_NORM", raising=False)
+        else:
+            monkeypatch.setenv("REPPO_NO_FUSE_NORM", "1")
+        eng = ReppoEngine(EngineConfig(obs_dim=17, action_dim=6, critic_hidden_dim=H, actor_hidden_dim=H, num_bins=151,
+                                       norm_type=norm, semantics="jax", gemm_mode="bf16", max_rows=512))
+        eng.load_params(cp, ap)
+        v, lg, pr, ft = eng.critic_forward(co, ac)
+        mu, sd = eng.actor_forward(ob)
+        outs.append([t.clone() for t in (v, lg, pr, ft, mu, sd)])
+    for a, b in zip(*outs):
+        torch.testing.assert_close(a, b, rtol=2e-3, atol=2e-3 * max(1.0, b.abs().max().item()))
+    v0, l0, p0, f0 = O.critic_forward(cp, co, ac, hp, O.JAX)
+    m0, s0 = O.actor_forward(ap, ob, hp, O.JAX)
+    for got, want in zip(outs[0], (v0, l0, p0, f0, m0, s0)):
+        scale = want.abs().max().item()
+        assert (got.cpu() - want).abs().max().item() <= 3e-2 * max(scale, 1.0)
