@@ -259,8 +259,12 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
 
 int wgrad_split(int out, int in, int rows, bool tc) {
   if (tc) {
+    static const char* env = getenv("REPPO_WGRAD_SPLIT");
+    if (env != nullptr && atoi(env) > 0) return std::min(atoi(env), std::max(1, rows / 64));
+    // measured at C2 (512 x 512 x 2048 rows): split 1 / 2 / 4 / 8 / 16 -> 160.9 / 147.8 / 140.9 / 147.7 / 166.9 ms per update.
+    // The weight-gradient GEMMs run beside the dgrad chain: ~64 CTAs keep the chain's SMs free and the atomics few.
     const int tiles = ((out + 127) / 128) * ((in + 127) / 128);
-    int split = std::max(1, 128 / std::max(1, tiles));
+    int split = std::max(1, 64 / std::max(1, tiles));
     return std::min(split, std::max(1, rows / 128));
   }
   const int tiles = ((out + 63) / 64) * ((in + 63) / 64);
