@@ -169,13 +169,11 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
                   int ldh, float* __restrict__ dbias) {
   REPPO_PDL_PROLOGUE();
   __shared__ float sm[8 * 3];
-  extern __shared__ float scol[];  // [P] column sums of dpred (only when dbias != nullptr)
+  extern __shared__ float scol[];  // [8 warps][P]: each warp parks its row of dpred (only when dbias != nullptr)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float vals[3] = {0.f, 0.f, 0.f};
-  if (dbias != nullptr) {
-    for (int c = threadIdx.x; c < P; c += blockDim.x) scol[c] = 0.f;
-    __syncthreads();
-  }
+  if (dbias != nullptr)
+    for (int c = lane; c < P; c += 32) scol[warp * P + c] = 0.f;   // rows past the end contribute nothing
   for (int rr = 0; rr < kLossRowsPerBlock / 8; ++rr) {
     const int row = blockIdx.x * kLossRowsPerBlock + rr * 8 + warp;
     if (row >= rows) break;
@@ -193,7 +191,7 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
       const float d = pr[off + c] - ne[c];
       sq += d * d;
       dr[off + c] = g * d;
-      if (dbias != nullptr) atomicAdd(&scol[off + c], g * d);
+      if (dbias != nullptr) scol[warp * P + off + c] = g * d;
       if (dp_h != nullptr) dp_h[static_cast<size_t>(row) * ldh + off + c] = __float2bfloat16_rn(g * d);
     }
     float r = 0.f;
@@ -203,7 +201,7 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
         const float d = pr[0] - r;
         sq += d * d;
         dr[0] = g * d;
-        if (dbias != nullptr) atomicAdd(&scol[0], g * d);
+        if (dbias != nullptr) scol[warp * P] = g * d;
         if (dp_h != nullptr) dp_h[static_cast<size_t>(row) * ldh] = __float2bfloat16_rn(g * d);
       }
     }
@@ -216,7 +214,12 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
   float* dst[3] = {metrics + M_CRITIC_LOSS, metrics + M_AUX_MEAN, metrics + M_REWARD_MEAN};
   block_metric_add<3>(vals, sm, dst);   // contains a __syncthreads: scol is complete afterwards
   if (dbias != nullptr)
-    for (int c = threadIdx.x; c < P; c += blockDim.x) atomicAdd(dbias + c, scol[c]);
+    for (int c = threadIdx.x; c < P; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += scol[w * P + c];
+      atomicAdd(dbias + c, t);
+    }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -430,7 +433,15 @@ cudaError_t launch_critic_aux(const float* pred, int P, int H, int reward_head, 
                               const float* reward, const float* done, const float* truncated, const int* idx, int rows,
                               float inv_rows, int no_mask, float aux_mult, float* dpred, float* metrics, void* dp_h, int ldh,
                               float* dbias, cudaStream_t st) {
-  const size_t smem = dbias ? static_cast<size_t>(P) * sizeof(float) : 0;
+  const size_t smem = dbias ? 8 * static_cast<size_t>(P) * sizeof(float) : 0;
+  if (smem > 48 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(critic_aux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2049 * 4);
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+  }
   launch_k((critic_aux_kernel), dim3((rows + kLossRowsPerBlock - 1) / kLossRowsPerBlock), dim3(256), smem, st, pred, P, H, reward_head, mask_done, next_emb, reward, done, truncated, idx, rows, inv_rows, no_mask, aux_mult, dpred, metrics, static_cast<__nv_bfloat16*>(dp_h), ldh, dbias);
   return cudaGetLastError();
 }
