@@ -246,17 +246,8 @@ def main():
     eng = ts.engine
     eng.load_params(cp, ap_)
     if world > 1:
-        import ctypes as C
-        from reppo_b200 import _lib as L
-        idbuf = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            raw = C.create_string_buffer(128)
-            L.check(eng.lib.reppo_nccl_unique_id(eng.ctx, raw), eng.ctx, "nccl id")
-            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
-        idbuf = idbuf.to(dev)
-        dist.broadcast(idbuf, 0)
-        raw = bytes(idbuf.cpu().tolist())
-        L.check(eng.lib.reppo_nccl_init(eng.ctx, raw, rank, world), eng.ctx, "nccl init")
+        from reppo_b200 import dist as D
+        D.attach_nccl(eng, rank, world)   # two communicators: critic chain + actor chain
     hyp = HyperParams(gamma=h.gamma, lmbda=h.lmbda, lr=h.lr, max_grad_norm=h.max_grad_norm, kl_bound=h.kl_bound,
                       ent_target_mult=h.ent_target_mult, aux_loss_mult=h.aux_loss_mult, actor_min_std=h.actor_min_std,
                       actor_kl_clip_mode=h.actor_kl_clip_mode, world_size=world)
@@ -381,12 +372,11 @@ def main():
             a_, b_ = torch.randn(mb, o, device=dev), torch.randn(o, i, device=dev)
         else:
             a_, b_ = torch.randn(mb, o, device=dev), torch.randn(mb, i, device=dev)
-        out = eng.linear(op, a_, b_)
-        if op == 2:
-            t_ms = time_fn(lambda: eng.lib.reppo_linear(eng.ctx, op, mb, i, o, a_.data_ptr(), b_.data_ptr(), out.data_ptr(), None,
-                                                         eng._stream()), 50)
-        else:
-            t_ms = time_fn(lambda: eng.linear(op, a_, b_, out=out), 50)
+        out = eng.linear(op, a_, b_)     # stages the bf16 operands (tensor-core mode)
+        flag = 0x100 if args.gemm == "bf16" else 0   # then time the GEMM kernel alone
+        # (wgrad accumulates into `out` with atomics: the values grow, the work per launch is unchanged)
+        t_ms = time_fn(lambda: eng.lib.reppo_linear(eng.ctx, op | flag, mb, i, o, a_.data_ptr(), b_.data_ptr(), out.data_ptr(),
+                                                     None, eng._stream()), 50)
         fl = 2.0 * mb * i * o
         gemm_ms += n * t_ms
         gemm_flops += n * fl
@@ -441,6 +431,7 @@ def main():
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_update * args.steps),
         "launches_per_update": int(launches_per_update), "cuda_graph": use_graph, "semantics": args.semantics,
         "sample_visits_per_s": value * E, "roofline": roofline, "scan": scan, "adam": adam, "cpu_baseline": cpu,
+        "knobs": {k: os.environ[k] for k in os.environ if k.startswith("REPPO_")},
         "final_metrics": {k: final_metrics[k] for k in ("critic_loss", "actor_loss", "kl", "entropy")},
     }
     print(json.dumps(line))

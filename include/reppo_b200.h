@@ -183,7 +183,9 @@ int reppo_actor_forward(reppo_ctx* ctx, const float* actor_params, const float* 
  *   op 0  forward : y[rows,out]  = x[rows,in] w[out,in]^T + bias   (bias may be NULL)
  *   op 1  dgrad   : dx[rows,in]  = dy[rows,out] w[out,in]
  *   op 2  wgrad   : dw[out,in]   = dy[rows,out]^T x[rows,in]       (dw must be zeroed by the caller)
- * a / b / c are (x, w, y), (dy, w, dx), (dy, x, dw) respectively. */
+ * a / b / c are (x, w, y), (dy, w, dx), (dy, x, dw) respectively.  In REPPO_GEMM_BF16 mode the fp32 operands are first
+ * rounded into bf16 staging buffers; op | 0x100 skips that and reuses the staging of the previous identical call
+ * (bench.py times the tcgen05 kernel alone this way). */
 int reppo_linear(reppo_ctx* ctx, int32_t op, int32_t rows, int32_t in_features, int32_t out_features, const float* a,
                  const float* b, float* c, const float* bias, reppo_stream stream);
 
@@ -218,7 +220,9 @@ int reppo_update(reppo_ctx* ctx, const reppo_state* state, const reppo_batch* ba
 int64_t reppo_launch_count(const reppo_ctx* ctx);
 
 /* ---- data-parallel gradient all-reduce (not in the reference) ----------------
- * The library dlopen()s libnccl.so.2; rank 0 creates the 128-byte unique id, the host broadcasts it. */
+ * The library dlopen()s libnccl.so.2; rank 0 creates the 128-byte unique id, the host broadcasts it.
+ * reppo_nccl_init may be called twice (with two different ids): the first communicator serves the critic chain, the
+ * second the actor chain, which lets the step pipeline of reppo_update keep both chains in flight under DP. */
 int reppo_nccl_unique_id(reppo_ctx* ctx, void* id_out_128);
 int reppo_nccl_init(reppo_ctx* ctx, const void* id_128, int32_t rank, int32_t world_size);
 int reppo_nccl_finalize(reppo_ctx* ctx);

@@ -59,7 +59,7 @@ struct Twin {  // bf16 copy of an fp32 activation buffer (REPPO_GEMM_BF16 only)
   uint16_t* p = nullptr;
   int ld = 0;
 };
-enum { SLOT_CRITIC = 0, SLOT_ACTOR = 1, SLOT_ACTOR_OLD = 2, NUM_SLOTS = 3 };
+enum { SLOT_CRITIC = 0, SLOT_ACTOR = 1, SLOT_ACTOR_OLD = 2, SLOT_CRITIC_ALT = 3, NUM_SLOTS = 4 };
 
 // minimal NCCL surface (resolved with dlsym from libnccl.so.2)
 typedef struct ncclComm* ncclComm_t;
@@ -108,8 +108,14 @@ struct reppo_ctx {
   float *dxs = nullptr, *dxs2 = nullptr, *dfeat = nullptr, *dlogits = nullptr, *dpred = nullptr, *dout = nullptr, *dx0 = nullptr;
   float *logp = nullptr, *kl = nullptr, *q = nullptr, *gmu = nullptr, *gsig = nullptr, *scratch_metrics = nullptr;
   std::unordered_map<const float*, Twin> twins;
-  uint16_t* shadow_b[NUM_SLOTS] = {nullptr, nullptr, nullptr};
-  uint16_t* shadow_t[NUM_SLOTS] = {nullptr, nullptr, nullptr};
+  uint16_t* shadow_b[NUM_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  // step pipelining: second copy of the critic parameters (Adam ping-pongs between the two), and a private set of
+  // critic-trunk buffers for the actor step, so that critic step k+1 can overlap actor step k
+  float* cp_alt = nullptr;
+  Acts fa2, ha2;
+  float *xs2 = nullptr, *dxs_a = nullptr, *dfeat_a = nullptr, *dlogits_a = nullptr, *partials2 = nullptr;
+  bool pipeline = true;       // REPPO_NO_PIPELINE=1 disables
+  cudaEvent_t ev_c[4] = {nullptr, nullptr, nullptr, nullptr}, ev_a[4] = {nullptr, nullptr, nullptr, nullptr};
   uint16_t *lin_a = nullptr, *lin_b = nullptr, *lin_c = nullptr;  // scratch operands of reppo_linear
   std::string err;
   int64_t launches = 0;
@@ -123,12 +129,12 @@ struct reppo_ctx {
   // parallel branches): [0] pred-head branch, [1] weight-gradient GEMMs, [2] actor-only prefix of the actor step
   bool concurrent = true;
   bool fuse_norm = true;   // REPPO_NO_FUSE_NORM=1: separate GEMM + norm/swish kernels
-  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // [3]: weight gradients of the actor chain
   std::vector<cudaEvent_t> events;
   size_t ev_next = 0;
   // nccl
   NcclApi nccl;
-  ncclComm_t comm = nullptr;
+  ncclComm_t comm[2] = {nullptr, nullptr};   // [0] critic chain, [1] actor chain (optional: enables step pipelining under DP)
   int world = 1, rank = 0;
 
   Twin twin(const float* p) const {
@@ -242,6 +248,9 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
   acts(c->fa, c->feature, H); acts(c->ha, c->head, B); acts(c->pa, c->pred, P);
   acts(c->aa, c->actor, 2 * A); acts(c->oa, c->actor, 2 * A);
   bwd_scratch(c->fa, c->feature); bwd_scratch(c->ha, c->head); bwd_scratch(c->pa, c->pred); bwd_scratch(c->aa, c->actor);
+  acts(c->fa2, c->feature, H); acts(c->ha2, c->head, B); bwd_scratch(c->fa2, c->feature); bwd_scratch(c->ha2, c->head);
+  c->xs2 = FT(H); c->dxs_a = F(R * H); c->dfeat_a = FT(H); c->dlogits_a = FT(B); c->partials2 = F(kMaxPartials);
+  c->cp_alt = F(static_cast<size_t>(c->critic_count) + 4);
   const size_t maxdim = c->maxdim;
   c->x0a = FT(K0);
   c->dxs = F(R * H); c->dxs2 = F(R * H); c->dfeat = FT(H); c->dlogits = FT(B); c->dpred = FT(P); c->dout = FT(2 * A);
@@ -251,6 +260,7 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
     c->shadow_b[SLOT_CRITIC] = Hf(c->shadow_b_elems[0]);
     c->shadow_b[SLOT_ACTOR] = Hf(c->shadow_b_elems[1]);
     c->shadow_b[SLOT_ACTOR_OLD] = Hf(c->shadow_b_elems[1]);
+    c->shadow_b[SLOT_CRITIC_ALT] = Hf(c->shadow_b_elems[0]);
     const size_t md8 = round8(static_cast<int>(maxdim));
     c->lin_a = Hf(R * md8); c->lin_c = Hf(R * md8); c->lin_b = Hf(maxdim * md8);
   }
@@ -325,7 +335,7 @@ int pack_shadows(reppo_ctx* c, int slot, const float* params, cudaStream_t st) {
       e.out = L.out; e.in = L.in; e.ld_b = L.ld_b; e.ld_t = L.ld_t;
     }
   };
-  if (slot == SLOT_CRITIC) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
+  if (slot == SLOT_CRITIC || slot == SLOT_CRITIC_ALT) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
   CK(launch_pack_weights(t, st));
   return REPPO_OK;
 }
@@ -381,9 +391,13 @@ int dep(reppo_ctx* c, cudaStream_t from, cudaStream_t to) {
 
 int ensure_streams(reppo_ctx* c) {
   if (!c->events.empty()) return REPPO_OK;
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 4; ++i)
     if (cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking) != cudaSuccess)
       return fail(c, REPPO_ERR_CUDA, "cudaStreamCreate failed");
+  for (int i = 0; i < 4; ++i)
+    if (cudaEventCreateWithFlags(&c->ev_c[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_a[i], cudaEventDisableTiming) != cudaSuccess)
+      return fail(c, REPPO_ERR_CUDA, "cudaEventCreate failed");
   c->events.resize(64);
   for (auto& e : c->events)
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaEventCreate failed");
@@ -432,31 +446,36 @@ int check_rows(reppo_ctx* c, int rows) {
   return REPPO_OK;
 }
 
-int critic_trunk_encoder(reppo_ctx* c, const float* cp, const float* x0, int rows, cudaStream_t st);
-int critic_trunk(reppo_ctx* c, const float* cp, const float* x0, int rows, bool with_pred, cudaStream_t st) {
-  RET(critic_trunk_encoder(c, cp, x0, rows, st));
-  RET(mlp_forward(c, c->head, cp, SLOT_CRITIC, c->xs, rows, c->ha, st));
-  if (with_pred) RET(mlp_forward(c, c->pred, cp, SLOT_CRITIC, c->xs, rows, c->pa, st));
-  return REPPO_OK;
-}
+// the buffers one evaluation of the critic trunk (encoder + categorical head) runs in
+struct TrunkBufs { Acts* fa; Acts* ha; float* xs; float* dxs; float* dfeat; float* dlogits; };
+TrunkBufs trunk_main(reppo_ctx* c) { return TrunkBufs{&c->fa, &c->ha, c->xs, c->dxs, c->dfeat, c->dlogits}; }
+TrunkBufs trunk_actor(reppo_ctx* c) { return TrunkBufs{&c->fa2, &c->ha2, c->xs2, c->dxs_a, c->dfeat_a, c->dlogits_a}; }
 
 // encoder + swish(features) -> xs
-int critic_trunk_encoder(reppo_ctx* c, const float* cp, const float* x0, int rows, cudaStream_t st) {
-  const Twin tw = c->twin(c->xs);
+int critic_trunk_encoder(reppo_ctx* c, const float* cp, int cslot, const float* x0, int rows, const TrunkBufs& tb, cudaStream_t st) {
+  const Twin tw = c->twin(tb.xs);
   if (c->tc && getenv("REPPO_NO_FUSE_ACT") == nullptr) {
     // swish(features), the input of both heads, leaves the encoder's last GEMM epilogue directly as bf16
-    RET(mlp_forward(c, c->feature, cp, SLOT_CRITIC, x0, rows, c->fa, st, tw));
+    RET(mlp_forward(c, c->feature, cp, cslot, x0, rows, *tb.fa, st, tw));
   } else {
-    RET(mlp_forward(c, c->feature, cp, SLOT_CRITIC, x0, rows, c->fa, st));
-    CK(launch_norm_act_fwd(NORM_NONE, c->fa.out, nullptr, nullptr, rows, c->shape.critic_hidden, 0.f, c->tc ? nullptr : c->xs,
+    RET(mlp_forward(c, c->feature, cp, cslot, x0, rows, *tb.fa, st));
+    CK(launch_norm_act_fwd(NORM_NONE, tb.fa->out, nullptr, nullptr, rows, c->shape.critic_hidden, 0.f, c->tc ? nullptr : tb.xs,
                            nullptr, nullptr, tw.p, tw.ld, st));
   }
   return REPPO_OK;
 }
+int critic_trunk(reppo_ctx* c, const float* cp, int cslot, const float* x0, int rows, bool with_pred, const TrunkBufs& tb,
+                 cudaStream_t st) {
+  RET(critic_trunk_encoder(c, cp, cslot, x0, rows, tb, st));
+  RET(mlp_forward(c, c->head, cp, cslot, tb.xs, rows, *tb.ha, st));
+  if (with_pred) RET(mlp_forward(c, c->pred, cp, cslot, tb.xs, rows, c->pa, st));
+  return REPPO_OK;
+}
 
-int allreduce_grads(reppo_ctx* c, float* g, int64_t n, cudaStream_t st) {
-  if (c->comm == nullptr) return REPPO_OK;
-  const int r = c->nccl.AllReduce(g, g, static_cast<size_t>(n), /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, st);
+int allreduce_grads(reppo_ctx* c, float* g, int64_t n, int chain, cudaStream_t st) {
+  if (c->comm[0] == nullptr) return REPPO_OK;
+  ncclComm_t comm = (chain == 1 && c->comm[1] != nullptr) ? c->comm[1] : c->comm[0];
+  const int r = c->nccl.AllReduce(g, g, static_cast<size_t>(n), /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, st);
   ++c->launches;
   if (r != 0) return fail(c, REPPO_ERR_NCCL, std::string("ncclAllReduce: ") + c->nccl.GetErrorString(r));
   return REPPO_OK;
@@ -467,11 +486,11 @@ float inv_rows(const reppo_hyper* hp, int mb) {
   return 1.f / (static_cast<float>(mb) * static_cast<float>(w));
 }
 
+// cp / cslot: the critic parameters (and their bf16 shadow slot) this step READS
 int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb,
-                     const reppo_hyper* hp, float* metrics, cudaStream_t st) {
+                     const reppo_hyper* hp, float* metrics, const float* cp, int cslot, cudaStream_t st) {
   RET(check_rows(c, mb));
   const reppo_shape& sh = c->shape;
-  const float* cp = s->critic.params;
   float* cg = s->critic.grads;
   const float inv = inv_rows(hp, mb);
   const int no_mask = (sh.semantics == REPPO_SEM_TORCH && hp->partial_reset) ? 1 : 0;
@@ -485,28 +504,28 @@ int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
   Twin tw = c->twin(c->x0);
   CK(launch_gather_concat(b->critic_obs, sh.critic_obs_dim, b->action, sh.action_dim, idx, 0, mb, c->x0, c->K0, tw.p, tw.ld, st));
   // encoder, then swish(features) feeds two independent heads
-  RET(critic_trunk_encoder(c, cp, c->x0, mb, st));
+  RET(critic_trunk_encoder(c, cp, cslot, c->x0, mb, trunk_main(c), st));
   RET(dep(c, st, s1));
   // --- branch s1: prediction head forward, aux loss, backward down to d swish(features)
-  RET(mlp_forward(c, c->pred, cp, SLOT_CRITIC, c->xs, mb, c->pa, s1));
+  RET(mlp_forward(c, c->pred, cp, cslot, c->xs, mb, c->pa, s1));
   tw = c->twin(c->dpred);
   CK(launch_critic_aux(c->pa.out, c->pred_out, Hc, c->sem.reward_head, c->sem.aux_mask_done, b->next_emb, b->reward, b->done,
                        b->truncated, idx, mb, inv, no_mask, hp->aux_loss_mult, c->dpred, metrics, tw.p, tw.ld,
                        cg + c->pred.layers.back().b, s1));
-  RET(mlp_backward(c, c->pred, cp, SLOT_CRITIC, cg, c->xs, mb, c->pa, c->dpred, c->dxs2, GEMM_STORE, nullptr, 0.f, true, s1, sw));
+  RET(mlp_backward(c, c->pred, cp, cslot, cg, c->xs, mb, c->pa, c->dpred, c->dxs2, GEMM_STORE, nullptr, 0.f, true, s1, sw));
   // --- main: categorical head forward, HL-Gauss cross-entropy, backward (the loss kernels also accumulate the
   //     bias / zero_dist gradients of the two last layers)
-  RET(mlp_forward(c, c->head, cp, SLOT_CRITIC, c->xs, mb, c->ha, st));
+  RET(mlp_forward(c, c->head, cp, cslot, c->xs, mb, c->ha, st));
   tw = c->twin(c->dlogits);
   CK(launch_critic_ce(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, b->target, b->truncated, idx, mb, inv, no_mask,
                       c->dlogits, metrics, tw.p, tw.ld, cg + c->head.layers.back().b, cg + c->zero_dist_off, st));
-  RET(mlp_backward(c, c->head, cp, SLOT_CRITIC, cg, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, true, st, sw));
+  RET(mlp_backward(c, c->head, cp, cslot, cg, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, true, st, sw));
   RET(dep(c, s1, st));
   // d feat = (d swish(feat) from both heads) * swish'(feat); its column sums are the bias gradient of the encoder's last Linear
   tw = c->twin(c->dfeat);
   CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->dxs2, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, Hc,
                          c->tc ? nullptr : c->dfeat, nullptr, nullptr, cg + c->feature.layers.back().b, tw.p, tw.ld, st));
-  RET(mlp_backward(c, c->feature, cp, SLOT_CRITIC, cg, c->x0, mb, c->fa, c->dfeat, nullptr, GEMM_STORE, nullptr, 0.f, true, st, sw));
+  RET(mlp_backward(c, c->feature, cp, cslot, cg, c->x0, mb, c->fa, c->dfeat, nullptr, GEMM_STORE, nullptr, 0.f, true, st, sw));
   RET(dep(c, sw, st));
   return REPPO_OK;
 }
@@ -530,18 +549,19 @@ ActorConsts actor_consts(const reppo_ctx* c, const reppo_hyper* hp) {
 // old_table: optional [S, 2A] behaviour-policy outputs for every batch row (precomputed once per update)
 int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb,
                     const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, const float* old_table,
-                    cudaStream_t prefix_stream, cudaStream_t st) {
+                    cudaStream_t prefix_stream, const float* cp, int cslot, cudaEvent_t critic_ready, cudaEvent_t critic_read_done,
+                    cudaStream_t st) {
   RET(check_rows(c, mb));
   if (hp->kl_clip_mode < 0 || hp->kl_clip_mode > 2) return fail(c, REPPO_ERR_INVALID, "unknown actor_kl_clip_mode");
   const reppo_shape& sh = c->shape;
   const int A = sh.action_dim, Dc = sh.critic_obs_dim;
-  const float* cp = s->critic.params;
+  const TrunkBufs tb = trunk_actor(c);
   const float* ap = s->actor.params;
   float* ag = s->actor.grads;
   const float inv = inv_rows(hp, mb);
   const ActorConsts ac = actor_consts(c, hp);
   RET(ensure_streams(c));
-  cudaStream_t sw = c->concurrent ? c->side[1] : st;
+  cudaStream_t sw = c->concurrent ? c->side[3] : st;
   // The actor-only prefix (policy forward, sampling, KL statistics) does not depend on the critic update that precedes
   // it on `st`: when `pre` is a different stream it overlaps the critic step (the caller forked it before that step).
   cudaStream_t pre = prefix_stream ? prefix_stream : st;
@@ -558,15 +578,20 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
                          tx0.ld, pre));
   RET(dep(c, pre, st));
   // Q(s, a) through the (already updated, frozen) critic and dQ/da
-  RET(critic_trunk(c, cp, c->x0a, mb, false, st));
-  tw = c->twin(c->dlogits);
-  CK(launch_actor_q(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, c->kl, mb, inv, ac.kl_mode, ac.kl_bound, c->q,
-                    c->dlogits, tw.p, tw.ld, st));
-  RET(mlp_backward(c, c->head, cp, SLOT_CRITIC, nullptr, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, false, st, st));
-  tw = c->twin(c->dfeat);
-  CK(launch_norm_act_bwd(NORM_NONE, c->dxs, nullptr, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden,
-                         c->tc ? nullptr : c->dfeat, nullptr, nullptr, nullptr, tw.p, tw.ld, st));
-  RET(mlp_backward(c, c->feature, cp, SLOT_CRITIC, nullptr, c->x0a, mb, c->fa, c->dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, false, st, st));
+  if (critic_ready != nullptr && cudaStreamWaitEvent(st, critic_ready, 0) != cudaSuccess)
+    return fail(c, REPPO_ERR_CUDA, "cudaStreamWaitEvent failed");
+  RET(critic_trunk(c, cp, cslot, c->x0a, mb, false, tb, st));
+  tw = c->twin(tb.dlogits);
+  CK(launch_actor_q(tb.ha->out, sh.num_bins, cp + c->zero_dist_off, c->hl, c->kl, mb, inv, ac.kl_mode, ac.kl_bound, c->q,
+                    tb.dlogits, tw.p, tw.ld, st));
+  RET(mlp_backward(c, c->head, cp, cslot, nullptr, tb.xs, mb, *tb.ha, tb.dlogits, tb.dxs, GEMM_STORE, nullptr, 0.f, false, st, st));
+  tw = c->twin(tb.dfeat);
+  CK(launch_norm_act_bwd(NORM_NONE, tb.dxs, nullptr, tb.fa->out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden,
+                         c->tc ? nullptr : tb.dfeat, nullptr, nullptr, nullptr, tw.p, tw.ld, st));
+  RET(mlp_backward(c, c->feature, cp, cslot, nullptr, c->x0a, mb, *tb.fa, tb.dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, false, st, st));
+  // last read of the critic snapshot: the critic chain may overwrite it from here on
+  if (critic_read_done != nullptr && cudaEventRecord(critic_read_done, st) != cudaSuccess)
+    return fail(c, REPPO_ERR_CUDA, "cudaEventRecord failed");
   tw = c->twin(c->dout);
   CK(launch_actor_grad(c->aa.out, eps_pi, c->x0a + Dc, c->K0, c->dx0 + Dc, c->K0, c->logp, c->kl, c->q, c->gmu, c->gsig, ap,
                        mb, A, inv, ac, c->dout, ag, metrics, tw.p, tw.ld, ag + c->actor.layers.back().b, st));
@@ -576,8 +601,9 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
 }
 
 // slot < 0: plain arena (no bf16 shadow to refresh)
+// p_out: where the updated parameters go (nullptr = in place); partials: scratch of the global-norm reduction
 int clip_adam_impl(reppo_ctx* c, const reppo_net_state* net, int64_t n, const reppo_hyper* hp, float* gn_out, int slot,
-                   cudaStream_t st) {
+                   const float* p_in, float* p_out, float* partials, cudaStream_t st) {
   if (c->ws == nullptr) return fail(c, REPPO_ERR_WORKSPACE, "workspace not set (reppo_set_workspace)");
   ShadowTable sh{};
   if (c->tc && slot >= 0) {
@@ -588,37 +614,45 @@ int clip_adam_impl(reppo_ctx* c, const reppo_net_state* net, int64_t n, const re
         e.dst = c->shadow_b[slot] + L.sb;
       }
     };
-    if (slot == SLOT_CRITIC) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
+    if (slot == SLOT_CRITIC || slot == SLOT_CRITIC_ALT) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
   }
   AdamConsts a{};
   a.lr = hp->lr; a.b1 = 0.9f; a.b2 = 0.999f; a.eps = 1e-8f;
   a.weight_decay = c->sem.torch_opt ? 0.01f : 0.f;  // torch.optim.AdamW default (src/torchrl/reppo.py:527-534)
   a.max_grad_norm = hp->max_grad_norm;
   a.torch_clip = c->sem.torch_opt;
-  CK(launch_clip_adam(net->params, net->grads, net->adam_m, net->adam_v, n, net->step, c->partials, a, &sh, gn_out, st));
+  CK(launch_clip_adam(p_in ? p_in : net->params, p_out ? p_out : net->params, net->grads, net->adam_m, net->adam_v, n, net->step,
+                      partials ? partials : c->partials, a, &sh, gn_out, st));
   ++c->launches;  // two kernels
   return REPPO_OK;
 }
 
 int critic_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb,
                      const reppo_hyper* hp, float* metrics, cudaStream_t st) {
-  RET(critic_grad_impl(c, s, b, idx, mb, hp, metrics, st));
-  RET(allreduce_grads(c, s->critic.grads, c->critic_count, st));
-  return clip_adam_impl(c, &s->critic, c->critic_count, hp, metrics + M_CRITIC_GRAD_NORM, SLOT_CRITIC, st);
+  RET(critic_grad_impl(c, s, b, idx, mb, hp, metrics, s->critic.params, SLOT_CRITIC, st));
+  RET(allreduce_grads(c, s->critic.grads, c->critic_count, 0, st));
+  return clip_adam_impl(c, &s->critic, c->critic_count, hp, metrics + M_CRITIC_GRAD_NORM, SLOT_CRITIC, nullptr, nullptr, nullptr, st);
 }
 
 int actor_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb, const float* eps_pi,
                     const float* eps_kl, const reppo_hyper* hp, float* metrics, const float* old_table,
                     cudaStream_t prefix_stream, cudaStream_t st) {
-  RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, old_table, prefix_stream, st));
-  RET(allreduce_grads(c, s->actor.grads, c->actor_count, st));
-  return clip_adam_impl(c, &s->actor, c->actor_count, hp, metrics + M_ACTOR_GRAD_NORM, SLOT_ACTOR, st);
+  RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, old_table, prefix_stream, s->critic.params, SLOT_CRITIC,
+                      nullptr, nullptr, st));
+  RET(allreduce_grads(c, s->actor.grads, c->actor_count, 1, st));
+  return clip_adam_impl(c, &s->actor, c->actor_count, hp, metrics + M_ACTOR_GRAD_NORM, SLOT_ACTOR, nullptr, nullptr, c->partials2, st);
 }
 
+// All epochs x minibatches.  Software pipeline over steps: the critic update of step k+1 depends only on the critic
+// update of step k, the actor update of step k only on the actor update of step k-1 and on the critic parameters
+// AFTER critic update k.  The two chains therefore run on two streams; the critic's Adam ping-pongs between two
+// copies of the critic parameters (and bf16 shadows) so that actor step k keeps reading snapshot k while critic step
+// k+1 already produces snapshot k+1.  Same arithmetic, same dependencies, half the serial chain.
 int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const reppo_plan* p, const reppo_hyper* hp,
               cudaStream_t st) {
   const int A = c->shape.action_dim, mb = p->minibatch, ks = c->shape.kl_samples;
   const int64_t per_epoch = static_cast<int64_t>(p->num_mini_batches) * mb;
+  RET(ensure_streams(c));
   RET(pack_all(c, s, st));
   if (p->old_policy_out != nullptr) {
     // behaviour policy on every batch row, once: max_rows-sized chunks through the actor's forward buffers
@@ -631,19 +665,47 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
       CK(cudaMemcpyAsync(p->old_policy_out + r0 * 2 * A, c->oa.out, sizeof(float) * rows * 2 * A, cudaMemcpyDeviceToDevice, st));
     }
   }
+  // one NCCL communicator serves one chain: pipelining under data parallelism needs the second communicator
+  const bool pipe = c->concurrent && c->pipeline && (c->comm[0] == nullptr || c->comm[1] != nullptr);
+  cudaStream_t sa = pipe ? c->side[2] : st;   // the actor chain
+  float* P[2] = {s->critic.params, pipe ? c->cp_alt : s->critic.params};
+  const int S[2] = {SLOT_CRITIC, pipe ? SLOT_CRITIC_ALT : SLOT_CRITIC};
+  if (pipe) RET(dep(c, st, sa));
+  int64_t k = 0;
   for (int e = 0; e < p->num_epochs; ++e) {
-    for (int j = 0; j < p->num_mini_batches; ++j) {
+    for (int j = 0; j < p->num_mini_batches; ++j, ++k) {
       const int64_t slot = p->noise_per_minibatch ? static_cast<int64_t>(e) * p->num_mini_batches + j : e;
       const float* eps_pi = p->eps_pi + slot * mb * A;
       const float* eps_kl = p->eps_kl + slot * ks * mb * A;
       const int32_t* idx = p->perms + e * per_epoch + static_cast<int64_t>(j) * mb;
-      const int64_t step = static_cast<int64_t>(e) * p->num_mini_batches + j;
-      float* m = p->step_metrics ? p->step_metrics + step * M_NUM : c->scratch_metrics;
-      // the actor-only prefix of this step's actor update is forked here and overlaps the critic update
-      cudaStream_t pre = nullptr;
-      if (c->concurrent) { RET(ensure_streams(c)); pre = c->side[2]; RET(dep(c, st, pre)); }
-      RET(critic_step_impl(c, s, b, idx, mb, hp, m, st));
-      RET(actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, p->old_policy_out, pre, st));
+      float* m = p->step_metrics ? p->step_metrics + k * M_NUM : c->scratch_metrics;
+      const int cur = static_cast<int>(k & 1), nxt = pipe ? static_cast<int>((k + 1) & 1) : 0;
+      if (!pipe) {
+        // the actor-only prefix of this step's actor update is forked here and overlaps the critic update
+        cudaStream_t pre = nullptr;
+        if (c->concurrent) { pre = c->side[2]; RET(dep(c, st, pre)); }
+        RET(critic_step_impl(c, s, b, idx, mb, hp, m, st));
+        RET(actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, p->old_policy_out, pre, st));
+        continue;
+      }
+      // ---- critic chain (stream st): reads snapshot `cur`, Adam writes snapshot `nxt`
+      RET(critic_grad_impl(c, s, b, idx, mb, hp, m, P[cur], S[cur], st));
+      RET(allreduce_grads(c, s->critic.grads, c->critic_count, 0, st));
+      // snapshot `nxt` was last read by actor step k-2
+      if (k >= 2 && cudaStreamWaitEvent(st, c->ev_a[(k - 2) & 3], 0) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaStreamWaitEvent failed");
+      RET(clip_adam_impl(c, &s->critic, c->critic_count, hp, m + M_CRITIC_GRAD_NORM, S[nxt], P[cur], P[nxt], c->partials, st));
+      if (cudaEventRecord(c->ev_c[k & 3], st) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaEventRecord failed");
+      // ---- actor chain (stream sa): needs snapshot `nxt`
+      RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, p->old_policy_out, nullptr, P[nxt], S[nxt], c->ev_c[k & 3],
+                          c->ev_a[k & 3], sa));
+      RET(allreduce_grads(c, s->actor.grads, c->actor_count, 1, sa));
+      RET(clip_adam_impl(c, &s->actor, c->actor_count, hp, m + M_ACTOR_GRAD_NORM, SLOT_ACTOR, nullptr, nullptr, c->partials2, sa));
+    }
+  }
+  if (pipe) {
+    RET(dep(c, sa, st));
+    if (k & 1) {  // odd number of steps: the final critic parameters sit in the alternate copy
+      CK(cudaMemcpyAsync(s->critic.params, c->cp_alt, sizeof(float) * c->critic_count, cudaMemcpyDeviceToDevice, st));
     }
   }
   if (p->metrics != nullptr && p->step_metrics != nullptr)
@@ -683,6 +745,7 @@ int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
   c->tc = (s.gemm_mode == REPPO_GEMM_BF16);
   c->concurrent = (getenv("REPPO_SERIAL") == nullptr);
   c->fuse_norm = (getenv("REPPO_NO_FUSE_NORM") == nullptr);
+  c->pipeline = (getenv("REPPO_NO_PIPELINE") == nullptr);
   if (s.semantics == REPPO_SEM_JAX) {
     // flax RMSNorm/LayerNorm eps 1e-6; logits + 40.0 * zero_dist (jax_models.py:298); clip 1-1e-4
     // (jaxrl/reppo.py:558); min_std 0.1 because the constructor ignores cfg (jax_models.py:336);
@@ -735,8 +798,8 @@ void reppo_ctx_destroy(reppo_ctx* c) {
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   for (auto& e : c->events) cudaEventDestroy(e);
-  for (int i = 0; i < 3; ++i) if (c->side[i]) cudaStreamDestroy(c->side[i]);
-  if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
+  for (int i = 0; i < 4; ++i) { if (c->side[i]) cudaStreamDestroy(c->side[i]); if (c->ev_c[i]) cudaEventDestroy(c->ev_c[i]); if (c->ev_a[i]) cudaEventDestroy(c->ev_a[i]); }
+  for (int i = 0; i < 2; ++i) if (c->comm[i] && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm[i]);
   delete c;
 }
 
@@ -806,7 +869,7 @@ int reppo_critic_forward(reppo_ctx* c, const float* cp, const float* critic_obs,
   RET(pack_shadows(c, SLOT_CRITIC, cp, st));
   const Twin tw = c->twin(c->x0);
   CK(launch_gather_concat(critic_obs, sh.critic_obs_dim, action, sh.action_dim, nullptr, 0, rows, c->x0, c->K0, tw.p, tw.ld, st));
-  RET(critic_trunk(c, cp, c->x0, rows, pred != nullptr, st));
+  RET(critic_trunk(c, cp, SLOT_CRITIC, c->x0, rows, pred != nullptr, trunk_main(c), st));
   if (value || logits) CK(launch_value_head(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, rows, value, logits, st));
   if (pred) CK(cudaMemcpyAsync(pred, c->pa.out, sizeof(float) * rows * c->pred_out, cudaMemcpyDeviceToDevice, st));
   if (features) CK(cudaMemcpyAsync(features, c->fa.out, sizeof(float) * rows * sh.critic_hidden, cudaMemcpyDeviceToDevice, st));
@@ -830,6 +893,8 @@ int reppo_actor_forward(reppo_ctx* c, const float* ap, const float* obs, int32_t
 int reppo_linear(reppo_ctx* c, int32_t op, int32_t rows, int32_t in_f, int32_t out_f, const float* a, const float* b,
                  float* out, const float* bias, reppo_stream stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool staged = (op & 0x100) != 0;   // bf16 operands of the previous identical call are still staged: GEMM only
+  op &= 0xff;
   if (!a || !b || !out || rows <= 0 || in_f <= 0 || out_f <= 0 || op < 0 || op > 2)
     return fail(c, REPPO_ERR_INVALID, "reppo_linear: bad argument");
   c->launches = 0;
@@ -844,16 +909,22 @@ int reppo_linear(reppo_ctx* c, int32_t op, int32_t rows, int32_t in_f, int32_t o
   if (in_f > c->maxdim || out_f > c->maxdim) return fail(c, REPPO_ERR_INVALID, "reppo_linear (bf16): dimension exceeds the context's largest layer");
   const int ldi = round8(in_f), ldo = round8(out_f);
   if (op == 0) {
-    CK(launch_cast_bf16(a, rows, in_f, in_f, c->lin_a, ldi, st));
-    CK(launch_cast_bf16(b, out_f, in_f, in_f, c->lin_b, ldi, st));
+    if (!staged) {
+      CK(launch_cast_bf16(a, rows, in_f, in_f, c->lin_a, ldi, st));
+      CK(launch_cast_bf16(b, out_f, in_f, in_f, c->lin_b, ldi, st));
+    }
     CK(launch_gemm_bf16_tc(false, false, rows, out_f, in_f, c->lin_a, ldi, c->lin_b, ldi, out, out_f, bias, GEMM_STORE, 1, nullptr, 0, st));
   } else if (op == 1) {
-    CK(launch_cast_bf16(a, rows, out_f, out_f, c->lin_a, ldo, st));
-    CK(launch_cast_bf16(b, out_f, in_f, in_f, c->lin_b, ldi, st));
+    if (!staged) {
+      CK(launch_cast_bf16(a, rows, out_f, out_f, c->lin_a, ldo, st));
+      CK(launch_cast_bf16(b, out_f, in_f, in_f, c->lin_b, ldi, st));
+    }
     CK(launch_gemm_bf16_tc(false, true, rows, in_f, out_f, c->lin_a, ldo, c->lin_b, ldi, out, in_f, nullptr, GEMM_STORE, 1, nullptr, 0, st));
   } else {
-    CK(launch_cast_bf16(a, rows, out_f, out_f, c->lin_a, ldo, st));
-    CK(launch_cast_bf16(b, rows, in_f, in_f, c->lin_c, ldi, st));
+    if (!staged) {
+      CK(launch_cast_bf16(a, rows, out_f, out_f, c->lin_a, ldo, st));
+      CK(launch_cast_bf16(b, rows, in_f, in_f, c->lin_c, ldi, st));
+    }
     CK(launch_gemm_bf16_tc(true, true, out_f, in_f, rows, c->lin_a, ldo, c->lin_c, ldi, out, in_f, nullptr, GEMM_ATOMIC,
                            wgrad_split(out_f, in_f, rows, true), nullptr, 0, st));
   }
@@ -864,13 +935,14 @@ int reppo_critic_grad(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, 
                       const reppo_hyper* hp, float* metrics, reppo_stream stream) {
   c->launches = 0;
   RET(pack_all(c, s, static_cast<cudaStream_t>(stream)));
-  return critic_grad_impl(c, s, b, idx, mb, hp, metrics, static_cast<cudaStream_t>(stream));
+  return critic_grad_impl(c, s, b, idx, mb, hp, metrics, s->critic.params, SLOT_CRITIC, static_cast<cudaStream_t>(stream));
 }
 int reppo_actor_grad(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int32_t mb,
                      const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, reppo_stream stream) {
   c->launches = 0;
   RET(pack_all(c, s, static_cast<cudaStream_t>(stream)));
-  return actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+  return actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, nullptr, nullptr, s->critic.params, SLOT_CRITIC, nullptr,
+                         nullptr, static_cast<cudaStream_t>(stream));
 }
 int reppo_critic_step(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int32_t mb,
                       const reppo_hyper* hp, float* metrics, reppo_stream stream) {
@@ -886,7 +958,7 @@ int reppo_actor_step(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
 }
 int reppo_clip_adam(reppo_ctx* c, const reppo_net_state* net, int64_t n, const reppo_hyper* hp, float* gn, reppo_stream stream) {
   c->launches = 0;
-  return clip_adam_impl(c, net, n, hp, gn, -1, static_cast<cudaStream_t>(stream));
+  return clip_adam_impl(c, net, n, hp, gn, -1, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const reppo_plan* p, const reppo_hyper* hp,
@@ -965,15 +1037,19 @@ int reppo_nccl_init(reppo_ctx* c, const void* id_128, int32_t rank, int32_t worl
   RET(nccl_load(c));
   NcclId id;
   memcpy(&id, id_128, sizeof(id));
-  const int r = c->nccl.CommInitRank(&c->comm, world_size, id, rank);
-  if (r != 0) { c->comm = nullptr; return fail(c, REPPO_ERR_NCCL, std::string("ncclCommInitRank: ") + c->nccl.GetErrorString(r)); }
+  // first call: the communicator of the critic chain (and of everything when it stays the only one);
+  // second call (with a fresh unique id): the actor chain's, which lets the two chains all-reduce concurrently
+  const int which = (c->comm[0] == nullptr) ? 0 : 1;
+  if (which == 1 && c->comm[1] != nullptr) return fail(c, REPPO_ERR_INVALID, "both communicators are already attached");
+  const int r = c->nccl.CommInitRank(&c->comm[which], world_size, id, rank);
+  if (r != 0) { c->comm[which] = nullptr; return fail(c, REPPO_ERR_NCCL, std::string("ncclCommInitRank: ") + c->nccl.GetErrorString(r)); }
   c->world = world_size; c->rank = rank;
   c->graph_valid = false;
   return REPPO_OK;
 }
 
 int reppo_nccl_finalize(reppo_ctx* c) {
-  if (c->comm) { c->nccl.CommDestroy(c->comm); c->comm = nullptr; }
+  for (int i = 0; i < 2; ++i) if (c->comm[i]) { c->nccl.CommDestroy(c->comm[i]); c->comm[i] = nullptr; }
   c->graph_valid = false;
   return REPPO_OK;
 }

@@ -96,7 +96,7 @@ cudaError_t launch_mean_std(const float* out, int rows, int A, float min_std, fl
 // bf16 shadows of the weight matrices, refreshed by the Adam kernel itself (REPPO_GEMM_BF16)
 struct ShadowEntry { long long start, end; int in, ld; void* dst; };
 struct ShadowTable { int n; ShadowEntry e[kMaxPack]; };
-cudaError_t launch_clip_adam(float* p, const float* g, float* m, float* v, long long n, int* step, float* partials,
+cudaError_t launch_clip_adam(const float* p_in, float* p, const float* g, float* m, float* v, long long n, int* step, float* partials,
                              const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out, cudaStream_t st);
 cudaError_t launch_metrics_mean(const float* step_metrics, int first, int count, int nm, float* out, cudaStream_t st);
 cudaError_t launch_metrics_init(float* m, uint32_t mask, cudaStream_t st);

@@ -33,7 +33,7 @@ sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict
 }
 
 __global__ void __launch_bounds__(256)
-adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+adam_kernel(const float* p_in, float* p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
             const float* __restrict__ partials, int num_partials, const int* __restrict__ step, AdamConsts c,
             const ShadowTable sh, float* __restrict__ grad_norm_out) {
   REPPO_PDL_PROLOGUE();
@@ -75,12 +75,13 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   };
   const long long n4 = n >> 2;
   float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* pi4 = reinterpret_cast<const float4*>(p_in);   // may alias p (in-place update)
   float4* m4 = reinterpret_cast<float4*>(m);
   float4* v4 = reinterpret_cast<float4*>(v);
   const float4* g4 = reinterpret_cast<const float4*>(g);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    float4 pp = pi4[i], mm = m4[i], vv = v4[i];
     const float4 gg = g4[i];
     upd(pp.x, gg.x, mm.x, vv.x, 4 * i); upd(pp.y, gg.y, mm.y, vv.y, 4 * i + 1); upd(pp.z, gg.z, mm.z, vv.z, 4 * i + 2);
     upd(pp.w, gg.w, mm.w, vv.w, 4 * i + 3);
@@ -88,11 +89,13 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long long i = (n4 << 2) + threadIdx.x;
-    upd(p[i], g[i], m[i], v[i], i);
+    float pp = p_in[i];
+    upd(pp, g[i], m[i], v[i], i);
+    p[i] = pp;
   }
 }
 
-cudaError_t launch_clip_adam(float* p, const float* g, float* m, float* v, long long n, int* step, float* partials,
+cudaError_t launch_clip_adam(const float* p_in, float* p, const float* g, float* m, float* v, long long n, int* step, float* partials,
                              const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   const long long want = (n / 4 + 255) / 256;
@@ -101,7 +104,7 @@ cudaError_t launch_clip_adam(float* p, const float* g, float* m, float* v, long 
   launch_k((sumsq_partial_kernel), dim3(blocks), dim3(256), 0, st, g, n, partials, step);
   ShadowTable sh{};
   if (shadow != nullptr) sh = *shadow;
-  launch_k((adam_kernel), dim3(blocks), dim3(256), 0, st, p, g, m, v, n, partials, blocks, step, c, sh, grad_norm_out);
+  launch_k((adam_kernel), dim3(blocks), dim3(256), 0, st, p_in, p, g, m, v, n, partials, blocks, step, c, sh, grad_norm_out);
   return cudaGetLastError();
 }
 

@@ -47,16 +47,19 @@ def local_permutations(seed: int, num_epochs: int, rows_local: int, rank: int, d
     return p.to(device) if device is not None else p
 
 
-def attach_nccl(engine, rank: int, world: int):
-    """Create the library's own NCCL communicator: rank 0 makes the unique id, torch.distributed broadcasts it."""
-    raw = C.create_string_buffer(128)
-    if rank == 0:
-        L.check(engine.lib.reppo_nccl_unique_id(engine.ctx, raw), engine.ctx, "reppo_nccl_unique_id")
+def attach_nccl(engine, rank: int, world: int, communicators: int = 2):
+    """Create the library's own NCCL communicators: rank 0 makes each unique id, torch.distributed broadcasts it.
+    The first communicator serves the critic chain, the optional second one the actor chain (two chains may not
+    share a communicator; with only one, the engine runs the two chains serially under data parallelism)."""
     dev = engine.device if dist.get_backend() == "nccl" else torch.device("cpu")
-    t = torch.tensor(list(raw.raw), dtype=torch.uint8, device=dev)
-    dist.broadcast(t, 0)
-    ident = bytes(t.cpu().tolist())
-    L.check(engine.lib.reppo_nccl_init(engine.ctx, ident, rank, world), engine.ctx, "reppo_nccl_init")
+    for _ in range(communicators):
+        raw = C.create_string_buffer(128)
+        if rank == 0:
+            L.check(engine.lib.reppo_nccl_unique_id(engine.ctx, raw), engine.ctx, "reppo_nccl_unique_id")
+        t = torch.tensor(list(raw.raw), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0)
+        ident = bytes(t.cpu().tolist())
+        L.check(engine.lib.reppo_nccl_init(engine.ctx, ident, rank, world), engine.ctx, "reppo_nccl_init")
 
 
 def reduce_metrics(m: torch.Tensor) -> torch.Tensor:
