@@ -24,6 +24,7 @@
 
 #include "../../include/reppo_b200.h"
 #include "kernels.h"
+#include "slab.h"
 
 using namespace reppo;
 
@@ -129,6 +130,8 @@ struct reppo_ctx {
   // parallel branches): [0] pred-head branch, [1] weight-gradient GEMMs, [2] actor-only prefix of the actor step
   bool concurrent = true;
   bool fuse_norm = true;   // REPPO_NO_FUSE_NORM=1: separate GEMM + norm/swish kernels
+  bool slab = false;       // whole chains of a step in one persistent cluster kernel (slab.cu); REPPO_NO_SLAB=1 disables
+  int slab_cluster = 0;    // CTAs per cluster = max(hidden) / 64
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // [3]: weight gradients of the actor chain
   std::vector<cudaEvent_t> events;
   size_t ev_next = 0;
@@ -440,6 +443,134 @@ int mlp_backward(reppo_ctx* c, const Mlp& m, const float* params, int slot, floa
   return REPPO_OK;
 }
 
+
+// ---- slab programs (slab.cu): the forward / loss / input-gradient chain of a step as ONE kernel ----------------
+struct SlabBuilder {
+  reppo_ctx* c;
+  SlabProgram p;
+  int rows;
+  int max_tiles = 1;
+  bool ok = true;
+  std::string why;
+
+  SlabBuilder(reppo_ctx* ctx, int rows_) : c(ctx), rows(rows_) {
+    memset(&p, 0, sizeof(p));
+    p.rows = rows_;
+  }
+  SlabStep* next() {
+    if (p.num_steps >= kSlabMaxSteps) { ok = false; why = "too many steps for one slab program"; return nullptr; }
+    SlabStep* s = &p.steps[p.num_steps++];
+    return s;
+  }
+  void row(int which) {
+    SlabStep* s = next();
+    if (!s) return;
+    s->kind = SLAB_ROW; s->row = which;
+  }
+  // A = bf16 twin of `a_f32` [rows, K]; W = shadow of layer L in `slot`; dgrad: out[rows, L.in] = A[rows, L.out] W
+  SlabStep* gemm(const float* a_f32, const Linear& L, int slot, bool dgrad) {
+    SlabStep* s = next();
+    if (!s) return nullptr;
+    const Twin ta = c->twin(a_f32);
+    if (ta.p == nullptr) { ok = false; why = "slab operand has no bf16 twin"; return nullptr; }
+    s->kind = SLAB_GEMM;
+    s->K = dgrad ? L.out : L.in;
+    s->N = dgrad ? L.in : L.out;
+    s->b_mn = dgrad ? 1 : 0;
+    const uint16_t* w = c->shadow_b[slot] + L.sb;
+    bool e = slab_encode_2d(&s->ta, ta.p, rows, s->K, ta.ld, 64, 128);
+    // forward: W [out, in] K-major, tile [64 n][64 k]; dgrad: the same matrix read as [k = out][n = in]
+    e = e && slab_encode_2d(&s->tb, w, L.out, L.in, L.ld_b, 64, 64);
+    if (!e) { ok = false; why = "cuTensorMapEncodeTiled failed"; return nullptr; }
+    const int tiles = (s->N + 63) / 64;
+    max_tiles = std::max(max_tiles, (tiles + c->slab_cluster - 1) / c->slab_cluster);
+    return s;
+  }
+  void set_twin(SlabStep* s, const float* f32) {
+    const Twin t = c->twin(f32);
+    if (t.p == nullptr) { ok = false; why = "slab output has no bf16 twin"; return; }
+    s->twin = reinterpret_cast<__nv_bfloat16*>(t.p); s->ld_twin = t.ld;
+  }
+  // forward of one MLP; last_epi / last_twin describe what happens to the last layer's output
+  void mlp_fwd(const Mlp& m, const float* params, int slot, const float* in, Acts& a, int last_epi, const float* last_twin) {
+    const float* cur = in;
+    const int n = static_cast<int>(m.layers.size());
+    for (int i = 0; i < n && ok; ++i) {
+      const Linear& L = m.layers[i];
+      SlabStep* s = gemm(cur, L, slot, false);
+      if (!s) return;
+      s->bias = params + L.b;
+      if (i < n - 1) {
+        s->epi = (m.norm != NORM_NONE) ? EPI_FWD_NORM : EPI_FWD_ACT;
+        s->norm = m.norm; s->eps = c->sem.norm_eps;
+        s->gamma = L.g >= 0 ? params + L.g : nullptr; s->beta = L.beta >= 0 ? params + L.beta : nullptr;
+        s->out = a.z[i]; s->ld_out = L.out; s->rstd = a.rstd[i]; s->mean = a.mean[i];
+        set_twin(s, a.x[i]);
+        cur = a.x[i];
+      } else {
+        s->epi = last_epi; s->out = a.out; s->ld_out = L.out;
+        if (last_twin != nullptr) set_twin(s, last_twin);
+      }
+    }
+  }
+  // input-gradient chain of one MLP from d_out down to dz of the first layer (and optionally through the first layer)
+  //   first: 0 = stop at dz[0]; 1 = EPI_NONE (accumulate into the next GEMM); 2 = the `first_*` epilogue below
+  void mlp_bwd(const Mlp& m, const float* params, int slot, float* grads, const Acts& a, const float* d_out, int first,
+               bool first_accumulate, int first_epi, float* first_out, int first_ld, const float* first_twin, float* first_gbias) {
+    const int n = static_cast<int>(m.layers.size());
+    const float* d = d_out;
+    for (int i = n - 1; i >= 0 && ok; --i) {
+      const Linear& L = m.layers[i];
+      if (i > 0) {
+        const Linear& Lp = m.layers[i - 1];
+        SlabStep* s = gemm(d, L, slot, true);
+        if (!s) return;
+        s->epi = (m.norm != NORM_NONE) ? EPI_BWD_NORM : EPI_BWD_ACT;
+        s->norm = m.norm;
+        s->gamma = Lp.g >= 0 ? params + Lp.g : nullptr; s->beta = Lp.beta >= 0 ? params + Lp.beta : nullptr;
+        s->out = a.z[i - 1]; s->ld_out = Lp.out; s->rstd = a.rstd[i - 1]; s->mean = a.mean[i - 1];
+        set_twin(s, a.dz[i - 1]);
+        if (grads != nullptr) {
+          s->g_gamma = Lp.g >= 0 ? grads + Lp.g : nullptr; s->g_beta = Lp.beta >= 0 ? grads + Lp.beta : nullptr;
+          s->g_bias = grads + Lp.b;
+        }
+        d = a.dz[i - 1];
+      } else if (first != 0) {
+        SlabStep* s = gemm(d, L, slot, true);
+        if (!s) return;
+        s->accumulate = first_accumulate ? 1 : 0;
+        if (first == 1) { s->epi = EPI_NONE; }
+        else {
+          s->epi = first_epi; s->out = first_out; s->ld_out = first_ld; s->g_bias = first_gbias;
+          if (first_twin != nullptr) set_twin(s, first_twin);
+        }
+      }
+    }
+  }
+  int finish(cudaStream_t st) {
+    if (!ok) return fail(c, REPPO_ERR_INVALID, "slab program: " + why);
+    int cols = 64;
+    while (cols < 64 * max_tiles) cols *= 2;
+    if (cols > 256) return fail(c, REPPO_ERR_UNSUPPORTED, "slab program: layer too wide for the cluster");
+    p.tmem_cols = cols;
+    const cudaError_t e = launch_slab(p, c->slab_cluster, st);
+    ++c->launches;
+    if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("launch_slab: ") + cudaGetErrorString(e));
+    return REPPO_OK;
+  }
+};
+
+// weight gradients of one MLP after a slab program produced every dz twin (bias / norm gradients are already in)
+int mlp_wgrads(reppo_ctx* c, const Mlp& m, float* grads, const float* in, int rows, const Acts& a, const float* d_out,
+               cudaStream_t wst) {
+  const int n = static_cast<int>(m.layers.size());
+  for (int i = n - 1; i >= 0; --i) {
+    const Linear& L = m.layers[i];
+    RET(linear_wgrad(c, L, i == n - 1 ? d_out : a.dz[i], i == 0 ? in : a.x[i - 1], rows, grads + L.w, wst));
+  }
+  return REPPO_OK;
+}
+
 int check_rows(reppo_ctx* c, int rows) {
   if (c->ws == nullptr) return fail(c, REPPO_ERR_WORKSPACE, "workspace not set (reppo_set_workspace)");
   if (rows <= 0 || rows > c->shape.max_rows) return fail(c, REPPO_ERR_INVALID, "rows outside (0, shape.max_rows]");
@@ -501,6 +632,46 @@ int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
   const int Hc = sh.critic_hidden;
   CK(launch_metrics_init(metrics, kCriticMetricMask, st));
   CK(cudaMemsetAsync(cg, 0, static_cast<size_t>(c->critic_count) * sizeof(float), st));
+  if (c->slab) {
+    // the whole forward / loss / input-gradient chain as one cluster kernel; weight gradients follow on side streams
+    SlabBuilder sb(c, mb);
+    SlabRowArgs& r = sb.p.r;
+    r.critic_obs = b->critic_obs; r.action = b->action; r.idx = idx;
+    r.D = sh.obs_dim; r.Dc = sh.critic_obs_dim; r.A = sh.action_dim; r.K0 = c->K0;
+    const Twin tx0 = c->twin(c->x0), tdl = c->twin(c->dlogits);
+    r.x0_twin = reinterpret_cast<__nv_bfloat16*>(tx0.p); r.x0_ld = tx0.ld;
+    r.head_out = c->ha.out; r.ld_head = sh.num_bins; r.zero_dist = cp + c->zero_dist_off; r.hl = c->hl;
+    r.target = b->target; r.truncated = b->truncated; r.inv_rows = inv; r.no_mask = no_mask;
+    r.dl_twin = reinterpret_cast<__nv_bfloat16*>(tdl.p); r.dl_ld = tdl.ld;
+    r.g_bias_head = cg + c->head.layers.back().b; r.g_zero = cg + c->zero_dist_off; r.metrics = metrics;
+    r.next_emb = b->next_emb; r.reward = b->reward; r.done = b->done; r.P = c->pred_out; r.H = Hc;
+    r.reward_head = c->sem.reward_head; r.mask_done = c->sem.aux_mask_done; r.aux_mult = hp->aux_loss_mult;
+    sb.row(ROW_GATHER_CRITIC);
+    sb.mlp_fwd(c->feature, cp, cslot, c->x0, c->fa, EPI_FWD_ACT, c->xs);
+    sb.mlp_fwd(c->head, cp, cslot, c->xs, c->ha, EPI_FWD_OUT, nullptr);
+    sb.row(ROW_CE);
+    sb.mlp_fwd(c->pred, cp, cslot, c->xs, c->pa, EPI_FWD_AUX, c->dpred);
+    if (sb.ok) sb.p.steps[sb.p.num_steps - 1].g_bias = cg + c->pred.layers.back().b;
+    sb.mlp_bwd(c->head, cp, cslot, cg, c->ha, c->dlogits, 0, false, 0, nullptr, 0, nullptr, nullptr);
+    sb.mlp_bwd(c->pred, cp, cslot, cg, c->pa, c->dpred, 0, false, 0, nullptr, 0, nullptr, nullptr);
+    // d swish(features) = both heads' input gradients summed in one TMEM accumulator, times swish'(features)
+    if (SlabStep* s1 = sb.gemm(c->ha.dz[0], c->head.layers[0], cslot, true)) s1->epi = EPI_NONE;
+    if (SlabStep* s2 = sb.gemm(c->pa.dz[0], c->pred.layers[0], cslot, true)) {
+      s2->accumulate = 1; s2->epi = EPI_BWD_ACT; s2->out = c->fa.out; s2->ld_out = Hc;
+      s2->g_bias = cg + c->feature.layers.back().b;
+      sb.set_twin(s2, c->dfeat);
+    }
+    sb.mlp_bwd(c->feature, cp, cslot, cg, c->fa, c->dfeat, 0, false, 0, nullptr, 0, nullptr, nullptr);
+    RET(sb.finish(st));
+    RET(dep(c, st, sw));
+    RET(dep(c, st, s1));
+    RET(mlp_wgrads(c, c->head, cg, c->xs, mb, c->ha, c->dlogits, sw));
+    RET(mlp_wgrads(c, c->pred, cg, c->xs, mb, c->pa, c->dpred, s1));
+    RET(mlp_wgrads(c, c->feature, cg, c->x0, mb, c->fa, c->dfeat, st));
+    RET(dep(c, s1, st));
+    RET(dep(c, sw, st));
+    return REPPO_OK;
+  }
   Twin tw = c->twin(c->x0);
   CK(launch_gather_concat(b->critic_obs, sh.critic_obs_dim, b->action, sh.action_dim, idx, 0, mb, c->x0, c->K0, tw.p, tw.ld, st));
   // encoder, then swish(features) feeds two independent heads
@@ -567,6 +738,57 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
   cudaStream_t pre = prefix_stream ? prefix_stream : st;
   CK(launch_metrics_init(metrics, kActorMetricMask, pre));
   CK(cudaMemsetAsync(ag, 0, static_cast<size_t>(c->actor_count) * sizeof(float), pre));
+  if (c->slab) {
+    if (old_table == nullptr) {
+      // stand-alone call without a behaviour-policy table: evaluate actor_old on this minibatch (separate kernels)
+      const Twin t0 = c->twin(c->xa0);
+      CK(launch_gather_concat(b->obs, sh.obs_dim, nullptr, 0, idx, 0, mb, c->xa0, sh.obs_dim, t0.p, t0.ld, pre));
+      RET(mlp_forward(c, c->actor, s->actor_old, SLOT_ACTOR_OLD, c->xa0, mb, c->oa, pre));
+    }
+    auto fill_rows = [&](SlabRowArgs& r) {
+      r.obs = b->obs; r.critic_obs = b->critic_obs; r.idx = idx;
+      r.D = sh.obs_dim; r.Dc = Dc; r.A = A; r.K0 = c->K0;
+      const Twin tx0 = c->twin(c->x0a), txa = c->twin(c->xa0), tdl = c->twin(tb.dlogits), tdo = c->twin(c->dout);
+      r.x0_twin = reinterpret_cast<__nv_bfloat16*>(tx0.p); r.x0_ld = tx0.ld;
+      r.xa0_twin = reinterpret_cast<__nv_bfloat16*>(txa.p); r.xa0_ld = txa.ld;
+      r.x0a = c->x0a;
+      r.head_out = tb.ha->out; r.ld_head = sh.num_bins; r.zero_dist = cp + c->zero_dist_off; r.hl = c->hl;
+      r.inv_rows = inv; r.dl_twin = reinterpret_cast<__nv_bfloat16*>(tdl.p); r.dl_ld = tdl.ld; r.metrics = metrics;
+      r.actor_out = c->aa.out; r.old_out = old_table ? old_table : c->oa.out; r.old_idx = old_table ? idx : nullptr;
+      r.eps_pi = eps_pi; r.eps_kl = eps_kl; r.kl_samples = sh.kl_samples; r.ac = ac;
+      r.logp = c->logp; r.kl = c->kl; r.gmu = c->gmu; r.gsig = c->gsig; r.q = c->q;
+      r.dx0 = c->dx0; r.actor_params = ap; r.actor_grads = ag;
+      r.dout_twin = reinterpret_cast<__nv_bfloat16*>(tdo.p); r.dout_ld = tdo.ld;
+      r.g_bias_actor_last = ag + c->actor.layers.back().b;
+    };
+    {   // prefix: policy forward + sampling (independent of the critic update that precedes the rest)
+      SlabBuilder sb(c, mb);
+      fill_rows(sb.p.r);
+      sb.row(ROW_GATHER_ACTOR);
+      sb.mlp_fwd(c->actor, ap, SLOT_ACTOR, c->xa0, c->aa, EPI_FWD_OUT, nullptr);
+      sb.row(ROW_SAMPLE);
+      RET(sb.finish(pre));
+    }
+    RET(dep(c, pre, st));
+    if (critic_ready != nullptr && cudaStreamWaitEvent(st, critic_ready, 0) != cudaSuccess)
+      return fail(c, REPPO_ERR_CUDA, "cudaStreamWaitEvent failed");
+    {   // Q(s, a) through the frozen critic, dQ/da, the policy gradient and the policy's input-gradient chain
+      SlabBuilder sb(c, mb);
+      fill_rows(sb.p.r);
+      sb.mlp_fwd(c->feature, cp, cslot, c->x0a, *tb.fa, EPI_FWD_ACT, tb.xs);
+      sb.mlp_fwd(c->head, cp, cslot, tb.xs, *tb.ha, EPI_FWD_OUT, nullptr);
+      sb.row(ROW_Q);
+      sb.mlp_bwd(c->head, cp, cslot, nullptr, *tb.ha, tb.dlogits, 2, false, EPI_BWD_ACT, tb.fa->out, sh.critic_hidden, tb.dfeat, nullptr);
+      sb.mlp_bwd(c->feature, cp, cslot, nullptr, *tb.fa, tb.dfeat, 2, false, EPI_BWD_OUT, c->dx0, c->K0, nullptr, nullptr);
+      sb.row(ROW_ACTOR_GRAD);
+      sb.mlp_bwd(c->actor, ap, SLOT_ACTOR, ag, c->aa, c->dout, 0, false, 0, nullptr, 0, nullptr, nullptr);
+      RET(sb.finish(st));
+    }
+    if (critic_read_done != nullptr && cudaEventRecord(critic_read_done, st) != cudaSuccess)
+      return fail(c, REPPO_ERR_CUDA, "cudaEventRecord failed");
+    RET(mlp_wgrads(c, c->actor, ag, c->xa0, mb, c->aa, c->dout, st));
+    return REPPO_OK;
+  }
   Twin tw = c->twin(c->xa0);
   CK(launch_gather_concat(b->obs, sh.obs_dim, nullptr, 0, idx, 0, mb, c->xa0, sh.obs_dim, tw.p, tw.ld, pre));
   RET(mlp_forward(c, c->actor, ap, SLOT_ACTOR, c->xa0, mb, c->aa, pre));
@@ -787,6 +1009,12 @@ int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
   } else {
     c->hl.den = sqrtf(2.f) * static_cast<float>(sigma) + 1e-6f;               // reppo_util.py:767-769
     c->hl.z_eps = 1e-6f;                                                      // :773
+  }
+  {
+    const int hmax = std::max(s.critic_hidden, s.actor_hidden);
+    c->slab = c->tc && getenv("REPPO_NO_SLAB") == nullptr && s.critic_hidden % 64 == 0 && s.actor_hidden % 64 == 0 &&
+              hmax <= 512 && s.action_dim <= 32 && s.num_bins <= 256;
+    c->slab_cluster = hmax / 64;
   }
   c->ws_need = layout_workspace(c, nullptr);
   *out = c;

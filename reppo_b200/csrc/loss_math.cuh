@@ -1,0 +1,50 @@
+// Row-wise math shared by the loss kernels (losses.cu) and the slab programs (slab.cu).
+#pragma once
+#include "common.cuh"
+
+namespace reppo {
+
+constexpr int kMaxBinsPerLane = 8;  // num_bins <= 256
+constexpr float kLog2 = 0.6931471805599453f;
+constexpr float kHalfLog2Pi = 0.9189385332046727f;
+
+struct RowSoftmax {
+  float p[kMaxBinsPerLane];
+  float lg[kMaxBinsPerLane];
+  float lse, value;
+};
+
+// logits = head + bias_scale * zero_dist; softmax; value = p . support
+REPPO_DEVINL void row_softmax(const float* __restrict__ head_row, const float* __restrict__ zero_dist,
+                              const float* __restrict__ support, float bias_scale, int B, int lane, RowSoftmax& o) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kMaxBinsPerLane; ++j) {
+    const int c = lane + 32 * j;
+    o.lg[j] = (c < B) ? head_row[c] + bias_scale * zero_dist[c] : -INFINITY;
+    m = fmaxf(m, o.lg[j]);
+  }
+  m = warp_max(m);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxBinsPerLane; ++j) {
+    const int c = lane + 32 * j;
+    o.p[j] = (c < B) ? expf(o.lg[j] - m) : 0.f;
+    s += o.p[j];
+  }
+  s = warp_sum(s);
+  const float inv = 1.f / s;
+  float v = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxBinsPerLane; ++j) {
+    const int c = lane + 32 * j;
+    o.p[j] *= inv;
+    if (c < B) v += o.p[j] * support[c];
+  }
+  o.value = warp_sum(v);
+  o.lse = m + logf(s);
+}
+
+REPPO_DEVINL float fldj_(float x) { return 2.f * (kLog2 - x - softplusf_(-2.f * x)); }
+
+}  // namespace reppo

@@ -1,0 +1,856 @@
+// Slab kernel: ONE persistent tcgen05 kernel runs a whole critic (or actor) chain of a REPPO minibatch step.
+//
+//   reference path: critic_loss_fn / actor_loss and their backward, src/jaxrl/reppo.py:474-622;
+//                   update_critic / update_actor, src/torchrl/reppo.py:227-358; FCNN src/networks/jax_models.py:57-124.
+//
+// Why.  A step is a chain of ~25 dependent few-microsecond kernels per network; on B200 the chain, not the math
+// (17 us of bf16 FLOPs per step), sets the step time.  Forward and input-gradient passes never mix minibatch rows, so
+// a thread-block CLUSTER owns a slab of 128 rows and walks the whole chain inside one launch:
+//   * grid = (C, ceil(rows / 128)), cluster = (C, 1, 1), C = hidden / 64: CTA `rank` owns the 64-wide output-column
+//     tiles rank, rank + C, ... of every layer (UMMA 128 x 64 x 16, bf16 -> fp32 accumulators in TMEM);
+//   * operands arrive by TMA (128 B swizzle) through a 4-stage mbarrier ring; warp 0 = producer, warp 1 = MMA issuer,
+//     warps 2..9 = epilogue (tcgen05.ld -> shared-memory transpose -> row-contiguous global accesses);
+//   * a layer's output leaves as a bf16 "twin" in global memory (the weight-gradient GEMMs need it there anyway) and
+//     the next layer's TMA loads read it back from L2 after a cluster barrier (generic -> async proxy fence);
+//   * row statistics of RMSNorm / LayerNorm (forward and backward) are exchanged through distributed shared memory;
+//   * the losses (HL-Gauss cross-entropy, auxiliary MSE, tanh-Gaussian sampling + KL, Q, policy gradient) run as ROW
+//     phases between GEMM steps: one warp per row, the slab's rows spread over every warp of the cluster.
+// What stays outside: weight gradients (reduction over ALL rows), the gradient norm and Adam.
+#include "slab.h"
+
+#include "common.cuh"
+#include "launch.h"
+#include "loss_math.cuh"
+
+namespace reppo {
+namespace {
+
+constexpr int SB_M = 128, SB_N = 64, SB_K = 64, SB_UMMA_K = 16;
+constexpr int kABytes = SB_M * SB_K * 2;            // 16 KB
+constexpr int kBBytes = SB_N * SB_K * 2;            //  8 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kRingBytes = kSlabStages * kStageBytes;   // 96 KB; doubles as epilogue staging and row-phase scratch
+constexpr int kBarOffset = kRingBytes;
+constexpr int kStatOffset = kBarOffset + 128;
+// part[2][2][128] | cta_stat[2][128] | rowa[8][32] | rowb[8][32] | colpart[3][8][32] | metpart[8][4]
+constexpr int kOffCtaStat = 512, kOffRowA = 768, kOffRowB = 1024, kOffColPart = 1280, kOffMetPart = 2048, kStatFloats = 2080;
+constexpr int kSlabSmem = kStatOffset + kStatFloats * 4 + 1024;
+constexpr int kStgLd = 36;   // floats per staged row (32 + 4: conflict-free float4 rows)
+static_assert(8 * 32 * kStgLd * 4 <= kRingBytes, "epilogue staging must fit in the ring");
+static_assert((8 * 256 + 8 * 8 + 16) * 4 <= kRingBytes, "row-phase scratch must fit in the ring");
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------
+REPPO_DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+REPPO_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+REPPO_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+REPPO_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "SLAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra SLAB_DONE;\n\t"
+      "bra SLAB_WAIT;\n\t"
+      "SLAB_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+REPPO_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+REPPO_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+REPPO_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+REPPO_DEVINL void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+REPPO_DEVINL void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+REPPO_DEVINL void tc_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// shared-memory matrix descriptor: SWIZZLE_128B, sm_100 descriptor version
+REPPO_DEVINL uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// bf16 x bf16 -> f32, M = 128, N = 64, A K-major, B K-major or MN-major
+REPPO_DEVINL uint32_t make_idesc(bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(SB_N >> 3) << 17) | (static_cast<uint32_t>(SB_M >> 4) << 24);
+}
+REPPO_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Between two steps: every global-memory result of the previous step (written through the generic proxy by any
+// CTA of the cluster) becomes visible to the next step's TMA loads (async proxy) and plain loads.
+REPPO_DEVINL void handoff_sync() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();
+  tc_fence_after();
+}
+REPPO_DEVINL float ld_dsmem_f32(const float* local_smem_ptr, uint32_t cta_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(cta_rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+REPPO_DEVINL void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+
+REPPO_DEVINL void store_bf16x4(__nv_bfloat16* p, float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&lo);
+  u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ---- row phases ------------------------------------------------------------------------------------
+// gw / nw: this warp's index among, and the number of, the cluster's epilogue warps; ew: index inside the CTA.
+struct RowCtx {
+  int m0, rows_here, M, gw, nw, ew, lane, rank;
+  float* scratch;   // ring memory (idle during row phases)
+};
+
+__device__ void row_gather(const SlabRowArgs& a, const RowCtx& rc, bool actor) {
+  for (int r = rc.gw; r < rc.rows_here; r += rc.nw) {
+    const int row = rc.m0 + r;
+    const long long src = a.idx ? a.idx[row] : row;
+    if (!actor) {
+      for (int c = rc.lane; c < a.K0; c += 32) {
+        const float v = c < a.Dc ? a.critic_obs[src * a.Dc + c] : a.action[src * a.A + (c - a.Dc)];
+        a.x0_twin[static_cast<size_t>(row) * a.x0_ld + c] = __float2bfloat16_rn(v);
+      }
+    } else {
+      for (int c = rc.lane; c < a.D; c += 32)
+        a.xa0_twin[static_cast<size_t>(row) * a.xa0_ld + c] = __float2bfloat16_rn(a.obs[src * a.D + c]);
+      for (int c = rc.lane; c < a.Dc; c += 32)
+        a.x0_twin[static_cast<size_t>(row) * a.x0_ld + c] = __float2bfloat16_rn(a.critic_obs[src * a.Dc + c]);
+    }
+  }
+}
+
+// HL-Gauss cross-entropy + d logits (critic_ce_kernel of losses.cu, one warp per row)
+__device__ void row_ce(const SlabRowArgs& a, const RowCtx& rc) {
+  const HLConsts& hl = a.hl;
+  const int B = hl.num_bins, lane = rc.lane;
+  float* scol = rc.scratch;              // [8][256]
+  float* smet = rc.scratch + 8 * 256;    // [8][8]
+  float vals[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float tmax = -INFINITY, tmin = INFINITY;
+  float cs[kMaxBinsPerLane];
+#pragma unroll
+  for (int j = 0; j < kMaxBinsPerLane; ++j) cs[j] = 0.f;
+  for (int r = rc.gw; r < rc.rows_here; r += rc.nw) {
+    const int row = rc.m0 + r;
+    const long long src = a.idx ? a.idx[row] : row;
+    const float tgt = a.target[src];
+    const float mask = a.no_mask ? 1.f : 1.f - a.truncated[src];
+    RowSoftmax sx;
+    row_softmax(a.head_out + static_cast<size_t>(row) * a.ld_head, a.zero_dist, hl.support, hl.bias_scale, B, lane, sx);
+    const float x = fminf(fmaxf(tgt, hl.vmin), hl.vmax);
+    const float z = erff((hl.edges[B] - x) / hl.den) - erff((hl.edges[0] - x) / hl.den) + hl.z_eps;
+    float ce = 0.f, sum_tp = 0.f, tp[kMaxBinsPerLane];
+#pragma unroll
+    for (int j = 0; j < kMaxBinsPerLane; ++j) {
+      const int c = lane + 32 * j;
+      tp[j] = 0.f;
+      if (c < B) {
+        const float lo = erff((hl.edges[c] - x) / hl.den), hi = erff((hl.edges[c + 1] - x) / hl.den);
+        tp[j] = (hi - lo) / z;
+        ce -= tp[j] * (sx.lg[j] - sx.lse);
+        sum_tp += tp[j];
+      }
+    }
+    ce = warp_sum(ce);
+    sum_tp = warp_sum(sum_tp);
+    const float coef = mask * a.inv_rows;
+#pragma unroll
+    for (int j = 0; j < kMaxBinsPerLane; ++j) {
+      const int c = lane + 32 * j;
+      if (c < B) {
+        const float o = coef * (sum_tp * sx.p[j] - tp[j]);
+        cs[j] += o;
+        a.dl_twin[static_cast<size_t>(row) * a.dl_ld + c] = __float2bfloat16_rn(o);
+      }
+    }
+    vals[0] += mask * ce * a.inv_rows;
+    vals[1] += ce * a.inv_rows;
+    vals[2] += (sx.value - tgt) * (sx.value - tgt) * a.inv_rows;
+    vals[3] += sx.value * a.inv_rows;
+    vals[4] += tgt * a.inv_rows;
+    tmax = fmaxf(tmax, tgt); tmin = fminf(tmin, tgt);
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxBinsPerLane; ++j) scol[rc.ew * 256 + lane + 32 * j] = cs[j];
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) smet[rc.ew * 8 + k] = vals[k];
+    smet[rc.ew * 8 + 5] = tmax; smet[rc.ew * 8 + 6] = tmin;
+  }
+  epi_bar();
+  if (rc.rank * 8 < rc.rows_here) {   // this CTA had rows
+    const int t = rc.ew * 32 + lane;
+    if (t < B) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += scol[w * 256 + t];
+      if (a.g_bias_head != nullptr) atomicAdd(a.g_bias_head + t, s);
+      if (a.g_zero != nullptr) atomicAdd(a.g_zero + t, s * hl.bias_scale);
+    }
+    if (t == 255) {
+      float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, mx = -INFINITY, mn = INFINITY;
+      for (int w = 0; w < 8; ++w) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] += smet[w * 8 + k];
+        mx = fmaxf(mx, smet[w * 8 + 5]); mn = fminf(mn, smet[w * 8 + 6]);
+      }
+      atomicAdd(a.metrics + M_CRITIC_LOSS, v[0]);
+      atomicAdd(a.metrics + M_CE_MEAN, v[1]);
+      atomicAdd(a.metrics + M_VALUE_LOSS, v[2]);
+      atomicAdd(a.metrics + M_Q_MEAN, v[3]);
+      atomicAdd(a.metrics + M_TARGET_MEAN, v[4]);
+      if (mx > -INFINITY) { atomic_max_float(a.metrics + M_TARGET_MAX, mx); atomic_min_float(a.metrics + M_TARGET_MIN, mn); }
+    }
+  }
+  epi_bar();
+}
+
+// tanh-Gaussian sample, log-prob, 16-sample forward KL and its gradient (actor_sample_kernel of losses.cu);
+// lane k owns action dimension k
+__device__ void row_sample(const SlabRowArgs& a, const RowCtx& rc) {
+  const int A = a.A, k = rc.lane;
+  const ActorConsts& ac = a.ac;
+  for (int r = rc.gw; r < rc.rows_here; r += rc.nw) {
+    const int row = rc.m0 + r;
+    float logp = 0.f, lp_old = 0.f, lp_new = 0.f;
+    if (k < A) {
+      const float* o = a.actor_out + static_cast<size_t>(row) * 2 * A;
+      const float* oo = a.old_out + static_cast<size_t>(a.old_idx ? a.old_idx[row] : row) * 2 * A;
+      const float mu = o[k], sig = expf(o[A + k]) + ac.min_std;
+      const float e = a.eps_pi[static_cast<size_t>(row) * A + k];
+      const float x = mu + sig * e;
+      const float act = tanhf(x);
+      a.x0a[static_cast<size_t>(row) * a.K0 + a.Dc + k] = act;
+      a.x0_twin[static_cast<size_t>(row) * a.x0_ld + a.Dc + k] = __float2bfloat16_rn(act);
+      const float log_sig = logf(sig);
+      if (ac.clip_policy_sample) {
+        const float xc = atanhf(fminf(fmaxf(act, -ac.action_clip), ac.action_clip));
+        const float zz = (xc - mu) / sig;
+        logp = -0.5f * zz * zz - log_sig - kHalfLog2Pi - fldj_(xc);
+      } else {
+        logp = -0.5f * e * e - log_sig - kHalfLog2Pi - fldj_(x);
+      }
+      const float mu_o = oo[k], sig_o = expf(oo[A + k]) + ac.min_std;
+      const float log_sig_o = logf(sig_o);
+      const float inv_sig = 1.f / sig;
+      float gm = 0.f, gs = 0.f;
+      for (int s = 0; s < a.kl_samples; ++s) {
+        const float eo = a.eps_kl[(static_cast<size_t>(s) * rc.M + row) * A + k];
+        const float xo = mu_o + sig_o * eo;
+        const float u = atanhf(fminf(fmaxf(tanhf(xo), -ac.action_clip), ac.action_clip));
+        const float fu = fldj_(u);
+        if (ac.old_logp_at_clipped) {
+          const float zo = (u - mu_o) / sig_o;
+          lp_old += -0.5f * zo * zo - log_sig_o - kHalfLog2Pi - fu;
+        } else {
+          lp_old += -0.5f * eo * eo - log_sig_o - kHalfLog2Pi - fldj_(xo);
+        }
+        const float zn = (u - mu) * inv_sig;
+        lp_new += -0.5f * zn * zn - log_sig - kHalfLog2Pi - fu;
+        gm += zn * inv_sig;
+        gs += (zn * zn - 1.f) * inv_sig;
+      }
+      const float inv_s = 1.f / static_cast<float>(a.kl_samples);
+      a.gmu[static_cast<size_t>(row) * A + k] = gm * inv_s;
+      a.gsig[static_cast<size_t>(row) * A + k] = gs * inv_s;
+    }
+    logp = warp_sum(logp); lp_old = warp_sum(lp_old); lp_new = warp_sum(lp_new);
+    if (k == 0) {
+      a.logp[row] = logp;
+      a.kl[row] = (lp_old - lp_new) / static_cast<float>(a.kl_samples);
+    }
+  }
+}
+
+// Q = softmax(logits) . support and d loss / d logits of the pathwise term (actor_q_kernel of losses.cu)
+__device__ void row_q(const SlabRowArgs& a, const RowCtx& rc) {
+  const HLConsts& hl = a.hl;
+  const int B = hl.num_bins, lane = rc.lane;
+  for (int r = rc.gw; r < rc.rows_here; r += rc.nw) {
+    const int row = rc.m0 + r;
+    RowSoftmax sx;
+    row_softmax(a.head_out + static_cast<size_t>(row) * a.ld_head, a.zero_dist, hl.support, hl.bias_scale, B, lane, sx);
+    const float w_path = (a.ac.kl_mode == KL_CLIPPED) ? (a.kl[row] < a.ac.kl_bound ? 1.f : 0.f) : 1.f;
+    const float coef = -w_path * a.inv_rows;
+#pragma unroll
+    for (int j = 0; j < kMaxBinsPerLane; ++j) {
+      const int c = lane + 32 * j;
+      if (c < B) a.dl_twin[static_cast<size_t>(row) * a.dl_ld + c] = __float2bfloat16_rn(coef * sx.p[j] * (hl.support[c] - sx.value));
+    }
+    if (lane == 0) a.q[row] = sx.value;
+  }
+}
+
+// d loss / d (mu, log_std), temperature / Lagrange gradients, metrics (actor_grad_kernel of losses.cu)
+__device__ void row_actor_grad(const SlabRowArgs& a, const RowCtx& rc) {
+  const int A = a.A, k = rc.lane;
+  const ActorConsts& ac = a.ac;
+  float* scol = rc.scratch;             // [8][64]
+  float* smet = rc.scratch + 8 * 64;    // [8][8]
+  const float alpha = expf(a.actor_params[0]), beta = expf(a.actor_params[1]);
+  float m_path = 0.f, m_kl = 0.f, m_ent = 0.f, m_q = 0.f, m_abs = 0.f, m_ent_t = 0.f, m_cnt = 0.f;
+  float c_mu = 0.f, c_sig = 0.f;
+  for (int r = rc.gw; r < rc.rows_here; r += rc.nw) {
+    const int row = rc.m0 + r;
+    const float logp = a.logp[row], kl = a.kl[row], q = a.q[row];
+    float w_path, w_kl;
+    if (ac.kl_mode == KL_CLIPPED) { w_path = kl < ac.kl_bound ? 1.f : 0.f; w_kl = 1.f - w_path; }
+    else if (ac.kl_mode == KL_FULL) { w_path = 1.f; w_kl = 1.f; }
+    else { w_path = 1.f; w_kl = 0.f; }
+    const float g_logp = a.inv_rows * w_path * alpha;
+    const float g_lpnew = -a.inv_rows * w_kl * beta * ac.reduce_kl;
+    float abs_a = 0.f;
+    if (k < A) {
+      const float* o = a.actor_out + static_cast<size_t>(row) * 2 * A;
+      const float mu = o[k], ex = expf(o[A + k]), sig = ex + ac.min_std;
+      const float e = a.eps_pi[static_cast<size_t>(row) * A + k];
+      const float act = a.x0a[static_cast<size_t>(row) * a.K0 + a.Dc + k];
+      const float da = a.dx0[static_cast<size_t>(row) * a.K0 + a.Dc + k] * (1.f - act * act);
+      float dlp_mu, dlp_sig;
+      const bool clamped = ac.clip_policy_sample && !(act >= -ac.action_clip && act <= ac.action_clip);
+      if (!clamped) {
+        dlp_mu = 2.f * act;
+        dlp_sig = -1.f / sig + 2.f * act * e;
+      } else {
+        const float xc = atanhf(fminf(fmaxf(act, -ac.action_clip), ac.action_clip));
+        const float zz = (xc - mu) / sig;
+        dlp_mu = zz / sig;
+        dlp_sig = (zz * zz - 1.f) / sig;
+      }
+      const float dmu = da + g_logp * dlp_mu + g_lpnew * a.gmu[static_cast<size_t>(row) * A + k];
+      const float dsig = (da * e + g_logp * dlp_sig + g_lpnew * a.gsig[static_cast<size_t>(row) * A + k]) * ex;
+      a.dout_twin[static_cast<size_t>(row) * a.dout_ld + k] = __float2bfloat16_rn(dmu);
+      a.dout_twin[static_cast<size_t>(row) * a.dout_ld + A + k] = __float2bfloat16_rn(dsig);
+      c_mu += dmu; c_sig += dsig;
+      abs_a = fabsf(act);
+    }
+    abs_a = warp_sum(abs_a);
+    m_path += w_path * (alpha * logp - q) + w_kl * beta * ac.reduce_kl * kl;
+    m_kl += kl;
+    m_ent += -logp;
+    m_q += q;
+    m_abs += abs_a / static_cast<float>(A);
+    m_ent_t += ac.target_entropy - logp;
+    m_cnt += 1.f;
+  }
+  scol[rc.ew * 64 + k] = c_mu;
+  scol[rc.ew * 64 + 32 + k] = c_sig;
+  if (k == 0) {
+    float* m = smet + rc.ew * 8;
+    m[0] = m_path; m[1] = m_kl; m[2] = m_ent; m[3] = m_q; m[4] = m_abs; m[5] = m_ent_t; m[6] = m_cnt;
+  }
+  epi_bar();
+  if (rc.rank * 8 < rc.rows_here) {
+    const int t = rc.ew * 32 + k;
+    if (t < 2 * A && a.g_bias_actor_last != nullptr) {
+      const int slot = t < A ? t : 32 + (t - A);
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += scol[w * 64 + slot];
+      atomicAdd(a.g_bias_actor_last + t, s);
+    }
+    if (t == 255) {
+      float v[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int w = 0; w < 8; ++w)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) v[j] += smet[w * 8 + j];
+      const float inv = a.inv_rows;
+      const float s_path = v[0] * inv, s_kl = v[1] * inv, s_ent = v[2] * inv, s_q = v[3] * inv, s_abs = v[4] * inv;
+      const float s_ent_t = v[5] * inv, frac = v[6] * inv;
+      const float ent_loss = alpha * s_ent_t;
+      const float lag_loss = -beta * (s_kl - ac.kl_bound * frac);
+      float total = s_path;
+      if (ac.update_entropy) { total += ent_loss; atomicAdd(a.actor_grads + 0, ent_loss); }
+      if (ac.update_kl) { total += lag_loss; atomicAdd(a.actor_grads + 1, lag_loss); }
+      atomicAdd(a.metrics + M_ACTOR_LOSS, total);
+      atomicAdd(a.metrics + M_POLICY_LOSS, s_path);
+      atomicAdd(a.metrics + M_KL, s_kl);
+      atomicAdd(a.metrics + M_ENTROPY, s_ent);
+      atomicAdd(a.metrics + M_ENTROPY_LOSS, ent_loss);
+      atomicAdd(a.metrics + M_LAGRANGIAN_LOSS, lag_loss);
+      atomicAdd(a.metrics + M_ACTOR_Q_MEAN, s_q);
+      atomicAdd(a.metrics + M_ABS_PRED_ACTION, s_abs);
+      if (blockIdx.x == 0 && blockIdx.y == 0) { a.metrics[M_TEMPERATURE] = alpha; a.metrics[M_LAGRANGIAN] = beta; }
+    }
+  }
+  epi_bar();
+}
+
+// ---- the kernel --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSlabThreads, 2) slab_kernel(const __grid_constant__ SlabProgram prog) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBarOffset);
+  uint64_t* empty_bar = full_bar + kSlabStages;
+  uint64_t* tmem_full_bar = empty_bar + kSlabStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* stats = reinterpret_cast<float*>(smem + kStatOffset);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = blockIdx.x, ncta = gridDim.x;
+  const int m0 = blockIdx.y * SB_M, M = prog.rows;
+  const int rows_here = min(SB_M, M - m0);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(prog.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  } else if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kSlabStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  // everything above overlapped the previous kernel's tail.  The dependents are released at the LAST step, not here:
+  // this kernel runs for tens of microseconds and early-launched dependents would only park on its SMs.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // epilogue-warp coordinates (warps 2..9): TMEM lane quarter = warp % 4; the two warps of a quarter split the 64 columns
+  const int ew = warp - 2, half = (ew >> 2) & 1, lane_base = (warp & 3) * 32, cbase = half * 32;
+  const int rrow = lane_base + lane;            // row of the slab this thread owns in the row-per-thread layout
+  const int cl = (lane & 7) * 4, rg = lane >> 3; // coalesced layout: 8 lanes sweep 32 columns, 4 rows per pass
+  float* stg = reinterpret_cast<float*>(smem) + (ew & 7) * 32 * kStgLd;
+  float* part = stats;
+  float* cta_stat = stats + kOffCtaStat;
+  float* rowa = stats + kOffRowA + (ew & 7) * 32;
+  float* rowb = stats + kOffRowB + (ew & 7) * 32;
+  float* colpart = stats + kOffColPart;
+  float* metpart = stats + kOffMetPart;
+
+  RowCtx rc;
+  rc.m0 = m0; rc.rows_here = rows_here; rc.M = M; rc.gw = rank * 8 + ew; rc.nw = ncta * 8; rc.ew = ew; rc.lane = lane; rc.rank = rank;
+  rc.scratch = reinterpret_cast<float*>(smem);
+
+  uint32_t it = 0, tf = 0;   // ring iterations and accumulator hand-overs so far (uniform over the CTA)
+  for (int s = 0; s < prog.num_steps; ++s) {
+    const SlabStep& st = prog.steps[s];
+    handoff_sync();
+    if (s == prog.num_steps - 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (st.kind == SLAB_ROW) {
+      if (warp >= 2) {
+        if (st.row == ROW_GATHER_CRITIC) row_gather(prog.r, rc, false);
+        else if (st.row == ROW_GATHER_ACTOR) row_gather(prog.r, rc, true);
+        else if (st.row == ROW_CE) row_ce(prog.r, rc);
+        else if (st.row == ROW_SAMPLE) row_sample(prog.r, rc);
+        else if (st.row == ROW_Q) row_q(prog.r, rc);
+        else row_actor_grad(prog.r, rc);
+      }
+      continue;
+    }
+    const int N = st.N, epi = st.epi;
+    const int ntiles = (N + SB_N - 1) / SB_N;
+    const int my_tiles = rank < ntiles ? (ntiles - rank + ncta - 1) / ncta : 0;
+    const int nkb = (st.K + SB_K - 1) / SB_K;
+    const bool is_norm = (epi == EPI_FWD_NORM || epi == EPI_BWD_NORM);
+
+    if (warp == 0) {
+      if (lane == 0) {
+        // ===== TMA producer =====
+        asm volatile("fence.proxy.async;" ::: "memory");
+        uint32_t i = it;
+        for (int t = 0; t < my_tiles; ++t) {
+          const int n0 = (rank + t * ncta) * SB_N;
+          for (int kb = 0; kb < nkb; ++kb, ++i) {
+            const int sg = i % kSlabStages;
+            const uint32_t ph = (i / kSlabStages) & 1;
+            mbar_wait(&empty_bar[sg], ph ^ 1);
+            uint8_t* sa = smem + sg * kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_expect_tx(&full_bar[sg], kStageBytes);
+            tma_load_2d(&st.ta, &full_bar[sg], sa, kb * SB_K, m0);
+            if (!st.b_mn) tma_load_2d(&st.tb, &full_bar[sg], sb, kb * SB_K, n0);   // [n][k] tile, coordinates {k, n}
+            else tma_load_2d(&st.tb, &full_bar[sg], sb, n0, kb * SB_K);            // [k][n] tile, coordinates {n, k}
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = make_idesc(st.b_mn != 0);
+        uint32_t i = it;
+        for (int t = 0; t < my_tiles; ++t) {
+          for (int kb = 0; kb < nkb; ++kb, ++i) {
+            const int sg = i % kSlabStages;
+            const uint32_t ph = (i / kSlabStages) & 1;
+            mbar_wait(&full_bar[sg], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + sg * kStageBytes);
+            const uint32_t sb = sa + kABytes;
+#pragma unroll
+            for (int k = 0; k < SB_K / SB_UMMA_K; ++k) {
+              const uint64_t da = make_smem_desc(sa + k * (SB_UMMA_K * 2), 16, 1024);
+              const uint64_t db = st.b_mn ? make_smem_desc(sb + k * (SB_UMMA_K * 128), SB_K * 128, 1024)
+                                          : make_smem_desc(sb + k * (SB_UMMA_K * 2), 16, 1024);
+              tc_mma_bf16(tmem_base + t * SB_N, da, db, idesc, (kb > 0 || k > 0 || st.accumulate) ? 1u : 0u);
+            }
+            tc_commit(&empty_bar[sg]);
+          }
+        }
+        if (my_tiles > 0 && epi != EPI_NONE) tc_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    } else if (epi != EPI_NONE) {
+      // ===== epilogue, part 1: accumulators -> staging; row statistics of this CTA's columns =====
+      if (my_tiles == 0) {
+        if (is_norm && half == 0) { cta_stat[rrow] = 0.f; cta_stat[128 + rrow] = 0.f; }
+      } else {
+        mbar_wait(tmem_full_bar, tf & 1);
+        tc_fence_after();
+      }
+      if (my_tiles > 0 && is_norm) {
+        // one tile per CTA (N <= 64 * cluster size for normalised layers)
+        const int n0 = rank * SB_N;
+        float v[32];
+        tc_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + cbase, v);
+        float s1 = 0.f, s2 = 0.f;
+        if (epi == EPI_FWD_NORM) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = n0 + cbase + j;
+            v[j] = (col < N) ? v[j] + st.bias[col] : 0.f;
+            s1 += v[j];
+            s2 += v[j] * v[j];
+          }
+        }
+        float4* dst = reinterpret_cast<float4*>(stg + lane * kStgLd);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        if (epi == EPI_FWD_NORM) {
+          part[(0 * 2 + half) * 128 + rrow] = s1;
+          part[(1 * 2 + half) * 128 + rrow] = s2;
+        } else {
+          // BWD_NORM pass A (coalesced): dy = d * swish'(y) replaces d in the staging; partial sums of dzh and dzh * zh
+          const int col = n0 + cbase + cl;
+          float g[4], be[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { g[j] = st.gamma[col + j]; if (st.norm == NORM_LAYER) be[j] = st.beta[col + j]; }
+#pragma unroll 2
+          for (int i = 0; i < 8; ++i) {
+            const int r = rg + 4 * i;
+            const int row = m0 + lane_base + r;
+            float a1 = 0.f, a2 = 0.f;
+            if (row < M) {
+              const float4 d4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);
+              const float4 z4 = *reinterpret_cast<const float4*>(st.out + static_cast<size_t>(row) * st.ld_out + col);
+              const float rstd = st.rstd[row];
+              const float mean = (st.norm == NORM_LAYER) ? st.mean[row] : 0.f;
+              const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
+              float dy[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float zh = (zz[j] - mean) * rstd;
+                const float y = zh * g[j] + be[j];
+                dy[j] = dd[j] * swish_grad_(y);
+                const float dzh = dy[j] * g[j];
+                a1 += dzh; a2 += dzh * zh;
+              }
+              *reinterpret_cast<float4*>(stg + r * kStgLd + cl) = make_float4(dy[0], dy[1], dy[2], dy[3]);
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+            if ((lane & 7) == 0) {
+              part[(0 * 2 + half) * 128 + lane_base + r] = a1;
+              part[(1 * 2 + half) * 128 + lane_base + r] = a2;
+            }
+          }
+        }
+        epi_bar();
+        if (half == 0) {
+          cta_stat[rrow] = part[0 * 128 + rrow] + part[1 * 128 + rrow];
+          cta_stat[128 + rrow] = part[2 * 128 + rrow] + part[3 * 128 + rrow];
+        }
+      }
+      tc_fence_before();
+    }
+    if (is_norm) cluster_sync_all();   // every CTA's row statistics are published
+
+    if (warp >= 2 && epi != EPI_NONE && my_tiles > 0) {
+      // ===== epilogue, part 2 =====
+      for (int t = 0; t < my_tiles; ++t) {
+        const int n0 = (rank + t * ncta) * SB_N;
+        const int col = n0 + cbase + cl;
+        if (is_norm) {
+          float t1 = 0.f, t2 = 0.f;
+          for (int r = 0; r < ncta; ++r) { t1 += ld_dsmem_f32(cta_stat + rrow, r); t2 += ld_dsmem_f32(cta_stat + 128 + rrow, r); }
+          const float inv_n = 1.f / static_cast<float>(N);
+          if (epi == EPI_FWD_NORM) {
+            float mean = 0.f, rstd;
+            if (st.norm == NORM_RMS) {
+              rstd = rsqrtf(t2 * inv_n + st.eps);
+            } else {
+              mean = t1 * inv_n;
+              rstd = rsqrtf(t2 * inv_n - mean * mean + st.eps);   // flax use_fast_variance
+            }
+            rowa[lane] = rstd; rowb[lane] = mean;
+            if (rank == 0 && half == 0 && m0 + rrow < M) {
+              st.rstd[m0 + rrow] = rstd;
+              if (st.norm == NORM_LAYER) st.mean[m0 + rrow] = mean;
+            }
+          } else {
+            rowa[lane] = (st.norm == NORM_LAYER) ? t1 * inv_n : 0.f;   // mean(dzh)
+            rowb[lane] = t2 * inv_n;                                   // mean(dzh * zh)
+          }
+          __syncwarp();
+        } else {
+          // plain tiles: accumulators (+ bias) -> staging
+          float v[32];
+          tc_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + t * SB_N + cbase, v);
+          if (st.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const int c = n0 + cbase + j; if (c < N) v[j] += st.bias[c]; }
+          }
+          __syncwarp();   // the previous tile's readers are done with the staging
+          float4* dst = reinterpret_cast<float4*>(stg + lane * kStgLd);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+        }
+        const bool full4 = (col + 3 < N);
+        float pg[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f}, pd[4] = {0.f, 0.f, 0.f, 0.f};
+        float mv0 = 0.f, mv1 = 0.f, mv2 = 0.f;
+        float g[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+        if (is_norm) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { g[j] = st.gamma[col + j]; if (st.norm == NORM_LAYER) be[j] = st.beta[col + j]; }
+        }
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+          const int r = rg + 4 * i;
+          const int row = m0 + lane_base + r;
+          if (row >= M || col >= N) continue;
+          const float4 x4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);
+          const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+          if (epi == EPI_FWD_NORM) {
+            *reinterpret_cast<float4*>(st.out + static_cast<size_t>(row) * st.ld_out + col) = x4;
+            const float rr = rowa[r], mm = rowb[r];
+            float y[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) y[j] = swishf_((x[j] - mm) * rr * g[j] + be[j]);
+            store_bf16x4(st.twin + static_cast<size_t>(row) * st.ld_twin + col, y[0], y[1], y[2], y[3]);
+          } else if (epi == EPI_FWD_ACT) {
+            *reinterpret_cast<float4*>(st.out + static_cast<size_t>(row) * st.ld_out + col) = x4;
+            store_bf16x4(st.twin + static_cast<size_t>(row) * st.ld_twin + col, swishf_(x[0]), swishf_(x[1]), swishf_(x[2]), swishf_(x[3]));
+          } else if (epi == EPI_FWD_OUT || epi == EPI_BWD_OUT) {
+            float* o = st.out + static_cast<size_t>(row) * st.ld_out + col;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (col + j < N) o[j] = x[j];
+          } else if (epi == EPI_FWD_AUX) {
+            const SlabRowArgs& a = prog.r;
+            const long long src = a.idx ? a.idx[row] : row;
+            const float mask = a.no_mask ? 1.f : 1.f - a.truncated[src];
+            const float nd = a.mask_done ? 1.f - a.done[src] : 1.f;
+            const float gg = 2.f * mask * nd * a.aux_mult * a.inv_rows / static_cast<float>(a.P);
+            const int off = a.reward_head ? 1 : 0;
+            float sq = 0.f, dp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = col + j;
+              if (c < N) {
+                float tgt;
+                if (a.reward_head && c == 0) { tgt = a.reward[src]; mv2 += tgt * a.inv_rows; }
+                else tgt = a.next_emb[static_cast<size_t>(src) * a.H + (c - off)];
+                const float d = x[j] - tgt;
+                sq += d * d;
+                dp[j] = gg * d;
+                pd[j] += dp[j];
+              }
+            }
+            __nv_bfloat16* tw = st.twin + static_cast<size_t>(row) * st.ld_twin + col;
+            if (full4) store_bf16x4(tw, dp[0], dp[1], dp[2], dp[3]);
+            else
+#pragma unroll
+              for (int j = 0; j < 4; ++j) if (col + j < N) tw[j] = __float2bfloat16_rn(dp[j]);
+            const float aux = nd * sq / static_cast<float>(a.P);
+            mv0 += mask * a.aux_mult * aux * a.inv_rows;
+            mv1 += (a.reward_head ? aux : mask * aux) * a.inv_rows;
+          } else if (epi == EPI_BWD_NORM) {
+            const float4 z4 = *reinterpret_cast<const float4*>(st.out + static_cast<size_t>(row) * st.ld_out + col);
+            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+            const float rstd = st.rstd[row];
+            const float mean = (st.norm == NORM_LAYER) ? st.mean[row] : 0.f;
+            const float S1 = rowa[r], S2 = rowb[r];
+            float dz[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float zh = (zz[j] - mean) * rstd;
+              dz[j] = rstd * (x[j] * g[j] - S1 - zh * S2);   // x = dy
+              pg[j] += x[j] * zh;
+              pb[j] += x[j];
+              pd[j] += dz[j];
+            }
+            store_bf16x4(st.twin + static_cast<size_t>(row) * st.ld_twin + col, dz[0], dz[1], dz[2], dz[3]);
+          } else {   // EPI_BWD_ACT
+            const float4 z4 = *reinterpret_cast<const float4*>(st.out + static_cast<size_t>(row) * st.ld_out + col);
+            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+            float dz[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { dz[j] = x[j] * swish_grad_(zz[j]); pd[j] += dz[j]; }
+            store_bf16x4(st.twin + static_cast<size_t>(row) * st.ld_twin + col, dz[0], dz[1], dz[2], dz[3]);
+          }
+        }
+        // ---- column sums (bias / gamma / beta gradients) and metric partials of this tile ----
+        const bool need_g = (epi == EPI_BWD_NORM && st.g_gamma != nullptr);
+        const bool need_b = (epi == EPI_BWD_NORM && st.norm == NORM_LAYER && st.g_beta != nullptr);
+        const bool need_d = ((epi == EPI_BWD_NORM || epi == EPI_BWD_ACT || epi == EPI_FWD_AUX) && st.g_bias != nullptr);
+        if (need_g || need_b || need_d || epi == EPI_FWD_AUX) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            pg[j] += __shfl_xor_sync(0xffffffffu, pg[j], 8);  pg[j] += __shfl_xor_sync(0xffffffffu, pg[j], 16);
+            pb[j] += __shfl_xor_sync(0xffffffffu, pb[j], 8);  pb[j] += __shfl_xor_sync(0xffffffffu, pb[j], 16);
+            pd[j] += __shfl_xor_sync(0xffffffffu, pd[j], 8);  pd[j] += __shfl_xor_sync(0xffffffffu, pd[j], 16);
+          }
+          if (lane < 8) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              colpart[(0 * 8 + ew) * 32 + cl + j] = pg[j];
+              colpart[(1 * 8 + ew) * 32 + cl + j] = pb[j];
+              colpart[(2 * 8 + ew) * 32 + cl + j] = pd[j];
+            }
+          }
+          if (epi == EPI_FWD_AUX) {
+            mv0 = warp_sum(mv0); mv1 = warp_sum(mv1); mv2 = warp_sum(mv2);
+            if (lane == 0) { metpart[ew * 4 + 0] = mv0; metpart[ew * 4 + 1] = mv1; metpart[ew * 4 + 2] = mv2; }
+          }
+          epi_bar();
+          const int te = ew * 32 + lane;
+          if (te < 64) {
+            const int c = n0 + te, h = te >> 5, cc = te & 31;
+            if (c < N) {
+              float sg = 0.f, sb = 0.f, sd = 0.f;
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                sg += colpart[(0 * 8 + h * 4 + w) * 32 + cc];
+                sb += colpart[(1 * 8 + h * 4 + w) * 32 + cc];
+                sd += colpart[(2 * 8 + h * 4 + w) * 32 + cc];
+              }
+              if (need_g) atomicAdd(st.g_gamma + c, sg);
+              if (need_b) atomicAdd(st.g_beta + c, sb);
+              if (need_d) atomicAdd(st.g_bias + c, sd);
+            }
+          } else if (te == 64 && epi == EPI_FWD_AUX) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            for (int w = 0; w < 8; ++w) { a0 += metpart[w * 4 + 0]; a1 += metpart[w * 4 + 1]; a2 += metpart[w * 4 + 2]; }
+            atomicAdd(prog.r.metrics + M_CRITIC_LOSS, a0);
+            atomicAdd(prog.r.metrics + M_AUX_MEAN, a1);
+            if (a2 != 0.f) atomicAdd(prog.r.metrics + M_REWARD_MEAN, a2);
+          }
+          epi_bar();
+        }
+      }
+      tc_fence_before();
+    }
+    it += static_cast<uint32_t>(my_tiles * nkb);
+    if (my_tiles > 0 && epi != EPI_NONE) ++tf;
+  }
+  // nobody leaves (and frees its shared memory / TMEM) while a peer may still read its statistics
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(prog.tmem_cols));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+bool slab_encode_2d(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  if ((ld & 7) || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+cudaError_t launch_slab(const SlabProgram& prog, int cluster_ctas, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlabSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (prog.rows <= 0 || prog.num_steps <= 0) return cudaSuccess;
+  if (cluster_ctas < 1 || cluster_ctas > 8 || prog.num_steps > kSlabMaxSteps) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cluster_ctas, (prog.rows + SB_M - 1) / SB_M, 1);
+  cfg.blockDim = dim3(kSlabThreads);
+  cfg.dynamicSmemBytes = kSlabSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, slab_kernel, prog);
+}
+
+}  // namespace reppo
