@@ -219,6 +219,11 @@ int reppo_update(reppo_ctx* ctx, const reppo_state* state, const reppo_batch* ba
 /* kernels launched by the most recent reppo_update / step call on this ctx (bench.py's gpu_launches) */
 int64_t reppo_launch_count(const reppo_ctx* ctx);
 
+/* Profiling aid (no reference counterpart): device pointer + size of a named internal buffer inside the caller's
+ * workspace.  "slab_timing": int64[3][448] clock64() stamps ([0..63] step starts, [64 + 12 s + k] stage k of step s) of every step of the critic / policy-prefix / policy-main slab
+ * programs, recorded by CTA (0,0) when the context was created with REPPO_SLAB_TIMING=1 in the environment. */
+int reppo_debug_buffer(const reppo_ctx* ctx, const char* name, void** ptr, size_t* bytes);
+
 /* ---- data-parallel gradient all-reduce (not in the reference) ----------------
  * The library dlopen()s libnccl.so.2; rank 0 creates the 128-byte unique id, the host broadcasts it.
  * reppo_nccl_init may be called twice (with two different ids): the first communicator serves the critic chain, the

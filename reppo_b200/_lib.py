@@ -89,6 +89,7 @@ SYMBOLS = {
     "reppo_clip_adam": (C.c_int, [_vp, C.POINTER(NetState), _i64, C.POINTER(Hyper), _vp, _vp]),
     "reppo_update": (C.c_int, [_vp, C.POINTER(State), C.POINTER(Batch), C.POINTER(Plan), C.POINTER(Hyper), _vp]),
     "reppo_launch_count": (_i64, [_vp]),
+    "reppo_debug_buffer": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "reppo_nccl_unique_id": (C.c_int, [_vp, _vp]),
     "reppo_nccl_init": (C.c_int, [_vp, _vp, _i32, _i32]),
     "reppo_nccl_finalize": (C.c_int, [_vp]),

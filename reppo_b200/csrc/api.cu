@@ -130,8 +130,10 @@ struct reppo_ctx {
   // parallel branches): [0] pred-head branch, [1] weight-gradient GEMMs, [2] actor-only prefix of the actor step
   bool concurrent = true;
   bool fuse_norm = true;   // REPPO_NO_FUSE_NORM=1: separate GEMM + norm/swish kernels
-  bool slab = false;       // whole chains of a step in one persistent cluster kernel (slab.cu); REPPO_NO_SLAB=1 disables
+  bool slab = false;       // whole chains of a step in one persistent cluster kernel (slab.cu); opt-in with REPPO_SLAB=1
   int slab_cluster = 0;    // CTAs per cluster = max(hidden) / 64
+  long long* slab_timing = nullptr;   // [3][64] per-step clock stamps of the three slab programs (REPPO_SLAB_TIMING=1)
+  bool slab_timing_on = false;
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // [3]: weight gradients of the actor chain
   std::vector<cudaEvent_t> events;
   size_t ev_next = 0;
@@ -256,6 +258,7 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
   c->cp_alt = F(static_cast<size_t>(c->critic_count) + 4);
   const size_t maxdim = c->maxdim;
   c->x0a = FT(K0);
+  c->slab_timing = reinterpret_cast<long long*>(F(3 * 448 * 2));
   c->dxs = F(R * H); c->dxs2 = F(R * H); c->dfeat = FT(H); c->dlogits = FT(B); c->dpred = FT(P); c->dout = FT(2 * A);
   c->dx0 = F(R * K0);
   c->logp = F(R); c->kl = F(R); c->q = F(R); c->gmu = F(R * A); c->gsig = F(R * A);
@@ -465,12 +468,13 @@ struct SlabBuilder {
   void row(int which) {
     SlabStep* s = next();
     if (!s) return;
-    s->kind = SLAB_ROW; s->row = which;
+    s->f.kind = SLAB_ROW; s->f.row = which;
   }
   // A = bf16 twin of `a_f32` [rows, K]; W = shadow of layer L in `slot`; dgrad: out[rows, L.in] = A[rows, L.out] W
-  SlabStep* gemm(const float* a_f32, const Linear& L, int slot, bool dgrad) {
-    SlabStep* s = next();
-    if (!s) return nullptr;
+  SlabStepInfo* gemm(const float* a_f32, const Linear& L, int slot, bool dgrad) {
+    SlabStep* full = next();
+    if (!full) return nullptr;
+    SlabStepInfo* s = &full->f;
     const Twin ta = c->twin(a_f32);
     if (ta.p == nullptr) { ok = false; why = "slab operand has no bf16 twin"; return nullptr; }
     s->kind = SLAB_GEMM;
@@ -478,15 +482,15 @@ struct SlabBuilder {
     s->N = dgrad ? L.in : L.out;
     s->b_mn = dgrad ? 1 : 0;
     const uint16_t* w = c->shadow_b[slot] + L.sb;
-    bool e = slab_encode_2d(&s->ta, ta.p, rows, s->K, ta.ld, 64, 128);
+    bool e = slab_encode_2d(&full->ta, ta.p, rows, s->K, ta.ld, 64, 128);
     // forward: W [out, in] K-major, tile [64 n][64 k]; dgrad: the same matrix read as [k = out][n = in]
-    e = e && slab_encode_2d(&s->tb, w, L.out, L.in, L.ld_b, 64, 64);
+    e = e && slab_encode_2d(&full->tb, w, L.out, L.in, L.ld_b, 64, 64);
     if (!e) { ok = false; why = "cuTensorMapEncodeTiled failed"; return nullptr; }
     const int tiles = (s->N + 63) / 64;
     max_tiles = std::max(max_tiles, (tiles + c->slab_cluster - 1) / c->slab_cluster);
     return s;
   }
-  void set_twin(SlabStep* s, const float* f32) {
+  void set_twin(SlabStepInfo* s, const float* f32) {
     const Twin t = c->twin(f32);
     if (t.p == nullptr) { ok = false; why = "slab output has no bf16 twin"; return; }
     s->twin = reinterpret_cast<__nv_bfloat16*>(t.p); s->ld_twin = t.ld;
@@ -497,7 +501,7 @@ struct SlabBuilder {
     const int n = static_cast<int>(m.layers.size());
     for (int i = 0; i < n && ok; ++i) {
       const Linear& L = m.layers[i];
-      SlabStep* s = gemm(cur, L, slot, false);
+      SlabStepInfo* s = gemm(cur, L, slot, false);
       if (!s) return;
       s->bias = params + L.b;
       if (i < n - 1) {
@@ -523,7 +527,7 @@ struct SlabBuilder {
       const Linear& L = m.layers[i];
       if (i > 0) {
         const Linear& Lp = m.layers[i - 1];
-        SlabStep* s = gemm(d, L, slot, true);
+        SlabStepInfo* s = gemm(d, L, slot, true);
         if (!s) return;
         s->epi = (m.norm != NORM_NONE) ? EPI_BWD_NORM : EPI_BWD_ACT;
         s->norm = m.norm;
@@ -536,7 +540,7 @@ struct SlabBuilder {
         }
         d = a.dz[i - 1];
       } else if (first != 0) {
-        SlabStep* s = gemm(d, L, slot, true);
+        SlabStepInfo* s = gemm(d, L, slot, true);
         if (!s) return;
         s->accumulate = first_accumulate ? 1 : 0;
         if (first == 1) { s->epi = EPI_NONE; }
@@ -547,7 +551,8 @@ struct SlabBuilder {
       }
     }
   }
-  int finish(cudaStream_t st) {
+  int finish(cudaStream_t st, int prog_id = 0) {
+    p.timing = c->slab_timing_on ? c->slab_timing + 448 * prog_id : nullptr;
     if (!ok) return fail(c, REPPO_ERR_INVALID, "slab program: " + why);
     int cols = 64;
     while (cols < 64 * max_tiles) cols *= 2;
@@ -618,8 +623,9 @@ float inv_rows(const reppo_hyper* hp, int mb) {
 }
 
 // cp / cslot: the critic parameters (and their bf16 shadow slot) this step READS
+// prepped: the metric vector is already initialised and the gradient arena already zero (whole-update path)
 int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb,
-                     const reppo_hyper* hp, float* metrics, const float* cp, int cslot, cudaStream_t st) {
+                     const reppo_hyper* hp, float* metrics, const float* cp, int cslot, cudaStream_t st, bool prepped = false) {
   RET(check_rows(c, mb));
   const reppo_shape& sh = c->shape;
   float* cg = s->critic.grads;
@@ -630,8 +636,10 @@ int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
   cudaStream_t s1 = c->concurrent ? c->side[0] : st;   // pred-head branch
   cudaStream_t sw = c->concurrent ? c->side[1] : st;   // weight gradients
   const int Hc = sh.critic_hidden;
-  CK(launch_metrics_init(metrics, kCriticMetricMask, st));
-  CK(cudaMemsetAsync(cg, 0, static_cast<size_t>(c->critic_count) * sizeof(float), st));
+  if (!prepped) {
+    CK(launch_metrics_init(metrics, kCriticMetricMask, st));
+    CK(cudaMemsetAsync(cg, 0, static_cast<size_t>(c->critic_count) * sizeof(float), st));
+  }
   if (c->slab) {
     // the whole forward / loss / input-gradient chain as one cluster kernel; weight gradients follow on side streams
     SlabBuilder sb(c, mb);
@@ -651,12 +659,12 @@ int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
     sb.mlp_fwd(c->head, cp, cslot, c->xs, c->ha, EPI_FWD_OUT, nullptr);
     sb.row(ROW_CE);
     sb.mlp_fwd(c->pred, cp, cslot, c->xs, c->pa, EPI_FWD_AUX, c->dpred);
-    if (sb.ok) sb.p.steps[sb.p.num_steps - 1].g_bias = cg + c->pred.layers.back().b;
+    if (sb.ok) sb.p.steps[sb.p.num_steps - 1].f.g_bias = cg + c->pred.layers.back().b;
     sb.mlp_bwd(c->head, cp, cslot, cg, c->ha, c->dlogits, 0, false, 0, nullptr, 0, nullptr, nullptr);
     sb.mlp_bwd(c->pred, cp, cslot, cg, c->pa, c->dpred, 0, false, 0, nullptr, 0, nullptr, nullptr);
     // d swish(features) = both heads' input gradients summed in one TMEM accumulator, times swish'(features)
-    if (SlabStep* s1 = sb.gemm(c->ha.dz[0], c->head.layers[0], cslot, true)) s1->epi = EPI_NONE;
-    if (SlabStep* s2 = sb.gemm(c->pa.dz[0], c->pred.layers[0], cslot, true)) {
+    if (SlabStepInfo* s1 = sb.gemm(c->ha.dz[0], c->head.layers[0], cslot, true)) s1->epi = EPI_NONE;
+    if (SlabStepInfo* s2 = sb.gemm(c->pa.dz[0], c->pred.layers[0], cslot, true)) {
       s2->accumulate = 1; s2->epi = EPI_BWD_ACT; s2->out = c->fa.out; s2->ld_out = Hc;
       s2->g_bias = cg + c->feature.layers.back().b;
       sb.set_twin(s2, c->dfeat);
@@ -721,7 +729,7 @@ ActorConsts actor_consts(const reppo_ctx* c, const reppo_hyper* hp) {
 int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb,
                     const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, const float* old_table,
                     cudaStream_t prefix_stream, const float* cp, int cslot, cudaEvent_t critic_ready, cudaEvent_t critic_read_done,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool prepped = false) {
   RET(check_rows(c, mb));
   if (hp->kl_clip_mode < 0 || hp->kl_clip_mode > 2) return fail(c, REPPO_ERR_INVALID, "unknown actor_kl_clip_mode");
   const reppo_shape& sh = c->shape;
@@ -736,8 +744,10 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
   // The actor-only prefix (policy forward, sampling, KL statistics) does not depend on the critic update that precedes
   // it on `st`: when `pre` is a different stream it overlaps the critic step (the caller forked it before that step).
   cudaStream_t pre = prefix_stream ? prefix_stream : st;
-  CK(launch_metrics_init(metrics, kActorMetricMask, pre));
-  CK(cudaMemsetAsync(ag, 0, static_cast<size_t>(c->actor_count) * sizeof(float), pre));
+  if (!prepped) {
+    CK(launch_metrics_init(metrics, kActorMetricMask, pre));
+    CK(cudaMemsetAsync(ag, 0, static_cast<size_t>(c->actor_count) * sizeof(float), pre));
+  }
   if (c->slab) {
     if (old_table == nullptr) {
       // stand-alone call without a behaviour-policy table: evaluate actor_old on this minibatch (separate kernels)
@@ -767,7 +777,7 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
       sb.row(ROW_GATHER_ACTOR);
       sb.mlp_fwd(c->actor, ap, SLOT_ACTOR, c->xa0, c->aa, EPI_FWD_OUT, nullptr);
       sb.row(ROW_SAMPLE);
-      RET(sb.finish(pre));
+      RET(sb.finish(pre, 1));
     }
     RET(dep(c, pre, st));
     if (critic_ready != nullptr && cudaStreamWaitEvent(st, critic_ready, 0) != cudaSuccess)
@@ -782,7 +792,7 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
       sb.mlp_bwd(c->feature, cp, cslot, nullptr, *tb.fa, tb.dfeat, 2, false, EPI_BWD_OUT, c->dx0, c->K0, nullptr, nullptr);
       sb.row(ROW_ACTOR_GRAD);
       sb.mlp_bwd(c->actor, ap, SLOT_ACTOR, ag, c->aa, c->dout, 0, false, 0, nullptr, 0, nullptr, nullptr);
-      RET(sb.finish(st));
+      RET(sb.finish(st, 2));
     }
     if (critic_read_done != nullptr && cudaEventRecord(critic_read_done, st) != cudaSuccess)
       return fail(c, REPPO_ERR_CUDA, "cudaEventRecord failed");
@@ -790,11 +800,12 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
     return REPPO_OK;
   }
   Twin tw = c->twin(c->xa0);
-  CK(launch_gather_concat(b->obs, sh.obs_dim, nullptr, 0, idx, 0, mb, c->xa0, sh.obs_dim, tw.p, tw.ld, pre));
+  const Twin tx0 = c->twin(c->x0a);
+  // policy input and the observation part of the critic input, one launch
+  CK(launch_gather_pair(b->obs, sh.obs_dim, b->critic_obs, Dc, idx, mb, c->xa0, sh.obs_dim, tw.p, tw.ld, c->x0a, c->K0, tx0.p,
+                        tx0.ld, pre));
   RET(mlp_forward(c, c->actor, ap, SLOT_ACTOR, c->xa0, mb, c->aa, pre));
   if (old_table == nullptr) RET(mlp_forward(c, c->actor, s->actor_old, SLOT_ACTOR_OLD, c->xa0, mb, c->oa, pre));
-  const Twin tx0 = c->twin(c->x0a);
-  CK(launch_gather_concat(b->critic_obs, Dc, nullptr, 0, idx, 0, mb, c->x0a, c->K0, tx0.p, tx0.ld, pre));
   CK(launch_actor_sample(c->aa.out, old_table ? old_table : c->oa.out, old_table ? idx : nullptr, eps_pi, eps_kl, mb, A,
                          sh.kl_samples, ac, c->x0a + Dc, c->K0, c->logp, c->kl, c->gmu, c->gsig, tx0.p ? tx0.p + Dc : nullptr,
                          tx0.ld, pre));
@@ -825,7 +836,7 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
 // slot < 0: plain arena (no bf16 shadow to refresh)
 // p_out: where the updated parameters go (nullptr = in place); partials: scratch of the global-norm reduction
 int clip_adam_impl(reppo_ctx* c, const reppo_net_state* net, int64_t n, const reppo_hyper* hp, float* gn_out, int slot,
-                   const float* p_in, float* p_out, float* partials, cudaStream_t st) {
+                   const float* p_in, float* p_out, float* partials, cudaStream_t st, bool zero_grads = false) {
   if (c->ws == nullptr) return fail(c, REPPO_ERR_WORKSPACE, "workspace not set (reppo_set_workspace)");
   ShadowTable sh{};
   if (c->tc && slot >= 0) {
@@ -844,25 +855,27 @@ int clip_adam_impl(reppo_ctx* c, const reppo_net_state* net, int64_t n, const re
   a.max_grad_norm = hp->max_grad_norm;
   a.torch_clip = c->sem.torch_opt;
   CK(launch_clip_adam(p_in ? p_in : net->params, p_out ? p_out : net->params, net->grads, net->adam_m, net->adam_v, n, net->step,
-                      partials ? partials : c->partials, a, &sh, gn_out, st));
+                      partials ? partials : c->partials, a, &sh, gn_out, zero_grads ? 1 : 0, st));
   ++c->launches;  // two kernels
   return REPPO_OK;
 }
 
 int critic_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb,
-                     const reppo_hyper* hp, float* metrics, cudaStream_t st) {
-  RET(critic_grad_impl(c, s, b, idx, mb, hp, metrics, s->critic.params, SLOT_CRITIC, st));
+                     const reppo_hyper* hp, float* metrics, cudaStream_t st, bool prepped = false) {
+  RET(critic_grad_impl(c, s, b, idx, mb, hp, metrics, s->critic.params, SLOT_CRITIC, st, prepped));
   RET(allreduce_grads(c, s->critic.grads, c->critic_count, 0, st));
-  return clip_adam_impl(c, &s->critic, c->critic_count, hp, metrics + M_CRITIC_GRAD_NORM, SLOT_CRITIC, nullptr, nullptr, nullptr, st);
+  return clip_adam_impl(c, &s->critic, c->critic_count, hp, metrics + M_CRITIC_GRAD_NORM, SLOT_CRITIC, nullptr, nullptr, nullptr, st,
+                        prepped);
 }
 
 int actor_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb, const float* eps_pi,
                     const float* eps_kl, const reppo_hyper* hp, float* metrics, const float* old_table,
-                    cudaStream_t prefix_stream, cudaStream_t st) {
+                    cudaStream_t prefix_stream, cudaStream_t st, bool prepped = false) {
   RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, old_table, prefix_stream, s->critic.params, SLOT_CRITIC,
-                      nullptr, nullptr, st));
+                      nullptr, nullptr, st, prepped));
   RET(allreduce_grads(c, s->actor.grads, c->actor_count, 1, st));
-  return clip_adam_impl(c, &s->actor, c->actor_count, hp, metrics + M_ACTOR_GRAD_NORM, SLOT_ACTOR, nullptr, nullptr, c->partials2, st);
+  return clip_adam_impl(c, &s->actor, c->actor_count, hp, metrics + M_ACTOR_GRAD_NORM, SLOT_ACTOR, nullptr, nullptr, c->partials2, st,
+                        prepped);
 }
 
 // All epochs x minibatches.  Software pipeline over steps: the critic update of step k+1 depends only on the critic
@@ -892,6 +905,14 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
   cudaStream_t sa = pipe ? c->side[2] : st;   // the actor chain
   float* P[2] = {s->critic.params, pipe ? c->cp_alt : s->critic.params};
   const int S[2] = {SLOT_CRITIC, pipe ? SLOT_CRITIC_ALT : SLOT_CRITIC};
+  // With per-step metric vectors the whole update is prepared once: all metric rows initialised by one kernel, both
+  // gradient arenas cleared once (every Adam launch leaves its arena zeroed for the next step).
+  const bool prepped = p->step_metrics != nullptr;
+  if (prepped) {
+    CK(launch_metrics_init_all(p->step_metrics, p->num_epochs * p->num_mini_batches, st));
+    CK(cudaMemsetAsync(s->critic.grads, 0, static_cast<size_t>(c->critic_count) * sizeof(float), st));
+    CK(cudaMemsetAsync(s->actor.grads, 0, static_cast<size_t>(c->actor_count) * sizeof(float), st));
+  }
   if (pipe) RET(dep(c, st, sa));
   int64_t k = 0;
   for (int e = 0; e < p->num_epochs; ++e) {
@@ -906,22 +927,22 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
         // the actor-only prefix of this step's actor update is forked here and overlaps the critic update
         cudaStream_t pre = nullptr;
         if (c->concurrent) { pre = c->side[2]; RET(dep(c, st, pre)); }
-        RET(critic_step_impl(c, s, b, idx, mb, hp, m, st));
-        RET(actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, p->old_policy_out, pre, st));
+        RET(critic_step_impl(c, s, b, idx, mb, hp, m, st, prepped));
+        RET(actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, p->old_policy_out, pre, st, prepped));
         continue;
       }
       // ---- critic chain (stream st): reads snapshot `cur`, Adam writes snapshot `nxt`
-      RET(critic_grad_impl(c, s, b, idx, mb, hp, m, P[cur], S[cur], st));
+      RET(critic_grad_impl(c, s, b, idx, mb, hp, m, P[cur], S[cur], st, prepped));
       RET(allreduce_grads(c, s->critic.grads, c->critic_count, 0, st));
       // snapshot `nxt` was last read by actor step k-2
       if (k >= 2 && cudaStreamWaitEvent(st, c->ev_a[(k - 2) & 3], 0) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaStreamWaitEvent failed");
-      RET(clip_adam_impl(c, &s->critic, c->critic_count, hp, m + M_CRITIC_GRAD_NORM, S[nxt], P[cur], P[nxt], c->partials, st));
+      RET(clip_adam_impl(c, &s->critic, c->critic_count, hp, m + M_CRITIC_GRAD_NORM, S[nxt], P[cur], P[nxt], c->partials, st, prepped));
       if (cudaEventRecord(c->ev_c[k & 3], st) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaEventRecord failed");
       // ---- actor chain (stream sa): needs snapshot `nxt`
       RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, p->old_policy_out, nullptr, P[nxt], S[nxt], c->ev_c[k & 3],
-                          c->ev_a[k & 3], sa));
+                          c->ev_a[k & 3], sa, prepped));
       RET(allreduce_grads(c, s->actor.grads, c->actor_count, 1, sa));
-      RET(clip_adam_impl(c, &s->actor, c->actor_count, hp, m + M_ACTOR_GRAD_NORM, SLOT_ACTOR, nullptr, nullptr, c->partials2, sa));
+      RET(clip_adam_impl(c, &s->actor, c->actor_count, hp, m + M_ACTOR_GRAD_NORM, SLOT_ACTOR, nullptr, nullptr, c->partials2, sa, prepped));
     }
   }
   if (pipe) {
@@ -1012,9 +1033,10 @@ int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
   }
   {
     const int hmax = std::max(s.critic_hidden, s.actor_hidden);
-    c->slab = c->tc && getenv("REPPO_NO_SLAB") == nullptr && s.critic_hidden % 64 == 0 && s.actor_hidden % 64 == 0 &&
+    c->slab = c->tc && getenv("REPPO_SLAB") != nullptr && s.critic_hidden % 64 == 0 && s.actor_hidden % 64 == 0 &&
               hmax <= 512 && s.action_dim <= 32 && s.num_bins <= 256;
     c->slab_cluster = hmax / 64;
+    c->slab_timing_on = getenv("REPPO_SLAB_TIMING") != nullptr;
   }
   c->ws_need = layout_workspace(c, nullptr);
   *out = c;
@@ -1232,6 +1254,12 @@ int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const
 }
 
 int64_t reppo_launch_count(const reppo_ctx* c) { return c->launches; }
+
+int reppo_debug_buffer(const reppo_ctx* c, const char* name, void** ptr, size_t* bytes) {
+  if (c == nullptr || name == nullptr || ptr == nullptr || bytes == nullptr) return REPPO_ERR_INVALID;
+  if (strcmp(name, "slab_timing") == 0) { *ptr = c->slab_timing; *bytes = 3 * 448 * sizeof(long long); return REPPO_OK; }
+  return REPPO_ERR_INVALID;
+}
 
 static int nccl_load(reppo_ctx* c) {
   if (c->nccl.lib) return REPPO_OK;

@@ -18,6 +18,7 @@
 // that global stores are row-contiguous 128 B / 512 B segments.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -491,7 +492,9 @@ cudaError_t launch_gemm_bf16_tc_norm(int norm, int M, int N, int K, const void* 
       (reinterpret_cast<uintptr_t>(B) & 15) || (reinterpret_cast<uintptr_t>(C) & 15))
     return cudaErrorNotSupported;
   int block_n = 0;
-  if (N % 64 == 0 && N / 64 <= 8) block_n = 64;            // portable cluster size <= 8
+  static const bool prefer128 = getenv("REPPO_NORM_BN128") != nullptr;
+  if (prefer128 && N % 128 == 0 && N / 128 <= 8) block_n = 128;
+  else if (N % 64 == 0 && N / 64 <= 8) block_n = 64;       // portable cluster size <= 8
   else if (N % 128 == 0 && N / 128 <= 8) block_n = 128;
   if (block_n == 0) return cudaErrorNotSupported;
   CUtensorMap ta, tb;
@@ -520,7 +523,8 @@ cudaError_t launch_gemm_bf16_tc(bool a_mn, bool b_mn, int M, int N, int K, const
   CUtensorMap ta, tb;
   // narrow tiles when 128-wide ones would leave most of the 148 SMs idle
   const int tiles128 = ((M + TC_BLOCK_M - 1) / TC_BLOCK_M) * ((N + 127) / 128) * (split_k > 0 ? split_k : 1);
-  const bool wide = (N > 64) && (tiles128 >= 120);
+  static const int wide_min = getenv("REPPO_TC_WIDE_MIN") ? atoi(getenv("REPPO_TC_WIDE_MIN")) : 120;
+  const bool wide = (N > 64) && (tiles128 >= wide_min);
   const int block_n = wide ? 128 : 64;
   const bool ok_a = a_mn ? encode_2d(&ta, A, K, M, lda, 64, TC_BLOCK_K) : encode_2d(&ta, A, M, K, lda, TC_BLOCK_K, TC_BLOCK_M);
   const bool ok_b = b_mn ? encode_2d(&tb, B, K, N, ldb, 64, TC_BLOCK_K) : encode_2d(&tb, B, N, K, ldb, TC_BLOCK_K, block_n);

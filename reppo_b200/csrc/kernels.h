@@ -64,6 +64,9 @@ cudaError_t launch_colsum(const float* X, int M, int N, int ld, float* out, floa
 
 cudaError_t launch_gather_concat(const float* a, int da, const float* b, int db, const int* idx, int b_is_local,
                                  int rows, float* out, int out_ld, void* out_h, int out_ldh, cudaStream_t st);
+// two gathers in one launch: out_a[r, :] = a[idx[r], 0:da], out_b[r, 0:db] = b[idx[r], 0:db]  (fp32 + bf16 twins, all optional)
+cudaError_t launch_gather_pair(const float* a, int da, const float* b, int db, const int* idx, int rows, float* out_a, int lda,
+                               void* out_ah, int ldah, float* out_b, int ldb, void* out_bh, int ldbh, cudaStream_t st);
 cudaError_t launch_norm_act_fwd(int norm, const float* z, const float* gamma, const float* beta, int rows, int H,
                                 float eps, float* x, float* rstd, float* mean, void* x_h, int ldh, cudaStream_t st);
 cudaError_t launch_norm_act_bwd(int norm, const float* dx, const float* dx2, const float* z, const float* gamma, const float* beta,
@@ -96,9 +99,10 @@ cudaError_t launch_mean_std(const float* out, int rows, int A, float min_std, fl
 // bf16 shadows of the weight matrices, refreshed by the Adam kernel itself (REPPO_GEMM_BF16)
 struct ShadowEntry { long long start, end; int in, ld; void* dst; };
 struct ShadowTable { int n; ShadowEntry e[kMaxPack]; };
-cudaError_t launch_clip_adam(const float* p_in, float* p, const float* g, float* m, float* v, long long n, int* step, float* partials,
-                             const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out, cudaStream_t st);
+cudaError_t launch_clip_adam(const float* p_in, float* p, float* g, float* m, float* v, long long n, int* step, float* partials,
+                             const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out, int zero_grads, cudaStream_t st);
 cudaError_t launch_metrics_mean(const float* step_metrics, int first, int count, int nm, float* out, cudaStream_t st);
 cudaError_t launch_metrics_init(float* m, uint32_t mask, cudaStream_t st);
+cudaError_t launch_metrics_init_all(float* m, int steps, cudaStream_t st);
 
 }  // namespace reppo

@@ -186,7 +186,9 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
 // actor: sample + log-prob + KL estimate (thread per row)
 // -------------------------------------------------------------------------------------------------
 
-// one thread per (row, action dim); the A per-dimension partial sums of a row meet in shared memory
+// One half-warp per row.  Inside the half, lane sl owns KL sample sl (+16, ...) -- the 16 samples of the forward-KL
+// estimate are the long part of the row's work, so they run in parallel and meet in shuffle reductions -- and, for the
+// policy sample itself, action dimension sl (+16).
 __global__ void __launch_bounds__(256)
 actor_sample_kernel(const float* __restrict__ out, const float* __restrict__ out_old, const int* __restrict__ old_idx,
                     const float* __restrict__ eps_pi, const float* __restrict__ eps_kl, int rows, int A, int kl_samples,
@@ -194,38 +196,41 @@ actor_sample_kernel(const float* __restrict__ out, const float* __restrict__ out
                     float* __restrict__ kl_out, float* __restrict__ gmu_kl, float* __restrict__ gsig_kl,
                     __nv_bfloat16* __restrict__ act_h, int act_ldh) {
   REPPO_PDL_PROLOGUE();
-  __shared__ float s_logp[256], s_old[256], s_new[256];
-  const int rows_per_block = blockDim.x / A;
-  const int rl = threadIdx.x / A, k = threadIdx.x - rl * A;
-  const int row = blockIdx.x * rows_per_block + rl;
-  const bool active = (rl < rows_per_block) && (row < rows);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hw = lane >> 4, sl = lane & 15;
+  const int rl = (blockIdx.x * 8 + warp) * 2 + hw;
+  const bool ok = rl < rows;
+  const int row = ok ? rl : rows - 1;   // idle halves shadow a valid row (loads stay in bounds, nothing is written)
+  const float* o = out + static_cast<size_t>(row) * 2 * A;
+  const float* oo = out_old + static_cast<size_t>(old_idx ? old_idx[row] : row) * 2 * A;
+  const float inv_s = 1.f / static_cast<float>(kl_samples);
   float logp = 0.f, lp_old = 0.f, lp_new = 0.f;
-  if (active) {
-    const float* o = out + static_cast<size_t>(row) * 2 * A;
-    // behaviour-policy outputs: either this minibatch's rows, or rows of a whole-batch table gathered by old_idx
-    const float* oo = out_old + static_cast<size_t>(old_idx ? old_idx[row] : row) * 2 * A;
+  for (int k = sl; k < A; k += 16) {
     const float mu = o[k], sig = expf(o[A + k]) + ac.min_std;
     const float e = eps_pi[static_cast<size_t>(row) * A + k];
     const float x = mu + sig * e;
     const float a = tanhf(x);
-    act_out[static_cast<size_t>(row) * act_ld + k] = a;
-    if (act_h != nullptr) act_h[static_cast<size_t>(row) * act_ldh + k] = __float2bfloat16_rn(a);
+    if (ok) {
+      act_out[static_cast<size_t>(row) * act_ld + k] = a;
+      if (act_h != nullptr) act_h[static_cast<size_t>(row) * act_ldh + k] = __float2bfloat16_rn(a);
+    }
     const float log_sig = logf(sig);
     if (ac.clip_policy_sample) {
       // torchrl/reppo.py:301: log_prob(actions.clip(+-c)) -> base.log_prob(atanh(.)) - fldj(atanh(.))
       const float xc = atanhf(fminf(fmaxf(a, -ac.action_clip), ac.action_clip));
       const float zz = (xc - mu) / sig;
-      logp = -0.5f * zz * zz - log_sig - kHalfLog2Pi - fldj_(xc);
+      logp += -0.5f * zz * zz - log_sig - kHalfLog2Pi - fldj_(xc);
     } else {
       // distrax sample_and_log_prob: base log-prob at the pre-tanh sample minus fldj
-      logp = -0.5f * e * e - log_sig - kHalfLog2Pi - fldj_(x);
+      logp += -0.5f * e * e - log_sig - kHalfLog2Pi - fldj_(x);
     }
-    // forward KL samples from the behaviour policy
-    const float mu_o = oo[k], sig_o = expf(oo[A + k]) + ac.min_std;
-    const float log_sig_o = logf(sig_o);
-    const float inv_sig = 1.f / sig;
+  }
+  // forward KL samples from the behaviour policy
+  for (int k = 0; k < A; ++k) {
+    const float mu = o[k], sig = expf(o[A + k]) + ac.min_std, log_sig = logf(sig), inv_sig = 1.f / sig;
+    const float mu_o = oo[k], sig_o = expf(oo[A + k]) + ac.min_std, log_sig_o = logf(sig_o);
     float gm = 0.f, gs = 0.f;
-    for (int s = 0; s < kl_samples; ++s) {
+    for (int s = sl; s < kl_samples; s += 16) {
       const float eo = eps_kl[(static_cast<size_t>(s) * rows + row) * A + k];
       const float xo = mu_o + sig_o * eo;
       const float u = atanhf(fminf(fmaxf(tanhf(xo), -ac.action_clip), ac.action_clip));
@@ -241,17 +246,22 @@ actor_sample_kernel(const float* __restrict__ out, const float* __restrict__ out
       gm += zn * inv_sig;                   // d lp_new / d mu
       gs += (zn * zn - 1.f) * inv_sig;      // d lp_new / d sigma
     }
-    const float inv_s = 1.f / static_cast<float>(kl_samples);
-    gmu_kl[static_cast<size_t>(row) * A + k] = gm * inv_s;
-    gsig_kl[static_cast<size_t>(row) * A + k] = gs * inv_s;
+#pragma unroll
+    for (int of = 8; of > 0; of >>= 1) { gm += __shfl_xor_sync(0xffffffffu, gm, of); gs += __shfl_xor_sync(0xffffffffu, gs, of); }
+    if (sl == 0 && ok) {
+      gmu_kl[static_cast<size_t>(row) * A + k] = gm * inv_s;
+      gsig_kl[static_cast<size_t>(row) * A + k] = gs * inv_s;
+    }
   }
-  s_logp[threadIdx.x] = logp; s_old[threadIdx.x] = lp_old; s_new[threadIdx.x] = lp_new;
-  __syncthreads();
-  if (active && k == 0) {
-    float l = 0.f, lo = 0.f, ln = 0.f;
-    for (int j = 0; j < A; ++j) { l += s_logp[threadIdx.x + j]; lo += s_old[threadIdx.x + j]; ln += s_new[threadIdx.x + j]; }
-    logp_out[row] = l;
-    kl_out[row] = (lo - ln) / static_cast<float>(kl_samples);
+#pragma unroll
+  for (int of = 8; of > 0; of >>= 1) {
+    logp += __shfl_xor_sync(0xffffffffu, logp, of);
+    lp_old += __shfl_xor_sync(0xffffffffu, lp_old, of);
+    lp_new += __shfl_xor_sync(0xffffffffu, lp_new, of);
+  }
+  if (sl == 0 && ok) {
+    logp_out[row] = logp;
+    kl_out[row] = (lp_old - lp_new) * inv_s;
   }
 }
 
@@ -409,8 +419,8 @@ cudaError_t launch_actor_sample(const float* out, const float* out_old, const in
                                 const float* eps_kl, int rows, int A, int kl_samples, const ActorConsts& ac, float* act_out,
                                 int act_ld, float* logp, float* kl, float* gmu, float* gsig, void* act_h, int act_ldh,
                                 cudaStream_t st) {
-  if (A > 256) return cudaErrorInvalidValue;
-  const int rows_per_block = 256 / A;
+  if (rows <= 0) return cudaSuccess;
+  const int rows_per_block = 16;   // 8 warps x 2 half-warps
   launch_k((actor_sample_kernel), dim3((rows + rows_per_block - 1) / rows_per_block), dim3(256), 0, st, out, out_old, old_idx, eps_pi, eps_kl, rows, A, kl_samples, ac, act_out, act_ld, logp, kl, gmu, gsig, static_cast<__nv_bfloat16*>(act_h), act_ldh);
   return cudaGetLastError();
 }

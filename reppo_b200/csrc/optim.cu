@@ -33,9 +33,9 @@ sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict
 }
 
 __global__ void __launch_bounds__(256)
-adam_kernel(const float* p_in, float* p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
             const float* __restrict__ partials, int num_partials, const int* __restrict__ step, AdamConsts c,
-            const ShadowTable sh, float* __restrict__ grad_norm_out) {
+            const ShadowTable sh, float* __restrict__ grad_norm_out, int zero_grads) {
   REPPO_PDL_PROLOGUE();
   __shared__ float red[32];
   __shared__ float s_scale, s_bc1, s_bc2;
@@ -78,11 +78,12 @@ adam_kernel(const float* p_in, float* p, const float* __restrict__ g, float* __r
   const float4* pi4 = reinterpret_cast<const float4*>(p_in);   // may alias p (in-place update)
   float4* m4 = reinterpret_cast<float4*>(m);
   float4* v4 = reinterpret_cast<float4*>(v);
-  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* g4 = reinterpret_cast<float4*>(g);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float4 pp = pi4[i], mm = m4[i], vv = v4[i];
     const float4 gg = g4[i];
+    if (zero_grads) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // the next step accumulates into a clean arena (no memset node)
     upd(pp.x, gg.x, mm.x, vv.x, 4 * i); upd(pp.y, gg.y, mm.y, vv.y, 4 * i + 1); upd(pp.z, gg.z, mm.z, vv.z, 4 * i + 2);
     upd(pp.w, gg.w, mm.w, vv.w, 4 * i + 3);
     p4[i] = pp; m4[i] = mm; v4[i] = vv;
@@ -92,11 +93,12 @@ adam_kernel(const float* p_in, float* p, const float* __restrict__ g, float* __r
     float pp = p_in[i];
     upd(pp, g[i], m[i], v[i], i);
     p[i] = pp;
+    if (zero_grads) g[i] = 0.f;
   }
 }
 
-cudaError_t launch_clip_adam(const float* p_in, float* p, const float* g, float* m, float* v, long long n, int* step, float* partials,
-                             const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out, cudaStream_t st) {
+cudaError_t launch_clip_adam(const float* p_in, float* p, float* g, float* m, float* v, long long n, int* step, float* partials,
+                             const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out, int zero_grads, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   const long long want = (n / 4 + 255) / 256;
   int blocks = static_cast<int>(want < kMaxPartials ? want : kMaxPartials);
@@ -104,7 +106,7 @@ cudaError_t launch_clip_adam(const float* p_in, float* p, const float* g, float*
   launch_k((sumsq_partial_kernel), dim3(blocks), dim3(256), 0, st, g, n, partials, step);
   ShadowTable sh{};
   if (shadow != nullptr) sh = *shadow;
-  launch_k((adam_kernel), dim3(blocks), dim3(256), 0, st, p_in, p, g, m, v, n, partials, blocks, step, c, sh, grad_norm_out);
+  launch_k((adam_kernel), dim3(blocks), dim3(256), 0, st, p_in, p, g, m, v, n, partials, blocks, step, c, sh, grad_norm_out, zero_grads);
   return cudaGetLastError();
 }
 
@@ -128,6 +130,18 @@ __global__ void metrics_init_kernel(float* __restrict__ m, uint32_t mask) {
   REPPO_PDL_PROLOGUE();
   const int k = threadIdx.x;
   if (k < M_NUM && ((mask >> k) & 1u)) m[k] = (k == M_TARGET_MAX) ? -INFINITY : (k == M_TARGET_MIN ? INFINITY : 0.f);
+}
+// every step's metric vector of a whole update at once
+__global__ void metrics_init_all_kernel(float* __restrict__ m, int steps) {
+  REPPO_PDL_PROLOGUE();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= steps * M_NUM) return;
+  const int k = i % M_NUM;
+  m[i] = (k == M_TARGET_MAX) ? -INFINITY : (k == M_TARGET_MIN ? INFINITY : 0.f);
+}
+cudaError_t launch_metrics_init_all(float* m, int steps, cudaStream_t st) {
+  launch_k((metrics_init_all_kernel), dim3((steps * M_NUM + 255) / 256), dim3(256), 0, st, m, steps);
+  return cudaGetLastError();
 }
 cudaError_t launch_metrics_init(float* m, uint32_t mask, cudaStream_t st) {
   launch_k((metrics_init_kernel), dim3(1), dim3(32), 0, st, m, mask);

@@ -57,6 +57,42 @@ cudaError_t launch_gather_concat(const float* a, int da, const float* b, int db,
   return cudaGetLastError();
 }
 
+__global__ void gather_pair_kernel(const float* __restrict__ a, int da, const float* __restrict__ b, int db,
+                                   const int* __restrict__ idx, int rows, float* __restrict__ out_a, int lda,
+                                   __nv_bfloat16* __restrict__ out_ah, int ldah, float* __restrict__ out_b, int ldb,
+                                   __nv_bfloat16* __restrict__ out_bh, int ldbh) {
+  REPPO_PDL_PROLOGUE();
+  const int w = da + db;
+  const long long total = static_cast<long long>(rows) * w;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / w), c = static_cast<int>(i % w);
+    const long long src = idx ? idx[r] : r;
+    if (c < da) {
+      const float v = a[src * da + c];
+      if (out_a != nullptr) out_a[static_cast<long long>(r) * lda + c] = v;
+      if (out_ah != nullptr) out_ah[static_cast<long long>(r) * ldah + c] = __float2bfloat16_rn(v);
+    } else {
+      const int cc = c - da;
+      const float v = b[src * db + cc];
+      if (out_b != nullptr) out_b[static_cast<long long>(r) * ldb + cc] = v;
+      if (out_bh != nullptr) out_bh[static_cast<long long>(r) * ldbh + cc] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+cudaError_t launch_gather_pair(const float* a, int da, const float* b, int db, const int* idx, int rows, float* out_a, int lda,
+                               void* out_ah, int ldah, float* out_b, int ldb, void* out_bh, int ldbh, cudaStream_t st) {
+  const long long total = static_cast<long long>(rows) * (da + db);
+  if (total <= 0) return cudaSuccess;
+  const int block = 256;
+  const long long want = (total + block - 1) / block;
+  const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
+  launch_k((gather_pair_kernel), dim3(grid), dim3(block), 0, st, a, da, b, db, idx, rows, out_a, lda,
+           static_cast<__nv_bfloat16*>(out_ah), ldah, out_b, ldb, static_cast<__nv_bfloat16*>(out_bh), ldbh);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward: x = swish( norm(z) )      norm: none | rms (z * rsqrt(mean z^2 + eps) * g) | layer
 // saves rstd (and mean for layer norm) per row for the backward.  x (fp32) and x_h (bf16) are both

@@ -32,11 +32,13 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kRingBytes = kSlabStages * kStageBytes;   // 96 KB; doubles as epilogue staging and row-phase scratch
 constexpr int kBarOffset = kRingBytes;
 constexpr int kStatOffset = kBarOffset + 128;
-// part[2][2][128] | cta_stat[2][128] | rowa[8][32] | rowb[8][32] | colpart[3][8][32] | metpart[8][4]
-constexpr int kOffCtaStat = 512, kOffRowA = 768, kOffRowB = 1024, kOffColPart = 1280, kOffMetPart = 2048, kStatFloats = 2080;
-constexpr int kSlabSmem = kStatOffset + kStatFloats * 4 + 1024;
+// part[2][2][128] | rowa[8][32] | rowb[8][32] | colpart[3][8][32] | metpart[8][4] | colc[3][64] | allstat[8][2][128]
+constexpr int kOffRowA = 512, kOffRowB = 768, kOffColPart = 1024, kOffMetPart = 1792, kOffColC = 1824, kOffAllStat = 2016, kStatFloats = 2016 + 2048;
+constexpr int kInfoOffset = kStatOffset + kStatFloats * 4;   // shared-memory copy of the program (minus tensor maps)
+constexpr int kInfoBytes = ((kSlabMaxSteps * static_cast<int>(sizeof(SlabStepInfo)) + static_cast<int>(sizeof(SlabRowArgs)) + 15) / 16) * 16;
+constexpr int kSlabSmem = kInfoOffset + kInfoBytes + 1024;
 constexpr int kStgLd = 36;   // floats per staged row (32 + 4: conflict-free float4 rows)
-static_assert(8 * 32 * kStgLd * 4 <= kRingBytes, "epilogue staging must fit in the ring");
+static_assert(2 * 8 * 32 * kStgLd * 4 <= kRingBytes, "epilogue staging must fit in the ring");
 static_assert((8 * 256 + 8 * 8 + 16) * 4 <= kRingBytes, "row-phase scratch must fit in the ring");
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------
@@ -126,7 +128,21 @@ REPPO_DEVINL float ld_dsmem_f32(const float* local_smem_ptr, uint32_t cta_rank) 
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
   return v;
 }
+REPPO_DEVINL void st_dsmem_f32(float* local_smem_ptr, uint32_t cta_rank, float v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(cta_rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
 REPPO_DEVINL void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+
+// The slab path computes in bf16-operand precision anyway: the activation math of its epilogues uses the SFU
+// approximations (ex2.approx / rcp.approx, ~2 ulp) -- the exact expf / IEEE division made the epilogues issue-bound.
+REPPO_DEVINL float fsigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-fmaxf(x, -80.f))); }
+REPPO_DEVINL float fswish(float x) { return x * fsigmoid(x); }
+REPPO_DEVINL float fswish_grad(float x) {
+  const float s = fsigmoid(x);
+  return s * (1.f + x * (1.f - s));
+}
 
 REPPO_DEVINL void store_bf16x4(__nv_bfloat16* p, float a, float b, float c, float d) {
   const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
@@ -143,25 +159,35 @@ struct RowCtx {
   float* scratch;   // ring memory (idle during row phases)
 };
 
+// Row phases run two rows per warp pass with the rows' independent instruction streams interleaved (8 warps per
+// SM cannot hide the load / SFU latency of one row's dependent chain).
 __device__ void row_gather(const SlabRowArgs& a, const RowCtx& rc, bool actor) {
-  for (int r = rc.gw; r < rc.rows_here; r += rc.nw) {
-    const int row = rc.m0 + r;
-    const long long src = a.idx ? a.idx[row] : row;
-    if (!actor) {
-      for (int c = rc.lane; c < a.K0; c += 32) {
-        const float v = c < a.Dc ? a.critic_obs[src * a.Dc + c] : a.action[src * a.A + (c - a.Dc)];
-        a.x0_twin[static_cast<size_t>(row) * a.x0_ld + c] = __float2bfloat16_rn(v);
+  for (int r = rc.gw; r < rc.rows_here; r += 2 * rc.nw) {
+    int rows[2] = {rc.m0 + r, rc.m0 + r + rc.nw};
+    const bool ok[2] = {true, r + rc.nw < rc.rows_here};
+    long long src[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) src[q] = ok[q] ? (a.idx ? a.idx[rows[q]] : rows[q]) : 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (!ok[q]) continue;
+      const int row = rows[q];
+      if (!actor) {
+        for (int c = rc.lane; c < a.K0; c += 32) {
+          const float v = c < a.Dc ? a.critic_obs[src[q] * a.Dc + c] : a.action[src[q] * a.A + (c - a.Dc)];
+          a.x0_twin[static_cast<size_t>(row) * a.x0_ld + c] = __float2bfloat16_rn(v);
+        }
+      } else {
+        for (int c = rc.lane; c < a.D; c += 32)
+          a.xa0_twin[static_cast<size_t>(row) * a.xa0_ld + c] = __float2bfloat16_rn(a.obs[src[q] * a.D + c]);
+        for (int c = rc.lane; c < a.Dc; c += 32)
+          a.x0_twin[static_cast<size_t>(row) * a.x0_ld + c] = __float2bfloat16_rn(a.critic_obs[src[q] * a.Dc + c]);
       }
-    } else {
-      for (int c = rc.lane; c < a.D; c += 32)
-        a.xa0_twin[static_cast<size_t>(row) * a.xa0_ld + c] = __float2bfloat16_rn(a.obs[src * a.D + c]);
-      for (int c = rc.lane; c < a.Dc; c += 32)
-        a.x0_twin[static_cast<size_t>(row) * a.x0_ld + c] = __float2bfloat16_rn(a.critic_obs[src * a.Dc + c]);
     }
   }
 }
 
-// HL-Gauss cross-entropy + d logits (critic_ce_kernel of losses.cu, one warp per row)
+// HL-Gauss cross-entropy + d logits (critic_ce_kernel of losses.cu; lane owns columns lane + 32 j)
 __device__ void row_ce(const SlabRowArgs& a, const RowCtx& rc) {
   const HLConsts& hl = a.hl;
   const int B = hl.num_bins, lane = rc.lane;
@@ -170,47 +196,99 @@ __device__ void row_ce(const SlabRowArgs& a, const RowCtx& rc) {
   float vals[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   float tmax = -INFINITY, tmin = INFINITY;
   float cs[kMaxBinsPerLane];
+  // per-column constants of this lane (shared by every row): bin edges, support, logit offset
+  float e_lo[kMaxBinsPerLane], e_hi[kMaxBinsPerLane], sup[kMaxBinsPerLane], zoff[kMaxBinsPerLane];
 #pragma unroll
-  for (int j = 0; j < kMaxBinsPerLane; ++j) cs[j] = 0.f;
-  for (int r = rc.gw; r < rc.rows_here; r += rc.nw) {
-    const int row = rc.m0 + r;
-    const long long src = a.idx ? a.idx[row] : row;
-    const float tgt = a.target[src];
-    const float mask = a.no_mask ? 1.f : 1.f - a.truncated[src];
-    RowSoftmax sx;
-    row_softmax(a.head_out + static_cast<size_t>(row) * a.ld_head, a.zero_dist, hl.support, hl.bias_scale, B, lane, sx);
-    const float x = fminf(fmaxf(tgt, hl.vmin), hl.vmax);
-    const float z = erff((hl.edges[B] - x) / hl.den) - erff((hl.edges[0] - x) / hl.den) + hl.z_eps;
-    float ce = 0.f, sum_tp = 0.f, tp[kMaxBinsPerLane];
+  for (int j = 0; j < kMaxBinsPerLane; ++j) {
+    const int c = lane + 32 * j;
+    cs[j] = 0.f;
+    e_lo[j] = (c < B) ? hl.edges[c] : 0.f;
+    e_hi[j] = (c < B) ? hl.edges[c + 1] : 0.f;
+    sup[j] = (c < B) ? hl.support[c] : 0.f;
+    zoff[j] = (c < B) ? hl.bias_scale * a.zero_dist[c] : 0.f;
+  }
+  const float e_first = hl.edges[0], e_last = hl.edges[B];
+  for (int r = rc.gw; r < rc.rows_here; r += 2 * rc.nw) {
+    const int rows[2] = {rc.m0 + r, rc.m0 + r + rc.nw};
+    const bool ok[2] = {true, r + rc.nw < rc.rows_here};
+    long long src[2];
+    float tgt[2], mask[2], lg[2][kMaxBinsPerLane], tp[2][kMaxBinsPerLane];
 #pragma unroll
-    for (int j = 0; j < kMaxBinsPerLane; ++j) {
-      const int c = lane + 32 * j;
-      tp[j] = 0.f;
-      if (c < B) {
-        const float lo = erff((hl.edges[c] - x) / hl.den), hi = erff((hl.edges[c + 1] - x) / hl.den);
-        tp[j] = (hi - lo) / z;
-        ce -= tp[j] * (sx.lg[j] - sx.lse);
-        sum_tp += tp[j];
+    for (int q = 0; q < 2; ++q) src[q] = ok[q] ? (a.idx ? a.idx[rows[q]] : rows[q]) : 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float* hr = a.head_out + static_cast<size_t>(ok[q] ? rows[q] : rows[0]) * a.ld_head;
+#pragma unroll
+      for (int j = 0; j < kMaxBinsPerLane; ++j) {
+        const int c = lane + 32 * j;
+        lg[q][j] = (c < B) ? hr[c] + zoff[j] : -INFINITY;
+      }
+      tgt[q] = a.target[src[q]];
+      mask[q] = a.no_mask ? 1.f : 1.f - a.truncated[src[q]];
+    }
+    float m[2], ssum[2], val[2], ce[2], sum_tp[2], zden[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      m[q] = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kMaxBinsPerLane; ++j) m[q] = fmaxf(m[q], lg[q][j]);
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) m[q] = warp_max(m[q]);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      ssum[q] = 0.f; val[q] = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxBinsPerLane; ++j) {
+        const float p = (lane + 32 * j < B) ? __expf(lg[q][j] - m[q]) : 0.f;
+        ssum[q] += p;
+        val[q] += p * sup[j];
       }
     }
-    ce = warp_sum(ce);
-    sum_tp = warp_sum(sum_tp);
-    const float coef = mask * a.inv_rows;
 #pragma unroll
-    for (int j = 0; j < kMaxBinsPerLane; ++j) {
-      const int c = lane + 32 * j;
-      if (c < B) {
-        const float o = coef * (sum_tp * sx.p[j] - tp[j]);
-        cs[j] += o;
-        a.dl_twin[static_cast<size_t>(row) * a.dl_ld + c] = __float2bfloat16_rn(o);
+    for (int q = 0; q < 2; ++q) { ssum[q] = warp_sum(ssum[q]); val[q] = warp_sum(val[q]); }
+    const float inv_den = 1.f / hl.den;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float x = fminf(fmaxf(tgt[q], hl.vmin), hl.vmax);
+      zden[q] = erff((e_last - x) * inv_den) - erff((e_first - x) * inv_den) + hl.z_eps;
+      const float inv_z = 1.f / zden[q];
+      const float lse = m[q] + logf(ssum[q]);
+      ce[q] = 0.f; sum_tp[q] = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxBinsPerLane; ++j) {
+        tp[q][j] = 0.f;
+        if (lane + 32 * j < B) {
+          tp[q][j] = (erff((e_hi[j] - x) * inv_den) - erff((e_lo[j] - x) * inv_den)) * inv_z;
+          ce[q] -= tp[q][j] * (lg[q][j] - lse);
+          sum_tp[q] += tp[q][j];
+        }
       }
     }
-    vals[0] += mask * ce * a.inv_rows;
-    vals[1] += ce * a.inv_rows;
-    vals[2] += (sx.value - tgt) * (sx.value - tgt) * a.inv_rows;
-    vals[3] += sx.value * a.inv_rows;
-    vals[4] += tgt * a.inv_rows;
-    tmax = fmaxf(tmax, tgt); tmin = fminf(tmin, tgt);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { ce[q] = warp_sum(ce[q]); sum_tp[q] = warp_sum(sum_tp[q]); }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (!ok[q]) continue;
+      const float coef = mask[q] * a.inv_rows, inv_s = 1.f / ssum[q];
+      const float value = val[q] * inv_s;
+#pragma unroll
+      for (int j = 0; j < kMaxBinsPerLane; ++j) {
+        const int c = lane + 32 * j;
+        if (c < B) {
+          const float p = __expf(lg[q][j] - m[q]) * inv_s;
+          const float o = coef * (sum_tp[q] * p - tp[q][j]);
+          cs[j] += o;
+          a.dl_twin[static_cast<size_t>(rows[q]) * a.dl_ld + c] = __float2bfloat16_rn(o);
+        }
+      }
+      vals[0] += mask[q] * ce[q] * a.inv_rows;
+      vals[1] += ce[q] * a.inv_rows;
+      vals[2] += (value - tgt[q]) * (value - tgt[q]) * a.inv_rows;
+      vals[3] += value * a.inv_rows;
+      vals[4] += tgt[q] * a.inv_rows;
+      tmax = fmaxf(tmax, tgt[q]); tmin = fminf(tmin, tgt[q]);
+    }
   }
 #pragma unroll
   for (int j = 0; j < kMaxBinsPerLane; ++j) scol[rc.ew * 256 + lane + 32 * j] = cs[j];
@@ -247,36 +325,43 @@ __device__ void row_ce(const SlabRowArgs& a, const RowCtx& rc) {
   epi_bar();
 }
 
-// tanh-Gaussian sample, log-prob, 16-sample forward KL and its gradient (actor_sample_kernel of losses.cu);
-// lane k owns action dimension k
+// tanh-Gaussian sample, log-prob, forward KL to the behaviour policy and its gradient (actor_sample_kernel of
+// losses.cu).  A warp takes two rows per pass, one per half-warp; inside a half, lane sl owns KL sample sl (+16 ...)
+// and, for the policy sample itself, action dimension sl (+16).
 __device__ void row_sample(const SlabRowArgs& a, const RowCtx& rc) {
-  const int A = a.A, k = rc.lane;
+  const int A = a.A, hw = rc.lane >> 4, sl = rc.lane & 15;
   const ActorConsts& ac = a.ac;
-  for (int r = rc.gw; r < rc.rows_here; r += rc.nw) {
-    const int row = rc.m0 + r;
+  const float inv_s = 1.f / static_cast<float>(a.kl_samples);
+  for (int r = rc.gw; r < rc.rows_here; r += 2 * rc.nw) {
+    const int rl = r + hw * rc.nw;
+    const bool ok = rl < rc.rows_here;
+    const int row = rc.m0 + (ok ? rl : r);
+    const float* o = a.actor_out + static_cast<size_t>(row) * 2 * A;
+    const float* oo = a.old_out + static_cast<size_t>(a.old_idx ? a.old_idx[row] : row) * 2 * A;
     float logp = 0.f, lp_old = 0.f, lp_new = 0.f;
-    if (k < A) {
-      const float* o = a.actor_out + static_cast<size_t>(row) * 2 * A;
-      const float* oo = a.old_out + static_cast<size_t>(a.old_idx ? a.old_idx[row] : row) * 2 * A;
-      const float mu = o[k], sig = expf(o[A + k]) + ac.min_std;
+    for (int k = sl; k < A; k += 16) {
+      const float mu = o[k], sig = __expf(o[A + k]) + ac.min_std;
       const float e = a.eps_pi[static_cast<size_t>(row) * A + k];
       const float x = mu + sig * e;
       const float act = tanhf(x);
-      a.x0a[static_cast<size_t>(row) * a.K0 + a.Dc + k] = act;
-      a.x0_twin[static_cast<size_t>(row) * a.x0_ld + a.Dc + k] = __float2bfloat16_rn(act);
+      if (ok) {
+        a.x0a[static_cast<size_t>(row) * a.K0 + a.Dc + k] = act;
+        a.x0_twin[static_cast<size_t>(row) * a.x0_ld + a.Dc + k] = __float2bfloat16_rn(act);
+      }
       const float log_sig = logf(sig);
       if (ac.clip_policy_sample) {
         const float xc = atanhf(fminf(fmaxf(act, -ac.action_clip), ac.action_clip));
         const float zz = (xc - mu) / sig;
-        logp = -0.5f * zz * zz - log_sig - kHalfLog2Pi - fldj_(xc);
+        logp += -0.5f * zz * zz - log_sig - kHalfLog2Pi - fldj_(xc);
       } else {
-        logp = -0.5f * e * e - log_sig - kHalfLog2Pi - fldj_(x);
+        logp += -0.5f * e * e - log_sig - kHalfLog2Pi - fldj_(x);
       }
-      const float mu_o = oo[k], sig_o = expf(oo[A + k]) + ac.min_std;
-      const float log_sig_o = logf(sig_o);
-      const float inv_sig = 1.f / sig;
+    }
+    for (int k = 0; k < A; ++k) {
+      const float mu = o[k], sig = __expf(o[A + k]) + ac.min_std, log_sig = logf(sig), inv_sig = 1.f / sig;
+      const float mu_o = oo[k], sig_o = __expf(oo[A + k]) + ac.min_std, log_sig_o = logf(sig_o);
       float gm = 0.f, gs = 0.f;
-      for (int s = 0; s < a.kl_samples; ++s) {
+      for (int s = sl; s < a.kl_samples; s += 16) {
         const float eo = a.eps_kl[(static_cast<size_t>(s) * rc.M + row) * A + k];
         const float xo = mu_o + sig_o * eo;
         const float u = atanhf(fminf(fmaxf(tanhf(xo), -ac.action_clip), ac.action_clip));
@@ -292,14 +377,22 @@ __device__ void row_sample(const SlabRowArgs& a, const RowCtx& rc) {
         gm += zn * inv_sig;
         gs += (zn * zn - 1.f) * inv_sig;
       }
-      const float inv_s = 1.f / static_cast<float>(a.kl_samples);
-      a.gmu[static_cast<size_t>(row) * A + k] = gm * inv_s;
-      a.gsig[static_cast<size_t>(row) * A + k] = gs * inv_s;
+#pragma unroll
+      for (int of = 8; of > 0; of >>= 1) { gm += __shfl_xor_sync(0xffffffffu, gm, of); gs += __shfl_xor_sync(0xffffffffu, gs, of); }
+      if (sl == 0 && ok) {
+        a.gmu[static_cast<size_t>(row) * A + k] = gm * inv_s;
+        a.gsig[static_cast<size_t>(row) * A + k] = gs * inv_s;
+      }
     }
-    logp = warp_sum(logp); lp_old = warp_sum(lp_old); lp_new = warp_sum(lp_new);
-    if (k == 0) {
+#pragma unroll
+    for (int of = 8; of > 0; of >>= 1) {
+      logp += __shfl_xor_sync(0xffffffffu, logp, of);
+      lp_old += __shfl_xor_sync(0xffffffffu, lp_old, of);
+      lp_new += __shfl_xor_sync(0xffffffffu, lp_new, of);
+    }
+    if (sl == 0 && ok) {
       a.logp[row] = logp;
-      a.kl[row] = (lp_old - lp_new) / static_cast<float>(a.kl_samples);
+      a.kl[row] = (lp_old - lp_new) * inv_s;
     }
   }
 }
@@ -308,18 +401,58 @@ __device__ void row_sample(const SlabRowArgs& a, const RowCtx& rc) {
 __device__ void row_q(const SlabRowArgs& a, const RowCtx& rc) {
   const HLConsts& hl = a.hl;
   const int B = hl.num_bins, lane = rc.lane;
-  for (int r = rc.gw; r < rc.rows_here; r += rc.nw) {
-    const int row = rc.m0 + r;
-    RowSoftmax sx;
-    row_softmax(a.head_out + static_cast<size_t>(row) * a.ld_head, a.zero_dist, hl.support, hl.bias_scale, B, lane, sx);
-    const float w_path = (a.ac.kl_mode == KL_CLIPPED) ? (a.kl[row] < a.ac.kl_bound ? 1.f : 0.f) : 1.f;
-    const float coef = -w_path * a.inv_rows;
+  float sup[kMaxBinsPerLane], zoff[kMaxBinsPerLane];
 #pragma unroll
-    for (int j = 0; j < kMaxBinsPerLane; ++j) {
-      const int c = lane + 32 * j;
-      if (c < B) a.dl_twin[static_cast<size_t>(row) * a.dl_ld + c] = __float2bfloat16_rn(coef * sx.p[j] * (hl.support[c] - sx.value));
+  for (int j = 0; j < kMaxBinsPerLane; ++j) {
+    const int c = lane + 32 * j;
+    sup[j] = (c < B) ? hl.support[c] : 0.f;
+    zoff[j] = (c < B) ? hl.bias_scale * a.zero_dist[c] : 0.f;
+  }
+  for (int r = rc.gw; r < rc.rows_here; r += 2 * rc.nw) {
+    const int rows[2] = {rc.m0 + r, rc.m0 + r + rc.nw};
+    const bool ok[2] = {true, r + rc.nw < rc.rows_here};
+    float lg[2][kMaxBinsPerLane], klv[2], m[2], ssum[2], val[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int row = ok[q] ? rows[q] : rows[0];
+      const float* hr = a.head_out + static_cast<size_t>(row) * a.ld_head;
+#pragma unroll
+      for (int j = 0; j < kMaxBinsPerLane; ++j) lg[q][j] = (lane + 32 * j < B) ? hr[lane + 32 * j] + zoff[j] : -INFINITY;
+      klv[q] = a.kl[row];
     }
-    if (lane == 0) a.q[row] = sx.value;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      m[q] = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kMaxBinsPerLane; ++j) m[q] = fmaxf(m[q], lg[q][j]);
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) m[q] = warp_max(m[q]);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      ssum[q] = 0.f; val[q] = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxBinsPerLane; ++j) {
+        lg[q][j] = (lane + 32 * j < B) ? __expf(lg[q][j] - m[q]) : 0.f;   // un-normalised probabilities from here on
+        ssum[q] += lg[q][j];
+        val[q] += lg[q][j] * sup[j];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { ssum[q] = warp_sum(ssum[q]); val[q] = warp_sum(val[q]); }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (!ok[q]) continue;
+      const float inv_s = 1.f / ssum[q], value = val[q] * inv_s;
+      const float w_path = (a.ac.kl_mode == KL_CLIPPED) ? (klv[q] < a.ac.kl_bound ? 1.f : 0.f) : 1.f;
+      const float coef = -w_path * a.inv_rows * inv_s;
+#pragma unroll
+      for (int j = 0; j < kMaxBinsPerLane; ++j) {
+        const int c = lane + 32 * j;
+        if (c < B) a.dl_twin[static_cast<size_t>(rows[q]) * a.dl_ld + c] = __float2bfloat16_rn(coef * lg[q][j] * (sup[j] - value));
+      }
+      if (lane == 0) a.q[rows[q]] = value;
+    }
   }
 }
 
@@ -419,7 +552,7 @@ __device__ void row_actor_grad(const SlabRowArgs& a, const RowCtx& rc) {
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSlabThreads, 2) slab_kernel(const __grid_constant__ SlabProgram prog) {
+__global__ void __launch_bounds__(kSlabThreads, 1) slab_kernel(const __grid_constant__ SlabProgram prog) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBarOffset);
@@ -444,6 +577,23 @@ __global__ void __launch_bounds__(kSlabThreads, 2) slab_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // The program lives in the kernel-parameter constant bank; cluster barriers invalidate the constant caches along
+  // with L1, so every descriptor field read after a barrier would be an L2 round trip: keep a shared-memory copy.
+  SlabStepInfo* sinfo = reinterpret_cast<SlabStepInfo*>(smem + kInfoOffset);
+  SlabRowArgs* rargs_s = reinterpret_cast<SlabRowArgs*>(sinfo + kSlabMaxSteps);
+  {
+    constexpr int kW = sizeof(SlabStepInfo) / 4;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sinfo);
+    for (int w = threadIdx.x; w < prog.num_steps * kW; w += kSlabThreads)
+      dst[w] = reinterpret_cast<const uint32_t*>(&prog.steps[w / kW].f)[w % kW];
+    uint32_t* dr = reinterpret_cast<uint32_t*>(rargs_s);
+    for (int w = threadIdx.x; w < static_cast<int>(sizeof(SlabRowArgs) / 4); w += kSlabThreads)
+      dr[w] = reinterpret_cast<const uint32_t*>(&prog.r)[w];
+  }
+  __syncthreads();
+  const SlabRowArgs& rargs = *rargs_s;
+  const int num_steps = prog.num_steps;
+  long long* const timing = prog.timing;
   const uint32_t tmem_base = *tmem_ptr_smem;
   // everything above overlapped the previous kernel's tail.  The dependents are released at the LAST step, not here:
   // this kernel runs for tens of microseconds and early-launched dependents would only park on its SMs.
@@ -454,30 +604,36 @@ __global__ void __launch_bounds__(kSlabThreads, 2) slab_kernel(const __grid_cons
   const int rrow = lane_base + lane;            // row of the slab this thread owns in the row-per-thread layout
   const int cl = (lane & 7) * 4, rg = lane >> 3; // coalesced layout: 8 lanes sweep 32 columns, 4 rows per pass
   float* stg = reinterpret_cast<float*>(smem) + (ew & 7) * 32 * kStgLd;
+  float* stg2 = stg + 8 * 32 * kStgLd;   // second staging plane (norm backward keeps dy and zh)
   float* part = stats;
-  float* cta_stat = stats + kOffCtaStat;
   float* rowa = stats + kOffRowA + (ew & 7) * 32;
   float* rowb = stats + kOffRowB + (ew & 7) * 32;
   float* colpart = stats + kOffColPart;
   float* metpart = stats + kOffMetPart;
+  float* allstat = stats + kOffAllStat;   // [source rank][2][128]: every CTA's row statistics, pushed by the owners
+  float* colc = stats + kOffColC;   // bias | gamma | beta of this CTA's first tile (fetched while the MMAs run)
 
   RowCtx rc;
   rc.m0 = m0; rc.rows_here = rows_here; rc.M = M; rc.gw = rank * 8 + ew; rc.nw = ncta * 8; rc.ew = ew; rc.lane = lane; rc.rank = rank;
   rc.scratch = reinterpret_cast<float*>(smem);
 
   uint32_t it = 0, tf = 0;   // ring iterations and accumulator hand-overs so far (uniform over the CTA)
-  for (int s = 0; s < prog.num_steps; ++s) {
-    const SlabStep& st = prog.steps[s];
+  const bool timed = timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+#define SLAB_STAMP(k) do { if (timed) timing[64 + s * 12 + (k)] = clock64(); } while (0)
+  for (int s = 0; s < num_steps; ++s) {
+    const SlabStepInfo& st = sinfo[s];
+    const SlabStep& maps = prog.steps[s];
     handoff_sync();
-    if (s == prog.num_steps - 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (timed && threadIdx.x == 64) timing[s] = clock64();
+    if (s == num_steps - 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (st.kind == SLAB_ROW) {
       if (warp >= 2) {
-        if (st.row == ROW_GATHER_CRITIC) row_gather(prog.r, rc, false);
-        else if (st.row == ROW_GATHER_ACTOR) row_gather(prog.r, rc, true);
-        else if (st.row == ROW_CE) row_ce(prog.r, rc);
-        else if (st.row == ROW_SAMPLE) row_sample(prog.r, rc);
-        else if (st.row == ROW_Q) row_q(prog.r, rc);
-        else row_actor_grad(prog.r, rc);
+        if (st.row == ROW_GATHER_CRITIC) row_gather(rargs, rc, false);
+        else if (st.row == ROW_GATHER_ACTOR) row_gather(rargs, rc, true);
+        else if (st.row == ROW_CE) row_ce(rargs, rc);
+        else if (st.row == ROW_SAMPLE) row_sample(rargs, rc);
+        else if (st.row == ROW_Q) row_q(rargs, rc);
+        else row_actor_grad(rargs, rc);
       }
       continue;
     }
@@ -486,6 +642,8 @@ __global__ void __launch_bounds__(kSlabThreads, 2) slab_kernel(const __grid_cons
     const int my_tiles = rank < ntiles ? (ntiles - rank + ncta - 1) / ncta : 0;
     const int nkb = (st.K + SB_K - 1) / SB_K;
     const bool is_norm = (epi == EPI_FWD_NORM || epi == EPI_BWD_NORM);
+    float4 pre[8];              // epilogue operands fetched from global memory during the main loop
+    float prow[8], prow2[8];
 
     if (warp == 0) {
       if (lane == 0) {
@@ -501,11 +659,12 @@ __global__ void __launch_bounds__(kSlabThreads, 2) slab_kernel(const __grid_cons
             uint8_t* sa = smem + sg * kStageBytes;
             uint8_t* sb = sa + kABytes;
             mbar_expect_tx(&full_bar[sg], kStageBytes);
-            tma_load_2d(&st.ta, &full_bar[sg], sa, kb * SB_K, m0);
-            if (!st.b_mn) tma_load_2d(&st.tb, &full_bar[sg], sb, kb * SB_K, n0);   // [n][k] tile, coordinates {k, n}
-            else tma_load_2d(&st.tb, &full_bar[sg], sb, n0, kb * SB_K);            // [k][n] tile, coordinates {n, k}
+            tma_load_2d(&maps.ta, &full_bar[sg], sa, kb * SB_K, m0);
+            if (!st.b_mn) tma_load_2d(&maps.tb, &full_bar[sg], sb, kb * SB_K, n0);   // [n][k] tile, coordinates {k, n}
+            else tma_load_2d(&maps.tb, &full_bar[sg], sb, n0, kb * SB_K);            // [k][n] tile, coordinates {n, k}
           }
         }
+        SLAB_STAMP(1);
       }
       __syncwarp();
     } else if (warp == 1) {
@@ -519,6 +678,7 @@ __global__ void __launch_bounds__(kSlabThreads, 2) slab_kernel(const __grid_cons
             const uint32_t ph = (i / kSlabStages) & 1;
             mbar_wait(&full_bar[sg], ph);
             tc_fence_after();
+            if (t == 0 && kb == 0) SLAB_STAMP(2);
             const uint32_t sa = smem_u32(smem + sg * kStageBytes);
             const uint32_t sb = sa + kABytes;
 #pragma unroll
@@ -532,66 +692,109 @@ __global__ void __launch_bounds__(kSlabThreads, 2) slab_kernel(const __grid_cons
           }
         }
         if (my_tiles > 0 && epi != EPI_NONE) tc_commit(tmem_full_bar);
+        SLAB_STAMP(3);
       }
       __syncwarp();
     } else if (epi != EPI_NONE) {
+      // ===== epilogue, part 0: what the epilogue needs from global memory is requested while the MMAs run =====
+      // (coalesced layout: this thread's rows rg + 4 i, columns col0 .. col0 + 3 of the CTA's first tile)
+      const int col0 = rank * SB_N + cbase + cl;
+      if (my_tiles > 0) {
+        const int te = ew * 32 + lane;
+        if (te < SB_N) {
+          const int c = rank * SB_N + te;
+          colc[te] = (st.bias != nullptr && c < N) ? st.bias[c] : 0.f;
+          colc[64 + te] = (is_norm && st.gamma != nullptr && c < N) ? st.gamma[c] : 1.f;
+          colc[128 + te] = (is_norm && st.beta != nullptr && c < N) ? st.beta[c] : 0.f;
+        }
+      }
+      if (my_tiles > 0 && (epi == EPI_BWD_NORM || epi == EPI_BWD_ACT)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = m0 + lane_base + rg + 4 * i;
+          pre[i] = make_float4(0.f, 0.f, 0.f, 0.f); prow[i] = 0.f; prow2[i] = 0.f;
+          if (row < M && col0 < N) {
+            pre[i] = *reinterpret_cast<const float4*>(st.out + static_cast<size_t>(row) * st.ld_out + col0);   // saved z
+            if (epi == EPI_BWD_NORM) { prow[i] = st.rstd[row]; if (st.norm == NORM_LAYER) prow2[i] = st.mean[row]; }
+          }
+        }
+      } else if (my_tiles > 0 && epi == EPI_FWD_AUX) {
+        const SlabRowArgs& a = rargs;
+        int srcs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = m0 + lane_base + rg + 4 * i;
+          srcs[i] = (row < M) ? (a.idx ? a.idx[row] : row) : -1;
+        }
+        const int off = a.reward_head ? 1 : 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          pre[i] = make_float4(0.f, 0.f, 0.f, 0.f); prow[i] = 0.f; prow2[i] = 0.f;
+          if (srcs[i] >= 0) {
+            const size_t sr = static_cast<size_t>(srcs[i]);
+            prow[i] = a.no_mask ? 1.f : 1.f - a.truncated[sr];
+            prow2[i] = a.mask_done ? 1.f - a.done[sr] : 1.f;
+            float tg[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int cc = col0 + j;
+              tg[j] = (cc < N) ? ((a.reward_head && cc == 0) ? a.reward[sr] : a.next_emb[sr * a.H + (cc - off)]) : 0.f;
+            }
+            pre[i] = make_float4(tg[0], tg[1], tg[2], tg[3]);
+          }
+        }
+      }
       // ===== epilogue, part 1: accumulators -> staging; row statistics of this CTA's columns =====
-      if (my_tiles == 0) {
-        if (is_norm && half == 0) { cta_stat[rrow] = 0.f; cta_stat[128 + rrow] = 0.f; }
-      } else {
+      if (my_tiles > 0) {
+        epi_bar();   // colc is complete
         mbar_wait(tmem_full_bar, tf & 1);
         tc_fence_after();
+        if (threadIdx.x == 64) SLAB_STAMP(4);
       }
       if (my_tiles > 0 && is_norm) {
         // one tile per CTA (N <= 64 * cluster size for normalised layers)
         const int n0 = rank * SB_N;
-        float v[32];
-        tc_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + cbase, v);
         float s1 = 0.f, s2 = 0.f;
-        if (epi == EPI_FWD_NORM) {
+        {
+          float v[32];
+          tc_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + cbase, v);
+          if (epi == EPI_FWD_NORM) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = n0 + cbase + j;
-            v[j] = (col < N) ? v[j] + st.bias[col] : 0.f;
-            s1 += v[j];
-            s2 += v[j] * v[j];
+            for (int j = 0; j < 32; ++j) {
+              const int col = n0 + cbase + j;
+              v[j] = (col < N) ? v[j] + colc[cbase + j] : 0.f;
+              s1 += v[j];
+              s2 += v[j] * v[j];
+            }
           }
-        }
-        float4* dst = reinterpret_cast<float4*>(stg + lane * kStgLd);
+          float4* dst = reinterpret_cast<float4*>(stg + lane * kStgLd);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
         __syncwarp();
         if (epi == EPI_FWD_NORM) {
           part[(0 * 2 + half) * 128 + rrow] = s1;
           part[(1 * 2 + half) * 128 + rrow] = s2;
         } else {
-          // BWD_NORM pass A (coalesced): dy = d * swish'(y) replaces d in the staging; partial sums of dzh and dzh * zh
-          const int col = n0 + cbase + cl;
+          // BWD_NORM pass A (coalesced): dy = d * swish'(y) and zh replace d in the staging; partial sums of dzh and dzh * zh
           float g[4], be[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { g[j] = st.gamma[col + j]; if (st.norm == NORM_LAYER) be[j] = st.beta[col + j]; }
-#pragma unroll 2
+          for (int j = 0; j < 4; ++j) { g[j] = colc[64 + cbase + cl + j]; be[j] = colc[128 + cbase + cl + j]; }
+#pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = rg + 4 * i;
-            const int row = m0 + lane_base + r;
-            float a1 = 0.f, a2 = 0.f;
-            if (row < M) {
-              const float4 d4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);
-              const float4 z4 = *reinterpret_cast<const float4*>(st.out + static_cast<size_t>(row) * st.ld_out + col);
-              const float rstd = st.rstd[row];
-              const float mean = (st.norm == NORM_LAYER) ? st.mean[row] : 0.f;
-              const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
-              float dy[4];
+            const float4 d4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);
+            const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, zz[4] = {pre[i].x, pre[i].y, pre[i].z, pre[i].w};
+            float dy[4], zh[4], a1 = 0.f, a2 = 0.f;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float zh = (zz[j] - mean) * rstd;
-                const float y = zh * g[j] + be[j];
-                dy[j] = dd[j] * swish_grad_(y);
-                const float dzh = dy[j] * g[j];
-                a1 += dzh; a2 += dzh * zh;
-              }
-              *reinterpret_cast<float4*>(stg + r * kStgLd + cl) = make_float4(dy[0], dy[1], dy[2], dy[3]);
+            for (int j = 0; j < 4; ++j) {
+              zh[j] = (zz[j] - prow2[i]) * prow[i];
+              dy[j] = dd[j] * fswish_grad(zh[j] * g[j] + be[j]);   // rows past the end: d = 0 (TMA zero fill), z = 0
+              const float dzh = dy[j] * g[j];
+              a1 += dzh; a2 += dzh * zh[j];
             }
+            *reinterpret_cast<float4*>(stg + r * kStgLd + cl) = make_float4(dy[0], dy[1], dy[2], dy[3]);
+            *reinterpret_cast<float4*>(stg2 + r * kStgLd + cl) = make_float4(zh[0], zh[1], zh[2], zh[3]);
 #pragma unroll
             for (int o = 1; o < 8; o <<= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
             if ((lane & 7) == 0) {
@@ -602,13 +805,21 @@ __global__ void __launch_bounds__(kSlabThreads, 2) slab_kernel(const __grid_cons
         }
         epi_bar();
         if (half == 0) {
-          cta_stat[rrow] = part[0 * 128 + rrow] + part[1 * 128 + rrow];
-          cta_stat[128 + rrow] = part[2 * 128 + rrow] + part[3 * 128 + rrow];
+          // push this CTA's per-row partial statistics into every peer (remote stores: fire and forget; the cluster
+          // barrier below publishes them) -- pulling them after the barrier costs one remote round trip per peer
+          const float u1 = part[0 * 128 + rrow] + part[1 * 128 + rrow];
+          const float u2 = part[2 * 128 + rrow] + part[3 * 128 + rrow];
+          for (int r = 0; r < ncta; ++r) {
+            st_dsmem_f32(allstat + (rank * 2 + 0) * 128 + rrow, r, u1);
+            st_dsmem_f32(allstat + (rank * 2 + 1) * 128 + rrow, r, u2);
+          }
         }
       }
       tc_fence_before();
+      if (threadIdx.x == 64) SLAB_STAMP(5);
     }
     if (is_norm) cluster_sync_all();   // every CTA's row statistics are published
+    if (threadIdx.x == 64) SLAB_STAMP(6);
 
     if (warp >= 2 && epi != EPI_NONE && my_tiles > 0) {
       // ===== epilogue, part 2 =====
@@ -616,8 +827,14 @@ __global__ void __launch_bounds__(kSlabThreads, 2) slab_kernel(const __grid_cons
         const int n0 = (rank + t * ncta) * SB_N;
         const int col = n0 + cbase + cl;
         if (is_norm) {
+          // totals over the cluster (pushed into this CTA's shared memory by the owners)
+          const int nsrc = min(ncta, ntiles);   // CTAs that own a tile of this layer
           float t1 = 0.f, t2 = 0.f;
-          for (int r = 0; r < ncta; ++r) { t1 += ld_dsmem_f32(cta_stat + rrow, r); t2 += ld_dsmem_f32(cta_stat + 128 + rrow, r); }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            if (r < nsrc) { t1 += allstat[(r * 2 + 0) * 128 + rrow]; t2 += allstat[(r * 2 + 1) * 128 + rrow]; }
+          }
+          if (threadIdx.x == 64) SLAB_STAMP(8);
           const float inv_n = 1.f / static_cast<float>(N);
           if (epi == EPI_FWD_NORM) {
             float mean = 0.f, rstd;
@@ -641,9 +858,13 @@ __global__ void __launch_bounds__(kSlabThreads, 2) slab_kernel(const __grid_cons
           // plain tiles: accumulators (+ bias) -> staging
           float v[32];
           tc_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) + t * SB_N + cbase, v);
-          if (st.bias != nullptr) {
+          if (threadIdx.x == 64) SLAB_STAMP(8);
+          if (t == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { const int c = n0 + cbase + j; if (c < N) v[j] += st.bias[c]; }
+            for (int j = 0; j < 32; ++j) v[j] += colc[cbase + j];
+          } else if (st.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const int c = n0 + cbase + j; v[j] += (c < N) ? st.bias[c] : 0.f; }
           }
           __syncwarp();   // the previous tile's readers are done with the staging
           float4* dst = reinterpret_cast<float4*>(stg + lane * kStgLd);
@@ -651,89 +872,129 @@ __global__ void __launch_bounds__(kSlabThreads, 2) slab_kernel(const __grid_cons
           for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           __syncwarp();
         }
+        if (threadIdx.x == 64) SLAB_STAMP(9);
+        float* const out_p = st.out;
+        __nv_bfloat16* const twin_p = st.twin;
+        const int ld_out = st.ld_out, ld_twin = st.ld_twin;
         const bool full4 = (col + 3 < N);
         float pg[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f}, pd[4] = {0.f, 0.f, 0.f, 0.f};
         float mv0 = 0.f, mv1 = 0.f, mv2 = 0.f;
-        float g[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
-        if (is_norm) {
+        if (epi == EPI_FWD_NORM) {
+          float g[4], be[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { g[j] = st.gamma[col + j]; if (st.norm == NORM_LAYER) be[j] = st.beta[col + j]; }
-        }
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
-          const int r = rg + 4 * i;
-          const int row = m0 + lane_base + r;
-          if (row >= M || col >= N) continue;
-          const float4 x4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);
-          const float x[4] = {x4.x, x4.y, x4.z, x4.w};
-          if (epi == EPI_FWD_NORM) {
-            *reinterpret_cast<float4*>(st.out + static_cast<size_t>(row) * st.ld_out + col) = x4;
+          for (int j = 0; j < 4; ++j) { g[j] = colc[64 + cbase + cl + j]; be[j] = colc[128 + cbase + cl + j]; }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rg + 4 * i, row = m0 + lane_base + r;
+            const float4 x4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);
             const float rr = rowa[r], mm = rowb[r];
-            float y[4];
+            const float y0 = fswish((x4.x - mm) * rr * g[0] + be[0]), y1 = fswish((x4.y - mm) * rr * g[1] + be[1]);
+            const float y2 = fswish((x4.z - mm) * rr * g[2] + be[2]), y3 = fswish((x4.w - mm) * rr * g[3] + be[3]);
+            if (row < M) {
+              *reinterpret_cast<float4*>(out_p + static_cast<size_t>(row) * ld_out + col) = x4;
+              store_bf16x4(twin_p + static_cast<size_t>(row) * ld_twin + col, y0, y1, y2, y3);
+            }
+          }
+        } else if (epi == EPI_FWD_ACT) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) y[j] = swishf_((x[j] - mm) * rr * g[j] + be[j]);
-            store_bf16x4(st.twin + static_cast<size_t>(row) * st.ld_twin + col, y[0], y[1], y[2], y[3]);
-          } else if (epi == EPI_FWD_ACT) {
-            *reinterpret_cast<float4*>(st.out + static_cast<size_t>(row) * st.ld_out + col) = x4;
-            store_bf16x4(st.twin + static_cast<size_t>(row) * st.ld_twin + col, swishf_(x[0]), swishf_(x[1]), swishf_(x[2]), swishf_(x[3]));
-          } else if (epi == EPI_FWD_OUT || epi == EPI_BWD_OUT) {
-            float* o = st.out + static_cast<size_t>(row) * st.ld_out + col;
+          for (int i = 0; i < 8; ++i) {
+            const int r = rg + 4 * i, row = m0 + lane_base + r;
+            const float4 x4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);
+            const float y0 = fswish(x4.x), y1 = fswish(x4.y), y2 = fswish(x4.z), y3 = fswish(x4.w);
+            if (row < M && col < N) {
+              *reinterpret_cast<float4*>(out_p + static_cast<size_t>(row) * ld_out + col) = x4;
+              store_bf16x4(twin_p + static_cast<size_t>(row) * ld_twin + col, y0, y1, y2, y3);
+            }
+          }
+        } else if (epi == EPI_FWD_OUT || epi == EPI_BWD_OUT) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (col + j < N) o[j] = x[j];
-          } else if (epi == EPI_FWD_AUX) {
-            const SlabRowArgs& a = prog.r;
-            const long long src = a.idx ? a.idx[row] : row;
-            const float mask = a.no_mask ? 1.f : 1.f - a.truncated[src];
-            const float nd = a.mask_done ? 1.f - a.done[src] : 1.f;
-            const float gg = 2.f * mask * nd * a.aux_mult * a.inv_rows / static_cast<float>(a.P);
-            const int off = a.reward_head ? 1 : 0;
+          for (int i = 0; i < 8; ++i) {
+            const int r = rg + 4 * i, row = m0 + lane_base + r;
+            const float4 x4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);
+            const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+            float* o = out_p + static_cast<size_t>(row) * ld_out + col;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (row < M && col + j < N) o[j] = x[j];
+          }
+        } else if (epi == EPI_FWD_AUX) {
+          const SlabRowArgs& a = rargs;
+          const int off = a.reward_head ? 1 : 0;
+          const float inv_P = 1.f / static_cast<float>(a.P);
+          const float gscale = 2.f * a.aux_mult * a.inv_rows * inv_P;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rg + 4 * i, row = m0 + lane_base + r;
+            const bool okr = row < M && col < N;
+            const float4 x4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);
+            const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+            float mask = prow[i], nd = prow2[i];
+            float tg[4] = {pre[i].x, pre[i].y, pre[i].z, pre[i].w};
+            if (t > 0 && okr) {   // extra tiles (P > 64 * cluster size: the reward column of a full-width head): loaded here
+              const size_t sr = static_cast<size_t>(a.idx ? a.idx[row] : row);
+              mask = a.no_mask ? 1.f : 1.f - a.truncated[sr];
+              nd = a.mask_done ? 1.f - a.done[sr] : 1.f;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int cc = col + j;
+                tg[j] = (cc < N) ? ((a.reward_head && cc == 0) ? a.reward[sr] : a.next_emb[sr * a.H + (cc - off)]) : 0.f;
+              }
+            }
+            const float gg = gscale * mask * nd;
             float sq = 0.f, dp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int c = col + j;
-              if (c < N) {
-                float tgt;
-                if (a.reward_head && c == 0) { tgt = a.reward[src]; mv2 += tgt * a.inv_rows; }
-                else tgt = a.next_emb[static_cast<size_t>(src) * a.H + (c - off)];
-                const float d = x[j] - tgt;
+              if (okr && col + j < N) {
+                if (a.reward_head && col + j == 0) mv2 += tg[j] * a.inv_rows;
+                const float d = x[j] - tg[j];
                 sq += d * d;
                 dp[j] = gg * d;
                 pd[j] += dp[j];
               }
             }
-            __nv_bfloat16* tw = st.twin + static_cast<size_t>(row) * st.ld_twin + col;
-            if (full4) store_bf16x4(tw, dp[0], dp[1], dp[2], dp[3]);
-            else
+            __nv_bfloat16* tw = twin_p + static_cast<size_t>(row) * ld_twin + col;
+            if (okr) {
+              if (full4) store_bf16x4(tw, dp[0], dp[1], dp[2], dp[3]);
+              else
 #pragma unroll
-              for (int j = 0; j < 4; ++j) if (col + j < N) tw[j] = __float2bfloat16_rn(dp[j]);
-            const float aux = nd * sq / static_cast<float>(a.P);
+                for (int j = 0; j < 4; ++j) if (col + j < N) tw[j] = __float2bfloat16_rn(dp[j]);
+            }
+            const float aux = nd * sq * inv_P;
             mv0 += mask * a.aux_mult * aux * a.inv_rows;
             mv1 += (a.reward_head ? aux : mask * aux) * a.inv_rows;
-          } else if (epi == EPI_BWD_NORM) {
-            const float4 z4 = *reinterpret_cast<const float4*>(st.out + static_cast<size_t>(row) * st.ld_out + col);
-            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-            const float rstd = st.rstd[row];
-            const float mean = (st.norm == NORM_LAYER) ? st.mean[row] : 0.f;
-            const float S1 = rowa[r], S2 = rowb[r];
+          }
+        } else if (epi == EPI_BWD_NORM) {
+          float g[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) g[j] = colc[64 + cbase + cl + j];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rg + 4 * i, row = m0 + lane_base + r;
+            const float4 y4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);    // dy (0 for rows past the end)
+            const float4 h4 = *reinterpret_cast<const float4*>(stg2 + r * kStgLd + cl);   // zh
+            const float dy[4] = {y4.x, y4.y, y4.z, y4.w}, zh[4] = {h4.x, h4.y, h4.z, h4.w};
+            const float rstd = prow[i], S1 = rowa[r], S2 = rowb[r];
             float dz[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float zh = (zz[j] - mean) * rstd;
-              dz[j] = rstd * (x[j] * g[j] - S1 - zh * S2);   // x = dy
-              pg[j] += x[j] * zh;
-              pb[j] += x[j];
+              dz[j] = rstd * (dy[j] * g[j] - S1 - zh[j] * S2);
+              pg[j] += dy[j] * zh[j];
+              pb[j] += dy[j];
               pd[j] += dz[j];
             }
-            store_bf16x4(st.twin + static_cast<size_t>(row) * st.ld_twin + col, dz[0], dz[1], dz[2], dz[3]);
-          } else {   // EPI_BWD_ACT
-            const float4 z4 = *reinterpret_cast<const float4*>(st.out + static_cast<size_t>(row) * st.ld_out + col);
-            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-            float dz[4];
+            if (row < M) store_bf16x4(twin_p + static_cast<size_t>(row) * ld_twin + col, dz[0], dz[1], dz[2], dz[3]);
+          }
+        } else {   // EPI_BWD_ACT
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { dz[j] = x[j] * swish_grad_(zz[j]); pd[j] += dz[j]; }
-            store_bf16x4(st.twin + static_cast<size_t>(row) * st.ld_twin + col, dz[0], dz[1], dz[2], dz[3]);
+          for (int i = 0; i < 8; ++i) {
+            const int r = rg + 4 * i, row = m0 + lane_base + r;
+            const float4 x4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);   // 0 for rows past the end
+            const float dz0 = x4.x * fswish_grad(pre[i].x), dz1 = x4.y * fswish_grad(pre[i].y);
+            const float dz2 = x4.z * fswish_grad(pre[i].z), dz3 = x4.w * fswish_grad(pre[i].w);
+            pd[0] += dz0; pd[1] += dz1; pd[2] += dz2; pd[3] += dz3;
+            if (row < M && col < N) store_bf16x4(twin_p + static_cast<size_t>(row) * ld_twin + col, dz0, dz1, dz2, dz3);
           }
         }
+        if (threadIdx.x == 64) SLAB_STAMP(10);
         // ---- column sums (bias / gamma / beta gradients) and metric partials of this tile ----
         const bool need_g = (epi == EPI_BWD_NORM && st.g_gamma != nullptr);
         const bool need_b = (epi == EPI_BWD_NORM && st.norm == NORM_LAYER && st.g_beta != nullptr);
@@ -776,14 +1037,15 @@ __global__ void __launch_bounds__(kSlabThreads, 2) slab_kernel(const __grid_cons
           } else if (te == 64 && epi == EPI_FWD_AUX) {
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
             for (int w = 0; w < 8; ++w) { a0 += metpart[w * 4 + 0]; a1 += metpart[w * 4 + 1]; a2 += metpart[w * 4 + 2]; }
-            atomicAdd(prog.r.metrics + M_CRITIC_LOSS, a0);
-            atomicAdd(prog.r.metrics + M_AUX_MEAN, a1);
-            if (a2 != 0.f) atomicAdd(prog.r.metrics + M_REWARD_MEAN, a2);
+            atomicAdd(rargs.metrics + M_CRITIC_LOSS, a0);
+            atomicAdd(rargs.metrics + M_AUX_MEAN, a1);
+            if (a2 != 0.f) atomicAdd(rargs.metrics + M_REWARD_MEAN, a2);
           }
           epi_bar();
         }
       }
       tc_fence_before();
+      if (threadIdx.x == 64) SLAB_STAMP(7);
     }
     it += static_cast<uint32_t>(my_tiles * nkb);
     if (my_tiles > 0 && epi != EPI_NONE) ++tf;
@@ -792,6 +1054,7 @@ __global__ void __launch_bounds__(kSlabThreads, 2) slab_kernel(const __grid_cons
   tc_fence_before();
   __syncwarp();
   cluster_sync_all();
+  if (timed && threadIdx.x == 64) timing[num_steps] = clock64();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();

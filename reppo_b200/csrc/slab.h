@@ -34,24 +34,27 @@ constexpr int kSlabMaxSteps = 28;
 constexpr int kSlabStages = 4;
 constexpr int kSlabThreads = 320;
 
-struct alignas(64) SlabStep {
-  CUtensorMap ta, tb;        // A: bf16 [rows, K] (box 64 x 128); B: weights, K-major [N, K] or MN-major [K, N] (box 64 x 64)
+// everything about a step except its two tensor maps (the kernel keeps a shared-memory copy of these)
+struct SlabStepInfo {
   int kind, epi, row;
   int K, N, b_mn, accumulate;
   int norm;                  // NORM_RMS | NORM_LAYER for the *_NORM epilogues
   float eps;
+  int ld_out, ld_twin;
   const float* bias;
   const float* gamma;
   const float* beta;
   float* out;                // fp32 output [rows, ld_out]; for the BWD epilogues: the saved forward z (input)
-  int ld_out;
   float* rstd;               // FWD_NORM: out; BWD_NORM: in
   float* mean;
   __nv_bfloat16* twin;       // bf16 output [rows, ld_twin]
-  int ld_twin;
   float* g_gamma;            // gradient accumulators (column sums, atomics into the zeroed arena); nullable
   float* g_beta;
   float* g_bias;
+};
+struct alignas(64) SlabStep {
+  CUtensorMap ta, tb;        // A: bf16 [rows, K] (box 64 x 128); B: weights, K-major [N, K] or MN-major [K, N] (box 64 x 64)
+  SlabStepInfo f;
 };
 
 struct SlabRowArgs {
@@ -92,6 +95,7 @@ struct SlabProgram {
   int num_steps;
   int rows;        // minibatch rows
   int tmem_cols;   // power of two >= 64 * (largest number of tiles one CTA owns in a step)
+  long long* timing;   // optional [num_steps + 1] clock64() stamps of CTA (0,0) (REPPO_SLAB_TIMING=1; profiling aid)
   SlabRowArgs r;
   SlabStep steps[kSlabMaxSteps];
 };

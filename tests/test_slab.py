@@ -1,5 +1,5 @@
 """Slab programs (reppo_b200/csrc/slab.cu: a whole critic / actor chain of a step in one persistent cluster kernel)
-against (a) the same engine with REPPO_NO_SLAB=1 (separate tcgen05 GEMM + row kernels, identical bf16 operand rounding)
+(opt-in: REPPO_SLAB=1 at context creation) against (a) the default engine (separate tcgen05 GEMM + row kernels, identical bf16 operand rounding)
 and (b) the fp32 CPU oracle's autograd gradients.
 
 Tolerances.  (a) both paths round the same operands to bf16 and accumulate in fp32, so they differ only by fp32
@@ -33,13 +33,13 @@ CASES = [(O.JAX, MID), (O.TORCH, MID), (O.JAX, MIXED), (O.TORCH, dict(MIXED, nor
 
 def _make(hp, sem, slab):
     if slab:
-        os.environ.pop("REPPO_NO_SLAB", None)
+        os.environ["REPPO_SLAB"] = "1"
     else:
-        os.environ["REPPO_NO_SLAB"] = "1"
+        os.environ.pop("REPPO_SLAB", None)
     try:
         return _engine(hp, sem, gemm_mode="bf16")
     finally:
-        os.environ.pop("REPPO_NO_SLAB", None)
+        os.environ.pop("REPPO_SLAB", None)
 
 
 @pytest.mark.parametrize("sem,kw", CASES)
