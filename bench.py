@@ -247,8 +247,8 @@ def main():
     eng = ts.engine
     eng.load_params(cp, ap_)
     if world > 1:
-        from reppo_b200 import dist as D
-        D.attach_nccl(eng, rank, world)   # two communicators: critic chain + actor chain
+        from reppo_b200 import dist as dp_plumbing
+        dp_plumbing.attach_nccl(eng, rank, world)   # two communicators: critic chain + actor chain
     hyp = HyperParams(gamma=h.gamma, lmbda=h.lmbda, lr=h.lr, max_grad_norm=h.max_grad_norm, kl_bound=h.kl_bound,
                       ent_target_mult=h.ent_target_mult, aux_loss_mult=h.aux_loss_mult, actor_min_std=h.actor_min_std,
                       actor_kl_clip_mode=h.actor_kl_clip_mode, world_size=world)

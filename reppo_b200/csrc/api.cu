@@ -415,9 +415,21 @@ int ensure_streams(reppo_ctx* c) {
 // last_bias_done: the producer of d_out already accumulated the last layer's bias gradient (column sums of d_out).
 // The dgrad / norm-backward chain runs on `st`; every weight-gradient GEMM only depends on one link of the chain and
 // runs on `wst` (the caller joins `wst` before the optimizer).
+// Optional fusion of the MLP's input gradient with the swish backward that follows it:
+//   dz = (d_in [+ addend]) * swish'(z) -> bf16 twin of `dz`, column sums -> g_bias  (one tcgen05 kernel instead of a
+//   dgrad GEMM + a row kernel).  join_from: stream that produces `addend` (joined right before the fused launch).
+struct FusedIn {
+  const float* z = nullptr;
+  const float* addend = nullptr;
+  const float* dz = nullptr;
+  float* g_bias = nullptr;
+  cudaStream_t join_from = nullptr;
+  bool done = false;
+};
+
 int mlp_backward(reppo_ctx* c, const Mlp& m, const float* params, int slot, float* grads, const float* in, int rows,
                  const Acts& a, const float* d_out, float* dx_in, int dx_mode, float* bias2, float scale2, bool last_bias_done,
-                 cudaStream_t st, cudaStream_t wst) {
+                 cudaStream_t st, cudaStream_t wst, FusedIn* fin = nullptr) {
   const int n = static_cast<int>(m.layers.size());
   const float* d = d_out;
   for (int i = n - 1; i >= 0; --i) {
@@ -431,15 +443,35 @@ int mlp_backward(reppo_ctx* c, const Mlp& m, const float* params, int slot, floa
     }
     if (i > 0) {
       const Linear& Lp = m.layers[i - 1];
-      RET(linear_dgrad(c, L, params, slot, d, rows, a.tmp, GEMM_STORE, st));
       float* dz = a.dz[i - 1];
       const Twin tw = c->twin(dz);
+      if (c->tc) {
+        // dgrad + norm / swish backward (+ d gamma, d beta, d bias column sums) in ONE tcgen05 kernel
+        const Twin td = c->twin(d);
+        const cudaError_t e = launch_gemm_bf16_tc_bwd(
+            m.norm, rows, L.in, L.out, td.p, td.ld, c->shadow_b[slot] + L.sb, L.ld_b, a.z[i - 1], a.rstd[i - 1], a.mean[i - 1],
+            Lp.g >= 0 ? params + Lp.g : nullptr, Lp.beta >= 0 ? params + Lp.beta : nullptr, nullptr, tw.p, tw.ld,
+            (grads && Lp.g >= 0) ? grads + Lp.g : nullptr, (grads && Lp.beta >= 0) ? grads + Lp.beta : nullptr,
+            grads ? grads + Lp.b : nullptr, st);
+        if (e == cudaSuccess) { ++c->launches; d = dz; continue; }
+        if (e != cudaErrorNotSupported) return fail(c, REPPO_ERR_CUDA, std::string("launch_gemm_bf16_tc_bwd: ") + cudaGetErrorString(e));
+      }
+      RET(linear_dgrad(c, L, params, slot, d, rows, a.tmp, GEMM_STORE, st));
       CK(launch_norm_act_bwd(m.norm, a.tmp, nullptr, a.z[i - 1], Lp.g >= 0 ? params + Lp.g : nullptr,
                              Lp.beta >= 0 ? params + Lp.beta : nullptr, a.rstd[i - 1], a.mean[i - 1], rows, L.in,
                              c->tc ? nullptr : dz, (grads && Lp.g >= 0) ? grads + Lp.g : nullptr,
                              (grads && Lp.beta >= 0) ? grads + Lp.beta : nullptr, grads ? grads + Lp.b : nullptr, tw.p, tw.ld, st));
       d = dz;
     } else if (dx_in != nullptr) {
+      if (fin != nullptr && c->tc) {
+        if (fin->join_from != nullptr) RET(dep(c, fin->join_from, st));
+        const Twin td = c->twin(d), tz = c->twin(fin->dz);
+        const cudaError_t e = launch_gemm_bf16_tc_bwd(NORM_NONE, rows, L.in, L.out, td.p, td.ld, c->shadow_b[slot] + L.sb, L.ld_b,
+                                                      fin->z, nullptr, nullptr, nullptr, nullptr, fin->addend, tz.p, tz.ld, nullptr,
+                                                      nullptr, fin->g_bias, st);
+        if (e == cudaSuccess) { ++c->launches; fin->done = true; continue; }
+        if (e != cudaErrorNotSupported) return fail(c, REPPO_ERR_CUDA, std::string("launch_gemm_bf16_tc_bwd: ") + cudaGetErrorString(e));
+      }
       RET(linear_dgrad(c, L, params, slot, d, rows, dx_in, dx_mode, st));
     }
   }
@@ -698,12 +730,17 @@ int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
   tw = c->twin(c->dlogits);
   CK(launch_critic_ce(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, b->target, b->truncated, idx, mb, inv, no_mask,
                       c->dlogits, metrics, tw.p, tw.ld, cg + c->head.layers.back().b, cg + c->zero_dist_off, st));
-  RET(mlp_backward(c, c->head, cp, cslot, cg, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, true, st, sw));
-  RET(dep(c, s1, st));
-  // d feat = (d swish(feat) from both heads) * swish'(feat); its column sums are the bias gradient of the encoder's last Linear
-  tw = c->twin(c->dfeat);
-  CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->dxs2, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, Hc,
-                         c->tc ? nullptr : c->dfeat, nullptr, nullptr, cg + c->feature.layers.back().b, tw.p, tw.ld, st));
+  // d feat = (d swish(feat) from both heads) * swish'(feat); its column sums are the bias gradient of the encoder's last
+  // Linear.  Tensor-core mode: fused into the head's last dgrad (the pred branch's contribution enters as an addend).
+  FusedIn fin;
+  fin.z = c->fa.out; fin.addend = c->dxs2; fin.dz = c->dfeat; fin.g_bias = cg + c->feature.layers.back().b; fin.join_from = s1;
+  RET(mlp_backward(c, c->head, cp, cslot, cg, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, true, st, sw, &fin));
+  if (!fin.done) {
+    RET(dep(c, s1, st));
+    tw = c->twin(c->dfeat);
+    CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->dxs2, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, Hc,
+                           c->tc ? nullptr : c->dfeat, nullptr, nullptr, cg + c->feature.layers.back().b, tw.p, tw.ld, st));
+  }
   RET(mlp_backward(c, c->feature, cp, cslot, cg, c->x0, mb, c->fa, c->dfeat, nullptr, GEMM_STORE, nullptr, 0.f, true, st, sw));
   RET(dep(c, sw, st));
   return REPPO_OK;
@@ -817,10 +854,14 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
   tw = c->twin(tb.dlogits);
   CK(launch_actor_q(tb.ha->out, sh.num_bins, cp + c->zero_dist_off, c->hl, c->kl, mb, inv, ac.kl_mode, ac.kl_bound, c->q,
                     tb.dlogits, tw.p, tw.ld, st));
-  RET(mlp_backward(c, c->head, cp, cslot, nullptr, tb.xs, mb, *tb.ha, tb.dlogits, tb.dxs, GEMM_STORE, nullptr, 0.f, false, st, st));
-  tw = c->twin(tb.dfeat);
-  CK(launch_norm_act_bwd(NORM_NONE, tb.dxs, nullptr, tb.fa->out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden,
-                         c->tc ? nullptr : tb.dfeat, nullptr, nullptr, nullptr, tw.p, tw.ld, st));
+  FusedIn fin;
+  fin.z = tb.fa->out; fin.dz = tb.dfeat;
+  RET(mlp_backward(c, c->head, cp, cslot, nullptr, tb.xs, mb, *tb.ha, tb.dlogits, tb.dxs, GEMM_STORE, nullptr, 0.f, false, st, st, &fin));
+  if (!fin.done) {
+    tw = c->twin(tb.dfeat);
+    CK(launch_norm_act_bwd(NORM_NONE, tb.dxs, nullptr, tb.fa->out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden,
+                           c->tc ? nullptr : tb.dfeat, nullptr, nullptr, nullptr, tw.p, tw.ld, st));
+  }
   RET(mlp_backward(c, c->feature, cp, cslot, nullptr, c->x0a, mb, *tb.fa, tb.dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, false, st, st));
   // last read of the critic snapshot: the critic chain may overwrite it from here on
   if (critic_read_done != nullptr && cudaEventRecord(critic_read_done, st) != cudaSuccess)

@@ -54,6 +54,12 @@ cudaError_t launch_gemm_bf16_tc(bool a_mn, bool b_mn, int M, int N, int K, const
 struct NormArgs { const float* gamma; const float* beta; float eps; float* rstd_out; float* mean_out; };
 cudaError_t launch_gemm_bf16_tc_norm(int norm, int M, int N, int K, const void* A, int lda, const void* B, int ldb, float* C,
                                      int ldc, const float* bias, void* act_out, int act_ld, const NormArgs& na, cudaStream_t st);
+// dgrad with the backward of [norm -> swish] (or plain swish: norm == NORM_NONE, optional fp32 addend) fused into the
+// epilogue (gemm_bf16_tc_bwd.cu); cudaErrorNotSupported = shape not eligible
+cudaError_t launch_gemm_bf16_tc_bwd(int norm, int M, int N, int K, const void* dy, int lda, const void* W, int ldw, const float* z,
+                                    const float* rstd, const float* mean, const float* gamma, const float* beta,
+                                    const float* addend, void* dz_twin, int ld_twin, float* g_gamma, float* g_beta, float* g_bias,
+                                    cudaStream_t st);
 // fp32 -> bf16 copies: plain (row-padded) and, for weights, the [out,in] matrix plus its transpose
 struct PackEntry { const float* w; void* wb; void* wtb; int out, in, ld_b, ld_t; };
 constexpr int kMaxPack = 16;

@@ -1,0 +1,126 @@
+// tcgen05 / TMA / mbarrier / cluster PTX wrappers shared by the cluster kernels (slab.cu, gemm_bf16_tc_bwd.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace reppo {
+namespace tcx {
+
+constexpr int SB_M = 128, SB_N = 64, SB_K = 64, SB_UMMA_K = 16;
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------
+REPPO_DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+REPPO_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+REPPO_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+REPPO_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "SLAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra SLAB_DONE;\n\t"
+      "bra SLAB_WAIT;\n\t"
+      "SLAB_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+REPPO_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+REPPO_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+REPPO_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+REPPO_DEVINL void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+REPPO_DEVINL void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+REPPO_DEVINL void tc_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// shared-memory matrix descriptor: SWIZZLE_128B, sm_100 descriptor version
+REPPO_DEVINL uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// bf16 x bf16 -> f32, M = 128, N = 64, A K-major, B K-major or MN-major
+REPPO_DEVINL uint32_t make_idesc(bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(SB_N >> 3) << 17) | (static_cast<uint32_t>(SB_M >> 4) << 24);
+}
+REPPO_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Between two steps: every global-memory result of the previous step (written through the generic proxy by any
+// CTA of the cluster) becomes visible to the next step's TMA loads (async proxy) and plain loads.
+REPPO_DEVINL void handoff_sync() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();
+  tc_fence_after();
+}
+REPPO_DEVINL float ld_dsmem_f32(const float* local_smem_ptr, uint32_t cta_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(cta_rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+REPPO_DEVINL void st_dsmem_f32(float* local_smem_ptr, uint32_t cta_rank, float v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(cta_rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+REPPO_DEVINL void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+
+// The slab path computes in bf16-operand precision anyway: the activation math of its epilogues uses the SFU
+// approximations (ex2.approx / rcp.approx, ~2 ulp) -- the exact expf / IEEE division made the epilogues issue-bound.
+REPPO_DEVINL float fsigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-fmaxf(x, -80.f))); }
+REPPO_DEVINL float fswish(float x) { return x * fsigmoid(x); }
+REPPO_DEVINL float fswish_grad(float x) {
+  const float s = fsigmoid(x);
+  return s * (1.f + x * (1.f - s));
+}
+
+REPPO_DEVINL void store_bf16x4(__nv_bfloat16* p, float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&lo);
+  u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+
+}  // namespace tcx
+}  // namespace reppo

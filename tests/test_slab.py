@@ -88,6 +88,44 @@ def test_slab_matches_kernel_chain_and_oracle(sem, kw):
             assert _cos(ga1[k], gref) >= 0.998, k
 
 
+@pytest.mark.parametrize("sem,kw", [(O.JAX, MID), (O.JAX, MIXED), (O.TORCH, dict(MID, use_critic_norm=False, use_actor_norm=False))])
+def test_fused_dgrad_norm_backward_matches_kernel_chain(sem, kw):
+    """REPPO_FUSE_BWD=1: dgrad + norm / swish backward in one tcgen05 cluster kernel (gemm_bf16_tc_bwd.cu) against the
+    default dgrad GEMM + row kernel pair."""
+    hp = O.Hyper(**kw)
+    cp, ap, ap_old, flat, eps_pi, eps_kl, perms = _setup(hp, sem)
+    hyp = _hyper(hp)
+    idx = perms[0, :hp.minibatch_size]
+    out = {}
+    for fused in (True, False):
+        if fused:
+            os.environ["REPPO_FUSE_BWD"] = "1"
+        eng = _engine(hp, sem, gemm_mode="bf16")
+        eng.load_params(cp, ap)
+        for k in eng.actor.layout:
+            eng.actor.view(eng.actor_old, k).copy_(ap_old[k])
+        batch = eng.make_batch(flat)
+        eng.critic_grad(batch, idx, hyp)
+        gc = {k: eng.critic.view(eng.critic.grads, k).detach().cpu().clone() for k in eng.critic.layout}
+        eng.actor_grad(batch, idx, eps_pi[0], eps_kl[0], hyp)
+        ga = {k: eng.actor.view(eng.actor.grads, k).detach().cpu().clone() for k in eng.actor.layout}
+        launches = eng.launch_count()
+        torch.cuda.synchronize()
+        out[fused] = (gc, ga, launches)
+        os.environ.pop("REPPO_FUSE_BWD", None)
+    assert out[True][2] < out[False][2], "the fused path must launch fewer kernels"
+    for name, i in (("critic", 0), ("actor", 1)):
+        for k in out[True][i]:
+            _grad_close(f"{name}.{k} (fused vs chain)", out[True][i][k], out[False][i][k], rel=1e-2)
+    mb = O.take(flat, idx)
+    _, _, gref_c = O._value_and_grad(lambda p: O.critic_loss(p, mb, hp, sem), cp)
+    _, _, gref_a = O._value_and_grad(lambda p: O.actor_loss(p, ap_old, cp, mb, eps_pi[0], eps_kl[0], hp, sem), ap)
+    for k, g in gref_c.items():
+        _grad_close(f"critic.{k}", out[True][0][k], g, rel=4e-2)
+    for k, g in gref_a.items():
+        _grad_close(f"actor.{k}", out[True][1][k], g, rel=8e-2)
+
+
 def test_slab_full_update_pipeline():
     """Whole update (graph, two-chain pipeline) with slab programs against the kernel chain: same losses step by step."""
     hp = O.Hyper(**dict(MID, num_epochs=2))
