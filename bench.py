@@ -50,6 +50,16 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def load_traffic():
+    """dram bytes per launch of the dominant kernel family from the newest committed `ncu --set full` capture."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    return d.get("dram_bytes_per_launch_mean"), os.path.basename(files[-1])
+
+
 def make_cfg(name, semantics):
     from reppo_b200.config import compose
     env, ov, D, A, term, rs, extra = CONFIGS[name]
@@ -397,9 +407,12 @@ def main():
     n_steps = E * n_mb
     peak_tf = peaks["bf16_tflops_sustained"]
     achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    traffic, traffic_src = load_traffic()
     roofline = {
         "bound": "tensor", "kernel": "gemm_f32_kernel (fp32 FFMA)" if args.gemm == "fp32" else "gemm_bf16_tc_kernel (tcgen05)",
-        "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+        "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
+        "traffic_note": f"mean dram__bytes_read+write per GEMM launch inside the update, profiles/{traffic_src} (operands are "
+                        "L2-resident: below the algorithmic 2.5-8.5 MB per launch)" if traffic is not None else None,
         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
         "method": "every distinct Linear GEMM of one critic+actor minibatch step timed alone: 50 back-to-back launches "
                   "replayed as a CUDA graph between CUDA events, weighted by its launches per step",
