@@ -292,8 +292,11 @@ actor_q_kernel(const float* __restrict__ head_out, int ld, const float* __restri
   if (lane == 0) q_out[row] = sx.value;
 }
 
-// d loss / d (mu, log_std) per row, scalar gradients for log_temp / log_lagrange, metrics
-__global__ void __launch_bounds__(128)
+// d loss / d (mu, log_std) per row, scalar gradients for log_temp / log_lagrange, metrics.
+// One warp per row (lane k owns action dimension k, +32 ...): 2048 rows give 2048 warps instead of 16 blocks of
+// row-serial threads; metric partials and the bias-gradient column sums meet per block in shared memory.
+constexpr int kGradMaxA = 64;   // action_dim <= 64 on this path
+__global__ void __launch_bounds__(256)
 actor_grad_kernel(const float* __restrict__ out, const float* __restrict__ eps_pi, const float* __restrict__ act, int act_ld,
                   const float* __restrict__ dact, int dact_ld, const float* __restrict__ logp_in,
                   const float* __restrict__ kl_in, const float* __restrict__ q_in, const float* __restrict__ gmu_kl,
@@ -301,25 +304,26 @@ actor_grad_kernel(const float* __restrict__ out, const float* __restrict__ eps_p
                   ActorConsts ac, float* __restrict__ dout, float* __restrict__ actor_grads, float* __restrict__ metrics,
                   __nv_bfloat16* __restrict__ dout_h, int ldh, float* __restrict__ dbias) {
   REPPO_PDL_PROLOGUE();
-  __shared__ float red[32];
-  __shared__ float scol[64];  // column sums of dout = bias gradient of the policy's last Linear (2A <= 64)
-  if (threadIdx.x < 64) scol[threadIdx.x] = 0.f;
-  __syncthreads();
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float scol[8][2 * kGradMaxA];
+  __shared__ float smet[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 8 + warp;
   const float alpha = expf(actor_params[0]), beta = expf(actor_params[1]);
-  float v_path = 0.f, v_kl = 0.f, v_ent = 0.f, v_q = 0.f, v_abs = 0.f, v_ent_t = 0.f;
+  float m[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j = lane; j < 2 * A; j += 32) scol[warp][j] = 0.f;
+  __syncwarp();
   if (row < rows) {
     const float logp = logp_in[row], kl = kl_in[row], q = q_in[row];
     float w_path, w_kl;
     if (ac.kl_mode == KL_CLIPPED) { w_path = kl < ac.kl_bound ? 1.f : 0.f; w_kl = 1.f - w_path; }
     else if (ac.kl_mode == KL_FULL) { w_path = 1.f; w_kl = 1.f; }
     else { w_path = 1.f; w_kl = 0.f; }
-    const float g_logp = inv_rows * w_path * alpha;           // d L / d logp   (alpha is stop-gradient here)
+    const float g_logp = inv_rows * w_path * alpha;                // d L / d logp   (alpha is stop-gradient here)
     const float g_lpnew = -inv_rows * w_kl * beta * ac.reduce_kl;  // d L / d lp_new = - d L / d kl
     const float* o = out + static_cast<size_t>(row) * 2 * A;
     float* d = dout + static_cast<size_t>(row) * 2 * A;
     float abs_a = 0.f;
-    for (int k = 0; k < A; ++k) {
+    for (int k = lane; k < A; k += 32) {
       const float mu = o[k], ex = expf(o[A + k]), sig = ex + ac.min_std;
       const float e = eps_pi[static_cast<size_t>(row) * A + k];
       const float a = act[static_cast<size_t>(row) * act_ld + k];
@@ -336,32 +340,46 @@ actor_grad_kernel(const float* __restrict__ out, const float* __restrict__ eps_p
         dlp_sig = (zz * zz - 1.f) / sig;
       }
       const float dmu = da + g_logp * dlp_mu + g_lpnew * gmu_kl[static_cast<size_t>(row) * A + k];
-      const float dsig = da * e + g_logp * dlp_sig + g_lpnew * gsig_kl[static_cast<size_t>(row) * A + k];
+      const float dls = (da * e + g_logp * dlp_sig + g_lpnew * gsig_kl[static_cast<size_t>(row) * A + k]) * ex;
       d[k] = dmu;
-      d[A + k] = dsig * ex;
-
+      d[A + k] = dls;
       if (dout_h != nullptr) {
         dout_h[static_cast<size_t>(row) * ldh + k] = __float2bfloat16_rn(dmu);
-        dout_h[static_cast<size_t>(row) * ldh + A + k] = __float2bfloat16_rn(dsig * ex);
+        dout_h[static_cast<size_t>(row) * ldh + A + k] = __float2bfloat16_rn(dls);
       }
+      scol[warp][k] = dmu;
+      scol[warp][A + k] = dls;
       abs_a += fabsf(a);
     }
-    v_path = w_path * (alpha * logp - q) + w_kl * beta * ac.reduce_kl * kl;
-    v_kl = kl;
-    v_ent = -logp;
-    v_q = q;
-    v_abs = abs_a / static_cast<float>(A);
-    v_ent_t = ac.target_entropy - logp;
+    abs_a = warp_sum(abs_a);
+    m[0] = w_path * (alpha * logp - q) + w_kl * beta * ac.reduce_kl * kl;
+    m[1] = kl;
+    m[2] = -logp;
+    m[3] = q;
+    m[4] = abs_a / static_cast<float>(A);
+    m[5] = ac.target_entropy - logp;
+    m[6] = 1.f;
   }
-  const float s_path = block_sum(v_path, red) * inv_rows;
-  const float s_kl = block_sum(v_kl, red) * inv_rows;
-  const float s_ent = block_sum(v_ent, red) * inv_rows;
-  const float s_q = block_sum(v_q, red) * inv_rows;
-  const float s_abs = block_sum(v_abs, red) * inv_rows;
-  const float s_ent_t = block_sum(v_ent_t, red) * inv_rows;
+  if (lane == 0)
+#pragma unroll
+    for (int j = 0; j < 7; ++j) smet[warp][j] = m[j];
+  __syncthreads();
+  if (dbias != nullptr) {
+    for (int j = threadIdx.x; j < 2 * A; j += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += scol[w][j];
+      atomicAdd(dbias + j, t);
+    }
+  }
   if (threadIdx.x == 0) {
+    float v[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int w = 0; w < 8; ++w)
+#pragma unroll
+      for (int j = 0; j < 7; ++j) v[j] += smet[w][j];
+    const float s_path = v[0] * inv_rows, s_kl = v[1] * inv_rows, s_ent = v[2] * inv_rows, s_q = v[3] * inv_rows;
+    const float s_abs = v[4] * inv_rows, s_ent_t = v[5] * inv_rows, frac = v[6] * inv_rows;
     // entropy_loss = alpha * mean(sg(target_entropy - logp)); lagrangian_loss = -beta * mean(sg(kl - bound))
-    const float frac = static_cast<float>(min(rows - static_cast<int>(blockIdx.x * blockDim.x), static_cast<int>(blockDim.x))) * inv_rows;
     const float ent_loss = alpha * s_ent_t;
     const float lag_loss = -beta * (s_kl - ac.kl_bound * frac);
     float total = s_path;
@@ -376,16 +394,6 @@ actor_grad_kernel(const float* __restrict__ out, const float* __restrict__ eps_p
     atomicAdd(metrics + M_ACTOR_Q_MEAN, s_q);
     atomicAdd(metrics + M_ABS_PRED_ACTION, s_abs);
     if (blockIdx.x == 0) { metrics[M_TEMPERATURE] = alpha; metrics[M_LAGRANGIAN] = beta; }
-  }
-  if (dbias != nullptr) {
-    // column sums of dout: warp shuffle per column, one shared atomic per warp, one global atomic per block
-    float* d = dout + static_cast<size_t>(row) * 2 * A;
-    for (int j = 0; j < 2 * A; ++j) {
-      const float v = warp_sum(row < rows ? d[j] : 0.f);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&scol[j], v);
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 * A) atomicAdd(dbias + threadIdx.x, scol[threadIdx.x]);
   }
 }
 
@@ -438,8 +446,8 @@ cudaError_t launch_actor_grad(const float* out, const float* eps_pi, const float
                               const float* gsig, const float* actor_params, int rows, int A, float inv_rows,
                               const ActorConsts& ac, float* dout, float* actor_grads, float* metrics, void* dout_h, int ldh,
                               float* dbias, cudaStream_t st) {
-  if (dbias != nullptr && 2 * A > 64) return cudaErrorInvalidValue;
-  launch_k((actor_grad_kernel), dim3((rows + 127) / 128), dim3(128), 0, st, out, eps_pi, act, act_ld, dact, dact_ld, logp, kl, q, gmu, gsig, actor_params, rows, A, inv_rows, ac, dout, actor_grads, metrics, static_cast<__nv_bfloat16*>(dout_h), ldh, dbias);
+  if (A > kGradMaxA) return cudaErrorInvalidValue;
+  launch_k((actor_grad_kernel), dim3((rows + 7) / 8), dim3(256), 0, st, out, eps_pi, act, act_ld, dact, dact_ld, logp, kl, q, gmu, gsig, actor_params, rows, A, inv_rows, ac, dout, actor_grads, metrics, static_cast<__nv_bfloat16*>(dout_h), ldh, dbias);
   return cudaGetLastError();
 }
 
