@@ -114,7 +114,10 @@ struct TcSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kStatOffset = kBarOffset + (2 * STAGES + 1) * 8 + 16;      // fused-norm row statistics
-  static constexpr int kStatBytes = (4 * 128 + 2 * 128 + 2 * 8 * 32) * 4;          // part[2][2][128], cta_stat[2][128], rs/mu[8][32]
+  // part[2][2][128], cta_stat[2][128] (unused), rs/mu[8][32], colc[3][BLOCK_N], allstat[8][2][128]
+  static constexpr int kColcOffsetF = 4 * 128 + 2 * 128 + 2 * 8 * 32;
+  static constexpr int kAllStatOffsetF = kColcOffsetF + 3 * BLOCK_N;
+  static constexpr int kStatBytes = (kAllStatOffsetF + 8 * 2 * 128) * 4;
   static constexpr int kTotal = kStatOffset + kStatBytes + 1024;                   // + alignment slack
 };
 
@@ -122,6 +125,12 @@ REPPO_DEVINL void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+REPPO_DEVINL void st_dsmem_f32(float* local_smem_ptr, uint32_t cta_rank, float v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(cta_rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+REPPO_DEVINL float fast_swish(float x) { return x * __fdividef(1.f, 1.f + __expf(-fmaxf(x, -80.f))); }
 REPPO_DEVINL float ld_dsmem_f32(const float* local_smem_ptr, uint32_t cta_rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(cta_rank));
@@ -225,6 +234,28 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====
     // 8 warps: warp w may only touch TMEM lanes 32*(w%4)..+32, so two warps share each lane quarter and split the
     // tile's columns between them (the epilogue, not the MMA, bounds these short-K GEMMs).
+    float4 bias_pre = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (NORM == NORM_NONE) {
+      // this thread's 4 bias values of the coalesced store layout, requested while the MMAs run
+      if (bias != nullptr && blockIdx.z == 0) {
+        const int colp = n0 + ((warp - 2) >> 2) * (BLOCK_N / 2) + (lane % (BLOCK_N / 8)) * 4;
+        if (colp + 0 < N) bias_pre.x = bias[colp + 0];
+        if (colp + 1 < N) bias_pre.y = bias[colp + 1];
+        if (colp + 2 < N) bias_pre.z = bias[colp + 2];
+        if (colp + 3 < N) bias_pre.w = bias[colp + 3];
+      }
+    }
+    if constexpr (NORM != NORM_NONE) {
+      // per-column constants are fetched while the MMAs run: after the cluster barrier below L1 is cold and every
+      // global load would be an L2 round trip on the critical path
+      float* colc = reinterpret_cast<float*>(smem + S::kStatOffset) + S::kColcOffsetF;
+      for (int t = (warp - 2) * 32 + lane; t < BLOCK_N; t += 256) {
+        colc[t] = bias[n0 + t];
+        colc[BLOCK_N + t] = na.gamma[n0 + t];
+        colc[2 * BLOCK_N + t] = (NORM == NORM_LAYER) ? na.beta[n0 + t] : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     // all TMA loads were consumed by MMAs that have retired: the pipeline stages are free to reuse
@@ -249,7 +280,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // bias first: the statistics are those of z = x W^T + b
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          v[j] += bias[n0 + cbase + c0 + j];
+          v[j] += (reinterpret_cast<const float*>(smem + S::kStatOffset) + S::kColcOffsetF)[cbase + c0 + j];
           s1 += v[j];
           s2 += v[j] * v[j];
         }
@@ -260,14 +291,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     if constexpr (NORM != NORM_NONE) {
       float* part = reinterpret_cast<float*>(smem + S::kStatOffset);        // [2 stats][2 halves][128 rows]
-      float* cta_stat = part + 4 * 128;                                      // [2 stats][128 rows]
       const int rrow = lane_base + lane, half = ew >> 2;
       part[(0 * 2 + half) * 128 + rrow] = s1;
       part[(1 * 2 + half) * 128 + rrow] = s2;
       asm volatile("bar.sync 1, 256;" ::: "memory");                       // the 8 epilogue warps
       if (half == 0) {
-        cta_stat[rrow] = part[0 * 128 + rrow] + part[1 * 128 + rrow];
-        cta_stat[128 + rrow] = part[2 * 128 + rrow] + part[3 * 128 + rrow];
+        // push this CTA's per-row partial statistics into every peer of the cluster (remote stores; published by the
+        // cluster barrier) instead of pulling 2 x cluster-size remote values per thread after it
+        const float u1 = part[0 * 128 + rrow] + part[1 * 128 + rrow];
+        const float u2 = part[2 * 128 + rrow] + part[3 * 128 + rrow];
+        float* allstat = part + S::kAllStatOffsetF;
+        const uint32_t ncl = gridDim.x, me = blockIdx.x;
+        for (uint32_t r = 0; r < ncl; ++r) {
+          st_dsmem_f32(allstat + (me * 2 + 0) * 128 + rrow, r, u1);
+          st_dsmem_f32(allstat + (me * 2 + 1) * 128 + rrow, r, u2);
+        }
       }
     }
     __syncwarp();
@@ -280,13 +318,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       constexpr int kRowsPerIter = 32 / kLanesPerRow;    // 2 or 4
       const int cl = (lane % kLanesPerRow) * 4;
       const int col = n0 + cbase + cl;
-      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (add_bias) {
-        if (col + 0 < N) bv.x = bias[col + 0];
-        if (col + 1 < N) bv.y = bias[col + 1];
-        if (col + 2 < N) bv.z = bias[col + 2];
-        if (col + 3 < N) bv.w = bias[col + 3];
-      }
+      const float4 bv = bias_pre;   // zero when there is no bias / not the first K split
 #pragma unroll 4
       for (int r = lane / kLanesPerRow; r < 32; r += kRowsPerIter) {
         const int row = m0 + lane_base + r;
@@ -301,7 +333,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           *reinterpret_cast<float4*>(cp) = x;
           if (act_out != nullptr) {   // fused epilogue: swish(y) as the bf16 operand of the next GEMM
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(swishf_(x.x), swishf_(x.y)), hi = __floats2bfloat162_rn(swishf_(x.z), swishf_(x.w));
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(fast_swish(x.x), fast_swish(x.y)), hi = __floats2bfloat162_rn(fast_swish(x.z), fast_swish(x.w));
             uint2 u;
             u.x = *reinterpret_cast<const uint32_t*>(&lo);
             u.y = *reinterpret_cast<const uint32_t*>(&hi);
@@ -350,12 +382,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const float* stg = reinterpret_cast<const float*>(smem) + ew * 32 * kStgLd;
       const int lane_base = (warp & 3) * 32, cbase = (ew >> 2) * kCols, rrow = lane_base + lane;
       float* part = reinterpret_cast<float*>(smem + S::kStatOffset);
-      const float* cta_stat = part + 4 * 128;
       float* rs = part + 6 * 128 + ew * 32;          // per-warp copies of the row statistics
       float* mu = part + 6 * 128 + 8 * 32 + ew * 32;
       float t1 = 0.f, t2 = 0.f;
       const uint32_t ncta = gridDim.x;                // cluster spans the whole row
-      for (uint32_t r = 0; r < ncta; ++r) { t1 += ld_dsmem_f32(cta_stat + rrow, r); t2 += ld_dsmem_f32(cta_stat + 128 + rrow, r); }
+      const float* allstat = part + S::kAllStatOffsetF;
+#pragma unroll
+      for (uint32_t r = 0; r < 8; ++r)
+        if (r < ncta) { t1 += allstat[(r * 2 + 0) * 128 + rrow]; t2 += allstat[(r * 2 + 1) * 128 + rrow]; }
       const float inv_n = 1.f / static_cast<float>(N);
       float mean = 0.f, rstd;
       if (NORM == NORM_RMS) {
@@ -375,7 +409,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int col = n0 + cbase + cl;
       float g[4], be[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { g[j] = na.gamma[col + j]; if (NORM == NORM_LAYER) be[j] = na.beta[col + j]; }
+      for (int j = 0; j < 4; ++j) {
+        const float* colc = part + S::kColcOffsetF;
+        g[j] = colc[BLOCK_N + cbase + cl + j];
+        be[j] = colc[2 * BLOCK_N + cbase + cl + j];
+      }
 #pragma unroll 4
       for (int r = lane / kLanesPerRow; r < 32; r += kRowsPerIter) {
         const int row = m0 + lane_base + r;
@@ -383,8 +421,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const float4 x = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);   // z (bias included)
         *reinterpret_cast<float4*>(C + static_cast<size_t>(row) * ldc + col) = x;
         const float rr = rs[r], mm = mu[r];
-        const float y0 = swishf_((x.x - mm) * rr * g[0] + be[0]), y1 = swishf_((x.y - mm) * rr * g[1] + be[1]);
-        const float y2 = swishf_((x.z - mm) * rr * g[2] + be[2]), y3 = swishf_((x.w - mm) * rr * g[3] + be[3]);
+        // bf16-operand mode: SFU sigmoid (ex2.approx / rcp.approx); the exact expf + IEEE division made this loop issue-bound
+        const float y0 = fast_swish((x.x - mm) * rr * g[0] + be[0]), y1 = fast_swish((x.y - mm) * rr * g[1] + be[1]);
+        const float y2 = fast_swish((x.z - mm) * rr * g[2] + be[2]), y3 = fast_swish((x.w - mm) * rr * g[3] + be[3]);
         const __nv_bfloat162 lo = __floats2bfloat162_rn(y0, y1), hi = __floats2bfloat162_rn(y2, y3);
         uint2 u;
         u.x = *reinterpret_cast<const uint32_t*>(&lo);
@@ -392,8 +431,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         *reinterpret_cast<uint2*>(act_out + static_cast<size_t>(row) * act_ld + col) = u;
       }
     }
-    // ---- nobody leaves (and frees its shared memory) while a peer may still read it ----
-    cluster_sync_all();
+    // (no second cluster barrier: peers only WRITE into this CTA's shared memory, and only before the barrier above)
   }
   __syncthreads();
   if (warp == 0) {
