@@ -178,6 +178,28 @@ int reppo_critic_forward(reppo_ctx* ctx, const float* critic_params, const float
 int reppo_actor_forward(reppo_ctx* ctx, const float* actor_params, const float* obs, int32_t rows, float min_std,
                         float* mean, float* std, reppo_stream stream);
 
+/* ---- rollout side: what the collection loop runs per environment step --------
+ * EmpiricalNormalization, src/torchrl/reppo_util.py:394-471: when update != 0 the running mean / var / std [dim] and the
+ * int64 device counter are first merged with the batch (Chan's parallel algorithm, :432-466; skipped once
+ * count >= until when until >= 0), then out = (x - mean) / (std + eps) (center != 0) or x / (std + eps).  No ctx needed. */
+int reppo_obs_normalize(const float* x, int64_t rows, int32_t dim, float* mean, float* var, float* std, int64_t* count, float eps,
+                        int32_t update, int32_t center, int64_t until, float* out, reppo_stream stream);
+/* Policy step of collect_fn (src/torchrl/reppo.py:104-109,146) / step_env (src/jaxrl/reppo.py:347-364): actor MLP forward,
+ * action = tanh(mu + std * scale * eps) with injected standard normals eps [rows, A] and an optional per-row exploration scale
+ * (jax_models.py:362-367), log_prob [rows] of the action clipped to +-clip under the UNscaled policy and (optional)
+ * log_prob_scaled under the scaled one; clip <= 0: distrax sample_and_log_prob (log-prob at the pre-tanh sample).
+ * store_clipped != 0 writes the clipped action (src/jaxrl/reppo.py:357). */
+int reppo_policy_act(reppo_ctx* ctx, const float* actor_params, const float* obs, const float* eps, const float* scale, int32_t rows,
+                     float min_std, float clip, int32_t store_clipped, float* action, float* log_prob, float* log_prob_scaled,
+                     reppo_stream stream);
+/* Bootstrap half of the same step (src/torchrl/reppo.py:117-138; src/jaxrl/reppo.py:367-374): next action + log-prob from the
+ * policy at next_obs, Critic.forward(next_critic_obs, next_action) -> next_value [rows], next_emb [rows, H] (= features),
+ * soft_reward = reward - gamma * log_prob * exp(log_temp).  Output pointers may be NULL. */
+int reppo_bootstrap(reppo_ctx* ctx, const float* actor_params, const float* critic_params, const float* next_obs,
+                    const float* next_critic_obs, const float* eps, const float* reward, int32_t rows, float gamma, float min_std,
+                    float clip, float* next_value, float* next_emb, float* soft_reward, float* next_action, float* next_log_prob,
+                    reppo_stream stream);
+
 /* One Linear layer of FCNN (src/networks/torch_models.py:71-79, jax_models.py:35-49) in isolation -- the
  * GEMM family the MLP forward / backward is built from; used by the kernel tests and bench.py's roofline leg.
  *   op 0  forward : y[rows,out]  = x[rows,in] w[out,in]^T + bias   (bias may be NULL)

@@ -101,6 +101,49 @@ def gen_subfunctions(ref):
     print("hl_gauss goldens written")
 
 
+
+def gen_rollout(ref):
+    """Rollout-side goldens from the reference modules: the policy / bootstrap arithmetic of collect_fn
+    (src/torchrl/reppo.py:100-158) with injected noise, and EmpiricalNormalization (reppo_util.py:394-471)."""
+    kwargs = CASES["torch_small"][0]
+    hp = O.Hyper(**kwargs)
+    cp, ap = O.init_params(hp, O.TORCH, seed=0)
+    ts0 = RB.build_train_state(ref, hp, cp, ap)
+    g = torch.Generator().manual_seed(5)
+    n = 96
+    obs = torch.randn(n, hp.obs_dim, generator=g)
+    nobs = torch.randn(n, hp.obs_dim, generator=g)
+    ncobs = torch.randn(n, hp.critic_obs_dim, generator=g)
+    eps, eps2 = torch.randn(n, hp.action_dim, generator=g), torch.randn(n, hp.action_dim, generator=g) * 1.5
+    reward = torch.rand(n, generator=g)
+    with torch.no_grad():
+        pi, _, _, _ = ts0.actor(obs)
+        a = torch.tanh(pi.base_dist.loc + pi.base_dist.scale * eps)                 # pi.sample() with the noise injected
+        lp = pi.log_prob(a.clip(-0.999, 0.999)).sum(-1)                              # :146
+        npi, _, temp, _ = ts0.actor(nobs)
+        na = torch.tanh(npi.base_dist.loc + npi.base_dist.scale * eps2)
+        nlp = npi.log_prob(na.clip(-1 + 1e-6, 1 - 1e-6)).sum(-1)                     # :132-134
+        nv, _, _, nemb = ts0.critic(ncobs, na)                                       # :135
+        soft = reward - hp.gamma * nlp * temp                                        # :136-138
+    out = {"hyper": kwargs, "obs": obs, "next_obs": nobs, "next_critic_obs": ncobs, "eps": eps, "eps_next": eps2, "reward": reward,
+           "action": a, "log_prob": lp, "next_action": na, "next_log_prob": nlp, "next_value": nv, "next_emb": nemb,
+           "soft_reward": soft}
+    # normaliser: three training-mode calls, then one eval call
+    norm = ref.util.EmpiricalNormalization(shape=7, device="cpu")
+    xs = [torch.randn(33, 7, generator=g) * 3 + 1, torch.randn(64, 7, generator=g) * 0.5 - 2, torch.randn(5, 7, generator=g)]
+    ys, states = [], []
+    norm.train()
+    for x in xs:
+        ys.append(norm(x).clone())
+        states.append({"mean": norm._mean.clone(), "var": norm._var.clone(), "std": norm._std.clone(), "count": int(norm.count)})
+    norm.eval()
+    ys.append(norm(xs[0]).clone())
+    out["norm"] = {"xs": xs, "ys": ys, "states": states, "keys": list(norm.state_dict().keys())}
+    out["state_dict_keys"] = {"actor": list(ts0.actor.state_dict().keys()), "critic": list(ts0.critic.state_dict().keys())}
+    torch.save(out, os.path.join(OUT, "torch_rollout.pt"))
+    print(f"rollout goldens written: logp[0]={lp[0].item():.6f} next_value[0]={nv[0].item():.6f}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -109,6 +152,7 @@ def main():
     for name, (kw, term, full) in CASES.items():
         gen_case(ref, name, kw, term, full)
     gen_subfunctions(ref)
+    gen_rollout(ref)
 
 
 if __name__ == "__main__":

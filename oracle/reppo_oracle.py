@@ -374,6 +374,68 @@ def _normal_logpdf(x, mu, std):
     return -0.5 * ((x - mu) / std) ** 2 - torch.log(std) - HALF_LOG_2PI
 
 
+
+# ----------------------------------------------------------------------------------------
+# rollout side: policy step, bootstrap, observation normalisation
+# ----------------------------------------------------------------------------------------
+def policy_act(pa, obs, eps, hp: Hyper, sem: Semantics, clip: float, scale: Optional[Tensor] = None):
+    """collect_fn src/torchrl/reppo.py:104-109,146 / step_env src/jaxrl/reppo.py:347-364.
+    Returns (action, log_prob of the clipped action under the unscaled policy, the same under the scaled policy);
+    clip <= 0: distrax ``sample_and_log_prob`` (log-prob at the pre-tanh sample, src/jaxrl/reppo.py:367-369)."""
+    mu, std = actor_forward(pa, obs, hp, sem)
+    s = std if scale is None else std * scale.reshape(-1, 1)   # jax_models.py:366
+    x = mu + s * eps
+    a = torch.tanh(x)
+    if clip > 0:
+        u = torch.atanh(a.clip(-clip, clip))
+        lp = (_normal_logpdf(u, mu, std) - _fldj(u)).sum(-1)
+        lps = (_normal_logpdf(u, mu, s) - _fldj(u)).sum(-1)
+    else:
+        lp = lps = (_normal_logpdf(x, mu, s) - _fldj(x)).sum(-1)
+    return a, lp, lps
+
+
+def bootstrap(pa, pc, next_obs, next_critic_obs, eps, reward, hp: Hyper, sem: Semantics, clip: float):
+    """src/torchrl/reppo.py:117-138 (clip 1 - 1e-6) / src/jaxrl/reppo.py:367-374 (clip <= 0)."""
+    a, lp, _ = policy_act(pa, next_obs, eps, hp, sem, clip)
+    value, _, _, feat = critic_forward(pc, next_critic_obs, a, hp, sem)
+    soft = reward - hp.gamma * lp * torch.exp(pa["log_temp"])
+    return {"next_value": value, "next_emb": feat, "soft_reward": soft, "next_action": a, "next_log_prob": lp}
+
+
+class EmpiricalNormalization:
+    """Restatement of src/torchrl/reppo_util.py:394-471 (running mean / var by Chan's parallel algorithm)."""
+
+    def __init__(self, dim: int, eps: float = 1e-2, until: Optional[int] = None, dtype=torch.float32):
+        self.eps, self.until = eps, until
+        self.mean = torch.zeros(1, dim, dtype=dtype)
+        self.var = torch.ones(1, dim, dtype=dtype)
+        self.std = torch.ones(1, dim, dtype=dtype)
+        self.count = 0
+
+    def update(self, x: Tensor):
+        x = x.reshape(-1, x.shape[-1])
+        if self.until is not None and self.count >= self.until:
+            return
+        b = x.shape[0]
+        bm = x.mean(0, keepdim=True)
+        new = self.count + b
+        self.mean = self.mean + (b / new) * (bm - self.mean)                      # :446-447
+        if self.count > 0:
+            bv = ((x - bm) ** 2).mean(0, keepdim=True)                             # :452
+            d2 = bm - self.mean                                                    # the UPDATED mean (:453)
+            m2 = self.var * self.count + bv * b + d2 ** 2 * (self.count * b / new)
+            self.var = m2 / new
+        else:
+            self.var = ((x - self.mean) ** 2).mean(0, keepdim=True)                # :461-462
+        self.std = torch.sqrt(self.var)
+        self.count = new
+
+    def __call__(self, x: Tensor, update: bool = True, center: bool = True) -> Tensor:
+        if update:
+            self.update(x)
+        return (x - self.mean) / (self.std + self.eps) if center else x / (self.std + self.eps)
+
 # ----------------------------------------------------------------------------------------
 # A.3 critic loss
 # ----------------------------------------------------------------------------------------

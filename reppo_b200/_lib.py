@@ -81,6 +81,9 @@ SYMBOLS = {
     "reppo_td_lambda": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _d, _d, _i32, _i32, _vp]),
     "reppo_critic_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "reppo_actor_forward": (C.c_int, [_vp, _vp, _vp, _i32, _f, _vp, _vp, _vp]),
+    "reppo_obs_normalize": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _f, _i32, _i32, _i64, _vp, _vp]),
+    "reppo_policy_act": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _f, _f, _i32, _vp, _vp, _vp, _vp]),
+    "reppo_bootstrap": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "reppo_linear": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "reppo_critic_step": (C.c_int, [_vp, C.POINTER(State), C.POINTER(Batch), _vp, _i32, C.POINTER(Hyper), _vp, _vp]),
     "reppo_actor_step": (C.c_int, [_vp, C.POINTER(State), C.POINTER(Batch), _vp, _i32, _vp, _vp, C.POINTER(Hyper), _vp, _vp]),

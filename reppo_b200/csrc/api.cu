@@ -1222,6 +1222,68 @@ int reppo_linear(reppo_ctx* c, int32_t op, int32_t rows, int32_t in_f, int32_t o
   return REPPO_OK;
 }
 
+
+// ---- rollout side -----------------------------------------------------------------------------
+int reppo_obs_normalize(const float* x, int64_t rows, int32_t dim, float* mean, float* var, float* std, int64_t* count, float eps,
+                        int32_t update, int32_t center, int64_t until, float* out, reppo_stream stream) {
+  if (!x || !mean || !var || !std || !out || rows <= 0 || dim <= 0 || (update && !count)) return REPPO_ERR_INVALID;
+  const cudaError_t e = launch_obs_normalize(x, rows, dim, mean, var, std, reinterpret_cast<long long*>(count), eps, update, center,
+                                             until, out, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) { g_create_error = std::string("obs_normalize: ") + cudaGetErrorString(e); return REPPO_ERR_CUDA; }
+  return REPPO_OK;
+}
+
+static int policy_act_impl(reppo_ctx* c, const float* ap, const float* obs, const float* eps, const float* scale, int rows,
+                           float min_std, float clip, int store_clipped, float* action, int act_ld, void* act_h, int act_ldh,
+                           float* logp, float* logp_scaled, cudaStream_t st) {
+  RET(pack_shadows(c, SLOT_ACTOR, ap, st));
+  const Twin tw = c->twin(c->xa0);
+  CK(launch_gather_concat(obs, c->shape.obs_dim, nullptr, 0, nullptr, 0, rows, c->xa0, c->shape.obs_dim, tw.p, tw.ld, st));
+  RET(mlp_forward(c, c->actor, ap, SLOT_ACTOR, c->xa0, rows, c->aa, st));
+  const float ms = c->sem.force_min_std >= 0.f ? c->sem.force_min_std : min_std;
+  CK(launch_policy_sample(c->aa.out, eps, scale, rows, c->shape.action_dim, ms, clip, store_clipped, action, act_ld, act_h, act_ldh,
+                          logp, logp_scaled, st));
+  return REPPO_OK;
+}
+
+int reppo_policy_act(reppo_ctx* c, const float* actor_params, const float* obs, const float* eps, const float* scale, int32_t rows,
+                     float min_std, float clip, int32_t store_clipped, float* action, float* log_prob, float* log_prob_scaled,
+                     reppo_stream stream) {
+  if (!actor_params || !obs || !eps || !action) return fail(c, REPPO_ERR_INVALID, "reppo_policy_act: null argument");
+  RET(check_rows(c, rows));
+  c->launches = 0;
+  return policy_act_impl(c, actor_params, obs, eps, scale, rows, min_std, clip, store_clipped, action, c->shape.action_dim, nullptr, 0,
+                         log_prob, log_prob_scaled, static_cast<cudaStream_t>(stream));
+}
+
+int reppo_bootstrap(reppo_ctx* c, const float* actor_params, const float* critic_params, const float* next_obs,
+                    const float* next_critic_obs, const float* eps, const float* reward, int32_t rows, float gamma, float min_std,
+                    float clip, float* next_value, float* next_emb, float* soft_reward, float* next_action, float* next_log_prob,
+                    reppo_stream stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!actor_params || !critic_params || !next_obs || !next_critic_obs || !eps)
+    return fail(c, REPPO_ERR_INVALID, "reppo_bootstrap: null argument");
+  if (soft_reward != nullptr && reward == nullptr) return fail(c, REPPO_ERR_INVALID, "reppo_bootstrap: soft_reward needs reward");
+  RET(check_rows(c, rows));
+  c->launches = 0;
+  const reppo_shape& sh = c->shape;
+  const int Dc = sh.critic_obs_dim, A = sh.action_dim;
+  // critic input [next_critic_obs | next_action]: the observation part is gathered, the sampled action lands beside it
+  const Twin tx = c->twin(c->x0);
+  CK(launch_gather_concat(next_critic_obs, Dc, nullptr, 0, nullptr, 0, rows, c->x0, c->K0, tx.p, tx.ld, st));
+  RET(policy_act_impl(c, actor_params, next_obs, eps, nullptr, rows, min_std, clip, 0, c->x0 + Dc, c->K0,
+                      tx.p ? tx.p + Dc : nullptr, tx.ld, c->logp, nullptr, st));
+  RET(pack_shadows(c, SLOT_CRITIC, critic_params, st));
+  RET(critic_trunk(c, critic_params, SLOT_CRITIC, c->x0, rows, false, trunk_main(c), st));
+  if (next_value) CK(launch_value_head(c->ha.out, sh.num_bins, critic_params + c->zero_dist_off, c->hl, rows, next_value, nullptr, st));
+  if (next_emb) CK(cudaMemcpyAsync(next_emb, c->fa.out, sizeof(float) * rows * sh.critic_hidden, cudaMemcpyDeviceToDevice, st));
+  if (soft_reward) CK(launch_soft_reward(reward, c->logp, actor_params, gamma, rows, soft_reward, st));
+  if (next_action) CK(cudaMemcpy2DAsync(next_action, sizeof(float) * A, c->x0 + Dc, sizeof(float) * c->K0, sizeof(float) * A, rows,
+                                        cudaMemcpyDeviceToDevice, st));
+  if (next_log_prob) CK(cudaMemcpyAsync(next_log_prob, c->logp, sizeof(float) * rows, cudaMemcpyDeviceToDevice, st));
+  return REPPO_OK;
+}
+
 int reppo_critic_grad(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int32_t mb,
                       const reppo_hyper* hp, float* metrics, reppo_stream stream) {
   c->launches = 0;

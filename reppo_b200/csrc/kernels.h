@@ -102,6 +102,15 @@ cudaError_t launch_value_head(const float* head_out, int ld, const float* zero_d
                               float* value, float* logits, cudaStream_t st);
 cudaError_t launch_mean_std(const float* out, int rows, int A, float min_std, float* mean, float* std, cudaStream_t st);
 
+// rollout side (rollout.cu)
+cudaError_t launch_policy_sample(const float* out, const float* eps, const float* scale, int rows, int A, float min_std, float clip,
+                                 int store_clipped, float* action, int act_ld, void* act_h, int act_ldh, float* logp,
+                                 float* logp_scaled, cudaStream_t st);
+cudaError_t launch_soft_reward(const float* reward, const float* logp, const float* log_temp, float gamma, int rows, float* out,
+                               cudaStream_t st);
+cudaError_t launch_obs_normalize(const float* x, long long rows, int D, float* mean, float* var, float* stdv, long long* count,
+                                 float eps, int update, int center, long long until, float* out, cudaStream_t st);
+
 // bf16 shadows of the weight matrices, refreshed by the Adam kernel itself (REPPO_GEMM_BF16)
 struct ShadowEntry { long long start, end; int in, ld; void* dst; };
 struct ShadowTable { int n; ShadowEntry e[kMaxPack]; };

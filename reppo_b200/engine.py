@@ -254,6 +254,40 @@ class ReppoEngine:
                                       bias.data_ptr() if bias is not None else None, self._stream()), self.ctx, "reppo_linear")
         return out
 
+    # ---- rollout side ------------------------------------------------------------
+    def policy_act(self, obs, eps, scale: Optional[torch.Tensor] = None, clip: float = 0.999, store_clipped: bool = False,
+                   min_std: float = 0.0, params: Optional[torch.Tensor] = None, want_scaled: bool = False):
+        """Policy step of the collection loop (src/torchrl/reppo.py:104-109,146; src/jaxrl/reppo.py:347-364):
+        action = tanh(mu + std * scale * eps), log-prob of the action clipped to +-clip (clip <= 0: at the pre-tanh
+        sample).  Returns (action [rows, A], log_prob [rows], log_prob under the scaled policy or None)."""
+        ob, e = self._f32(obs), self._f32(eps)
+        rows = ob.shape[0]
+        action = torch.empty(rows, self.cfg.action_dim, device=self.device)
+        logp = torch.empty(rows, device=self.device)
+        logps = torch.empty(rows, device=self.device) if (want_scaled or scale is not None) else None
+        sc = self._f32(scale).reshape(-1) if scale is not None else None
+        p = self.actor.params if params is None else params
+        L.check(self.lib.reppo_policy_act(self.ctx, p.data_ptr(), ob.data_ptr(), e.data_ptr(), sc.data_ptr() if sc is not None else None,
+                                          rows, float(min_std), float(clip), int(store_clipped), action.data_ptr(), logp.data_ptr(),
+                                          logps.data_ptr() if logps is not None else None, self._stream()),
+                self.ctx, "reppo_policy_act")
+        return action, logp, logps
+
+    def bootstrap(self, next_obs, next_critic_obs, eps, reward, gamma: float, clip: float = 1.0 - 1e-6, min_std: float = 0.0):
+        """Bootstrap half of the collection step (src/torchrl/reppo.py:117-138; src/jaxrl/reppo.py:367-374)."""
+        ob, co, e, r = self._f32(next_obs), self._f32(next_critic_obs), self._f32(eps), self._f32(reward).reshape(-1)
+        rows = ob.shape[0]
+        dev = self.device
+        out = {"next_value": torch.empty(rows, device=dev), "next_emb": torch.empty(rows, self.cfg.critic_hidden_dim, device=dev),
+               "soft_reward": torch.empty(rows, device=dev), "next_action": torch.empty(rows, self.cfg.action_dim, device=dev),
+               "next_log_prob": torch.empty(rows, device=dev)}
+        L.check(self.lib.reppo_bootstrap(self.ctx, self.actor.params.data_ptr(), self.critic.params.data_ptr(), ob.data_ptr(),
+                                         co.data_ptr(), e.data_ptr(), r.data_ptr(), rows, float(gamma), float(min_std), float(clip),
+                                         out["next_value"].data_ptr(), out["next_emb"].data_ptr(), out["soft_reward"].data_ptr(),
+                                         out["next_action"].data_ptr(), out["next_log_prob"].data_ptr(), self._stream()),
+                self.ctx, "reppo_bootstrap")
+        return out
+
     # ---- steps ------------------------------------------------------------------------------
     def _idx(self, idx):
         if isinstance(idx, int):  # identity gather over the first `idx` rows of the batch

@@ -18,7 +18,7 @@ hand-written CUDA kernels through the C ABI.  ``TensorDict`` is not installed he
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass
+from dataclasses import dataclass, replace
 from typing import Any, Dict, Mapping, Optional
 
 import torch
@@ -310,6 +310,137 @@ def _engine_for(cfg, train_state: TrainState) -> ReppoEngine:
         train_state.engine = bind_engine(train_state.actor, train_state.critic, train_state.old_actor, max_rows=mb,
                                          device=train_state.device)
     return train_state.engine
+
+
+# -------------------------------------------------------------------------------------------------
+# rollout side: observation normalisation, collection loop, checkpoints
+# -------------------------------------------------------------------------------------------------
+class EmpiricalNormalization(nn.Module):
+    """Drop-in for src/torchrl/reppo_util.py:394-471 (same constructor, buffers ``_mean/_var/_std/count`` and
+    ``state_dict`` keys); the Chan update and the normalisation run as two CUDA kernels (rollout.cu)."""
+
+    def __init__(self, shape, device, eps=1e-2, until=None):
+        super().__init__()
+        if not torch.cuda.is_available():
+            raise RuntimeError("reppo_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.eps, self.until = eps, until
+        self.device = torch.device(device)
+        shape = (shape,) if isinstance(shape, int) else tuple(shape)
+        self.register_buffer("_mean", torch.zeros(shape).unsqueeze(0).to(self.device))
+        self.register_buffer("_var", torch.ones(shape).unsqueeze(0).to(self.device))
+        self.register_buffer("_std", torch.ones(shape).unsqueeze(0).to(self.device))
+        self.register_buffer("count", torch.tensor(0, dtype=torch.long).to(self.device))
+        self._lib = L.load()
+
+    @property
+    def mean(self):
+        return self._mean.squeeze(0).clone()
+
+    @property
+    def std(self):
+        return self._std.squeeze(0).clone()
+
+    def forward(self, x: torch.Tensor, center: bool = True) -> torch.Tensor:
+        if x.shape[-1:] != self._mean.shape[-1:]:
+            raise ValueError(f"Expected input of shape (*,{self._mean.shape[-1:]}), got {x.shape}")
+        xf = x.to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty_like(xf)
+        dim = xf.shape[-1]
+        rows = xf.numel() // dim
+        L.check(self._lib.reppo_obs_normalize(
+            xf.data_ptr(), rows, dim, self._mean.data_ptr(), self._var.data_ptr(), self._std.data_ptr(), self.count.data_ptr(),
+            float(self.eps), int(self.training), int(center), -1 if self.until is None else int(self.until), out.data_ptr(),
+            torch.cuda.current_stream(self.device).cuda_stream), None, "reppo_obs_normalize")
+        return out
+
+    def update(self, x):
+        self.training, was = True, self.training
+        try:
+            self.forward(x)
+        finally:
+            self.training = was
+
+    def inverse(self, y):
+        return y * (self._std + self.eps) + self._mean
+
+
+def make_collect_fn(cfg, env, generator: Optional[torch.Generator] = None):
+    """Collection loop of src/torchrl/reppo.py:89-171 over the engine's rollout kernels: per environment step one
+    policy launch group (normalise -> actor -> sample + log-prob) and one bootstrap group (normalise -> actor -> next
+    action + log-prob -> critic -> next value / embedding -> soft reward).  ``env`` needs ``step(actions) -> (next_obs,
+    rewards, dones, truncations, infos)``, ``num_envs`` and ``asymmetric_obs`` like the reference's wrappers."""
+    h = cfg.hyperparameters
+    asymmetric_obs = getattr(env, "asymmetric_obs", False)
+
+    def collect_fn(train_state: TrainState):
+        eng = _engine_for(cfg, train_state)
+        dev = eng.device
+        transitions, info_list = [], []
+        obs, critic_obs = train_state.obs, train_state.critic_obs
+        A = eng.cfg.action_dim
+        for _ in range(int(h.num_steps)):
+            norm_obs = train_state.normalizer(obs)
+            norm_critic_obs = train_state.critic_normalizer(critic_obs)
+            eps = torch.randn(norm_obs.shape[0], A, device=dev, generator=generator)
+            actions, log_probs, _ = eng.policy_act(norm_obs, eps, clip=0.999, min_std=float(train_state.actor.min_std))
+            next_obs, rewards, dones, truncations, infos = env.step(actions)
+            next_critic_obs = infos["observations"]["critic"] if asymmetric_obs else next_obs
+            if cfg.env.get("has_final_obs", False) and cfg.env.get("partial_reset", False) and "final_observation" in infos:
+                _next_obs = infos["final_observation"]
+                _next_critic_obs = _next_obs
+            else:
+                _next_obs, _next_critic_obs = next_obs, next_critic_obs
+            eps2 = torch.randn(norm_obs.shape[0], A, device=dev, generator=generator)
+            b = eng.bootstrap(train_state.normalizer(_next_obs), train_state.critic_normalizer(_next_critic_obs), eps2, rewards,
+                              float(h.gamma), clip=1.0 - 1e-6, min_std=float(train_state.actor.min_std))
+            transitions.append({
+                "observations": norm_obs, "critic_observations": norm_critic_obs, "actions": actions, "log_probs": log_probs,
+                "rewards": b["soft_reward"].unsqueeze(-1), "raw_rewards": rewards.to(dev, torch.float32).reshape(-1, 1),
+                "next_embeddings": b["next_emb"], "next_values": b["next_value"].unsqueeze(-1),
+                "dones": dones.unsqueeze(-1).float(), "truncations": truncations.unsqueeze(-1).float()})
+            info_list.append(infos)
+            obs, critic_obs = next_obs, next_critic_obs
+        train_state = replace(train_state, obs=obs, critic_obs=critic_obs)
+        stacked = TensorBatch({k: torch.stack([t[k] for t in transitions], dim=0) for k in transitions[0]},
+                              batch_size=(int(h.num_steps), transitions[0]["actions"].shape[0]))
+        return train_state, stacked, info_list
+
+    return collect_fn
+
+
+def _cpu_state(sd):
+    return {k: v.detach().to("cpu", non_blocking=True) for k, v in sd.items()}
+
+
+def save_params(global_step, actor, qnet, qnet_target, obs_normalizer, critic_obs_normalizer, args, save_path):
+    """Checkpoint with the reference's layout and keys (src/torchrl/reppo_util.py:723-753): the façade modules'
+    ``state_dict()`` keys are the reference modules' keys, so the file loads into either implementation."""
+    import os
+    os.makedirs(os.path.dirname(save_path) or ".", exist_ok=True)
+    save_dict = {
+        "actor_state_dict": _cpu_state(actor.state_dict()),
+        "qnet_state_dict": _cpu_state(qnet.state_dict()),
+        "qnet_target_state_dict": _cpu_state(qnet_target.state_dict()) if qnet_target is not None else None,
+        "obs_normalizer_state": _cpu_state(obs_normalizer.state_dict()) if hasattr(obs_normalizer, "state_dict") else None,
+        "critic_obs_normalizer_state": (_cpu_state(critic_obs_normalizer.state_dict())
+                                        if hasattr(critic_obs_normalizer, "state_dict") else None),
+        "args": dict(vars(args)) if hasattr(args, "__dict__") else dict(args),
+        "global_step": global_step,
+    }
+    torch.save(save_dict, save_path, _use_new_zipfile_serialization=True)
+
+
+def load_params(path, actor, qnet, obs_normalizer=None, critic_obs_normalizer=None, old_actor=None):
+    """Inverse of ``save_params``: copies the tensors into the engine arenas through the façade modules."""
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    actor.load_state_dict(ck["actor_state_dict"])
+    qnet.load_state_dict(ck["qnet_state_dict"])
+    if old_actor is not None:
+        old_actor.load_state_dict(ck["actor_state_dict"])
+    for mod, key in ((obs_normalizer, "obs_normalizer_state"), (critic_obs_normalizer, "critic_obs_normalizer_state")):
+        if mod is not None and ck.get(key) and hasattr(mod, "load_state_dict") and len(ck[key]) > 0:
+            mod.load_state_dict(ck[key])
+    return ck.get("global_step", 0)
 
 
 # -------------------------------------------------------------------------------------------------
