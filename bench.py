@@ -444,6 +444,26 @@ def main():
     adam = {"kernel": "sumsq_partial_kernel + adam_kernel", "bound": "hbm (L2-resident at this size)",
             "achieved": 28.0 * eng.critic.count / (adam_ms * 1e-3) / 1e9, "unit": "GB/s", "ms": adam_ms, "params": eng.critic.count}
 
+    # rollout-side inference: one policy step + one bootstrap step over this GPU's environments
+    n_env = hp.num_envs
+    r_obs = torch.randn(n_env, D, device=dev)
+    r_eps = torch.randn(n_env, A, device=dev)
+    r_rew = torch.rand(n_env, device=dev)
+    def rollout_step():
+        eng.policy_act(r_obs, r_eps, clip=0.999, min_std=h.actor_min_std)
+        eng.bootstrap(r_obs, r_obs, r_eps, r_rew, h.gamma, clip=1.0 - 1e-6, min_std=h.actor_min_std)
+    rs_ms = time_fn(rollout_step, 50)
+    nrm = T.EmpiricalNormalization(D, device=dev)
+    big_obs = torch.randn(1 << 20, D, device=dev)
+    nrm.train()
+    nrm_ms = time_fn(lambda: nrm(big_obs), 20)
+    rollout = {"kernels": "policy_sample_kernel + MLP forwards + value_head_kernel + soft_reward_kernel", "envs": n_env,
+               "ms_per_env_step": rs_ms, "env_steps_per_s": n_env / (rs_ms * 1e-3),
+               "obs_normalize": {"rows": 1 << 20, "dim": D, "ms": nrm_ms, "bound": "hbm",
+                                 "achieved": (3 * 4.0 * (1 << 20) * D + 4.0 * (1 << 20) * D) / (nrm_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                 "algorithmic_bytes": "3 reads (mean pass, variance pass, apply) + 1 write of the batch"}}
+    del big_obs
+
     cpu = None
     if not args.no_cpu_baseline:
         cpu, _ = cpu_sample(hp, args.semantics, seconds=12.0)
@@ -455,7 +475,7 @@ def main():
         "config": workload_config(args.config, cfg, D, A, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_update * args.steps),
         "launches_per_update": int(launches_per_update), "cuda_graph": use_graph, "semantics": args.semantics,
-        "sample_visits_per_s": value * E, "roofline": roofline, "scan": scan, "adam": adam, "cpu_baseline": cpu,
+        "sample_visits_per_s": value * E, "roofline": roofline, "scan": scan, "adam": adam, "rollout": rollout, "cpu_baseline": cpu,
         "knobs": {k: os.environ[k] for k in os.environ if k.startswith("REPPO_")},
         "final_metrics": {k: final_metrics[k] for k in ("critic_loss", "actor_loss", "kl", "entropy")},
     }
