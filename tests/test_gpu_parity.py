@@ -457,3 +457,56 @@ def test_bf16_mode_full_update(use_graph):
     for k in cp:
         err = (eng.critic.view(eng.critic.params, k).cpu() - ts2.critic[k]).abs().max().item()
         assert err <= 2 * hp.lr * len(traces) + 1e-6, (k, err)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json's named configurations at their real layer shapes, reduced T x N:
+# gradients of one minibatch in both GEMM modes against the oracle's autograd.
+# ---------------------------------------------------------------------------------------------
+_RED = dict(num_steps=4, num_envs=64, num_mini_batches=2, num_epochs=1)
+NAMED = {
+    "C1_cartpole": dict(_RED, obs_dim=5, critic_obs_dim=5, action_dim=1, critic_hidden_dim=512, actor_hidden_dim=512,
+                        num_bins=151, vmin=0.0, vmax=150.0),
+    "C2_cheetah": dict(_RED, obs_dim=17, critic_obs_dim=17, action_dim=6, critic_hidden_dim=512, actor_hidden_dim=512,
+                       num_bins=151, vmin=0.0, vmax=150.0),
+    "C3_ant": dict(_RED, obs_dim=27, critic_obs_dim=27, action_dim=8, critic_hidden_dim=512, actor_hidden_dim=512,
+                   num_bins=151, vmin=0.0, vmax=150.0),
+    "C4_humanoid": dict(_RED, obs_dim=244, critic_obs_dim=244, action_dim=17, critic_hidden_dim=512, actor_hidden_dim=512,
+                        num_bins=151, vmin=0.0, vmax=200.0),
+    "C5_wide": dict(_RED, obs_dim=17, critic_obs_dim=17, action_dim=6, critic_hidden_dim=1024, actor_hidden_dim=1024,
+                    num_bins=151, vmin=0.0, vmax=150.0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(NAMED))
+@pytest.mark.parametrize("gemm_mode", ["fp32", "bf16"])
+def test_named_config_shapes(name, gemm_mode):
+    hp = O.Hyper(**NAMED[name])
+    sem = O.JAX
+    terminate = name in ("C3_ant", "C4_humanoid")
+    cp, ap, ap_old, flat, eps_pi, eps_kl, perms = _setup(hp, sem, terminate=terminate)
+    eng = _engine(hp, sem, gemm_mode=gemm_mode)
+    eng.load_params(cp, ap)
+    for k in eng.actor.layout:
+        eng.actor.view(eng.actor_old, k).copy_(ap_old[k])
+    hyp = _hyper(hp)
+    batch = eng.make_batch(flat)
+    idx = perms[0, :hp.minibatch_size]
+    mb = O.take(flat, idx)
+    rel_c, rel_a, cos_min, ltol = (2e-5, 5e-5, 0.999999, 5e-5) if gemm_mode == "fp32" else (4e-2, 8e-2, 0.998, 2e-2)
+    m = eng.metrics_dict(eng.critic_grad(batch, idx, hyp))
+    loss, _, grads = O._value_and_grad(lambda p: O.critic_loss(p, mb, hp, sem), cp)
+    assert math.isclose(m["critic_loss"], loss.item(), rel_tol=ltol, abs_tol=1e-6)
+    for k, gref in grads.items():
+        got = eng.critic.view(eng.critic.grads, k)
+        _grad_close(f"critic.{k}", got, gref, rel=rel_c)
+        if gref.numel() > 8:
+            assert _cos(got, gref) >= cos_min, k
+    m = eng.metrics_dict(eng.actor_grad(batch, idx, eps_pi[0], eps_kl[0], hyp))
+    loss, _, grads = O._value_and_grad(lambda p: O.actor_loss(p, ap_old, cp, mb, eps_pi[0], eps_kl[0], hp, sem), ap)
+    assert math.isclose(m["actor_loss"], loss.item(), rel_tol=max(ltol, 1e-4), abs_tol=2e-3 if gemm_mode == "bf16" else 2e-6)
+    for k, gref in grads.items():
+        got = eng.actor.view(eng.actor.grads, k)
+        _grad_close(f"actor.{k}", got, gref, rel=rel_a)
+        if gref.numel() > 8:
+            assert _cos(got, gref) >= cos_min, k
