@@ -110,6 +110,7 @@ struct reppo_ctx {
   float *logp = nullptr, *kl = nullptr, *q = nullptr, *gmu = nullptr, *gsig = nullptr, *scratch_metrics = nullptr;
   std::unordered_map<const float*, Twin> twins;
   uint16_t* shadow_b[NUM_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  uint16_t* shadow_t[NUM_SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // W^T of thin first layers
   // step pipelining: second copy of the critic parameters (Adam ping-pongs between the two), and a private set of
   // critic-trunk buffers for the actor step, so that critic step k+1 can overlap actor step k
   float* cp_alt = nullptr;
@@ -186,7 +187,9 @@ void add_fcnn(std::vector<TensorInfo>& ts, int64_t& off, int64_t& sb, int64_t& s
     }
     L.ld_b = round8(L.in); L.ld_t = round8(L.out);
     L.sb = sb; sb += static_cast<int64_t>(L.out) * L.ld_b; sb = (sb + 63) & ~static_cast<int64_t>(63);
-    L.st = st; st += static_cast<int64_t>(L.in) * L.ld_t; st = (st + 63) & ~static_cast<int64_t>(63);
+    // W^T shadow only for thin first layers (few input features): the SIMT first-layer kernel (thin.cu) reads it
+    if (i == 0 && layers >= 2 && L.in <= 64) { L.st = st; st += static_cast<int64_t>(L.in) * L.ld_t; st = (st + 63) & ~static_cast<int64_t>(63); }
+    else L.st = -1;
     mlp.layers.push_back(L);
   }
 }
@@ -267,6 +270,10 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
     c->shadow_b[SLOT_ACTOR] = Hf(c->shadow_b_elems[1]);
     c->shadow_b[SLOT_ACTOR_OLD] = Hf(c->shadow_b_elems[1]);
     c->shadow_b[SLOT_CRITIC_ALT] = Hf(c->shadow_b_elems[0]);
+    c->shadow_t[SLOT_CRITIC] = Hf(c->shadow_t_elems[0] + 64);
+    c->shadow_t[SLOT_CRITIC_ALT] = Hf(c->shadow_t_elems[0] + 64);
+    c->shadow_t[SLOT_ACTOR] = Hf(c->shadow_t_elems[1] + 64);
+    c->shadow_t[SLOT_ACTOR_OLD] = Hf(c->shadow_t_elems[1] + 64);
     const size_t md8 = round8(static_cast<int>(maxdim));
     c->lin_a = Hf(R * md8); c->lin_c = Hf(R * md8); c->lin_b = Hf(maxdim * md8);
   }
@@ -337,7 +344,7 @@ int pack_shadows(reppo_ctx* c, int slot, const float* params, cudaStream_t st) {
     for (const Linear& L : m.layers) {
       PackEntry& e = t.e[t.n++];
       e.w = params + L.w; e.wb = c->shadow_b[slot] + L.sb;
-      e.wtb = nullptr;
+      e.wtb = (L.st >= 0) ? c->shadow_t[slot] + L.st : nullptr;
       e.out = L.out; e.in = L.in; e.ld_b = L.ld_b; e.ld_t = L.ld_t;
     }
   };
@@ -353,12 +360,42 @@ int pack_all(reppo_ctx* c, const reppo_state* s, cudaStream_t st) {
   return REPPO_OK;
 }
 
+// Where the first layer's input rows come from when the gather is fused into a SIMT first layer (thin.cu):
+//   x[r, :] = [ a[ia(r), 0:da] | b[ib(r), 0:db] ], ia(r) = idx ? idx[r] : r, ib(r) = b_local ? r : ia(r)
+struct ThinIn {
+  const float* a = nullptr; int da = 0, lda = 0;
+  const float* b = nullptr; int db = 0, ldb = 0;
+  const int32_t* idx = nullptr; int b_local = 0;
+  bool want_x_twin = true;   // the weight gradient of this layer needs the gathered input as a bf16 operand
+  bool done = false;         // out: the thin kernel ran (otherwise the caller gathers and the GEMM path runs)
+};
+
 // out_act: optional bf16 twin that receives swish(output) straight from the last GEMM's epilogue
+// thin: try the fused gather + first-layer SIMT kernel; when it is not eligible NOTHING is launched for layer 0 and
+//       thin->done stays false (the caller then gathers `in` itself and calls again without `thin`)
+// skip_last: stop before the last Linear (its GEMM is fused into the kernel that consumes it)
 int mlp_forward(reppo_ctx* c, const Mlp& m, const float* params, int slot, const float* in, int rows, Acts& a, cudaStream_t st,
-                Twin out_act = Twin{}) {
+                Twin out_act = Twin{}, ThinIn* thin = nullptr, bool skip_last = false) {
   const float* cur = in;
   const int n = static_cast<int>(m.layers.size());
-  for (int i = 0; i < n; ++i) {
+  int first = 0;
+  if (thin != nullptr) {
+    const Linear& L = m.layers[0];
+    thin->done = false;
+    if (!c->tc || n < 2 || L.st < 0) return REPPO_OK;
+    const Twin tw = c->twin(a.x[0]), tx = thin->want_x_twin ? c->twin(in) : Twin{};
+    const cudaError_t e = launch_thin_first_layer(
+        m.norm, thin->a, thin->da, thin->lda, thin->b, thin->db, thin->ldb, thin->idx, thin->b_local, rows, L.out,
+        c->shadow_t[slot] + L.st, L.ld_t, params + L.b, L.g >= 0 ? params + L.g : nullptr, L.beta >= 0 ? params + L.beta : nullptr,
+        c->sem.norm_eps, a.z[0], a.rstd[0], a.mean[0], tw.p, tw.ld, tx.p, tx.ld, st);
+    if (e == cudaErrorNotSupported) return REPPO_OK;
+    if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("launch_thin_first_layer: ") + cudaGetErrorString(e));
+    ++c->launches;
+    thin->done = true;
+    cur = a.x[0];
+    first = 1;
+  }
+  for (int i = first; i < n - (skip_last ? 1 : 0); ++i) {
     const Linear& L = m.layers[i];
     const bool last = (i == n - 1);
     float* dst = last ? a.out : a.z[i];
@@ -429,7 +466,7 @@ struct FusedIn {
 
 int mlp_backward(reppo_ctx* c, const Mlp& m, const float* params, int slot, float* grads, const float* in, int rows,
                  const Acts& a, const float* d_out, float* dx_in, int dx_mode, float* bias2, float scale2, bool last_bias_done,
-                 cudaStream_t st, cudaStream_t wst, FusedIn* fin = nullptr) {
+                 cudaStream_t st, cudaStream_t wst, FusedIn* fin = nullptr, bool last_dgrad_done = false) {
   const int n = static_cast<int>(m.layers.size());
   const float* d = d_out;
   for (int i = n - 1; i >= 0; --i) {
@@ -445,7 +482,8 @@ int mlp_backward(reppo_ctx* c, const Mlp& m, const float* params, int slot, floa
       const Linear& Lp = m.layers[i - 1];
       float* dz = a.dz[i - 1];
       const Twin tw = c->twin(dz);
-      if (c->tc) {
+      const bool have_dx = last_dgrad_done && i == n - 1;   // the producer of d_out already wrote this layer's dgrad to a.tmp
+      if (c->tc && !have_dx) {
         // dgrad + norm / swish backward (+ d gamma, d beta, d bias column sums) in ONE tcgen05 kernel
         const Twin td = c->twin(d);
         const cudaError_t e = launch_gemm_bf16_tc_bwd(
@@ -456,7 +494,7 @@ int mlp_backward(reppo_ctx* c, const Mlp& m, const float* params, int slot, floa
         if (e == cudaSuccess) { ++c->launches; d = dz; continue; }
         if (e != cudaErrorNotSupported) return fail(c, REPPO_ERR_CUDA, std::string("launch_gemm_bf16_tc_bwd: ") + cudaGetErrorString(e));
       }
-      RET(linear_dgrad(c, L, params, slot, d, rows, a.tmp, GEMM_STORE, st));
+      if (!have_dx) RET(linear_dgrad(c, L, params, slot, d, rows, a.tmp, GEMM_STORE, st));
       CK(launch_norm_act_bwd(m.norm, a.tmp, nullptr, a.z[i - 1], Lp.g >= 0 ? params + Lp.g : nullptr,
                              Lp.beta >= 0 ? params + Lp.beta : nullptr, a.rstd[i - 1], a.mean[i - 1], rows, L.in,
                              c->tc ? nullptr : dz, (grads && Lp.g >= 0) ? grads + Lp.g : nullptr,
@@ -620,11 +658,12 @@ TrunkBufs trunk_main(reppo_ctx* c) { return TrunkBufs{&c->fa, &c->ha, c->xs, c->
 TrunkBufs trunk_actor(reppo_ctx* c) { return TrunkBufs{&c->fa2, &c->ha2, c->xs2, c->dxs_a, c->dfeat_a, c->dlogits_a}; }
 
 // encoder + swish(features) -> xs
-int critic_trunk_encoder(reppo_ctx* c, const float* cp, int cslot, const float* x0, int rows, const TrunkBufs& tb, cudaStream_t st) {
+int critic_trunk_encoder(reppo_ctx* c, const float* cp, int cslot, const float* x0, int rows, const TrunkBufs& tb, cudaStream_t st,
+                         ThinIn* thin = nullptr) {
   const Twin tw = c->twin(tb.xs);
   if (c->tc && getenv("REPPO_NO_FUSE_ACT") == nullptr) {
     // swish(features), the input of both heads, leaves the encoder's last GEMM epilogue directly as bf16
-    RET(mlp_forward(c, c->feature, cp, cslot, x0, rows, *tb.fa, st, tw));
+    RET(mlp_forward(c, c->feature, cp, cslot, x0, rows, *tb.fa, st, tw, thin));
   } else {
     RET(mlp_forward(c, c->feature, cp, cslot, x0, rows, *tb.fa, st));
     CK(launch_norm_act_fwd(NORM_NONE, tb.fa->out, nullptr, nullptr, rows, c->shape.critic_hidden, 0.f, c->tc ? nullptr : tb.xs,
@@ -633,8 +672,8 @@ int critic_trunk_encoder(reppo_ctx* c, const float* cp, int cslot, const float* 
   return REPPO_OK;
 }
 int critic_trunk(reppo_ctx* c, const float* cp, int cslot, const float* x0, int rows, bool with_pred, const TrunkBufs& tb,
-                 cudaStream_t st) {
-  RET(critic_trunk_encoder(c, cp, cslot, x0, rows, tb, st));
+                 cudaStream_t st, ThinIn* thin = nullptr) {
+  RET(critic_trunk_encoder(c, cp, cslot, x0, rows, tb, st, thin));
   RET(mlp_forward(c, c->head, cp, cslot, tb.xs, rows, *tb.ha, st));
   if (with_pred) RET(mlp_forward(c, c->pred, cp, cslot, tb.xs, rows, c->pa, st));
   return REPPO_OK;
@@ -713,9 +752,21 @@ int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
     return REPPO_OK;
   }
   Twin tw = c->twin(c->x0);
-  CK(launch_gather_concat(b->critic_obs, sh.critic_obs_dim, b->action, sh.action_dim, idx, 0, mb, c->x0, c->K0, tw.p, tw.ld, st));
-  // encoder, then swish(features) feeds two independent heads
-  RET(critic_trunk_encoder(c, cp, cslot, c->x0, mb, trunk_main(c), st));
+  // encoder, then swish(features) feeds two independent heads.  Tensor-core mode: the minibatch gather and the thin first
+  // Linear (K = obs + action dims) run as ONE SIMT kernel; otherwise gather, then the GEMM path.
+  ThinIn thin;
+  thin.a = b->critic_obs; thin.da = sh.critic_obs_dim; thin.lda = sh.critic_obs_dim;
+  thin.b = b->action; thin.db = sh.action_dim; thin.ldb = sh.action_dim; thin.idx = idx;
+  bool thin_ok = false;
+  if (c->tc && getenv("REPPO_NO_FUSE_ACT") == nullptr) {
+    const Twin txs = c->twin(c->xs);
+    RET(mlp_forward(c, c->feature, cp, cslot, c->x0, mb, c->fa, st, txs, &thin));
+    thin_ok = thin.done;
+  }
+  if (!thin_ok) {
+    CK(launch_gather_concat(b->critic_obs, sh.critic_obs_dim, b->action, sh.action_dim, idx, 0, mb, c->x0, c->K0, tw.p, tw.ld, st));
+    RET(critic_trunk_encoder(c, cp, cslot, c->x0, mb, trunk_main(c), st));
+  }
   RET(dep(c, st, s1));
   // --- branch s1: prediction head forward, aux loss, backward down to d swish(features)
   RET(mlp_forward(c, c->pred, cp, cslot, c->xs, mb, c->pa, s1));
@@ -838,19 +889,61 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
   }
   Twin tw = c->twin(c->xa0);
   const Twin tx0 = c->twin(c->x0a);
-  // policy input and the observation part of the critic input, one launch
-  CK(launch_gather_pair(b->obs, sh.obs_dim, b->critic_obs, Dc, idx, mb, c->xa0, sh.obs_dim, tw.p, tw.ld, c->x0a, c->K0, tx0.p,
-                        tx0.ld, pre));
-  RET(mlp_forward(c, c->actor, ap, SLOT_ACTOR, c->xa0, mb, c->aa, pre));
-  if (old_table == nullptr) RET(mlp_forward(c, c->actor, s->actor_old, SLOT_ACTOR_OLD, c->xa0, mb, c->oa, pre));
-  CK(launch_actor_sample(c->aa.out, old_table ? old_table : c->oa.out, old_table ? idx : nullptr, eps_pi, eps_kl, mb, A,
-                         sh.kl_samples, ac, c->x0a + Dc, c->K0, c->logp, c->kl, c->gmu, c->gsig, tx0.p ? tx0.p + Dc : nullptr,
-                         tx0.ld, pre));
+  const int na = static_cast<int>(c->actor.layers.size());
+  // ---- policy forward.  Tensor-core mode: gather + thin first Linear as one SIMT kernel, the policy head (H -> 2A)
+  // inside the sampling kernel; otherwise (or for shapes outside the thin kernels) gather, GEMMs, sample.
+  ThinIn thin_a;
+  thin_a.a = b->obs; thin_a.da = sh.obs_dim; thin_a.lda = sh.obs_dim; thin_a.idx = idx;
+  bool head_fused = false, x0a_gathered = false;
+  if (c->tc) RET(mlp_forward(c, c->actor, ap, SLOT_ACTOR, c->xa0, mb, c->aa, pre, Twin{}, &thin_a, /*skip_last=*/true));
+  if (!thin_a.done) {
+    // policy input and the observation part of the critic input, one launch
+    CK(launch_gather_pair(b->obs, sh.obs_dim, b->critic_obs, Dc, idx, mb, c->xa0, sh.obs_dim, tw.p, tw.ld, c->x0a, c->K0, tx0.p,
+                          tx0.ld, pre));
+    x0a_gathered = true;
+    RET(mlp_forward(c, c->actor, ap, SLOT_ACTOR, c->xa0, mb, c->aa, pre, Twin{}, nullptr, /*skip_last=*/c->tc));
+  }
+  if (old_table == nullptr) {
+    if (thin_a.done) {   // the behaviour policy's GEMM path needs the gathered input
+      CK(launch_gather_concat(b->obs, sh.obs_dim, nullptr, 0, idx, 0, mb, c->xa0, sh.obs_dim, tw.p, tw.ld, pre));
+    }
+    RET(mlp_forward(c, c->actor, s->actor_old, SLOT_ACTOR_OLD, c->xa0, mb, c->oa, pre));
+  }
+  const float* old_out = old_table ? old_table : c->oa.out;
+  const int32_t* old_idx = old_table ? idx : nullptr;
+  if (c->tc) {
+    const Linear& L3 = c->actor.layers.back();
+    const Twin txl = c->twin(c->aa.x[na - 2]);
+    const cudaError_t e = launch_actor_head_sample(txl.p, txl.ld, L3.in, c->shadow_b[SLOT_ACTOR] + L3.sb, L3.ld_b, ap + L3.b, c->aa.out,
+                                                   old_out, old_idx, eps_pi, eps_kl, mb, A, sh.kl_samples, ac, c->x0a + Dc, c->K0,
+                                                   c->logp, c->kl, c->gmu, c->gsig, tx0.p ? tx0.p + Dc : nullptr, tx0.ld, pre);
+    if (e == cudaSuccess) { ++c->launches; head_fused = true; }
+    else if (e != cudaErrorNotSupported) return fail(c, REPPO_ERR_CUDA, std::string("launch_actor_head_sample: ") + cudaGetErrorString(e));
+    else RET(linear_fwd(c, L3, ap, SLOT_ACTOR, c->aa.x[na - 2], mb, c->aa.out, Twin{}, pre));
+  }
+  if (!head_fused)
+    CK(launch_actor_sample(c->aa.out, old_out, old_idx, eps_pi, eps_kl, mb, A, sh.kl_samples, ac, c->x0a + Dc, c->K0, c->logp, c->kl,
+                           c->gmu, c->gsig, tx0.p ? tx0.p + Dc : nullptr, tx0.ld, pre));
   RET(dep(c, pre, st));
-  // Q(s, a) through the (already updated, frozen) critic and dQ/da
+  // ---- Q(s, a) through the (already updated, frozen) critic and dQ/da
   if (critic_ready != nullptr && cudaStreamWaitEvent(st, critic_ready, 0) != cudaSuccess)
     return fail(c, REPPO_ERR_CUDA, "cudaStreamWaitEvent failed");
-  RET(critic_trunk(c, cp, cslot, c->x0a, mb, false, tb, st));
+  ThinIn thin_c;   // critic input = [critic_obs[idx] | sampled action (local rows of x0a)]
+  thin_c.a = b->critic_obs; thin_c.da = Dc; thin_c.lda = Dc; thin_c.b = c->x0a + Dc; thin_c.db = A; thin_c.ldb = c->K0;
+  thin_c.idx = idx; thin_c.b_local = 1; thin_c.want_x_twin = false;
+  bool trunk_done = false;
+  if (c->tc && getenv("REPPO_NO_FUSE_ACT") == nullptr) {
+    RET(critic_trunk_encoder(c, cp, cslot, c->x0a, mb, tb, st, &thin_c));
+    if (thin_c.done) {
+      RET(mlp_forward(c, c->head, cp, cslot, tb.xs, mb, *tb.ha, st));
+      trunk_done = true;
+    }
+  }
+  if (!trunk_done) {
+    if (!x0a_gathered)
+      CK(launch_gather_concat(b->critic_obs, Dc, nullptr, 0, idx, 0, mb, c->x0a, c->K0, tx0.p, tx0.ld, st));   // action columns stay
+    RET(critic_trunk(c, cp, cslot, c->x0a, mb, false, tb, st));
+  }
   tw = c->twin(tb.dlogits);
   CK(launch_actor_q(tb.ha->out, sh.num_bins, cp + c->zero_dist_off, c->hl, c->kl, mb, inv, ac.kl_mode, ac.kl_bound, c->q,
                     tb.dlogits, tw.p, tw.ld, st));
@@ -862,14 +955,34 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
     CK(launch_norm_act_bwd(NORM_NONE, tb.dxs, nullptr, tb.fa->out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden,
                            c->tc ? nullptr : tb.dfeat, nullptr, nullptr, nullptr, tw.p, tw.ld, st));
   }
-  RET(mlp_backward(c, c->feature, cp, cslot, nullptr, c->x0a, mb, *tb.fa, tb.dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, false, st, st));
+  // ---- policy gradient.  Tensor-core mode: dQ/da through the critic's thin first Linear, the row math and the policy
+  // head's dgrad in ONE SIMT kernel (two tcgen05 launches fewer on the chain).
+  tw = c->twin(c->dout);
+  bool grad_fused = false;
+  if (c->tc && na >= 2 && c->feature.layers.size() >= 2) {
+    // the critic's input-gradient chain stops at dz of its first layer
+    RET(mlp_backward(c, c->feature, cp, cslot, nullptr, c->x0a, mb, *tb.fa, tb.dfeat, nullptr, GEMM_STORE, nullptr, 0.f, false, st, st));
+    const Linear& L1 = c->feature.layers[0];
+    const Linear& L3 = c->actor.layers.back();
+    const Twin tdz = c->twin(tb.fa->dz[0]);
+    const cudaError_t e = launch_actor_grad_thin(tdz.p, tdz.ld, L1.out, c->shadow_b[cslot] + L1.sb, L1.ld_b, Dc,
+                                                 c->shadow_b[SLOT_ACTOR] + L3.sb, L3.ld_b, L3.in, c->aa.out, eps_pi, c->x0a + Dc, c->K0,
+                                                 c->logp, c->kl, c->q, c->gmu, c->gsig, ap, mb, A, inv, ac, c->dout, ag, metrics,
+                                                 tw.p, tw.ld, ag + L3.b, c->aa.tmp, st);
+    if (e == cudaSuccess) { ++c->launches; grad_fused = true; }
+    else if (e != cudaErrorNotSupported) return fail(c, REPPO_ERR_CUDA, std::string("launch_actor_grad_thin: ") + cudaGetErrorString(e));
+    else RET(linear_dgrad(c, L1, cp, cslot, tb.fa->dz[0], mb, c->dx0, GEMM_STORE, st));
+  } else {
+    RET(mlp_backward(c, c->feature, cp, cslot, nullptr, c->x0a, mb, *tb.fa, tb.dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, false, st, st));
+  }
   // last read of the critic snapshot: the critic chain may overwrite it from here on
   if (critic_read_done != nullptr && cudaEventRecord(critic_read_done, st) != cudaSuccess)
     return fail(c, REPPO_ERR_CUDA, "cudaEventRecord failed");
-  tw = c->twin(c->dout);
-  CK(launch_actor_grad(c->aa.out, eps_pi, c->x0a + Dc, c->K0, c->dx0 + Dc, c->K0, c->logp, c->kl, c->q, c->gmu, c->gsig, ap,
-                       mb, A, inv, ac, c->dout, ag, metrics, tw.p, tw.ld, ag + c->actor.layers.back().b, st));
-  RET(mlp_backward(c, c->actor, ap, SLOT_ACTOR, ag, c->xa0, mb, c->aa, c->dout, nullptr, GEMM_STORE, nullptr, 0.f, true, st, sw));
+  if (!grad_fused)
+    CK(launch_actor_grad(c->aa.out, eps_pi, c->x0a + Dc, c->K0, c->dx0 + Dc, c->K0, c->logp, c->kl, c->q, c->gmu, c->gsig, ap,
+                         mb, A, inv, ac, c->dout, ag, metrics, tw.p, tw.ld, ag + c->actor.layers.back().b, st));
+  RET(mlp_backward(c, c->actor, ap, SLOT_ACTOR, ag, c->xa0, mb, c->aa, c->dout, nullptr, GEMM_STORE, nullptr, 0.f, true, st, sw, nullptr,
+                   /*last_dgrad_done=*/grad_fused));
   RET(dep(c, sw, st));
   return REPPO_OK;
 }
@@ -886,6 +999,7 @@ int clip_adam_impl(reppo_ctx* c, const reppo_net_state* net, int64_t n, const re
         ShadowEntry& e = sh.e[sh.n++];
         e.start = L.w; e.end = L.w + static_cast<int64_t>(L.out) * L.in; e.in = L.in; e.ld = L.ld_b;
         e.dst = c->shadow_b[slot] + L.sb;
+        e.dst_t = (L.st >= 0) ? c->shadow_t[slot] + L.st : nullptr; e.ld_t = L.ld_t;
       }
     };
     if (slot == SLOT_CRITIC || slot == SLOT_CRITIC_ALT) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }

@@ -102,6 +102,22 @@ cudaError_t launch_value_head(const float* head_out, int ld, const float* zero_d
                               float* value, float* logits, cudaStream_t st);
 cudaError_t launch_mean_std(const float* out, int rows, int A, float min_std, float* mean, float* std, cudaStream_t st);
 
+// thin layers on the SIMT pipes (thin.cu); cudaErrorNotSupported = shape not eligible, caller takes the GEMM path
+cudaError_t launch_thin_first_layer(int norm, const float* a, int da, int lda, const float* b, int db, int ldb, const int* idx,
+                                    int b_local, int rows, int H, const void* wT_bf16, int ldw, const float* bias, const float* gamma,
+                                    const float* beta, float eps, float* z, float* rstd, float* mean, void* y_h, int ldy, void* x_h,
+                                    int ldx, cudaStream_t st);
+cudaError_t launch_actor_head_sample(const void* x_h, int ldx, int H, const void* w_bf16, int ldw, const float* bias, float* out,
+                                     const float* out_old, const int* old_idx, const float* eps_pi, const float* eps_kl, int rows,
+                                     int A, int kl_samples, const ActorConsts& ac, float* act_out, int act_ld, float* logp,
+                                     float* kl, float* gmu, float* gsig, void* act_h, int act_ldh, cudaStream_t st);
+cudaError_t launch_actor_grad_thin(const void* dz1_h, int lddz, int Hc, const void* w1_bf16, int ldw1, int Dc, const void* w3_bf16,
+                                   int ldw3, int Ha, const float* out, const float* eps_pi, const float* act, int act_ld,
+                                   const float* logp, const float* kl, const float* q, const float* gmu, const float* gsig,
+                                   const float* actor_params, int rows, int A, float inv_rows, const ActorConsts& ac, float* dout,
+                                   float* actor_grads, float* metrics, void* dout_h, int ldh, float* dbias, float* dx,
+                                   cudaStream_t st);
+
 // rollout side (rollout.cu)
 cudaError_t launch_policy_sample(const float* out, const float* eps, const float* scale, int rows, int A, float min_std, float clip,
                                  int store_clipped, float* action, int act_ld, void* act_h, int act_ldh, float* logp,
@@ -112,7 +128,7 @@ cudaError_t launch_obs_normalize(const float* x, long long rows, int D, float* m
                                  float eps, int update, int center, long long until, float* out, cudaStream_t st);
 
 // bf16 shadows of the weight matrices, refreshed by the Adam kernel itself (REPPO_GEMM_BF16)
-struct ShadowEntry { long long start, end; int in, ld; void* dst; };
+struct ShadowEntry { long long start, end; int in, ld; void* dst; void* dst_t; int ld_t; };   // dst_t: optional transposed copy [in][ld_t]
 struct ShadowTable { int n; ShadowEntry e[kMaxPack]; };
 cudaError_t launch_clip_adam(const float* p_in, float* p, float* g, float* m, float* v, long long n, int* step, float* partials,
                              const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out, int zero_grads, cudaStream_t st);

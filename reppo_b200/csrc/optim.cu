@@ -69,6 +69,8 @@ adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __restric
         const int off = static_cast<int>(idx - sh.e[t].start);
         const int r = off / sh.e[t].in, col = off - r * sh.e[t].in;
         static_cast<__nv_bfloat16*>(sh.e[t].dst)[static_cast<size_t>(r) * sh.e[t].ld + col] = __float2bfloat16_rn(pp);
+        if (sh.e[t].dst_t != nullptr)   // thin first layers also keep W^T (thin.cu)
+          static_cast<__nv_bfloat16*>(sh.e[t].dst_t)[static_cast<size_t>(col) * sh.e[t].ld_t + r] = __float2bfloat16_rn(pp);
         break;
       }
     }
