@@ -526,6 +526,9 @@ cudaError_t launch_gemm_bf16_tc_norm(int norm, int M, int N, int K, const void* 
                                      int ldc, const float* bias, void* act_out_v, int act_ld, const NormArgs& na,
                                      cudaStream_t st) {
   if (norm == NORM_NONE || bias == nullptr || act_out_v == nullptr) return cudaErrorNotSupported;
+  // large shapes: the persistent CTA-pair GEMM + the row kernel beats this one-tile-per-CTA fused kernel
+  static const bool keep_fused = getenv("REPPO_FUSE_NORM_LARGE") != nullptr;
+  if (!keep_fused && gemm_bf16_tc2_eligible(false, false, M, N, K, GEMM_STORE, 1)) return cudaErrorNotSupported;
   if ((lda & 7) || (ldb & 7) || (ldc & 3) || (act_ld & 3) || (reinterpret_cast<uintptr_t>(A) & 15) ||
       (reinterpret_cast<uintptr_t>(B) & 15) || (reinterpret_cast<uintptr_t>(C) & 15))
     return cudaErrorNotSupported;
@@ -558,6 +561,11 @@ cudaError_t launch_gemm_bf16_tc(bool a_mn, bool b_mn, int M, int N, int K, const
   if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
     return cudaErrorInvalidValue;
   if (a_mn && !b_mn) return cudaErrorInvalidValue;  // arrangement not used by the MLP
+  {
+    // shapes that fill the machine with 256-row pair tiles: persistent cta_group::2 kernel
+    const cudaError_t e2 = launch_gemm_bf16_tc2(a_mn, b_mn, M, N, K, A, lda, B, ldb, C, ldc, bias, mode, split_k, act_out_v, act_ld, st);
+    if (e2 != cudaErrorNotSupported) return e2;
+  }
   CUtensorMap ta, tb;
   // narrow tiles when 128-wide ones would leave most of the 148 SMs idle
   const int tiles128 = ((M + TC_BLOCK_M - 1) / TC_BLOCK_M) * ((N + 127) / 128) * (split_k > 0 ? split_k : 1);

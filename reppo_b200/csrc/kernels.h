@@ -50,6 +50,11 @@ cudaError_t launch_gemm_f32(bool ta, bool tb, int M, int N, int K, const float* 
 cudaError_t launch_gemm_bf16_tc(bool a_mn, bool b_mn, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
                                 float* C, int ldc, const float* bias, int mode, int split_k, void* act_out, int act_ld,
                                 cudaStream_t st);
+// persistent CTA-pair (cta_group::2) variant for large shapes (gemm_bf16_tc2.cu); cudaErrorNotSupported = not eligible
+cudaError_t launch_gemm_bf16_tc2(bool a_mn, bool b_mn, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
+                                 float* C, int ldc, const float* bias, int mode, int split_k, void* act_out, int act_ld,
+                                 cudaStream_t st);
+bool gemm_bf16_tc2_eligible(bool a_mn, bool b_mn, int M, int N, int K, int mode, int split_k);
 // fused forward Linear + bias + norm + swish (cluster / DSMEM row statistics); cudaErrorNotSupported = shape not eligible
 struct NormArgs { const float* gamma; const float* beta; float eps; float* rstd_out; float* mean_out; };
 cudaError_t launch_gemm_bf16_tc_norm(int norm, int M, int N, int K, const void* A, int lda, const void* B, int ldb, float* C,

@@ -132,7 +132,7 @@ norm_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma
   }
 }
 
-template <int NORM, int VPL>
+template <int NORM, int VPL, bool FAST>
 __global__ void __launch_bounds__(256)
 norm_act_fwd_vec_kernel(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
                         int rows, float eps, float* __restrict__ x, float* __restrict__ rstd_out,
@@ -176,7 +176,7 @@ norm_act_fwd_vec_kernel(const float* __restrict__ z, const float* __restrict__ g
       for (int j = 0; j < 4; ++j) y[j] = (NORM == NORM_RMS) ? y[j] * rstd * gg[j] : (y[j] - mean) * rstd * gg[j] + bb[j];
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) y[j] = swishf_(y[j]);
+    for (int j = 0; j < 4; ++j) y[j] = FAST ? y[j] * __fdividef(1.f, 1.f + __expf(-fmaxf(y[j], -80.f))) : swishf_(y[j]);
     const int c = 4 * (lane + 32 * i);
     if (x != nullptr) reinterpret_cast<float4*>(x + static_cast<size_t>(row) * H)[lane + 32 * i] = make_float4(y[0], y[1], y[2], y[3]);
     if (x_h != nullptr) store_bf16x4(x_h + static_cast<size_t>(row) * ldh + c, y[0], y[1], y[2], y[3]);
@@ -187,14 +187,17 @@ template <int NORM>
 static void launch_fwd_norm(const float* z, const float* gamma, const float* beta, int rows, int H, float eps, float* x,
                             float* rstd, float* mean, __nv_bfloat16* xh, int ldh, cudaStream_t st) {
   const int wpb = 8, grid = (rows + wpb - 1) / wpb;
-  const bool vec = (H % 128 == 0) && H <= 1024 && (ldh % 4 == 0) && getenv("REPPO_NO_VEC") == nullptr;
-#define REPPO_FWD_VEC(V) launch_k((norm_act_fwd_vec_kernel<NORM, V>), dim3(grid), dim3(wpb * 32), 0, st, z, gamma, beta, rows, eps, x, rstd, mean, xh, ldh)
+  const bool vec = (H % 128 == 0) && H <= 2048 && (ldh % 4 == 0) && getenv("REPPO_NO_VEC") == nullptr;
+  const bool fast = (x == nullptr) && H >= 1024;   // bf16-operand mode at the wide shapes: SFU sigmoid
+#define REPPO_FWD_VEC(V) do { if (fast) launch_k((norm_act_fwd_vec_kernel<NORM, V, true>), dim3(grid), dim3(wpb * 32), 0, st, z, gamma, beta, rows, eps, x, rstd, mean, xh, ldh); \
+    else launch_k((norm_act_fwd_vec_kernel<NORM, V, false>), dim3(grid), dim3(wpb * 32), 0, st, z, gamma, beta, rows, eps, x, rstd, mean, xh, ldh); } while (0)
   if (vec && H == 128) REPPO_FWD_VEC(1);
   else if (vec && H == 256) REPPO_FWD_VEC(2);
   else if (vec && H == 384) REPPO_FWD_VEC(3);
   else if (vec && H == 512) REPPO_FWD_VEC(4);
   else if (vec && H == 768) REPPO_FWD_VEC(6);
   else if (vec && H == 1024) REPPO_FWD_VEC(8);
+  else if (vec && H == 2048) REPPO_FWD_VEC(16);
   else launch_k((norm_act_fwd_kernel<NORM>), dim3(grid), dim3(wpb * 32), 0, st, z, gamma, beta, rows, H, eps, x, rstd, mean, xh, ldh);
 #undef REPPO_FWD_VEC
 }
@@ -411,6 +414,144 @@ norm_act_bwd_vec_kernel(const float* __restrict__ dx, const float* __restrict__ 
   if (dbias != nullptr) flush(pd, dbias);
 }
 
+
+// Wide rows (H = 512 * WPR, WPR warps per row): at H >= 1024 the one-warp-per-row kernel above needs > 230 registers
+// (one block of 8 warps per SM, nothing to hide the load latency behind).  Here every warp owns a 512-column segment
+// (VPL = 4, two blocks per SM); the row statistics of the norm backward are combined across the WPR warps of a row
+// through a double-buffered shared-memory slot and ONE block barrier per row iteration.
+// FAST (bf16-operand mode only): SFU sigmoid (ex2.approx / rcp.approx), far below the bf16 rounding of dz.
+template <bool FAST>
+REPPO_DEVINL float swish_grad_sel(float x) {
+  if (FAST) {
+    const float sg = __fdividef(1.f, 1.f + __expf(-fmaxf(x, -80.f)));
+    return sg * (1.f + x * (1.f - sg));
+  }
+  return swish_grad_(x);
+}
+
+template <int NORM, int WPR, bool FAST>
+__global__ void __launch_bounds__(256, 2)
+norm_act_bwd_wide_kernel(const float* __restrict__ dx, const float* __restrict__ dx2, const float* __restrict__ z,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rstd_in,
+                         const float* __restrict__ mean_in, int rows, int rows_per_block, float* __restrict__ dz,
+                         float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                         __nv_bfloat16* __restrict__ dz_h, int ldh) {
+  REPPO_PDL_PROLOGUE();
+  constexpr int VPL = 4, SEG = 128 * VPL, H = SEG * WPR, RPI = 8 / WPR;   // rows per block iteration
+  __shared__ float xs[2][8][2];
+  __shared__ float colp[8][SEG];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = warp % WPR, rslot = warp / WPR;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  const int niter = (r1 - r0 + RPI - 1) / RPI;
+  const int c0 = sub * SEG;
+
+  float g[VPL][4], b[VPL][4];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { g[i][j] = 1.f; b[i][j] = 0.f; }
+    const int cg = c0 + 4 * (lane + 32 * i);
+    if (NORM != NORM_NONE) { g[i][0] = gamma[cg]; g[i][1] = gamma[cg + 1]; g[i][2] = gamma[cg + 2]; g[i][3] = gamma[cg + 3]; }
+    if (NORM == NORM_LAYER) { b[i][0] = beta[cg]; b[i][1] = beta[cg + 1]; b[i][2] = beta[cg + 2]; b[i][3] = beta[cg + 3]; }
+  }
+  float pg[VPL][4], pb[VPL][4], pd[VPL][4];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { pg[i][j] = 0.f; pb[i][j] = 0.f; pd[i][j] = 0.f; }
+
+  for (int it = 0; it < niter; ++it) {
+    const int row = r0 + it * RPI + rslot;
+    const bool valid = row < r1;
+    float zh[VPL][4], dy[VPL][4];
+    float s1 = 0.f, s2 = 0.f, rstd = 1.f, mean = 0.f;
+    if (valid) {
+      const float4* zr = reinterpret_cast<const float4*>(z + static_cast<size_t>(row) * H + c0);
+      const float4* dxr = reinterpret_cast<const float4*>(dx + static_cast<size_t>(row) * H + c0);
+      float4 zv[VPL], dv[VPL];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) { zv[i] = zr[lane + 32 * i]; dv[i] = dxr[lane + 32 * i]; }
+      if (dx2 != nullptr) {
+        const float4* dx2r = reinterpret_cast<const float4*>(dx2 + static_cast<size_t>(row) * H + c0);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const float4 t = dx2r[lane + 32 * i];
+          dv[i].x += t.x; dv[i].y += t.y; dv[i].z += t.z; dv[i].w += t.w;
+        }
+      }
+      if (NORM != NORM_NONE) { rstd = rstd_in[row]; if (NORM == NORM_LAYER) mean = mean_in[row]; }
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const float zz[4] = {zv[i].x, zv[i].y, zv[i].z, zv[i].w};
+        const float dd[4] = {dv[i].x, dv[i].y, dv[i].z, dv[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (NORM == NORM_NONE) {
+            zh[i][j] = zz[j];
+            dy[i][j] = dd[j] * swish_grad_sel<FAST>(zz[j]);
+          } else {
+            zh[i][j] = (zz[j] - mean) * rstd;
+            const float y = zh[i][j] * g[i][j] + b[i][j];
+            dy[i][j] = dd[j] * swish_grad_sel<FAST>(y);
+            const float dzh = dy[i][j] * g[i][j];
+            s1 += dzh; s2 += dzh * zh[i][j];
+          }
+        }
+      }
+    }
+    if (NORM != NORM_NONE) {
+      s1 = warp_sum(s1); s2 = warp_sum(s2);
+      if (lane == 0) { xs[it & 1][warp][0] = s1; xs[it & 1][warp][1] = s2; }
+      __syncthreads();
+      s1 = 0.f; s2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPR; ++w) { s1 += xs[it & 1][rslot * WPR + w][0]; s2 += xs[it & 1][rslot * WPR + w][1]; }
+      s1 *= (1.f / H); s2 *= (1.f / H);
+      if (NORM == NORM_RMS) s1 = 0.f;
+    }
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (NORM == NORM_NONE) {
+            o[j] = dy[i][j];
+          } else {
+            o[j] = rstd * (dy[i][j] * g[i][j] - s1 - zh[i][j] * s2);
+            pg[i][j] += dy[i][j] * zh[i][j];
+            pb[i][j] += dy[i][j];
+          }
+          pd[i][j] += o[j];
+        }
+        const int c = c0 + 4 * (lane + 32 * i);
+        if (dz != nullptr) *reinterpret_cast<float4*>(dz + static_cast<size_t>(row) * H + c) = make_float4(o[0], o[1], o[2], o[3]);
+        if (dz_h != nullptr) store_bf16x4(dz_h + static_cast<size_t>(row) * ldh + c, o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  // column sums: the RPI warps that own the same column segment are added in shared memory, one global RED per column per block
+  auto flush = [&](float (&acc)[VPL][4], float* __restrict__ dst) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      reinterpret_cast<float4*>(&colp[warp][0])[lane + 32 * i] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+      const int sg = c / SEG, cc = c - sg * SEG;
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < RPI; ++r) t += colp[r * WPR + sg][cc];
+      atomicAdd(dst + c, t);
+    }
+  };
+  if (NORM != NORM_NONE && dgamma != nullptr) flush(pg, dgamma);
+  if (NORM == NORM_LAYER && dbeta != nullptr) flush(pb, dbeta);
+  if (dbias != nullptr) flush(pd, dbias);
+}
+
 template <int NORM>
 static cudaError_t launch_bwd_norm(const float* dx, const float* dx2, const float* z, const float* gamma, const float* beta, const float* rstd,
                                    const float* mean, int rows, int H, float* dz, float* dgamma, float* dbeta, float* dbias,
@@ -419,8 +560,23 @@ static cudaError_t launch_bwd_norm(const float* dx, const float* dx2, const floa
   static const int rpb_env = getenv("REPPO_BWD_RPB") ? atoi(getenv("REPPO_BWD_RPB")) : 0;
   int rows_per_block = rpb_env > 0 ? rpb_env : 8;   // one row per warp: lowest latency (measured 134.4 vs 135.3 ms at 16)
   while ((rows + rows_per_block - 1) / rows_per_block > 148 * 4 && rows_per_block < 128) rows_per_block *= 2;
-  const int grid = (rows + rows_per_block - 1) / rows_per_block;
   const bool vec = (H % 128 == 0) && H <= 1024 && (ldh % 4 == 0) && getenv("REPPO_NO_VEC") == nullptr;
+  if ((H == 1024 || H == 2048) && (ldh % 4 == 0) && getenv("REPPO_NO_WIDE") == nullptr) {
+    // wide rows: 2 / 4 warps per row, ~8 blocks per SM worth of work items so that the tail is short
+    const int rpi = H == 1024 ? 4 : 2;
+    int rpb = (rows + 148 * 8 - 1) / (148 * 8);
+    rpb = ((rpb + rpi - 1) / rpi) * rpi;
+    if (rpb < 2 * rpi) rpb = 2 * rpi;
+    const int gridw = (rows + rpb - 1) / rpb;
+    const bool fast = (dz == nullptr);   // bf16-operand mode: only the bf16 twin of dz is produced
+#define REPPO_BWD_WIDE(W, F) \
+  launch_k((norm_act_bwd_wide_kernel<NORM, W, F>), dim3(gridw), dim3(256), 0, st, dx, dx2, z, gamma, beta, rstd, mean, rows, rpb, dz, dgamma, dbeta, dbias, dzh, ldh)
+    if (H == 1024) { if (fast) REPPO_BWD_WIDE(2, true); else REPPO_BWD_WIDE(2, false); }
+    else { if (fast) REPPO_BWD_WIDE(4, true); else REPPO_BWD_WIDE(4, false); }
+#undef REPPO_BWD_WIDE
+    return cudaGetLastError();
+  }
+  const int grid = (rows + rows_per_block - 1) / rows_per_block;
 #define REPPO_BWD_VEC(V) \
   launch_k((norm_act_bwd_vec_kernel<NORM, V>), dim3(grid), dim3(256), 0, st, dx, dx2, z, gamma, beta, rstd, mean, rows, rows_per_block, dz, dgamma, dbeta, dbias, dzh, ldh)
   if (vec && H == 128) REPPO_BWD_VEC(1);

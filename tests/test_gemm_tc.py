@@ -41,6 +41,28 @@ def test_forward_dgrad_wgrad_vs_torch(rows, in_f, out_f):
     torch.testing.assert_close(dw, _bf(dy).T @ _bf(x), rtol=1e-4, atol=2e-4 * math.sqrt(rows))
 
 
+# Shapes that fill the machine with 256-row pair tiles run the persistent cta_group::2 kernel (gemm_bf16_tc2.cu):
+# full tiles, ragged rows / columns (scalar epilogue, TMA out-of-bounds fill), split-K wgrad, 128- and 256-wide tiles.
+LARGE_SHAPES = [(16384, 1024, 1024), (4100, 1024, 1025), (8192, 512, 768), (5000, 1024, 384), (16384, 256, 1024)]
+
+
+@pytest.mark.parametrize("rows,in_f,out_f", LARGE_SHAPES)
+def test_large_shapes_pair_kernel_vs_torch(rows, in_f, out_f):
+    eng = _engine(max_rows=16384, H=1024)
+    g = torch.Generator(device="cuda").manual_seed(rows + in_f)
+    x = torch.randn(rows, in_f, device="cuda", generator=g)
+    w = torch.randn(out_f, in_f, device="cuda", generator=g) / math.sqrt(in_f)
+    b = torch.randn(out_f, device="cuda", generator=g)
+    dy = torch.randn(rows, out_f, device="cuda", generator=g)
+    y = eng.linear(0, x, w, bias=b)
+    torch.testing.assert_close(y, _bf(x) @ _bf(w).T + b, rtol=1e-4, atol=2e-4 * math.sqrt(in_f))
+    assert torch.equal(y, eng.linear(0, x, w, bias=b))          # deterministic (no split-K in the forward)
+    dx = eng.linear(1, dy, w)
+    torch.testing.assert_close(dx, _bf(dy) @ _bf(w), rtol=1e-4, atol=2e-4 * math.sqrt(out_f))
+    dw = eng.linear(2, dy, x)
+    torch.testing.assert_close(dw, _bf(dy).T @ _bf(x), rtol=1e-4, atol=2e-4 * math.sqrt(rows))
+
+
 def test_fp32_mode_linear_vs_torch():
     eng = _engine(max_rows=512, mode="fp32")
     g = torch.Generator(device="cuda").manual_seed(0)

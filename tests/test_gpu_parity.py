@@ -479,6 +479,8 @@ NAMED = {
                         num_bins=151, vmin=0.0, vmax=200.0),
     "C5_wide": dict(_RED, obs_dim=17, critic_obs_dim=17, action_dim=6, critic_hidden_dim=1024, actor_hidden_dim=1024,
                     num_bins=151, vmin=0.0, vmax=150.0),
+    "C5_very_wide": dict(_RED, obs_dim=17, critic_obs_dim=17, action_dim=6, critic_hidden_dim=2048, actor_hidden_dim=2048,
+                         num_bins=151, vmin=0.0, vmax=150.0),
 }
 
 
