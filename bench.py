@@ -220,6 +220,7 @@ def main():
                     help="bf16 = tcgen05 tensor-core path (bf16 operands, fp32 accumulate; the product); fp32 = FFMA reference-precision mode")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-large", action="store_true", help="skip the large-shape GEMM leg (C5 sweep shapes)")
     ap.add_argument("--profile-only", action="store_true", help="warm-up + one update, no timing legs (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -464,6 +465,21 @@ def main():
                                  "algorithmic_bytes": "3 reads (mean pass, variance pass, apply) + 1 write of the batch"}}
     del big_obs
 
+    # the large Linear shapes of the wide-net / 256k-sample sweep (BASELINE.json configs[4]): persistent
+    # CTA-pair tcgen05 kernel (gemm_bf16_tc2.cu), each GEMM timed alone against the measured bf16 BURST peak
+    gemm_large = None
+    if args.gemm == "bf16" and not args.no_large:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import gemm_bench
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) \
+            else {"bf16_tflops": peaks["bf16_tflops"]}
+        rows_l = []
+        for rows_, H_ in ((16384, 1024), (32768, 2048)):
+            rows_l += gemm_bench.measure(rows_, H_, reps=20, check=False, peaks=pk)
+        gemm_large = {"kernel": "gemm_bf16_tc2_kernel (tcgen05 cta_group::2, persistent)", "bound": "tensor", "unit": "TFLOP/s",
+                      "peak": pk["bf16_tflops"], "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)",
+                      "shapes": rows_l, "best_frac": max(r["frac_burst"] for r in rows_l)}
+
     cpu = None
     if not args.no_cpu_baseline:
         cpu, _ = cpu_sample(hp, args.semantics, seconds=12.0)
@@ -475,7 +491,8 @@ def main():
         "config": workload_config(args.config, cfg, D, A, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_update * args.steps),
         "launches_per_update": int(launches_per_update), "cuda_graph": use_graph, "semantics": args.semantics,
-        "sample_visits_per_s": value * E, "roofline": roofline, "scan": scan, "adam": adam, "rollout": rollout, "cpu_baseline": cpu,
+        "sample_visits_per_s": value * E, "roofline": roofline, "gemm_large": gemm_large, "scan": scan, "adam": adam, "rollout": rollout,
+        "cpu_baseline": cpu,
         "knobs": {k: os.environ[k] for k in os.environ if k.startswith("REPPO_")},
         "final_metrics": {k: final_metrics[k] for k in ("critic_loss", "actor_loss", "kl", "entropy")},
     }
