@@ -350,7 +350,7 @@ static T2Plan t2_plan(bool a_mn, bool b_mn, int M, int N, int K, int mode, int s
   static const int force_bn = getenv("REPPO_TC2_BN") ? atoi(getenv("REPPO_TC2_BN")) : 0;
   T2Plan p{0, 1};
   if (!enabled || (a_mn && !b_mn)) return p;
-  if (K < 4 * T2_K || N < 128 || M < 256) return p;
+  if (K < 8 || N < 128 || M < 256) return p;   // thin-K first layers too: at these row counts they are epilogue (store) bound
   const int max_pairs = t2_max_pairs();
   const int total_kb = (K + T2_K - 1) / T2_K;
   const int mt = (M + 2 * T2_M - 1) / (2 * T2_M);
