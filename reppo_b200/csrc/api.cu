@@ -122,11 +122,15 @@ struct reppo_ctx {
   std::string err;
   int64_t launches = 0;
   // graph cache
-  cudaGraphExec_t graph_exec = nullptr;
+  // two entries: a host that double-buffers its rollout staging (H2D of batch k+1 under update k) alternates two pointer sets
+  static constexpr int kGraphSlots = 2;
+  cudaGraphExec_t graph_exec[kGraphSlots] = {nullptr, nullptr};
   cudaStream_t cap_stream = nullptr;  // capture happens here: the caller's stream may be the legacy default stream
-  GraphKey graph_key{};
-  bool graph_valid = false;
-  int64_t graph_launches = 0;
+  GraphKey graph_key[kGraphSlots] = {};
+  bool graph_valid[kGraphSlots] = {false, false};
+  int64_t graph_launches[kGraphSlots] = {0, 0};
+  int graph_next = 0;   // slot to evict next
+  void invalidate_graphs() { for (int i = 0; i < kGraphSlots; ++i) graph_valid[i] = false; }
   // concurrency: independent branches of a step run on context-owned side streams (captured into the graph as
   // parallel branches): [0] pred-head branch, [1] weight-gradient GEMMs, [2] actor-only prefix of the actor step
   bool concurrent = true;
@@ -1200,7 +1204,7 @@ int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
 
 void reppo_ctx_destroy(reppo_ctx* c) {
   if (c == nullptr) return;
-  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  for (int i = 0; i < reppo_ctx::kGraphSlots; ++i) if (c->graph_exec[i]) cudaGraphExecDestroy(c->graph_exec[i]);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   for (auto& e : c->events) cudaEventDestroy(e);
   for (int i = 0; i < 4; ++i) { if (c->side[i]) cudaStreamDestroy(c->side[i]); if (c->ev_c[i]) cudaEventDestroy(c->ev_c[i]); if (c->ev_a[i]) cudaEventDestroy(c->ev_a[i]); }
@@ -1246,7 +1250,7 @@ int reppo_set_workspace(reppo_ctx* c, void* workspace, size_t bytes) {
   layout_workspace(c, c->ws);
   c->hl.edges = c->edges_d;
   c->hl.support = c->support_d;
-  c->graph_valid = false;
+  c->invalidate_graphs();
   if (c->tc) {
     // bf16 twins / shadows are read through TMA with their padded leading dimension: clear the padding once
     if (cudaMemset(workspace, 0, c->ws_need) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "clearing the workspace failed");
@@ -1441,9 +1445,14 @@ int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const
   }
   GraphKey key{};
   key.state = *s; key.batch = *b; key.plan = *p; key.hp = *hp;
-  if (!c->graph_valid || memcmp(&key, &c->graph_key, sizeof(GraphKey)) != 0) {
-    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
-    c->graph_valid = false;
+  int slot = -1;
+  for (int i = 0; i < reppo_ctx::kGraphSlots; ++i)
+    if (c->graph_valid[i] && memcmp(&key, &c->graph_key[i], sizeof(GraphKey)) == 0) slot = i;
+  if (slot < 0) {
+    slot = c->graph_next;
+    c->graph_next = (c->graph_next + 1) % reppo_ctx::kGraphSlots;
+    if (c->graph_exec[slot]) { cudaGraphExecDestroy(c->graph_exec[slot]); c->graph_exec[slot] = nullptr; }
+    c->graph_valid[slot] = false;
     c->launches = 0;
     cudaError_t e = cudaSuccess;
     if (c->cap_stream == nullptr) {
@@ -1457,16 +1466,16 @@ int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const
     e = cudaStreamEndCapture(c->cap_stream, &graph);
     if (r != REPPO_OK) { if (graph) cudaGraphDestroy(graph); return r; }
     if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+    e = cudaGraphInstantiate(&c->graph_exec[slot], graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-    memcpy(&c->graph_key, &key, sizeof(GraphKey));
-    c->graph_valid = true;
-    c->graph_launches = c->launches;
+    memcpy(&c->graph_key[slot], &key, sizeof(GraphKey));
+    c->graph_valid[slot] = true;
+    c->graph_launches[slot] = c->launches;
   }
-  const cudaError_t e = cudaGraphLaunch(c->graph_exec, st);
+  const cudaError_t e = cudaGraphLaunch(c->graph_exec[slot], st);
   if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
-  c->launches = c->graph_launches;
+  c->launches = c->graph_launches[slot];
   return REPPO_OK;
 }
 
@@ -1517,13 +1526,13 @@ int reppo_nccl_init(reppo_ctx* c, const void* id_128, int32_t rank, int32_t worl
   const int r = c->nccl.CommInitRank(&c->comm[which], world_size, id, rank);
   if (r != 0) { c->comm[which] = nullptr; return fail(c, REPPO_ERR_NCCL, std::string("ncclCommInitRank: ") + c->nccl.GetErrorString(r)); }
   c->world = world_size; c->rank = rank;
-  c->graph_valid = false;
+  c->invalidate_graphs();
   return REPPO_OK;
 }
 
 int reppo_nccl_finalize(reppo_ctx* c) {
   for (int i = 0; i < 2; ++i) if (c->comm[i]) { c->nccl.CommDestroy(c->comm[i]); c->comm[i] = nullptr; }
-  c->graph_valid = false;
+  c->invalidate_graphs();
   return REPPO_OK;
 }
 

@@ -530,10 +530,61 @@ def make_actor_update_fn(cfg, train_state: TrainState, generator: Optional[torch
 # -------------------------------------------------------------------------------------------------
 # the whole update in one call
 # -------------------------------------------------------------------------------------------------
+def _stage_dict(eng, index: int) -> dict:
+    """Device staging buffers of an engine: sets 0 / 1 hold a rollout each, -1 the per-update scratch."""
+    return eng.__dict__.setdefault("_stages", {}).setdefault(index, {})
+
+
+def _rollout_fields(eng, transition, T: int, N: int):
+    """(staging name, reference key, shape) of every field of a ``[T, N, ...]`` rollout that the update reads."""
+    conv = eng.cfg.semantics
+    fields = [("obs", "observations", (T, N, eng.cfg.obs_dim)),
+              ("critic_obs", "critic_observations", (T, N, eng._shape.critic_obs_dim)),
+              ("action", "actions", (T, N, eng.cfg.action_dim)), ("soft_reward", "rewards", (T, N)),
+              ("next_emb", "next_embeddings", (T, N, eng.cfg.critic_hidden_dim)), ("value", "next_values", (T, N)),
+              ("done", "dones", (T, N)), ("truncated", "truncations", (T, N))]
+    if "raw_rewards" in transition:
+        fields.append(("reward", "raw_rewards", (T, N)))
+    if "importance_weight" in transition and conv == "jax":
+        fields.append(("iw", "importance_weight", (T, N)))
+    return fields
+
+
+def reppo_prefetch(train_state: TrainState, transition: Mapping[str, torch.Tensor], cfg) -> None:
+    """Start the host-to-device copy of the NEXT rollout while the current update is still running.
+
+    The copy goes into the staging set that the running update does not read, on a dedicated copy stream, after that
+    set's previous update has finished; ``reppo_update`` called with the same ``transition`` object then skips its own
+    copies and waits for the copy's event instead.  (The reference keeps rollouts on the device, src/torchrl/reppo.py:
+    89-171; this is the input pipeline for hosts whose simulator is not on the GPU.)"""
+    eng = _engine_for(cfg, train_state)
+    h = cfg.hyperparameters
+    T, N = int(h.num_steps), int(h.num_envs)
+    dev = eng.device
+    si = 1 - eng.__dict__.get("_stage_set", 0)
+    stage = _stage_dict(eng, si)
+    cs = eng.__dict__.get("_copy_stream")
+    if cs is None:
+        cs = eng._copy_stream = torch.cuda.Stream(device=dev)
+    free = eng.__dict__.get("_stage_free", {}).get(si)
+    if free is not None:
+        cs.wait_event(free)
+    with torch.cuda.stream(cs):
+        for name, key, shape in _rollout_fields(eng, transition, T, N):
+            t = stage.get(name)
+            if t is None or tuple(t.shape) != tuple(shape):
+                t = stage[name] = torch.empty(shape, dtype=torch.float32, device=dev)
+            t.copy_(transition[key].reshape(shape), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+    eng._prefetched = {"src": transition, "set": si, "event": ev}
+
+
 def reppo_update(train_state: TrainState, transition: Mapping[str, torch.Tensor], cfg, *,
                  perms: Optional[torch.Tensor] = None, eps_pi: Optional[torch.Tensor] = None,
                  eps_kl: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None,
-                 use_graph: Optional[bool] = None, return_device_metrics: bool = False, world_size: int = 1):
+                 use_graph: Optional[bool] = None, return_device_metrics: bool = False, world_size: int = 1,
+                 prefetch_next: Optional[Mapping[str, torch.Tensor]] = None):
     """One full REPPO update over a rollout batch = ``learn_step`` (src/jaxrl/reppo.py:417-673) /
     lines 614-632 of src/torchrl/reppo.py: TD(lambda) scan, ``num_epochs`` x ``num_mini_batches`` critic+actor
     steps on shuffled minibatches, then ``old_actor <- actor``.
@@ -542,6 +593,10 @@ def reppo_update(train_state: TrainState, transition: Mapping[str, torch.Tensor]
     ``eps_pi`` and ``eps_kl`` may be injected (parity tests); by default they are drawn on the device:
     JAX semantics reuses one noise draw per epoch, Torch semantics draws per minibatch.
     Returns the metrics of the last epoch averaged over its minibatches, as a dict of Python floats.
+
+    ``prefetch_next``: the NEXT rollout (host tensors, ideally pinned).  Its host-to-device copy is issued on a copy
+    stream into the idle staging set as soon as this update is enqueued, so it overlaps this update's kernels; the next
+    ``reppo_update`` call that is given that same mapping finds it staged (see ``reppo_prefetch``).
     """
     eng = _engine_for(cfg, train_state)
     h = cfg.hyperparameters
@@ -554,32 +609,39 @@ def reppo_update(train_state: TrainState, transition: Mapping[str, torch.Tensor]
 
     # Persistent device staging buffers: the rollout is copied INTO them (one async H2D per field from pinned host
     # memory), so every pointer the engine sees is stable across calls and the captured CUDA graph is replayed
-    # instead of being re-captured.
-    stage = eng.__dict__.setdefault("_stage", {})
+    # instead of being re-captured.  There are TWO staging sets: ``reppo_prefetch`` (or ``prefetch_next=``) copies the
+    # next rollout into the idle set on a copy stream while this update runs; the engine keeps one graph per set.
+    pf = eng.__dict__.get("_prefetched")
+    if pf is not None and pf["src"] is transition:
+        si, staged = pf["set"], True
+        torch.cuda.current_stream(dev).wait_event(pf["event"])
+        eng._prefetched = None
+    else:
+        si, staged = eng.__dict__.get("_stage_set", 0), False
+    eng._stage_set = si
+    stage = _stage_dict(eng, si)
+    shared = _stage_dict(eng, -1)   # per-update scratch that is not part of the rollout (same pointers for both sets)
 
-    def buf(name, shape, dtype=torch.float32):
-        t = stage.get(name)
+    def buf(name, shape, dtype=torch.float32, where=None):
+        d = stage if where is None else where
+        t = d.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
             t = torch.empty(shape, dtype=dtype, device=dev)
-            stage[name] = t
+            d[name] = t
         return t
 
     def put(name, src, shape):
         dst = buf(name, shape)
-        dst.copy_(src.reshape(shape), non_blocking=True)
+        if not staged:
+            dst.copy_(src.reshape(shape), non_blocking=True)
         return dst
 
-    obs = put("obs", transition["observations"], (T, N, eng.cfg.obs_dim))
-    cobs = put("critic_obs", transition["critic_observations"], (T, N, eng._shape.critic_obs_dim))
-    act = put("action", transition["actions"], (T, N, A))
-    soft = put("soft_reward", transition["rewards"], (T, N))
-    nemb = put("next_emb", transition["next_embeddings"], (T, N, eng.cfg.critic_hidden_dim))
-    val = put("value", transition["next_values"], (T, N))
-    done = put("done", transition["dones"], (T, N))
-    trunc = put("truncated", transition["truncations"], (T, N))
-    has = (lambda k: k in transition)
-    raw = put("reward", transition["raw_rewards"], (T, N)) if has("raw_rewards") else (soft if conv == "jax" else None)
-    iw = put("iw", transition["importance_weight"], (T, N)) if (has("importance_weight") and conv == "jax") else None
+    fields = _rollout_fields(eng, transition, T, N)
+    placed = {name: put(name, transition[key], shape) for name, key, shape in fields}
+    obs, cobs, act, soft = placed["obs"], placed["critic_obs"], placed["action"], placed["soft_reward"]
+    nemb, val, done, trunc = placed["next_emb"], placed["value"], placed["done"], placed["truncated"]
+    raw = placed.get("reward", soft if conv == "jax" else None)
+    iw = placed.get("iw")
     target = buf("target", (T, N))
     eng.td_lambda(soft, val, done, trunc, iw, float(h.gamma), float(h.lmbda), convention=conv, out=target)
     if conv == "torch":
@@ -591,14 +653,14 @@ def reppo_update(train_state: TrainState, transition: Mapping[str, torch.Tensor]
     if conv == "jax":
         eng.sync_actor_old()  # actor_target <- actor at the START of learn_step (src/jaxrl/reppo.py:457-464)
     per_mb = conv == "torch"
-    pbuf = buf("perms", (E, S), torch.int32)
+    pbuf = buf("perms", (E, S), torch.int32, shared)
     if perms is None:
         for e in range(E):
             pbuf[e].copy_(torch.randperm(S, device=dev, generator=generator))
     else:
         pbuf.copy_(perms.to(torch.int32), non_blocking=True)
-    e1 = buf("eps_pi", (E, n_mb, mb, A) if per_mb else (E, mb, A))
-    e2 = buf("eps_kl", (E, n_mb, ks, mb, A) if per_mb else (E, ks, mb, A))
+    e1 = buf("eps_pi", (E, n_mb, mb, A) if per_mb else (E, mb, A), where=shared)
+    e2 = buf("eps_kl", (E, n_mb, ks, mb, A) if per_mb else (E, ks, mb, A), where=shared)
     if eps_pi is None:
         e1.normal_(generator=generator)
     else:
@@ -611,8 +673,16 @@ def reppo_update(train_state: TrainState, transition: Mapping[str, torch.Tensor]
     graph = bool(b200.get("use_graph", True)) if use_graph is None else use_graph
     hyp = _hyper(cfg, train_state)
     hyp.world_size = world_size  # data-parallel ranks sharing every minibatch (gradients all-reduced by the engine)
-    m, sm = eng.update(batch, pbuf, e1, e2, hyp, n_mb, use_graph=graph, step_metrics=buf("step_metrics", (E * n_mb, L.NUM_METRICS)))
+    m, sm = eng.update(batch, pbuf, e1, e2, hyp, n_mb, use_graph=graph, step_metrics=buf("step_metrics", (E * n_mb, L.NUM_METRICS), where=shared))
     eng.sync_actor_old()  # src/torchrl/reppo.py:631-632 (same state as the JAX ordering at the next call)
+    # this staging set is free again once everything enqueued so far has run
+    free = eng.__dict__.setdefault("_stage_free", {})
+    ev = free.get(si)
+    if ev is None:
+        ev = free[si] = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    if prefetch_next is not None:
+        reppo_prefetch(train_state, prefetch_next, cfg)
     if return_device_metrics:
         return m, sm
     md = eng.metrics_dict(m)  # one device->host read per update
