@@ -60,11 +60,11 @@ def load_traffic():
     return d.get("dram_bytes_per_launch_mean"), os.path.basename(files[-1])
 
 
-def make_cfg(name, semantics):
+def make_cfg(name, semantics, more=()):
     from reppo_b200.config import compose
     env, ov, D, A, term, rs, extra = CONFIGS[name]
     overrides = [f"env={env}", f"experiment_overrides={ov}", f"b200.semantics={semantics}"]
-    overrides += [f"hyperparameters.{k}={v}" for k, v in extra.items()]
+    overrides += [f"hyperparameters.{k}={v}" for k, v in extra.items()] + list(more)
     cfg = compose(overrides)
     return cfg, D, A, term, rs
 
@@ -219,9 +219,14 @@ def main():
     ap.add_argument("--gemm", default=os.environ.get("REPPO_GEMM", "bf16"), choices=["fp32", "bf16"],
                     help="bf16 = tcgen05 tensor-core path (bf16 operands, fp32 accumulate; the product); fp32 = FFMA reference-precision mode")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--override", action="append", default=[], metavar="KEY=VALUE",
+                    help="extra hydra-style override for experiments, e.g. hyperparameters.num_epochs=4 (not the named workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large", action="store_true", help="skip the large-shape GEMM leg (C5 sweep shapes)")
     ap.add_argument("--profile-only", action="store_true", help="warm-up + one update, no timing legs (for ncu)")
+    ap.add_argument("--timeline", default=None, metavar="CSV",
+                    help="warm-up, then ONE update under the CUPTI kernel tracer (torch.profiler): per-kernel in-situ start / "
+                         "duration / stream written to CSV, summarised by tools/timeline_summary.py; no timing legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -242,7 +247,7 @@ def main():
     dev = torch.device(f"cuda:{local}")
     peaks = load_peaks()
 
-    cfg, D, A, term, rs = make_cfg(args.config, args.semantics)
+    cfg, D, A, term, rs = make_cfg(args.config, args.semantics, args.override)
     if args.gemm == "bf16":
         cfg.platform.amp_dtype = "bf16"
     h = cfg.hyperparameters
@@ -292,6 +297,25 @@ def main():
     if args.profile_only:
         one_update()
         torch.cuda.synchronize()
+        return
+    if args.timeline:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            one_update()
+            torch.cuda.synchronize()
+        rows = []
+        for ev in prof.profiler.kineto_results.events():
+            if "cuda" in str(ev.device_type()).lower():
+                rows.append((ev.start_ns() / 1e3, ev.duration_ns() / 1e3, ev.device_resource_id(), ev.name()))
+        rows.sort()
+        import csv
+        with open(args.timeline, "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(["start_us", "dur_us", "stream", "name"])
+            t0_ = rows[0][0] if rows else 0
+            for st_, du_, dv_, nm_ in rows:
+                w.writerow([round(st_ - t0_, 3), round(du_, 3), dv_, nm_[:100]])
+        print(json.dumps({"timeline": args.timeline, "kernels": len(rows)}))
         return
     launches_per_update = eng.launch_count() + 2  # + scan + actor_old copy
     sampler = ClockSampler(local)
