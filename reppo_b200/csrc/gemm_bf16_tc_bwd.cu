@@ -331,7 +331,10 @@ cudaError_t launch_gemm_bf16_tc_bwd(int norm, int M, int N, int K, const void* d
                                     cudaStream_t st) {
   // measured at C2 (r01): 116.0 ms per update fused vs 111.6 ms with the separate dgrad + row kernels -- the 8-warp epilogue of a
   // one-CTA-per-SM tcgen05 kernel is slower at this elementwise work than a full-occupancy row kernel.  Opt-in.
-  const bool off = getenv("REPPO_FUSE_BWD") == nullptr;   // read per launch (launches are captured into the graph once)
+  // REPPO_FUSE_BWD=1: every eligible layer; =2: only passes through a frozen network (no column-sum atomics in the epilogue)
+  const char* env = getenv("REPPO_FUSE_BWD");   // read per launch (launches are captured into the graph once)
+  const int fmode = env ? atoi(env) : 0;
+  const bool off = fmode == 0 || (fmode == 2 && (g_gamma != nullptr || g_beta != nullptr || g_bias != nullptr));
   if (off || M <= 0 || N % SB_N != 0 || (norm != NORM_NONE && N / SB_N > 8) || (ld_twin & 3) || z == nullptr || dz_twin == nullptr)
     return cudaErrorNotSupported;
   if ((reinterpret_cast<uintptr_t>(z) & 15) || (addend != nullptr && (reinterpret_cast<uintptr_t>(addend) & 15)))

@@ -5,6 +5,7 @@
 // increment; (2) every block re-reduces the <= kMaxPartials partials, derives the clip scale and
 // the bias corrections, and streams its slice: 28 B per parameter (read g,p,m,v; write p,m,v).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -103,7 +104,9 @@ cudaError_t launch_clip_adam(const float* p_in, float* p, float* g, float* m, fl
                              const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out, int zero_grads, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   const long long want = (n / 4 + 255) / 256;
-  int blocks = static_cast<int>(want < kMaxPartials ? want : kMaxPartials);
+  static const int cap_env = getenv("REPPO_ADAM_BLOCKS") ? atoi(getenv("REPPO_ADAM_BLOCKS")) : 0;   // experiment knob
+  const int cap = (cap_env > 0 && cap_env < kMaxPartials) ? cap_env : kMaxPartials;
+  int blocks = static_cast<int>(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
   launch_k((sumsq_partial_kernel), dim3(blocks), dim3(256), 0, st, g, n, partials, step);
   ShadowTable sh{};
