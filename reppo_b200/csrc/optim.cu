@@ -59,12 +59,14 @@ adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __restric
   __syncthreads();
   const float scale = s_scale, bc1 = s_bc1, bc2 = s_bc2;
   const float decay = 1.f - c.lr * c.weight_decay;
-  auto upd = [&](float& pp, float gg, float& mm, float& vv, long long idx) {
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
     gg *= scale;
     mm = c.b1 * mm + (1.f - c.b1) * gg;
     vv = c.b2 * vv + (1.f - c.b2) * gg * gg;
     pp = pp * decay - c.lr * (mm / bc1) / (sqrtf(vv / bc2) + c.eps);
-    // re-round the updated master weight into the bf16 operand shadow W[out, ld] of the tcgen05 GEMMs
+  };
+  // re-round updated master weights into the bf16 operand shadow W[out, ld] of the tcgen05 GEMMs (one element)
+  auto shadow1 = [&](float pp, long long idx) {
     for (int t = 0; t < sh.n; ++t) {
       if (idx >= sh.e[t].start && idx < sh.e[t].end) {
         const int off = static_cast<int>(idx - sh.e[t].start);
@@ -87,14 +89,40 @@ adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __restric
     float4 pp = pi4[i], mm = m4[i], vv = v4[i];
     const float4 gg = g4[i];
     if (zero_grads) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // the next step accumulates into a clean arena (no memset node)
-    upd(pp.x, gg.x, mm.x, vv.x, 4 * i); upd(pp.y, gg.y, mm.y, vv.y, 4 * i + 1); upd(pp.z, gg.z, mm.z, vv.z, 4 * i + 2);
-    upd(pp.w, gg.w, mm.w, vv.w, 4 * i + 3);
+    upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
     p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    if (sh.n > 0) {
+      // one table search per float4: the four elements almost always sit in one row of one weight matrix
+      const long long idx = 4 * i;
+      bool done = false;
+      for (int t = 0; t < sh.n; ++t) {
+        if (idx >= sh.e[t].start && idx + 3 < sh.e[t].end) {
+          const int off = static_cast<int>(idx - sh.e[t].start);
+          const int r = off / sh.e[t].in, col = off - r * sh.e[t].in;
+          if (col + 3 < sh.e[t].in && sh.e[t].dst_t == nullptr) {
+            __nv_bfloat16* d = static_cast<__nv_bfloat16*>(sh.e[t].dst) + static_cast<size_t>(r) * sh.e[t].ld + col;
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+            if ((reinterpret_cast<uintptr_t>(d) & 7) == 0) {
+              uint2 u;
+              u.x = *reinterpret_cast<const uint32_t*>(&lo);
+              u.y = *reinterpret_cast<const uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(d) = u;
+            } else {
+              d[0] = __low2bfloat16(lo); d[1] = __high2bfloat16(lo); d[2] = __low2bfloat16(hi); d[3] = __high2bfloat16(hi);
+            }
+            done = true;
+          }
+          break;
+        }
+      }
+      if (!done) { shadow1(pp.x, idx); shadow1(pp.y, idx + 1); shadow1(pp.z, idx + 2); shadow1(pp.w, idx + 3); }
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long long i = (n4 << 2) + threadIdx.x;
     float pp = p_in[i];
-    upd(pp, g[i], m[i], v[i], i);
+    upd(pp, g[i], m[i], v[i]);
+    shadow1(pp, i);
     p[i] = pp;
     if (zero_grads) g[i] = 0.f;
   }
