@@ -229,6 +229,8 @@ def main():
                     help="warm-up, then ONE update under the CUPTI kernel tracer (torch.profiler): per-kernel in-situ start / "
                          "duration / stream written to CSV, summarised by tools/timeline_summary.py; no timing legs")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         return run_reference(args)
 
