@@ -516,3 +516,46 @@ def test_named_config_shapes(name, gemm_mode):
         _grad_close(f"actor.{k}", got, gref, rel=rel_a)
         if gref.numel() > 8:
             assert _cos(got, gref) >= cos_min, k
+
+
+# ---------------------------------------------------------------------------------------------
+# Minibatches large enough for the persistent CTA-pair GEMM (gemm_bf16_tc2.cu: >= 56 pair tiles), the unfused
+# norm path it selects and the wide-row norm backward (H = 1024): one minibatch's gradients against the oracle.
+# ---------------------------------------------------------------------------------------------
+LARGE_MB = {
+    "mb16384_H256": dict(num_steps=8, num_envs=2048, num_mini_batches=1, num_epochs=1, obs_dim=17, critic_obs_dim=17,
+                         action_dim=6, critic_hidden_dim=256, actor_hidden_dim=256, num_bins=151, vmin=0.0, vmax=150.0),
+    "mb4096_H1024": dict(num_steps=4, num_envs=1024, num_mini_batches=1, num_epochs=1, obs_dim=17, critic_obs_dim=17,
+                         action_dim=6, critic_hidden_dim=1024, actor_hidden_dim=1024, num_bins=151, vmin=0.0, vmax=150.0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LARGE_MB))
+def test_large_minibatch_pair_gemm_path(name):
+    hp = O.Hyper(**LARGE_MB[name])
+    sem = O.JAX
+    cp, ap, ap_old, flat, eps_pi, eps_kl, perms = _setup(hp, sem, terminate=False)
+    eng = _engine(hp, sem, gemm_mode="bf16")
+    eng.load_params(cp, ap)
+    for k in eng.actor.layout:
+        eng.actor.view(eng.actor_old, k).copy_(ap_old[k])
+    hyp = _hyper(hp)
+    batch = eng.make_batch(flat)
+    idx = perms[0, :hp.minibatch_size]
+    mb = O.take(flat, idx)
+    m = eng.metrics_dict(eng.critic_grad(batch, idx, hyp))
+    loss, _, grads = O._value_and_grad(lambda p: O.critic_loss(p, mb, hp, sem), cp)
+    assert math.isclose(m["critic_loss"], loss.item(), rel_tol=2e-2, abs_tol=1e-6)
+    for k, gref in grads.items():
+        got = eng.critic.view(eng.critic.grads, k)
+        _grad_close(f"critic.{k}", got, gref, rel=4e-2)
+        if gref.numel() > 8:
+            assert _cos(got, gref) >= 0.998, k
+    m = eng.metrics_dict(eng.actor_grad(batch, idx, eps_pi[0], eps_kl[0], hyp))
+    loss, _, grads = O._value_and_grad(lambda p: O.actor_loss(p, ap_old, cp, mb, eps_pi[0], eps_kl[0], hp, sem), ap)
+    assert math.isclose(m["actor_loss"], loss.item(), rel_tol=2e-2, abs_tol=2e-3)
+    for k, gref in grads.items():
+        got = eng.actor.view(eng.actor.grads, k)
+        _grad_close(f"actor.{k}", got, gref, rel=8e-2)
+        if gref.numel() > 8:
+            assert _cos(got, gref) >= 0.998, k
