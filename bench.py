@@ -42,6 +42,16 @@ CONFIGS = {
 }
 
 
+_RESULT_OUT = None
+
+
+def emit(obj):
+    """The one JSON line of this run, on the real stdout."""
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -194,7 +204,7 @@ def run_reference(args):
         "note": "jax/flax/optax are not installable in this image and /root/reference does not exist on the GPU box: "
                 "this arm times oracle/reppo_oracle.py (CPU restatement of the reference update) on all host cores",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(name, cfg, D, A, world):
@@ -229,8 +239,13 @@ def main():
                     help="warm-up, then ONE update under the CUPTI kernel tracer (torch.profiler): per-kernel in-situ start / "
                          "duration / stream written to CSV, summarised by tools/timeline_summary.py; no timing legs")
     args = ap.parse_args()
-    # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line.  Native libraries write to file descriptor 1 behind Python's back (NCCL prints
+    # its version banner there when NCCL_DEBUG=VERSION and ignores NCCL_DEBUG_FILE at that level), so fd 1 is pointed at
+    # stderr for the whole run and the result line goes to a private duplicate of the original stdout.
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -318,7 +333,7 @@ def main():
             t0_ = rows[0][0] if rows else 0
             for st_, du_, dv_, nm_ in rows:
                 w.writerow([round(st_ - t0_, 3), round(du_, 3), dv_, nm_[:100]])
-        print(json.dumps({"timeline": args.timeline, "kernels": len(rows)}))
+        emit({"timeline": args.timeline, "kernels": len(rows)})
         return
     launches_per_update = eng.launch_count() + 2  # + scan + actor_old copy
     sampler = ClockSampler(local)
@@ -539,7 +554,7 @@ def main():
         "knobs": {k: os.environ[k] for k in os.environ if k.startswith("REPPO_")},
         "final_metrics": {k: final_metrics[k] for k in ("critic_loss", "actor_loss", "kl", "entropy")},
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

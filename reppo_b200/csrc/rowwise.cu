@@ -564,7 +564,8 @@ static cudaError_t launch_bwd_norm(const float* dx, const float* dx2, const floa
   if ((H == 1024 || H == 2048) && (ldh % 4 == 0) && getenv("REPPO_NO_WIDE") == nullptr) {
     // wide rows: 2 / 4 warps per row, ~8 blocks per SM worth of work items so that the tail is short
     const int rpi = H == 1024 ? 4 : 2;
-    int rpb = (rows + 148 * 8 - 1) / (148 * 8);
+    static const int bps = getenv("REPPO_WIDE_BPS") ? atoi(getenv("REPPO_WIDE_BPS")) : 8;   // blocks per SM worth of work items
+    int rpb = (rows + 148 * bps - 1) / (148 * bps);
     rpb = ((rpb + rpi - 1) / rpi) * rpi;
     if (rpb < 2 * rpi) rpb = 2 * rpi;
     const int gridw = (rows + rpb - 1) / rpb;
