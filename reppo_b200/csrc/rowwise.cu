@@ -562,9 +562,10 @@ static cudaError_t launch_bwd_norm(const float* dx, const float* dx2, const floa
   while ((rows + rows_per_block - 1) / rows_per_block > 148 * 4 && rows_per_block < 128) rows_per_block *= 2;
   const bool vec = (H % 128 == 0) && H <= 1024 && (ldh % 4 == 0) && getenv("REPPO_NO_VEC") == nullptr;
   if ((H == 1024 || H == 2048) && (ldh % 4 == 0) && getenv("REPPO_NO_WIDE") == nullptr) {
-    // wide rows: 2 / 4 warps per row, ~8 blocks per SM worth of work items so that the tail is short
+    // wide rows: 2 / 4 warps per row; two blocks per SM worth of work items (C5: 225.7 ms, vs 227.8 / 228.2 / 230.2 at 4 / 8 / 16:
+    // fewer blocks = fewer column-sum atomics)
     const int rpi = H == 1024 ? 4 : 2;
-    static const int bps = getenv("REPPO_WIDE_BPS") ? atoi(getenv("REPPO_WIDE_BPS")) : 8;   // blocks per SM worth of work items
+    static const int bps = getenv("REPPO_WIDE_BPS") ? atoi(getenv("REPPO_WIDE_BPS")) : 2;   // blocks per SM worth of work items
     int rpb = (rows + 148 * bps - 1) / (148 * bps);
     rpb = ((rpb + rpi - 1) / rpi) * rpi;
     if (rpb < 2 * rpi) rpb = 2 * rpi;
