@@ -523,6 +523,34 @@ def main():
                                  "algorithmic_bytes": "3 reads (mean pass, variance pass, apply) + 1 write of the batch"}}
     del big_obs
 
+    # loss / sampling kernels at a row count where they move more than L2 holds (S = 1M rows): HBM GB/s against the measured
+    # copy bandwidth (algorithmic bytes per row: SURVEY 8(d))
+    loss_kernels = None
+    if not args.no_large:
+        R_ = 1 << 20
+        Bn, Pn, Hn = hp.num_bins, Hc + (1 if args.semantics == "jax" else 0), Hc
+        probes = []
+        def probe(name, which, ins, out, scratch, bytes_per_row):
+            t_ms = time_fn(lambda: eng.kernel_probe(which, ins[0], ins[1], ins[2], ins[3], out, scratch, hyp), 10)
+            gbs = bytes_per_row * R_ / (t_ms * 1e-3) / 1e9
+            probes.append({"kernel": name, "rows": R_, "ms": t_ms, "algorithmic_bytes_per_row": bytes_per_row, "achieved": gbs,
+                           "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"]})
+        x_ = torch.randn(R_, Bn, device=dev); o_ = torch.empty(R_, Bn, device=dev)
+        tg_ = float(h.vmin) + (float(h.vmax) - float(h.vmin)) * torch.rand(R_, device=dev)
+        probe("critic_ce_kernel", 0, (x_, tg_, torch.zeros(R_, device=dev), torch.zeros(Bn, device=dev)), o_,
+              torch.zeros(24 + 2 * Bn, device=dev), 2.0 * Bn * 4 + 12)
+        del x_, o_, tg_
+        x_ = torch.randn(R_, Pn, device=dev); ne_ = torch.randn(R_, Hn, device=dev); o_ = torch.empty(R_, Pn, device=dev)
+        probe("critic_aux_kernel", 1, (x_, ne_, torch.rand(R_, device=dev), torch.zeros(R_, device=dev)), o_,
+              torch.zeros(24 + Pn, device=dev), (2.0 * Pn + Hn) * 4 + 8)
+        del x_, ne_, o_
+        x_ = 0.3 * torch.randn(R_, 2 * A, device=dev); xo_ = 0.3 * torch.randn(R_, 2 * A, device=dev)
+        probe("actor_sample_kernel", 2, (x_, xo_, torch.randn(R_, A, device=dev), torch.randn(16, R_, A, device=dev)),
+              torch.empty(R_, A, device=dev), torch.zeros(R_ * (2 + 2 * A), device=dev), (2 * 2 * A + A + 16 * A + A + 2 + 2 * A) * 4.0)
+        del x_, xo_
+        torch.cuda.empty_cache()
+        loss_kernels = {"bound": "hbm", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})", "kernels": probes}
+
     # the large Linear shapes of the wide-net / 256k-sample sweep (BASELINE.json configs[4]): persistent
     # CTA-pair tcgen05 kernel (gemm_bf16_tc2.cu), each GEMM timed alone against the measured bf16 BURST peak
     gemm_large = None
@@ -549,7 +577,7 @@ def main():
         "config": workload_config(args.config, cfg, D, A, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_update * args.steps),
         "launches_per_update": int(launches_per_update), "cuda_graph": use_graph, "semantics": args.semantics,
-        "sample_visits_per_s": value * E, "roofline": roofline, "gemm_large": gemm_large, "scan": scan, "adam": adam, "rollout": rollout,
+        "sample_visits_per_s": value * E, "roofline": roofline, "gemm_large": gemm_large, "loss_kernels": loss_kernels, "scan": scan, "adam": adam, "rollout": rollout,
         "cpu_baseline": cpu,
         "knobs": {k: os.environ[k] for k in os.environ if k.startswith("REPPO_")},
         "final_metrics": {k: final_metrics[k] for k in ("critic_loss", "actor_loss", "kl", "entropy")},

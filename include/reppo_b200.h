@@ -211,6 +211,20 @@ int reppo_bootstrap(reppo_ctx* ctx, const float* actor_params, const float* crit
 int reppo_linear(reppo_ctx* ctx, int32_t op, int32_t rows, int32_t in_features, int32_t out_features, const float* a,
                  const float* b, float* c, const float* bias, reppo_stream stream);
 
+/* Roofline probe of the memory-bound loss / sampling kernels of one minibatch step at an arbitrary row count (bench.py's
+ * `loss_kernels` leg and the kernel tests; not a reference entry point).  Every buffer is caller-owned device memory.
+ *   which 0  HL-Gauss cross-entropy (critic_loss_fn, src/jaxrl/reppo.py:474-513; hl_gauss src/jaxrl/utils.py:43-59):
+ *            in0 = head output [rows, B], in1 = target [rows], in2 = truncated [rows], in3 = zero_dist [B];
+ *            out0 = d logits [rows, B]; scratch >= 24 + 2 B floats
+ *   which 1  next-embedding (+ reward) regression (src/jaxrl/reppo.py:491-507):
+ *            in0 = pred [rows, P] (P = H + 1 JAX / H Torch), in1 = next_emb [rows, H], in2 = reward [rows], in3 = done [rows];
+ *            out0 = d pred [rows, P]; scratch >= 24 + P floats
+ *   which 2  tanh-Gaussian sample, log-prob and 16-sample KL to the behaviour policy (actor_loss, src/jaxrl/reppo.py:526-571):
+ *            in0 = policy output [rows, 2A], in1 = behaviour-policy output [rows, 2A], in2 = eps_pi [rows, A],
+ *            in3 = eps_kl [kl_samples, rows, A]; out0 = action [rows, A]; scratch >= rows * (2 + 2 A) floats */
+int reppo_kernel_probe(reppo_ctx* ctx, int32_t which, int32_t rows, const float* in0, const float* in1, const float* in2,
+                       const float* in3, float* out0, float* scratch, const reppo_hyper* hyper, reppo_stream stream);
+
 /* ---- one minibatch step ---------------------------------------------------------------------
  * update_critic, src/torchrl/reppo.py:227-283  == critic_loss_fn + apply_gradients,
  * src/jaxrl/reppo.py:474-524,624-626.  idx: [mb] int32 rows of `batch` (device). */

@@ -85,6 +85,7 @@ SYMBOLS = {
     "reppo_policy_act": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _f, _f, _i32, _vp, _vp, _vp, _vp]),
     "reppo_bootstrap": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "reppo_linear": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "reppo_kernel_probe": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "reppo_critic_step": (C.c_int, [_vp, C.POINTER(State), C.POINTER(Batch), _vp, _i32, C.POINTER(Hyper), _vp, _vp]),
     "reppo_actor_step": (C.c_int, [_vp, C.POINTER(State), C.POINTER(Batch), _vp, _i32, _vp, _vp, C.POINTER(Hyper), _vp, _vp]),
     "reppo_critic_grad": (C.c_int, [_vp, C.POINTER(State), C.POINTER(Batch), _vp, _i32, C.POINTER(Hyper), _vp, _vp]),

@@ -1341,6 +1341,35 @@ int reppo_linear(reppo_ctx* c, int32_t op, int32_t rows, int32_t in_f, int32_t o
 }
 
 
+int reppo_kernel_probe(reppo_ctx* c, int32_t which, int32_t rows, const float* in0, const float* in1, const float* in2,
+                       const float* in3, float* out0, float* scratch, const reppo_hyper* hp, reppo_stream stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!c || !in0 || !in1 || !in2 || !in3 || !out0 || !scratch || !hp || rows <= 0 || which < 0 || which > 2)
+    return fail(c, REPPO_ERR_INVALID, "reppo_kernel_probe: bad argument");
+  const reppo_shape& sh = c->shape;
+  const float inv = 1.f / static_cast<float>(rows);
+  c->launches = 0;
+  if (which == 0) {
+    const int B = sh.num_bins;
+    CK(launch_critic_ce(in0, B, in3, c->hl, in1, in2, nullptr, rows, inv, 0, out0, scratch, nullptr, 0, scratch + M_NUM,
+                        scratch + M_NUM + B, st));
+  } else if (which == 1) {
+    const int H = sh.critic_hidden;
+    CK(launch_critic_aux(in0, c->pred_out, H, c->sem.reward_head, c->sem.aux_mask_done, in1, in2, in3, in3, nullptr, rows, inv, 0,
+                         hp->aux_loss_mult, out0, scratch, nullptr, 0, scratch + M_NUM, st));
+  } else {
+    const int A = sh.action_dim;
+    const ActorConsts ac = actor_consts(c, hp);
+    float* logp = scratch;
+    float* kl = scratch + rows;
+    float* gmu = scratch + 2 * static_cast<size_t>(rows);
+    float* gsig = gmu + static_cast<size_t>(rows) * A;
+    CK(launch_actor_sample(in0, in1, nullptr, in2, in3, rows, A, sh.kl_samples, ac, out0, A, logp, kl, gmu, gsig, nullptr, 0, st));
+  }
+  ++c->launches;
+  return REPPO_OK;
+}
+
 // ---- rollout side -----------------------------------------------------------------------------
 int reppo_obs_normalize(const float* x, int64_t rows, int32_t dim, float* mean, float* var, float* std, int64_t* count, float eps,
                         int32_t update, int32_t center, int64_t until, float* out, reppo_stream stream) {

@@ -8,18 +8,21 @@ constexpr int kMaxBinsPerLane = 8;  // num_bins <= 256
 constexpr float kLog2 = 0.6931471805599453f;
 constexpr float kHalfLog2Pi = 0.9189385332046727f;
 
-struct RowSoftmax {
-  float p[kMaxBinsPerLane];
-  float lg[kMaxBinsPerLane];
+template <int NB>
+struct RowSoftmaxT {
+  float p[NB];
+  float lg[NB];
   float lse, value;
 };
+using RowSoftmax = RowSoftmaxT<kMaxBinsPerLane>;
 
-// logits = head + bias_scale * zero_dist; softmax; value = p . support
+// logits = head + bias_scale * zero_dist; softmax; value = p . support      (NB = bins per lane the caller unrolls for)
+template <int NB>
 REPPO_DEVINL void row_softmax(const float* __restrict__ head_row, const float* __restrict__ zero_dist,
-                              const float* __restrict__ support, float bias_scale, int B, int lane, RowSoftmax& o) {
+                              const float* __restrict__ support, float bias_scale, int B, int lane, RowSoftmaxT<NB>& o) {
   float m = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < kMaxBinsPerLane; ++j) {
+  for (int j = 0; j < NB; ++j) {
     const int c = lane + 32 * j;
     o.lg[j] = (c < B) ? head_row[c] + bias_scale * zero_dist[c] : -INFINITY;
     m = fmaxf(m, o.lg[j]);
@@ -27,7 +30,7 @@ REPPO_DEVINL void row_softmax(const float* __restrict__ head_row, const float* _
   m = warp_max(m);
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < kMaxBinsPerLane; ++j) {
+  for (int j = 0; j < NB; ++j) {
     const int c = lane + 32 * j;
     o.p[j] = (c < B) ? expf(o.lg[j] - m) : 0.f;
     s += o.p[j];
@@ -36,7 +39,7 @@ REPPO_DEVINL void row_softmax(const float* __restrict__ head_row, const float* _
   const float inv = 1.f / s;
   float v = 0.f;
 #pragma unroll
-  for (int j = 0; j < kMaxBinsPerLane; ++j) {
+  for (int j = 0; j < NB; ++j) {
     const int c = lane + 32 * j;
     o.p[j] *= inv;
     if (c < B) v += o.p[j] * support[c];

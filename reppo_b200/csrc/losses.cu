@@ -36,10 +36,12 @@ REPPO_DEVINL void block_metric_add(float (&vals)[NM], float* sm /* [8][NM] */, f
 }
 
 constexpr int kLossRowsPerBlock = 8;   // one row per warp: these kernels are latency-bound per row, parallelism wins
+constexpr int kLossMaxBlocks = 148 * 8;   // beyond that the blocks walk the rows grid-stride (large-batch sweep)
 
 // dbias (+)= column sums of dlogits (bias gradient of the head's last Linear); dzero (+)= bias_scale * the same
 // (gradient of zero_dist, which enters the logits as bias_scale * zero_dist).  Both nullable.
-__global__ void __launch_bounds__(256)
+template <int NB>   // bins per lane the row loops are unrolled for: ceil(num_bins / 32) <= NB
+__global__ void __launch_bounds__(256, NB <= 5 ? 4 : 3)
 critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __restrict__ zero_dist, HLConsts hl,
                  const float* __restrict__ target, const float* __restrict__ truncated, const int* __restrict__ idx,
                  int rows, float inv_rows, int no_mask, float* __restrict__ dlogits, float* __restrict__ metrics,
@@ -47,32 +49,42 @@ critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __rest
   REPPO_PDL_PROLOGUE();
   __shared__ float sm[8 * 5];
   __shared__ float smax[8], smin[8];
-  __shared__ float scol[8][32 * kMaxBinsPerLane];
+  __shared__ float scol[8][32 * NB];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int B = hl.num_bins;
   float vals[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   float tmax = -INFINITY, tmin = INFINITY;
-  float cs[kMaxBinsPerLane];
+  float cs[NB];
 #pragma unroll
-  for (int j = 0; j < kMaxBinsPerLane; ++j) cs[j] = 0.f;
-  for (int rr = 0; rr < kLossRowsPerBlock / 8; ++rr) {
-    const int row = blockIdx.x * kLossRowsPerBlock + rr * 8 + warp;
-    if (row >= rows) break;
+  for (int j = 0; j < NB; ++j) cs[j] = 0.f;
+  // grid-stride over rows (the launch caps the grid at a few blocks per SM): the per-block metric / column-sum atomics
+  // below are issued once per block, not once per 8 rows
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     const long long src = idx ? idx[row] : row;
     const float tgt = target[src];
     const float mask = no_mask ? 1.f : 1.f - truncated[src];
-    RowSoftmax sx;
+    RowSoftmaxT<NB> sx;
     row_softmax(head_out + static_cast<size_t>(row) * ld, zero_dist, hl.support, hl.bias_scale, B, lane, sx);
     // HL-Gauss histogram of the clipped target
     const float x = fminf(fmaxf(tgt, hl.vmin), hl.vmax);
     const float z = erff((hl.edges[B] - x) / hl.den) - erff((hl.edges[0] - x) / hl.den) + hl.z_eps;
-    float ce = 0.f, sum_tp = 0.f, tp[kMaxBinsPerLane];
+    float ce = 0.f, sum_tp = 0.f, tp[NB];
+    // erf at the lower edge of this lane's bins; the upper edge of bin c is the lower edge of bin c + 1 = the next lane's
+    // value (lane 31: this lane's value of the next group of 32 bins), so every edge is evaluated once
+    float lo_e[NB + 1];
 #pragma unroll
-    for (int j = 0; j < kMaxBinsPerLane; ++j) {
+    for (int j = 0; j <= NB; ++j) {
+      const int c = lane + 32 * j;
+      lo_e[j] = (c <= B) ? erff((hl.edges[c] - x) / hl.den) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
       const int c = lane + 32 * j;
       tp[j] = 0.f;
+      const float nxt = __shfl_down_sync(0xffffffffu, lo_e[j], 1);
+      const float wrap = __shfl_sync(0xffffffffu, lo_e[j + 1], 0);
       if (c < B) {
-        const float lo = erff((hl.edges[c] - x) / hl.den), hi = erff((hl.edges[c + 1] - x) / hl.den);
+        const float lo = lo_e[j], hi = (lane == 31) ? wrap : nxt;
         tp[j] = (hi - lo) / z;
         ce -= tp[j] * (sx.lg[j] - sx.lse);
         sum_tp += tp[j];
@@ -83,7 +95,7 @@ critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __rest
     const float coef = mask * inv_rows;
     float* drow = dlogits + static_cast<size_t>(row) * ld;
 #pragma unroll
-    for (int j = 0; j < kMaxBinsPerLane; ++j) {
+    for (int j = 0; j < NB; ++j) {
       const int c = lane + 32 * j;
       if (c < B) {
         const float o = coef * (sum_tp * sx.p[j] - tp[j]);
@@ -103,7 +115,7 @@ critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __rest
                    metrics + M_TARGET_MEAN};
   if (lane == 0) { smax[warp] = tmax; smin[warp] = tmin; }
 #pragma unroll
-  for (int j = 0; j < kMaxBinsPerLane; ++j) scol[warp][lane + 32 * j] = cs[j];
+  for (int j = 0; j < NB; ++j) scol[warp][lane + 32 * j] = cs[j];
   block_metric_add<5>(vals, sm, dst);   // contains the __syncthreads that publishes smax / smin / scol
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; ++w) { tmax = fmaxf(tmax, smax[w]); tmin = fminf(tmin, smin[w]); }
@@ -134,9 +146,7 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
   float vals[3] = {0.f, 0.f, 0.f};
   if (dbias != nullptr)
     for (int c = lane; c < P; c += 32) scol[warp * P + c] = 0.f;   // rows past the end contribute nothing
-  for (int rr = 0; rr < kLossRowsPerBlock / 8; ++rr) {
-    const int row = blockIdx.x * kLossRowsPerBlock + rr * 8 + warp;
-    if (row >= rows) break;
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     const long long src = idx ? idx[row] : row;
     const float mask = no_mask ? 1.f : 1.f - truncated[src];
     const float nd = mask_done ? 1.f - done[src] : 1.f;
@@ -151,7 +161,7 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
       const float d = pr[off + c] - ne[c];
       sq += d * d;
       dr[off + c] = g * d;
-      if (dbias != nullptr) scol[warp * P + off + c] = g * d;
+      if (dbias != nullptr) scol[warp * P + off + c] += g * d;
       if (dp_h != nullptr) dp_h[static_cast<size_t>(row) * ldh + off + c] = __float2bfloat16_rn(g * d);
     }
     float r = 0.f;
@@ -161,7 +171,7 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
         const float d = pr[0] - r;
         sq += d * d;
         dr[0] = g * d;
-        if (dbias != nullptr) scol[warp * P] = g * d;
+        if (dbias != nullptr) scol[warp * P] += g * d;
         if (dp_h != nullptr) dp_h[static_cast<size_t>(row) * ldh] = __float2bfloat16_rn(g * d);
       }
     }
@@ -402,7 +412,13 @@ cudaError_t launch_critic_ce(const float* head_out, int ld, const float* zero_di
                              const float* truncated, const int* idx, int rows, float inv_rows, int no_mask, float* dlogits,
                              float* metrics, void* dl_h, int ldh, float* dbias, float* dzero, cudaStream_t st) {
   if (hl.num_bins > 32 * kMaxBinsPerLane) return cudaErrorInvalidValue;
-  launch_k((critic_ce_kernel), dim3((rows + kLossRowsPerBlock - 1) / kLossRowsPerBlock), dim3(256), 0, st, head_out, ld, zero_dist, hl, target, truncated, idx, rows, inv_rows, no_mask, dlogits, metrics, static_cast<__nv_bfloat16*>(dl_h), ldh, dbias, dzero);
+  const int want = (rows + kLossRowsPerBlock - 1) / kLossRowsPerBlock;
+  const dim3 grid(want < kLossMaxBlocks ? want : kLossMaxBlocks);
+#define REPPO_CE(NB) launch_k((critic_ce_kernel<NB>), grid, dim3(256), 0, st, head_out, ld, zero_dist, hl, target, truncated, idx, rows, inv_rows, no_mask, dlogits, metrics, static_cast<__nv_bfloat16*>(dl_h), ldh, dbias, dzero)
+  if (hl.num_bins <= 64) REPPO_CE(2);
+  else if (hl.num_bins <= 160) REPPO_CE(5);
+  else REPPO_CE(8);
+#undef REPPO_CE
   return cudaGetLastError();
 }
 
@@ -419,7 +435,8 @@ cudaError_t launch_critic_aux(const float* pred, int P, int H, int reward_head, 
       configured = true;
     }
   }
-  launch_k((critic_aux_kernel), dim3((rows + kLossRowsPerBlock - 1) / kLossRowsPerBlock), dim3(256), smem, st, pred, P, H, reward_head, mask_done, next_emb, reward, done, truncated, idx, rows, inv_rows, no_mask, aux_mult, dpred, metrics, static_cast<__nv_bfloat16*>(dp_h), ldh, dbias);
+  const int want = (rows + kLossRowsPerBlock - 1) / kLossRowsPerBlock;
+  launch_k((critic_aux_kernel), dim3(want < kLossMaxBlocks ? want : kLossMaxBlocks), dim3(256), smem, st, pred, P, H, reward_head, mask_done, next_emb, reward, done, truncated, idx, rows, inv_rows, no_mask, aux_mult, dpred, metrics, static_cast<__nv_bfloat16*>(dp_h), ldh, dbias);
   return cudaGetLastError();
 }
 

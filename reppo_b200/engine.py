@@ -254,6 +254,16 @@ class ReppoEngine:
                                       bias.data_ptr() if bias is not None else None, self._stream()), self.ctx, "reppo_linear")
         return out
 
+    def kernel_probe(self, which: int, in0, in1, in2, in3, out0, scratch, hyper: "HyperParams") -> None:
+        """One loss / sampling kernel in isolation at any row count (reppo_kernel_probe): 0 = HL-Gauss cross-entropy,
+        1 = next-embedding regression, 2 = tanh-Gaussian sample + KL.  All tensors are caller-allocated fp32 CUDA."""
+        import ctypes as C
+        rows = int(in0.shape[0])
+        hs = hyper.c_struct()
+        L.check(self.lib.reppo_kernel_probe(self.ctx, which, rows, in0.data_ptr(), in1.data_ptr(), in2.data_ptr(), in3.data_ptr(),
+                                            out0.data_ptr(), scratch.data_ptr(), C.byref(hs), self._stream()), self.ctx,
+                "reppo_kernel_probe")
+
     # ---- rollout side (SURVEY.md 8(f)) ------------------------------------------------------------
     def policy_act(self, obs, eps, scale: Optional[torch.Tensor] = None, clip: float = 0.999, store_clipped: bool = False,
                    min_std: float = 0.0, params: Optional[torch.Tensor] = None, want_scaled: bool = False):

@@ -559,3 +559,26 @@ def test_large_minibatch_pair_gemm_path(name):
         _grad_close(f"actor.{k}", got, gref, rel=8e-2)
         if gref.numel() > 8:
             assert _cos(got, gref) >= 0.998, k
+
+
+def test_kernel_probe_cross_entropy_matches_oracle():
+    """reppo_kernel_probe(0): the fused HL-Gauss histogram + softmax cross-entropy kernel on free-standing buffers against
+    autograd through the oracle's restatement (the entry point bench.py's `loss_kernels` roofline leg times)."""
+    import torch.nn.functional as F
+    hp = O.Hyper(**SMALL)
+    sem = O.JAX
+    eng = _engine(hp, sem)
+    rows, B = 777, hp.num_bins
+    g = torch.Generator().manual_seed(5)
+    head = torch.randn(rows, B, generator=g)
+    zero = torch.rand(B, generator=g) * 0.1
+    target = hp.vmin + (hp.vmax - hp.vmin) * torch.rand(rows, generator=g)
+    trunc = (torch.rand(rows, generator=g) < 0.1).float()
+    h = head.clone().requires_grad_(True)
+    logits = h + sem.logit_bias_scale * zero
+    ce = -(O.hl_gauss_jax(target, B, hp.vmin, hp.vmax) * F.log_softmax(logits, dim=-1)).sum(-1)
+    ((1.0 - trunc) * ce).mean().backward()
+    out = torch.empty(rows, B, device="cuda")
+    scratch = torch.zeros(24 + 2 * B, device="cuda")
+    eng.kernel_probe(0, head.cuda(), target.cuda(), trunc.cuda(), zero.cuda(), out, scratch, _hyper(hp))
+    torch.testing.assert_close(out.cpu(), h.grad, rtol=2e-4, atol=2e-7)
