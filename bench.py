@@ -366,7 +366,7 @@ def main():
     # Input pipeline of the public API: the H2D copy of the NEXT rollout (prefetch_next) is issued inside every call and
     # overlaps that call's kernels (copy stream, second staging set).  Every timed step therefore still contains one full
     # 292 MB H2D and one metrics D2H; the clock stops only after the last copy has completed (barrier = device sync).
-    T.reppo_prefetch(ts, host, cfg)
+    T.reppo_prefetch(ts, host, cfg, generator=g)
     for _ in range(2):
         T.reppo_update(ts, host, cfg, generator=g, use_graph=use_graph, world_size=world, prefetch_next=host)
     barrier()

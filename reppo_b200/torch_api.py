@@ -550,12 +550,41 @@ def _rollout_fields(eng, transition, T: int, N: int):
     return fields
 
 
-def reppo_prefetch(train_state: TrainState, transition: Mapping[str, torch.Tensor], cfg) -> None:
+def _noise_shapes(eng, cfg):
+    h = cfg.hyperparameters
+    T, N, n_mb, E = int(h.num_steps), int(h.num_envs), int(h.num_mini_batches), int(h.num_epochs)
+    S = T * N
+    mb = S // n_mb
+    A, ks = eng.cfg.action_dim, eng.cfg.kl_samples
+    per_mb = eng.cfg.semantics == "torch"   # fresh draw per minibatch (Torch) / one draw per epoch (JAX)
+    return (E, S), ((E, n_mb, mb, A) if per_mb else (E, mb, A)), ((E, n_mb, ks, mb, A) if per_mb else (E, ks, mb, A))
+
+
+def _stage_buf(d: dict, name: str, shape, dtype, dev):
+    t = d.get(name)
+    if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+        t = d[name] = torch.empty(shape, dtype=dtype, device=dev)
+    return t
+
+
+def _draw_plan(stage: dict, eng, cfg, generator, dev):
+    """Minibatch permutations and actor noise of one update, drawn on the current stream into `stage`."""
+    ps, s1, s2 = _noise_shapes(eng, cfg)
+    pbuf = _stage_buf(stage, "perms", ps, torch.int32, dev)
+    for e in range(ps[0]):
+        pbuf[e].copy_(torch.randperm(ps[1], device=dev, generator=generator))
+    _stage_buf(stage, "eps_pi", s1, torch.float32, dev).normal_(generator=generator)
+    _stage_buf(stage, "eps_kl", s2, torch.float32, dev).normal_(generator=generator)
+
+
+def reppo_prefetch(train_state: TrainState, transition: Mapping[str, torch.Tensor], cfg, *,
+                   generator: Optional[torch.Generator] = None, draw_plan: bool = True) -> None:
     """Start the host-to-device copy of the NEXT rollout while the current update is still running.
 
     The copy goes into the staging set that the running update does not read, on a dedicated copy stream, after that
     set's previous update has finished; ``reppo_update`` called with the same ``transition`` object then skips its own
-    copies and waits for the copy's event instead.  (The reference keeps rollouts on the device, src/torchrl/reppo.py:
+    copies and waits for the copy's event instead.  With ``draw_plan`` the minibatch permutations and the actor noise of
+    that update are drawn on the copy stream as well (pass the generator the update calls use).  (The reference keeps rollouts on the device, src/torchrl/reppo.py:
     89-171; this is the input pipeline for hosts whose simulator is not on the GPU.)"""
     eng = _engine_for(cfg, train_state)
     h = cfg.hyperparameters
@@ -575,9 +604,12 @@ def reppo_prefetch(train_state: TrainState, transition: Mapping[str, torch.Tenso
             if t is None or tuple(t.shape) != tuple(shape):
                 t = stage[name] = torch.empty(shape, dtype=torch.float32, device=dev)
             t.copy_(transition[key].reshape(shape), non_blocking=True)
+        if draw_plan:
+            # the next update's permutations and noise are drawn here too (same generator, same order as the plain calls)
+            _draw_plan(stage, eng, cfg, generator, dev)
         ev = torch.cuda.Event()
         ev.record(cs)
-    eng._prefetched = {"src": transition, "set": si, "event": ev}
+    eng._prefetched = {"src": transition, "set": si, "event": ev, "plan": bool(draw_plan)}
 
 
 def reppo_update(train_state: TrainState, transition: Mapping[str, torch.Tensor], cfg, *,
@@ -612,8 +644,10 @@ def reppo_update(train_state: TrainState, transition: Mapping[str, torch.Tensor]
     # instead of being re-captured.  There are TWO staging sets: ``reppo_prefetch`` (or ``prefetch_next=``) copies the
     # next rollout into the idle set on a copy stream while this update runs; the engine keeps one graph per set.
     pf = eng.__dict__.get("_prefetched")
+    have_plan = False
     if pf is not None and pf["src"] is transition:
         si, staged = pf["set"], True
+        have_plan = pf.get("plan", False) and perms is None and eps_pi is None and eps_kl is None
         torch.cuda.current_stream(dev).wait_event(pf["event"])
         eng._prefetched = None
     else:
@@ -653,22 +687,25 @@ def reppo_update(train_state: TrainState, transition: Mapping[str, torch.Tensor]
     if conv == "jax":
         eng.sync_actor_old()  # actor_target <- actor at the START of learn_step (src/jaxrl/reppo.py:457-464)
     per_mb = conv == "torch"
-    pbuf = buf("perms", (E, S), torch.int32, shared)
-    if perms is None:
-        for e in range(E):
-            pbuf[e].copy_(torch.randperm(S, device=dev, generator=generator))
-    else:
-        pbuf.copy_(perms.to(torch.int32), non_blocking=True)
-    e1 = buf("eps_pi", (E, n_mb, mb, A) if per_mb else (E, mb, A), where=shared)
-    e2 = buf("eps_kl", (E, n_mb, ks, mb, A) if per_mb else (E, ks, mb, A), where=shared)
-    if eps_pi is None:
-        e1.normal_(generator=generator)
-    else:
-        e1.copy_(eps_pi.reshape(e1.shape), non_blocking=True)
-    if eps_kl is None:
-        e2.normal_(generator=generator)
-    else:
-        e2.copy_(eps_kl.reshape(e2.shape), non_blocking=True)
+    # permutations and noise live in the staging set (one captured graph per set): already drawn by reppo_prefetch,
+    # injected by the caller (parity tests), or drawn here
+    pbuf = buf("perms", (E, S), torch.int32)
+    e1 = buf("eps_pi", (E, n_mb, mb, A) if per_mb else (E, mb, A))
+    e2 = buf("eps_kl", (E, n_mb, ks, mb, A) if per_mb else (E, ks, mb, A))
+    if not have_plan:
+        if perms is None:
+            for e in range(E):
+                pbuf[e].copy_(torch.randperm(S, device=dev, generator=generator))
+        else:
+            pbuf.copy_(perms.to(torch.int32), non_blocking=True)
+        if eps_pi is None:
+            e1.normal_(generator=generator)
+        else:
+            e1.copy_(eps_pi.reshape(e1.shape), non_blocking=True)
+        if eps_kl is None:
+            e2.normal_(generator=generator)
+        else:
+            e2.copy_(eps_kl.reshape(e2.shape), non_blocking=True)
     b200 = cfg.get("b200", {}) if hasattr(cfg, "get") else {}
     graph = bool(b200.get("use_graph", True)) if use_graph is None else use_graph
     hyp = _hyper(cfg, train_state)
@@ -682,7 +719,7 @@ def reppo_update(train_state: TrainState, transition: Mapping[str, torch.Tensor]
         ev = free[si] = torch.cuda.Event()
     ev.record(torch.cuda.current_stream(dev))
     if prefetch_next is not None:
-        reppo_prefetch(train_state, prefetch_next, cfg)
+        reppo_prefetch(train_state, prefetch_next, cfg, generator=generator)
     if return_device_metrics:
         return m, sm
     md = eng.metrics_dict(m)  # one device->host read per update
