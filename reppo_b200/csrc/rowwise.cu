@@ -28,67 +28,75 @@ REPPO_DEVINL void store_bf16x4(__nv_bfloat16* p, float a, float b, float c, floa
 }
 
 // out[r, :] = [ a[idx[r], 0:da] | b[(b_is_local ? r : idx[r]), 0:db] ]   (idx may be NULL = identity)
-__global__ void gather_concat_kernel(const float* __restrict__ a, int da, const float* __restrict__ b, int db,
-                                     const int* __restrict__ idx, int b_is_local, int rows, float* __restrict__ out,
-                                     int out_ld, __nv_bfloat16* __restrict__ out_h, int out_ldh) {
+// One warp per row, lanes over columns: no integer division, 32-bit index arithmetic inside the row (these kernels sit
+// directly behind the Adam kernel on both chains; the flat-index version compiled to 30-55 KB of 64-bit div/mod code).
+__global__ void __launch_bounds__(256)
+gather_concat_kernel(const float* __restrict__ a, int da, const float* __restrict__ b, int db,
+                     const int* __restrict__ idx, int b_is_local, int rows, float* __restrict__ out,
+                     int out_ld, __nv_bfloat16* __restrict__ out_h, int out_ldh) {
   REPPO_PDL_PROLOGUE();
-  const int w = da + db;
-  const long long total = static_cast<long long>(rows) * w;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / w), c = static_cast<int>(i % w);
-    const long long src = idx ? idx[r] : r;
-    float v;
-    if (c < da) v = a[src * da + c];
-    else v = b[(b_is_local ? static_cast<long long>(r) : src) * db + (c - da)];
-    out[static_cast<long long>(r) * out_ld + c] = v;
-    if (out_h != nullptr) out_h[static_cast<long long>(r) * out_ldh + c] = __float2bfloat16_rn(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
+    const size_t src = idx ? static_cast<size_t>(idx[r]) : static_cast<size_t>(r);
+    const float* ar = a + src * da;
+    float* orow = out + static_cast<size_t>(r) * out_ld;
+    __nv_bfloat16* hrow = out_h ? out_h + static_cast<size_t>(r) * out_ldh : nullptr;
+    for (int c = lane; c < da; c += 32) {
+      const float v = ar[c];
+      orow[c] = v;
+      if (hrow != nullptr) hrow[c] = __float2bfloat16_rn(v);
+    }
+    if (db > 0) {
+      const float* br = b + (b_is_local ? static_cast<size_t>(r) : src) * db;
+      for (int c = lane; c < db; c += 32) {
+        const float v = br[c];
+        orow[da + c] = v;
+        if (hrow != nullptr) hrow[da + c] = __float2bfloat16_rn(v);
+      }
+    }
   }
 }
 
 cudaError_t launch_gather_concat(const float* a, int da, const float* b, int db, const int* idx, int b_is_local,
                                  int rows, float* out, int out_ld, void* out_h, int out_ldh, cudaStream_t st) {
-  const long long total = static_cast<long long>(rows) * (da + db);
-  if (total <= 0) return cudaSuccess;
-  const int block = 256;
-  const long long want = (total + block - 1) / block;
-  const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
-  launch_k((gather_concat_kernel), dim3(grid), dim3(block), 0, st, a, da, b, db, idx, b_is_local, rows, out, out_ld, static_cast<__nv_bfloat16*>(out_h), out_ldh);
+  if (rows <= 0 || da + db <= 0) return cudaSuccess;
+  const int want = (rows + 7) / 8;
+  const int grid = want < 148 * 8 ? want : 148 * 8;
+  launch_k((gather_concat_kernel), dim3(grid), dim3(256), 0, st, a, da, b, db, idx, b_is_local, rows, out, out_ld, static_cast<__nv_bfloat16*>(out_h), out_ldh);
   return cudaGetLastError();
 }
 
-__global__ void gather_pair_kernel(const float* __restrict__ a, int da, const float* __restrict__ b, int db,
-                                   const int* __restrict__ idx, int rows, float* __restrict__ out_a, int lda,
-                                   __nv_bfloat16* __restrict__ out_ah, int ldah, float* __restrict__ out_b, int ldb,
-                                   __nv_bfloat16* __restrict__ out_bh, int ldbh) {
+// two gathers through the same index in one launch: a[idx[r]] -> out_a (+ bf16 twin), b[idx[r]] -> out_b (+ bf16 twin)
+__global__ void __launch_bounds__(256)
+gather_pair_kernel(const float* __restrict__ a, int da, const float* __restrict__ b, int db,
+                   const int* __restrict__ idx, int rows, float* __restrict__ out_a, int lda,
+                   __nv_bfloat16* __restrict__ out_ah, int ldah, float* __restrict__ out_b, int ldb,
+                   __nv_bfloat16* __restrict__ out_bh, int ldbh) {
   REPPO_PDL_PROLOGUE();
-  const int w = da + db;
-  const long long total = static_cast<long long>(rows) * w;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / w), c = static_cast<int>(i % w);
-    const long long src = idx ? idx[r] : r;
-    if (c < da) {
-      const float v = a[src * da + c];
-      if (out_a != nullptr) out_a[static_cast<long long>(r) * lda + c] = v;
-      if (out_ah != nullptr) out_ah[static_cast<long long>(r) * ldah + c] = __float2bfloat16_rn(v);
-    } else {
-      const int cc = c - da;
-      const float v = b[src * db + cc];
-      if (out_b != nullptr) out_b[static_cast<long long>(r) * ldb + cc] = v;
-      if (out_bh != nullptr) out_bh[static_cast<long long>(r) * ldbh + cc] = __float2bfloat16_rn(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
+    const size_t src = idx ? static_cast<size_t>(idx[r]) : static_cast<size_t>(r);
+    const float* ar = a + src * da;
+    const float* br = b + src * db;
+    for (int c = lane; c < da; c += 32) {
+      const float v = ar[c];
+      if (out_a != nullptr) out_a[static_cast<size_t>(r) * lda + c] = v;
+      if (out_ah != nullptr) out_ah[static_cast<size_t>(r) * ldah + c] = __float2bfloat16_rn(v);
+    }
+    for (int c = lane; c < db; c += 32) {
+      const float v = br[c];
+      if (out_b != nullptr) out_b[static_cast<size_t>(r) * ldb + c] = v;
+      if (out_bh != nullptr) out_bh[static_cast<size_t>(r) * ldbh + c] = __float2bfloat16_rn(v);
     }
   }
 }
 
 cudaError_t launch_gather_pair(const float* a, int da, const float* b, int db, const int* idx, int rows, float* out_a, int lda,
                                void* out_ah, int ldah, float* out_b, int ldb, void* out_bh, int ldbh, cudaStream_t st) {
-  const long long total = static_cast<long long>(rows) * (da + db);
-  if (total <= 0) return cudaSuccess;
-  const int block = 256;
-  const long long want = (total + block - 1) / block;
-  const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
-  launch_k((gather_pair_kernel), dim3(grid), dim3(block), 0, st, a, da, b, db, idx, rows, out_a, lda,
+  if (rows <= 0 || da + db <= 0) return cudaSuccess;
+  const int want = (rows + 7) / 8;
+  const int grid = want < 148 * 8 ? want : 148 * 8;
+  launch_k((gather_pair_kernel), dim3(grid), dim3(256), 0, st, a, da, b, db, idx, rows, out_a, lda,
            static_cast<__nv_bfloat16*>(out_ah), ldah, out_b, ldb, static_cast<__nv_bfloat16*>(out_bh), ldbh);
   return cudaGetLastError();
 }
