@@ -582,3 +582,40 @@ def test_kernel_probe_cross_entropy_matches_oracle():
     scratch = torch.zeros(24 + 2 * B, device="cuda")
     eng.kernel_probe(0, head.cuda(), target.cuda(), trunc.cuda(), zero.cuda(), out, scratch, _hyper(hp))
     torch.testing.assert_close(out.cpu(), h.grad, rtol=2e-4, atol=2e-7)
+
+
+def test_kernel_probe_aux_regression_matches_autograd():
+    """reppo_kernel_probe(1): next-embedding (+ reward, JAX: slot 0 of the prediction head) regression and d pred on
+    free-standing buffers against autograd of the restated loss term (src/jaxrl/reppo.py:491-507)."""
+    hp = O.Hyper(**SMALL)
+    sem = O.JAX
+    eng = _engine(hp, sem)
+    rows, H = 513, hp.critic_hidden_dim
+    P = H + 1
+    g = torch.Generator().manual_seed(11)
+    pred = torch.randn(rows, P, generator=g)
+    nxt = torch.randn(rows, H, generator=g)
+    rew = torch.rand(rows, generator=g)
+    done = (torch.rand(rows, generator=g) < 0.2).float()
+    p = pred.clone().requires_grad_(True)
+    sq = torch.cat([(p[:, 1:] - nxt) ** 2, (p[:, :1] - rew.reshape(-1, 1)) ** 2], dim=-1)
+    aux = ((1.0 - done).reshape(-1, 1) * sq).mean(-1)
+    # the probe passes `done` as the truncation mask too (mask = 1 - done)
+    ((1.0 - done) * hp.aux_loss_mult * aux).mean().backward()
+    out = torch.empty(rows, P, device="cuda")
+    scratch = torch.zeros(24 + P, device="cuda")
+    eng.kernel_probe(1, pred.cuda(), nxt.cuda(), rew.cuda(), done.cuda(), out, scratch, _hyper(hp))
+    torch.testing.assert_close(out.cpu(), p.grad, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("rows,in_f,out_f", [(256, 8, 128), (14336, 256, 128), (257, 1024, 256)])
+def test_pair_kernel_boundary_shapes(rows, in_f, out_f):
+    """Shapes on either side of the CTA-pair kernel's eligibility threshold (56 pair tiles: 14336 x 128 is exactly 56
+    128-wide tiles; one pair tile and a ragged 257-row case fall back to the one-tile-per-CTA kernel)."""
+    from tests.test_gemm_tc import _bf, _engine as _geng
+    eng = _geng(max_rows=16384, H=1024)
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    x = torch.randn(rows, in_f, device="cuda", generator=g)
+    w = torch.randn(out_f, in_f, device="cuda", generator=g) / math.sqrt(in_f)
+    y = eng.linear(0, x, w)
+    torch.testing.assert_close(y, _bf(x) @ _bf(w).T, rtol=1e-4, atol=2e-4 * math.sqrt(in_f))
