@@ -108,8 +108,9 @@ def test_td_lambda_jax_matches_direct_recursion_in_numpy():
         lam_ret, trunc_next, w_next = val[T - 1, n], 1.0, 0.0     # scan carry: (value[-1], truncated = 1, iw = 0)
         for t in range(T - 1, -1, -1):
             lam_t = lam * math.exp(w_next)
-            boot = (1.0 - trunc_next) * ((1.0 - lam_t) * val[t, n] + lam_t * lam_ret) + trunc_next * val[t, n]
-            lam_ret = sr[t, n] + gamma * (1.0 - done[t, n]) * boot
+            lam_sum = lam_t * lam_ret + (1.0 - lam_t) * val[t, n]
+            # jnp.where(truncated, value, (1 - done) * lambda_sum): the truncation branch is not masked by done
+            lam_ret = sr[t, n] + gamma * (val[t, n] if trunc_next != 0 else (1.0 - done[t, n]) * lam_sum)
             want[t, n] = lam_ret
             trunc_next, w_next = trunc[t, n], iw[t, n]
     np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12)
