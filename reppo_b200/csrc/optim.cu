@@ -40,6 +40,27 @@ adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __restric
   REPPO_PDL_PROLOGUE();
   __shared__ float red[32];
   __shared__ float s_scale, s_bc1, s_bc2;
+  const long long n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* pi4 = reinterpret_cast<const float4*>(p_in);   // may alias p (in-place update)
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  float4* g4 = reinterpret_cast<float4*>(g);
+  // Two float4 per thread per pass, and the first pass's loads are issued BEFORE the global-norm prologue below (they do
+  // not depend on it): the kernel is load-latency bound (ncu: 54 % of the stall samples sit on the first use of the loaded
+  // values, 28 warps per SM), so the prologue's reduction / pow and the second float4 hide behind the first one's latency.
+  constexpr int U = 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long base = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float4 pp[U], mm[U], vv[U], gg[U];
+  auto load = [&](long long b0) {
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const long long i = b0 + k * stride;
+      if (i < n4) { pp[k] = pi4[i]; mm[k] = m4[i]; vv[k] = v4[i]; gg[k] = g4[i]; }
+    }
+  };
+  load(base);
   float s = 0.f;
   for (int i = threadIdx.x; i < num_partials; i += blockDim.x) s += partials[i];
   s = block_sum(s, red);
@@ -59,64 +80,63 @@ adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __restric
   __syncthreads();
   const float scale = s_scale, bc1 = s_bc1, bc2 = s_bc2;
   const float decay = 1.f - c.lr * c.weight_decay;
-  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
-    gg *= scale;
-    mm = c.b1 * mm + (1.f - c.b1) * gg;
-    vv = c.b2 * vv + (1.f - c.b2) * gg * gg;
-    pp = pp * decay - c.lr * (mm / bc1) / (sqrtf(vv / bc2) + c.eps);
+  auto upd = [&](float& p1, float g1, float& m1, float& v1) {
+    g1 *= scale;
+    m1 = c.b1 * m1 + (1.f - c.b1) * g1;
+    v1 = c.b2 * v1 + (1.f - c.b2) * g1 * g1;
+    p1 = p1 * decay - c.lr * (m1 / bc1) / (sqrtf(v1 / bc2) + c.eps);
   };
   // re-round updated master weights into the bf16 operand shadow W[out, ld] of the tcgen05 GEMMs (one element)
-  auto shadow1 = [&](float pp, long long idx) {
+  auto shadow1 = [&](float p1, long long idx) {
     for (int t = 0; t < sh.n; ++t) {
       if (idx >= sh.e[t].start && idx < sh.e[t].end) {
         const int off = static_cast<int>(idx - sh.e[t].start);
         const int r = off / sh.e[t].in, col = off - r * sh.e[t].in;
-        static_cast<__nv_bfloat16*>(sh.e[t].dst)[static_cast<size_t>(r) * sh.e[t].ld + col] = __float2bfloat16_rn(pp);
+        static_cast<__nv_bfloat16*>(sh.e[t].dst)[static_cast<size_t>(r) * sh.e[t].ld + col] = __float2bfloat16_rn(p1);
         if (sh.e[t].dst_t != nullptr)   // thin first layers also keep W^T (thin.cu)
-          static_cast<__nv_bfloat16*>(sh.e[t].dst_t)[static_cast<size_t>(col) * sh.e[t].ld_t + r] = __float2bfloat16_rn(pp);
+          static_cast<__nv_bfloat16*>(sh.e[t].dst_t)[static_cast<size_t>(col) * sh.e[t].ld_t + r] = __float2bfloat16_rn(p1);
         break;
       }
     }
   };
-  const long long n4 = n >> 2;
-  float4* p4 = reinterpret_cast<float4*>(p);
-  const float4* pi4 = reinterpret_cast<const float4*>(p_in);   // may alias p (in-place update)
-  float4* m4 = reinterpret_cast<float4*>(m);
-  float4* v4 = reinterpret_cast<float4*>(v);
-  float4* g4 = reinterpret_cast<float4*>(g);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float4 pp = pi4[i], mm = m4[i], vv = v4[i];
-    const float4 gg = g4[i];
-    if (zero_grads) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // the next step accumulates into a clean arena (no memset node)
-    upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
-    p4[i] = pp; m4[i] = mm; v4[i] = vv;
-    if (sh.n > 0) {
-      // one table search per float4: the four elements almost always sit in one row of one weight matrix
-      const long long idx = 4 * i;
-      bool done = false;
-      for (int t = 0; t < sh.n; ++t) {
-        if (idx >= sh.e[t].start && idx + 3 < sh.e[t].end) {
-          const int off = static_cast<int>(idx - sh.e[t].start);
-          const int r = off / sh.e[t].in, col = off - r * sh.e[t].in;
-          if (col + 3 < sh.e[t].in && sh.e[t].dst_t == nullptr) {
-            __nv_bfloat16* d = static_cast<__nv_bfloat16*>(sh.e[t].dst) + static_cast<size_t>(r) * sh.e[t].ld + col;
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
-            if ((reinterpret_cast<uintptr_t>(d) & 7) == 0) {
-              uint2 u;
-              u.x = *reinterpret_cast<const uint32_t*>(&lo);
-              u.y = *reinterpret_cast<const uint32_t*>(&hi);
-              *reinterpret_cast<uint2*>(d) = u;
-            } else {
-              d[0] = __low2bfloat16(lo); d[1] = __high2bfloat16(lo); d[2] = __low2bfloat16(hi); d[3] = __high2bfloat16(hi);
-            }
-            done = true;
+  // one table search per float4: the four elements almost always sit in one row of one weight matrix
+  auto shadow4 = [&](const float4& q, long long idx) {
+    bool done = false;
+    for (int t = 0; t < sh.n; ++t) {
+      if (idx >= sh.e[t].start && idx + 3 < sh.e[t].end) {
+        const int off = static_cast<int>(idx - sh.e[t].start);
+        const int r = off / sh.e[t].in, col = off - r * sh.e[t].in;
+        if (col + 3 < sh.e[t].in && sh.e[t].dst_t == nullptr) {
+          __nv_bfloat16* d = static_cast<__nv_bfloat16*>(sh.e[t].dst) + static_cast<size_t>(r) * sh.e[t].ld + col;
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(q.x, q.y), hi = __floats2bfloat162_rn(q.z, q.w);
+          if ((reinterpret_cast<uintptr_t>(d) & 7) == 0) {
+            uint2 u;
+            u.x = *reinterpret_cast<const uint32_t*>(&lo);
+            u.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(d) = u;
+          } else {
+            d[0] = __low2bfloat16(lo); d[1] = __high2bfloat16(lo); d[2] = __low2bfloat16(hi); d[3] = __high2bfloat16(hi);
           }
-          break;
+          done = true;
         }
+        break;
       }
-      if (!done) { shadow1(pp.x, idx); shadow1(pp.y, idx + 1); shadow1(pp.z, idx + 2); shadow1(pp.w, idx + 3); }
     }
+    if (!done) { shadow1(q.x, idx); shadow1(q.y, idx + 1); shadow1(q.z, idx + 2); shadow1(q.w, idx + 3); }
+  };
+  for (; base < n4; base += U * stride) {
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const long long i = base + k * stride;
+      if (i < n4) {
+        if (zero_grads) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // the next step accumulates into a clean arena (no memset node)
+        upd(pp[k].x, gg[k].x, mm[k].x, vv[k].x); upd(pp[k].y, gg[k].y, mm[k].y, vv[k].y);
+        upd(pp[k].z, gg[k].z, mm[k].z, vv[k].z); upd(pp[k].w, gg[k].w, mm[k].w, vv[k].w);
+        p4[i] = pp[k]; m4[i] = mm[k]; v4[i] = vv[k];
+        if (sh.n > 0) shadow4(pp[k], 4 * i);
+      }
+    }
+    if (base + U * stride < n4) load(base + U * stride);
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long long i = (n4 << 2) + threadIdx.x;
