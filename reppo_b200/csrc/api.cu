@@ -60,7 +60,7 @@ struct Twin {  // bf16 copy of an fp32 activation buffer (REPPO_GEMM_BF16 only)
   uint16_t* p = nullptr;
   int ld = 0;
 };
-enum { SLOT_CRITIC = 0, SLOT_ACTOR = 1, SLOT_ACTOR_OLD = 2, SLOT_CRITIC_ALT = 3, NUM_SLOTS = 4 };
+enum { SLOT_CRITIC = 0, SLOT_ACTOR = 1, SLOT_ACTOR_OLD = 2, SLOT_CRITIC_ALT = 3, SLOT_CRITIC_ALT2 = 4, NUM_SLOTS = 5 };
 
 // minimal NCCL surface (resolved with dlsym from libnccl.so.2)
 typedef struct ncclComm* ncclComm_t;
@@ -109,11 +109,12 @@ struct reppo_ctx {
   float *dxs = nullptr, *dxs2 = nullptr, *dfeat = nullptr, *dlogits = nullptr, *dpred = nullptr, *dout = nullptr, *dx0 = nullptr;
   float *logp = nullptr, *kl = nullptr, *q = nullptr, *gmu = nullptr, *gsig = nullptr, *scratch_metrics = nullptr;
   std::unordered_map<const float*, Twin> twins;
-  uint16_t* shadow_b[NUM_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
-  uint16_t* shadow_t[NUM_SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // W^T of thin first layers
+  uint16_t* shadow_b[NUM_SLOTS] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint16_t* shadow_t[NUM_SLOTS] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // W^T of thin first layers
   // step pipelining: second copy of the critic parameters (Adam ping-pongs between the two), and a private set of
   // critic-trunk buffers for the actor step, so that critic step k+1 can overlap actor step k
   float* cp_alt = nullptr;
+  float* cp_alt2 = nullptr;   // third snapshot: the critic chain may run two steps ahead of the actor chain (REPPO_DEPTH=3)
   Acts fa2, ha2;
   float *xs2 = nullptr, *dxs_a = nullptr, *dfeat_a = nullptr, *dlogits_a = nullptr, *partials2 = nullptr;
   bool pipeline = true;       // REPPO_NO_PIPELINE=1 disables
@@ -263,6 +264,7 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
   acts(c->fa2, c->feature, H); acts(c->ha2, c->head, B); bwd_scratch(c->fa2, c->feature); bwd_scratch(c->ha2, c->head);
   c->xs2 = FT(H); c->dxs_a = F(R * H); c->dfeat_a = FT(H); c->dlogits_a = FT(B); c->partials2 = F(kMaxPartials);
   c->cp_alt = F(static_cast<size_t>(c->critic_count) + 4);
+  c->cp_alt2 = F(static_cast<size_t>(c->critic_count) + 4);
   const size_t maxdim = c->maxdim;
   c->x0a = FT(K0);
   c->slab_timing = reinterpret_cast<long long*>(F(3 * 448 * 2));
@@ -274,8 +276,10 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
     c->shadow_b[SLOT_ACTOR] = Hf(c->shadow_b_elems[1]);
     c->shadow_b[SLOT_ACTOR_OLD] = Hf(c->shadow_b_elems[1]);
     c->shadow_b[SLOT_CRITIC_ALT] = Hf(c->shadow_b_elems[0]);
+    c->shadow_b[SLOT_CRITIC_ALT2] = Hf(c->shadow_b_elems[0]);
     c->shadow_t[SLOT_CRITIC] = Hf(c->shadow_t_elems[0] + 64);
     c->shadow_t[SLOT_CRITIC_ALT] = Hf(c->shadow_t_elems[0] + 64);
+    c->shadow_t[SLOT_CRITIC_ALT2] = Hf(c->shadow_t_elems[0] + 64);
     c->shadow_t[SLOT_ACTOR] = Hf(c->shadow_t_elems[1] + 64);
     c->shadow_t[SLOT_ACTOR_OLD] = Hf(c->shadow_t_elems[1] + 64);
     const size_t md8 = round8(static_cast<int>(maxdim));
@@ -352,7 +356,7 @@ int pack_shadows(reppo_ctx* c, int slot, const float* params, cudaStream_t st) {
       e.out = L.out; e.in = L.in; e.ld_b = L.ld_b; e.ld_t = L.ld_t;
     }
   };
-  if (slot == SLOT_CRITIC || slot == SLOT_CRITIC_ALT) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
+  if (slot == SLOT_CRITIC || slot == SLOT_CRITIC_ALT || slot == SLOT_CRITIC_ALT2) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
   CK(launch_pack_weights(t, st));
   return REPPO_OK;
 }
@@ -1006,7 +1010,7 @@ int clip_adam_impl(reppo_ctx* c, const reppo_net_state* net, int64_t n, const re
         e.dst_t = (L.st >= 0) ? c->shadow_t[slot] + L.st : nullptr; e.ld_t = L.ld_t;
       }
     };
-    if (slot == SLOT_CRITIC || slot == SLOT_CRITIC_ALT) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
+    if (slot == SLOT_CRITIC || slot == SLOT_CRITIC_ALT || slot == SLOT_CRITIC_ALT2) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
   }
   AdamConsts a{};
   a.lr = hp->lr; a.b1 = 0.9f; a.b2 = 0.999f; a.eps = 1e-8f;
@@ -1062,8 +1066,12 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
   // one NCCL communicator serves one chain: pipelining under data parallelism needs the second communicator
   const bool pipe = c->concurrent && c->pipeline && (c->comm[0] == nullptr || c->comm[1] != nullptr);
   cudaStream_t sa = pipe ? c->side[2] : st;   // the actor chain
-  float* P[2] = {s->critic.params, pipe ? c->cp_alt : s->critic.params};
-  const int S[2] = {SLOT_CRITIC, pipe ? SLOT_CRITIC_ALT : SLOT_CRITIC};
+  // snapshot j of the critic parameters lives in copy j % depth; depth 3 (REPPO_DEPTH=3) lets the critic chain run two steps
+  // ahead of the actor chain instead of one
+  static const int depth_env = getenv("REPPO_DEPTH") ? atoi(getenv("REPPO_DEPTH")) : 2;
+  const int depth = pipe ? (depth_env == 3 ? 3 : 2) : 1;
+  float* P[3] = {s->critic.params, pipe ? c->cp_alt : s->critic.params, c->cp_alt2};
+  const int S[3] = {SLOT_CRITIC, pipe ? SLOT_CRITIC_ALT : SLOT_CRITIC, SLOT_CRITIC_ALT2};
   // With per-step metric vectors the whole update is prepared once: all metric rows initialised by one kernel, both
   // gradient arenas cleared once (every Adam launch leaves its arena zeroed for the next step).
   const bool prepped = p->step_metrics != nullptr;
@@ -1081,7 +1089,7 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
       const float* eps_kl = p->eps_kl + slot * ks * mb * A;
       const int32_t* idx = p->perms + e * per_epoch + static_cast<int64_t>(j) * mb;
       float* m = p->step_metrics ? p->step_metrics + k * M_NUM : c->scratch_metrics;
-      const int cur = static_cast<int>(k & 1), nxt = pipe ? static_cast<int>((k + 1) & 1) : 0;
+      const int cur = static_cast<int>(k % depth), nxt = pipe ? static_cast<int>((k + 1) % depth) : 0;
       if (!pipe) {
         // the actor-only prefix of this step's actor update is forked here and overlaps the critic update
         cudaStream_t pre = nullptr;
@@ -1093,8 +1101,8 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
       // ---- critic chain (stream st): reads snapshot `cur`, Adam writes snapshot `nxt`
       RET(critic_grad_impl(c, s, b, idx, mb, hp, m, P[cur], S[cur], st, prepped));
       RET(allreduce_grads(c, s->critic.grads, c->critic_count, 0, st));
-      // snapshot `nxt` was last read by actor step k-2
-      if (k >= 2 && cudaStreamWaitEvent(st, c->ev_a[(k - 2) & 3], 0) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaStreamWaitEvent failed");
+      // the copy that receives snapshot k+1 held snapshot k+1-depth, last read by actor step k-depth
+      if (k >= depth && cudaStreamWaitEvent(st, c->ev_a[(k - depth) & 3], 0) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaStreamWaitEvent failed");
       RET(clip_adam_impl(c, &s->critic, c->critic_count, hp, m + M_CRITIC_GRAD_NORM, S[nxt], P[cur], P[nxt], c->partials, st, prepped));
       if (cudaEventRecord(c->ev_c[k & 3], st) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaEventRecord failed");
       // ---- actor chain (stream sa): needs snapshot `nxt`
@@ -1106,8 +1114,8 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
   }
   if (pipe) {
     RET(dep(c, sa, st));
-    if (k & 1) {  // odd number of steps: the final critic parameters sit in the alternate copy
-      CK(cudaMemcpyAsync(s->critic.params, c->cp_alt, sizeof(float) * c->critic_count, cudaMemcpyDeviceToDevice, st));
+    if (k % depth != 0) {  // the final critic parameters sit in an alternate copy
+      CK(cudaMemcpyAsync(s->critic.params, P[k % depth], sizeof(float) * c->critic_count, cudaMemcpyDeviceToDevice, st));
     }
   }
   if (p->metrics != nullptr && p->step_metrics != nullptr)
