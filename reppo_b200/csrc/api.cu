@@ -440,10 +440,43 @@ int dep(reppo_ctx* c, cudaStream_t from, cudaStream_t to) {
   return REPPO_OK;
 }
 
+// The actor chain (side[2]) is the critical path of the two-chain pipeline (profiles/r01_v8_timeline_summary.txt): its kernels
+// are captured from a high-priority stream and the graph is instantiated with cudaGraphInstantiateFlagUseNodePriority, so
+// their CTAs are dispatched first whenever both chains have work pending.  Measured at C2 (ms per update): off 103.9,
+// actor chain only (mode 2, default) 98.2, + actor weight gradients (1) 98.9, + critic main above critic weight
+// gradients (4) 102.8, graded (3) 105.8.  REPPO_PRIO=0 disables.
+// one minibatch step is a chain of few-microsecond kernels (the named configurations) rather than machine-filling ones
+bool small_step(const reppo_ctx* c) {
+  return static_cast<long long>(c->shape.max_rows) * std::max(c->shape.critic_hidden, c->shape.actor_hidden) <= (4LL << 20);
+}
+int prio_mode() {
+  static const int m = getenv("REPPO_PRIO") ? atoi(getenv("REPPO_PRIO")) : 2;
+  return m;
+}
+bool prio_enabled() { return prio_mode() != 0; }
+// side stream i: 0 = critic pred branch, 1 = critic weight gradients, 2 = actor chain, 3 = actor weight gradients
+cudaError_t create_side_stream(cudaStream_t* s, int i, bool small_step) {
+  int least = 0, greatest = 0;
+  // latency-bound steps only (explicit REPPO_PRIO forces it): at the wide-net shapes every kernel fills the machine and
+  // the priorities cost 4 % (C5: 229.7 vs 221.2 ms)
+  const bool want = prio_enabled() && (small_step || getenv("REPPO_PRIO") != nullptr);
+  if (want && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest < least) {
+    int pr = least;
+    const int mode = prio_mode();
+    const int mid = (least + greatest) / 2;
+    if (mode == 1) pr = (i == 2 || i == 3) ? greatest : least;
+    else if (mode == 2) pr = (i == 2) ? greatest : least;
+    else if (mode == 3) pr = (i == 2) ? greatest : (i == 3 ? greatest + 1 : (i == 1 ? least : mid));
+    else if (mode == 4) pr = (i == 2 || i == 3) ? greatest : (i == 1 ? least : mid);
+    return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, pr);
+  }
+  return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+}
+
 int ensure_streams(reppo_ctx* c) {
   if (!c->events.empty()) return REPPO_OK;
   for (int i = 0; i < 4; ++i)
-    if (cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking) != cudaSuccess)
+    if (create_side_stream(&c->side[i], i, small_step(c)) != cudaSuccess)
       return fail(c, REPPO_ERR_CUDA, "cudaStreamCreate failed");
   for (int i = 0; i < 4; ++i)
     if (cudaEventCreateWithFlags(&c->ev_c[i], cudaEventDisableTiming) != cudaSuccess ||
@@ -1493,7 +1526,11 @@ int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const
     c->launches = 0;
     cudaError_t e = cudaSuccess;
     if (c->cap_stream == nullptr) {
-      e = cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking);
+      int least = 0, greatest = 0;
+      if (prio_mode() >= 3 && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest < least)
+        e = cudaStreamCreateWithPriority(&c->cap_stream, cudaStreamNonBlocking, (least + greatest) / 2);
+      else
+        e = cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking);
       if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
     e = cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal);
@@ -1503,7 +1540,8 @@ int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const
     e = cudaStreamEndCapture(c->cap_stream, &graph);
     if (r != REPPO_OK) { if (graph) cudaGraphDestroy(graph); return r; }
     if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&c->graph_exec[slot], graph, 0);
+    const bool use_prio = prio_enabled() && (small_step(c) || getenv("REPPO_PRIO") != nullptr);
+    e = cudaGraphInstantiate(&c->graph_exec[slot], graph, use_prio ? cudaGraphInstantiateFlagUseNodePriority : 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
     memcpy(&c->graph_key[slot], &key, sizeof(GraphKey));
