@@ -140,6 +140,7 @@ struct reppo_ctx {
   int slab_cluster = 0;    // CTAs per cluster = max(hidden) / 64
   long long* slab_timing = nullptr;   // [3][64] per-step clock stamps of the three slab programs (REPPO_SLAB_TIMING=1)
   bool slab_timing_on = false;
+  cudaStream_t comm_stream[2] = {nullptr, nullptr};   // highest-priority streams for the two chains' gradient all-reduces
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // [3]: weight gradients of the actor chain
   std::vector<cudaEvent_t> events;
   size_t ev_next = 0;
@@ -468,6 +469,7 @@ cudaError_t create_side_stream(cudaStream_t* s, int i, bool small_step) {
     else if (mode == 2) pr = (i == 2) ? greatest : least;
     else if (mode == 3) pr = (i == 2) ? greatest : (i == 3 ? greatest + 1 : (i == 1 ? least : mid));
     else if (mode == 4) pr = (i == 2 || i == 3) ? greatest : (i == 1 ? least : mid);
+    else if (mode == 5) pr = (i == 0) ? greatest : least;   // critic chain first (its main stream is the capture stream)
     return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, pr);
   }
   return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
@@ -478,6 +480,14 @@ int ensure_streams(reppo_ctx* c) {
   for (int i = 0; i < 4; ++i)
     if (create_side_stream(&c->side[i], i, small_step(c)) != cudaSuccess)
       return fail(c, REPPO_ERR_CUDA, "cudaStreamCreate failed");
+  {
+    int least = 0, greatest = 0;
+    const bool want = prio_enabled() && getenv("REPPO_PRIO") != nullptr && getenv("REPPO_NO_NCCL_PRIO") == nullptr;   // experiments only
+    if (want && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest < least)
+      for (int i = 0; i < 2; ++i)
+        if (cudaStreamCreateWithPriority(&c->comm_stream[i], cudaStreamNonBlocking, greatest) != cudaSuccess)
+          return fail(c, REPPO_ERR_CUDA, "cudaStreamCreate failed");
+  }
   for (int i = 0; i < 4; ++i)
     if (cudaEventCreateWithFlags(&c->ev_c[i], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_a[i], cudaEventDisableTiming) != cudaSuccess)
@@ -720,12 +730,18 @@ int critic_trunk(reppo_ctx* c, const float* cp, int cslot, const float* x0, int 
   return REPPO_OK;
 }
 
+int dep(reppo_ctx* c, cudaStream_t from, cudaStream_t to);
 int allreduce_grads(reppo_ctx* c, float* g, int64_t n, int chain, cudaStream_t st) {
   if (c->comm[0] == nullptr) return REPPO_OK;
   ncclComm_t comm = (chain == 1 && c->comm[1] != nullptr) ? c->comm[1] : c->comm[0];
-  const int r = c->nccl.AllReduce(g, g, static_cast<size_t>(n), /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, st);
+  // With node priorities on, the collective runs from its own highest-priority stream: a low-priority all-reduce that is
+  // dispatched late on one rank keeps the peer's all-reduce kernel spinning (2 GPUs: 123.6 ms vs 115.7 ms without priorities)
+  cudaStream_t cs = c->comm_stream[chain == 1 ? 1 : 0];
+  if (cs != nullptr) RET(dep(c, st, cs));
+  const int r = c->nccl.AllReduce(g, g, static_cast<size_t>(n), /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, cs != nullptr ? cs : st);
   ++c->launches;
   if (r != 0) return fail(c, REPPO_ERR_NCCL, std::string("ncclAllReduce: ") + c->nccl.GetErrorString(r));
+  if (cs != nullptr) RET(dep(c, cs, st));
   return REPPO_OK;
 }
 
@@ -1248,6 +1264,7 @@ void reppo_ctx_destroy(reppo_ctx* c) {
   for (int i = 0; i < reppo_ctx::kGraphSlots; ++i) if (c->graph_exec[i]) cudaGraphExecDestroy(c->graph_exec[i]);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   for (auto& e : c->events) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) if (c->comm_stream[i]) cudaStreamDestroy(c->comm_stream[i]);
   for (int i = 0; i < 4; ++i) { if (c->side[i]) cudaStreamDestroy(c->side[i]); if (c->ev_c[i]) cudaEventDestroy(c->ev_c[i]); if (c->ev_a[i]) cudaEventDestroy(c->ev_a[i]); }
   for (int i = 0; i < 2; ++i) if (c->comm[i] && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm[i]);
   delete c;
@@ -1528,7 +1545,7 @@ int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const
     if (c->cap_stream == nullptr) {
       int least = 0, greatest = 0;
       if (prio_mode() >= 3 && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest < least)
-        e = cudaStreamCreateWithPriority(&c->cap_stream, cudaStreamNonBlocking, (least + greatest) / 2);
+        e = cudaStreamCreateWithPriority(&c->cap_stream, cudaStreamNonBlocking, prio_mode() == 5 ? greatest : (least + greatest) / 2);
       else
         e = cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking);
       if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
@@ -1540,7 +1557,9 @@ int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const
     e = cudaStreamEndCapture(c->cap_stream, &graph);
     if (r != REPPO_OK) { if (graph) cudaGraphDestroy(graph); return r; }
     if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-    const bool use_prio = prio_enabled() && (small_step(c) || getenv("REPPO_PRIO") != nullptr);
+    // single-GPU only by default: with the gradient all-reduces in the chains every assignment tried lost to no priorities
+    // (2 GPUs: 115.6 ms off, 120.5 actor-first with the collectives on highest-priority streams, 123.5 without, 131.3 critic-first)
+    const bool use_prio = prio_enabled() && ((small_step(c) && c->comm[0] == nullptr) || getenv("REPPO_PRIO") != nullptr);
     e = cudaGraphInstantiate(&c->graph_exec[slot], graph, use_prio ? cudaGraphInstantiateFlagUseNodePriority : 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
