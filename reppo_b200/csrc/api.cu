@@ -72,6 +72,8 @@ struct NcclApi {
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
+  int (*GroupStart)() = nullptr;   // optional (grouped data-parallel schedule)
+  int (*GroupEnd)() = nullptr;
 };
 
 struct GraphKey {
@@ -1130,6 +1132,57 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
     CK(cudaMemsetAsync(s->actor.grads, 0, static_cast<size_t>(c->actor_count) * sizeof(float), st));
   }
   if (pipe) RET(dep(c, st, sa));
+  // ---- grouped data-parallel schedule (REPPO_DP_GROUPED=1): iteration k runs the critic gradients of step k and the actor
+  // gradients of step k-1 side by side (both read critic snapshot k), then reduces BOTH gradient arenas in one grouped NCCL
+  // call (one collective launch per iteration instead of two per step), then the two Adam updates side by side.
+  static const bool grouped_env = getenv("REPPO_DP_GROUPED") != nullptr && atoi(getenv("REPPO_DP_GROUPED")) != 0;
+  if (pipe && grouped_env && c->comm[0] != nullptr && c->nccl.GroupStart != nullptr && c->nccl.GroupEnd != nullptr) {
+    const int64_t K = static_cast<int64_t>(p->num_epochs) * p->num_mini_batches;
+    auto step_args = [&](int64_t k, const float*& eps_pi, const float*& eps_kl, const int32_t*& idx, float*& m) {
+      const int e = static_cast<int>(k / p->num_mini_batches), j = static_cast<int>(k % p->num_mini_batches);
+      const int64_t slot = p->noise_per_minibatch ? k : e;
+      eps_pi = p->eps_pi + slot * mb * A;
+      eps_kl = p->eps_kl + slot * ks * mb * A;
+      idx = p->perms + e * per_epoch + static_cast<int64_t>(j) * mb;
+      m = p->step_metrics ? p->step_metrics + k * M_NUM : c->scratch_metrics;
+    };
+    for (int64_t k = 0; k <= K; ++k) {
+      const float *eps_pi = nullptr, *eps_kl = nullptr; const int32_t* idx = nullptr; float* m = nullptr;
+      const int cur = static_cast<int>(k & 1), nxt = static_cast<int>((k + 1) & 1);
+      if (k < K) {
+        step_args(k, eps_pi, eps_kl, idx, m);
+        RET(critic_grad_impl(c, s, b, idx, mb, hp, m, P[cur], S[cur], st, prepped));
+      }
+      if (k >= 1) {   // actor step k-1 reads snapshot k = P[cur] (written by the critic Adam of iteration k-1 on st)
+        step_args(k - 1, eps_pi, eps_kl, idx, m);
+        RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, p->old_policy_out, nullptr, P[cur], S[cur], c->ev_c[(k - 1) & 3],
+                            nullptr, sa, prepped));
+      }
+      RET(dep(c, sa, st));
+      if (c->nccl.GroupStart() != 0) return fail(c, REPPO_ERR_NCCL, "ncclGroupStart failed");
+      int r1 = 0, r2 = 0;
+      if (k < K) r1 = c->nccl.AllReduce(s->critic.grads, s->critic.grads, static_cast<size_t>(c->critic_count), 7, 0, c->comm[0], st);
+      if (k >= 1) r2 = c->nccl.AllReduce(s->actor.grads, s->actor.grads, static_cast<size_t>(c->actor_count), 7, 0, c->comm[0], st);
+      const int r3 = c->nccl.GroupEnd();
+      ++c->launches;
+      if (r1 != 0 || r2 != 0 || r3 != 0) return fail(c, REPPO_ERR_NCCL, "grouped ncclAllReduce failed");
+      RET(dep(c, st, sa));
+      if (k < K) {
+        step_args(k, eps_pi, eps_kl, idx, m);
+        RET(clip_adam_impl(c, &s->critic, c->critic_count, hp, m + M_CRITIC_GRAD_NORM, S[nxt], P[cur], P[nxt], c->partials, st, prepped));
+        if (cudaEventRecord(c->ev_c[k & 3], st) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaEventRecord failed");
+      }
+      if (k >= 1) {
+        step_args(k - 1, eps_pi, eps_kl, idx, m);
+        RET(clip_adam_impl(c, &s->actor, c->actor_count, hp, m + M_ACTOR_GRAD_NORM, SLOT_ACTOR, nullptr, nullptr, c->partials2, sa, prepped));
+      }
+    }
+    RET(dep(c, sa, st));
+    if (K & 1) CK(cudaMemcpyAsync(s->critic.params, P[1], sizeof(float) * c->critic_count, cudaMemcpyDeviceToDevice, st));
+    if (p->metrics != nullptr && p->step_metrics != nullptr)
+      CK(launch_metrics_mean(p->step_metrics, (p->num_epochs - 1) * p->num_mini_batches, p->num_mini_batches, M_NUM, p->metrics, st));
+    return REPPO_OK;
+  }
   int64_t k = 0;
   for (int e = 0; e < p->num_epochs; ++e) {
     for (int j = 0; j < p->num_mini_batches; ++j, ++k) {
@@ -1595,6 +1648,8 @@ static int nccl_load(reppo_ctx* c) {
   c->nccl.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t)>(dlsym(c->nccl.lib, "ncclAllReduce"));
   c->nccl.CommDestroy = reinterpret_cast<int (*)(ncclComm_t)>(dlsym(c->nccl.lib, "ncclCommDestroy"));
   c->nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(c->nccl.lib, "ncclGetErrorString"));
+  c->nccl.GroupStart = reinterpret_cast<int (*)()>(dlsym(c->nccl.lib, "ncclGroupStart"));
+  c->nccl.GroupEnd = reinterpret_cast<int (*)()>(dlsym(c->nccl.lib, "ncclGroupEnd"));
   if (!c->nccl.GetUniqueId || !c->nccl.CommInitRank || !c->nccl.AllReduce || !c->nccl.CommDestroy || !c->nccl.GetErrorString)
     return fail(c, REPPO_ERR_NCCL, "libnccl is missing required symbols");
   return REPPO_OK;
