@@ -47,6 +47,9 @@ typedef struct reppo_shape {
   int32_t max_rows;   /* largest minibatch / forward batch the workspace must hold */
   int32_t kl_samples; /* 16: src/jaxrl/reppo.py:557, src/torchrl/reppo.py:308 */
   float vmin, vmax;   /* config/env/<env>.yaml vmin / vmax */
+  int32_t max_batch_rows; /* optional (0 = off): rows one epoch of reppo_update visits (num_mini_batches * minibatch).  When
+                             set, the workspace also holds two epoch-sized sets of pre-gathered first-layer inputs and the
+                             minibatch gathers leave the per-step chains (one gather per epoch instead of two per step) */
 } reppo_shape;
 
 /* Per-call hyper-parameters (config/reppo.yaml:16-70). */
@@ -58,6 +61,10 @@ typedef struct reppo_hyper {
   int32_t partial_reset;                 /* cfg.env.partial_reset, src/torchrl/reppo.py:237 (Torch semantics only) */
   int32_t world_size;                    /* data-parallel ranks sharing each minibatch (>= 1); losses are means over
                                             world_size * mb rows and gradients are all-reduced when a communicator is attached */
+  int32_t lr_anneal_steps;               /* cfg.anneal_lr (src/jaxrl/reppo.py:239-244): > 0 = optax.linear_schedule(lr, 0,
+                                            lr_anneal_steps) evaluated on the device at each network's own optimizer step
+                                            counter (lr is NOT re-read from the host per step, so a captured graph stays
+                                            valid across updates); 0 = constant lr */
 } reppo_hyper;
 
 /* One network's flat fp32 arenas (layout: reppo_param_* below) plus its Adam step counter. */
@@ -254,11 +261,6 @@ int reppo_update(reppo_ctx* ctx, const reppo_state* state, const reppo_batch* ba
                  const reppo_hyper* hp, reppo_stream stream);
 /* kernels launched by the most recent reppo_update / step call on this ctx (bench.py's gpu_launches) */
 int64_t reppo_launch_count(const reppo_ctx* ctx);
-
-/* Profiling aid (no reference counterpart): device pointer + size of a named internal buffer inside the caller's
- * workspace.  "slab_timing": int64[3][448] clock64() stamps ([0..63] step starts, [64 + 12 s + k] stage k of step s) of every step of the critic / policy-prefix / policy-main slab
- * programs, recorded by CTA (0,0) when the context was created with REPPO_SLAB_TIMING=1 in the environment. */
-int reppo_debug_buffer(const reppo_ctx* ctx, const char* name, void** ptr, size_t* bytes);
 
 /* ---- data-parallel gradient all-reduce (not in the reference) ----------------
  * The library dlopen()s libnccl.so.2; rank 0 creates the 128-byte unique id, the host broadcasts it.

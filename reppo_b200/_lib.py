@@ -34,14 +34,15 @@ class Shape(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "obs_dim", "critic_obs_dim", "action_dim", "critic_hidden", "actor_hidden", "num_bins",
         "enc_layers", "head_layers", "pred_layers", "actor_layers", "critic_norm", "actor_norm",
-        "semantics", "gemm_mode", "max_rows", "kl_samples")] + [("vmin", C.c_float), ("vmax", C.c_float)]
+        "semantics", "gemm_mode", "max_rows", "kl_samples")] + [("vmin", C.c_float), ("vmax", C.c_float),
+                                                                      ("max_batch_rows", C.c_int32)]
 
 
 class Hyper(C.Structure):
     _fields_ = [(n, C.c_float) for n in (
         "gamma", "lmbda", "lr", "max_grad_norm", "kl_bound", "ent_target_mult", "aux_loss_mult", "actor_min_std")] + [
         (n, C.c_int32) for n in ("kl_clip_mode", "reduce_kl", "update_entropy_lagrangian", "update_kl_lagrangian",
-                                 "partial_reset", "world_size")]
+                                 "partial_reset", "world_size", "lr_anneal_steps")]
 
 
 class NetState(C.Structure):
@@ -93,7 +94,6 @@ SYMBOLS = {
     "reppo_clip_adam": (C.c_int, [_vp, C.POINTER(NetState), _i64, C.POINTER(Hyper), _vp, _vp]),
     "reppo_update": (C.c_int, [_vp, C.POINTER(State), C.POINTER(Batch), C.POINTER(Plan), C.POINTER(Hyper), _vp]),
     "reppo_launch_count": (_i64, [_vp]),
-    "reppo_debug_buffer": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "reppo_nccl_unique_id": (C.c_int, [_vp, _vp]),
     "reppo_nccl_init": (C.c_int, [_vp, _vp, _i32, _i32]),
     "reppo_nccl_finalize": (C.c_int, [_vp]),

@@ -18,7 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libreppo_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "td_lambda.cu", "gemm_f32.cu", "gemm_bf16_tc.cu", "convert.cu", "rowwise.cu", "losses.cu", "optim.cu", "slab.cu", "gemm_bf16_tc_bwd.cu", "rollout.cu", "thin.cu", "gemm_bf16_tc2.cu"]
+SOURCES = ["api.cu", "tmap.cu", "td_lambda.cu", "gemm_f32.cu", "gemm_bf16_tc.cu", "gemm_bf16_tc2.cu", "convert.cu", "rowwise.cu",
+           "losses.cu", "optim.cu", "rollout.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

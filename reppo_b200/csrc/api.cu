@@ -24,7 +24,7 @@
 
 #include "../../include/reppo_b200.h"
 #include "kernels.h"
-#include "slab.h"
+#include "knobs.h"
 
 using namespace reppo;
 
@@ -33,8 +33,8 @@ namespace {
 struct Linear {
   int64_t w = -1, b = -1, g = -1, beta = -1;  // offsets into the flat fp32 arena (floats)
   int in = 0, out = 0;
-  int64_t sb = 0, st = 0;                     // offsets into the bf16 shadows W [out, ld_b] / W^T [in, ld_t] (elements)
-  int ld_b = 0, ld_t = 0;
+  int64_t sb = 0;                             // offset into the bf16 shadow W [out, ld_b] (elements)
+  int ld_b = 0;
 };
 struct Mlp {
   std::vector<Linear> layers;
@@ -60,7 +60,7 @@ struct Twin {  // bf16 copy of an fp32 activation buffer (REPPO_GEMM_BF16 only)
   uint16_t* p = nullptr;
   int ld = 0;
 };
-enum { SLOT_CRITIC = 0, SLOT_ACTOR = 1, SLOT_ACTOR_OLD = 2, SLOT_CRITIC_ALT = 3, SLOT_CRITIC_ALT2 = 4, NUM_SLOTS = 5 };
+enum { SLOT_CRITIC = 0, SLOT_ACTOR = 1, SLOT_ACTOR_OLD = 2, SLOT_CRITIC_ALT = 3, NUM_SLOTS = 4 };
 
 // minimal NCCL surface (resolved with dlsym from libnccl.so.2)
 typedef struct ncclComm* ncclComm_t;
@@ -95,7 +95,7 @@ struct reppo_ctx {
   bool tc = false;  // REPPO_GEMM_BF16
   Mlp feature, head, pred, actor;
   int64_t zero_dist_off = 0, critic_count = 0, actor_count = 0;
-  int64_t shadow_b_elems[2] = {0, 0}, shadow_t_elems[2] = {0, 0};  // per network (critic, actor)
+  int64_t shadow_b_elems[2] = {0, 0};  // per network (critic, actor)
   int pred_out = 0, K0 = 0, maxdim = 0;
   std::vector<TensorInfo> critic_tensors, actor_tensors;
   std::vector<float> edges_h, support_h;
@@ -111,12 +111,16 @@ struct reppo_ctx {
   float *dxs = nullptr, *dxs2 = nullptr, *dfeat = nullptr, *dlogits = nullptr, *dpred = nullptr, *dout = nullptr, *dx0 = nullptr;
   float *logp = nullptr, *kl = nullptr, *q = nullptr, *gmu = nullptr, *gsig = nullptr, *scratch_metrics = nullptr;
   std::unordered_map<const float*, Twin> twins;
-  uint16_t* shadow_b[NUM_SLOTS] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  uint16_t* shadow_t[NUM_SLOTS] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // W^T of thin first layers
+  // epoch-sized pre-gathered first-layer inputs (two sets, alternating by epoch): any row slice of them has a twin too
+  struct TwinRange { const float* base; size_t floats; int cols; Twin t; };
+  std::vector<TwinRange> twin_ranges;
+  float *x0_ep[2] = {nullptr, nullptr}, *xa0_ep[2] = {nullptr, nullptr}, *x0a_ep[2] = {nullptr, nullptr};
+  cudaEvent_t ev_epoch[2] = {nullptr, nullptr};
+  unsigned int* adam_bar = nullptr;   // 3 x {arrival count, generation}: critic chain, actor chain, stand-alone calls
+  uint16_t* shadow_b[NUM_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
   // step pipelining: second copy of the critic parameters (Adam ping-pongs between the two), and a private set of
   // critic-trunk buffers for the actor step, so that critic step k+1 can overlap actor step k
   float* cp_alt = nullptr;
-  float* cp_alt2 = nullptr;   // third snapshot: the critic chain may run two steps ahead of the actor chain (REPPO_DEPTH=3)
   Acts fa2, ha2;
   float *xs2 = nullptr, *dxs_a = nullptr, *dfeat_a = nullptr, *dlogits_a = nullptr, *partials2 = nullptr;
   bool pipeline = true;       // REPPO_NO_PIPELINE=1 disables
@@ -138,11 +142,6 @@ struct reppo_ctx {
   // parallel branches): [0] pred-head branch, [1] weight-gradient GEMMs, [2] actor-only prefix of the actor step
   bool concurrent = true;
   bool fuse_norm = true;   // REPPO_NO_FUSE_NORM=1: separate GEMM + norm/swish kernels
-  bool slab = false;       // whole chains of a step in one persistent cluster kernel (slab.cu); opt-in with REPPO_SLAB=1
-  int slab_cluster = 0;    // CTAs per cluster = max(hidden) / 64
-  long long* slab_timing = nullptr;   // [3][64] per-step clock stamps of the three slab programs (REPPO_SLAB_TIMING=1)
-  bool slab_timing_on = false;
-  cudaStream_t comm_stream[2] = {nullptr, nullptr};   // highest-priority streams for the two chains' gradient all-reduces
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // [3]: weight gradients of the actor chain
   std::vector<cudaEvent_t> events;
   size_t ev_next = 0;
@@ -153,7 +152,11 @@ struct reppo_ctx {
 
   Twin twin(const float* p) const {
     auto it = twins.find(p);
-    return it == twins.end() ? Twin{} : it->second;
+    if (it != twins.end()) return it->second;
+    for (const TwinRange& r : twin_ranges)
+      if (p > r.base && p < r.base + r.floats && (p - r.base) % r.cols == 0)
+        return Twin{r.t.p + static_cast<size_t>((p - r.base) / r.cols) * r.t.ld, r.t.ld};
+    return Twin{};
   }
 };
 
@@ -177,7 +180,7 @@ int fail(reppo_ctx* c, int code, const std::string& msg) {
     if (r__ != REPPO_OK) return r__;    \
   } while (0)
 
-void add_fcnn(std::vector<TensorInfo>& ts, int64_t& off, int64_t& sb, int64_t& st, Mlp& mlp, const std::string& prefix,
+void add_fcnn(std::vector<TensorInfo>& ts, int64_t& off, int64_t& sb, Mlp& mlp, const std::string& prefix,
               int in_f, int hidden, int out_f, int layers, bool input_activation, int norm) {
   // Sequential indices of torch_models.FCNN (:97-139): an input activation occupies slot 0.
   const int shift = input_activation ? 1 : 0;
@@ -193,11 +196,8 @@ void add_fcnn(std::vector<TensorInfo>& ts, int64_t& off, int64_t& sb, int64_t& s
       L.g = off; ts.push_back({blk + ".1.weight", off, L.out, 0}); off += L.out;
       if (norm == NORM_LAYER) { L.beta = off; ts.push_back({blk + ".1.bias", off, L.out, 0}); off += L.out; }
     }
-    L.ld_b = round8(L.in); L.ld_t = round8(L.out);
+    L.ld_b = round8(L.in);
     L.sb = sb; sb += static_cast<int64_t>(L.out) * L.ld_b; sb = (sb + 63) & ~static_cast<int64_t>(63);
-    // W^T shadow only for thin first layers (few input features): the SIMT first-layer kernel (thin.cu) reads it
-    if (i == 0 && layers >= 2 && L.in <= 64) { L.st = st; st += static_cast<int64_t>(L.in) * L.ld_t; st = (st + 63) & ~static_cast<int64_t>(63); }
-    else L.st = -1;
     mlp.layers.push_back(L);
   }
 }
@@ -226,6 +226,7 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
   const size_t P = c->pred_out, K0 = c->K0, D = s.obs_dim;
   Bump bp;
   c->twins.clear();
+  c->twin_ranges.clear();
   auto F = [&](size_t n) -> float* {
     const size_t o = bp.take(n * sizeof(float));
     return base ? reinterpret_cast<float*>(base + o) : nullptr;
@@ -260,6 +261,7 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
     a.tmp = F(R * hmax);
   };
   c->edges_d = F(B + 1); c->support_d = F(B); c->partials = F(kMaxPartials); c->scratch_metrics = F(M_NUM);
+  c->adam_bar = reinterpret_cast<unsigned int*>(F(8));
   c->x0 = FT(K0); c->xs = FT(H); c->xa0 = FT(D);
   acts(c->fa, c->feature, H); acts(c->ha, c->head, B); acts(c->pa, c->pred, P);
   acts(c->aa, c->actor, 2 * A); acts(c->oa, c->actor, 2 * A);
@@ -267,24 +269,28 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
   acts(c->fa2, c->feature, H); acts(c->ha2, c->head, B); bwd_scratch(c->fa2, c->feature); bwd_scratch(c->ha2, c->head);
   c->xs2 = FT(H); c->dxs_a = F(R * H); c->dfeat_a = FT(H); c->dlogits_a = FT(B); c->partials2 = F(kMaxPartials);
   c->cp_alt = F(static_cast<size_t>(c->critic_count) + 4);
-  c->cp_alt2 = F(static_cast<size_t>(c->critic_count) + 4);
   const size_t maxdim = c->maxdim;
   c->x0a = FT(K0);
-  c->slab_timing = reinterpret_cast<long long*>(F(3 * 448 * 2));
   c->dxs = F(R * H); c->dxs2 = F(R * H); c->dfeat = FT(H); c->dlogits = FT(B); c->dpred = FT(P); c->dout = FT(2 * A);
   c->dx0 = F(R * K0);
   c->logp = F(R); c->kl = F(R); c->q = F(R); c->gmu = F(R * A); c->gsig = F(R * A);
+  // epoch-sized gathered inputs: [critic_obs | action], obs, [critic_obs | sampled action]
+  const size_t E = (s.max_batch_rows > 0 && !knobs().no_pregather) ? static_cast<size_t>(s.max_batch_rows) : 0;
+  for (int i = 0; i < 2 && E > 0; ++i) {
+    auto big = [&](size_t cols) -> float* {
+      float* p = F(E * cols);
+      reppo_ctx::TwinRange r{p, E * cols, static_cast<int>(cols), Twin{}};
+      if (c->tc) { r.t.ld = round8(static_cast<int>(cols)); r.t.p = Hf(E * r.t.ld); }
+      if (base) { if (c->tc) c->twins[p] = r.t; c->twin_ranges.push_back(r); }
+      return p;
+    };
+    c->x0_ep[i] = big(K0); c->xa0_ep[i] = big(D); c->x0a_ep[i] = big(K0);
+  }
   if (c->tc) {
     c->shadow_b[SLOT_CRITIC] = Hf(c->shadow_b_elems[0]);
     c->shadow_b[SLOT_ACTOR] = Hf(c->shadow_b_elems[1]);
     c->shadow_b[SLOT_ACTOR_OLD] = Hf(c->shadow_b_elems[1]);
     c->shadow_b[SLOT_CRITIC_ALT] = Hf(c->shadow_b_elems[0]);
-    c->shadow_b[SLOT_CRITIC_ALT2] = Hf(c->shadow_b_elems[0]);
-    c->shadow_t[SLOT_CRITIC] = Hf(c->shadow_t_elems[0] + 64);
-    c->shadow_t[SLOT_CRITIC_ALT] = Hf(c->shadow_t_elems[0] + 64);
-    c->shadow_t[SLOT_CRITIC_ALT2] = Hf(c->shadow_t_elems[0] + 64);
-    c->shadow_t[SLOT_ACTOR] = Hf(c->shadow_t_elems[1] + 64);
-    c->shadow_t[SLOT_ACTOR_OLD] = Hf(c->shadow_t_elems[1] + 64);
     const size_t md8 = round8(static_cast<int>(maxdim));
     c->lin_a = Hf(R * md8); c->lin_c = Hf(R * md8); c->lin_b = Hf(maxdim * md8);
   }
@@ -293,8 +299,7 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
 
 int wgrad_split(int out, int in, int rows, bool tc) {
   if (tc) {
-    static const char* env = getenv("REPPO_WGRAD_SPLIT");
-    if (env != nullptr && atoi(env) > 0) return std::min(atoi(env), std::max(1, rows / 64));
+    if (knobs().wgrad_split > 0) return std::min(knobs().wgrad_split, std::max(1, rows / 64));
     // measured at C2 (512 x 512 x 2048 rows): split 1 / 2 / 4 / 8 / 16 -> 160.9 / 147.8 / 140.9 / 147.7 / 166.9 ms per update.
     // The weight-gradient GEMMs run beside the dgrad chain: ~64 CTAs keep the chain's SMs free and the atomics few.
     const int tiles = ((out + 127) / 128) * ((in + 127) / 128);
@@ -355,11 +360,10 @@ int pack_shadows(reppo_ctx* c, int slot, const float* params, cudaStream_t st) {
     for (const Linear& L : m.layers) {
       PackEntry& e = t.e[t.n++];
       e.w = params + L.w; e.wb = c->shadow_b[slot] + L.sb;
-      e.wtb = (L.st >= 0) ? c->shadow_t[slot] + L.st : nullptr;
-      e.out = L.out; e.in = L.in; e.ld_b = L.ld_b; e.ld_t = L.ld_t;
+      e.out = L.out; e.in = L.in; e.ld_b = L.ld_b;
     }
   };
-  if (slot == SLOT_CRITIC || slot == SLOT_CRITIC_ALT || slot == SLOT_CRITIC_ALT2) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
+  if (slot == SLOT_CRITIC || slot == SLOT_CRITIC_ALT) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
   CK(launch_pack_weights(t, st));
   return REPPO_OK;
 }
@@ -371,42 +375,12 @@ int pack_all(reppo_ctx* c, const reppo_state* s, cudaStream_t st) {
   return REPPO_OK;
 }
 
-// Where the first layer's input rows come from when the gather is fused into a SIMT first layer (thin.cu):
-//   x[r, :] = [ a[ia(r), 0:da] | b[ib(r), 0:db] ], ia(r) = idx ? idx[r] : r, ib(r) = b_local ? r : ia(r)
-struct ThinIn {
-  const float* a = nullptr; int da = 0, lda = 0;
-  const float* b = nullptr; int db = 0, ldb = 0;
-  const int32_t* idx = nullptr; int b_local = 0;
-  bool want_x_twin = true;   // the weight gradient of this layer needs the gathered input as a bf16 operand
-  bool done = false;         // out: the thin kernel ran (otherwise the caller gathers and the GEMM path runs)
-};
-
 // out_act: optional bf16 twin that receives swish(output) straight from the last GEMM's epilogue
-// thin: try the fused gather + first-layer SIMT kernel; when it is not eligible NOTHING is launched for layer 0 and
-//       thin->done stays false (the caller then gathers `in` itself and calls again without `thin`)
-// skip_last: stop before the last Linear (its GEMM is fused into the kernel that consumes it)
 int mlp_forward(reppo_ctx* c, const Mlp& m, const float* params, int slot, const float* in, int rows, Acts& a, cudaStream_t st,
-                Twin out_act = Twin{}, ThinIn* thin = nullptr, bool skip_last = false) {
+                Twin out_act = Twin{}) {
   const float* cur = in;
   const int n = static_cast<int>(m.layers.size());
-  int first = 0;
-  if (thin != nullptr) {
-    const Linear& L = m.layers[0];
-    thin->done = false;
-    if (!c->tc || n < 2 || L.st < 0) return REPPO_OK;
-    const Twin tw = c->twin(a.x[0]), tx = thin->want_x_twin ? c->twin(in) : Twin{};
-    const cudaError_t e = launch_thin_first_layer(
-        m.norm, thin->a, thin->da, thin->lda, thin->b, thin->db, thin->ldb, thin->idx, thin->b_local, rows, L.out,
-        c->shadow_t[slot] + L.st, L.ld_t, params + L.b, L.g >= 0 ? params + L.g : nullptr, L.beta >= 0 ? params + L.beta : nullptr,
-        c->sem.norm_eps, a.z[0], a.rstd[0], a.mean[0], tw.p, tw.ld, tx.p, tx.ld, st);
-    if (e == cudaErrorNotSupported) return REPPO_OK;
-    if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("launch_thin_first_layer: ") + cudaGetErrorString(e));
-    ++c->launches;
-    thin->done = true;
-    cur = a.x[0];
-    first = 1;
-  }
-  for (int i = first; i < n - (skip_last ? 1 : 0); ++i) {
+  for (int i = 0; i < n; ++i) {
     const Linear& L = m.layers[i];
     const bool last = (i == n - 1);
     float* dst = last ? a.out : a.z[i];
@@ -431,8 +405,6 @@ int mlp_forward(reppo_ctx* c, const Mlp& m, const float* params, int slot, const
   return REPPO_OK;
 }
 
-// d_out: gradient w.r.t. the MLP output [rows, out_last] (read only).  grads == nullptr: frozen network (dgrad only).
-// dx_in != nullptr: also produce the gradient w.r.t. the MLP input (mode GEMM_STORE / GEMM_ACCUM).
 // `to` waits for everything enqueued so far on `from` (an edge of the step's DAG; captured as a graph dependency)
 int dep(reppo_ctx* c, cudaStream_t from, cudaStream_t to) {
   if (from == to) return REPPO_OK;
@@ -445,55 +417,36 @@ int dep(reppo_ctx* c, cudaStream_t from, cudaStream_t to) {
 
 // The actor chain (side[2]) is the critical path of the two-chain pipeline (profiles/r01_v8_timeline_summary.txt): its kernels
 // are captured from a high-priority stream and the graph is instantiated with cudaGraphInstantiateFlagUseNodePriority, so
-// their CTAs are dispatched first whenever both chains have work pending.  Measured at C2 (ms per update): off 103.9,
-// actor chain only (mode 2, default) 98.2, + actor weight gradients (1) 98.9, + critic main above critic weight
-// gradients (4) 102.8, graded (3) 105.8.  REPPO_PRIO=0 disables.
+// their CTAs are dispatched first whenever both chains have work pending.  Measured at C2 (ms per update): off 103.9, actor
+// chain first 98.2; every other assignment tried lost.  REPPO_PRIO=0 disables, REPPO_PRIO=1 forces.
 // one minibatch step is a chain of few-microsecond kernels (the named configurations) rather than machine-filling ones
 bool small_step(const reppo_ctx* c) {
   return static_cast<long long>(c->shape.max_rows) * std::max(c->shape.critic_hidden, c->shape.actor_hidden) <= (4LL << 20);
 }
-int prio_mode() {
-  static const int m = getenv("REPPO_PRIO") ? atoi(getenv("REPPO_PRIO")) : 2;
-  return m;
-}
-bool prio_enabled() { return prio_mode() != 0; }
-// side stream i: 0 = critic pred branch, 1 = critic weight gradients, 2 = actor chain, 3 = actor weight gradients
-cudaError_t create_side_stream(cudaStream_t* s, int i, bool small_step) {
-  int least = 0, greatest = 0;
-  // latency-bound steps only (explicit REPPO_PRIO forces it): at the wide-net shapes every kernel fills the machine and
-  // the priorities cost 4 % (C5: 229.7 vs 221.2 ms)
-  const bool want = prio_enabled() && (small_step || getenv("REPPO_PRIO") != nullptr);
-  if (want && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest < least) {
-    int pr = least;
-    const int mode = prio_mode();
-    const int mid = (least + greatest) / 2;
-    if (mode == 1) pr = (i == 2 || i == 3) ? greatest : least;
-    else if (mode == 2) pr = (i == 2) ? greatest : least;
-    else if (mode == 3) pr = (i == 2) ? greatest : (i == 3 ? greatest + 1 : (i == 1 ? least : mid));
-    else if (mode == 4) pr = (i == 2 || i == 3) ? greatest : (i == 1 ? least : mid);
-    else if (mode == 5) pr = (i == 0) ? greatest : least;   // critic chain first (its main stream is the capture stream)
-    return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, pr);
-  }
-  return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+// latency-bound steps only: at the wide-net shapes every kernel fills the machine and the priorities cost 4 %
+// (C5: 229.7 vs 221.2 ms); with NCCL collectives inside the chains they lose as well (2 GPUs: 115.6 ms off, 120.5 on)
+bool want_prio(const reppo_ctx* c) {
+  const int k = knobs().prio;
+  if (k >= 0) return k != 0;
+  return small_step(c) && c->comm[0] == nullptr;
 }
 
 int ensure_streams(reppo_ctx* c) {
   if (!c->events.empty()) return REPPO_OK;
-  for (int i = 0; i < 4; ++i)
-    if (create_side_stream(&c->side[i], i, small_step(c)) != cudaSuccess)
-      return fail(c, REPPO_ERR_CUDA, "cudaStreamCreate failed");
-  {
-    int least = 0, greatest = 0;
-    const bool want = prio_enabled() && getenv("REPPO_PRIO") != nullptr && getenv("REPPO_NO_NCCL_PRIO") == nullptr;   // experiments only
-    if (want && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest < least)
-      for (int i = 0; i < 2; ++i)
-        if (cudaStreamCreateWithPriority(&c->comm_stream[i], cudaStreamNonBlocking, greatest) != cudaSuccess)
-          return fail(c, REPPO_ERR_CUDA, "cudaStreamCreate failed");
+  // side stream i: 0 = critic pred branch, 1 = critic weight gradients, 2 = actor chain, 3 = actor weight gradients
+  int least = 0, greatest = 0;
+  const bool prio = want_prio(c) && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest < least;
+  for (int i = 0; i < 4; ++i) {
+    const cudaError_t e = prio ? cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, i == 2 ? greatest : least)
+                               : cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
+    if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaStreamCreate failed");
   }
   for (int i = 0; i < 4; ++i)
     if (cudaEventCreateWithFlags(&c->ev_c[i], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_a[i], cudaEventDisableTiming) != cudaSuccess)
       return fail(c, REPPO_ERR_CUDA, "cudaEventCreate failed");
+  for (int i = 0; i < 2; ++i)
+    if (cudaEventCreateWithFlags(&c->ev_epoch[i], cudaEventDisableTiming) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaEventCreate failed");
   c->events.resize(64);
   for (auto& e : c->events)
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaEventCreate failed");
@@ -505,21 +458,9 @@ int ensure_streams(reppo_ctx* c) {
 // last_bias_done: the producer of d_out already accumulated the last layer's bias gradient (column sums of d_out).
 // The dgrad / norm-backward chain runs on `st`; every weight-gradient GEMM only depends on one link of the chain and
 // runs on `wst` (the caller joins `wst` before the optimizer).
-// Optional fusion of the MLP's input gradient with the swish backward that follows it:
-//   dz = (d_in [+ addend]) * swish'(z) -> bf16 twin of `dz`, column sums -> g_bias  (one tcgen05 kernel instead of a
-//   dgrad GEMM + a row kernel).  join_from: stream that produces `addend` (joined right before the fused launch).
-struct FusedIn {
-  const float* z = nullptr;
-  const float* addend = nullptr;
-  const float* dz = nullptr;
-  float* g_bias = nullptr;
-  cudaStream_t join_from = nullptr;
-  bool done = false;
-};
-
 int mlp_backward(reppo_ctx* c, const Mlp& m, const float* params, int slot, float* grads, const float* in, int rows,
                  const Acts& a, const float* d_out, float* dx_in, int dx_mode, float* bias2, float scale2, bool last_bias_done,
-                 cudaStream_t st, cudaStream_t wst, FusedIn* fin = nullptr, bool last_dgrad_done = false) {
+                 cudaStream_t st, cudaStream_t wst) {
   const int n = static_cast<int>(m.layers.size());
   const float* d = d_out;
   for (int i = n - 1; i >= 0; --i) {
@@ -535,166 +476,15 @@ int mlp_backward(reppo_ctx* c, const Mlp& m, const float* params, int slot, floa
       const Linear& Lp = m.layers[i - 1];
       float* dz = a.dz[i - 1];
       const Twin tw = c->twin(dz);
-      const bool have_dx = last_dgrad_done && i == n - 1;   // the producer of d_out already wrote this layer's dgrad to a.tmp
-      if (c->tc && !have_dx) {
-        // dgrad + norm / swish backward (+ d gamma, d beta, d bias column sums) in ONE tcgen05 kernel
-        const Twin td = c->twin(d);
-        const cudaError_t e = launch_gemm_bf16_tc_bwd(
-            m.norm, rows, L.in, L.out, td.p, td.ld, c->shadow_b[slot] + L.sb, L.ld_b, a.z[i - 1], a.rstd[i - 1], a.mean[i - 1],
-            Lp.g >= 0 ? params + Lp.g : nullptr, Lp.beta >= 0 ? params + Lp.beta : nullptr, nullptr, tw.p, tw.ld,
-            (grads && Lp.g >= 0) ? grads + Lp.g : nullptr, (grads && Lp.beta >= 0) ? grads + Lp.beta : nullptr,
-            grads ? grads + Lp.b : nullptr, st);
-        if (e == cudaSuccess) { ++c->launches; d = dz; continue; }
-        if (e != cudaErrorNotSupported) return fail(c, REPPO_ERR_CUDA, std::string("launch_gemm_bf16_tc_bwd: ") + cudaGetErrorString(e));
-      }
-      if (!have_dx) RET(linear_dgrad(c, L, params, slot, d, rows, a.tmp, GEMM_STORE, st));
+      RET(linear_dgrad(c, L, params, slot, d, rows, a.tmp, GEMM_STORE, st));
       CK(launch_norm_act_bwd(m.norm, a.tmp, nullptr, a.z[i - 1], Lp.g >= 0 ? params + Lp.g : nullptr,
                              Lp.beta >= 0 ? params + Lp.beta : nullptr, a.rstd[i - 1], a.mean[i - 1], rows, L.in,
                              c->tc ? nullptr : dz, (grads && Lp.g >= 0) ? grads + Lp.g : nullptr,
                              (grads && Lp.beta >= 0) ? grads + Lp.beta : nullptr, grads ? grads + Lp.b : nullptr, tw.p, tw.ld, st));
       d = dz;
     } else if (dx_in != nullptr) {
-      if (fin != nullptr && c->tc) {
-        if (fin->join_from != nullptr) RET(dep(c, fin->join_from, st));
-        const Twin td = c->twin(d), tz = c->twin(fin->dz);
-        const cudaError_t e = launch_gemm_bf16_tc_bwd(NORM_NONE, rows, L.in, L.out, td.p, td.ld, c->shadow_b[slot] + L.sb, L.ld_b,
-                                                      fin->z, nullptr, nullptr, nullptr, nullptr, fin->addend, tz.p, tz.ld, nullptr,
-                                                      nullptr, fin->g_bias, st);
-        if (e == cudaSuccess) { ++c->launches; fin->done = true; continue; }
-        if (e != cudaErrorNotSupported) return fail(c, REPPO_ERR_CUDA, std::string("launch_gemm_bf16_tc_bwd: ") + cudaGetErrorString(e));
-      }
       RET(linear_dgrad(c, L, params, slot, d, rows, dx_in, dx_mode, st));
     }
-  }
-  return REPPO_OK;
-}
-
-
-// ---- slab programs (slab.cu): the forward / loss / input-gradient chain of a step as ONE kernel ----------------
-struct SlabBuilder {
-  reppo_ctx* c;
-  SlabProgram p;
-  int rows;
-  int max_tiles = 1;
-  bool ok = true;
-  std::string why;
-
-  SlabBuilder(reppo_ctx* ctx, int rows_) : c(ctx), rows(rows_) {
-    memset(&p, 0, sizeof(p));
-    p.rows = rows_;
-  }
-  SlabStep* next() {
-    if (p.num_steps >= kSlabMaxSteps) { ok = false; why = "too many steps for one slab program"; return nullptr; }
-    SlabStep* s = &p.steps[p.num_steps++];
-    return s;
-  }
-  void row(int which) {
-    SlabStep* s = next();
-    if (!s) return;
-    s->f.kind = SLAB_ROW; s->f.row = which;
-  }
-  // A = bf16 twin of `a_f32` [rows, K]; W = shadow of layer L in `slot`; dgrad: out[rows, L.in] = A[rows, L.out] W
-  SlabStepInfo* gemm(const float* a_f32, const Linear& L, int slot, bool dgrad) {
-    SlabStep* full = next();
-    if (!full) return nullptr;
-    SlabStepInfo* s = &full->f;
-    const Twin ta = c->twin(a_f32);
-    if (ta.p == nullptr) { ok = false; why = "slab operand has no bf16 twin"; return nullptr; }
-    s->kind = SLAB_GEMM;
-    s->K = dgrad ? L.out : L.in;
-    s->N = dgrad ? L.in : L.out;
-    s->b_mn = dgrad ? 1 : 0;
-    const uint16_t* w = c->shadow_b[slot] + L.sb;
-    bool e = slab_encode_2d(&full->ta, ta.p, rows, s->K, ta.ld, 64, 128);
-    // forward: W [out, in] K-major, tile [64 n][64 k]; dgrad: the same matrix read as [k = out][n = in]
-    e = e && slab_encode_2d(&full->tb, w, L.out, L.in, L.ld_b, 64, 64);
-    if (!e) { ok = false; why = "cuTensorMapEncodeTiled failed"; return nullptr; }
-    const int tiles = (s->N + 63) / 64;
-    max_tiles = std::max(max_tiles, (tiles + c->slab_cluster - 1) / c->slab_cluster);
-    return s;
-  }
-  void set_twin(SlabStepInfo* s, const float* f32) {
-    const Twin t = c->twin(f32);
-    if (t.p == nullptr) { ok = false; why = "slab output has no bf16 twin"; return; }
-    s->twin = reinterpret_cast<__nv_bfloat16*>(t.p); s->ld_twin = t.ld;
-  }
-  // forward of one MLP; last_epi / last_twin describe what happens to the last layer's output
-  void mlp_fwd(const Mlp& m, const float* params, int slot, const float* in, Acts& a, int last_epi, const float* last_twin) {
-    const float* cur = in;
-    const int n = static_cast<int>(m.layers.size());
-    for (int i = 0; i < n && ok; ++i) {
-      const Linear& L = m.layers[i];
-      SlabStepInfo* s = gemm(cur, L, slot, false);
-      if (!s) return;
-      s->bias = params + L.b;
-      if (i < n - 1) {
-        s->epi = (m.norm != NORM_NONE) ? EPI_FWD_NORM : EPI_FWD_ACT;
-        s->norm = m.norm; s->eps = c->sem.norm_eps;
-        s->gamma = L.g >= 0 ? params + L.g : nullptr; s->beta = L.beta >= 0 ? params + L.beta : nullptr;
-        s->out = a.z[i]; s->ld_out = L.out; s->rstd = a.rstd[i]; s->mean = a.mean[i];
-        set_twin(s, a.x[i]);
-        cur = a.x[i];
-      } else {
-        s->epi = last_epi; s->out = a.out; s->ld_out = L.out;
-        if (last_twin != nullptr) set_twin(s, last_twin);
-      }
-    }
-  }
-  // input-gradient chain of one MLP from d_out down to dz of the first layer (and optionally through the first layer)
-  //   first: 0 = stop at dz[0]; 1 = EPI_NONE (accumulate into the next GEMM); 2 = the `first_*` epilogue below
-  void mlp_bwd(const Mlp& m, const float* params, int slot, float* grads, const Acts& a, const float* d_out, int first,
-               bool first_accumulate, int first_epi, float* first_out, int first_ld, const float* first_twin, float* first_gbias) {
-    const int n = static_cast<int>(m.layers.size());
-    const float* d = d_out;
-    for (int i = n - 1; i >= 0 && ok; --i) {
-      const Linear& L = m.layers[i];
-      if (i > 0) {
-        const Linear& Lp = m.layers[i - 1];
-        SlabStepInfo* s = gemm(d, L, slot, true);
-        if (!s) return;
-        s->epi = (m.norm != NORM_NONE) ? EPI_BWD_NORM : EPI_BWD_ACT;
-        s->norm = m.norm;
-        s->gamma = Lp.g >= 0 ? params + Lp.g : nullptr; s->beta = Lp.beta >= 0 ? params + Lp.beta : nullptr;
-        s->out = a.z[i - 1]; s->ld_out = Lp.out; s->rstd = a.rstd[i - 1]; s->mean = a.mean[i - 1];
-        set_twin(s, a.dz[i - 1]);
-        if (grads != nullptr) {
-          s->g_gamma = Lp.g >= 0 ? grads + Lp.g : nullptr; s->g_beta = Lp.beta >= 0 ? grads + Lp.beta : nullptr;
-          s->g_bias = grads + Lp.b;
-        }
-        d = a.dz[i - 1];
-      } else if (first != 0) {
-        SlabStepInfo* s = gemm(d, L, slot, true);
-        if (!s) return;
-        s->accumulate = first_accumulate ? 1 : 0;
-        if (first == 1) { s->epi = EPI_NONE; }
-        else {
-          s->epi = first_epi; s->out = first_out; s->ld_out = first_ld; s->g_bias = first_gbias;
-          if (first_twin != nullptr) set_twin(s, first_twin);
-        }
-      }
-    }
-  }
-  int finish(cudaStream_t st, int prog_id = 0) {
-    p.timing = c->slab_timing_on ? c->slab_timing + 448 * prog_id : nullptr;
-    if (!ok) return fail(c, REPPO_ERR_INVALID, "slab program: " + why);
-    int cols = 64;
-    while (cols < 64 * max_tiles) cols *= 2;
-    if (cols > 256) return fail(c, REPPO_ERR_UNSUPPORTED, "slab program: layer too wide for the cluster");
-    p.tmem_cols = cols;
-    const cudaError_t e = launch_slab(p, c->slab_cluster, st);
-    ++c->launches;
-    if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("launch_slab: ") + cudaGetErrorString(e));
-    return REPPO_OK;
-  }
-};
-
-// weight gradients of one MLP after a slab program produced every dz twin (bias / norm gradients are already in)
-int mlp_wgrads(reppo_ctx* c, const Mlp& m, float* grads, const float* in, int rows, const Acts& a, const float* d_out,
-               cudaStream_t wst) {
-  const int n = static_cast<int>(m.layers.size());
-  for (int i = n - 1; i >= 0; --i) {
-    const Linear& L = m.layers[i];
-    RET(linear_wgrad(c, L, i == n - 1 ? d_out : a.dz[i], i == 0 ? in : a.x[i - 1], rows, grads + L.w, wst));
   }
   return REPPO_OK;
 }
@@ -711,12 +501,11 @@ TrunkBufs trunk_main(reppo_ctx* c) { return TrunkBufs{&c->fa, &c->ha, c->xs, c->
 TrunkBufs trunk_actor(reppo_ctx* c) { return TrunkBufs{&c->fa2, &c->ha2, c->xs2, c->dxs_a, c->dfeat_a, c->dlogits_a}; }
 
 // encoder + swish(features) -> xs
-int critic_trunk_encoder(reppo_ctx* c, const float* cp, int cslot, const float* x0, int rows, const TrunkBufs& tb, cudaStream_t st,
-                         ThinIn* thin = nullptr) {
+int critic_trunk_encoder(reppo_ctx* c, const float* cp, int cslot, const float* x0, int rows, const TrunkBufs& tb, cudaStream_t st) {
   const Twin tw = c->twin(tb.xs);
-  if (c->tc && getenv("REPPO_NO_FUSE_ACT") == nullptr) {
+  if (c->tc && !knobs().no_fuse_act) {
     // swish(features), the input of both heads, leaves the encoder's last GEMM epilogue directly as bf16
-    RET(mlp_forward(c, c->feature, cp, cslot, x0, rows, *tb.fa, st, tw, thin));
+    RET(mlp_forward(c, c->feature, cp, cslot, x0, rows, *tb.fa, st, tw));
   } else {
     RET(mlp_forward(c, c->feature, cp, cslot, x0, rows, *tb.fa, st));
     CK(launch_norm_act_fwd(NORM_NONE, tb.fa->out, nullptr, nullptr, rows, c->shape.critic_hidden, 0.f, c->tc ? nullptr : tb.xs,
@@ -725,25 +514,20 @@ int critic_trunk_encoder(reppo_ctx* c, const float* cp, int cslot, const float* 
   return REPPO_OK;
 }
 int critic_trunk(reppo_ctx* c, const float* cp, int cslot, const float* x0, int rows, bool with_pred, const TrunkBufs& tb,
-                 cudaStream_t st, ThinIn* thin = nullptr) {
-  RET(critic_trunk_encoder(c, cp, cslot, x0, rows, tb, st, thin));
+                 cudaStream_t st) {
+  RET(critic_trunk_encoder(c, cp, cslot, x0, rows, tb, st));
   RET(mlp_forward(c, c->head, cp, cslot, tb.xs, rows, *tb.ha, st));
   if (with_pred) RET(mlp_forward(c, c->pred, cp, cslot, tb.xs, rows, c->pa, st));
   return REPPO_OK;
 }
 
-int dep(reppo_ctx* c, cudaStream_t from, cudaStream_t to);
+// gradient all-reduce of one chain (0 = critic, 1 = actor); no-op on a single GPU
 int allreduce_grads(reppo_ctx* c, float* g, int64_t n, int chain, cudaStream_t st) {
   if (c->comm[0] == nullptr) return REPPO_OK;
   ncclComm_t comm = (chain == 1 && c->comm[1] != nullptr) ? c->comm[1] : c->comm[0];
-  // With node priorities on, the collective runs from its own highest-priority stream: a low-priority all-reduce that is
-  // dispatched late on one rank keeps the peer's all-reduce kernel spinning (2 GPUs: 123.6 ms vs 115.7 ms without priorities)
-  cudaStream_t cs = c->comm_stream[chain == 1 ? 1 : 0];
-  if (cs != nullptr) RET(dep(c, st, cs));
-  const int r = c->nccl.AllReduce(g, g, static_cast<size_t>(n), /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, cs != nullptr ? cs : st);
+  const int r = c->nccl.AllReduce(g, g, static_cast<size_t>(n), /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, st);
   ++c->launches;
   if (r != 0) return fail(c, REPPO_ERR_NCCL, std::string("ncclAllReduce: ") + c->nccl.GetErrorString(r));
-  if (cs != nullptr) RET(dep(c, cs, st));
   return REPPO_OK;
 }
 
@@ -754,8 +538,10 @@ float inv_rows(const reppo_hyper* hp, int mb) {
 
 // cp / cslot: the critic parameters (and their bf16 shadow slot) this step READS
 // prepped: the metric vector is already initialised and the gradient arena already zero (whole-update path)
+// x0_pre: this minibatch's rows of [critic_obs | action], already gathered (whole-update path); nullptr = gather here
 int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb,
-                     const reppo_hyper* hp, float* metrics, const float* cp, int cslot, cudaStream_t st, bool prepped = false) {
+                     const reppo_hyper* hp, float* metrics, const float* cp, int cslot, cudaStream_t st, bool prepped = false,
+                     float* x0_pre = nullptr) {
   RET(check_rows(c, mb));
   const reppo_shape& sh = c->shape;
   float* cg = s->critic.grads;
@@ -770,62 +556,12 @@ int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
     CK(launch_metrics_init(metrics, kCriticMetricMask, st));
     CK(cudaMemsetAsync(cg, 0, static_cast<size_t>(c->critic_count) * sizeof(float), st));
   }
-  if (c->slab) {
-    // the whole forward / loss / input-gradient chain as one cluster kernel; weight gradients follow on side streams
-    SlabBuilder sb(c, mb);
-    SlabRowArgs& r = sb.p.r;
-    r.critic_obs = b->critic_obs; r.action = b->action; r.idx = idx;
-    r.D = sh.obs_dim; r.Dc = sh.critic_obs_dim; r.A = sh.action_dim; r.K0 = c->K0;
-    const Twin tx0 = c->twin(c->x0), tdl = c->twin(c->dlogits);
-    r.x0_twin = reinterpret_cast<__nv_bfloat16*>(tx0.p); r.x0_ld = tx0.ld;
-    r.head_out = c->ha.out; r.ld_head = sh.num_bins; r.zero_dist = cp + c->zero_dist_off; r.hl = c->hl;
-    r.target = b->target; r.truncated = b->truncated; r.inv_rows = inv; r.no_mask = no_mask;
-    r.dl_twin = reinterpret_cast<__nv_bfloat16*>(tdl.p); r.dl_ld = tdl.ld;
-    r.g_bias_head = cg + c->head.layers.back().b; r.g_zero = cg + c->zero_dist_off; r.metrics = metrics;
-    r.next_emb = b->next_emb; r.reward = b->reward; r.done = b->done; r.P = c->pred_out; r.H = Hc;
-    r.reward_head = c->sem.reward_head; r.mask_done = c->sem.aux_mask_done; r.aux_mult = hp->aux_loss_mult;
-    sb.row(ROW_GATHER_CRITIC);
-    sb.mlp_fwd(c->feature, cp, cslot, c->x0, c->fa, EPI_FWD_ACT, c->xs);
-    sb.mlp_fwd(c->head, cp, cslot, c->xs, c->ha, EPI_FWD_OUT, nullptr);
-    sb.row(ROW_CE);
-    sb.mlp_fwd(c->pred, cp, cslot, c->xs, c->pa, EPI_FWD_AUX, c->dpred);
-    if (sb.ok) sb.p.steps[sb.p.num_steps - 1].f.g_bias = cg + c->pred.layers.back().b;
-    sb.mlp_bwd(c->head, cp, cslot, cg, c->ha, c->dlogits, 0, false, 0, nullptr, 0, nullptr, nullptr);
-    sb.mlp_bwd(c->pred, cp, cslot, cg, c->pa, c->dpred, 0, false, 0, nullptr, 0, nullptr, nullptr);
-    // d swish(features) = both heads' input gradients summed in one TMEM accumulator, times swish'(features)
-    if (SlabStepInfo* s1 = sb.gemm(c->ha.dz[0], c->head.layers[0], cslot, true)) s1->epi = EPI_NONE;
-    if (SlabStepInfo* s2 = sb.gemm(c->pa.dz[0], c->pred.layers[0], cslot, true)) {
-      s2->accumulate = 1; s2->epi = EPI_BWD_ACT; s2->out = c->fa.out; s2->ld_out = Hc;
-      s2->g_bias = cg + c->feature.layers.back().b;
-      sb.set_twin(s2, c->dfeat);
-    }
-    sb.mlp_bwd(c->feature, cp, cslot, cg, c->fa, c->dfeat, 0, false, 0, nullptr, 0, nullptr, nullptr);
-    RET(sb.finish(st));
-    RET(dep(c, st, sw));
-    RET(dep(c, st, s1));
-    RET(mlp_wgrads(c, c->head, cg, c->xs, mb, c->ha, c->dlogits, sw));
-    RET(mlp_wgrads(c, c->pred, cg, c->xs, mb, c->pa, c->dpred, s1));
-    RET(mlp_wgrads(c, c->feature, cg, c->x0, mb, c->fa, c->dfeat, st));
-    RET(dep(c, s1, st));
-    RET(dep(c, sw, st));
-    return REPPO_OK;
-  }
-  Twin tw = c->twin(c->x0);
-  // encoder, then swish(features) feeds two independent heads.  Tensor-core mode: the minibatch gather and the thin first
-  // Linear (K = obs + action dims) run as ONE SIMT kernel; otherwise gather, then the GEMM path.
-  ThinIn thin;
-  thin.a = b->critic_obs; thin.da = sh.critic_obs_dim; thin.lda = sh.critic_obs_dim;
-  thin.b = b->action; thin.db = sh.action_dim; thin.ldb = sh.action_dim; thin.idx = idx;
-  bool thin_ok = false;
-  if (c->tc && getenv("REPPO_NO_FUSE_ACT") == nullptr) {
-    const Twin txs = c->twin(c->xs);
-    RET(mlp_forward(c, c->feature, cp, cslot, c->x0, mb, c->fa, st, txs, &thin));
-    thin_ok = thin.done;
-  }
-  if (!thin_ok) {
-    CK(launch_gather_concat(b->critic_obs, sh.critic_obs_dim, b->action, sh.action_dim, idx, 0, mb, c->x0, c->K0, tw.p, tw.ld, st));
-    RET(critic_trunk_encoder(c, cp, cslot, c->x0, mb, trunk_main(c), st));
-  }
+  float* x0 = x0_pre ? x0_pre : c->x0;
+  Twin tw = c->twin(x0);
+  // encoder, then swish(features) feeds two independent heads
+  if (x0_pre == nullptr)
+    CK(launch_gather_concat(b->critic_obs, sh.critic_obs_dim, b->action, sh.action_dim, idx, 0, mb, x0, c->K0, tw.p, tw.ld, st));
+  RET(critic_trunk_encoder(c, cp, cslot, x0, mb, trunk_main(c), st));
   RET(dep(c, st, s1));
   // --- branch s1: prediction head forward, aux loss, backward down to d swish(features)
   RET(mlp_forward(c, c->pred, cp, cslot, c->xs, mb, c->pa, s1));
@@ -840,18 +576,13 @@ int critic_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
   tw = c->twin(c->dlogits);
   CK(launch_critic_ce(c->ha.out, sh.num_bins, cp + c->zero_dist_off, c->hl, b->target, b->truncated, idx, mb, inv, no_mask,
                       c->dlogits, metrics, tw.p, tw.ld, cg + c->head.layers.back().b, cg + c->zero_dist_off, st));
-  // d feat = (d swish(feat) from both heads) * swish'(feat); its column sums are the bias gradient of the encoder's last
-  // Linear.  Tensor-core mode: fused into the head's last dgrad (the pred branch's contribution enters as an addend).
-  FusedIn fin;
-  fin.z = c->fa.out; fin.addend = c->dxs2; fin.dz = c->dfeat; fin.g_bias = cg + c->feature.layers.back().b; fin.join_from = s1;
-  RET(mlp_backward(c, c->head, cp, cslot, cg, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, true, st, sw, &fin));
-  if (!fin.done) {
-    RET(dep(c, s1, st));
-    tw = c->twin(c->dfeat);
-    CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->dxs2, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, Hc,
-                           c->tc ? nullptr : c->dfeat, nullptr, nullptr, cg + c->feature.layers.back().b, tw.p, tw.ld, st));
-  }
-  RET(mlp_backward(c, c->feature, cp, cslot, cg, c->x0, mb, c->fa, c->dfeat, nullptr, GEMM_STORE, nullptr, 0.f, true, st, sw));
+  RET(mlp_backward(c, c->head, cp, cslot, cg, c->xs, mb, c->ha, c->dlogits, c->dxs, GEMM_STORE, nullptr, 0.f, true, st, sw));
+  // d feat = (d swish(feat) from both heads) * swish'(feat); its column sums are the bias gradient of the encoder's last Linear
+  RET(dep(c, s1, st));
+  tw = c->twin(c->dfeat);
+  CK(launch_norm_act_bwd(NORM_NONE, c->dxs, c->dxs2, c->fa.out, nullptr, nullptr, nullptr, nullptr, mb, Hc,
+                         c->tc ? nullptr : c->dfeat, nullptr, nullptr, cg + c->feature.layers.back().b, tw.p, tw.ld, st));
+  RET(mlp_backward(c, c->feature, cp, cslot, cg, x0, mb, c->fa, c->dfeat, nullptr, GEMM_STORE, nullptr, 0.f, true, st, sw));
   RET(dep(c, sw, st));
   return REPPO_OK;
 }
@@ -876,7 +607,7 @@ ActorConsts actor_consts(const reppo_ctx* c, const reppo_hyper* hp) {
 int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb,
                     const float* eps_pi, const float* eps_kl, const reppo_hyper* hp, float* metrics, const float* old_table,
                     cudaStream_t prefix_stream, const float* cp, int cslot, cudaEvent_t critic_ready, cudaEvent_t critic_read_done,
-                    cudaStream_t st, bool prepped = false) {
+                    cudaStream_t st, bool prepped = false, float* xa0_pre = nullptr, float* x0a_pre = nullptr) {
   RET(check_rows(c, mb));
   if (hp->kl_clip_mode < 0 || hp->kl_clip_mode > 2) return fail(c, REPPO_ERR_INVALID, "unknown actor_kl_clip_mode");
   const reppo_shape& sh = c->shape;
@@ -895,161 +626,51 @@ int actor_grad_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, co
     CK(launch_metrics_init(metrics, kActorMetricMask, pre));
     CK(cudaMemsetAsync(ag, 0, static_cast<size_t>(c->actor_count) * sizeof(float), pre));
   }
-  if (c->slab) {
-    if (old_table == nullptr) {
-      // stand-alone call without a behaviour-policy table: evaluate actor_old on this minibatch (separate kernels)
-      const Twin t0 = c->twin(c->xa0);
-      CK(launch_gather_concat(b->obs, sh.obs_dim, nullptr, 0, idx, 0, mb, c->xa0, sh.obs_dim, t0.p, t0.ld, pre));
-      RET(mlp_forward(c, c->actor, s->actor_old, SLOT_ACTOR_OLD, c->xa0, mb, c->oa, pre));
-    }
-    auto fill_rows = [&](SlabRowArgs& r) {
-      r.obs = b->obs; r.critic_obs = b->critic_obs; r.idx = idx;
-      r.D = sh.obs_dim; r.Dc = Dc; r.A = A; r.K0 = c->K0;
-      const Twin tx0 = c->twin(c->x0a), txa = c->twin(c->xa0), tdl = c->twin(tb.dlogits), tdo = c->twin(c->dout);
-      r.x0_twin = reinterpret_cast<__nv_bfloat16*>(tx0.p); r.x0_ld = tx0.ld;
-      r.xa0_twin = reinterpret_cast<__nv_bfloat16*>(txa.p); r.xa0_ld = txa.ld;
-      r.x0a = c->x0a;
-      r.head_out = tb.ha->out; r.ld_head = sh.num_bins; r.zero_dist = cp + c->zero_dist_off; r.hl = c->hl;
-      r.inv_rows = inv; r.dl_twin = reinterpret_cast<__nv_bfloat16*>(tdl.p); r.dl_ld = tdl.ld; r.metrics = metrics;
-      r.actor_out = c->aa.out; r.old_out = old_table ? old_table : c->oa.out; r.old_idx = old_table ? idx : nullptr;
-      r.eps_pi = eps_pi; r.eps_kl = eps_kl; r.kl_samples = sh.kl_samples; r.ac = ac;
-      r.logp = c->logp; r.kl = c->kl; r.gmu = c->gmu; r.gsig = c->gsig; r.q = c->q;
-      r.dx0 = c->dx0; r.actor_params = ap; r.actor_grads = ag;
-      r.dout_twin = reinterpret_cast<__nv_bfloat16*>(tdo.p); r.dout_ld = tdo.ld;
-      r.g_bias_actor_last = ag + c->actor.layers.back().b;
-    };
-    {   // prefix: policy forward + sampling (independent of the critic update that precedes the rest)
-      SlabBuilder sb(c, mb);
-      fill_rows(sb.p.r);
-      sb.row(ROW_GATHER_ACTOR);
-      sb.mlp_fwd(c->actor, ap, SLOT_ACTOR, c->xa0, c->aa, EPI_FWD_OUT, nullptr);
-      sb.row(ROW_SAMPLE);
-      RET(sb.finish(pre, 1));
-    }
-    RET(dep(c, pre, st));
-    if (critic_ready != nullptr && cudaStreamWaitEvent(st, critic_ready, 0) != cudaSuccess)
-      return fail(c, REPPO_ERR_CUDA, "cudaStreamWaitEvent failed");
-    {   // Q(s, a) through the frozen critic, dQ/da, the policy gradient and the policy's input-gradient chain
-      SlabBuilder sb(c, mb);
-      fill_rows(sb.p.r);
-      sb.mlp_fwd(c->feature, cp, cslot, c->x0a, *tb.fa, EPI_FWD_ACT, tb.xs);
-      sb.mlp_fwd(c->head, cp, cslot, tb.xs, *tb.ha, EPI_FWD_OUT, nullptr);
-      sb.row(ROW_Q);
-      sb.mlp_bwd(c->head, cp, cslot, nullptr, *tb.ha, tb.dlogits, 2, false, EPI_BWD_ACT, tb.fa->out, sh.critic_hidden, tb.dfeat, nullptr);
-      sb.mlp_bwd(c->feature, cp, cslot, nullptr, *tb.fa, tb.dfeat, 2, false, EPI_BWD_OUT, c->dx0, c->K0, nullptr, nullptr);
-      sb.row(ROW_ACTOR_GRAD);
-      sb.mlp_bwd(c->actor, ap, SLOT_ACTOR, ag, c->aa, c->dout, 0, false, 0, nullptr, 0, nullptr, nullptr);
-      RET(sb.finish(st, 2));
-    }
-    if (critic_read_done != nullptr && cudaEventRecord(critic_read_done, st) != cudaSuccess)
-      return fail(c, REPPO_ERR_CUDA, "cudaEventRecord failed");
-    RET(mlp_wgrads(c, c->actor, ag, c->xa0, mb, c->aa, c->dout, st));
-    return REPPO_OK;
-  }
-  Twin tw = c->twin(c->xa0);
-  const Twin tx0 = c->twin(c->x0a);
-  const int na = static_cast<int>(c->actor.layers.size());
-  // ---- policy forward.  Tensor-core mode: gather + thin first Linear as one SIMT kernel, the policy head (H -> 2A)
-  // inside the sampling kernel; otherwise (or for shapes outside the thin kernels) gather, GEMMs, sample.
-  ThinIn thin_a;
-  thin_a.a = b->obs; thin_a.da = sh.obs_dim; thin_a.lda = sh.obs_dim; thin_a.idx = idx;
-  bool head_fused = false, x0a_gathered = false;
-  if (c->tc) RET(mlp_forward(c, c->actor, ap, SLOT_ACTOR, c->xa0, mb, c->aa, pre, Twin{}, &thin_a, /*skip_last=*/true));
-  if (!thin_a.done) {
-    // policy input and the observation part of the critic input, one launch
-    CK(launch_gather_pair(b->obs, sh.obs_dim, b->critic_obs, Dc, idx, mb, c->xa0, sh.obs_dim, tw.p, tw.ld, c->x0a, c->K0, tx0.p,
-                          tx0.ld, pre));
-    x0a_gathered = true;
-    RET(mlp_forward(c, c->actor, ap, SLOT_ACTOR, c->xa0, mb, c->aa, pre, Twin{}, nullptr, /*skip_last=*/c->tc));
-  }
-  if (old_table == nullptr) {
-    if (thin_a.done) {   // the behaviour policy's GEMM path needs the gathered input
-      CK(launch_gather_concat(b->obs, sh.obs_dim, nullptr, 0, idx, 0, mb, c->xa0, sh.obs_dim, tw.p, tw.ld, pre));
-    }
-    RET(mlp_forward(c, c->actor, s->actor_old, SLOT_ACTOR_OLD, c->xa0, mb, c->oa, pre));
-  }
+  // xa0_pre / x0a_pre: this minibatch's rows of obs and of [critic_obs | .], already gathered (whole-update path)
+  float* xa0 = xa0_pre ? xa0_pre : c->xa0;
+  float* x0a = x0a_pre ? x0a_pre : c->x0a;
+  Twin tw = c->twin(xa0);
+  const Twin tx0 = c->twin(x0a);
+  // ---- policy forward: policy input and the observation part of the critic input gathered by one launch
+  if (xa0_pre == nullptr)
+    CK(launch_gather_pair(b->obs, sh.obs_dim, b->critic_obs, Dc, idx, mb, xa0, sh.obs_dim, tw.p, tw.ld, x0a, c->K0, tx0.p, tx0.ld, pre));
+  RET(mlp_forward(c, c->actor, ap, SLOT_ACTOR, xa0, mb, c->aa, pre));
+  if (old_table == nullptr) RET(mlp_forward(c, c->actor, s->actor_old, SLOT_ACTOR_OLD, xa0, mb, c->oa, pre));
   const float* old_out = old_table ? old_table : c->oa.out;
   const int32_t* old_idx = old_table ? idx : nullptr;
-  if (c->tc) {
-    const Linear& L3 = c->actor.layers.back();
-    const Twin txl = c->twin(c->aa.x[na - 2]);
-    const cudaError_t e = launch_actor_head_sample(txl.p, txl.ld, L3.in, c->shadow_b[SLOT_ACTOR] + L3.sb, L3.ld_b, ap + L3.b, c->aa.out,
-                                                   old_out, old_idx, eps_pi, eps_kl, mb, A, sh.kl_samples, ac, c->x0a + Dc, c->K0,
-                                                   c->logp, c->kl, c->gmu, c->gsig, tx0.p ? tx0.p + Dc : nullptr, tx0.ld, pre);
-    if (e == cudaSuccess) { ++c->launches; head_fused = true; }
-    else if (e != cudaErrorNotSupported) return fail(c, REPPO_ERR_CUDA, std::string("launch_actor_head_sample: ") + cudaGetErrorString(e));
-    else RET(linear_fwd(c, L3, ap, SLOT_ACTOR, c->aa.x[na - 2], mb, c->aa.out, Twin{}, pre));
-  }
-  if (!head_fused)
-    CK(launch_actor_sample(c->aa.out, old_out, old_idx, eps_pi, eps_kl, mb, A, sh.kl_samples, ac, c->x0a + Dc, c->K0, c->logp, c->kl,
-                           c->gmu, c->gsig, tx0.p ? tx0.p + Dc : nullptr, tx0.ld, pre));
+  CK(launch_actor_sample(c->aa.out, old_out, old_idx, eps_pi, eps_kl, mb, A, sh.kl_samples, ac, x0a + Dc, c->K0, c->logp, c->kl,
+                         c->gmu, c->gsig, tx0.p ? tx0.p + Dc : nullptr, tx0.ld, pre));
   RET(dep(c, pre, st));
   // ---- Q(s, a) through the (already updated, frozen) critic and dQ/da
   if (critic_ready != nullptr && cudaStreamWaitEvent(st, critic_ready, 0) != cudaSuccess)
     return fail(c, REPPO_ERR_CUDA, "cudaStreamWaitEvent failed");
-  ThinIn thin_c;   // critic input = [critic_obs[idx] | sampled action (local rows of x0a)]
-  thin_c.a = b->critic_obs; thin_c.da = Dc; thin_c.lda = Dc; thin_c.b = c->x0a + Dc; thin_c.db = A; thin_c.ldb = c->K0;
-  thin_c.idx = idx; thin_c.b_local = 1; thin_c.want_x_twin = false;
-  bool trunk_done = false;
-  if (c->tc && getenv("REPPO_NO_FUSE_ACT") == nullptr) {
-    RET(critic_trunk_encoder(c, cp, cslot, c->x0a, mb, tb, st, &thin_c));
-    if (thin_c.done) {
-      RET(mlp_forward(c, c->head, cp, cslot, tb.xs, mb, *tb.ha, st));
-      trunk_done = true;
-    }
-  }
-  if (!trunk_done) {
-    if (!x0a_gathered)
-      CK(launch_gather_concat(b->critic_obs, Dc, nullptr, 0, idx, 0, mb, c->x0a, c->K0, tx0.p, tx0.ld, st));   // action columns stay
-    RET(critic_trunk(c, cp, cslot, c->x0a, mb, false, tb, st));
-  }
+  RET(critic_trunk(c, cp, cslot, x0a, mb, false, tb, st));
   tw = c->twin(tb.dlogits);
   CK(launch_actor_q(tb.ha->out, sh.num_bins, cp + c->zero_dist_off, c->hl, c->kl, mb, inv, ac.kl_mode, ac.kl_bound, c->q,
                     tb.dlogits, tw.p, tw.ld, st));
-  FusedIn fin;
-  fin.z = tb.fa->out; fin.dz = tb.dfeat;
-  RET(mlp_backward(c, c->head, cp, cslot, nullptr, tb.xs, mb, *tb.ha, tb.dlogits, tb.dxs, GEMM_STORE, nullptr, 0.f, false, st, st, &fin));
-  if (!fin.done) {
-    tw = c->twin(tb.dfeat);
-    CK(launch_norm_act_bwd(NORM_NONE, tb.dxs, nullptr, tb.fa->out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden,
-                           c->tc ? nullptr : tb.dfeat, nullptr, nullptr, nullptr, tw.p, tw.ld, st));
-  }
-  // ---- policy gradient.  Tensor-core mode: dQ/da through the critic's thin first Linear, the row math and the policy
-  // head's dgrad in ONE SIMT kernel (two tcgen05 launches fewer on the chain).
-  tw = c->twin(c->dout);
-  bool grad_fused = false;
-  if (c->tc && na >= 2 && c->feature.layers.size() >= 2) {
-    // the critic's input-gradient chain stops at dz of its first layer
-    RET(mlp_backward(c, c->feature, cp, cslot, nullptr, c->x0a, mb, *tb.fa, tb.dfeat, nullptr, GEMM_STORE, nullptr, 0.f, false, st, st));
-    const Linear& L1 = c->feature.layers[0];
-    const Linear& L3 = c->actor.layers.back();
-    const Twin tdz = c->twin(tb.fa->dz[0]);
-    const cudaError_t e = launch_actor_grad_thin(tdz.p, tdz.ld, L1.out, c->shadow_b[cslot] + L1.sb, L1.ld_b, Dc,
-                                                 c->shadow_b[SLOT_ACTOR] + L3.sb, L3.ld_b, L3.in, c->aa.out, eps_pi, c->x0a + Dc, c->K0,
-                                                 c->logp, c->kl, c->q, c->gmu, c->gsig, ap, mb, A, inv, ac, c->dout, ag, metrics,
-                                                 tw.p, tw.ld, ag + L3.b, c->aa.tmp, st);
-    if (e == cudaSuccess) { ++c->launches; grad_fused = true; }
-    else if (e != cudaErrorNotSupported) return fail(c, REPPO_ERR_CUDA, std::string("launch_actor_grad_thin: ") + cudaGetErrorString(e));
-    else RET(linear_dgrad(c, L1, cp, cslot, tb.fa->dz[0], mb, c->dx0, GEMM_STORE, st));
-  } else {
-    RET(mlp_backward(c, c->feature, cp, cslot, nullptr, c->x0a, mb, *tb.fa, tb.dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, false, st, st));
-  }
+  RET(mlp_backward(c, c->head, cp, cslot, nullptr, tb.xs, mb, *tb.ha, tb.dlogits, tb.dxs, GEMM_STORE, nullptr, 0.f, false, st, st));
+  tw = c->twin(tb.dfeat);
+  CK(launch_norm_act_bwd(NORM_NONE, tb.dxs, nullptr, tb.fa->out, nullptr, nullptr, nullptr, nullptr, mb, sh.critic_hidden,
+                         c->tc ? nullptr : tb.dfeat, nullptr, nullptr, nullptr, tw.p, tw.ld, st));
+  RET(mlp_backward(c, c->feature, cp, cslot, nullptr, x0a, mb, *tb.fa, tb.dfeat, c->dx0, GEMM_STORE, nullptr, 0.f, false, st, st));
   // last read of the critic snapshot: the critic chain may overwrite it from here on
   if (critic_read_done != nullptr && cudaEventRecord(critic_read_done, st) != cudaSuccess)
     return fail(c, REPPO_ERR_CUDA, "cudaEventRecord failed");
-  if (!grad_fused)
-    CK(launch_actor_grad(c->aa.out, eps_pi, c->x0a + Dc, c->K0, c->dx0 + Dc, c->K0, c->logp, c->kl, c->q, c->gmu, c->gsig, ap,
-                         mb, A, inv, ac, c->dout, ag, metrics, tw.p, tw.ld, ag + c->actor.layers.back().b, st));
-  RET(mlp_backward(c, c->actor, ap, SLOT_ACTOR, ag, c->xa0, mb, c->aa, c->dout, nullptr, GEMM_STORE, nullptr, 0.f, true, st, sw, nullptr,
-                   /*last_dgrad_done=*/grad_fused));
+  // ---- policy gradient
+  tw = c->twin(c->dout);
+  CK(launch_actor_grad(c->aa.out, eps_pi, x0a + Dc, c->K0, c->dx0 + Dc, c->K0, c->logp, c->kl, c->q, c->gmu, c->gsig, ap,
+                       mb, A, inv, ac, c->dout, ag, metrics, tw.p, tw.ld, ag + c->actor.layers.back().b, st));
+  RET(mlp_backward(c, c->actor, ap, SLOT_ACTOR, ag, xa0, mb, c->aa, c->dout, nullptr, GEMM_STORE, nullptr, 0.f, true, st, sw));
   RET(dep(c, sw, st));
   return REPPO_OK;
 }
 
 // slot < 0: plain arena (no bf16 shadow to refresh)
 // p_out: where the updated parameters go (nullptr = in place); partials: scratch of the global-norm reduction
+// chain: which grid-barrier words the kernel uses (0 critic chain, 1 actor chain, 2 stand-alone) -- launches that may run
+// concurrently must not share them
 int clip_adam_impl(reppo_ctx* c, const reppo_net_state* net, int64_t n, const reppo_hyper* hp, float* gn_out, int slot,
-                   const float* p_in, float* p_out, float* partials, cudaStream_t st, bool zero_grads = false) {
+                   const float* p_in, float* p_out, float* partials, int chain, cudaStream_t st, bool zero_grads = false) {
   if (c->ws == nullptr) return fail(c, REPPO_ERR_WORKSPACE, "workspace not set (reppo_set_workspace)");
   ShadowTable sh{};
   if (c->tc && slot >= 0) {
@@ -1058,37 +679,37 @@ int clip_adam_impl(reppo_ctx* c, const reppo_net_state* net, int64_t n, const re
         ShadowEntry& e = sh.e[sh.n++];
         e.start = L.w; e.end = L.w + static_cast<int64_t>(L.out) * L.in; e.in = L.in; e.ld = L.ld_b;
         e.dst = c->shadow_b[slot] + L.sb;
-        e.dst_t = (L.st >= 0) ? c->shadow_t[slot] + L.st : nullptr; e.ld_t = L.ld_t;
       }
     };
-    if (slot == SLOT_CRITIC || slot == SLOT_CRITIC_ALT || slot == SLOT_CRITIC_ALT2) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
+    if (slot == SLOT_CRITIC || slot == SLOT_CRITIC_ALT) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
   }
   AdamConsts a{};
   a.lr = hp->lr; a.b1 = 0.9f; a.b2 = 0.999f; a.eps = 1e-8f;
   a.weight_decay = c->sem.torch_opt ? 0.01f : 0.f;  // torch.optim.AdamW default (src/torchrl/reppo.py:527-534)
   a.max_grad_norm = hp->max_grad_norm;
   a.torch_clip = c->sem.torch_opt;
+  a.anneal_steps = hp->lr_anneal_steps > 0 ? hp->lr_anneal_steps : 0;
   CK(launch_clip_adam(p_in ? p_in : net->params, p_out ? p_out : net->params, net->grads, net->adam_m, net->adam_v, n, net->step,
-                      partials ? partials : c->partials, a, &sh, gn_out, zero_grads ? 1 : 0, st));
-  ++c->launches;  // two kernels
+                      partials ? partials : c->partials, c->adam_bar + 2 * chain, a, &sh, gn_out, zero_grads ? 1 : 0, st));
   return REPPO_OK;
 }
 
 int critic_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb,
-                     const reppo_hyper* hp, float* metrics, cudaStream_t st, bool prepped = false) {
-  RET(critic_grad_impl(c, s, b, idx, mb, hp, metrics, s->critic.params, SLOT_CRITIC, st, prepped));
+                     const reppo_hyper* hp, float* metrics, cudaStream_t st, bool prepped = false, float* x0_pre = nullptr) {
+  RET(critic_grad_impl(c, s, b, idx, mb, hp, metrics, s->critic.params, SLOT_CRITIC, st, prepped, x0_pre));
   RET(allreduce_grads(c, s->critic.grads, c->critic_count, 0, st));
-  return clip_adam_impl(c, &s->critic, c->critic_count, hp, metrics + M_CRITIC_GRAD_NORM, SLOT_CRITIC, nullptr, nullptr, nullptr, st,
+  return clip_adam_impl(c, &s->critic, c->critic_count, hp, metrics + M_CRITIC_GRAD_NORM, SLOT_CRITIC, nullptr, nullptr, nullptr, 0, st,
                         prepped);
 }
 
 int actor_step_impl(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const int32_t* idx, int mb, const float* eps_pi,
                     const float* eps_kl, const reppo_hyper* hp, float* metrics, const float* old_table,
-                    cudaStream_t prefix_stream, cudaStream_t st, bool prepped = false) {
+                    cudaStream_t prefix_stream, cudaStream_t st, bool prepped = false, float* xa0_pre = nullptr,
+                    float* x0a_pre = nullptr) {
   RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, metrics, old_table, prefix_stream, s->critic.params, SLOT_CRITIC,
-                      nullptr, nullptr, st, prepped));
+                      nullptr, nullptr, st, prepped, xa0_pre, x0a_pre));
   RET(allreduce_grads(c, s->actor.grads, c->actor_count, 1, st));
-  return clip_adam_impl(c, &s->actor, c->actor_count, hp, metrics + M_ACTOR_GRAD_NORM, SLOT_ACTOR, nullptr, nullptr, c->partials2, st,
+  return clip_adam_impl(c, &s->actor, c->actor_count, hp, metrics + M_ACTOR_GRAD_NORM, SLOT_ACTOR, nullptr, nullptr, c->partials2, 1, st,
                         prepped);
 }
 
@@ -1117,12 +738,10 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
   // one NCCL communicator serves one chain: pipelining under data parallelism needs the second communicator
   const bool pipe = c->concurrent && c->pipeline && (c->comm[0] == nullptr || c->comm[1] != nullptr);
   cudaStream_t sa = pipe ? c->side[2] : st;   // the actor chain
-  // snapshot j of the critic parameters lives in copy j % depth; depth 3 (REPPO_DEPTH=3) lets the critic chain run two steps
-  // ahead of the actor chain instead of one
-  static const int depth_env = getenv("REPPO_DEPTH") ? atoi(getenv("REPPO_DEPTH")) : 2;
-  const int depth = pipe ? (depth_env == 3 ? 3 : 2) : 1;
-  float* P[3] = {s->critic.params, pipe ? c->cp_alt : s->critic.params, c->cp_alt2};
-  const int S[3] = {SLOT_CRITIC, pipe ? SLOT_CRITIC_ALT : SLOT_CRITIC, SLOT_CRITIC_ALT2};
+  // snapshot j of the critic parameters lives in copy j % depth
+  const int depth = pipe ? 2 : 1;
+  float* P[2] = {s->critic.params, pipe ? c->cp_alt : s->critic.params};
+  const int S[2] = {SLOT_CRITIC, pipe ? SLOT_CRITIC_ALT : SLOT_CRITIC};
   // With per-step metric vectors the whole update is prepared once: all metric rows initialised by one kernel, both
   // gradient arenas cleared once (every Adam launch leaves its arena zeroed for the next step).
   const bool prepped = p->step_metrics != nullptr;
@@ -1132,60 +751,27 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
     CK(cudaMemsetAsync(s->actor.grads, 0, static_cast<size_t>(c->actor_count) * sizeof(float), st));
   }
   if (pipe) RET(dep(c, st, sa));
-  // ---- grouped data-parallel schedule (REPPO_DP_GROUPED=1): iteration k runs the critic gradients of step k and the actor
-  // gradients of step k-1 side by side (both read critic snapshot k), then reduces BOTH gradient arenas in one grouped NCCL
-  // call (one collective launch per iteration instead of two per step), then the two Adam updates side by side.
-  static const bool grouped_env = getenv("REPPO_DP_GROUPED") != nullptr && atoi(getenv("REPPO_DP_GROUPED")) != 0;
-  if (pipe && grouped_env && c->comm[0] != nullptr && c->nccl.GroupStart != nullptr && c->nccl.GroupEnd != nullptr) {
-    const int64_t K = static_cast<int64_t>(p->num_epochs) * p->num_mini_batches;
-    auto step_args = [&](int64_t k, const float*& eps_pi, const float*& eps_kl, const int32_t*& idx, float*& m) {
-      const int e = static_cast<int>(k / p->num_mini_batches), j = static_cast<int>(k % p->num_mini_batches);
-      const int64_t slot = p->noise_per_minibatch ? k : e;
-      eps_pi = p->eps_pi + slot * mb * A;
-      eps_kl = p->eps_kl + slot * ks * mb * A;
-      idx = p->perms + e * per_epoch + static_cast<int64_t>(j) * mb;
-      m = p->step_metrics ? p->step_metrics + k * M_NUM : c->scratch_metrics;
-    };
-    for (int64_t k = 0; k <= K; ++k) {
-      const float *eps_pi = nullptr, *eps_kl = nullptr; const int32_t* idx = nullptr; float* m = nullptr;
-      const int cur = static_cast<int>(k & 1), nxt = static_cast<int>((k + 1) & 1);
-      if (k < K) {
-        step_args(k, eps_pi, eps_kl, idx, m);
-        RET(critic_grad_impl(c, s, b, idx, mb, hp, m, P[cur], S[cur], st, prepped));
-      }
-      if (k >= 1) {   // actor step k-1 reads snapshot k = P[cur] (written by the critic Adam of iteration k-1 on st)
-        step_args(k - 1, eps_pi, eps_kl, idx, m);
-        RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, p->old_policy_out, nullptr, P[cur], S[cur], c->ev_c[(k - 1) & 3],
-                            nullptr, sa, prepped));
-      }
-      RET(dep(c, sa, st));
-      if (c->nccl.GroupStart() != 0) return fail(c, REPPO_ERR_NCCL, "ncclGroupStart failed");
-      int r1 = 0, r2 = 0;
-      if (k < K) r1 = c->nccl.AllReduce(s->critic.grads, s->critic.grads, static_cast<size_t>(c->critic_count), 7, 0, c->comm[0], st);
-      if (k >= 1) r2 = c->nccl.AllReduce(s->actor.grads, s->actor.grads, static_cast<size_t>(c->actor_count), 7, 0, c->comm[0], st);
-      const int r3 = c->nccl.GroupEnd();
-      ++c->launches;
-      if (r1 != 0 || r2 != 0 || r3 != 0) return fail(c, REPPO_ERR_NCCL, "grouped ncclAllReduce failed");
-      RET(dep(c, st, sa));
-      if (k < K) {
-        step_args(k, eps_pi, eps_kl, idx, m);
-        RET(clip_adam_impl(c, &s->critic, c->critic_count, hp, m + M_CRITIC_GRAD_NORM, S[nxt], P[cur], P[nxt], c->partials, st, prepped));
-        if (cudaEventRecord(c->ev_c[k & 3], st) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaEventRecord failed");
-      }
-      if (k >= 1) {
-        step_args(k - 1, eps_pi, eps_kl, idx, m);
-        RET(clip_adam_impl(c, &s->actor, c->actor_count, hp, m + M_ACTOR_GRAD_NORM, SLOT_ACTOR, nullptr, nullptr, c->partials2, sa, prepped));
-      }
-    }
-    RET(dep(c, sa, st));
-    if (K & 1) CK(cudaMemcpyAsync(s->critic.params, P[1], sizeof(float) * c->critic_count, cudaMemcpyDeviceToDevice, st));
-    if (p->metrics != nullptr && p->step_metrics != nullptr)
-      CK(launch_metrics_mean(p->step_metrics, (p->num_epochs - 1) * p->num_mini_batches, p->num_mini_batches, M_NUM, p->metrics, st));
-    return REPPO_OK;
-  }
+  // Pre-gathered first-layer inputs: one gather per EPOCH through that epoch's permutation (three launches) instead of
+  // two per step at the head of both chains; minibatch j is then rows [j mb, (j+1) mb) of the epoch buffers.  Two sets
+  // alternate by epoch; set e % 2 was last read by the actor chain in epoch e - 2.
+  const bool pregather = c->x0_ep[0] != nullptr && per_epoch <= c->shape.max_batch_rows;
+  const int D = c->shape.obs_dim, Dc = c->shape.critic_obs_dim, K0 = c->K0;
   int64_t k = 0;
   for (int e = 0; e < p->num_epochs; ++e) {
+    const int set = e & 1;
+    if (pregather) {
+      const int32_t* eidx = p->perms + e * per_epoch;
+      const int er = static_cast<int>(per_epoch);
+      if (pipe && e >= 2 && cudaStreamWaitEvent(st, c->ev_epoch[set], 0) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaStreamWaitEvent failed");
+      Twin t0 = c->twin(c->x0_ep[set]), t1 = c->twin(c->xa0_ep[set]), t2 = c->twin(c->x0a_ep[set]);
+      CK(launch_gather_concat(b->critic_obs, Dc, b->action, A, eidx, 0, er, c->x0_ep[set], K0, t0.p, t0.ld, st));
+      CK(launch_gather_pair(b->obs, D, b->critic_obs, Dc, eidx, er, c->xa0_ep[set], D, t1.p, t1.ld, c->x0a_ep[set], K0, t2.p, t2.ld, st));
+      if (pipe) RET(dep(c, st, sa));
+    }
     for (int j = 0; j < p->num_mini_batches; ++j, ++k) {
+      float* x0_pre = pregather ? c->x0_ep[set] + static_cast<size_t>(j) * mb * K0 : nullptr;
+      float* xa0_pre = pregather ? c->xa0_ep[set] + static_cast<size_t>(j) * mb * D : nullptr;
+      float* x0a_pre = pregather ? c->x0a_ep[set] + static_cast<size_t>(j) * mb * K0 : nullptr;
       const int64_t slot = p->noise_per_minibatch ? static_cast<int64_t>(e) * p->num_mini_batches + j : e;
       const float* eps_pi = p->eps_pi + slot * mb * A;
       const float* eps_kl = p->eps_kl + slot * ks * mb * A;
@@ -1196,23 +782,24 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
         // the actor-only prefix of this step's actor update is forked here and overlaps the critic update
         cudaStream_t pre = nullptr;
         if (c->concurrent) { pre = c->side[2]; RET(dep(c, st, pre)); }
-        RET(critic_step_impl(c, s, b, idx, mb, hp, m, st, prepped));
-        RET(actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, p->old_policy_out, pre, st, prepped));
+        RET(critic_step_impl(c, s, b, idx, mb, hp, m, st, prepped, x0_pre));
+        RET(actor_step_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, p->old_policy_out, pre, st, prepped, xa0_pre, x0a_pre));
         continue;
       }
       // ---- critic chain (stream st): reads snapshot `cur`, Adam writes snapshot `nxt`
-      RET(critic_grad_impl(c, s, b, idx, mb, hp, m, P[cur], S[cur], st, prepped));
+      RET(critic_grad_impl(c, s, b, idx, mb, hp, m, P[cur], S[cur], st, prepped, x0_pre));
       RET(allreduce_grads(c, s->critic.grads, c->critic_count, 0, st));
       // the copy that receives snapshot k+1 held snapshot k+1-depth, last read by actor step k-depth
       if (k >= depth && cudaStreamWaitEvent(st, c->ev_a[(k - depth) & 3], 0) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaStreamWaitEvent failed");
-      RET(clip_adam_impl(c, &s->critic, c->critic_count, hp, m + M_CRITIC_GRAD_NORM, S[nxt], P[cur], P[nxt], c->partials, st, prepped));
+      RET(clip_adam_impl(c, &s->critic, c->critic_count, hp, m + M_CRITIC_GRAD_NORM, S[nxt], P[cur], P[nxt], c->partials, 0, st, prepped));
       if (cudaEventRecord(c->ev_c[k & 3], st) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaEventRecord failed");
       // ---- actor chain (stream sa): needs snapshot `nxt`
       RET(actor_grad_impl(c, s, b, idx, mb, eps_pi, eps_kl, hp, m, p->old_policy_out, nullptr, P[nxt], S[nxt], c->ev_c[k & 3],
-                          c->ev_a[k & 3], sa, prepped));
+                          c->ev_a[k & 3], sa, prepped, xa0_pre, x0a_pre));
       RET(allreduce_grads(c, s->actor.grads, c->actor_count, 1, sa));
-      RET(clip_adam_impl(c, &s->actor, c->actor_count, hp, m + M_ACTOR_GRAD_NORM, SLOT_ACTOR, nullptr, nullptr, c->partials2, sa, prepped));
+      RET(clip_adam_impl(c, &s->actor, c->actor_count, hp, m + M_ACTOR_GRAD_NORM, SLOT_ACTOR, nullptr, nullptr, c->partials2, 1, sa, prepped));
     }
+    if (pregather && pipe && cudaEventRecord(c->ev_epoch[set], sa) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaEventRecord failed");
   }
   if (pipe) {
     RET(dep(c, sa, st));
@@ -1255,9 +842,9 @@ int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
   reppo_ctx* c = new reppo_ctx();
   c->shape = s;
   c->tc = (s.gemm_mode == REPPO_GEMM_BF16);
-  c->concurrent = (getenv("REPPO_SERIAL") == nullptr);
-  c->fuse_norm = (getenv("REPPO_NO_FUSE_NORM") == nullptr);
-  c->pipeline = (getenv("REPPO_NO_PIPELINE") == nullptr);
+  c->concurrent = !knobs().serial;
+  c->fuse_norm = !knobs().no_fuse_norm;
+  c->pipeline = !knobs().no_pipeline;
   if (s.semantics == REPPO_SEM_JAX) {
     // flax RMSNorm/LayerNorm eps 1e-6; logits + 40.0 * zero_dist (jax_models.py:298); clip 1-1e-4
     // (jaxrl/reppo.py:558); min_std 0.1 because the constructor ignores cfg (jax_models.py:336);
@@ -1274,19 +861,19 @@ int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
   c->maxdim = std::max(std::max(s.critic_hidden, s.actor_hidden),
                        std::max(std::max(s.num_bins, c->pred_out), std::max(std::max(c->K0, s.obs_dim), 2 * s.action_dim)));
 
-  int64_t off = 0, sb = 0, st = 0;
+  int64_t off = 0, sb = 0;
   c->zero_dist_off = 0;
   c->critic_tensors.push_back({"zero_dist", 0, s.num_bins, 0});
   off += s.num_bins;
-  add_fcnn(c->critic_tensors, off, sb, st, c->feature, "feature_module", c->K0, s.critic_hidden, s.critic_hidden, s.enc_layers, false, s.critic_norm);
-  add_fcnn(c->critic_tensors, off, sb, st, c->head, "critic_module", s.critic_hidden, s.critic_hidden, s.num_bins, s.head_layers, true, s.critic_norm);
-  add_fcnn(c->critic_tensors, off, sb, st, c->pred, "pred_module", s.critic_hidden, s.critic_hidden, c->pred_out, s.pred_layers, true, s.critic_norm);
-  c->critic_count = off; c->shadow_b_elems[0] = sb; c->shadow_t_elems[0] = st;
+  add_fcnn(c->critic_tensors, off, sb, c->feature, "feature_module", c->K0, s.critic_hidden, s.critic_hidden, s.enc_layers, false, s.critic_norm);
+  add_fcnn(c->critic_tensors, off, sb, c->head, "critic_module", s.critic_hidden, s.critic_hidden, s.num_bins, s.head_layers, true, s.critic_norm);
+  add_fcnn(c->critic_tensors, off, sb, c->pred, "pred_module", s.critic_hidden, s.critic_hidden, c->pred_out, s.pred_layers, true, s.critic_norm);
+  c->critic_count = off; c->shadow_b_elems[0] = sb;
   c->actor_tensors.push_back({"log_temp", 0, 0, 0});
   c->actor_tensors.push_back({"log_lagrange", 1, 0, 0});
-  off = 2; sb = 0; st = 0;
-  add_fcnn(c->actor_tensors, off, sb, st, c->actor, "model", s.obs_dim, s.actor_hidden, 2 * s.action_dim, s.actor_layers, false, s.actor_norm);
-  c->actor_count = off; c->shadow_b_elems[1] = sb; c->shadow_t_elems[1] = st;
+  off = 2; sb = 0;
+  add_fcnn(c->actor_tensors, off, sb, c->actor, "model", s.obs_dim, s.actor_hidden, 2 * s.action_dim, s.actor_layers, false, s.actor_norm);
+  c->actor_count = off; c->shadow_b_elems[1] = sb;
 
   const double bw = (static_cast<double>(s.vmax) - static_cast<double>(s.vmin)) / (s.num_bins - 1);
   const double sigma = bw * 0.75;
@@ -1300,13 +887,6 @@ int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
     c->hl.den = sqrtf(2.f) * static_cast<float>(sigma) + 1e-6f;               // reppo_util.py:767-769
     c->hl.z_eps = 1e-6f;                                                      // :773
   }
-  {
-    const int hmax = std::max(s.critic_hidden, s.actor_hidden);
-    c->slab = c->tc && getenv("REPPO_SLAB") != nullptr && s.critic_hidden % 64 == 0 && s.actor_hidden % 64 == 0 &&
-              hmax <= 512 && s.action_dim <= 32 && s.num_bins <= 256;
-    c->slab_cluster = hmax / 64;
-    c->slab_timing_on = getenv("REPPO_SLAB_TIMING") != nullptr;
-  }
   c->ws_need = layout_workspace(c, nullptr);
   *out = c;
   return REPPO_OK;
@@ -1317,8 +897,8 @@ void reppo_ctx_destroy(reppo_ctx* c) {
   for (int i = 0; i < reppo_ctx::kGraphSlots; ++i) if (c->graph_exec[i]) cudaGraphExecDestroy(c->graph_exec[i]);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   for (auto& e : c->events) cudaEventDestroy(e);
-  for (int i = 0; i < 2; ++i) if (c->comm_stream[i]) cudaStreamDestroy(c->comm_stream[i]);
   for (int i = 0; i < 4; ++i) { if (c->side[i]) cudaStreamDestroy(c->side[i]); if (c->ev_c[i]) cudaEventDestroy(c->ev_c[i]); if (c->ev_a[i]) cudaEventDestroy(c->ev_a[i]); }
+  for (int i = 0; i < 2; ++i) if (c->ev_epoch[i]) cudaEventDestroy(c->ev_epoch[i]);
   for (int i = 0; i < 2; ++i) if (c->comm[i] && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm[i]);
   delete c;
 }
@@ -1362,10 +942,9 @@ int reppo_set_workspace(reppo_ctx* c, void* workspace, size_t bytes) {
   c->hl.edges = c->edges_d;
   c->hl.support = c->support_d;
   c->invalidate_graphs();
-  if (c->tc) {
-    // bf16 twins / shadows are read through TMA with their padded leading dimension: clear the padding once
-    if (cudaMemset(workspace, 0, c->ws_need) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "clearing the workspace failed");
-  }
+  // bf16 twins / shadows are read through TMA with their padded leading dimension (clear the padding once), and the
+  // optimizer's grid-barrier words start at zero
+  if (cudaMemset(workspace, 0, c->ws_need) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "clearing the workspace failed");
   return reppo_set_bins(c, nullptr, nullptr);
 }
 
@@ -1569,7 +1148,7 @@ int reppo_actor_step(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, c
 }
 int reppo_clip_adam(reppo_ctx* c, const reppo_net_state* net, int64_t n, const reppo_hyper* hp, float* gn, reppo_stream stream) {
   c->launches = 0;
-  return clip_adam_impl(c, net, n, hp, gn, -1, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+  return clip_adam_impl(c, net, n, hp, gn, -1, nullptr, nullptr, nullptr, 2, static_cast<cudaStream_t>(stream));
 }
 
 int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const reppo_plan* p, const reppo_hyper* hp,
@@ -1596,11 +1175,7 @@ int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const
     c->launches = 0;
     cudaError_t e = cudaSuccess;
     if (c->cap_stream == nullptr) {
-      int least = 0, greatest = 0;
-      if (prio_mode() >= 3 && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest < least)
-        e = cudaStreamCreateWithPriority(&c->cap_stream, cudaStreamNonBlocking, prio_mode() == 5 ? greatest : (least + greatest) / 2);
-      else
-        e = cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking);
+      e = cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking);
       if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
     e = cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal);
@@ -1610,9 +1185,7 @@ int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const
     e = cudaStreamEndCapture(c->cap_stream, &graph);
     if (r != REPPO_OK) { if (graph) cudaGraphDestroy(graph); return r; }
     if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-    // single-GPU only by default: with the gradient all-reduces in the chains every assignment tried lost to no priorities
-    // (2 GPUs: 115.6 ms off, 120.5 actor-first with the collectives on highest-priority streams, 123.5 without, 131.3 critic-first)
-    const bool use_prio = prio_enabled() && ((small_step(c) && c->comm[0] == nullptr) || getenv("REPPO_PRIO") != nullptr);
+    const bool use_prio = want_prio(c);   // the side streams were created with the same decision
     e = cudaGraphInstantiate(&c->graph_exec[slot], graph, use_prio ? cudaGraphInstantiateFlagUseNodePriority : 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
@@ -1628,15 +1201,9 @@ int reppo_update(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const
 
 int64_t reppo_launch_count(const reppo_ctx* c) { return c->launches; }
 
-int reppo_debug_buffer(const reppo_ctx* c, const char* name, void** ptr, size_t* bytes) {
-  if (c == nullptr || name == nullptr || ptr == nullptr || bytes == nullptr) return REPPO_ERR_INVALID;
-  if (strcmp(name, "slab_timing") == 0) { *ptr = c->slab_timing; *bytes = 3 * 448 * sizeof(long long); return REPPO_OK; }
-  return REPPO_ERR_INVALID;
-}
-
 static int nccl_load(reppo_ctx* c) {
   if (c->nccl.lib) return REPPO_OK;
-  const char* names[] = {getenv("REPPO_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  const char* names[] = {knobs().nccl_lib, "libnccl.so.2", "libnccl.so"};
   for (const char* n : names) {
     if (n == nullptr) continue;
     c->nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);

@@ -1,7 +1,7 @@
 // fp32 -> bf16 operand staging for the tcgen05 GEMMs (REPPO_GEMM_BF16 mode).
-//  * pack_weights_kernel: after every Adam step the fp32 master weights W[out,in] of one network are
-//    re-rounded into two bf16 shadows in one launch: W (K-major B operand of the forward GEMM) and
-//    W^T (K-major B operand of the dgrad GEMM).  32x32 smem tiles make both writes coalesced.
+//  * pack_weights_kernel: the fp32 master weights W[out,in] of one network re-rounded into their bf16 shadows in
+//    one launch (entry points that receive parameters from the caller; inside an update the Adam kernel refreshes
+//    the shadows itself).  The same shadow serves the forward GEMM (K-major B) and the dgrad GEMM (MN-major B).
 //  * cast_bf16_kernel: plain row-padded cast (stand-alone reppo_linear calls).
 #include <cuda_bf16.h>
 
@@ -14,34 +14,13 @@ namespace reppo {
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const PackTable t) {
   REPPO_PDL_PROLOGUE();
-  __shared__ float tile[32][33];
-  // blockIdx.y = tensor, blockIdx.x = tile index inside the tensor (grid-strided)
+  // blockIdx.y = tensor, blockIdx.x grid-strides over its elements (rows of the shadow are padded to ld_b)
   const PackEntry e = t.e[blockIdx.y];
-  const int tiles_c = (e.in + 31) / 32, tiles_r = (e.out + 31) / 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   __nv_bfloat16* wb = static_cast<__nv_bfloat16*>(e.wb);
-  __nv_bfloat16* wtb = static_cast<__nv_bfloat16*>(e.wtb);
-  for (int tl = blockIdx.x; tl < tiles_c * tiles_r; tl += gridDim.x) {
-    const int r0 = (tl / tiles_c) * 32, c0 = (tl % tiles_c) * 32;
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      const int r = r0 + ty + i, c = c0 + tx;
-      float v = 0.f;
-      if (r < e.out && c < e.in) {
-        v = e.w[static_cast<size_t>(r) * e.in + c];
-        if (wb != nullptr) wb[static_cast<size_t>(r) * e.ld_b + c] = __float2bfloat16_rn(v);
-      }
-      tile[ty + i][tx] = v;
-    }
-    __syncthreads();
-    if (wtb != nullptr) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        const int c = c0 + ty + i, r = r0 + tx;  // transposed: row index of W^T is the column of W
-        if (c < e.in && r < e.out) wtb[static_cast<size_t>(c) * e.ld_t + r] = __float2bfloat16_rn(tile[tx][ty + i]);
-      }
-    }
-    __syncthreads();
+  const int total = e.out * e.in;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / e.in, c = i - r * e.in;
+    wb[static_cast<size_t>(r) * e.ld_b + c] = __float2bfloat16_rn(e.w[i]);
   }
 }
 

@@ -22,83 +22,19 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "knobs.h"
 #include "launch.h"
+#include "tc_ptx.cuh"
+#include "tmap.h"
 
 namespace reppo {
+
+using namespace tcx;
 
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int TC_UMMA_K = 16;
 constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-
-// ---- PTX wrappers --------------------------------------------------------------------------------
-REPPO_DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-REPPO_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-REPPO_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-REPPO_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-REPPO_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-REPPO_DEVINL void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-REPPO_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-REPPO_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-REPPO_DEVINL void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-REPPO_DEVINL void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
-REPPO_DEVINL void tc_ld_32x32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, sm_100 version bit
-REPPO_DEVINL uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;   // version = 1 (Blackwell)
-  d |= static_cast<uint64_t>(2) << 61;   // layout type SWIZZLE_128B
-  return d;
-}
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M = 128
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
@@ -120,24 +56,6 @@ struct TcSmem {
   static constexpr int kStatBytes = (kAllStatOffsetF + 8 * 2 * 128) * 4;
   static constexpr int kTotal = kStatOffset + kStatBytes + 1024;                   // + alignment slack
 };
-
-REPPO_DEVINL void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-REPPO_DEVINL void st_dsmem_f32(float* local_smem_ptr, uint32_t cta_rank, float v) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(cta_rank));
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
-}
-REPPO_DEVINL float fast_swish(float x) { return x * __fdividef(1.f, 1.f + __expf(-fmaxf(x, -80.f))); }
-REPPO_DEVINL float ld_dsmem_f32(const float* local_smem_ptr, uint32_t cta_rank) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(cta_rank));
-  float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
-  return v;
-}
 
 // mode: GEMM_STORE / GEMM_ACCUM / GEMM_ATOMIC.  A_MN / B_MN: operand is MN-major (reduction dim is the outer dim).
 // NORM != NORM_NONE: forward Linear with the whole FCNN block fused into the epilogue
@@ -333,7 +251,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           *reinterpret_cast<float4*>(cp) = x;
           if (act_out != nullptr) {   // fused epilogue: swish(y) as the bf16 operand of the next GEMM
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(fast_swish(x.x), fast_swish(x.y)), hi = __floats2bfloat162_rn(fast_swish(x.z), fast_swish(x.w));
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(fswish(x.x), fswish(x.y)), hi = __floats2bfloat162_rn(fswish(x.z), fswish(x.w));
             uint2 u;
             u.x = *reinterpret_cast<const uint32_t*>(&lo);
             u.y = *reinterpret_cast<const uint32_t*>(&hi);
@@ -422,8 +340,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         *reinterpret_cast<float4*>(C + static_cast<size_t>(row) * ldc + col) = x;
         const float rr = rs[r], mm = mu[r];
         // bf16-operand mode: SFU sigmoid (ex2.approx / rcp.approx); the exact expf + IEEE division made this loop issue-bound
-        const float y0 = fast_swish((x.x - mm) * rr * g[0] + be[0]), y1 = fast_swish((x.y - mm) * rr * g[1] + be[1]);
-        const float y2 = fast_swish((x.z - mm) * rr * g[2] + be[2]), y3 = fast_swish((x.w - mm) * rr * g[3] + be[3]);
+        const float y0 = fswish((x.x - mm) * rr * g[0] + be[0]), y1 = fswish((x.y - mm) * rr * g[1] + be[1]);
+        const float y2 = fswish((x.z - mm) * rr * g[2] + be[2]), y3 = fswish((x.w - mm) * rr * g[3] + be[3]);
         const __nv_bfloat162 lo = __floats2bfloat162_rn(y0, y1), hi = __floats2bfloat162_rn(y2, y3);
         uint2 u;
         u.x = *reinterpret_cast<const uint32_t*>(&lo);
@@ -441,35 +359,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // ---- host side -------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// row-major bf16 matrix [rows, cols] with leading dimension ld (elements); box = {box_cols, box_rows}
-static bool encode_2d(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_cols, int box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (fn == nullptr) return false;
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
 static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int ldc, const float* bias, int M, int N,
                              int K, int split_k, int mode, __nv_bfloat16* act_out, int act_ld, cudaStream_t st) {
@@ -527,19 +416,17 @@ cudaError_t launch_gemm_bf16_tc_norm(int norm, int M, int N, int K, const void* 
                                      cudaStream_t st) {
   if (norm == NORM_NONE || bias == nullptr || act_out_v == nullptr) return cudaErrorNotSupported;
   // large shapes: the persistent CTA-pair GEMM + the row kernel beats this one-tile-per-CTA fused kernel
-  static const bool keep_fused = getenv("REPPO_FUSE_NORM_LARGE") != nullptr;
-  if (!keep_fused && gemm_bf16_tc2_eligible(false, false, M, N, K, GEMM_STORE, 1)) return cudaErrorNotSupported;
+  if (!knobs().fuse_norm_large && gemm_bf16_tc2_eligible(false, false, M, N, K, GEMM_STORE, 1)) return cudaErrorNotSupported;
   if ((lda & 7) || (ldb & 7) || (ldc & 3) || (act_ld & 3) || (reinterpret_cast<uintptr_t>(A) & 15) ||
       (reinterpret_cast<uintptr_t>(B) & 15) || (reinterpret_cast<uintptr_t>(C) & 15))
     return cudaErrorNotSupported;
   int block_n = 0;
-  static const bool prefer128 = getenv("REPPO_NORM_BN128") != nullptr;
-  if (prefer128 && N % 128 == 0 && N / 128 <= 8) block_n = 128;
+  if (knobs().norm_bn128 && N % 128 == 0 && N / 128 <= 8) block_n = 128;
   else if (N % 64 == 0 && N / 64 <= 8) block_n = 64;       // portable cluster size <= 8
   else if (N % 128 == 0 && N / 128 <= 8) block_n = 128;
   if (block_n == 0) return cudaErrorNotSupported;
   CUtensorMap ta, tb;
-  if (!encode_2d(&ta, A, M, K, lda, TC_BLOCK_K, TC_BLOCK_M) || !encode_2d(&tb, B, N, K, ldb, TC_BLOCK_K, block_n))
+  if (!tmap_encode_2d(&ta, A, M, K, lda, TC_BLOCK_K, TC_BLOCK_M) || !tmap_encode_2d(&tb, B, N, K, ldb, TC_BLOCK_K, block_n))
     return cudaErrorInvalidValue;
   __nv_bfloat16* act_out = static_cast<__nv_bfloat16*>(act_out_v);
   if (block_n == 64) {
@@ -569,11 +456,10 @@ cudaError_t launch_gemm_bf16_tc(bool a_mn, bool b_mn, int M, int N, int K, const
   CUtensorMap ta, tb;
   // narrow tiles when 128-wide ones would leave most of the 148 SMs idle
   const int tiles128 = ((M + TC_BLOCK_M - 1) / TC_BLOCK_M) * ((N + 127) / 128) * (split_k > 0 ? split_k : 1);
-  static const int wide_min = getenv("REPPO_TC_WIDE_MIN") ? atoi(getenv("REPPO_TC_WIDE_MIN")) : 120;
-  const bool wide = (N > 64) && (tiles128 >= wide_min);
+  const bool wide = (N > 64) && (tiles128 >= knobs().tc_wide_min);
   const int block_n = wide ? 128 : 64;
-  const bool ok_a = a_mn ? encode_2d(&ta, A, K, M, lda, 64, TC_BLOCK_K) : encode_2d(&ta, A, M, K, lda, TC_BLOCK_K, TC_BLOCK_M);
-  const bool ok_b = b_mn ? encode_2d(&tb, B, K, N, ldb, 64, TC_BLOCK_K) : encode_2d(&tb, B, N, K, ldb, TC_BLOCK_K, block_n);
+  const bool ok_a = a_mn ? tmap_encode_2d(&ta, A, K, M, lda, 64, TC_BLOCK_K) : tmap_encode_2d(&ta, A, M, K, lda, TC_BLOCK_K, TC_BLOCK_M);
+  const bool ok_b = b_mn ? tmap_encode_2d(&tb, B, K, N, ldb, 64, TC_BLOCK_K) : tmap_encode_2d(&tb, B, N, K, ldb, TC_BLOCK_K, block_n);
   if (!ok_a || !ok_b) return cudaErrorInvalidValue;
 #define REPPO_TC_DISPATCH(AMN, BMN)                                                                           \
   return wide ? launch_tc<128, 4, AMN, BMN>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, act_out, act_ld, st) \

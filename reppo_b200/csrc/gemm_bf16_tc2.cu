@@ -22,9 +22,10 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "knobs.h"
 #include "launch.h"
-#include "slab.h"
 #include "tc_ptx.cuh"
+#include "tmap.h"
 
 namespace reppo {
 using namespace tcx;
@@ -50,9 +51,6 @@ struct T2Smem {
   static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024;
 };
 
-REPPO_DEVINL void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
 REPPO_DEVINL uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -345,9 +343,8 @@ int t2_max_pairs() {
 // tile width (256 / 128) and split-K factor of the pair kernel for this shape; bn == 0: not eligible
 struct T2Plan { int bn, splits; };
 static T2Plan t2_plan(bool a_mn, bool b_mn, int M, int N, int K, int mode, int split_k) {
-  static const bool enabled = !(getenv("REPPO_TC2") != nullptr && atoi(getenv("REPPO_TC2")) == 0);
-  static const int min_tiles = getenv("REPPO_TC2_MIN") ? atoi(getenv("REPPO_TC2_MIN")) : 56;
-  static const int force_bn = getenv("REPPO_TC2_BN") ? atoi(getenv("REPPO_TC2_BN")) : 0;
+  const bool enabled = knobs().tc2;
+  const int min_tiles = knobs().tc2_min, force_bn = knobs().tc2_bn;
   T2Plan p{0, 1};
   if (!enabled || (a_mn && !b_mn)) return p;
   if (K < 8 || N < 128 || M < 256) return p;   // thin-K first layers too: at these row counts they are epilogue (store) bound
@@ -382,11 +379,11 @@ cudaError_t launch_gemm_bf16_tc2(bool a_mn, bool b_mn, int M, int N, int K, cons
   if (plan.bn == 0) return cudaErrorNotSupported;
   const int bn = plan.bn, splits = plan.splits, max_pairs = t2_max_pairs();
   CUtensorMap ta, tb;
-  const bool ok_a = a_mn ? slab_encode_2d(&ta, A, K, M, lda, 64, T2_K) : slab_encode_2d(&ta, A, M, K, lda, T2_K, T2_M);
-  const bool ok_b = b_mn ? slab_encode_2d(&tb, B, K, N, ldb, 64, T2_K) : slab_encode_2d(&tb, B, N, K, ldb, T2_K, bn / 2);
+  const bool ok_a = a_mn ? tmap_encode_2d(&ta, A, K, M, lda, 64, T2_K) : tmap_encode_2d(&ta, A, M, K, lda, T2_K, T2_M);
+  const bool ok_b = b_mn ? tmap_encode_2d(&tb, B, K, N, ldb, 64, T2_K) : tmap_encode_2d(&tb, B, N, K, ldb, T2_K, bn / 2);
   if (!ok_a || !ok_b) return cudaErrorNotSupported;
   __nv_bfloat16* act_out = static_cast<__nv_bfloat16*>(act_out_v);
-  static const int stages_env = getenv("REPPO_TC2_STAGES") ? atoi(getenv("REPPO_TC2_STAGES")) : 0;   // experiments: 3 / 4
+  const int stages_env = knobs().tc2_stages;   // experiments: 3 / 4 / 5
 #define REPPO_T2_ARGS ta, tb, C, ldc, bias, M, N, K, splits, mode, act_out, act_ld, max_pairs, st
 #define REPPO_T2_DISPATCH(AMN, BMN)                                                    \
   if (bn == 256) {                                                                     \

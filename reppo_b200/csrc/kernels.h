@@ -38,6 +38,7 @@ struct ActorConsts {
 struct AdamConsts {
   float lr, b1, b2, eps, weight_decay, max_grad_norm;
   int torch_clip;
+  int anneal_steps;   // > 0: optax.linear_schedule(lr, 0, anneal_steps) evaluated at the device step counter
 };
 
 cudaError_t launch_td_lambda(const float* sr, const float* val, const float* done, float* trunc, const float* iw,
@@ -59,14 +60,8 @@ bool gemm_bf16_tc2_eligible(bool a_mn, bool b_mn, int M, int N, int K, int mode,
 struct NormArgs { const float* gamma; const float* beta; float eps; float* rstd_out; float* mean_out; };
 cudaError_t launch_gemm_bf16_tc_norm(int norm, int M, int N, int K, const void* A, int lda, const void* B, int ldb, float* C,
                                      int ldc, const float* bias, void* act_out, int act_ld, const NormArgs& na, cudaStream_t st);
-// dgrad with the backward of [norm -> swish] (or plain swish: norm == NORM_NONE, optional fp32 addend) fused into the
-// epilogue (gemm_bf16_tc_bwd.cu); cudaErrorNotSupported = shape not eligible
-cudaError_t launch_gemm_bf16_tc_bwd(int norm, int M, int N, int K, const void* dy, int lda, const void* W, int ldw, const float* z,
-                                    const float* rstd, const float* mean, const float* gamma, const float* beta,
-                                    const float* addend, void* dz_twin, int ld_twin, float* g_gamma, float* g_beta, float* g_bias,
-                                    cudaStream_t st);
-// fp32 -> bf16 copies: plain (row-padded) and, for weights, the [out,in] matrix plus its transpose
-struct PackEntry { const float* w; void* wb; void* wtb; int out, in, ld_b, ld_t; };
+// fp32 -> bf16 copies: plain (row-padded) and, for weights, the [out,in] matrices of one network in one launch
+struct PackEntry { const float* w; void* wb; int out, in, ld_b; };
 constexpr int kMaxPack = 16;
 struct PackTable { int n; PackEntry e[kMaxPack]; };
 cudaError_t launch_pack_weights(const PackTable& t, cudaStream_t st);
@@ -107,22 +102,6 @@ cudaError_t launch_value_head(const float* head_out, int ld, const float* zero_d
                               float* value, float* logits, cudaStream_t st);
 cudaError_t launch_mean_std(const float* out, int rows, int A, float min_std, float* mean, float* std, cudaStream_t st);
 
-// thin layers on the SIMT pipes (thin.cu); cudaErrorNotSupported = shape not eligible, caller takes the GEMM path
-cudaError_t launch_thin_first_layer(int norm, const float* a, int da, int lda, const float* b, int db, int ldb, const int* idx,
-                                    int b_local, int rows, int H, const void* wT_bf16, int ldw, const float* bias, const float* gamma,
-                                    const float* beta, float eps, float* z, float* rstd, float* mean, void* y_h, int ldy, void* x_h,
-                                    int ldx, cudaStream_t st);
-cudaError_t launch_actor_head_sample(const void* x_h, int ldx, int H, const void* w_bf16, int ldw, const float* bias, float* out,
-                                     const float* out_old, const int* old_idx, const float* eps_pi, const float* eps_kl, int rows,
-                                     int A, int kl_samples, const ActorConsts& ac, float* act_out, int act_ld, float* logp,
-                                     float* kl, float* gmu, float* gsig, void* act_h, int act_ldh, cudaStream_t st);
-cudaError_t launch_actor_grad_thin(const void* dz1_h, int lddz, int Hc, const void* w1_bf16, int ldw1, int Dc, const void* w3_bf16,
-                                   int ldw3, int Ha, const float* out, const float* eps_pi, const float* act, int act_ld,
-                                   const float* logp, const float* kl, const float* q, const float* gmu, const float* gsig,
-                                   const float* actor_params, int rows, int A, float inv_rows, const ActorConsts& ac, float* dout,
-                                   float* actor_grads, float* metrics, void* dout_h, int ldh, float* dbias, float* dx,
-                                   cudaStream_t st);
-
 // rollout side (rollout.cu)
 cudaError_t launch_policy_sample(const float* out, const float* eps, const float* scale, int rows, int A, float min_std, float clip,
                                  int store_clipped, float* action, int act_ld, void* act_h, int act_ldh, float* logp,
@@ -133,10 +112,13 @@ cudaError_t launch_obs_normalize(const float* x, long long rows, int D, float* m
                                  float eps, int update, int center, long long until, float* out, cudaStream_t st);
 
 // bf16 shadows of the weight matrices, refreshed by the Adam kernel itself (REPPO_GEMM_BF16)
-struct ShadowEntry { long long start, end; int in, ld; void* dst; void* dst_t; int ld_t; };   // dst_t: optional transposed copy [in][ld_t]
+struct ShadowEntry { long long start, end; int in, ld; void* dst; };
 struct ShadowTable { int n; ShadowEntry e[kMaxPack]; };
+// bar: two device uint32 {arrival count, generation} of the kernel's grid barrier (zero-initialised once; one pair per
+// concurrently running chain)
 cudaError_t launch_clip_adam(const float* p_in, float* p, float* g, float* m, float* v, long long n, int* step, float* partials,
-                             const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out, int zero_grads, cudaStream_t st);
+                             unsigned int* bar, const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out,
+                             int zero_grads, cudaStream_t st);
 cudaError_t launch_metrics_mean(const float* step_metrics, int first, int count, int nm, float* out, cudaStream_t st);
 cudaError_t launch_metrics_init(float* m, uint32_t mask, cudaStream_t st);
 cudaError_t launch_metrics_init_all(float* m, int steps, cudaStream_t st);

@@ -11,7 +11,8 @@
 // kernel waits unconditionally, completion is transitive along the chain.  REPPO_NO_PDL=1 disables the attribute.
 #pragma once
 #include <cuda_runtime.h>
-#include <stdlib.h>
+
+#include "knobs.h"
 
 #define REPPO_PDL_PROLOGUE()                                   \
   do {                                                         \
@@ -21,10 +22,7 @@
 
 namespace reppo {
 
-inline bool pdl_enabled() {
-  static const bool on = (getenv("REPPO_NO_PDL") == nullptr);
-  return on;
-}
+inline bool pdl_enabled() { return !knobs().no_pdl; }
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

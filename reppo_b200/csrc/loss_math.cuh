@@ -1,4 +1,4 @@
-// Row-wise math shared by the loss kernels (losses.cu) and the slab programs (slab.cu).
+// Row-wise math shared by the loss kernels (losses.cu) and the rollout kernels (rollout.cu).
 #pragma once
 #include "common.cuh"
 

@@ -57,6 +57,7 @@ critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __rest
   float cs[NB];
 #pragma unroll
   for (int j = 0; j < NB; ++j) cs[j] = 0.f;
+  const float inv_bw = static_cast<float>(B) / (hl.edges[B] - hl.edges[0]);
   // grid-stride over rows (the launch caps the grid at a few blocks per SM): the per-block metric / column-sum atomics
   // below are issued once per block, not once per 8 rows
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
@@ -70,12 +71,19 @@ critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __rest
     const float z = erff((hl.edges[B] - x) / hl.den) - erff((hl.edges[0] - x) / hl.den) + hl.z_eps;
     float ce = 0.f, sum_tp = 0.f, tp[NB];
     // erf at the lower edge of this lane's bins; the upper edge of bin c is the lower edge of bin c + 1 = the next lane's
-    // value (lane 31: this lane's value of the next group of 32 bins), so every edge is evaluated once
+    // value (lane 31: this lane's value of the next group of 32 bins), so every edge is evaluated once.
+    // Only the edges near the target need the evaluation at all: sigma = 0.75 bin widths (utils.py:47, reppo_util.py:766),
+    // so an edge more than 5.5 bins away from x sits at |t| > 5.1 where erff(t) is exactly +-1.0f (it saturates at
+    // |t| >= 3.92); those edges take the constant, and whole groups of 32 edges outside the window skip erff.
+    const float pos = (x - hl.edges[0]) * inv_bw;   // target position in units of bins (edge index scale)
     float lo_e[NB + 1];
 #pragma unroll
     for (int j = 0; j <= NB; ++j) {
       const int c = lane + 32 * j;
-      lo_e[j] = (c <= B) ? erff((hl.edges[c] - x) / hl.den) : 0.f;
+      const float dc = static_cast<float>(c) - pos;
+      float e = (dc > 0.f) ? 1.f : -1.f;
+      if (fabsf(dc) < 5.5f && c <= B) e = erff((hl.edges[c] - x) / hl.den);
+      lo_e[j] = (c <= B) ? e : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
@@ -85,9 +93,11 @@ critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __rest
       const float wrap = __shfl_sync(0xffffffffu, lo_e[j + 1], 0);
       if (c < B) {
         const float lo = lo_e[j], hi = (lane == 31) ? wrap : nxt;
-        tp[j] = (hi - lo) / z;
-        ce -= tp[j] * (sx.lg[j] - sx.lse);
-        sum_tp += tp[j];
+        if (hi != lo) {   // bins outside the window have probability exactly 0 (0 / z), no division needed
+          tp[j] = (hi - lo) / z;
+          ce -= tp[j] * (sx.lg[j] - sx.lse);
+          sum_tp += tp[j];
+        }
       }
     }
     ce = warp_sum(ce);
@@ -146,6 +156,7 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
   float vals[3] = {0.f, 0.f, 0.f};
   if (dbias != nullptr)
     for (int c = lane; c < P; c += 32) scol[warp * P + c] = 0.f;   // rows past the end contribute nothing
+  __syncwarp();   // with the reward head (off = 1) a lane accumulates into columns another lane zeroed
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     const long long src = idx ? idx[row] : row;
     const float mask = no_mask ? 1.f : 1.f - truncated[src];
@@ -427,13 +438,9 @@ cudaError_t launch_critic_aux(const float* pred, int P, int H, int reward_head, 
                               float inv_rows, int no_mask, float aux_mult, float* dpred, float* metrics, void* dp_h, int ldh,
                               float* dbias, cudaStream_t st) {
   const size_t smem = dbias ? 8 * static_cast<size_t>(P) * sizeof(float) : 0;
-  if (smem > 48 * 1024) {
-    static bool configured = false;
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(critic_aux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2049 * 4);
-      if (e != cudaSuccess) return e;
-      configured = true;
-    }
+  if (smem > 48 * 1024) {   // per device, and cheap: set unconditionally
+    cudaError_t e = cudaFuncSetAttribute(critic_aux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2049 * 4);
+    if (e != cudaSuccess) return e;
   }
   const int want = (rows + kLossRowsPerBlock - 1) / kLossRowsPerBlock;
   launch_k((critic_aux_kernel), dim3(want < kLossMaxBlocks ? want : kLossMaxBlocks), dim3(256), smem, st, pred, P, H, reward_head, mask_done, next_emb, reward, done, truncated, idx, rows, inv_rows, no_mask, aux_mult, dpred, metrics, static_cast<__nv_bfloat16*>(dp_h), ldh, dbias);

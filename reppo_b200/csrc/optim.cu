@@ -1,11 +1,22 @@
-// K12 -- global-norm clip + Adam / AdamW on one flat fp32 arena.
+// K12 -- global-norm clip + Adam / AdamW on one flat fp32 arena, ONE launch.
 //   JAX  : optax.chain(clip_by_global_norm(max_grad_norm), adam(lr))  src/jaxrl/reppo.py:246-257
+//          lr = optax.linear_schedule(cfg.lr, 0, num_updates) when cfg.anneal_lr (:239-244)
 //   Torch: clip_grad_norm_ (+1e-6) -> AdamW(weight_decay=0.01)         src/torchrl/reppo.py:270-273,527-534
-// Two launches: (1) per-block partial sums of squares (deterministic, no atomics) + step counter
-// increment; (2) every block re-reduces the <= kMaxPartials partials, derives the clip scale and
-// the bias corrections, and streams its slice: 28 B per parameter (read g,p,m,v; write p,m,v).
+// Phase 1: every block reduces the squares of its slice of the gradient (kept in registers) to one partial, publishes
+// it and arrives at a grid-wide barrier (arrival counter + generation word in the workspace; the last block to arrive
+// resets the counter and bumps the generation, so the kernel is replayable inside a CUDA graph with any grid size).  While it waits, the loads of p / m / v for phase 2 are in flight.  Phase 2: every
+// block re-adds the <= kMaxPartials partials in a fixed order (deterministic global norm, no float atomics), derives
+// the clip scale, the bias corrections and the (optionally annealed) learning rate from the device step counter, and
+// streams its slice: 28 B per parameter (read g, p, m, v; write p, m, v) + the bf16 shadow + the zeroed gradient.
+// Co-residency (the barrier must not deadlock): the grid never exceeds the number of SMs and the kernel is held to 64
+// registers (512 threads, no dynamic shared memory), so TWO blocks fit on an SM.  The only kernels that can wait on each
+// other are the critic chain's and the actor chain's clip_adam running at the same time (<= 2 x 148 blocks <= 296 slots):
+// both are always fully resident.  Blocks of other kernels that occupy SMs complete on their own, and programmatic
+// dependents of THIS kernel are only launched once all of its blocks have started (launch_dependents is per block).
 #include <cuda_bf16.h>
 #include <stdlib.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -13,88 +24,107 @@
 
 namespace reppo {
 
-__global__ void __launch_bounds__(256)
-sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partials, int* __restrict__ step) {
-  REPPO_PDL_PROLOGUE();
-  __shared__ float red[32];
-  float s = 0.f;
-  const long long n4 = n >> 2;
-  const float4* g4 = reinterpret_cast<const float4*>(g);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float4 v = g4[i];
-    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-  }
-  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = g[(n4 << 2) + threadIdx.x]; s += v * v; }
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x] = s;
-    if (blockIdx.x == 0 && step != nullptr) *step = *step + 1;
-  }
-}
+constexpr int kAdamThreads = 512;
+constexpr int kAdamKeep = 4;   // float4 gradient chunks a thread keeps in registers across the barrier
 
-__global__ void __launch_bounds__(256)
-adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-            const float* __restrict__ partials, int num_partials, const int* __restrict__ step, AdamConsts c,
-            const ShadowTable sh, float* __restrict__ grad_norm_out, int zero_grads) {
+__global__ void __launch_bounds__(kAdamThreads, 2)
+clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                 float* __restrict__ partials, unsigned int* __restrict__ bar, int* __restrict__ step, AdamConsts c,
+                 const ShadowTable sh, float* __restrict__ grad_norm_out, int zero_grads) {
   REPPO_PDL_PROLOGUE();
   __shared__ float red[32];
-  __shared__ float s_scale, s_bc1, s_bc2;
+  __shared__ float s_scale, s_bc1, s_bc2, s_lr;
   const long long n4 = n >> 2;
   float4* p4 = reinterpret_cast<float4*>(p);
   const float4* pi4 = reinterpret_cast<const float4*>(p_in);   // may alias p (in-place update)
   float4* m4 = reinterpret_cast<float4*>(m);
   float4* v4 = reinterpret_cast<float4*>(v);
   float4* g4 = reinterpret_cast<float4*>(g);
-  // Two float4 per thread per pass, and the first pass's loads are issued BEFORE the global-norm prologue below (they do
-  // not depend on it): the kernel is load-latency bound (ncu: 54 % of the stall samples sit on the first use of the loaded
-  // values, 28 warps per SM), so the prologue's reduction / pow and the second float4 hide behind the first one's latency.
-  constexpr int U = 2;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  long long base = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  float4 pp[U], mm[U], vv[U], gg[U];
-  auto load = [&](long long b0) {
-#pragma unroll
-    for (int k = 0; k < U; ++k) {
-      const long long i = b0 + k * stride;
-      if (i < n4) { pp[k] = pi4[i]; mm[k] = m4[i]; vv[k] = v4[i]; gg[k] = g4[i]; }
-    }
-  };
-  load(base);
+  const long long first = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // ---- phase 1: this block's partial sum of squares
+  float4 gk[kAdamKeep];
   float s = 0.f;
-  for (int i = threadIdx.x; i < num_partials; i += blockDim.x) s += partials[i];
+#pragma unroll
+  for (int k = 0; k < kAdamKeep; ++k) {
+    const long long i = first + k * stride;
+    gk[k] = (i < n4) ? g4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < kAdamKeep; ++k) s += gk[k].x * gk[k].x + gk[k].y * gk[k].y + gk[k].z * gk[k].z + gk[k].w * gk[k].w;
+  for (long long i = first + kAdamKeep * stride; i < n4; i += stride) {   // wide networks only
+    const float4 q = g4[i];
+    s += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float q = g[(n4 << 2) + threadIdx.x]; s += q * q; }
   s = block_sum(s, red);
+  const int t = *step + 1;   // every block reads the counter before the barrier; block 0 writes it after
+  unsigned int my_gen = 0;
+  bool last = false;
   if (threadIdx.x == 0) {
-    const float gn = sqrtf(s);
+    partials[blockIdx.x] = s;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(my_gen) : "l"(bar + 1) : "memory");   // before arriving
+    __threadfence();
+    last = (atomicAdd(bar, 1u) == gridDim.x - 1);
+  }
+  // phase-2 operands of the first pass are requested before the wait
+  float4 pp = make_float4(0.f, 0.f, 0.f, 0.f), mm = pp, vv = pp;
+  if (first < n4) { pp = pi4[first]; mm = m4[first]; vv = v4[first]; }
+  if (threadIdx.x == 0) {
+    if (last) {
+      bar[0] = 0u;   // nobody touches the counter again before the generation moves
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(my_gen + 1u) : "memory");
+    } else {
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar + 1) : "memory");
+      } while (seen == my_gen);
+    }
+  }
+  __syncthreads();
+  // ---- phase 2
+  float tot = 0.f;
+  for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += blockDim.x) tot += __ldcg(partials + i);
+  tot = block_sum(tot, red);
+  if (threadIdx.x == 0) {
+    const float gn = sqrtf(tot);
     float scale = 1.f;
     if (c.max_grad_norm > 0.f) {
       if (c.torch_clip) scale = fminf(c.max_grad_norm / (gn + 1e-6f), 1.f);   // clip_grad_norm_
       else scale = (gn < c.max_grad_norm) ? 1.f : c.max_grad_norm / gn;       // optax.clip_by_global_norm
     }
-    const int t = *step;
     s_scale = scale;
     s_bc1 = static_cast<float>(1.0 - pow(static_cast<double>(c.b1), static_cast<double>(t)));
     s_bc2 = static_cast<float>(1.0 - pow(static_cast<double>(c.b2), static_cast<double>(t)));
-    if (blockIdx.x == 0 && grad_norm_out != nullptr) *grad_norm_out = gn;
+    float lr = c.lr;
+    if (c.anneal_steps > 0) {
+      // optax.linear_schedule(lr, 0, T) at count = t - 1 (polynomial_schedule, power 1): lr * (1 - min(count, T) / T)
+      const float cnt = static_cast<float>(min(t - 1, c.anneal_steps));
+      lr = c.lr * (1.f - cnt / static_cast<float>(c.anneal_steps));
+    }
+    s_lr = lr;
+    if (blockIdx.x == 0) {
+      *step = t;
+      if (grad_norm_out != nullptr) *grad_norm_out = gn;
+    }
   }
   __syncthreads();
-  const float scale = s_scale, bc1 = s_bc1, bc2 = s_bc2;
-  const float decay = 1.f - c.lr * c.weight_decay;
+  const float scale = s_scale, bc1 = s_bc1, bc2 = s_bc2, lr = s_lr;
+  const float decay = 1.f - lr * c.weight_decay;
   auto upd = [&](float& p1, float g1, float& m1, float& v1) {
     g1 *= scale;
     m1 = c.b1 * m1 + (1.f - c.b1) * g1;
     v1 = c.b2 * v1 + (1.f - c.b2) * g1 * g1;
-    p1 = p1 * decay - c.lr * (m1 / bc1) / (sqrtf(v1 / bc2) + c.eps);
+    p1 = p1 * decay - lr * (m1 / bc1) / (sqrtf(v1 / bc2) + c.eps);
   };
   // re-round updated master weights into the bf16 operand shadow W[out, ld] of the tcgen05 GEMMs (one element)
   auto shadow1 = [&](float p1, long long idx) {
-    for (int t = 0; t < sh.n; ++t) {
-      if (idx >= sh.e[t].start && idx < sh.e[t].end) {
-        const int off = static_cast<int>(idx - sh.e[t].start);
-        const int r = off / sh.e[t].in, col = off - r * sh.e[t].in;
-        static_cast<__nv_bfloat16*>(sh.e[t].dst)[static_cast<size_t>(r) * sh.e[t].ld + col] = __float2bfloat16_rn(p1);
-        if (sh.e[t].dst_t != nullptr)   // thin first layers also keep W^T (thin.cu)
-          static_cast<__nv_bfloat16*>(sh.e[t].dst_t)[static_cast<size_t>(col) * sh.e[t].ld_t + r] = __float2bfloat16_rn(p1);
+    for (int e = 0; e < sh.n; ++e) {
+      if (idx >= sh.e[e].start && idx < sh.e[e].end) {
+        const int off = static_cast<int>(idx - sh.e[e].start);
+        const int r = off / sh.e[e].in, col = off - r * sh.e[e].in;
+        static_cast<__nv_bfloat16*>(sh.e[e].dst)[static_cast<size_t>(r) * sh.e[e].ld + col] = __float2bfloat16_rn(p1);
         break;
       }
     }
@@ -102,12 +132,12 @@ adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __restric
   // one table search per float4: the four elements almost always sit in one row of one weight matrix
   auto shadow4 = [&](const float4& q, long long idx) {
     bool done = false;
-    for (int t = 0; t < sh.n; ++t) {
-      if (idx >= sh.e[t].start && idx + 3 < sh.e[t].end) {
-        const int off = static_cast<int>(idx - sh.e[t].start);
-        const int r = off / sh.e[t].in, col = off - r * sh.e[t].in;
-        if (col + 3 < sh.e[t].in && sh.e[t].dst_t == nullptr) {
-          __nv_bfloat16* d = static_cast<__nv_bfloat16*>(sh.e[t].dst) + static_cast<size_t>(r) * sh.e[t].ld + col;
+    for (int e = 0; e < sh.n; ++e) {
+      if (idx >= sh.e[e].start && idx + 3 < sh.e[e].end) {
+        const int off = static_cast<int>(idx - sh.e[e].start);
+        const int r = off / sh.e[e].in, col = off - r * sh.e[e].in;
+        if (col + 3 < sh.e[e].in) {
+          __nv_bfloat16* d = static_cast<__nv_bfloat16*>(sh.e[e].dst) + static_cast<size_t>(r) * sh.e[e].ld + col;
           const __nv_bfloat162 lo = __floats2bfloat162_rn(q.x, q.y), hi = __floats2bfloat162_rn(q.z, q.w);
           if ((reinterpret_cast<uintptr_t>(d) & 7) == 0) {
             uint2 u;
@@ -124,42 +154,52 @@ adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __restric
     }
     if (!done) { shadow1(q.x, idx); shadow1(q.y, idx + 1); shadow1(q.z, idx + 2); shadow1(q.w, idx + 3); }
   };
-  for (; base < n4; base += U * stride) {
-#pragma unroll
-    for (int k = 0; k < U; ++k) {
-      const long long i = base + k * stride;
-      if (i < n4) {
-        if (zero_grads) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // the next step accumulates into a clean arena (no memset node)
-        upd(pp[k].x, gg[k].x, mm[k].x, vv[k].x); upd(pp[k].y, gg[k].y, mm[k].y, vv[k].y);
-        upd(pp[k].z, gg[k].z, mm[k].z, vv[k].z); upd(pp[k].w, gg[k].w, mm[k].w, vv[k].w);
-        p4[i] = pp[k]; m4[i] = mm[k]; v4[i] = vv[k];
-        if (sh.n > 0) shadow4(pp[k], 4 * i);
-      }
+  int k = 0;
+  for (long long i = first; i < n4; i += stride, ++k) {
+    float4 gg;
+    if (k < kAdamKeep) {
+      // static indexing keeps gk in registers
+      gg = (k == 0) ? gk[0] : (k == 1) ? gk[1] : (k == 2) ? gk[2] : gk[3];
+    } else {
+      gg = g4[i];
     }
-    if (base + U * stride < n4) load(base + U * stride);
+    if (k > 0) { pp = pi4[i]; mm = m4[i]; vv = v4[i]; }
+    if (zero_grads) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // the next step accumulates into a clean arena (no memset node)
+    upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y);
+    upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    if (sh.n > 0) shadow4(pp, 4 * i);
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long long i = (n4 << 2) + threadIdx.x;
-    float pp = p_in[i];
-    upd(pp, g[i], m[i], v[i]);
-    shadow1(pp, i);
-    p[i] = pp;
+    float q = p_in[i];
+    upd(q, g[i], m[i], v[i]);
+    shadow1(q, i);
+    p[i] = q;
     if (zero_grads) g[i] = 0.f;
   }
 }
 
 cudaError_t launch_clip_adam(const float* p_in, float* p, float* g, float* m, float* v, long long n, int* step, float* partials,
-                             const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out, int zero_grads, cudaStream_t st) {
+                             unsigned int* bar, const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out,
+                             int zero_grads, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  const long long want = (n / 4 + 255) / 256;
-  static const int cap_env = getenv("REPPO_ADAM_BLOCKS") ? atoi(getenv("REPPO_ADAM_BLOCKS")) : 0;   // experiment knob
-  const int cap = (cap_env > 0 && cap_env < kMaxPartials) ? cap_env : kMaxPartials;
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
+  }
+  // all blocks must be co-resident (grid barrier): at most one per SM
+  const long long want = (n / 4 + kAdamThreads - 1) / kAdamThreads;
+  int cap = std::min(sm_count, kMaxPartials);
+  if (knobs().adam_blocks > 0 && knobs().adam_blocks < cap) cap = knobs().adam_blocks;
   int blocks = static_cast<int>(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
-  launch_k((sumsq_partial_kernel), dim3(blocks), dim3(256), 0, st, g, n, partials, step);
   ShadowTable sh{};
   if (shadow != nullptr) sh = *shadow;
-  launch_k((adam_kernel), dim3(blocks), dim3(256), 0, st, p_in, p, g, m, v, n, partials, blocks, step, c, sh, grad_norm_out, zero_grads);
+  launch_k((clip_adam_kernel), dim3(blocks), dim3(kAdamThreads), 0, st, p_in, p, g, m, v, n, partials, bar, step, c, sh,
+           grad_norm_out, zero_grads);
   return cudaGetLastError();
 }
 

@@ -195,7 +195,7 @@ template <int NORM>
 static void launch_fwd_norm(const float* z, const float* gamma, const float* beta, int rows, int H, float eps, float* x,
                             float* rstd, float* mean, __nv_bfloat16* xh, int ldh, cudaStream_t st) {
   const int wpb = 8, grid = (rows + wpb - 1) / wpb;
-  const bool vec = (H % 128 == 0) && H <= 2048 && (ldh % 4 == 0) && getenv("REPPO_NO_VEC") == nullptr;
+  const bool vec = (H % 128 == 0) && H <= 2048 && (ldh % 4 == 0) && !knobs().no_vec;
   const bool fast = (x == nullptr) && H >= 1024;   // bf16-operand mode at the wide shapes: SFU sigmoid
 #define REPPO_FWD_VEC(V) do { if (fast) launch_k((norm_act_fwd_vec_kernel<NORM, V, true>), dim3(grid), dim3(wpb * 32), 0, st, z, gamma, beta, rows, eps, x, rstd, mean, xh, ldh); \
     else launch_k((norm_act_fwd_vec_kernel<NORM, V, false>), dim3(grid), dim3(wpb * 32), 0, st, z, gamma, beta, rows, eps, x, rstd, mean, xh, ldh); } while (0)
@@ -565,15 +565,15 @@ static cudaError_t launch_bwd_norm(const float* dx, const float* dx2, const floa
                                    const float* mean, int rows, int H, float* dz, float* dgamma, float* dbeta, float* dbias,
                                    __nv_bfloat16* dzh, int ldh, cudaStream_t st) {
   // one block per ~SM: enough parallelism, few enough blocks that the per-block column atomics stay cheap
-  static const int rpb_env = getenv("REPPO_BWD_RPB") ? atoi(getenv("REPPO_BWD_RPB")) : 0;
+  const int rpb_env = knobs().bwd_rpb;
   int rows_per_block = rpb_env > 0 ? rpb_env : 8;   // one row per warp: lowest latency (measured 134.4 vs 135.3 ms at 16)
   while ((rows + rows_per_block - 1) / rows_per_block > 148 * 4 && rows_per_block < 128) rows_per_block *= 2;
-  const bool vec = (H % 128 == 0) && H <= 1024 && (ldh % 4 == 0) && getenv("REPPO_NO_VEC") == nullptr;
-  if ((H == 1024 || H == 2048) && (ldh % 4 == 0) && getenv("REPPO_NO_WIDE") == nullptr) {
+  const bool vec = (H % 128 == 0) && H <= 1024 && (ldh % 4 == 0) && !knobs().no_vec;
+  if ((H == 1024 || H == 2048) && (ldh % 4 == 0) && !knobs().no_wide) {
     // wide rows: 2 / 4 warps per row; two blocks per SM worth of work items (C5: 225.7 ms, vs 227.8 / 228.2 / 230.2 at 4 / 8 / 16:
     // fewer blocks = fewer column-sum atomics)
     const int rpi = H == 1024 ? 4 : 2;
-    static const int bps = getenv("REPPO_WIDE_BPS") ? atoi(getenv("REPPO_WIDE_BPS")) : 2;   // blocks per SM worth of work items
+    const int bps = knobs().wide_bps;   // blocks per SM worth of work items
     int rpb = (rows + 148 * bps - 1) / (148 * bps);
     rpb = ((rpb + rpi - 1) / rpi) * rpi;
     if (rpb < 2 * rpi) rpb = 2 * rpi;

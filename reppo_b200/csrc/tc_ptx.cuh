@@ -1,4 +1,4 @@
-// tcgen05 / TMA / mbarrier / cluster PTX wrappers shared by the cluster kernels (slab.cu, gemm_bf16_tc_bwd.cu).
+// tcgen05 / TMA / mbarrier / cluster PTX wrappers shared by the tcgen05 kernel files.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -7,8 +7,6 @@
 
 namespace reppo {
 namespace tcx {
-
-constexpr int SB_M = 128, SB_N = 64, SB_K = 64, SB_UMMA_K = 16;
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------
 REPPO_DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -33,6 +31,9 @@ REPPO_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, 
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+REPPO_DEVINL void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 REPPO_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 REPPO_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -72,23 +73,9 @@ REPPO_DEVINL uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uin
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// bf16 x bf16 -> f32, M = 128, N = 64, A K-major, B K-major or MN-major
-REPPO_DEVINL uint32_t make_idesc(bool b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
-         (static_cast<uint32_t>(SB_N >> 3) << 17) | (static_cast<uint32_t>(SB_M >> 4) << 24);
-}
 REPPO_DEVINL void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// Between two steps: every global-memory result of the previous step (written through the generic proxy by any
-// CTA of the cluster) becomes visible to the next step's TMA loads (async proxy) and plain loads.
-REPPO_DEVINL void handoff_sync() {
-  asm volatile("fence.proxy.async;" ::: "memory");
-  tc_fence_before();
-  __syncwarp();
-  cluster_sync_all();
-  tc_fence_after();
 }
 REPPO_DEVINL float ld_dsmem_f32(const float* local_smem_ptr, uint32_t cta_rank) {
   uint32_t remote;
@@ -104,7 +91,7 @@ REPPO_DEVINL void st_dsmem_f32(float* local_smem_ptr, uint32_t cta_rank, float v
 }
 REPPO_DEVINL void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 
-// The slab path computes in bf16-operand precision anyway: the activation math of its epilogues uses the SFU
+// The tcgen05 path computes in bf16-operand precision anyway: the activation math of its epilogues uses the SFU
 // approximations (ex2.approx / rcp.approx, ~2 ulp) -- the exact expf / IEEE division made the epilogues issue-bound.
 REPPO_DEVINL float fsigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-fmaxf(x, -80.f))); }
 REPPO_DEVINL float fswish(float x) { return x * fsigmoid(x); }

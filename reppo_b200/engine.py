@@ -39,6 +39,7 @@ class EngineConfig:
     gemm_mode: str = "fp32"         # "fp32" | "bf16"
     max_rows: int = 2048
     kl_samples: int = 16
+    max_batch_rows: int = 0         # rows per epoch of `update` (n_mb * mb): enables the per-epoch pre-gather (0 = per-step gathers)
 
     def shape(self) -> L.Shape:
         cod = self.critic_obs_dim if self.critic_obs_dim is not None else self.obs_dim
@@ -52,7 +53,8 @@ class EngineConfig:
             actor_norm=norm if self.use_actor_norm else L.NORM_NONE,
             semantics=L.SEM_JAX if self.semantics == "jax" else L.SEM_TORCH,
             gemm_mode=L.GEMM_FP32 if self.gemm_mode == "fp32" else L.GEMM_BF16,
-            max_rows=self.max_rows, kl_samples=self.kl_samples, vmin=self.vmin, vmax=self.vmax)
+            max_rows=self.max_rows, kl_samples=self.kl_samples, vmin=self.vmin, vmax=self.vmax,
+            max_batch_rows=self.max_batch_rows)
 
 
 @dataclass
@@ -72,6 +74,7 @@ class HyperParams:
     update_kl_lagrangian: bool = True
     partial_reset: bool = False
     world_size: int = 1
+    lr_anneal_steps: int = 0        # cfg.anneal_lr: optimizer steps over which lr decays linearly to 0 (src/jaxrl/reppo.py:239-244)
 
     def c_struct(self) -> L.Hyper:
         if self.actor_kl_clip_mode not in L.KL_MODES:
@@ -83,7 +86,7 @@ class HyperParams:
             actor_min_std=self.actor_min_std, kl_clip_mode=L.KL_MODES[self.actor_kl_clip_mode],
             reduce_kl=int(self.reduce_kl), update_entropy_lagrangian=int(self.update_entropy_lagrangian),
             update_kl_lagrangian=int(self.update_kl_lagrangian), partial_reset=int(self.partial_reset),
-            world_size=self.world_size)
+            world_size=self.world_size, lr_anneal_steps=int(self.lr_anneal_steps))
 
 
 class _Net:

@@ -396,10 +396,8 @@ def _cos(a, b):
     return float((a @ b) / (a.norm() * b.norm() + 1e-30))
 
 
-@pytest.mark.parametrize("thin", ["0", "7"])   # REPPO_THIN: opt-in SIMT thin-layer kernels (thin.cu), read per launch
 @pytest.mark.parametrize("sem,kw", [(O.JAX, SMALL), (O.TORCH, RAGGED), (O.JAX, dict(RAGGED, norm_type="layer"))])
-def test_bf16_mode_gradients(sem, kw, thin, monkeypatch):
-    monkeypatch.setenv("REPPO_THIN", thin)
+def test_bf16_mode_gradients(sem, kw):
     hp = O.Hyper(**kw)
     cp, ap, ap_old, flat, eps_pi, eps_kl, perms = _setup(hp, sem)
     eng = _engine(hp, sem, gemm_mode="bf16")
@@ -431,10 +429,8 @@ def test_bf16_mode_gradients(sem, kw, thin, monkeypatch):
             assert _cos(got, gref) >= 0.998, k
 
 
-@pytest.mark.parametrize("thin", ["0", "7"])
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_bf16_mode_full_update(use_graph, thin, monkeypatch):
-    monkeypatch.setenv("REPPO_THIN", thin)
+def test_bf16_mode_full_update(use_graph):
     hp = O.Hyper(**SMALL)
     sem = O.JAX
     cp, ap = O.init_params(hp, sem, seed=0)
