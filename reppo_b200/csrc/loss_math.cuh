@@ -48,6 +48,37 @@ REPPO_DEVINL void row_softmax(const float* __restrict__ head_row, const float* _
   o.lse = m + logf(s);
 }
 
+// the same with the row-invariant per-lane constants (bias_scale * zero_dist, support) already in registers: the
+// kernels that walk many rows per warp load them once
+template <int NB>
+REPPO_DEVINL void row_softmax_pre(const float* __restrict__ head_row, const float (&zb)[NB], const float (&sup)[NB], int B,
+                                  int lane, RowSoftmaxT<NB>& o) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const int c = lane + 32 * j;
+    o.lg[j] = (c < B) ? head_row[c] + zb[j] : -INFINITY;
+    m = fmaxf(m, o.lg[j]);
+  }
+  m = warp_max(m);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    o.p[j] = expf(o.lg[j] - m);   // exp(-inf) = 0 for the bins past B
+    s += o.p[j];
+  }
+  s = warp_sum(s);
+  const float inv = 1.f / s;
+  float v = 0.f;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    o.p[j] *= inv;
+    v += o.p[j] * sup[j];
+  }
+  o.value = warp_sum(v);
+  o.lse = m + logf(s);
+}
+
 REPPO_DEVINL float fldj_(float x) { return 2.f * (kLog2 - x - softplusf_(-2.f * x)); }
 
 }  // namespace reppo

@@ -58,6 +58,16 @@ critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __rest
 #pragma unroll
   for (int j = 0; j < NB; ++j) cs[j] = 0.f;
   const float inv_bw = static_cast<float>(B) / (hl.edges[B] - hl.edges[0]);
+  const float inv_den = 1.f / hl.den;
+  // row-invariant per-lane constants: the logit bias (bias_scale * zero_dist) and the support of this lane's bins
+  float zb[NB], sup[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const int c = lane + 32 * j;
+    zb[j] = (c < B) ? hl.bias_scale * zero_dist[c] : 0.f;
+    sup[j] = (c < B) ? hl.support[c] : 0.f;
+  }
+  const int jB = B >> 5, laneB = B & 31;   // where the erf of the top edge lives
   // grid-stride over rows (the launch caps the grid at a few blocks per SM): the per-block metric / column-sum atomics
   // below are issued once per block, not once per 8 rows
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
@@ -65,10 +75,9 @@ critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __rest
     const float tgt = target[src];
     const float mask = no_mask ? 1.f : 1.f - truncated[src];
     RowSoftmaxT<NB> sx;
-    row_softmax(head_out + static_cast<size_t>(row) * ld, zero_dist, hl.support, hl.bias_scale, B, lane, sx);
+    row_softmax_pre(head_out + static_cast<size_t>(row) * ld, zb, sup, B, lane, sx);
     // HL-Gauss histogram of the clipped target
     const float x = fminf(fmaxf(tgt, hl.vmin), hl.vmax);
-    const float z = erff((hl.edges[B] - x) / hl.den) - erff((hl.edges[0] - x) / hl.den) + hl.z_eps;
     float ce = 0.f, sum_tp = 0.f, tp[NB];
     // erf at the lower edge of this lane's bins; the upper edge of bin c is the lower edge of bin c + 1 = the next lane's
     // value (lane 31: this lane's value of the next group of 32 bins), so every edge is evaluated once.
@@ -77,14 +86,19 @@ critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __rest
     // |t| >= 3.92); those edges take the constant, and whole groups of 32 edges outside the window skip erff.
     const float pos = (x - hl.edges[0]) * inv_bw;   // target position in units of bins (edge index scale)
     float lo_e[NB + 1];
+    float e_top = 0.f;
 #pragma unroll
     for (int j = 0; j <= NB; ++j) {
       const int c = lane + 32 * j;
       const float dc = static_cast<float>(c) - pos;
       float e = (dc > 0.f) ? 1.f : -1.f;
-      if (fabsf(dc) < 5.5f && c <= B) e = erff((hl.edges[c] - x) / hl.den);
+      if (fabsf(dc) < 5.5f && c <= B) e = erff((hl.edges[c] - x) * inv_den);
       lo_e[j] = (c <= B) ? e : 0.f;
+      if (j == jB) e_top = lo_e[j];
     }
+    // z = erf(top edge) - erf(bottom edge) (+ eps): both already sit in registers (lane laneB group jB, lane 0 group 0)
+    const float z = __shfl_sync(0xffffffffu, e_top, laneB) - __shfl_sync(0xffffffffu, lo_e[0], 0) + hl.z_eps;
+    const float inv_z = 1.f / z;
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       const int c = lane + 32 * j;
@@ -93,8 +107,8 @@ critic_ce_kernel(const float* __restrict__ head_out, int ld, const float* __rest
       const float wrap = __shfl_sync(0xffffffffu, lo_e[j + 1], 0);
       if (c < B) {
         const float lo = lo_e[j], hi = (lane == 31) ? wrap : nxt;
-        if (hi != lo) {   // bins outside the window have probability exactly 0 (0 / z), no division needed
-          tp[j] = (hi - lo) / z;
+        if (hi != lo) {   // bins outside the window have probability exactly 0
+          tp[j] = (hi - lo) * inv_z;
           ce -= tp[j] * (sx.lg[j] - sx.lse);
           sum_tp += tp[j];
         }
@@ -207,82 +221,151 @@ critic_aux_kernel(const float* __restrict__ pred, int P, int H, int reward_head,
 // actor: sample + log-prob + KL estimate (thread per row)
 // -------------------------------------------------------------------------------------------------
 
-// One half-warp per row.  Inside the half, lane sl owns KL sample sl (+16, ...) -- the 16 samples of the forward-KL
-// estimate are the long part of the row's work, so they run in parallel and meet in shuffle reductions -- and, for the
-// policy sample itself, action dimension sl (+16).
-__global__ void __launch_bounds__(256)
+// A block of 256 threads owns 16 rows.  Phase 1: one thread per (row, action dimension) evaluates everything that needs
+// a transcendental -- the policy sample a = tanh(mu + sig eps), its log-prob term, and the per-dimension constants of the
+// current and the behaviour policy -- and parks the constants in shared memory.  Phase 2: thread (row, lane sl) owns KL
+// sample sl (+16, ...) of its row, reads that sample's A normals as one contiguous run and accumulates the row's KL term
+// and, per dimension, d lp_new / d mu and d lp_new / d sigma; the 16 lanes of a row meet through shared memory (one
+// column sum per thread) instead of 2 A shuffle reductions.
+//
+// KL samples (src/jaxrl/reppo.py:555-571, src/torchrl/reppo.py:306-312).  The reference evaluates
+//   u = atanh(clip(tanh(x_o), +-c)),  lp_old = N(.; mu_o, sig_o) - fldj,  lp_new = N(u; mu, sig) - fldj(u).
+// Two exact identities remove every transcendental from the 16 x A inner loop:
+//   (1) atanh(clip(tanh(x), +-c)) = clamp(x, +-atanh(c))  (tanh is monotone), and
+//   (2) fldj(u) appears in lp_old and lp_new with opposite signs whenever both are evaluated at u: Torch semantics always,
+//       JAX semantics whenever the sample is not clipped (there lp_old uses fldj(x_o) and u = x_o).  Only a clipped JAX
+//       sample (|x_o| > atanh(1 - 1e-4) = 4.95) keeps the correction fldj(x_o) - fldj(u).
+// In fp32 the reference's tanh -> atanh round trip carries a per-row error of 2e-5 .. 2e-3 against a float64 evaluation
+// (1 - tanh(x) loses relative precision as |x| grows); the identity form is within 1e-6 of float64, and the two agree to
+// <= 3e-6 on the batch-mean KL -- inside the fp32 tolerance the parity tests state (rel 2e-4 + 2e-6 on `kl`; the tests
+// additionally hold the kernel to 5e-5 against a float64 evaluation of the oracle).
+constexpr int kGradMaxA = 64;      // action_dim <= 64 on the actor-loss path
+constexpr int kSampleRows = 16;    // rows per block
+constexpr int kSampleChunk = 8;    // action dimensions per pass of phase 2
+__global__ void __launch_bounds__(256, 4)
 actor_sample_kernel(const float* __restrict__ out, const float* __restrict__ out_old, const int* __restrict__ old_idx,
                     const float* __restrict__ eps_pi, const float* __restrict__ eps_kl, int rows, int A, int kl_samples,
                     ActorConsts ac, float* __restrict__ act_out, int act_ld, float* __restrict__ logp_out,
                     float* __restrict__ kl_out, float* __restrict__ gmu_kl, float* __restrict__ gsig_kl,
                     __nv_bfloat16* __restrict__ act_h, int act_ldh) {
   REPPO_PDL_PROLOGUE();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int hw = lane >> 4, sl = lane & 15;
-  const int rl = (blockIdx.x * 8 + warp) * 2 + hw;
-  const bool ok = rl < rows;
-  const int row = ok ? rl : rows - 1;   // idle halves shadow a valid row (loads stay in bounds, nothing is written)
-  const float* o = out + static_cast<size_t>(row) * 2 * A;
-  const float* oo = out_old + static_cast<size_t>(old_idx ? old_idx[row] : row) * 2 * A;
+  __shared__ float4 cst[kSampleRows][kGradMaxA];                     // (mu, 1 / sig, mu_o, sig_o)
+  __shared__ float2 rowk[kSampleRows][kGradMaxA];                    // (log-prob term, log sig - log sig_o) per dimension
+  __shared__ float red[kSampleRows][16][2 * kSampleChunk + 1];       // per (row, sample lane): gm[8] | gs[8] (+1: banks)
+  const int t = threadIdx.x;
+  const int r = t >> 4, sl = t & 15;
+  const float u_max = atanhf(ac.action_clip);
   const float inv_s = 1.f / static_cast<float>(kl_samples);
-  float logp = 0.f, lp_old = 0.f, lp_new = 0.f;
-  for (int k = sl; k < A; k += 16) {
-    const float mu = o[k], sig = expf(o[A + k]) + ac.min_std;
-    const float e = eps_pi[static_cast<size_t>(row) * A + k];
-    const float x = mu + sig * e;
-    const float a = tanhf(x);
-    if (ok) {
-      act_out[static_cast<size_t>(row) * act_ld + k] = a;
-      if (act_h != nullptr) act_h[static_cast<size_t>(row) * act_ldh + k] = __float2bfloat16_rn(a);
-    }
-    const float log_sig = logf(sig);
-    if (ac.clip_policy_sample) {
-      // torchrl/reppo.py:301: log_prob(actions.clip(+-c)) -> base.log_prob(atanh(.)) - fldj(atanh(.))
-      const float xc = atanhf(fminf(fmaxf(a, -ac.action_clip), ac.action_clip));
-      const float zz = (xc - mu) / sig;
-      logp += -0.5f * zz * zz - log_sig - kHalfLog2Pi - fldj_(xc);
-    } else {
-      // distrax sample_and_log_prob: base log-prob at the pre-tanh sample minus fldj
-      logp += -0.5f * e * e - log_sig - kHalfLog2Pi - fldj_(x);
-    }
-  }
-  // forward KL samples from the behaviour policy
-  for (int k = 0; k < A; ++k) {
-    const float mu = o[k], sig = expf(o[A + k]) + ac.min_std, log_sig = logf(sig), inv_sig = 1.f / sig;
-    const float mu_o = oo[k], sig_o = expf(oo[A + k]) + ac.min_std, log_sig_o = logf(sig_o);
-    float gm = 0.f, gs = 0.f;
-    for (int s = sl; s < kl_samples; s += 16) {
-      const float eo = eps_kl[(static_cast<size_t>(s) * rows + row) * A + k];
-      const float xo = mu_o + sig_o * eo;
-      const float u = atanhf(fminf(fmaxf(tanhf(xo), -ac.action_clip), ac.action_clip));
-      const float fu = fldj_(u);
-      if (ac.old_logp_at_clipped) {
-        const float zo = (u - mu_o) / sig_o;
-        lp_old += -0.5f * zo * zo - log_sig_o - kHalfLog2Pi - fu;
-      } else {
-        lp_old += -0.5f * eo * eo - log_sig_o - kHalfLog2Pi - fldj_(xo);
+  const bool vec2 = ((A & 1) == 0) && ((reinterpret_cast<uintptr_t>(eps_kl) & 7) == 0);
+  for (int base = blockIdx.x * kSampleRows; base < rows; base += gridDim.x * kSampleRows) {
+    // ---- phase 1: one thread per (row, dimension)
+    for (int i = t; i < kSampleRows * A; i += 256) {
+      const int rr = i / A, k = i - rr * A, row = base + rr;
+      if (row < rows) {
+        const float* o = out + static_cast<size_t>(row) * 2 * A;
+        const float* oo = out_old + static_cast<size_t>(old_idx ? old_idx[row] : row) * 2 * A;
+        const float mu = o[k], sig = expf(o[A + k]) + ac.min_std;
+        const float mu_o = oo[k], sig_o = expf(oo[A + k]) + ac.min_std;
+        const float log_sig = logf(sig);
+        cst[rr][k] = make_float4(mu, 1.f / sig, mu_o, sig_o);
+        const float e = eps_pi[static_cast<size_t>(row) * A + k];
+        const float x = mu + sig * e;
+        const float a = tanhf(x);
+        act_out[static_cast<size_t>(row) * act_ld + k] = a;
+        if (act_h != nullptr) act_h[static_cast<size_t>(row) * act_ldh + k] = __float2bfloat16_rn(a);
+        float lp;
+        if (ac.clip_policy_sample) {
+          // torchrl/reppo.py:301: log_prob(actions.clip(+-c)) -> base.log_prob(atanh(.)) - fldj(atanh(.))
+          const float xc = atanhf(fminf(fmaxf(a, -ac.action_clip), ac.action_clip));
+          const float zz = (xc - mu) / sig;
+          lp = -0.5f * zz * zz - log_sig - kHalfLog2Pi - fldj_(xc);
+        } else {
+          // distrax sample_and_log_prob: base log-prob at the pre-tanh sample minus fldj
+          lp = -0.5f * e * e - log_sig - kHalfLog2Pi - fldj_(x);
+        }
+        rowk[rr][k] = make_float2(lp, log_sig - logf(sig_o));
       }
-      const float zn = (u - mu) * inv_sig;
-      lp_new += -0.5f * zn * zn - log_sig - kHalfLog2Pi - fu;
-      gm += zn * inv_sig;                   // d lp_new / d mu
-      gs += (zn * zn - 1.f) * inv_sig;      // d lp_new / d sigma
     }
+    __syncthreads();
+    // ---- phase 2: thread (r, sl) = KL sample sl (+16, ...) of row base + r
+    const int row = base + r;
+    const bool ok = row < rows;
+    float dsum = 0.f;   // sum over this lane's samples and all dimensions of (lp_old - lp_new) minus the constant part
+    for (int c0 = 0; c0 < A; c0 += kSampleChunk) {
+      float gm[kSampleChunk], gs[kSampleChunk];
 #pragma unroll
-    for (int of = 8; of > 0; of >>= 1) { gm += __shfl_xor_sync(0xffffffffu, gm, of); gs += __shfl_xor_sync(0xffffffffu, gs, of); }
+      for (int j = 0; j < kSampleChunk; ++j) { gm[j] = 0.f; gs[j] = 0.f; }
+      if (ok) {
+        for (int sidx = sl; sidx < kl_samples; sidx += 16) {
+          const float* ep = eps_kl + (static_cast<size_t>(sidx) * rows + row) * A + c0;
+          float eo[kSampleChunk];
+          if (vec2 && c0 + kSampleChunk <= A) {
+#pragma unroll
+            for (int j = 0; j < kSampleChunk; j += 2) {
+              const float2 v = *reinterpret_cast<const float2*>(ep + j);
+              eo[j] = v.x; eo[j + 1] = v.y;
+            }
+          } else if (vec2) {
+#pragma unroll
+            for (int j = 0; j < kSampleChunk; j += 2) {
+              float2 v = make_float2(0.f, 0.f);
+              if (c0 + j < A) v = *reinterpret_cast<const float2*>(ep + j);   // A even: the pair is inside or outside
+              eo[j] = v.x; eo[j + 1] = v.y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < kSampleChunk; ++j) eo[j] = (c0 + j < A) ? ep[j] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < kSampleChunk; ++j) {
+            if (c0 + j < A) {
+              const float4 cc = cst[r][c0 + j];
+              const float xo = cc.z + cc.w * eo[j];
+              const float u = fminf(fmaxf(xo, -u_max), u_max);
+              const float zn = (u - cc.x) * cc.y;
+              if (ac.old_logp_at_clipped) {
+                const float zo = (u - cc.z) / cc.w;
+                dsum += 0.5f * zn * zn - 0.5f * zo * zo;
+              } else {
+                dsum += 0.5f * zn * zn - 0.5f * eo[j] * eo[j];
+                if (u != xo) dsum -= fldj_(xo) - fldj_(u);   // clipped sample: the two fldj terms no longer cancel
+              }
+              gm[j] += zn * cc.y;                   // d lp_new / d mu
+              gs[j] += (zn * zn - 1.f) * cc.y;      // d lp_new / d sigma
+            }
+          }
+        }
+      }
+      __syncthreads();   // the previous chunk's column sums have been read
+#pragma unroll
+      for (int j = 0; j < kSampleChunk; ++j) { red[r][sl][j] = gm[j]; red[r][sl][kSampleChunk + j] = gs[j]; }
+      __syncthreads();
+      {
+        // thread (r, q): q < 8 -> d/d mu of dimension c0 + q, q >= 8 -> d/d sigma of dimension c0 + q - 8
+        const int q = sl, k = c0 + (q & (kSampleChunk - 1));
+        if (ok && k < A) {
+          float acc = 0.f;
+#pragma unroll
+          for (int l = 0; l < 16; ++l) acc += red[r][l][q];
+          (q < kSampleChunk ? gmu_kl : gsig_kl)[static_cast<size_t>(row) * A + k] = acc * inv_s;
+        }
+      }
+    }
+    // ---- row scalars: log-prob of the policy sample and the KL estimate
+    float logp = 0.f, klc = 0.f;
+    if (ok)
+      for (int k = sl; k < A; k += 16) { const float2 v = rowk[r][k]; logp += v.x; klc += v.y; }
+#pragma unroll
+    for (int of = 8; of > 0; of >>= 1) {
+      logp += __shfl_xor_sync(0xffffffffu, logp, of);
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, of);
+      klc += __shfl_xor_sync(0xffffffffu, klc, of);
+    }
     if (sl == 0 && ok) {
-      gmu_kl[static_cast<size_t>(row) * A + k] = gm * inv_s;
-      gsig_kl[static_cast<size_t>(row) * A + k] = gs * inv_s;
+      logp_out[row] = logp;
+      kl_out[row] = dsum * inv_s + klc;
     }
-  }
-#pragma unroll
-  for (int of = 8; of > 0; of >>= 1) {
-    logp += __shfl_xor_sync(0xffffffffu, logp, of);
-    lp_old += __shfl_xor_sync(0xffffffffu, lp_old, of);
-    lp_new += __shfl_xor_sync(0xffffffffu, lp_new, of);
-  }
-  if (sl == 0 && ok) {
-    logp_out[row] = logp;
-    kl_out[row] = (lp_old - lp_new) * inv_s;
+    __syncthreads();   // cst / rowk / red are rewritten by the next row block
   }
 }
 
@@ -316,7 +399,6 @@ actor_q_kernel(const float* __restrict__ head_out, int ld, const float* __restri
 // d loss / d (mu, log_std) per row, scalar gradients for log_temp / log_lagrange, metrics.
 // One warp per row (lane k owns action dimension k, +32 ...): 2048 rows give 2048 warps instead of 16 blocks of
 // row-serial threads; metric partials and the bias-gradient column sums meet per block in shared memory.
-constexpr int kGradMaxA = 64;   // action_dim <= 64 on this path
 __global__ void __launch_bounds__(256)
 actor_grad_kernel(const float* __restrict__ out, const float* __restrict__ eps_pi, const float* __restrict__ act, int act_ld,
                   const float* __restrict__ dact, int dact_ld, const float* __restrict__ logp_in,
@@ -452,8 +534,9 @@ cudaError_t launch_actor_sample(const float* out, const float* out_old, const in
                                 int act_ld, float* logp, float* kl, float* gmu, float* gsig, void* act_h, int act_ldh,
                                 cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
-  const int rows_per_block = 16;   // 8 warps x 2 half-warps
-  launch_k((actor_sample_kernel), dim3((rows + rows_per_block - 1) / rows_per_block), dim3(256), 0, st, out, out_old, old_idx, eps_pi, eps_kl, rows, A, kl_samples, ac, act_out, act_ld, logp, kl, gmu, gsig, static_cast<__nv_bfloat16*>(act_h), act_ldh);
+  if (A > kGradMaxA) return cudaErrorInvalidValue;
+  const int want = (rows + kSampleRows - 1) / kSampleRows;
+  launch_k((actor_sample_kernel), dim3(want < kLossMaxBlocks ? want : kLossMaxBlocks), dim3(256), 0, st, out, out_old, old_idx, eps_pi, eps_kl, rows, A, kl_samples, ac, act_out, act_ld, logp, kl, gmu, gsig, static_cast<__nv_bfloat16*>(act_h), act_ldh);
   return cudaGetLastError();
 }
 

@@ -244,7 +244,7 @@ def _engine_of(module: _ArenaModule) -> ReppoEngine:
 
 def bind_engine(actor: Actor, critic: Critic, old_actor: Optional[Actor] = None, *, max_rows: int = 2048,
                 semantics: Optional[str] = None, norm_type: str = "rms", gemm_mode: str = "fp32",
-                device=None) -> ReppoEngine:
+                device=None, max_batch_rows: int = 0) -> ReppoEngine:
     """Create the engine for (actor, critic) and move their parameters into its arenas."""
     semantics = semantics or critic.semantics
     ecfg = EngineConfig(
@@ -252,7 +252,8 @@ def bind_engine(actor: Actor, critic: Critic, old_actor: Optional[Actor] = None,
         actor_hidden_dim=actor.hidden_dim, num_bins=critic.num_atoms, vmin=critic.vmin, vmax=critic.vmax,
         num_critic_encoder_layers=critic.encoder_layers, num_critic_head_layers=critic.head_layers,
         num_critic_pred_layers=critic.pred_layers, num_actor_layers=actor.layers, use_critic_norm=critic.use_norm,
-        use_actor_norm=actor.use_norm, norm_type=norm_type, semantics=semantics, gemm_mode=gemm_mode, max_rows=max_rows)
+        use_actor_norm=actor.use_norm, norm_type=norm_type, semantics=semantics, gemm_mode=gemm_mode, max_rows=max_rows,
+        max_batch_rows=max_batch_rows)
     eng = ReppoEngine(ecfg, device=device)
     for mod, net in ((critic, eng.critic), (actor, eng.actor)):
         assert {k: v[1] for k, v in mod._layout.items()} == {k: tuple(v[1]) for k, v in net.layout.items()}, "layout mismatch"
@@ -283,8 +284,10 @@ def make_train_state(cfg, n_obs: int, n_critic_obs: int, n_act: int, device=None
     old_actor.load_state_dict(actor.state_dict())
     mb = (int(h.num_steps) * int(h.num_envs)) // int(h.num_mini_batches)
     gemm_mode = "bf16" if cfg.platform.get("amp_dtype", "f32") == "bf16" else "fp32"
-    eng = bind_engine(actor, critic, old_actor, max_rows=max_rows or mb, semantics=semantics,
-                      norm_type=b200.get("norm_type", "rms"), gemm_mode=gemm_mode, device=device)
+    # the workspace serves the minibatch steps AND the per-environment-step forwards of the collection loop (num_envs rows)
+    eng = bind_engine(actor, critic, old_actor, max_rows=max_rows or max(mb, int(h.num_envs)), semantics=semantics,
+                      norm_type=b200.get("norm_type", "rms"), gemm_mode=gemm_mode, device=device,
+                      max_batch_rows=mb * int(h.num_mini_batches))
     return TrainState(device=device, actor=actor, old_actor=old_actor, critic=critic, normalizer=nn.Identity(),
                       critic_normalizer=nn.Identity(), actor_optimizer=ArenaOptimizer(h.lr),
                       critic_optimizer=ArenaOptimizer(h.lr), scaler=None, engine=eng)
@@ -300,15 +303,27 @@ def _hyper(cfg, train_state: TrainState, which: str = "critic") -> HyperParams:
         actor_min_std=float(train_state.actor.min_std), actor_kl_clip_mode=str(h.actor_kl_clip_mode),
         reduce_kl=bool(h.get("reduce_kl", True)), update_entropy_lagrangian=bool(h.get("update_entropy_lagrangian", True)),
         update_kl_lagrangian=bool(h.get("update_kl_lagrangian", True)),
-        partial_reset=bool(cfg.env.get("partial_reset", False)))
+        partial_reset=bool(cfg.env.get("partial_reset", False)), lr_anneal_steps=_anneal_steps(cfg))
+
+
+def _anneal_steps(cfg) -> int:
+    """cfg.anneal_lr: optax.linear_schedule(lr, 0, num_updates) with num_updates = (total_time_steps // (num_steps *
+    num_envs)) * num_epochs * num_mini_batches (src/jaxrl/reppo.py:239-244); evaluated on the device at each network's
+    optimizer step counter (optim.cu), so the captured graph of reppo_update is reused across updates."""
+    h = cfg.hyperparameters
+    if not bool(h.get("anneal_lr", False)):
+        return 0
+    iters = int(h.total_time_steps) // (int(h.num_steps) * int(h.num_envs))
+    return max(1, iters * int(h.num_epochs) * int(h.num_mini_batches))
 
 
 def _engine_for(cfg, train_state: TrainState) -> ReppoEngine:
     if train_state.engine is None:
         h = cfg.hyperparameters
         mb = (int(h.num_steps) * int(h.num_envs)) // int(h.num_mini_batches)
-        train_state.engine = bind_engine(train_state.actor, train_state.critic, train_state.old_actor, max_rows=mb,
-                                         device=train_state.device)
+        train_state.engine = bind_engine(train_state.actor, train_state.critic, train_state.old_actor,
+                                         max_rows=max(mb, int(h.num_envs)), device=train_state.device,
+                                         max_batch_rows=mb * int(h.num_mini_batches))
     return train_state.engine
 
 
@@ -722,6 +737,10 @@ def reppo_update(train_state: TrainState, transition: Mapping[str, torch.Tensor]
         reppo_prefetch(train_state, prefetch_next, cfg, generator=generator)
     if return_device_metrics:
         return m, sm
+    if world_size > 1:
+        # per-rank metrics are partial sums over this rank's rows (already divided by world * mb): one all-reduce per update
+        from . import dist as _dp
+        m = _dp.reduce_metrics(m)
     md = eng.metrics_dict(m)  # one device->host read per update
     logs = {  # Torch keys (src/torchrl/reppo.py:275-283,348-358)
         "critic_grad_norm": md["critic_grad_norm"], "qf_loss": md["critic_loss"], "qf_max": md["target_max"],
