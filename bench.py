@@ -135,74 +135,102 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_sample(hp, sem_name, seconds=12.0, min_steps=2):
-    """Oracle port timed on the host cores: scan + a bounded number of minibatch steps, extrapolated."""
-    import torch
-    from oracle import reppo_oracle as O
-    sem = O.JAX if sem_name == "jax" else O.TORCH
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cp, ap = O.init_params(hp, sem, seed=0)
-    batch = O.synthetic_rollout(hp, seed=0)
-    eps_pi, eps_kl = O.synthetic_noise(hp)
-    perms = O.synthetic_perms(hp)
-    t0 = time.perf_counter()
-    target = O.compute_targets({k: v.clone() for k, v in batch.items()}, hp, sem)
-    t_scan = time.perf_counter() - t0
-    flat = O.flatten_batch(batch, target)
-    ts = O.TrainState.create(cp, ap)
-    mbs = hp.minibatch_size
-    times = []
-    j = 0
-    t_begin = time.perf_counter()
-    while True:
-        idx = perms[0, (j % hp.num_mini_batches) * mbs:(j % hp.num_mini_batches + 1) * mbs]
+class CpuArm:
+    """The reference update on the host cores, as a bounded sample of the workload.
+
+    kind "reference": the reference's OWN Torch closures (make_postprocess_fn / make_critic_update_fn /
+    make_actor_update_fn, src/torchrl/reppo.py:173-360, stock code path, its own noise draws) imported from
+    /root/reference or from the byte-compiled oracle/_ref that oracle/build_ref.py ships to the GPU box.
+    kind "port": oracle/reppo_oracle.py (only when neither exists).
+    One sample = compute_gve over the whole rollout + `m_steps` consecutive critic+actor minibatch steps, i.e. the fraction
+    f = m_steps / (num_epochs * num_mini_batches) of one update; value = f * S / wall time of the sample (nothing is
+    extrapolated: ms_per_step is the measured wall time of the sample)."""
+
+    def __init__(self, hp, sem_name, m_steps):
+        import torch
+        from oracle import ref_torch_shim as RB
+        from oracle import reppo_oracle as O
+        self.hp, self.O, self.m = hp, O, min(m_steps, hp.num_epochs * hp.num_mini_batches)
+        self.cores = os.cpu_count() or 1
+        self.kind = "reference" if RB.available() else "port"
+        self.sem_name = "torch" if self.kind == "reference" else sem_name
+        sem = O.TORCH if self.sem_name == "torch" else O.JAX
+        self.sem = sem
+        cp, ap = O.init_params(hp, sem, seed=0)
+        self.batch = O.synthetic_rollout(hp, seed=0)
+        g = torch.Generator().manual_seed(5)
+        self.perm = torch.randperm(hp.batch_size, generator=g)
+        if self.kind == "reference":
+            ref = RB.load_reference()   # importing the reference sets OMP_NUM_THREADS=1 (reppo.py:37); the shim restores it
+            self.ts = RB.build_train_state(ref, hp, cp, ap)
+            cfg = RB.make_cfg(hp)
+            self.post = ref.reppo.make_postprocess_fn(cfg, None)
+            self.upd_c = ref.reppo.make_critic_update_fn(cfg, self.ts)
+            self.upd_a = ref.reppo.make_actor_update_fn(cfg, self.ts)
+            self.transition = RB.to_ref_transition(self.batch)
+        else:
+            self.ts = O.TrainState.create(cp, ap)
+            self.eps = O.synthetic_noise(hp)
+        torch.set_num_threads(self.cores)
+        self.threads = torch.get_num_threads()
+
+    def run(self):
+        """One sample; returns its wall time in seconds."""
+        O, hp = self.O, self.hp
+        mbs, n_mb = hp.minibatch_size, hp.num_mini_batches
         t0 = time.perf_counter()
-        mb = O.take(flat, idx)
-        ts, _, _ = O.critic_step(ts, mb, hp, sem)
-        ts, _, _ = O.actor_step(ts, mb, eps_pi[0], eps_kl[0], hp, sem)
-        dt = time.perf_counter() - t0
-        if j > 0:
-            times.append(dt)  # first step is warm-up
-        j += 1
-        if len(times) >= min_steps and time.perf_counter() - t_begin > seconds:
-            break
-        if len(times) >= 64:
-            break
-    step = sorted(times)[len(times) // 2]
-    n_steps = hp.num_epochs * hp.num_mini_batches
-    total = t_scan + n_steps * step
-    return {"value": hp.batch_size / total, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"TD(lambda) scan ({t_scan * 1e3:.1f} ms) + median of {len(times)} critic+actor minibatch steps "
-                      f"({step * 1e3:.1f} ms each, mb={mbs}) of oracle/reppo_oracle.py ({sem_name} semantics, fp32, torch CPU), "
-                      f"extrapolated to {n_steps} steps"}, total
+        if self.kind == "reference":
+            data = self.post(self.ts, self.transition)          # compute_gve + flatten (:173-221)
+            for j in range(self.m):
+                mini = data[self.perm[(j % n_mb) * mbs:(j % n_mb + 1) * mbs]]
+                self.upd_c(mini)
+                self.upd_a(mini)
+        else:
+            target = O.compute_targets({k: v.clone() for k, v in self.batch.items()}, hp, self.sem)
+            flat = O.flatten_batch(self.batch, target)
+            for j in range(self.m):
+                mb = O.take(flat, self.perm[(j % n_mb) * mbs:(j % n_mb + 1) * mbs])
+                self.ts, _, _ = O.critic_step(self.ts, mb, hp, self.sem)
+                self.ts, _, _ = O.actor_step(self.ts, mb, self.eps[0][0], self.eps[1][0], hp, self.sem)
+        return time.perf_counter() - t0
+
+    def describe(self, wall):
+        hp = self.hp
+        frac = self.m / (hp.num_epochs * hp.num_mini_batches)
+        what = ("the reference's own Torch closures (src/torchrl/reppo.py make_postprocess_fn / make_critic_update_fn / "
+                "make_actor_update_fn, stock code path, byte-compiled copy oracle/_ref)" if self.kind == "reference"
+                else f"oracle/reppo_oracle.py ({self.sem_name} semantics)")
+        return {"value": frac * hp.batch_size / wall, "unit": "samples/s", "cores": self.threads, "kind": self.kind,
+                "sample": f"compute_gve over the whole rollout (S={hp.batch_size}) + {self.m} consecutive critic+actor minibatch "
+                          f"steps (mb={hp.minibatch_size}) = {frac:.4f} of one update, {wall:.2f} s wall, fp32 torch CPU, {what}; "
+                          f"value = {frac:.4f} * S / wall"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU path.  JAX is not installable here and /root/reference is absent on the
-    GPU box, so the arm times the oracle port (a line-by-line restatement pinned to the reference's Torch closures)."""
+    """--impl reference: the reference's own CPU implementation of the update on the host cores (JAX is not installable in
+    this image, so it is the reference's Torch closures; see CpuArm).  Each step is a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg, D, A, term, rs = make_cfg(args.config, args.semantics)
     hp = oracle_hyper(cfg, D, A)
-    vals, last = [], None
+    arm = CpuArm(hp, args.semantics, m_steps=hp.num_mini_batches)   # one epoch's worth of minibatch steps per sample
+    walls = []
     for i in range(args.warmup + args.steps):
-        base, total = cpu_sample(hp, args.semantics, seconds=6.0)
+        w = arm.run()
         if i >= args.warmup:
-            vals.append(total)
-        last = base
-    ms = 1e3 * sum(vals) / len(vals)
-    value = hp.batch_size / (ms / 1e3)
-    last["value"] = value
+            walls.append(w)
+    wall = sum(walls) / len(walls)
+    base = arm.describe(wall)
     line = {
-        "impl": "reference", "metric": "reppo_update_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": "reppo_update_samples_per_s", "value": base["value"], "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.config, cfg, D, A, 1), "cpu_baseline": last,
-        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "jax/flax/optax are not installable in this image and /root/reference does not exist on the GPU box: "
-                "this arm times oracle/reppo_oracle.py (CPU restatement of the reference update) on all host cores",
+        "config": workload_config(args.config, cfg, D, A, 1), "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "full_update_ms_at_this_rate": hp.batch_size / base["value"] * 1e3,
+        "note": "jax/flax/optax are not installable in this image: the reference arm runs the reference's Torch update path "
+                "(kind=reference) when oracle/_ref or /root/reference is present, else the oracle port (kind=port)",
     }
     emit(line)
 
@@ -217,6 +245,172 @@ def workload_config(name, cfg, D, A, world):
             "samples_per_gpu": S, "minibatch_per_gpu": S // h.num_mini_batches, "optimizer_steps": h.num_epochs * h.num_mini_batches,
             "parallelism": f"dp{world} over environments" if world > 1 else "single GPU",
             "l2": "rollout batch (292 MB at C2) exceeds the 126 MB L2; weights/Adam state are L2-resident by design"}
+
+
+def measure_config(name, semantics, gemm, world, rank, dev, steps, warmup, strong=False, overrides=()):
+    """One more workload at this GPU count: builds its own engine + synthetic rollout, times `steps` full updates (CUDA events,
+    max over ranks) and frees everything again.  strong=True: ONE named batch whose env columns are split over the ranks
+    (N / world envs and minibatch / world rows per rank) instead of one named batch per rank."""
+    import torch
+    import torch.distributed as dist
+    from oracle import reppo_oracle as O
+    from reppo_b200 import torch_api as T
+    from reppo_b200.engine import HyperParams
+    cfg, D, A, term, rs = make_cfg(name, semantics, list(overrides))
+    if gemm == "bf16":
+        cfg.platform.amp_dtype = "bf16"
+    h = cfg.hyperparameters
+    hp_g = oracle_hyper(cfg, D, A)                      # the named (global) batch
+    if strong:
+        if h.num_envs % world:
+            return {"skipped": f"num_envs={h.num_envs} not divisible by {world}"}
+        h.num_envs = h.num_envs // world
+    hp = oracle_hyper(cfg, D, A)                        # this rank's share
+    S, n_mb, E = hp.batch_size, hp.num_mini_batches, hp.num_epochs
+    mb = S // n_mb
+    sem = O.JAX if semantics == "jax" else O.TORCH
+    if strong:
+        batch = O.synthetic_rollout(hp_g, seed=0, terminate=term, reward_scaling=rs, num_envs=hp.num_envs,
+                                    env_offset=rank * hp.num_envs)
+    else:
+        batch = O.synthetic_rollout(hp, seed=rank, terminate=term, reward_scaling=rs)
+    cp, ap_ = O.init_params(hp, sem, seed=0)
+    ts = T.make_train_state(cfg, D, D, A, device=dev)
+    eng = ts.engine
+    eng.load_params(cp, ap_)
+    if world > 1:
+        from reppo_b200 import dist as dp_plumbing
+        dp_plumbing.attach_nccl(eng, rank, world)
+    hyp = HyperParams(gamma=h.gamma, lmbda=h.lmbda, lr=h.lr, max_grad_norm=h.max_grad_norm, kl_bound=h.kl_bound,
+                      ent_target_mult=h.ent_target_mult, aux_loss_mult=h.aux_loss_mult, actor_min_std=h.actor_min_std,
+                      actor_kl_clip_mode=h.actor_kl_clip_mode, world_size=world)
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    devb = {k: v.to(dev) for k, v in batch.items()}
+    del batch
+    perms = torch.stack([torch.randperm(S, device=dev, generator=g) for _ in range(E)]).to(torch.int32)
+    eps_pi = torch.randn(E, mb, A, device=dev, generator=g)
+    eps_kl = torch.randn(E, 16, mb, A, device=dev, generator=g)
+    target = torch.empty(hp.num_steps, hp.num_envs, device=dev)
+    flat = {k: v.reshape(-1, *v.shape[2:]) for k, v in devb.items()}
+    flat["target"] = target.reshape(-1)
+    cb = eng.make_batch(flat)
+    step_metrics = torch.empty(E * n_mb, 24, device=dev)
+
+    def one_update():
+        eng.td_lambda(devb["soft_reward"], devb["value"], devb["done"], devb["truncated"], devb["importance_weight"],
+                      h.gamma, h.lmbda, out=target)
+        eng.sync_actor_old()
+        eng.update(cb, perms, eps_pi, eps_kl, hyp, n_mb, use_graph=True, step_metrics=step_metrics)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        one_update()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        one_update()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    fm = eng.metrics_dict(eng.metrics)
+    out = {"value": S * world / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+           "dtype": "f32" if gemm == "fp32" else "bf16", "scaling": "strong" if strong else "weak",
+           "in_update_tflops": gemm_flops_per_update(hp) * world / (ms * 1e-3) / 1e12,
+           "workload": workload_config(name, cfg, D, A, world)["workload"],
+           "finite": bool(all(math.isfinite(fm[k]) for k in ("critic_loss", "actor_loss", "kl")))}
+    if world > 1:
+        eng.lib.reppo_nccl_finalize(eng.ctx)
+    del eng, ts, devb, flat, cb, perms, eps_pi, eps_kl, target, step_metrics
+    torch.cuda.empty_cache()
+    return out
+
+
+def dp_check(world, rank, dev, gemm):
+    """world > 1, outside every timed region: two epochs x two minibatch steps at the benchmarked step shape (global
+    minibatch 2048 rows, H = 512, obs 17 / act 6) with the env columns split over the ranks and the gradients all-reduced by
+    the library; rank 0 replays the rank-concatenated minibatches through the CPU oracle (tests/test_dp.py does the same on
+    2 GPUs).  Checks: step-0 critic loss / gradient norm / actor loss against the oracle, every rank bit-identical
+    parameters after the update."""
+    import torch
+    import torch.distributed as dist
+    from oracle import reppo_oracle as O
+    from reppo_b200 import _lib as L
+    from reppo_b200 import dist as D_
+    from reppo_b200.engine import EngineConfig, HyperParams, ReppoEngine
+    hp = O.Hyper(num_steps=4, num_envs=1024, num_mini_batches=2, num_epochs=2, critic_hidden_dim=512, actor_hidden_dim=512,
+                 num_bins=151, vmin=0.0, vmax=150.0, obs_dim=17, critic_obs_dim=17, action_dim=6)
+    if hp.num_envs % world or hp.minibatch_size % world:
+        return {"ok": None, "skipped": f"1024 envs not divisible by {world}"}
+    sem = O.JAX
+    cp, ap = O.init_params(hp, sem, seed=0)
+    batch = O.synthetic_rollout(hp, seed=0, terminate=True)
+    per = hp.num_envs // world
+    loc = D_.shard_envs(batch, rank, world)
+    S_loc = hp.num_steps * per
+    mb_loc = S_loc // hp.num_mini_batches
+    eps_pi_g, eps_kl_g = O.synthetic_noise(hp)
+    perms = D_.local_permutations(7, hp.num_epochs, S_loc, rank)
+    eng = ReppoEngine(EngineConfig(obs_dim=17, action_dim=6, semantics="jax", gemm_mode=gemm, max_rows=mb_loc,
+                                   max_batch_rows=S_loc), device=dev)
+    eng.load_params(cp, ap)
+    D_.attach_nccl(eng, rank, world)
+    devb = {k: v.to(dev) for k, v in loc.items()}
+    tgt = eng.td_lambda(devb["soft_reward"], devb["value"], devb["done"], devb["truncated"], devb["importance_weight"],
+                        hp.gamma, hp.lmbda)
+    flat = {k: v.reshape(-1, *v.shape[2:]) for k, v in devb.items()}
+    flat["target"] = tgt.reshape(-1)
+    e1 = eps_pi_g[:, rank * mb_loc:(rank + 1) * mb_loc].contiguous().to(dev)
+    e2 = eps_kl_g[:, :, rank * mb_loc:(rank + 1) * mb_loc].contiguous().to(dev)
+    m, sm = eng.update(eng.make_batch(flat), perms.to(dev), e1, e2, HyperParams(world_size=world), hp.num_mini_batches,
+                       use_graph=True)
+    torch.cuda.synchronize()
+    sm = D_.reduce_metrics(sm)
+    same = True
+    for net in (eng.critic, eng.actor):
+        p0 = net.params.clone()
+        dist.broadcast(p0, 0)
+        flag = torch.tensor([1.0 if torch.equal(net.params, p0) else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        same = same and bool(flag.item() == 1.0)
+    res = None
+    if rank == 0:
+        rows = []
+        for r in range(world):
+            pr = D_.local_permutations(7, hp.num_epochs, S_loc, r).long()
+            t, n = pr // per, pr % per
+            rows.append((t * hp.num_envs + r * per + n).reshape(hp.num_epochs, hp.num_mini_batches, mb_loc))
+        gperm = torch.cat(rows, dim=2).reshape(hp.num_epochs, -1)
+        ts2, _, _, traces = O.learn_step(O.TrainState.create(cp, ap), {k: v.clone() for k, v in batch.items()}, gperm,
+                                         eps_pi_g, eps_kl_g, hp, sem, trace=True)
+        col = {k: i for i, k in enumerate(L.METRIC_NAMES)}
+        tol = 2e-5 if gemm == "fp32" else 2e-2
+        rel = lambda a, b: abs(a - b) / (abs(b) + 1e-12)
+        smc = sm.cpu()
+        e_loss = rel(smc[0, col["critic_loss"]].item(), traces[0]["critic/loss"].item())
+        e_gn = rel(smc[0, col["critic_grad_norm"]].item(), traces[0]["critic/grad_norm"].item())
+        e_al = rel(smc[0, col["actor_loss"]].item(), traces[0]["actor/loss"].item())
+        perr = max((eng.critic.view(eng.critic.params, k).cpu() - v).abs().max().item() for k, v in ts2.critic.items())
+        ok = same and e_loss <= tol and e_gn <= 5 * tol and e_al <= 10 * tol and perr <= 2 * hp.lr * len(traces) + 1e-6
+        res = {"ok": bool(ok), "ranks_bit_identical_params": same, "step0_critic_loss_rel_err": e_loss,
+               "step0_critic_grad_norm_rel_err": e_gn, "step0_actor_loss_rel_err": e_al, "max_param_err": perr,
+               "param_bound": 2 * hp.lr * len(traces), "tolerance": tol, "steps": len(traces),
+               "shape": f"global minibatch {hp.minibatch_size} rows ({mb_loc} per rank), H=512, obs 17 / act 6, {gemm} GEMMs, "
+                        "graph + two-chain pipeline + NCCL all-reduce inside the graph",
+               "oracle": "oracle/reppo_oracle.py learn_step on the rank-concatenated minibatches (CPU, rank 0)"}
+    eng.lib.reppo_nccl_finalize(eng.ctx)
+    del eng
+    torch.cuda.empty_cache()
+    return res
+
 
 
 def main():
@@ -234,6 +428,8 @@ def main():
                     help="extra hydra-style override for experiments, e.g. hyperparameters.num_epochs=4 (not the named workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large", action="store_true", help="skip the large-shape GEMM leg (C5 sweep shapes)")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the extra workload legs (the other BASELINE.json configurations, the fp32 leg, strong scaling, dp_check)")
     ap.add_argument("--profile-only", action="store_true", help="warm-up + one update, no timing legs (for ncu)")
     ap.add_argument("--timeline", default=None, metavar="CSV",
                     help="warm-up, then ONE update under the CUPTI kernel tracer (torch.profiler): per-kernel in-situ start / "
@@ -383,6 +579,23 @@ def main():
         e2e_ms = t.item()
     e2e = {"value": S * world / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 24 * 4,
            "ms_per_step": e2e_ms, "pipeline": "H2D of rollout k+1 overlaps update k (torch_api.reppo_update prefetch_next)"}
+
+    # ---- the other named workloads, the reference-precision leg, strong scaling, DP numerics (all ranks take part) -----
+    extra_cfgs, fp32_leg, strong_leg, dpc = None, None, None, None
+    if not args.no_extra:
+        # (the main workload's engine stays alive for the roofline legs below)
+        extra_cfgs = {}
+        for name in sorted(CONFIGS):
+            if name == args.config:
+                continue
+            extra_cfgs[name] = measure_config(name, args.semantics, args.gemm, world, rank, dev, steps=3, warmup=2)
+        if args.gemm != "fp32":
+            fp32_leg = measure_config(args.config, args.semantics, "fp32", world, rank, dev, steps=2, warmup=1)
+            fp32_leg["note"] = ("reference-precision mode (fp32 FFMA GEMMs, src/jaxrl/__init__.py:3 'highest'); the headline value is "
+                                "bf16 operands / fp32 accumulate like the reference Torch path's 'medium' (src/torchrl/reppo.py:35)")
+        if world > 1:
+            strong_leg = measure_config(args.config, args.semantics, args.gemm, world, rank, dev, steps=3, warmup=2, strong=True)
+            dpc = dp_check(world, rank, dev, args.gemm)
 
     if rank != 0:
         if world > 1:
@@ -570,7 +783,12 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        cpu, _ = cpu_sample(hp, args.semantics, seconds=12.0)
+        arm = CpuArm(hp, args.semantics, m_steps=4 * hp.num_mini_batches)   # ~10 s of CPU work at C2
+        arm.run_warm = arm.m
+        arm.m = 2
+        arm.run()                      # warm-up (allocator, thread pool)
+        arm.m = arm.run_warm
+        cpu = arm.describe(arm.run())
 
     line = {
         "metric": "reppo_update_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -581,6 +799,7 @@ def main():
         "launches_per_update": int(launches_per_update), "cuda_graph": use_graph, "semantics": args.semantics,
         "sample_visits_per_s": value * E, "roofline": roofline, "gemm_large": gemm_large, "loss_kernels": loss_kernels, "scan": scan, "adam": adam, "rollout": rollout,
         "cpu_baseline": cpu,
+        "configs": extra_cfgs, "fp32": fp32_leg, "strong": strong_leg, "dp_check": dpc,
         "knobs": {k: os.environ[k] for k in os.environ if k.startswith("REPPO_")},
         "final_metrics": {k: final_metrics[k] for k in ("critic_loss", "actor_loss", "kl", "entropy")},
     }
