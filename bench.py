@@ -43,6 +43,22 @@ CONFIGS = {
 
 
 _RESULT_OUT = None
+_T0 = time.time()
+
+
+def stage(msg):
+    """Progress line on stderr (rank-tagged): which leg is running when a run is slow or stuck."""
+    sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')} +{time.time() - _T0:6.1f}s] {msg}\n")
+    sys.stderr.flush()
+
+
+def arm_watchdog():
+    """A stuck rank (a collective whose peer never arrives) must end the run, not hold the box: after
+    REPPO_BENCH_WATCHDOG_S seconds (default 1500) every thread's Python stack goes to stderr and the process exits."""
+    import faulthandler
+    limit = float(os.environ.get("REPPO_BENCH_WATCHDOG_S", "1500"))
+    if limit > 0:
+        faulthandler.dump_traceback_later(limit, exit=True)
 
 
 def emit(obj):
@@ -281,6 +297,7 @@ def measure_config(name, semantics, gemm, world, rank, dev, steps, warmup, stron
     if world > 1:
         from reppo_b200 import dist as dp_plumbing
         dp_plumbing.attach_nccl(eng, rank, world)
+        stage(f"  {name}: communicators up")
     hyp = HyperParams(gamma=h.gamma, lmbda=h.lmbda, lr=h.lr, max_grad_norm=h.max_grad_norm, kl_bound=h.kl_bound,
                       ent_target_mult=h.ent_target_mult, aux_loss_mult=h.aux_loss_mult, actor_min_std=h.actor_min_std,
                       actor_kl_clip_mode=h.actor_kl_clip_mode, world_size=world)
@@ -310,12 +327,14 @@ def measure_config(name, semantics, gemm, world, rank, dev, steps, warmup, stron
     for _ in range(warmup):
         one_update()
     barrier()
+    stage(f"  {name}: warm-up done")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(steps):
         one_update()
     ev1.record()
     barrier()
+    stage(f"  {name}: timed region done")
     ms = ev0.elapsed_time(ev1) / steps
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -373,6 +392,7 @@ def dp_check(world, rank, dev, gemm):
     m, sm = eng.update(eng.make_batch(flat), perms.to(dev), e1, e2, HyperParams(world_size=world), hp.num_mini_batches,
                        use_graph=True)
     torch.cuda.synchronize()
+    stage("  dp_check: update done")
     sm = D_.reduce_metrics(sm)
     same = True
     for net in (eng.critic, eng.actor):
@@ -442,6 +462,7 @@ def main():
     sys.stdout.flush()
     _RESULT_OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
+    arm_watchdog()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -505,9 +526,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    stage(f"main workload {args.config}: warm-up")
     for _ in range(args.warmup):
         one_update()
     barrier()
+    stage("main workload: timed region")
     if args.profile_only:
         one_update()
         torch.cuda.synchronize()
@@ -557,6 +580,7 @@ def main():
             "next_embeddings": batch["next_emb"], "next_values": batch["value"].unsqueeze(-1),
             "dones": batch["done"].unsqueeze(-1), "truncations": batch["truncated"].unsqueeze(-1),
             "importance_weight": batch["importance_weight"].unsqueeze(-1)}
+    stage("e2e leg")
     host = {k: v.contiguous().pin_memory() for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     # Input pipeline of the public API: the H2D copy of the NEXT rollout (prefetch_next) is issued inside every call and
@@ -588,14 +612,19 @@ def main():
         for name in sorted(CONFIGS):
             if name == args.config:
                 continue
+            stage(f"extra workload {name}")
             extra_cfgs[name] = measure_config(name, args.semantics, args.gemm, world, rank, dev, steps=3, warmup=2)
         if args.gemm != "fp32":
+            stage("fp32 leg")
             fp32_leg = measure_config(args.config, args.semantics, "fp32", world, rank, dev, steps=2, warmup=1)
             fp32_leg["note"] = ("reference-precision mode (fp32 FFMA GEMMs, src/jaxrl/__init__.py:3 'highest'); the headline value is "
                                 "bf16 operands / fp32 accumulate like the reference Torch path's 'medium' (src/torchrl/reppo.py:35)")
         if world > 1:
+            stage("strong-scaling leg")
             strong_leg = measure_config(args.config, args.semantics, args.gemm, world, rank, dev, steps=3, warmup=2, strong=True)
+            stage("dp_check")
             dpc = dp_check(world, rank, dev, args.gemm)
+        stage("extra legs done")
 
     if rank != 0:
         if world > 1:

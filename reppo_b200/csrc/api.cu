@@ -1247,8 +1247,16 @@ int reppo_nccl_init(reppo_ctx* c, const void* id_128, int32_t rank, int32_t worl
 }
 
 int reppo_nccl_finalize(reppo_ctx* c) {
-  for (int i = 0; i < 2; ++i) if (c->comm[i]) { c->nccl.CommDestroy(c->comm[i]); c->comm[i] = nullptr; }
+  // The captured graphs hold references on the communicators (NCCL counts graph-captured collectives as persistent
+  // operations and ncclCommDestroy waits for them): the executable graphs go first, the communicators after.
+  cudaDeviceSynchronize();
+  for (int i = 0; i < reppo_ctx::kGraphSlots; ++i)
+    if (c->graph_exec[i]) { cudaGraphExecDestroy(c->graph_exec[i]); c->graph_exec[i] = nullptr; }
   c->invalidate_graphs();
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 2; ++i) if (c->comm[i]) { c->nccl.CommDestroy(c->comm[i]); c->comm[i] = nullptr; }
+  c->world = 1;
+  c->rank = 0;
   return REPPO_OK;
 }
 
