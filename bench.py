@@ -251,6 +251,19 @@ def run_reference(args):
     emit(line)
 
 
+ALLREDUCE = {"mode": "none"}
+
+
+def _attach_multicast(eng, dp_plumbing):
+    """Data-parallel gradient exchange: ncclAllReduce inside the graph (default: it measured faster at 2 and 8 GPUs), or with
+    REPPO_ALLREDUCE=mc the multicast all-reduce fused into clip+Adam when the box has NVSwitch multicast memory."""
+    ALLREDUCE["mode"] = "nccl (ncclAllReduce per chain and step, inside the graph)"
+    if not os.environ.get("REPPO_ALLREDUCE", "").lower().startswith("m"):
+        return
+    if dp_plumbing.attach_multicast(eng):
+        ALLREDUCE["mode"] = "multicast (multimem.ld_reduce/st fused into the clip+Adam launch, no NCCL kernel in the step chains)"
+
+
 def workload_config(name, cfg, D, A, world):
     h = cfg.hyperparameters
     S = h.num_steps * h.num_envs
@@ -259,7 +272,7 @@ def workload_config(name, cfg, D, A, world):
                         f"{h.num_epochs} epochs (mb={S // h.num_mini_batches}/GPU), obs {D} / act {A}, H={h.critic_hidden_dim}, "
                         f"{h.num_bins} bins",
             "samples_per_gpu": S, "minibatch_per_gpu": S // h.num_mini_batches, "optimizer_steps": h.num_epochs * h.num_mini_batches,
-            "parallelism": f"dp{world} over environments" if world > 1 else "single GPU",
+            "parallelism": f"dp{world} over environments, gradient all-reduce: {ALLREDUCE['mode']}" if world > 1 else "single GPU",
             "l2": "rollout batch (292 MB at C2) exceeds the 126 MB L2; weights/Adam state are L2-resident by design"}
 
 
@@ -297,7 +310,8 @@ def measure_config(name, semantics, gemm, world, rank, dev, steps, warmup, stron
     if world > 1:
         from reppo_b200 import dist as dp_plumbing
         dp_plumbing.attach_nccl(eng, rank, world)
-        stage(f"  {name}: communicators up")
+        _attach_multicast(eng, dp_plumbing)
+        stage(f"  {name}: communicators up ({ALLREDUCE['mode']})")
     hyp = HyperParams(gamma=h.gamma, lmbda=h.lmbda, lr=h.lr, max_grad_norm=h.max_grad_norm, kl_bound=h.kl_bound,
                       ent_target_mult=h.ent_target_mult, aux_loss_mult=h.aux_loss_mult, actor_min_std=h.actor_min_std,
                       actor_kl_clip_mode=h.actor_kl_clip_mode, world_size=world)
@@ -347,6 +361,9 @@ def measure_config(name, semantics, gemm, world, rank, dev, steps, warmup, stron
            "workload": workload_config(name, cfg, D, A, world)["workload"],
            "finite": bool(all(math.isfinite(fm[k]) for k in ("critic_loss", "actor_loss", "kl")))}
     if world > 1:
+        from reppo_b200 import dist as dp_plumbing
+        out["allreduce"] = ALLREDUCE["mode"]
+        out["dp_timed_out"] = dp_plumbing.dp_timed_out(eng)
         eng.lib.reppo_nccl_finalize(eng.ctx)
     del eng, ts, devb, flat, cb, perms, eps_pi, eps_kl, target, step_metrics
     torch.cuda.empty_cache()
@@ -382,6 +399,7 @@ def dp_check(world, rank, dev, gemm):
                                    max_batch_rows=S_loc), device=dev)
     eng.load_params(cp, ap)
     D_.attach_nccl(eng, rank, world)
+    _attach_multicast(eng, D_)
     devb = {k: v.to(dev) for k, v in loc.items()}
     tgt = eng.td_lambda(devb["soft_reward"], devb["value"], devb["done"], devb["truncated"], devb["importance_weight"],
                         hp.gamma, hp.lmbda)
@@ -424,7 +442,7 @@ def dp_check(world, rank, dev, gemm):
                "step0_critic_grad_norm_rel_err": e_gn, "step0_actor_loss_rel_err": e_al, "max_param_err": perr,
                "param_bound": 2 * hp.lr * len(traces), "tolerance": tol, "steps": len(traces),
                "shape": f"global minibatch {hp.minibatch_size} rows ({mb_loc} per rank), H=512, obs 17 / act 6, {gemm} GEMMs, "
-                        "graph + two-chain pipeline + NCCL all-reduce inside the graph",
+                        f"graph + two-chain pipeline + gradient all-reduce inside the graph: {ALLREDUCE['mode']}",
                "oracle": "oracle/reppo_oracle.py learn_step on the rank-concatenated minibatches (CPU, rank 0)"}
     eng.lib.reppo_nccl_finalize(eng.ctx)
     del eng
@@ -500,6 +518,7 @@ def main():
     if world > 1:
         from reppo_b200 import dist as dp_plumbing
         dp_plumbing.attach_nccl(eng, rank, world)   # two communicators: critic chain + actor chain
+        _attach_multicast(eng, dp_plumbing)         # ... superseded by the multicast all-reduce inside clip+Adam when the box has it
     hyp = HyperParams(gamma=h.gamma, lmbda=h.lmbda, lr=h.lr, max_grad_norm=h.max_grad_norm, kl_bound=h.kl_bound,
                       ent_target_mult=h.ent_target_mult, aux_loss_mult=h.aux_loss_mult, actor_min_std=h.actor_min_std,
                       actor_kl_clip_mode=h.actor_kl_clip_mode, world_size=world)
@@ -568,6 +587,10 @@ def main():
     ms = ev0.elapsed_time(ev1) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     final_metrics = eng.metrics_dict(eng.metrics)
+    mc_phases = None
+    if world > 1 and os.environ.get("REPPO_MC_STAMPS") and ALLREDUCE["mode"].startswith("multicast"):
+        from reppo_b200 import dist as dp_plumbing
+        mc_phases = dp_plumbing.mc_phase_summary(eng)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -830,6 +853,8 @@ def main():
         "cpu_baseline": cpu,
         "configs": extra_cfgs, "fp32": fp32_leg, "strong": strong_leg, "dp_check": dpc,
         "knobs": {k: os.environ[k] for k in os.environ if k.startswith("REPPO_")},
+        "allreduce": ALLREDUCE["mode"] if world > 1 else None,
+        "mc_phases": mc_phases,
         "final_metrics": {k: final_metrics[k] for k in ("critic_loss", "actor_loss", "kl", "entropy")},
     }
     emit(line)

@@ -270,6 +270,30 @@ int reppo_nccl_unique_id(reppo_ctx* ctx, void* id_out_128);
 int reppo_nccl_init(reppo_ctx* ctx, const void* id_128, int32_t rank, int32_t world_size);
 int reppo_nccl_finalize(reppo_ctx* ctx);
 
+/* The same all-reduce without NCCL: fused into the clip + Adam launch over NVSwitch MULTICAST memory.
+ * The host places both gradient arenas and a flag block in ONE symmetric allocation (CUDA VMM + multicast object; from
+ * Python: torch.distributed._symmetric_memory) and hands over its three mappings.  Every step's clip+Adam kernel then
+ * (1) meets its twin blocks on the other ranks, (2) replaces its slice of the arena by the switch-side sum
+ * (multimem.ld_reduce -> multimem.st), (3) meets the twins again and goes on to the global norm, clip and Adam:
+ * no separate collective launch, no NCCL kernel in the chain.  world_size must divide 16.  state.{critic,actor}.grads of
+ * every later data-parallel call must be local_base + {critic,actor}_grads_off.  flags: >= (3*256*16 + 16)*4 bytes, zeroed, and
+ * all ranks past a host barrier before the first update.  When NCCL communicators are attached as well, NCCL serves unless
+ * REPPO_ALLREDUCE=mc is set (measured: DESIGN.md section 6). */
+typedef struct reppo_multicast {
+  void* local_base;        /* this rank's copy */
+  void* mc_base;           /* multicast mapping (all ranks' copies at once) */
+  void* peer_base[16];     /* rank r's copy as mapped here; peer_base[rank] == local_base */
+  int64_t critic_grads_off, actor_grads_off, flags_off;   /* bytes, 16-byte aligned */
+  int64_t flags_bytes;
+  int32_t rank, world_size;
+} reppo_multicast;
+int reppo_dp_attach_multicast(reppo_ctx* ctx, const reppo_multicast* m);
+/* *timed_out = 1 when a cross-GPU wait of the fused all-reduce gave up (a rank was lost); results are then invalid */
+int reppo_dp_status(reppo_ctx* ctx, int32_t* timed_out);
+/* profiling aid: with REPPO_MC_STAMPS=1 in the environment at attach time every clip+Adam block records globaltimer stamps
+ * of its all-reduce phases; this copies the ring (8 + 8192 x 8 uint64 words) out.  tools/mc_stamps.py reads it. */
+int reppo_dp_stamps(reppo_ctx* ctx, uint64_t* out, int64_t words);
+
 #ifdef __cplusplus
 }
 #endif

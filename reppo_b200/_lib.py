@@ -66,6 +66,14 @@ class Plan(C.Structure):
                 ("noise_per_minibatch", C.c_int32), ("old_policy_out", C.c_void_p)]
 
 
+class Multicast(C.Structure):
+    _fields_ = [("local_base", C.c_void_p), ("mc_base", C.c_void_p), ("peer_base", C.c_void_p * 16),
+                ("critic_grads_off", C.c_int64), ("actor_grads_off", C.c_int64), ("flags_off", C.c_int64),
+                ("flags_bytes", C.c_int64), ("rank", C.c_int32), ("world_size", C.c_int32)]
+
+
+MC_FLAG_BYTES = (3 * 256 * 16 + 16) * 4   # kMcChains * kMcFlagBlocks * kMcMaxRanks flag words + epoch words (csrc/kernels.h)
+
 # every symbol include/reppo_b200.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _f, _d = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 SYMBOLS = {
@@ -97,6 +105,9 @@ SYMBOLS = {
     "reppo_nccl_unique_id": (C.c_int, [_vp, _vp]),
     "reppo_nccl_init": (C.c_int, [_vp, _vp, _i32, _i32]),
     "reppo_nccl_finalize": (C.c_int, [_vp]),
+    "reppo_dp_attach_multicast": (C.c_int, [_vp, C.POINTER(Multicast)]),
+    "reppo_dp_status": (C.c_int, [_vp, i32p]),
+    "reppo_dp_stamps": (C.c_int, [_vp, _vp, _i64]),
 }
 
 _lib = None

@@ -149,6 +149,19 @@ struct reppo_ctx {
   NcclApi nccl;
   ncclComm_t comm[2] = {nullptr, nullptr};   // [0] critic chain, [1] actor chain (optional: enables step pipelining under DP)
   int world = 1, rank = 0;
+  // NVSwitch-multicast all-reduce fused into clip+Adam (reppo_dp_attach_multicast; kernels.h McArgs)
+  struct McState {
+    bool on = false;
+    char* local = nullptr;
+    char* mcast = nullptr;
+    char* peer[kMcMaxRanks] = {};
+    int64_t grads_off[2] = {0, 0};   // critic, actor gradient arenas (bytes into the symmetric buffer)
+    int64_t flags_off = 0;
+    int world = 1, rank = 0;
+    int* status = nullptr;           // device word: a cross-GPU wait timed out
+    unsigned long long* stamps = nullptr;   // REPPO_MC_STAMPS=1: phase stamps of the fused all-reduce (reppo_dp_stamps)
+  } mc;
+  bool mc_pending = false;           // allreduce_grads deferred the exchange to the next clip_adam launch
 
   Twin twin(const float* p) const {
     auto it = twins.find(p);
@@ -423,12 +436,16 @@ int dep(reppo_ctx* c, cudaStream_t from, cudaStream_t to) {
 bool small_step(const reppo_ctx* c) {
   return static_cast<long long>(c->shape.max_rows) * std::max(c->shape.critic_hidden, c->shape.actor_hidden) <= (4LL << 20);
 }
+bool dp_on(const reppo_ctx* c) { return c->comm[0] != nullptr || c->mc.on; }
+// Both attached: NCCL serves (it measured faster: 118.0 vs 126.4 ms per C2 update on 2 GPUs, 124.6 vs 128.6 ms on 8) unless
+// REPPO_ALLREDUCE=mc asks for the multicast kernel; multicast alone attached: multicast.
+bool use_mc(const reppo_ctx* c) { return c->mc.on && (knobs().nccl_own == 1 || c->comm[0] == nullptr); }
 // latency-bound steps only: at the wide-net shapes every kernel fills the machine and the priorities cost 4 %
 // (C5: 229.7 vs 221.2 ms); with NCCL collectives inside the chains they lose as well (2 GPUs: 115.6 ms off, 120.5 on)
 bool want_prio(const reppo_ctx* c) {
   const int k = knobs().prio;
   if (k >= 0) return k != 0;
-  return small_step(c) && c->comm[0] == nullptr;
+  return small_step(c) && !dp_on(c);
 }
 
 int ensure_streams(reppo_ctx* c) {
@@ -523,6 +540,14 @@ int critic_trunk(reppo_ctx* c, const float* cp, int cslot, const float* x0, int 
 
 // gradient all-reduce of one chain (0 = critic, 1 = actor); no-op on a single GPU
 int allreduce_grads(reppo_ctx* c, float* g, int64_t n, int chain, cudaStream_t st) {
+  if (use_mc(c)) {
+    // the exchange happens inside the clip+Adam launch that follows (multimem.ld_reduce / multimem.st, optim.cu)
+    const char* gb = reinterpret_cast<const char*>(g);
+    if (gb != c->mc.local + c->mc.grads_off[0] && gb != c->mc.local + c->mc.grads_off[1])
+      return fail(c, REPPO_ERR_INVALID, "data-parallel step: the gradient arena is not the one registered with reppo_dp_attach_multicast");
+    c->mc_pending = true;
+    return REPPO_OK;
+  }
   if (c->comm[0] == nullptr) return REPPO_OK;
   ncclComm_t comm = (chain == 1 && c->comm[1] != nullptr) ? c->comm[1] : c->comm[0];
   const int r = c->nccl.AllReduce(g, g, static_cast<size_t>(n), /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, st);
@@ -689,8 +714,21 @@ int clip_adam_impl(reppo_ctx* c, const reppo_net_state* net, int64_t n, const re
   a.max_grad_norm = hp->max_grad_norm;
   a.torch_clip = c->sem.torch_opt;
   a.anneal_steps = hp->lr_anneal_steps > 0 ? hp->lr_anneal_steps : 0;
+  McArgs mc{};
+  if (c->mc_pending) {
+    c->mc_pending = false;
+    const int64_t off = reinterpret_cast<const char*>(net->grads) - c->mc.local;
+    mc.g_mc = reinterpret_cast<float*>(c->mc.mcast + off);
+    for (int r = 0; r < c->mc.world; ++r)
+      mc.flags[r] = reinterpret_cast<unsigned int*>(c->mc.peer[r] + c->mc.flags_off) + static_cast<size_t>(chain) * kMcFlagBlocks * kMcMaxRanks;
+    // epoch words sit behind the flag rows of the three chains
+    mc.epoch = reinterpret_cast<unsigned int*>(c->mc.local + c->mc.flags_off) + static_cast<size_t>(kMcChains) * kMcFlagBlocks * kMcMaxRanks + chain;
+    mc.status = c->mc.status;
+    mc.stamps = c->mc.stamps;
+    mc.world = c->mc.world; mc.rank = c->mc.rank; mc.chain = chain;
+  }
   CK(launch_clip_adam(p_in ? p_in : net->params, p_out ? p_out : net->params, net->grads, net->adam_m, net->adam_v, n, net->step,
-                      partials ? partials : c->partials, c->adam_bar + 2 * chain, a, &sh, gn_out, zero_grads ? 1 : 0, st));
+                      partials ? partials : c->partials, c->adam_bar + 2 * chain, a, &sh, gn_out, zero_grads ? 1 : 0, st, &mc));
   return REPPO_OK;
 }
 
@@ -736,7 +774,7 @@ int run_steps(reppo_ctx* c, const reppo_state* s, const reppo_batch* b, const re
     }
   }
   // one NCCL communicator serves one chain: pipelining under data parallelism needs the second communicator
-  const bool pipe = c->concurrent && c->pipeline && (c->comm[0] == nullptr || c->comm[1] != nullptr);
+  const bool pipe = c->concurrent && c->pipeline && (!dp_on(c) || c->comm[1] != nullptr || use_mc(c));
   cudaStream_t sa = pipe ? c->side[2] : st;   // the actor chain
   // snapshot j of the critic parameters lives in copy j % depth
   const int depth = pipe ? 2 : 1;
@@ -900,6 +938,8 @@ void reppo_ctx_destroy(reppo_ctx* c) {
   for (int i = 0; i < 4; ++i) { if (c->side[i]) cudaStreamDestroy(c->side[i]); if (c->ev_c[i]) cudaEventDestroy(c->ev_c[i]); if (c->ev_a[i]) cudaEventDestroy(c->ev_a[i]); }
   for (int i = 0; i < 2; ++i) if (c->ev_epoch[i]) cudaEventDestroy(c->ev_epoch[i]);
   for (int i = 0; i < 2; ++i) if (c->comm[i] && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm[i]);
+  if (c->mc.status) cudaFree(c->mc.status);
+  if (c->mc.stamps) cudaFree(c->mc.stamps);
   delete c;
 }
 
@@ -1246,6 +1286,54 @@ int reppo_nccl_init(reppo_ctx* c, const void* id_128, int32_t rank, int32_t worl
   return REPPO_OK;
 }
 
+int reppo_dp_attach_multicast(reppo_ctx* c, const reppo_multicast* m) {
+  if (m == nullptr || m->local_base == nullptr || m->mc_base == nullptr || m->world_size < 2 || m->world_size > kMcMaxRanks ||
+      m->rank < 0 || m->rank >= m->world_size)
+    return fail(c, REPPO_ERR_INVALID, "reppo_dp_attach_multicast: bad argument");
+  if (16 % m->world_size != 0)
+    return fail(c, REPPO_ERR_INVALID, "reppo_dp_attach_multicast: world_size must divide 16 (warps of a clip+Adam block are dealt to ranks)");
+  const int64_t need = (static_cast<int64_t>(kMcChains) * kMcFlagBlocks * kMcMaxRanks + 16) * sizeof(unsigned int);
+  if (m->flags_bytes < need || (m->critic_grads_off & 15) || (m->actor_grads_off & 15) || (m->flags_off & 15))
+    return fail(c, REPPO_ERR_INVALID, "reppo_dp_attach_multicast: flag block too small or offsets not 16-byte aligned");
+  for (int r = 0; r < m->world_size; ++r)
+    if (m->peer_base[r] == nullptr) return fail(c, REPPO_ERR_INVALID, "reppo_dp_attach_multicast: missing peer mapping");
+  if (m->peer_base[m->rank] != m->local_base) return fail(c, REPPO_ERR_INVALID, "reppo_dp_attach_multicast: peer_base[rank] != local_base");
+  reppo_ctx::McState& s = c->mc;
+  if (s.status == nullptr) {
+    if (cudaMalloc(&s.status, sizeof(int)) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaMalloc failed");
+  }
+  cudaMemset(s.status, 0, sizeof(int));
+  if (s.stamps == nullptr && getenv("REPPO_MC_STAMPS") != nullptr) {
+    if (cudaMalloc(&s.stamps, kMcStampWords * sizeof(unsigned long long)) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaMalloc failed");
+    cudaMemset(s.stamps, 0, kMcStampWords * sizeof(unsigned long long));
+  }
+  s.local = static_cast<char*>(m->local_base); s.mcast = static_cast<char*>(m->mc_base);
+  for (int r = 0; r < m->world_size; ++r) s.peer[r] = static_cast<char*>(m->peer_base[r]);
+  s.grads_off[0] = m->critic_grads_off; s.grads_off[1] = m->actor_grads_off; s.flags_off = m->flags_off;
+  s.world = m->world_size; s.rank = m->rank; s.on = true;
+  c->world = m->world_size; c->rank = m->rank;
+  c->invalidate_graphs();
+  return REPPO_OK;
+}
+
+// debugging aid (REPPO_MC_STAMPS=1 at attach time): copies the stamp ring [count, 7 pad, 8192 x 8 words] to the host
+int reppo_dp_stamps(reppo_ctx* c, uint64_t* out, int64_t words) {
+  if (c->mc.stamps == nullptr) return fail(c, REPPO_ERR_INVALID, "reppo_dp_stamps: set REPPO_MC_STAMPS=1 before reppo_dp_attach_multicast");
+  const int64_t n = std::min<int64_t>(words, kMcStampWords);
+  if (cudaMemcpy(out, c->mc.stamps, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaMemcpy failed");
+  return REPPO_OK;
+}
+
+int reppo_dp_status(reppo_ctx* c, int32_t* timed_out) {
+  if (timed_out == nullptr) return fail(c, REPPO_ERR_INVALID, "reppo_dp_status: null argument");
+  *timed_out = 0;
+  if (c->mc.status == nullptr) return REPPO_OK;
+  int v = 0;
+  if (cudaMemcpy(&v, c->mc.status, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "cudaMemcpy failed");
+  *timed_out = v;
+  return REPPO_OK;
+}
+
 int reppo_nccl_finalize(reppo_ctx* c) {
   // The captured graphs hold references on the communicators (NCCL counts graph-captured collectives as persistent
   // operations and ncclCommDestroy waits for them): the executable graphs go first, the communicators after.
@@ -1255,6 +1343,7 @@ int reppo_nccl_finalize(reppo_ctx* c) {
   c->invalidate_graphs();
   cudaDeviceSynchronize();
   for (int i = 0; i < 2; ++i) if (c->comm[i]) { c->nccl.CommDestroy(c->comm[i]); c->comm[i] = nullptr; }
+  c->mc.on = false;
   c->world = 1;
   c->rank = 0;
   return REPPO_OK;

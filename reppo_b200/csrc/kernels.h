@@ -114,11 +114,27 @@ cudaError_t launch_obs_normalize(const float* x, long long rows, int D, float* m
 // bf16 shadows of the weight matrices, refreshed by the Adam kernel itself (REPPO_GEMM_BF16)
 struct ShadowEntry { long long start, end; int in, ld; void* dst; };
 struct ShadowTable { int n; ShadowEntry e[kMaxPack]; };
+// Data-parallel gradient all-reduce over NVSwitch multicast memory, fused into the clip+Adam launch (optim.cu).  The gradient
+// arena lives in a symmetric allocation that every rank maps three ways: its own copy (what the gradient kernels write),
+// every peer's copy (flags only) and the MULTICAST mapping, on which `multimem.ld_reduce` returns the switch-side sum over
+// all ranks and `multimem.st` writes every rank's copy at once.  world <= 1: no exchange.
+constexpr int kMcMaxRanks = 16;
+constexpr int kMcFlagBlocks = 256;    // flag rows per chain (>= grid of clip_adam_kernel)
+constexpr int kMcChains = 3;
+constexpr int kMcStampWords = 8 + 8192 * 8;
+struct McArgs {
+  float* g_mc;                          // multicast address of this launch's gradient arena
+  unsigned int* flags[kMcMaxRanks];     // every rank's flag block of this chain: [kMcFlagBlocks][world] words
+  unsigned int* epoch;                  // this rank's epoch word of this chain (+2 per launch; flags carry epoch + 1 / + 2)
+  int* status;                          // device word set to 1 when a cross-GPU wait timed out (reppo_dp_status)
+  unsigned long long* stamps;           // REPPO_MC_STAMPS=1: [0] = launches recorded, then 8 words per block (tools/mc_stamps.py)
+  int world, rank, chain;
+};
 // bar: two device uint32 {arrival count, generation} of the kernel's grid barrier (zero-initialised once; one pair per
 // concurrently running chain)
 cudaError_t launch_clip_adam(const float* p_in, float* p, float* g, float* m, float* v, long long n, int* step, float* partials,
                              unsigned int* bar, const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out,
-                             int zero_grads, cudaStream_t st);
+                             int zero_grads, cudaStream_t st, const McArgs* mc = nullptr);
 cudaError_t launch_metrics_mean(const float* step_metrics, int first, int count, int nm, float* out, cudaStream_t st);
 cudaError_t launch_metrics_init(float* m, uint32_t mask, cudaStream_t st);
 cudaError_t launch_metrics_init_all(float* m, int steps, cudaStream_t st);

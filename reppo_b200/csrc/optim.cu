@@ -27,10 +27,64 @@ namespace reppo {
 constexpr int kAdamThreads = 512;
 constexpr int kAdamKeep = 4;   // float4 gradient chunks a thread keeps in registers across the barrier
 
+// ---- data-parallel phase: all-reduce of the gradient arena through NVSwitch multicast memory -------------------------------
+// Every rank launches this kernel with the same grid.  Block b of rank R exchanges only with block b of the other ranks
+// ("twins"): the float4 chunks of block b's own slice (the ones it will clip and apply below) are split over the ranks by
+// warp -- warp w of every twin reduces the chunks of warp w iff w % world == R -- so after the second twin barrier block b
+// holds the summed gradient of exactly its slice and needs no device-wide wait beyond the norm barrier it has anyway.
+//   barrier A (twins)  : every rank's gradient kernels of this step have finished (stream order on each rank)
+//   multimem.ld_reduce : the switch returns the fp32 sum over all ranks' copies of 16 bytes; multimem.st writes it to all
+//   barrier B (twins)  : the twins' sums have landed in this rank's copy
+// One flag word per (block, source rank) in every rank's flag block.  Every launch of a chain advances that chain's EPOCH
+// word (local memory, written by the last block to reach the norm barrier, i.e. after every block has read it) by two;
+// barrier A publishes epoch + 1, barrier B epoch + 2.  All ranks replay the same launches, so their epochs agree, flags only
+// grow, and the kernel is replayable inside a CUDA graph.  A wait that exceeds two seconds raises *status and proceeds
+// (no device hang on a lost rank).
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// One twin barrier.  `seq` is the value this barrier instance publishes: flag words only ever grow (epoch counter below), so a
+// signal is ONE one-way store into the peer's memory and a wait is a poll of local memory -- no atomic round trips over
+// NVLink.  publish: the block's multimem stores must be performed before the flag (release by the signalling threads after
+// the block barrier; cumulativity carries the other warps' stores).  Returns the time every warp had arrived (stamps only).
+__device__ __forceinline__ unsigned long long mc_twin_barrier(const McArgs& mc, unsigned int seq, bool publish) {
+  __syncthreads();
+  const unsigned long long arrived = (mc.stamps != nullptr && threadIdx.x == 0) ? global_ns() : 0ull;
+  if (threadIdx.x < mc.world) {
+    const int peer = threadIdx.x;
+    unsigned int* put = mc.flags[peer] + (blockIdx.x * mc.world + mc.rank);
+    const unsigned int* get = mc.flags[mc.rank] + (blockIdx.x * mc.world + peer);
+    if (publish) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(put), "r"(seq) : "memory");
+    else asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(put), "r"(seq) : "memory");
+    if (*reinterpret_cast<volatile int*>(mc.status) == 0) {   // after a first time-out the rest of the graph drains without waiting
+      const unsigned long long t0 = global_ns();
+      unsigned int seen;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(get) : "memory");
+        if (static_cast<int>(seen - seq) >= 0) break;
+        if (global_ns() - t0 > 2000000000ull) { atomicExch(mc.status, 1); break; }
+      }
+    }
+  }
+  __syncthreads();
+  return arrived;
+}
+__device__ __forceinline__ float4 multimem_sum(const float4* p) {
+  float4 q;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "l"(p) : "memory");
+  return q;
+}
+__device__ __forceinline__ void multimem_store(float4* p, const float4& q) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(q.x), "f"(q.y), "f"(q.z), "f"(q.w) : "memory");
+}
+
 __global__ void __launch_bounds__(kAdamThreads, 2)
 clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
                  float* __restrict__ partials, unsigned int* __restrict__ bar, int* __restrict__ step, AdamConsts c,
-                 const ShadowTable sh, float* __restrict__ grad_norm_out, int zero_grads) {
+                 const ShadowTable sh, float* __restrict__ grad_norm_out, int zero_grads, const McArgs mc) {
   REPPO_PDL_PROLOGUE();
   __shared__ float red[32];
   __shared__ float s_scale, s_bc1, s_bc2, s_lr;
@@ -42,21 +96,53 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
   float4* g4 = reinterpret_cast<float4*>(g);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long first = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  unsigned long long ts[6] = {0, 0, 0, 0, 0, 0};
+  if (mc.world > 1) {
+    // ---- phase 0 (data parallel): this block's slice of the gradient becomes the sum over all ranks
+    const bool stamp = mc.stamps != nullptr && threadIdx.x == 0;
+    if (stamp) ts[0] = global_ns();
+    unsigned int epoch;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(epoch) : "l"(mc.epoch) : "memory");
+    ts[1] = mc_twin_barrier(mc, epoch + 1u, false);
+    if (stamp) ts[2] = global_ns();
+    float4* gm = reinterpret_cast<float4*>(mc.g_mc);
+    if (static_cast<int>(threadIdx.x >> 5) % mc.world == mc.rank) {
+      // four switch-side sums in flight per thread before the first store (a load + store pair per iteration would cost
+      // one NVLink round trip each: measured 11.5 us for the critic arena on 2 GPUs)
+      long long i = first;
+      for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 q0 = multimem_sum(gm + i), q1 = multimem_sum(gm + i + stride), q2 = multimem_sum(gm + i + 2 * stride),
+                     q3 = multimem_sum(gm + i + 3 * stride);
+        multimem_store(gm + i, q0); multimem_store(gm + i + stride, q1);
+        multimem_store(gm + i + 2 * stride, q2); multimem_store(gm + i + 3 * stride, q3);
+      }
+      if (i + stride < n4) {
+        const float4 q0 = multimem_sum(gm + i), q1 = multimem_sum(gm + i + stride);
+        multimem_store(gm + i, q0); multimem_store(gm + i + stride, q1);
+        i += 2 * stride;
+      }
+      for (; i < n4; i += stride) multimem_store(gm + i, multimem_sum(gm + i));
+    }
+    // the ragged tail (the arena is padded to a multiple of four floats) belongs to block 0, the only one that reads it
+    if (blockIdx.x == 0 && threadIdx.x == 0 && mc.rank == 0 && (n & 3)) multimem_store(gm + n4, multimem_sum(gm + n4));
+    ts[3] = mc_twin_barrier(mc, epoch + 2u, true);
+    if (stamp) ts[4] = global_ns();
+  }
   // ---- phase 1: this block's partial sum of squares
   float4 gk[kAdamKeep];
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < kAdamKeep; ++k) {
     const long long i = first + k * stride;
-    gk[k] = (i < n4) ? g4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    gk[k] = (i < n4) ? __ldcg(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 #pragma unroll
   for (int k = 0; k < kAdamKeep; ++k) s += gk[k].x * gk[k].x + gk[k].y * gk[k].y + gk[k].z * gk[k].z + gk[k].w * gk[k].w;
   for (long long i = first + kAdamKeep * stride; i < n4; i += stride) {   // wide networks only
-    const float4 q = g4[i];
+    const float4 q = __ldcg(g4 + i);
     s += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
   }
-  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float q = g[(n4 << 2) + threadIdx.x]; s += q * q; }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float q = __ldcg(g + (n4 << 2) + threadIdx.x); s += q * q; }
   s = block_sum(s, red);
   const int t = *step + 1;   // every block reads the counter before the barrier; block 0 writes it after
   unsigned int my_gen = 0;
@@ -72,6 +158,7 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
   if (first < n4) { pp = pi4[first]; mm = m4[first]; vv = v4[first]; }
   if (threadIdx.x == 0) {
     if (last) {
+      if (mc.world > 1) *mc.epoch += 2u;   // every block read the epoch before it arrived here
       bar[0] = 0u;   // nobody touches the counter again before the generation moves
       __threadfence();
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(my_gen + 1u) : "memory");
@@ -161,7 +248,7 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
       // static indexing keeps gk in registers
       gg = (k == 0) ? gk[0] : (k == 1) ? gk[1] : (k == 2) ? gk[2] : gk[3];
     } else {
-      gg = g4[i];
+      gg = __ldcg(g4 + i);
     }
     if (k > 0) { pp = pi4[i]; mm = m4[i]; vv = v4[i]; }
     if (zero_grads) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // the next step accumulates into a clean arena (no memset node)
@@ -173,16 +260,24 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long long i = (n4 << 2) + threadIdx.x;
     float q = p_in[i];
-    upd(q, g[i], m[i], v[i]);
+    upd(q, __ldcg(g + i), m[i], v[i]);
     shadow1(q, i);
     p[i] = q;
     if (zero_grads) g[i] = 0.f;
+  }
+  if (mc.world > 1 && mc.stamps != nullptr && threadIdx.x == 0) {
+    // entry, block arrived at A, A done, reduce done + fenced (arrived at B), B done, exit
+    ts[5] = global_ns();
+    const unsigned long long slot = atomicAdd(mc.stamps, 1ull) & 8191ull;
+    unsigned long long* o = mc.stamps + 8 + slot * 8;
+    o[0] = (static_cast<unsigned long long>(mc.chain) << 32) | blockIdx.x;
+    for (int k = 0; k < 6; ++k) o[1 + k] = ts[k];
   }
 }
 
 cudaError_t launch_clip_adam(const float* p_in, float* p, float* g, float* m, float* v, long long n, int* step, float* partials,
                              unsigned int* bar, const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out,
-                             int zero_grads, cudaStream_t st) {
+                             int zero_grads, cudaStream_t st, const McArgs* mc) {
   if (n <= 0) return cudaSuccess;
   static int sm_count = 0;
   if (sm_count == 0) {
@@ -198,8 +293,14 @@ cudaError_t launch_clip_adam(const float* p_in, float* p, float* g, float* m, fl
   if (blocks < 1) blocks = 1;
   ShadowTable sh{};
   if (shadow != nullptr) sh = *shadow;
+  McArgs ma{};
+  if (mc != nullptr && mc->world > 1) {
+    // warps of a block are dealt to ranks round-robin (16 warps), flag rows are per block
+    if ((kAdamThreads / 32) % mc->world != 0 || mc->world > kMcMaxRanks || blocks > kMcFlagBlocks) return cudaErrorInvalidValue;
+    ma = *mc;
+  }
   launch_k((clip_adam_kernel), dim3(blocks), dim3(kAdamThreads), 0, st, p_in, p, g, m, v, n, partials, bar, step, c, sh,
-           grad_norm_out, zero_grads);
+           grad_norm_out, zero_grads, ma);
   return cudaGetLastError();
 }
 

@@ -264,6 +264,11 @@ def bind_engine(actor: Actor, critic: Critic, old_actor: Optional[Actor] = None,
         old_actor._engine = eng
     else:
         eng.sync_actor_old()
+
+    def _regrad():   # dist.attach_multicast moved the gradient arenas into symmetric memory: re-point the .grad views
+        critic._rebind(eng.critic.params, eng.critic.grads)
+        actor._rebind(eng.actor.params, eng.actor.grads)
+    eng.__dict__.setdefault("_grads_moved", []).append(_regrad)
     return eng
 
 

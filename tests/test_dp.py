@@ -90,8 +90,10 @@ def test_dp_arithmetic_gloo_world2():
 
 
 # ---- GPU, 2 ranks over NCCL -------------------------------------------------------------------------
-def _nccl_worker(rank, world, port, out, gemm_mode):
+def _nccl_worker(rank, world, port, out, gemm_mode, allreduce="nccl"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if allreduce == "mc":
+        os.environ["REPPO_ALLREDUCE"] = "mc"   # both exchanges get attached below; the knob (read once by the library) picks
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
     try:
@@ -112,6 +114,9 @@ def _nccl_worker(rank, world, port, out, gemm_mode):
         eng = ReppoEngine(ecfg)
         eng.load_params(cp, ap)
         D.attach_nccl(eng, rank, world)
+        if allreduce == "mc":
+            # the all-reduce fused into clip+Adam over NVSwitch multicast memory (csrc/optim.cu) instead of ncclAllReduce
+            assert D.attach_multicast(eng), "no multicast-capable symmetric memory on this box"
         dev = {k: v.cuda() for k, v in loc.items()}
         tgt = eng.td_lambda(dev["soft_reward"], dev["value"], dev["done"], dev["truncated"], dev["importance_weight"],
                             hp.gamma, hp.lmbda)
@@ -122,6 +127,7 @@ def _nccl_worker(rank, world, port, out, gemm_mode):
         hyp = HyperParams(world_size=world)
         m, sm = eng.update(eng.make_batch(flat), perms.cuda(), e1, e2, hyp, hp.num_mini_batches, use_graph=True)
         torch.cuda.synchronize()
+        assert not D.dp_timed_out(eng)
         sm = D.reduce_metrics(sm)
         # single-process reference: the oracle on the equivalent global minibatches
         rows = []
@@ -151,14 +157,15 @@ def _nccl_worker(rank, world, port, out, gemm_mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("allreduce", ["nccl", "mc"])
 @pytest.mark.parametrize("gemm_mode", ["fp32", "bf16"])
-def test_dp_two_ranks_match_single_process_oracle(gemm_mode):
+def test_dp_two_ranks_match_single_process_oracle(gemm_mode, allreduce):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q, gemm_mode)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q, gemm_mode, allreduce)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
