@@ -286,8 +286,8 @@ def measure_config(name, semantics, gemm, world, rank, dev, steps, warmup, stron
     from reppo_b200 import torch_api as T
     from reppo_b200.engine import HyperParams
     cfg, D, A, term, rs = make_cfg(name, semantics, list(overrides))
-    if gemm == "bf16":
-        cfg.platform.amp_dtype = "bf16"
+    if gemm in ("bf16", "tf32"):
+        cfg.platform.amp_dtype = gemm
     h = cfg.hyperparameters
     hp_g = oracle_hyper(cfg, D, A)                      # the named (global) batch
     if strong:
@@ -356,7 +356,7 @@ def measure_config(name, semantics, gemm, world, rank, dev, steps, warmup, stron
         ms = t.item()
     fm = eng.metrics_dict(eng.metrics)
     out = {"value": S * world / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
-           "dtype": "f32" if gemm == "fp32" else "bf16", "scaling": "strong" if strong else "weak",
+           "dtype": {"fp32": "f32", "bf16": "bf16", "tf32": "tf32"}[gemm], "scaling": "strong" if strong else "weak",
            "in_update_tflops": gemm_flops_per_update(hp) * world / (ms * 1e-3) / 1e12,
            "workload": workload_config(name, cfg, D, A, world)["workload"],
            "finite": bool(all(math.isfinite(fm[k]) for k in ("critic_loss", "actor_loss", "kl")))}
@@ -459,7 +459,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--semantics", default="jax", choices=["jax", "torch"])
-    ap.add_argument("--gemm", default=os.environ.get("REPPO_GEMM", "bf16"), choices=["fp32", "bf16"],
+    ap.add_argument("--gemm", default=os.environ.get("REPPO_GEMM", "bf16"), choices=["fp32", "bf16", "tf32"],
                     help="bf16 = tcgen05 tensor-core path (bf16 operands, fp32 accumulate; the product); fp32 = FFMA reference-precision mode")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--override", action="append", default=[], metavar="KEY=VALUE",
@@ -501,8 +501,8 @@ def main():
     peaks = load_peaks()
 
     cfg, D, A, term, rs = make_cfg(args.config, args.semantics, args.override)
-    if args.gemm == "bf16":
-        cfg.platform.amp_dtype = "bf16"
+    if args.gemm in ("bf16", "tf32"):
+        cfg.platform.amp_dtype = args.gemm
     h = cfg.hyperparameters
     hp = oracle_hyper(cfg, D, A)
     S, n_mb, E = hp.batch_size, hp.num_mini_batches, hp.num_epochs
@@ -628,7 +628,7 @@ def main():
            "ms_per_step": e2e_ms, "pipeline": "H2D of rollout k+1 overlaps update k (torch_api.reppo_update prefetch_next)"}
 
     # ---- the other named workloads, the reference-precision leg, strong scaling, DP numerics (all ranks take part) -----
-    extra_cfgs, fp32_leg, strong_leg, dpc = None, None, None, None
+    extra_cfgs, fp32_leg, tf32_leg, strong_leg, dpc = None, None, None, None, None
     if not args.no_extra:
         # (the main workload's engine stays alive for the roofline legs below)
         extra_cfgs = {}
@@ -642,6 +642,14 @@ def main():
             fp32_leg = measure_config(args.config, args.semantics, "fp32", world, rank, dev, steps=2, warmup=1)
             fp32_leg["note"] = ("reference-precision mode (fp32 FFMA GEMMs, src/jaxrl/__init__.py:3 'highest'); the headline value is "
                                 "bf16 operands / fp32 accumulate like the reference Torch path's 'medium' (src/torchrl/reppo.py:35)")
+        if args.gemm != "tf32":
+            stage("tf32 leg")
+            tf32_leg = measure_config(args.config, args.semantics, "tf32", world, rank, dev, steps=2, warmup=1)
+            tf32_leg["dtype"] = "tf32"
+            tf32_leg["note"] = ("reference-precision mode on tensor cores: tcgen05.mma.kind::tf32 on the fp32 activations and an aligned "
+                                "fp32 copy of the weights (10-bit mantissa products, fp32 accumulation; what "
+                                "torch.set_float32_matmul_precision('high') asks for); GEMMs with ragged leading dimensions "
+                                "(K = obs + act first layer, the 151-bin and H+1 head outputs' dgrad / wgrad) run the FFMA kernel")
         if world > 1:
             stage("strong-scaling leg")
             strong_leg = measure_config(args.config, args.semantics, args.gemm, world, rank, dev, steps=3, warmup=2, strong=True)
@@ -851,7 +859,7 @@ def main():
         "launches_per_update": int(launches_per_update), "cuda_graph": use_graph, "semantics": args.semantics,
         "sample_visits_per_s": value * E, "roofline": roofline, "gemm_large": gemm_large, "loss_kernels": loss_kernels, "scan": scan, "adam": adam, "rollout": rollout,
         "cpu_baseline": cpu,
-        "configs": extra_cfgs, "fp32": fp32_leg, "strong": strong_leg, "dp_check": dpc,
+        "configs": extra_cfgs, "fp32": fp32_leg, "tf32": tf32_leg, "strong": strong_leg, "dp_check": dpc,
         "knobs": {k: os.environ[k] for k in os.environ if k.startswith("REPPO_")},
         "allreduce": ALLREDUCE["mode"] if world > 1 else None,
         "mc_phases": mc_phases,

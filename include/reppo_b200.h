@@ -33,7 +33,10 @@ enum { REPPO_NORM_NONE = 0, REPPO_NORM_RMS = 1 /* jax_models.py:46, torch_models
        REPPO_NORM_LAYER = 2 /* src/reppo_mj_playground.py:65-72 */ };
 enum { REPPO_KL_CLIPPED = 0, REPPO_KL_FULL = 1, REPPO_KL_VALUE = 2 }; /* actor_kl_clip_mode, config/reppo.yaml:64 */
 enum { REPPO_GEMM_FP32 = 0,  /* fp32 FFMA GEMMs: reference-precision mode ("highest", src/jaxrl/__init__.py:3) */
-       REPPO_GEMM_BF16 = 1   /* tcgen05 bf16 operands / fp32 TMEM accumulators ("medium", src/torchrl/reppo.py:35) */ };
+       REPPO_GEMM_BF16 = 1,  /* tcgen05 bf16 operands / fp32 TMEM accumulators ("medium", src/torchrl/reppo.py:35) */
+       REPPO_GEMM_TF32 = 2   /* tcgen05.mma.kind::tf32 on the fp32 operands themselves (10-bit mantissa products, fp32 accumulation):
+                                reference precision on tensor cores; everything outside the GEMMs as in REPPO_GEMM_FP32.
+                                GEMMs whose operands TMA cannot address (ragged leading dimensions) run the FFMA kernel. */ };
 enum { REPPO_NET_CRITIC = 0, REPPO_NET_ACTOR = 1 };
 
 /* Static shape of the two networks (config/reppo.yaml:38-55) and of the workspace. */

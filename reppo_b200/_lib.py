@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(HERE, "libreppo_b200.so")
 SEM_JAX, SEM_TORCH = 0, 1
 NORM_NONE, NORM_RMS, NORM_LAYER = 0, 1, 2
 KL_CLIPPED, KL_FULL, KL_VALUE = 0, 1, 2
-GEMM_FP32, GEMM_BF16 = 0, 1
+GEMM_FP32, GEMM_BF16, GEMM_TF32 = 0, 1, 2
+GEMM_MODES = {"fp32": GEMM_FP32, "bf16": GEMM_BF16, "tf32": GEMM_TF32}
 NET_CRITIC, NET_ACTOR = 0, 1
 NUM_METRICS = 24
 METRIC_NAMES = [

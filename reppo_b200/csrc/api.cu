@@ -118,6 +118,10 @@ struct reppo_ctx {
   cudaEvent_t ev_epoch[2] = {nullptr, nullptr};
   unsigned int* adam_bar = nullptr;   // 3 x {arrival count, generation}: critic chain, actor chain, stand-alone calls
   uint16_t* shadow_b[NUM_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  // REPPO_GEMM_TF32: aligned, row-padded fp32 copies of the weight matrices (same offsets / leading dimensions as the bf16
+  // shadows): the parameter arena follows the reference's state_dict order and its matrices are not 16-byte aligned
+  bool tf32 = false;
+  float* shadow_f[NUM_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
   // step pipelining: second copy of the critic parameters (Adam ping-pongs between the two), and a private set of
   // critic-trunk buffers for the actor step, so that critic step k+1 can overlap actor step k
   float* cp_alt = nullptr;
@@ -299,6 +303,12 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
     };
     c->x0_ep[i] = big(K0); c->xa0_ep[i] = big(D); c->x0a_ep[i] = big(K0);
   }
+  if (c->tf32) {
+    c->shadow_f[SLOT_CRITIC] = F(c->shadow_b_elems[0]);
+    c->shadow_f[SLOT_ACTOR] = F(c->shadow_b_elems[1]);
+    c->shadow_f[SLOT_ACTOR_OLD] = F(c->shadow_b_elems[1]);
+    c->shadow_f[SLOT_CRITIC_ALT] = F(c->shadow_b_elems[0]);
+  }
   if (c->tc) {
     c->shadow_b[SLOT_CRITIC] = Hf(c->shadow_b_elems[0]);
     c->shadow_b[SLOT_ACTOR] = Hf(c->shadow_b_elems[1]);
@@ -334,6 +344,11 @@ int linear_fwd(reppo_ctx* c, const Linear& L, const float* params, int slot, con
     CK(launch_gemm_bf16_tc(false, false, rows, L.out, L.in, tx.p, tx.ld, c->shadow_b[slot] + L.sb, L.ld_b, y, L.out,
                            params + L.b, GEMM_STORE, 1, act.p, act.ld, st));
   } else {
+    if (c->tf32) {
+      const cudaError_t e = launch_gemm_tf32_tc(false, false, rows, L.out, L.in, x, L.in, c->shadow_f[slot] + L.sb, L.ld_b, y, L.out,
+                                                params + L.b, GEMM_STORE, 1, st);
+      if (e != cudaErrorNotSupported) { CK(e); return REPPO_OK; }
+    }
     CK(launch_gemm_f32(false, true, rows, L.out, L.in, x, L.in, params + L.w, L.in, y, L.out, params + L.b, GEMM_STORE, 1, st));
   }
   return REPPO_OK;
@@ -348,13 +363,22 @@ int linear_dgrad(reppo_ctx* c, const Linear& L, const float* params, int slot, c
     CK(launch_gemm_bf16_tc(false, true, rows, L.in, L.out, td.p, td.ld, c->shadow_b[slot] + L.sb, L.ld_b, dx, L.in, nullptr, mode,
                            1, nullptr, 0, st));
   } else {
+    if (c->tf32) {
+      const cudaError_t e = launch_gemm_tf32_tc(false, true, rows, L.in, L.out, dy, L.out, c->shadow_f[slot] + L.sb, L.ld_b, dx, L.in,
+                                                nullptr, mode, 1, st);
+      if (e != cudaErrorNotSupported) { CK(e); return REPPO_OK; }
+    }
     CK(launch_gemm_f32(false, false, rows, L.in, L.out, dy, L.out, params + L.w, L.in, dx, L.in, nullptr, mode, 1, st));
   }
   return REPPO_OK;
 }
 // dW[out,in] += dy[rows,out]^T x[rows,in]   (dW zeroed at the start of the step)
 int linear_wgrad(reppo_ctx* c, const Linear& L, const float* dy, const float* x, int rows, float* dw, cudaStream_t st) {
-  const int split = wgrad_split(L.out, L.in, rows, c->tc);
+  const int split = wgrad_split(L.out, L.in, rows, c->tc || c->tf32);
+  if (c->tf32) {
+    const cudaError_t e = launch_gemm_tf32_tc(true, true, L.out, L.in, rows, dy, L.out, x, L.in, dw, L.in, nullptr, GEMM_ATOMIC, split, st);
+    if (e != cudaErrorNotSupported) { CK(e); return REPPO_OK; }
+  }
   if (c->tc) {
     const Twin td = c->twin(dy), tx = c->twin(x);
     if (td.p == nullptr || tx.p == nullptr) return fail(c, REPPO_ERR_INVALID, "internal: wgrad operand has no bf16 twin");
@@ -365,14 +389,16 @@ int linear_wgrad(reppo_ctx* c, const Linear& L, const float* dy, const float* x,
   return REPPO_OK;
 }
 
-// refresh the bf16 shadows of one network's weights (no-op in fp32 mode)
+// refresh the operand shadows of one network's weights: bf16 (tcgen05 bf16 mode) or aligned fp32 (tf32 mode); no-op in fp32 mode
 int pack_shadows(reppo_ctx* c, int slot, const float* params, cudaStream_t st) {
-  if (!c->tc) return REPPO_OK;
+  if (!c->tc && !c->tf32) return REPPO_OK;
   PackTable t{};
+  t.fp32 = c->tf32 ? 1 : 0;
   auto add = [&](const Mlp& m) {
     for (const Linear& L : m.layers) {
       PackEntry& e = t.e[t.n++];
-      e.w = params + L.w; e.wb = c->shadow_b[slot] + L.sb;
+      e.w = params + L.w;
+      e.wb = c->tf32 ? static_cast<void*>(c->shadow_f[slot] + L.sb) : static_cast<void*>(c->shadow_b[slot] + L.sb);
       e.out = L.out; e.in = L.in; e.ld_b = L.ld_b;
     }
   };
@@ -698,12 +724,13 @@ int clip_adam_impl(reppo_ctx* c, const reppo_net_state* net, int64_t n, const re
                    const float* p_in, float* p_out, float* partials, int chain, cudaStream_t st, bool zero_grads = false) {
   if (c->ws == nullptr) return fail(c, REPPO_ERR_WORKSPACE, "workspace not set (reppo_set_workspace)");
   ShadowTable sh{};
-  if (c->tc && slot >= 0) {
+  if ((c->tc || c->tf32) && slot >= 0) {
+    sh.fp32 = c->tf32 ? 1 : 0;
     auto add = [&](const Mlp& m) {
       for (const Linear& L : m.layers) {
         ShadowEntry& e = sh.e[sh.n++];
         e.start = L.w; e.end = L.w + static_cast<int64_t>(L.out) * L.in; e.in = L.in; e.ld = L.ld_b;
-        e.dst = c->shadow_b[slot] + L.sb;
+        e.dst = c->tf32 ? static_cast<void*>(c->shadow_f[slot] + L.sb) : static_cast<void*>(c->shadow_b[slot] + L.sb);
       }
     };
     if (slot == SLOT_CRITIC || slot == SLOT_CRITIC_ALT) { add(c->feature); add(c->head); add(c->pred); } else { add(c->actor); }
@@ -874,12 +901,14 @@ int reppo_ctx_create(const reppo_shape* shape, reppo_ctx** out) {
   if (s.critic_hidden > 2048 || s.actor_hidden > 2048) return fail(nullptr, REPPO_ERR_UNSUPPORTED, "hidden_dim > 2048");
   if (s.semantics != REPPO_SEM_JAX && s.semantics != REPPO_SEM_TORCH) return fail(nullptr, REPPO_ERR_INVALID, "semantics");
   if (s.critic_norm < 0 || s.critic_norm > 2 || s.actor_norm < 0 || s.actor_norm > 2) return fail(nullptr, REPPO_ERR_INVALID, "norm type");
-  if (s.gemm_mode != REPPO_GEMM_FP32 && s.gemm_mode != REPPO_GEMM_BF16) return fail(nullptr, REPPO_ERR_INVALID, "gemm_mode");
+  if (s.gemm_mode != REPPO_GEMM_FP32 && s.gemm_mode != REPPO_GEMM_BF16 && s.gemm_mode != REPPO_GEMM_TF32)
+    return fail(nullptr, REPPO_ERR_INVALID, "gemm_mode");
   if (!(s.vmax > s.vmin)) return fail(nullptr, REPPO_ERR_INVALID, "vmax <= vmin");
 
   reppo_ctx* c = new reppo_ctx();
   c->shape = s;
   c->tc = (s.gemm_mode == REPPO_GEMM_BF16);
+  c->tf32 = (s.gemm_mode == REPPO_GEMM_TF32);
   c->concurrent = !knobs().serial;
   c->fuse_norm = !knobs().no_fuse_norm;
   c->pipeline = !knobs().no_pipeline;
@@ -1037,6 +1066,15 @@ int reppo_linear(reppo_ctx* c, int32_t op, int32_t rows, int32_t in_f, int32_t o
   if (!a || !b || !out || rows <= 0 || in_f <= 0 || out_f <= 0 || op < 0 || op > 2)
     return fail(c, REPPO_ERR_INVALID, "reppo_linear: bad argument");
   c->launches = 0;
+  if (c->tf32) {
+    // fp32 operands read as tf32 straight from the caller's buffers when TMA can address them
+    cudaError_t e;
+    if (op == 0) e = launch_gemm_tf32_tc(false, false, rows, out_f, in_f, a, in_f, b, in_f, out, out_f, bias, GEMM_STORE, 1, st);
+    else if (op == 1) e = launch_gemm_tf32_tc(false, true, rows, in_f, out_f, a, out_f, b, in_f, out, in_f, nullptr, GEMM_STORE, 1, st);
+    else e = launch_gemm_tf32_tc(true, true, out_f, in_f, rows, a, out_f, b, in_f, out, in_f, nullptr, GEMM_ATOMIC,
+                                 wgrad_split(out_f, in_f, rows, true), st);
+    if (e != cudaErrorNotSupported) { CK(e); return REPPO_OK; }
+  }
   if (!c->tc) {
     if (op == 0) CK(launch_gemm_f32(false, true, rows, out_f, in_f, a, in_f, b, in_f, out, out_f, bias, GEMM_STORE, 1, st));
     else if (op == 1) CK(launch_gemm_f32(false, false, rows, in_f, out_f, a, out_f, b, in_f, out, in_f, nullptr, GEMM_STORE, 1, st));

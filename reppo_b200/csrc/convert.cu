@@ -17,10 +17,12 @@ pack_weights_kernel(const PackTable t) {
   // blockIdx.y = tensor, blockIdx.x grid-strides over its elements (rows of the shadow are padded to ld_b)
   const PackEntry e = t.e[blockIdx.y];
   __nv_bfloat16* wb = static_cast<__nv_bfloat16*>(e.wb);
+  float* wf = static_cast<float*>(e.wb);
   const int total = e.out * e.in;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int r = i / e.in, c = i - r * e.in;
-    wb[static_cast<size_t>(r) * e.ld_b + c] = __float2bfloat16_rn(e.w[i]);
+    if (t.fp32) wf[static_cast<size_t>(r) * e.ld_b + c] = e.w[i];   // aligned, row-padded fp32 copy (tf32 operands)
+    else wb[static_cast<size_t>(r) * e.ld_b + c] = __float2bfloat16_rn(e.w[i]);
   }
 }
 

@@ -36,9 +36,22 @@ constexpr int TC_BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int TC_UMMA_K = 16;
 constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M = 128
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+// Operand kind.  KIND_TF32 is the reference-precision mode on tensor cores (REPPO_GEMM_TF32): the fp32 activations and an
+// aligned fp32 copy of the weights are read as they are by TMA and multiplied by tcgen05.mma.kind::tf32 (10-bit mantissa
+// products, fp32 accumulation).  Everything scales with the element size: a 128-byte swizzle row holds 64 bf16 or 32 fp32
+// values (= one k-block of a K-major operand, one MN atom of an MN-major one), one MMA consumes 32 bytes of K (16 / 8).
+enum { KIND_BF16 = 0, KIND_TF32 = 1 };
+template <int KIND> struct KindTraits {
+  static constexpr int kElem = KIND == KIND_TF32 ? 4 : 2;
+  static constexpr int kBlockK = 128 / kElem;
+  static constexpr int kUmmaK = 32 / kElem;
+  static constexpr int kAtomMN = 128 / kElem;
+  static constexpr uint32_t kFormat = KIND == KIND_TF32 ? 2u : 1u;   // F16F32Format: 1 = BF16, 2 = TF32
+};
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): {bf16 | tf32} x same -> f32, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major, uint32_t fmt = 1u) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(TC_BLOCK_M >> 4) << 24);
 }
@@ -63,7 +76,7 @@ struct TcSmem {
 // The N = H columns of a 128-row slab are spread over the CTAs of one thread-block CLUSTER (gridDim.x CTAs of
 // BLOCK_N columns); every CTA reduces its own columns and the per-row partial (sum, sum of squares) are exchanged
 // through distributed shared memory (mapa + ld.shared::cluster) between two cluster barriers.
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int NORM>
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int NORM, int KIND = KIND_BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     float* __restrict__ C, int ldc, const float* __restrict__ bias, int M, int N, int K, int k_blocks_per_split,
@@ -78,7 +91,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BLOCK_M, n0 = blockIdx.x * BLOCK_N;
-  const int total_k_blocks = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+  using KT = KindTraits<KIND>;
+  static_assert(KIND == KIND_BF16 || NORM == NORM_NONE, "the fused-norm epilogue writes bf16 twins: bf16 kind only");
+  const int total_k_blocks = (K + KT::kBlockK - 1) / KT::kBlockK;
   const int kb_begin = blockIdx.z * k_blocks_per_split;
   const int kb_end = min(total_k_blocks, kb_begin + k_blocks_per_split);
   const int num_kb = kb_end - kb_begin;
@@ -109,24 +124,26 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint8_t* sa = smem + s * S::kStageBytes;
       uint8_t* sb = sa + S::kABytes;
       mbar_expect_tx(&full_bar[s], S::kStageBytes);
-      const int k0 = (kb_begin + i) * TC_BLOCK_K;
-      // K-major tile [rows][64 k]: coordinates {k, row}.  MN-major: atoms of [64 k-rows][64 mn], coordinates {mn, k-row}.
+      const int k0 = (kb_begin + i) * KT::kBlockK;
+      // K-major tile [rows][128 B of k]: coordinates {k, row}.  MN-major: atoms of [kBlockK k-rows][128 B of mn], coordinates {mn, k-row}.
       if (!A_MN) {
         tma_load_2d(&tmap_a, &full_bar[s], sa, k0, m0);
       } else {
 #pragma unroll
-        for (int a = 0; a < TC_BLOCK_M / 64; ++a) tma_load_2d(&tmap_a, &full_bar[s], sa + a * (TC_BLOCK_K * 128), m0 + a * 64, k0);
+        for (int a = 0; a < TC_BLOCK_M / KT::kAtomMN; ++a)
+          tma_load_2d(&tmap_a, &full_bar[s], sa + a * (KT::kBlockK * 128), m0 + a * KT::kAtomMN, k0);
       }
       if (!B_MN) {
         tma_load_2d(&tmap_b, &full_bar[s], sb, k0, n0);
       } else {
 #pragma unroll
-        for (int b = 0; b < BLOCK_N / 64; ++b) tma_load_2d(&tmap_b, &full_bar[s], sb + b * (TC_BLOCK_K * 128), n0 + b * 64, k0);
+        for (int b = 0; b < BLOCK_N / KT::kAtomMN; ++b)
+          tma_load_2d(&tmap_b, &full_bar[s], sb + b * (KT::kBlockK * 128), n0 + b * KT::kAtomMN, k0);
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc(BLOCK_N, A_MN, B_MN);
+    constexpr uint32_t idesc = make_idesc(BLOCK_N, A_MN, B_MN, KT::kFormat);
     for (int i = 0; i < num_kb; ++i) {
       const int s = i % STAGES;
       const uint32_t ph = (i / STAGES) & 1;
@@ -135,15 +152,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
       const uint32_t sb = sa + S::kABytes;
 #pragma unroll
-      for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+      for (int k = 0; k < KT::kBlockK / KT::kUmmaK; ++k) {
         // K-major SW128: 8-row groups 1024 B apart; advance 32 B per UMMA_K inside the swizzle row.
-        // MN-major SW128: LBO = stride between 64-wide MN atoms, SBO = stride between 8-row K groups;
-        // advance 16 k-rows = 2048 B per UMMA_K.
-        const uint64_t da = A_MN ? make_smem_desc(sa + k * (TC_UMMA_K * 128), TC_BLOCK_K * 128, 1024)
-                                 : make_smem_desc(sa + k * (TC_UMMA_K * 2), 16, 1024);
-        const uint64_t db = B_MN ? make_smem_desc(sb + k * (TC_UMMA_K * 128), TC_BLOCK_K * 128, 1024)
-                                 : make_smem_desc(sb + k * (TC_UMMA_K * 2), 16, 1024);
-        tc_mma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        // MN-major SW128: LBO = stride between 128-byte-wide MN atoms, SBO = stride between 8-row K groups;
+        // advance kUmmaK k-rows (2048 / 1024 B) per UMMA_K.
+        // MN-major tf32: the 32-byte-atom flavour of the 128-byte swizzle (the only one tcgen05 takes for MN-major 32-bit
+        // operands): swizzle groups of 4 k-rows, SBO = 512 B
+        constexpr uint32_t kMnSbo = KIND == KIND_TF32 ? 512 : 1024, kMnType = KIND == KIND_TF32 ? 1 : 2;
+        const uint64_t da = A_MN ? make_smem_desc(sa + k * (KT::kUmmaK * 128), KT::kBlockK * 128, kMnSbo, kMnType)
+                                 : make_smem_desc(sa + k * 32, 16, 1024);
+        const uint64_t db = B_MN ? make_smem_desc(sb + k * (KT::kUmmaK * 128), KT::kBlockK * 128, kMnSbo, kMnType)
+                                 : make_smem_desc(sb + k * 32, 16, 1024);
+        if constexpr (KIND == KIND_TF32) tc_mma_tf32(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        else tc_mma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
       }
       tc_commit(&empty_bar[s]);          // frees the smem slot when these MMAs retire
     }
@@ -359,12 +380,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // ---- host side -------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int KIND = KIND_BF16>
 static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int ldc, const float* bias, int M, int N,
                              int K, int split_k, int mode, __nv_bfloat16* act_out, int act_ld, cudaStream_t st) {
   using S = TcSmem<BLOCK_N, STAGES>;
+  constexpr int TC_BLOCK_K = KindTraits<KIND>::kBlockK;   // shadows the bf16 constant below
   static bool configured = false;
-  auto kern = gemm_bf16_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN, NORM_NONE>;
+  auto kern = gemm_bf16_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN, NORM_NONE, KIND>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) return e;
@@ -468,6 +490,32 @@ cudaError_t launch_gemm_bf16_tc(bool a_mn, bool b_mn, int M, int N, int K, const
   if (!a_mn && b_mn) { REPPO_TC_DISPATCH(false, true); }
   REPPO_TC_DISPATCH(true, true);
 #undef REPPO_TC_DISPATCH
+}
+
+// The same three arrangements on fp32 operands read as tf32 (REPPO_GEMM_TF32).  A, B: fp32 device pointers, leading
+// dimensions in elements.  cudaErrorNotSupported when TMA cannot address an operand (base not 16-byte aligned, leading
+// dimension not a multiple of 4 floats): the caller falls back to the FFMA kernel for that GEMM.
+cudaError_t launch_gemm_tf32_tc(bool a_mn, bool b_mn, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                                float* C, int ldc, const float* bias, int mode, int split_k, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
+  if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+    return cudaErrorNotSupported;
+  if (a_mn && !b_mn) return cudaErrorNotSupported;
+  using KT = KindTraits<KIND_TF32>;
+  CUtensorMap ta, tb;
+  const int tiles128 = ((M + TC_BLOCK_M - 1) / TC_BLOCK_M) * ((N + 127) / 128) * (split_k > 0 ? split_k : 1);
+  const bool wide = (N > 64) && (tiles128 >= knobs().tc_wide_min);
+  const int block_n = wide ? 128 : 64;
+  const bool ok_a = a_mn ? tmap_encode_2d(&ta, A, K, M, lda, KT::kAtomMN, KT::kBlockK, 4, true) : tmap_encode_2d(&ta, A, M, K, lda, KT::kBlockK, TC_BLOCK_M, 4);
+  const bool ok_b = b_mn ? tmap_encode_2d(&tb, B, K, N, ldb, KT::kAtomMN, KT::kBlockK, 4, true) : tmap_encode_2d(&tb, B, N, K, ldb, KT::kBlockK, block_n, 4);
+  if (!ok_a || !ok_b) return cudaErrorNotSupported;
+#define REPPO_TF32_DISPATCH(AMN, BMN)                                                                                        \
+  return wide ? launch_tc<128, 4, AMN, BMN, KIND_TF32>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, nullptr, 0, st)         \
+              : launch_tc<64, 4, AMN, BMN, KIND_TF32>(ta, tb, C, ldc, bias, M, N, K, split_k, mode, nullptr, 0, st)
+  if (!a_mn && !b_mn) { REPPO_TF32_DISPATCH(false, false); }
+  if (!a_mn && b_mn) { REPPO_TF32_DISPATCH(false, true); }
+  REPPO_TF32_DISPATCH(true, true);
+#undef REPPO_TF32_DISPATCH
 }
 
 }  // namespace reppo

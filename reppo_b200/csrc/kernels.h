@@ -51,6 +51,10 @@ cudaError_t launch_gemm_f32(bool ta, bool tb, int M, int N, int K, const float* 
 cudaError_t launch_gemm_bf16_tc(bool a_mn, bool b_mn, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
                                 float* C, int ldc, const float* bias, int mode, int split_k, void* act_out, int act_ld,
                                 cudaStream_t st);
+// the same kernel on fp32 operands read as tf32 (reference-precision mode on tensor cores); cudaErrorNotSupported = an operand is
+// not TMA-addressable (alignment / leading dimension): run launch_gemm_f32 instead
+cudaError_t launch_gemm_tf32_tc(bool a_mn, bool b_mn, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                                float* C, int ldc, const float* bias, int mode, int split_k, cudaStream_t st);
 // persistent CTA-pair (cta_group::2) variant for large shapes (gemm_bf16_tc2.cu); cudaErrorNotSupported = not eligible
 cudaError_t launch_gemm_bf16_tc2(bool a_mn, bool b_mn, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
                                  float* C, int ldc, const float* bias, int mode, int split_k, void* act_out, int act_ld,
@@ -63,7 +67,7 @@ cudaError_t launch_gemm_bf16_tc_norm(int norm, int M, int N, int K, const void* 
 // fp32 -> bf16 copies: plain (row-padded) and, for weights, the [out,in] matrices of one network in one launch
 struct PackEntry { const float* w; void* wb; int out, in, ld_b; };
 constexpr int kMaxPack = 16;
-struct PackTable { int n; PackEntry e[kMaxPack]; };
+struct PackTable { int n; int fp32; PackEntry e[kMaxPack]; };   // fp32: the shadow keeps fp32 (tf32 GEMM operands), else bf16
 cudaError_t launch_pack_weights(const PackTable& t, cudaStream_t st);
 cudaError_t launch_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, cudaStream_t st);
 cudaError_t launch_colsum(const float* X, int M, int N, int ld, float* out, float* out2, float scale2, cudaStream_t st);
@@ -113,7 +117,7 @@ cudaError_t launch_obs_normalize(const float* x, long long rows, int D, float* m
 
 // bf16 shadows of the weight matrices, refreshed by the Adam kernel itself (REPPO_GEMM_BF16)
 struct ShadowEntry { long long start, end; int in, ld; void* dst; };
-struct ShadowTable { int n; ShadowEntry e[kMaxPack]; };
+struct ShadowTable { int n; int fp32; ShadowEntry e[kMaxPack]; };
 // Data-parallel gradient all-reduce over NVSwitch multicast memory, fused into the clip+Adam launch (optim.cu).  The gradient
 // arena lives in a symmetric allocation that every rank maps three ways: its own copy (what the gradient kernels write),
 // every peer's copy (flags only) and the MULTICAST mapping, on which `multimem.ld_reduce` returns the switch-side sum over

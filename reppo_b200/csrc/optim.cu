@@ -211,7 +211,8 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
       if (idx >= sh.e[e].start && idx < sh.e[e].end) {
         const int off = static_cast<int>(idx - sh.e[e].start);
         const int r = off / sh.e[e].in, col = off - r * sh.e[e].in;
-        static_cast<__nv_bfloat16*>(sh.e[e].dst)[static_cast<size_t>(r) * sh.e[e].ld + col] = __float2bfloat16_rn(p1);
+        if (sh.fp32) static_cast<float*>(sh.e[e].dst)[static_cast<size_t>(r) * sh.e[e].ld + col] = p1;
+        else static_cast<__nv_bfloat16*>(sh.e[e].dst)[static_cast<size_t>(r) * sh.e[e].ld + col] = __float2bfloat16_rn(p1);
         break;
       }
     }
@@ -223,7 +224,7 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
       if (idx >= sh.e[e].start && idx + 3 < sh.e[e].end) {
         const int off = static_cast<int>(idx - sh.e[e].start);
         const int r = off / sh.e[e].in, col = off - r * sh.e[e].in;
-        if (col + 3 < sh.e[e].in) {
+        if (col + 3 < sh.e[e].in && !sh.fp32) {
           __nv_bfloat16* d = static_cast<__nv_bfloat16*>(sh.e[e].dst) + static_cast<size_t>(r) * sh.e[e].ld + col;
           const __nv_bfloat162 lo = __floats2bfloat162_rn(q.x, q.y), hi = __floats2bfloat162_rn(q.z, q.w);
           if ((reinterpret_cast<uintptr_t>(d) & 7) == 0) {

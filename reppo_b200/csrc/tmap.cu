@@ -22,7 +22,8 @@ EncodeTiledFn get_encode_fn() {
 }
 }  // namespace
 
-bool tmap_encode_2d(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_cols, int box_rows, int elem_bytes) {
+bool tmap_encode_2d(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_cols, int box_rows, int elem_bytes,
+                    bool atom_32b) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return false;
   if (elem_bytes != 2 && elem_bytes != 4) return false;
@@ -33,7 +34,7 @@ bool tmap_encode_2d(CUtensorMap* map, const void* base, int rows, int cols, int 
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   return fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            atom_32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace reppo

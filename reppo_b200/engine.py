@@ -36,7 +36,7 @@ class EngineConfig:
     use_actor_norm: bool = True
     norm_type: str = "rms"          # "rms" (jax_models.py:46) | "layer" (reppo_mj_playground.py:65-72)
     semantics: str = "jax"          # "jax" parity target | "torch" API semantics
-    gemm_mode: str = "fp32"         # "fp32" | "bf16"
+    gemm_mode: str = "fp32"         # "fp32" (FFMA) | "bf16" (tcgen05, bf16 operands) | "tf32" (tcgen05 on the fp32 operands)
     max_rows: int = 2048
     kl_samples: int = 16
     max_batch_rows: int = 0         # rows per epoch of `update` (n_mb * mb): enables the per-epoch pre-gather (0 = per-step gathers)
@@ -52,7 +52,7 @@ class EngineConfig:
             critic_norm=norm if self.use_critic_norm else L.NORM_NONE,
             actor_norm=norm if self.use_actor_norm else L.NORM_NONE,
             semantics=L.SEM_JAX if self.semantics == "jax" else L.SEM_TORCH,
-            gemm_mode=L.GEMM_FP32 if self.gemm_mode == "fp32" else L.GEMM_BF16,
+            gemm_mode=L.GEMM_MODES[self.gemm_mode],
             max_rows=self.max_rows, kl_samples=self.kl_samples, vmin=self.vmin, vmax=self.vmax,
             max_batch_rows=self.max_batch_rows)
 

@@ -288,7 +288,10 @@ def make_train_state(cfg, n_obs: int, n_critic_obs: int, n_act: int, device=None
                       use_norm=h.use_actor_norm, layers=h.num_actor_layers, min_std=h.actor_min_std)
     old_actor.load_state_dict(actor.state_dict())
     mb = (int(h.num_steps) * int(h.num_envs)) // int(h.num_mini_batches)
-    gemm_mode = "bf16" if cfg.platform.get("amp_dtype", "f32") == "bf16" else "fp32"
+    # platform.amp_dtype: bf16 -> tcgen05 on bf16 operands; tf32 -> tcgen05 on the fp32 operands (what
+    # torch.set_float32_matmul_precision("high") asks of the reference's matmuls); anything else -> fp32 FFMA ("highest")
+    amp = str(cfg.platform.get("amp_dtype", "f32"))
+    gemm_mode = amp if amp in ("bf16", "tf32") else "fp32"
     # the workspace serves the minibatch steps AND the per-environment-step forwards of the collection loop (num_envs rows)
     eng = bind_engine(actor, critic, old_actor, max_rows=max_rows or max(mb, int(h.num_envs)), semantics=semantics,
                       norm_type=b200.get("norm_type", "rms"), gemm_mode=gemm_mode, device=device,

@@ -76,6 +76,35 @@ def test_fp32_mode_linear_vs_torch():
     torch.testing.assert_close(eng.linear(2, dy, x), dy.T @ x, rtol=1e-5, atol=1e-4)
 
 
+# tf32 mode: tcgen05.mma.kind::tf32 reads the fp32 operands themselves (10-bit mantissa products, fp32 accumulation).  Shapes whose
+# operands TMA can address (leading dimensions multiples of 4 floats) run on the tensor cores in all three arrangements,
+# K-major and MN-major; ragged ones fall back to the FFMA kernel per GEMM -- both must agree with torch fp32 within tf32
+# operand precision (2^-11 relative per operand), and the tensor-core ones must be clearly closer than bf16 operands would be.
+TF32_SHAPES = [(2048, 512, 512), (128, 64, 64), (300, 24, 152), (2048, 512, 516), (1000, 512, 12), (77, 16, 512), (2048, 152, 512),
+               (300, 23, 151), (256, 512, 1), (640, 1024, 256)]
+
+
+@pytest.mark.parametrize("rows,in_f,out_f", TF32_SHAPES)
+def test_tf32_mode_forward_dgrad_wgrad_vs_torch(rows, in_f, out_f):
+    eng = _engine(max_rows=2048, mode="tf32", H=1024)
+    g = torch.Generator(device="cuda").manual_seed(rows * 5 + out_f)
+    x = torch.randn(rows, in_f, device="cuda", generator=g)
+    w = torch.randn(out_f, in_f, device="cuda", generator=g) / math.sqrt(in_f)
+    b = torch.randn(out_f, device="cuda", generator=g)
+    dy = torch.randn(rows, out_f, device="cuda", generator=g)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cases = [(eng.linear(0, x, w, bias=b), x @ w.T + b, _bf(x) @ _bf(w).T + b, in_f),
+             (eng.linear(1, dy, w), dy @ w, _bf(dy) @ _bf(w), out_f),
+             (eng.linear(2, dy, x), dy.T @ x, _bf(dy).T @ _bf(x), rows)]
+    for got, ref, ref_bf16, k in cases:
+        scale = ref.abs().max().item()
+        torch.testing.assert_close(got, ref, rtol=2e-3, atol=1.5e-3 * scale)
+        on_tc = in_f % 4 == 0 and out_f % 4 == 0
+        if on_tc and k >= 64:
+            # not bf16 in disguise: the error against fp32 is several times below that of bf16-rounded operands
+            assert (got - ref).abs().mean().item() < 0.35 * (ref_bf16 - ref).abs().mean().item()
+
+
 def test_forward_is_deterministic_and_row_independent():
     """Properties at the full C2 minibatch size: repeated launches are bit-identical, and any
     row subset of the input gives the same rows of the output (no cross-row leakage through the
