@@ -68,6 +68,9 @@ typedef struct reppo_hyper {
                                             lr_anneal_steps) evaluated on the device at each network's own optimizer step
                                             counter (lr is NOT re-read from the host per step, so a captured graph stays
                                             valid across updates); 0 = constant lr */
+  int32_t reverse_kl;                    /* cfg.reverse_kl (src/jaxrl/reppo.py:543-553, JAX semantics only): the KL estimate is
+                                            E_{a ~ pi}[log pi(a) - log pi_old(a)] over 16 reparameterised samples of the CURRENT
+                                            policy (gradient through the samples) instead of the forward KL from pi_old */
 } reppo_hyper;
 
 /* One network's flat fp32 arenas (layout: reppo_param_* below) plus its Adam step counter. */

@@ -97,6 +97,7 @@ class Hyper:
     kl_start: float = 0.01
     kl_bound: float = 0.1
     reduce_kl: bool = True
+    reverse_kl: bool = False  # jaxrl/reppo.py:543-553 (JAX update only)
     update_kl_lagrangian: bool = True
     actor_kl_clip_mode: str = "clipped"
     ent_start: float = 0.01
@@ -496,6 +497,17 @@ def actor_loss(pa, pa_old, pc, mb: Dict[str, Tensor], eps_pi: Tensor, eps_kl: Te
         logp = (-0.5 * eps_pi ** 2 - torch.log(std) - HALF_LOG_2PI - _fldj(x)).sum(-1)
     q = critic_value(pc, mb["critic_obs"], a, hp, sem)
 
+    if hp.reverse_kl and sem.name == "jax":
+        # jaxrl/reppo.py:543-553: 16 reparameterised samples of the CURRENT policy (gradient flows through them and
+        # through the clip), log pi at the pre-tanh sample (distrax sample_and_log_prob), log pi_old at the clipped action
+        with torch.no_grad():
+            mu_o, std_o = actor_forward(pa_old, mb["obs"], hp, sem)
+        x_s = mu.unsqueeze(0) + std.unsqueeze(0) * eps_kl
+        lp_pi = (-0.5 * eps_kl ** 2 - torch.log(std) - HALF_LOG_2PI - _fldj(x_s)).sum(-1).mean(0)
+        u_s = torch.atanh(torch.clamp(torch.tanh(x_s), -sem.action_clip, sem.action_clip))
+        lp_o = (_normal_logpdf(u_s, mu_o, std_o) - _fldj(u_s)).sum(-1).mean(0)
+        kl = lp_pi - lp_o
+        return _actor_loss_tail(pa, logp, q, a, kl, hp, sem)
     with torch.no_grad():
         mu_o, std_o = actor_forward(pa_old, mb["obs"], hp, sem)
         x_o = mu_o.unsqueeze(0) + std_o.unsqueeze(0) * eps_kl
@@ -507,7 +519,12 @@ def actor_loss(pa, pa_old, pc, mb: Dict[str, Tensor], eps_pi: Tensor, eps_kl: Te
             lp_old = (-0.5 * eps_kl ** 2 - torch.log(std_o) - HALF_LOG_2PI - _fldj(x_o)).sum(-1).mean(0)
     lp_new = (_normal_logpdf(u, mu, std) - _fldj(u)).sum(-1).mean(0)
     kl = lp_old - lp_new
+    return _actor_loss_tail(pa, logp, q, a, kl, hp, sem)
 
+
+def _actor_loss_tail(pa, logp, q, a, kl, hp: Hyper, sem: Semantics):
+    """Everything after the KL estimate (jaxrl/reppo.py:566-622; torchrl/reppo.py:313-338)."""
+    A = hp.action_dim
     alpha = torch.exp(pa["log_temp"])
     beta = torch.exp(pa["log_lagrange"])
     rk = 1.0 if hp.reduce_kl else 0.0

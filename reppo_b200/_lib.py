@@ -43,7 +43,7 @@ class Hyper(C.Structure):
     _fields_ = [(n, C.c_float) for n in (
         "gamma", "lmbda", "lr", "max_grad_norm", "kl_bound", "ent_target_mult", "aux_loss_mult", "actor_min_std")] + [
         (n, C.c_int32) for n in ("kl_clip_mode", "reduce_kl", "update_entropy_lagrangian", "update_kl_lagrangian",
-                                 "partial_reset", "world_size", "lr_anneal_steps")]
+                                 "partial_reset", "world_size", "lr_anneal_steps", "reverse_kl")]
 
 
 class NetState(C.Structure):

@@ -156,8 +156,9 @@ def validate_update_config(cfg: DictConfig):
     for k in ("use_simplical_embedding", "use_critic_skip", "use_actor_skip"):
         if h.get(k, False):
             raise NotImplementedError(f"{k}=true is a dead path in the reference and is not implemented")
-    if h.get("reverse_kl", False):
-        raise NotImplementedError("reverse_kl=true (src/jaxrl/reppo.py:543-553) is not implemented")
+    if h.get("reverse_kl", False) and cfg.get("b200", {}).get("semantics", "torch") != "jax":
+        # only the JAX update has the switch (src/jaxrl/reppo.py:543-553); src/torchrl/reppo.py never reads it
+        raise NotImplementedError("reverse_kl=true exists in the JAX update only: set b200.semantics=jax")
     if h.actor_kl_clip_mode not in ("clipped", "full", "value"):
         raise ValueError(f"Unknown actor loss mode: {h.actor_kl_clip_mode}")
     for k in ("num_critic_encoder_layers", "num_critic_head_layers", "num_critic_pred_layers", "num_actor_layers"):

@@ -651,6 +651,7 @@ ActorConsts actor_consts(const reppo_ctx* c, const reppo_hyper* hp) {
   ac.kl_mode = hp->kl_clip_mode;
   ac.update_entropy = (torch_sem || hp->update_entropy_lagrangian) ? 1 : 0;
   ac.update_kl = (torch_sem || hp->update_kl_lagrangian) ? 1 : 0;
+  ac.reverse_kl = (!torch_sem && hp->reverse_kl) ? 1 : 0;
   return ac;
 }
 

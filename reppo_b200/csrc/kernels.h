@@ -33,6 +33,7 @@ struct HLConsts {           // categorical head + HL-Gauss constants
 struct ActorConsts {
   float min_std, action_clip, kl_bound, target_entropy, reduce_kl;
   int clip_policy_sample, old_logp_at_clipped, kl_mode, update_entropy, update_kl;
+  int reverse_kl;   // KL(pi || pi_old) from samples of the current policy (src/jaxrl/reppo.py:543-553)
 };
 
 struct AdamConsts {

@@ -19,8 +19,7 @@ struct Knobs {
   int prio;              // REPPO_PRIO=0|1        : graph node priorities for the actor chain (-1 = auto: small steps, 1 GPU)
   int wgrad_split;       // REPPO_WGRAD_SPLIT=n   : split-K factor of the weight-gradient GEMMs (0 = auto)
   int nccl_own;          // REPPO_ALLREDUCE=nccl|mc : gradient all-reduce through NCCL or the NVSwitch-multicast kernel (-1 auto)
-  // GEMM selection (gemm_bf16_tc.cu / gemm_bf16_pair.cu / gemm_bf16_tc2.cu)
-  int pair;              // REPPO_PAIR=0|1        : CTA-pair (cta_group::2) one-tile kernel for the H x H layers (-1 = auto)
+  // GEMM selection (gemm_bf16_tc.cu / gemm_bf16_tc2.cu)
   int tc_wide_min;       // REPPO_TC_WIDE_MIN=n   : 128-wide tiles in the one-CTA kernel when >= n of them exist
   bool norm_bn128;       // REPPO_NORM_BN128=1    : 128-wide tiles in the one-CTA fused-norm kernel
   bool fuse_norm_large;  // REPPO_FUSE_NORM_LARGE=1 : keep the fused-norm kernel at the wide-net shapes
@@ -56,7 +55,6 @@ inline const Knobs& knobs() {
       const char* v = getenv("REPPO_ALLREDUCE");
       x.nccl_own = (v == nullptr) ? -1 : ((v[0] == 'm' || v[0] == 'M') ? 1 : 0);
     }
-    x.pair = knob_int("REPPO_PAIR", -1);
     x.tc_wide_min = knob_int("REPPO_TC_WIDE_MIN", 120);
     x.norm_bn128 = knob_set("REPPO_NORM_BN128");
     x.fuse_norm_large = knob_set("REPPO_FUSE_NORM_LARGE");

@@ -320,6 +320,27 @@ actor_sample_kernel(const float* __restrict__ out, const float* __restrict__ out
           for (int j = 0; j < kSampleChunk; ++j) {
             if (c0 + j < A) {
               const float4 cc = cst[r][c0 + j];
+              if (ac.reverse_kl) {
+                // sample of the CURRENT policy, gradient through it: kl = lp_pi(x) - lp_old(clip(tanh x)); per dimension
+                //   0.5 zo^2 - 0.5 eps^2 - (log sig - log sig_o) - (fldj(x) - fldj(u)),  zo = (u - mu_o) / sig_o
+                // (the log-sigma part is row-constant and joins below); gm / gs hold -d kl / d(mu, sigma) because the
+                // gradient kernel multiplies them by d L / d lp_new = -d L / d kl.
+                const float sig = 1.f / cc.y;
+                const float xs = cc.x + sig * eo[j];
+                const float u = fminf(fmaxf(xs, -u_max), u_max);
+                const float zo = (u - cc.z) / cc.w;
+                dsum += 0.5f * zo * zo - 0.5f * eo[j] * eo[j];
+                float dx;
+                if (u != xs) {   // clipped: the old policy's term is constant, -fldj(x) keeps its slope 2 tanh(x)
+                  dsum -= fldj_(xs) - fldj_(u);
+                  dx = 2.f * tanhf(xs);
+                } else {
+                  dx = zo / cc.w;
+                }
+                gm[j] -= dx;
+                gs[j] -= dx * eo[j] - cc.y;
+                continue;
+              }
               const float xo = cc.z + cc.w * eo[j];
               const float u = fminf(fmaxf(xo, -u_max), u_max);
               const float zn = (u - cc.x) * cc.y;
@@ -363,7 +384,7 @@ actor_sample_kernel(const float* __restrict__ out, const float* __restrict__ out
     }
     if (sl == 0 && ok) {
       logp_out[row] = logp;
-      kl_out[row] = dsum * inv_s + klc;
+      kl_out[row] = ac.reverse_kl ? dsum * inv_s - klc : dsum * inv_s + klc;
     }
     __syncthreads();   // cst / rowk / red are rewritten by the next row block
   }

@@ -74,6 +74,7 @@ class HyperParams:
     update_kl_lagrangian: bool = True
     partial_reset: bool = False
     world_size: int = 1
+    reverse_kl: bool = False        # cfg.reverse_kl (src/jaxrl/reppo.py:543-553): KL(pi || pi_old) from samples of the current policy
     lr_anneal_steps: int = 0        # cfg.anneal_lr: optimizer steps over which lr decays linearly to 0 (src/jaxrl/reppo.py:239-244)
 
     def c_struct(self) -> L.Hyper:
@@ -86,7 +87,7 @@ class HyperParams:
             actor_min_std=self.actor_min_std, kl_clip_mode=L.KL_MODES[self.actor_kl_clip_mode],
             reduce_kl=int(self.reduce_kl), update_entropy_lagrangian=int(self.update_entropy_lagrangian),
             update_kl_lagrangian=int(self.update_kl_lagrangian), partial_reset=int(self.partial_reset),
-            world_size=self.world_size, lr_anneal_steps=int(self.lr_anneal_steps))
+            world_size=self.world_size, lr_anneal_steps=int(self.lr_anneal_steps), reverse_kl=int(self.reverse_kl))
 
 
 class _Net:

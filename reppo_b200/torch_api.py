@@ -309,7 +309,7 @@ def _hyper(cfg, train_state: TrainState, which: str = "critic") -> HyperParams:
         gamma=float(h.gamma), lmbda=float(h.lmbda), lr=lr, max_grad_norm=float(h.max_grad_norm), kl_bound=float(h.kl_bound),
         ent_target_mult=float(h.ent_target_mult), aux_loss_mult=float(h.aux_loss_mult),
         actor_min_std=float(train_state.actor.min_std), actor_kl_clip_mode=str(h.actor_kl_clip_mode),
-        reduce_kl=bool(h.get("reduce_kl", True)), update_entropy_lagrangian=bool(h.get("update_entropy_lagrangian", True)),
+        reverse_kl=bool(h.get("reverse_kl", False)), reduce_kl=bool(h.get("reduce_kl", True)), update_entropy_lagrangian=bool(h.get("update_entropy_lagrangian", True)),
         update_kl_lagrangian=bool(h.get("update_kl_lagrangian", True)),
         partial_reset=bool(cfg.env.get("partial_reset", False)), lr_anneal_steps=_anneal_steps(cfg))
 

@@ -39,7 +39,8 @@ def _hyper(hp: O.Hyper):
                        ent_target_mult=hp.ent_target_mult, aux_loss_mult=hp.aux_loss_mult, actor_min_std=hp.actor_min_std,
                        actor_kl_clip_mode=hp.actor_kl_clip_mode, reduce_kl=hp.reduce_kl,
                        update_entropy_lagrangian=hp.update_entropy_lagrangian,
-                       update_kl_lagrangian=hp.update_kl_lagrangian, partial_reset=hp.partial_reset)
+                       update_kl_lagrangian=hp.update_kl_lagrangian, partial_reset=hp.partial_reset,
+                       reverse_kl=getattr(hp, "reverse_kl", False))
 
 
 def _grad_close(name, got, want, rel=2e-5):
@@ -232,6 +233,9 @@ GRAD_CASES = [
     (O.JAX, dict(SMALL, kl_bound=0.004, reduce_kl=True)),
     (O.JAX, dict(SMALL, update_entropy_lagrangian=False, update_kl_lagrangian=False, aux_loss_mult=0.3)),
     (O.TORCH, dict(SMALL, partial_reset=True, use_critic_norm=False, use_actor_norm=False)),
+    # cfg.reverse_kl (src/jaxrl/reppo.py:543-553): KL(pi || pi_old) from samples of the current policy, every clip mode
+    (O.JAX, dict(SMALL, reverse_kl=True)), (O.JAX, dict(RAGGED, reverse_kl=True, actor_kl_clip_mode="full", kl_bound=0.02)),
+    (O.JAX, dict(SMALL, reverse_kl=True, kl_bound=0.004)),
 ]
 
 

@@ -53,6 +53,43 @@ def test_tanh_gaussian_log_prob_matches_torch_distributions():
     torch.testing.assert_close(O._fldj(small), torch.log1p(-torch.tanh(small) ** 2), rtol=1e-9, atol=1e-9)
 
 
+def test_reverse_kl_matches_torch_distributions_and_closed_form():
+    """cfg.reverse_kl (src/jaxrl/reppo.py:543-553): mean over samples a ~ pi of log pi(a) - log pi_old(a).  Without clipping it
+    is an unbiased estimate of KL(N(mu, std) || N(mu_o, std_o)) (the tanh Jacobians cancel); the oracle's value is held against
+    torch.distributions on the same samples, and its sample mean against the Gaussian closed form."""
+    from torch.distributions import Normal, TransformedDistribution, kl_divergence
+    from torch.distributions.transforms import TanhTransform
+    hp = O.Hyper(num_steps=4, num_envs=64, num_mini_batches=1, num_epochs=1, critic_hidden_dim=32, actor_hidden_dim=32, num_bins=11,
+                 vmin=0.0, vmax=5.0, obs_dim=3, critic_obs_dim=3, action_dim=2, reverse_kl=True, actor_kl_clip_mode="full")
+    sem = O.JAX
+    cp, ap = O.init_params(hp, sem, seed=0)
+    ap_old = {k: v + 0.05 * torch.randn(v.shape, generator=torch.Generator().manual_seed(5)) for k, v in ap.items()}
+    batch = O.synthetic_rollout(hp, seed=0)
+    flat = O.flatten_batch(batch, O.compute_targets({k: v.clone() for k, v in batch.items()}, hp, sem))
+    eps_pi, eps_kl = O.synthetic_noise(hp)
+    _, m = O.actor_loss(ap, ap_old, cp, flat, eps_pi[0], eps_kl[0], hp, sem)
+    mu, std = O.actor_forward(ap, flat["obs"], hp, sem)
+    mu_o, std_o = O.actor_forward(ap_old, flat["obs"], hp, sem)
+    # float64 restatement through torch.distributions: log pi at the sample itself (distrax sample_and_log_prob, before the
+    # clip), log pi_old at the clipped action (old_pi.log_prob(pi_action) after jnp.clip)
+    d = lambda t: t.double()
+    x = d(mu).unsqueeze(0) + d(std).unsqueeze(0) * d(eps_kl[0])
+    pi = TransformedDistribution(Normal(d(mu), d(std)), TanhTransform())
+    old = TransformedDistribution(Normal(d(mu_o), d(std_o)), TanhTransform())
+    lp_pi = Normal(d(mu), d(std)).log_prob(x) - torch.log1p(-torch.tanh(x) ** 2)
+    a_c = torch.tanh(x).clamp(-sem.action_clip, sem.action_clip)
+    want = (lp_pi.sum(-1) - old.log_prob(a_c).sum(-1)).mean(0).mean()
+    assert abs(m["kl"].item() - want.item()) <= 2e-4 * max(1.0, abs(want.item()))   # the oracle runs in fp32
+    unclipped = (torch.tanh(x).abs() <= sem.action_clip).all(-1)
+    torch.testing.assert_close(pi.log_prob(torch.tanh(x))[unclipped.unsqueeze(-1).expand_as(x)], lp_pi[unclipped.unsqueeze(-1).expand_as(x)],
+                               rtol=1e-6, atol=1e-6)
+    # without the clip the estimate is unbiased for the Gaussian closed form (the tanh Jacobians cancel)
+    closed = kl_divergence(Normal(mu, std), Normal(mu_o, std_o)).sum(-1).mean()
+    free = (lp_pi.sum(-1) - (Normal(d(mu_o), d(std_o)).log_prob(x) - torch.log1p(-torch.tanh(x) ** 2)).sum(-1)).mean()
+    assert abs(free.item() - closed.item()) <= 0.25 * closed.item()                   # 16 x 256 samples
+    assert m["kl"].item() > 0
+
+
 def test_optax_adam_chain_matches_torch_adam():
     # optax.chain(clip_by_global_norm(c), adam(lr, b1=.9, b2=.999, eps=1e-8, eps_root=0)) : g <- g * min(1, c / ||g||),
     # bias-corrected moments, p <- p - lr * m_hat / (sqrt(v_hat) + eps).  torch.optim.Adam implements the same update.
