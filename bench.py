@@ -254,6 +254,11 @@ def run_reference(args):
 ALLREDUCE = {"mode": "none"}
 
 
+def dp_defaults():
+    from reppo_b200 import dist as dp_plumbing
+    return dp_plumbing.RECOMMENDED_NCCL_ENV
+
+
 def _attach_multicast(eng, dp_plumbing):
     """Data-parallel gradient exchange: ncclAllReduce inside the graph (default: it measured faster at 2 and 8 GPUs), or with
     REPPO_ALLREDUCE=mc the multicast all-reduce fused into clip+Adam when the box has NVSwitch multicast memory."""
@@ -496,6 +501,9 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
     torch.cuda.set_device(local)
     if world > 1:
+        # the per-step gradient all-reduces are ~1-5 MB and latency-bound: NCCL's LL protocol measured 2 % faster per update than
+        # its own choice at 2 and at 8 GPUs (115.2 -> 112.8 ms, 124.6 -> 122.1 ms); LL128 and a channel cap measured slower
+        os.environ.setdefault("NCCL_PROTO", dp_defaults()["NCCL_PROTO"])
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = torch.device(f"cuda:{local}")
     peaks = load_peaks()
@@ -862,6 +870,7 @@ def main():
         "configs": extra_cfgs, "fp32": fp32_leg, "tf32": tf32_leg, "strong": strong_leg, "dp_check": dpc,
         "knobs": {k: os.environ[k] for k in os.environ if k.startswith("REPPO_")},
         "allreduce": ALLREDUCE["mode"] if world > 1 else None,
+        "nccl_env": {k: os.environ[k] for k in os.environ if k.startswith("NCCL_")} if world > 1 else None,
         "mc_phases": mc_phases,
         "final_metrics": {k: final_metrics[k] for k in ("critic_loss", "actor_loss", "kl", "entropy")},
     }
