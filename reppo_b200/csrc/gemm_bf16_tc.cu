@@ -385,12 +385,14 @@ static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float
                              int K, int split_k, int mode, __nv_bfloat16* act_out, int act_ld, cudaStream_t st) {
   using S = TcSmem<BLOCK_N, STAGES>;
   constexpr int TC_BLOCK_K = KindTraits<KIND>::kBlockK;   // shadows the bf16 constant below
-  static bool configured = false;
+  static unsigned long long configured = 0ull;   // one bit per device: the attribute is per device
   auto kern = gemm_bf16_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN, NORM_NONE, KIND>;
-  if (!configured) {
+  int dev__ = 0;
+  cudaGetDevice(&dev__);
+  if (!((configured >> (dev__ & 63)) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured |= 1ull << (dev__ & 63);
   }
   const int total_kb = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
   if (split_k < 1) split_k = 1;
@@ -408,12 +410,14 @@ template <int BLOCK_N, int NORM>
 static cudaError_t launch_tc_norm(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int ldc, const float* bias, int M,
                                   int N, int K, __nv_bfloat16* act_out, int act_ld, const NormArgs& na, cudaStream_t st) {
   using S = TcSmem<BLOCK_N, 4>;
-  static bool configured = false;
+  static unsigned long long configured = 0ull;   // one bit per device: the attribute is per device
   auto kern = gemm_bf16_tc_kernel<BLOCK_N, 4, false, false, NORM>;
-  if (!configured) {
+  int dev__ = 0;
+  cudaGetDevice(&dev__);
+  if (!((configured >> (dev__ & 63)) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured |= 1ull << (dev__ & 63);
   }
   const int total_kb = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
   cudaLaunchConfig_t cfg{};

@@ -294,12 +294,14 @@ cudaError_t launch_t2(const CUtensorMap& ta, const CUtensorMap& tb, float* C, in
                       int splits, int mode, __nv_bfloat16* act_out, int act_ld, int max_pairs, cudaStream_t st) {
   using S = T2Smem<BN, STAGES>;
   static_assert(S::kTotal <= 227 * 1024, "shared memory");
-  static bool configured = false;
+  static unsigned long long configured = 0ull;   // one bit per device: the attribute is per device
   auto kern = gemm_bf16_tc2_kernel<BN, STAGES, A_MN, B_MN>;
-  if (!configured) {
+  int dev__ = 0;
+  cudaGetDevice(&dev__);
+  if (!((configured >> (dev__ & 63)) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured |= 1ull << (dev__ & 63);
   }
   const int total_kb = (K + T2_K - 1) / T2_K;
   if (splits < 1) splits = 1;

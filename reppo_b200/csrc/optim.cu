@@ -147,6 +147,18 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
   const int t = *step + 1;   // every block reads the counter before the barrier; block 0 writes it after
   unsigned int my_gen = 0;
   bool last = false;
+  if (threadIdx.x == 32) {
+    // step-dependent scalars (two double-precision pow) on another warp, while thread 0 sits at the grid barrier
+    s_bc1 = static_cast<float>(1.0 - pow(static_cast<double>(c.b1), static_cast<double>(t)));
+    s_bc2 = static_cast<float>(1.0 - pow(static_cast<double>(c.b2), static_cast<double>(t)));
+    float lr = c.lr;
+    if (c.anneal_steps > 0) {
+      // optax.linear_schedule(lr, 0, T) at count = t - 1 (polynomial_schedule, power 1): lr * (1 - min(count, T) / T)
+      const float cnt = static_cast<float>(min(t - 1, c.anneal_steps));
+      lr = c.lr * (1.f - cnt / static_cast<float>(c.anneal_steps));
+    }
+    s_lr = lr;
+  }
   if (threadIdx.x == 0) {
     partials[blockIdx.x] = s;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(my_gen) : "l"(bar + 1) : "memory");   // before arriving
@@ -182,15 +194,6 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
       else scale = (gn < c.max_grad_norm) ? 1.f : c.max_grad_norm / gn;       // optax.clip_by_global_norm
     }
     s_scale = scale;
-    s_bc1 = static_cast<float>(1.0 - pow(static_cast<double>(c.b1), static_cast<double>(t)));
-    s_bc2 = static_cast<float>(1.0 - pow(static_cast<double>(c.b2), static_cast<double>(t)));
-    float lr = c.lr;
-    if (c.anneal_steps > 0) {
-      // optax.linear_schedule(lr, 0, T) at count = t - 1 (polynomial_schedule, power 1): lr * (1 - min(count, T) / T)
-      const float cnt = static_cast<float>(min(t - 1, c.anneal_steps));
-      lr = c.lr * (1.f - cnt / static_cast<float>(c.anneal_steps));
-    }
-    s_lr = lr;
     if (blockIdx.x == 0) {
       *step = t;
       if (grad_norm_out != nullptr) *grad_norm_out = gn;

@@ -136,7 +136,8 @@ def _init_linear_(module: _ArenaModule, gen=None):
 
 
 class Critic(_ArenaModule):
-    """Categorical HL-Gauss critic (src/networks/torch_models.py:209-285)."""
+    """Categorical HL-Gauss critic (src/networks/torch_models.py:209-285).  ``forward`` returns plain tensors computed by the
+    library (no autograd graph; see ``Actor``): gradients come from ``make_critic_update_fn`` / ``reppo_update`` only."""
 
     def __init__(self, n_obs, n_act, num_atoms: int, vmin: float, vmax: float, hidden_dim=256, use_norm=True,
                  use_encoder_norm=False, encoder_layers=1, head_layers=1, pred_layers=1, device=None,
@@ -167,7 +168,12 @@ class Critic(_ArenaModule):
 
 
 class Actor(_ArenaModule):
-    """Tanh-Gaussian policy with temperature / Lagrange multipliers (src/networks/torch_models.py:288-335)."""
+    """Tanh-Gaussian policy with temperature / Lagrange multipliers (src/networks/torch_models.py:288-335).
+
+    ``forward`` is computed by the library and returns plain tensors: there is NO autograd graph behind it (and the
+    temperature / Lagrange multiplier come back detached), so a loss built from it cannot be back-propagated.  Gradients
+    exist only through ``make_actor_update_fn`` / ``reppo_update``, which write them into the ``.grad`` views of these
+    parameters."""
 
     def __init__(self, n_obs, n_act, ent_start: float, kl_start: float, hidden_dim=256, use_norm=True, layers=2,
                  min_std=0.1, device=None):
