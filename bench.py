@@ -59,6 +59,8 @@ def arm_watchdog():
     limit = float(os.environ.get("REPPO_BENCH_WATCHDOG_S", "1500"))
     if limit > 0:
         faulthandler.dump_traceback_later(limit, exit=True)
+    import signal
+    faulthandler.register(signal.SIGUSR1, all_threads=True)   # `kill -USR1 <pid>`: where is it right now?
 
 
 def emit(obj):

@@ -22,6 +22,9 @@ SOURCES = ["api.cu", "tmap.cu", "td_lambda.cu", "gemm_f32.cu", "gemm_bf16_tc.cu"
            "losses.cu", "optim.cu", "rollout.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+# REPPO_BUILD_DEFINES="A B=1": extra -D flags for a diagnostic build (e.g. REPPO_SPIN_DIAG: every device-side spin wait gets a
+# time-out that reports itself); part of the build digest, so switching them rebuilds
+FLAGS += [f"-D{d}" for d in os.environ.get("REPPO_BUILD_DEFINES", "").split()]
 
 
 def _nvcc() -> str:

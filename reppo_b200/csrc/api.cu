@@ -757,6 +757,7 @@ int clip_adam_impl(reppo_ctx* c, const reppo_net_state* net, int64_t n, const re
   }
   CK(launch_clip_adam(p_in ? p_in : net->params, p_out ? p_out : net->params, net->grads, net->adam_m, net->adam_v, n, net->step,
                       partials ? partials : c->partials, c->adam_bar + 2 * chain, a, &sh, gn_out, zero_grads ? 1 : 0, st, &mc));
+  if (!clip_adam_fused(&mc)) ++c->launches;   // partial sums and the update are two kernels
   return REPPO_OK;
 }
 

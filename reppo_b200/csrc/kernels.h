@@ -137,6 +137,8 @@ struct McArgs {
 };
 // bar: two device uint32 {arrival count, generation} of the kernel's grid barrier (zero-initialised once; one pair per
 // concurrently running chain)
+// true: one launch with a grid barrier (multicast all-reduce, REPPO_ADAM_FUSED=1); false: two launches (partials, then clip + Adam)
+bool clip_adam_fused(const McArgs* mc);
 cudaError_t launch_clip_adam(const float* p_in, float* p, float* g, float* m, float* v, long long n, int* step, float* partials,
                              unsigned int* bar, const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out,
                              int zero_grads, cudaStream_t st, const McArgs* mc = nullptr);

@@ -1,19 +1,22 @@
-// K12 -- global-norm clip + Adam / AdamW on one flat fp32 arena, ONE launch.
+// K12 -- global-norm clip + Adam / AdamW on one flat fp32 arena.
 //   JAX  : optax.chain(clip_by_global_norm(max_grad_norm), adam(lr))  src/jaxrl/reppo.py:246-257
 //          lr = optax.linear_schedule(cfg.lr, 0, num_updates) when cfg.anneal_lr (:239-244)
 //   Torch: clip_grad_norm_ (+1e-6) -> AdamW(weight_decay=0.01)         src/torchrl/reppo.py:270-273,527-534
-// Phase 1: every block reduces the squares of its slice of the gradient (kept in registers) to one partial, publishes
-// it and arrives at a grid-wide barrier (arrival counter + generation word in the workspace; the last block to arrive
-// resets the counter and bumps the generation, so the kernel is replayable inside a CUDA graph with any grid size).  While it waits, the loads of p / m / v for phase 2 are in flight.  Phase 2: every
-// block re-adds the <= kMaxPartials partials in a fixed order (deterministic global norm, no float atomics), derives
-// the clip scale, the bias corrections and the (optionally annealed) learning rate from the device step counter, and
-// streams its slice: 28 B per parameter (read g, p, m, v; write p, m, v) + the bf16 shadow + the zeroed gradient.
-// Co-residency (the barrier must not deadlock): the grid never exceeds the number of SMs and the kernel is held to 64
-// registers (512 threads, no dynamic shared memory), so TWO blocks fit on an SM.  The only kernels that can wait on each
-// other are the critic chain's and the actor chain's clip_adam running at the same time (<= 2 x 148 blocks <= 296 slots):
-// both are always fully resident.  Blocks of other kernels that occupy SMs complete on their own, and programmatic
-// dependents of THIS kernel are only launched once all of its blocks have started (launch_dependents is per block).
+// One kernel template, two ways to run it:
+//  * SPLIT (default): launch 1 (PHASE 1) reduces every block's slice of the gradient to one partial sum of squares and advances
+//    the device step counter; launch 2 (PHASE 2, programmatic dependent launch) re-adds the <= kMaxPartials partials in a fixed
+//    order (deterministic global norm, no float atomics), derives the clip scale, the bias corrections and the (optionally
+//    annealed) learning rate, and streams its slice: 28 B per parameter (read g, p, m, v; write p, m, v) + the operand shadow
+//    + the zeroed gradient.
+//  * FUSED (PHASE 0; REPPO_ADAM_FUSED=1, and always with the multicast all-reduce whose cross-GPU barriers live in this kernel):
+//    both phases in one launch around a grid-wide barrier (arrival counter + generation word, replayable inside a CUDA graph).
+//    The barrier needs every block resident at once.  The grid never exceeds the SM count and two 512-thread blocks fit on an
+//    SM, so the critic chain's and the actor chain's launches can always coexist -- but that holds only while nothing else
+//    occupies the SMs: with the input pipeline's kernels (torch.randperm / normal_ on the copy stream) running beside the graph
+//    the resident blocks were seen spinning for seconds (1 of 20 end-to-end runs; 4 of 18 in a variant), which is why the fused
+//    form is no longer the default, and why its barrier gives up after three seconds and says so instead of hanging the device.
 #include <cuda_bf16.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -24,7 +27,6 @@
 
 namespace reppo {
 
-constexpr int kAdamThreads = 512;
 constexpr int kAdamKeep = 4;   // float4 gradient chunks a thread keeps in registers across the barrier
 
 // ---- data-parallel phase: all-reduce of the gradient arena through NVSwitch multicast memory -------------------------------
@@ -81,7 +83,9 @@ __device__ __forceinline__ void multimem_store(float4* p, const float4& q) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(q.x), "f"(q.y), "f"(q.z), "f"(q.w) : "memory");
 }
 
-__global__ void __launch_bounds__(kAdamThreads, 2)
+// PHASE: 0 = one launch with the grid barrier (fused), 1 = partial sums of squares only, 2 = clip + Adam from the partials
+template <int THREADS, int PHASE>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
                  float* __restrict__ partials, unsigned int* __restrict__ bar, int* __restrict__ step, AdamConsts c,
                  const ShadowTable sh, float* __restrict__ grad_norm_out, int zero_grads, const McArgs mc) {
@@ -143,23 +147,19 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
     s += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float q = __ldcg(g + (n4 << 2) + threadIdx.x); s += q * q; }
-  s = block_sum(s, red);
-  const int t = *step + 1;   // every block reads the counter before the barrier; block 0 writes it after
+  if constexpr (PHASE != 2) s = block_sum(s, red);
+  if constexpr (PHASE == 1) {
+    if (threadIdx.x == 0) {
+      partials[blockIdx.x] = s;
+      if (blockIdx.x == 0) *step = *step + 1;   // the update launch only reads the counter: no block can see it half-way
+    }
+    return;
+  }
+  // fused: every block reads the counter before the barrier, block 0 writes it after; split: already advanced by launch 1
+  const int t = (PHASE == 2) ? *step : *step + 1;
   unsigned int my_gen = 0;
   bool last = false;
-  if (threadIdx.x == 32) {
-    // step-dependent scalars (two double-precision pow) on another warp, while thread 0 sits at the grid barrier
-    s_bc1 = static_cast<float>(1.0 - pow(static_cast<double>(c.b1), static_cast<double>(t)));
-    s_bc2 = static_cast<float>(1.0 - pow(static_cast<double>(c.b2), static_cast<double>(t)));
-    float lr = c.lr;
-    if (c.anneal_steps > 0) {
-      // optax.linear_schedule(lr, 0, T) at count = t - 1 (polynomial_schedule, power 1): lr * (1 - min(count, T) / T)
-      const float cnt = static_cast<float>(min(t - 1, c.anneal_steps));
-      lr = c.lr * (1.f - cnt / static_cast<float>(c.anneal_steps));
-    }
-    s_lr = lr;
-  }
-  if (threadIdx.x == 0) {
+  if (PHASE == 0 && threadIdx.x == 0) {
     partials[blockIdx.x] = s;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(my_gen) : "l"(bar + 1) : "memory");   // before arriving
     __threadfence();
@@ -168,7 +168,7 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
   // phase-2 operands of the first pass are requested before the wait
   float4 pp = make_float4(0.f, 0.f, 0.f, 0.f), mm = pp, vv = pp;
   if (first < n4) { pp = pi4[first]; mm = m4[first]; vv = v4[first]; }
-  if (threadIdx.x == 0) {
+  if (PHASE == 0 && threadIdx.x == 0) {
     if (last) {
       if (mc.world > 1) *mc.epoch += 2u;   // every block read the epoch before it arrived here
       bar[0] = 0u;   // nobody touches the counter again before the generation moves
@@ -176,8 +176,23 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(my_gen + 1u) : "memory");
     } else {
       unsigned int seen;
+      unsigned long long t0 = 0ull;
+      unsigned int spins = 0;
       do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar + 1) : "memory");
+        if (seen == my_gen && (++spins & 0xfffu) == 0u) {
+          // a grid barrier that cannot complete (not every block resident) must not hang the device: say so and go on
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0ull) t0 = now;
+          else if (now - t0 > 3000000000ull) {
+            unsigned int arrived;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(arrived) : "l"(bar) : "memory");
+            printf("reppo clip_adam_kernel: grid barrier timed out (block %d of %d, %u arrived, generation %u, n %lld)\n",
+                   static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), arrived, my_gen, n);
+            break;
+          }
+        }
       } while (seen == my_gen);
     }
   }
@@ -194,8 +209,17 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
       else scale = (gn < c.max_grad_norm) ? 1.f : c.max_grad_norm / gn;       // optax.clip_by_global_norm
     }
     s_scale = scale;
+    s_bc1 = static_cast<float>(1.0 - pow(static_cast<double>(c.b1), static_cast<double>(t)));
+    s_bc2 = static_cast<float>(1.0 - pow(static_cast<double>(c.b2), static_cast<double>(t)));
+    float lr = c.lr;
+    if (c.anneal_steps > 0) {
+      // optax.linear_schedule(lr, 0, T) at count = t - 1 (polynomial_schedule, power 1): lr * (1 - min(count, T) / T)
+      const float cnt = static_cast<float>(min(t - 1, c.anneal_steps));
+      lr = c.lr * (1.f - cnt / static_cast<float>(c.anneal_steps));
+    }
+    s_lr = lr;
     if (blockIdx.x == 0) {
-      *step = t;
+      if (PHASE == 0) *step = t;
       if (grad_norm_out != nullptr) *grad_norm_out = gn;
     }
   }
@@ -279,6 +303,8 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
   }
 }
 
+bool clip_adam_fused(const McArgs* mc) { return (mc != nullptr && mc->world > 1) || knobs().adam_fused; }
+
 cudaError_t launch_clip_adam(const float* p_in, float* p, float* g, float* m, float* v, long long n, int* step, float* partials,
                              unsigned int* bar, const AdamConsts& c, const ShadowTable* shadow, float* grad_norm_out,
                              int zero_grads, cudaStream_t st, const McArgs* mc) {
@@ -290,7 +316,10 @@ cudaError_t launch_clip_adam(const float* p_in, float* p, float* g, float* m, fl
     if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
   }
   // all blocks must be co-resident (grid barrier): at most one per SM
-  const long long want = (n / 4 + kAdamThreads - 1) / kAdamThreads;
+  // 256-thread blocks (16 K registers) find room on an SM that already runs two GEMM CTAs of the other chain, but measured
+  // slower (101.7 vs 96.2 ms per C2 update: twice the elements per thread after the barrier); 512 stays the default
+  const int threads = knobs().adam_threads == 256 ? 256 : 512;
+  const long long want = (n / 4 + threads - 1) / threads;
   int cap = std::min(sm_count, kMaxPartials);
   if (knobs().adam_blocks > 0 && knobs().adam_blocks < cap) cap = knobs().adam_blocks;
   int blocks = static_cast<int>(want < cap ? want : cap);
@@ -300,11 +329,23 @@ cudaError_t launch_clip_adam(const float* p_in, float* p, float* g, float* m, fl
   McArgs ma{};
   if (mc != nullptr && mc->world > 1) {
     // warps of a block are dealt to ranks round-robin (16 warps), flag rows are per block
-    if ((kAdamThreads / 32) % mc->world != 0 || mc->world > kMcMaxRanks || blocks > kMcFlagBlocks) return cudaErrorInvalidValue;
+    if ((threads / 32) % mc->world != 0 || mc->world > kMcMaxRanks || blocks > kMcFlagBlocks) return cudaErrorInvalidValue;
     ma = *mc;
   }
-  launch_k((clip_adam_kernel), dim3(blocks), dim3(kAdamThreads), 0, st, p_in, p, g, m, v, n, partials, bar, step, c, sh,
-           grad_norm_out, zero_grads, ma);
+  // Two launches by default: the fused kernel's grid barrier needs every block resident at once, and other work on the device
+  // (the input pipeline's kernels on the copy stream were enough) can keep the last blocks out while the resident ones spin --
+  // observed as a multi-second stall in 1 of 20 end-to-end runs.  The fused launch remains for the multicast all-reduce (its
+  // cross-GPU barriers live in the same kernel) and behind REPPO_ADAM_FUSED=1.
+  const bool fused = clip_adam_fused(mc);
+#define REPPO_ADAM_LAUNCH(T, PH)                                                                                      \
+  launch_k((clip_adam_kernel<T, PH>), dim3(blocks), dim3(T), 0, st, p_in, p, g, m, v, n, partials, bar, step, c, sh, \
+           grad_norm_out, zero_grads, ma)
+  if (threads == 512) {
+    if (fused) { REPPO_ADAM_LAUNCH(512, 0); } else { REPPO_ADAM_LAUNCH(512, 1); REPPO_ADAM_LAUNCH(512, 2); }
+  } else {
+    if (fused) { REPPO_ADAM_LAUNCH(256, 0); } else { REPPO_ADAM_LAUNCH(256, 1); REPPO_ADAM_LAUNCH(256, 2); }
+  }
+#undef REPPO_ADAM_LAUNCH
   return cudaGetLastError();
 }
 

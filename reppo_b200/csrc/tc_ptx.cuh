@@ -1,6 +1,7 @@
 // tcgen05 / TMA / mbarrier / cluster PTX wrappers shared by the tcgen05 kernel files.
 #pragma once
 #include <cuda.h>
+#include <stdio.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -16,6 +17,32 @@ REPPO_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
 REPPO_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+#ifdef REPPO_SPIN_DIAG
+// diagnostic build (REPPO_BUILD_DEFINES=REPPO_SPIN_DIAG): a wait that lasts three seconds reports itself and is abandoned
+REPPO_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  unsigned long long t0 = 0ull;
+  for (unsigned int spins = 1;; ++spins) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+    if ((spins & 0x3fffu) == 0u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0ull) t0 = now;
+      else if (now - t0 > 3000000000ull) {
+        printf("reppo: mbarrier wait timed out (block %d,%d,%d thread %d, barrier smem offset %u, parity %u)\n", blockIdx.x, blockIdx.y,
+               blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+        return;
+      }
+    }
+  }
+}
+#else
 REPPO_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -27,6 +54,7 @@ REPPO_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
       "SLAB_DONE:\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+#endif
 REPPO_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
