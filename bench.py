@@ -783,7 +783,7 @@ def main():
     import ctypes as C
     ns, hs = eng.critic.c_state(), hyp.c_struct()
     adam_ms = time_fn(lambda: eng.lib.reppo_clip_adam(eng.ctx, C.byref(ns), eng.critic.count, C.byref(hs), None, eng._stream()), 50)
-    adam = {"kernel": "clip_adam_kernel (one launch: global norm, grid barrier, clip, Adam, bf16 shadow refresh)", "bound": "hbm (L2-resident at this size)",
+    adam = {"kernel": "clip_adam_kernel (two launches: per-block partial sums of squares, then global norm + clip + Adam + bf16 shadow refresh)", "bound": "hbm (L2-resident at this size)",
             "achieved": 28.0 * eng.critic.count / (adam_ms * 1e-3) / 1e9, "unit": "GB/s", "ms": adam_ms, "params": eng.critic.count}
 
     # rollout-side inference: one policy step + one bootstrap step over this GPU's environments

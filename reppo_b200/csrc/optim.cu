@@ -101,7 +101,7 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long first = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   unsigned long long ts[6] = {0, 0, 0, 0, 0, 0};
-  if (mc.world > 1) {
+  if (PHASE == 0 && mc.world > 1) {
     // ---- phase 0 (data parallel): this block's slice of the gradient becomes the sum over all ranks
     const bool stamp = mc.stamps != nullptr && threadIdx.x == 0;
     if (stamp) ts[0] = global_ns();
@@ -293,7 +293,7 @@ clip_adam_kernel(const float* p_in, float* p, float* __restrict__ g, float* __re
     p[i] = q;
     if (zero_grads) g[i] = 0.f;
   }
-  if (mc.world > 1 && mc.stamps != nullptr && threadIdx.x == 0) {
+  if (PHASE == 0 && mc.world > 1 && mc.stamps != nullptr && threadIdx.x == 0) {
     // entry, block arrived at A, A done, reduce done + fenced (arrived at B), B done, exit
     ts[5] = global_ns();
     const unsigned long long slot = atomicAdd(mc.stamps, 1ull) & 8191ull;
