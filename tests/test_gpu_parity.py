@@ -352,7 +352,8 @@ def test_clip_adam_linear_lr_schedule():
 
 
 @pytest.mark.parametrize("sem,kw,use_graph", [(O.JAX, SMALL, False), (O.JAX, SMALL, True), (O.TORCH, SMALL, False),
-                                              (O.JAX, RAGGED, True)])
+                                              (O.JAX, RAGGED, True), (O.JAX, dict(SMALL, reverse_kl=True), True),
+                                              (O.JAX, dict(RAGGED, reverse_kl=True, actor_kl_clip_mode="full"), False)])
 def test_full_update_matches_oracle(sem, kw, use_graph):
     hp = O.Hyper(**kw)
     cp, ap = O.init_params(hp, sem, seed=0)
