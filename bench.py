@@ -658,8 +658,8 @@ def main():
             tf32_leg["dtype"] = "tf32"
             tf32_leg["note"] = ("reference-precision mode on tensor cores: tcgen05.mma.kind::tf32 on the fp32 activations and an aligned "
                                 "fp32 copy of the weights (10-bit mantissa products, fp32 accumulation; what "
-                                "torch.set_float32_matmul_precision('high') asks for); GEMMs with ragged leading dimensions "
-                                "(K = obs + act first layer, the 151-bin and H+1 head outputs' dgrad / wgrad) run the FFMA kernel")
+                                "torch.set_float32_matmul_precision('high') asks for); activation operands with ragged leading dimensions "
+                                "(obs + act inputs, the 151-bin / H+1 / 2A head gradients) are re-laid into row-padded scratch first")
         if world > 1:
             stage("strong-scaling leg")
             strong_leg = measure_config(args.config, args.semantics, args.gemm, world, rank, dev, steps=3, warmup=2, strong=True)

@@ -36,7 +36,8 @@ enum { REPPO_GEMM_FP32 = 0,  /* fp32 FFMA GEMMs: reference-precision mode ("high
        REPPO_GEMM_BF16 = 1,  /* tcgen05 bf16 operands / fp32 TMEM accumulators ("medium", src/torchrl/reppo.py:35) */
        REPPO_GEMM_TF32 = 2   /* tcgen05.mma.kind::tf32 on the fp32 operands themselves (10-bit mantissa products, fp32 accumulation):
                                 reference precision on tensor cores; everything outside the GEMMs as in REPPO_GEMM_FP32.
-                                GEMMs whose operands TMA cannot address (ragged leading dimensions) run the FFMA kernel. */ };
+                                Activation operands whose leading dimension TMA cannot address (not a multiple of 4 floats) are
+                                re-laid into row-padded scratch first; the FFMA kernel remains the fall-back. */ };
 enum { REPPO_NET_CRITIC = 0, REPPO_NET_ACTOR = 1 };
 
 /* Static shape of the two networks (config/reppo.yaml:38-55) and of the workspace. */

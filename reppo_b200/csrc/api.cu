@@ -122,6 +122,13 @@ struct reppo_ctx {
   // shadows): the parameter arena follows the reference's state_dict order and its matrices are not 16-byte aligned
   bool tf32 = false;
   float* shadow_f[NUM_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  // ... and row-padded copies of the activation operands whose leading dimension is not a multiple of four floats (the
+  // obs + act inputs, the 151-bin / H + 1 / 2A head gradients): two per stream that launches GEMMs, so concurrent chains and
+  // their weight-gradient side streams never share one
+  static constexpr int kTf32Streams = 8;
+  float* tf32_pad[kTf32Streams][2] = {};
+  cudaStream_t tf32_pad_owner[kTf32Streams] = {};
+  int tf32_pad_used = 0;
   // step pipelining: second copy of the critic parameters (Adam ping-pongs between the two), and a private set of
   // critic-trunk buffers for the actor step, so that critic step k+1 can overlap actor step k
   float* cp_alt = nullptr;
@@ -304,6 +311,8 @@ size_t layout_workspace(reppo_ctx* c, char* base) {
     c->x0_ep[i] = big(K0); c->xa0_ep[i] = big(D); c->x0a_ep[i] = big(K0);
   }
   if (c->tf32) {
+    const size_t md4 = (maxdim + 3) & ~static_cast<size_t>(3);
+    for (int i = 0; i < reppo_ctx::kTf32Streams; ++i) { c->tf32_pad[i][0] = F(R * md4); c->tf32_pad[i][1] = F(R * md4); }
     c->shadow_f[SLOT_CRITIC] = F(c->shadow_b_elems[0]);
     c->shadow_f[SLOT_ACTOR] = F(c->shadow_b_elems[1]);
     c->shadow_f[SLOT_ACTOR_OLD] = F(c->shadow_b_elems[1]);
@@ -334,6 +343,29 @@ int wgrad_split(int out, int in, int rows, bool tc) {
   return std::min(split, std::max(1, rows / 64));
 }
 
+// tf32 mode: `p` [rows, cols] with leading dimension cols as an operand TMA can address -- itself when cols is a multiple of four
+// floats, else a row-padded copy in this stream's scratch (`which` = 0 / 1: the two operands of one GEMM); ld receives the
+// leading dimension to use.  nullptr: no scratch left (more GEMM streams than kTf32Streams) -> the caller runs the FFMA kernel.
+const float* tf32_operand(reppo_ctx* c, const float* p, int rows, int cols, int which, int* ld, cudaStream_t st, cudaError_t* err) {
+  *err = cudaSuccess;
+  *ld = cols;
+  if ((cols & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) return p;
+  if (rows > c->shape.max_rows || cols > c->maxdim) return nullptr;
+  int slot = -1;
+  for (int i = 0; i < c->tf32_pad_used; ++i) if (c->tf32_pad_owner[i] == st) slot = i;
+  if (slot < 0) {
+    if (c->tf32_pad_used >= reppo_ctx::kTf32Streams) return nullptr;
+    slot = c->tf32_pad_used++;
+    c->tf32_pad_owner[slot] = st;
+  }
+  float* dst = c->tf32_pad[slot][which];
+  if (dst == nullptr) return nullptr;
+  *ld = (cols + 3) & ~3;
+  *err = launch_pad_rows_f32(p, rows, cols, cols, dst, *ld, st);
+  ++c->launches;
+  return dst;
+}
+
 // y[rows,out] = x[rows,in] W^T + b
 // act: optional bf16 twin that receives swish(y) from the GEMM epilogue (tensor-core mode only)
 int linear_fwd(reppo_ctx* c, const Linear& L, const float* params, int slot, const float* x, int rows, float* y, Twin act,
@@ -345,9 +377,15 @@ int linear_fwd(reppo_ctx* c, const Linear& L, const float* params, int slot, con
                            params + L.b, GEMM_STORE, 1, act.p, act.ld, st));
   } else {
     if (c->tf32) {
-      const cudaError_t e = launch_gemm_tf32_tc(false, false, rows, L.out, L.in, x, L.in, c->shadow_f[slot] + L.sb, L.ld_b, y, L.out,
-                                                params + L.b, GEMM_STORE, 1, st);
-      if (e != cudaErrorNotSupported) { CK(e); return REPPO_OK; }
+      int lda = L.in;
+      cudaError_t pe;
+      const float* xa = tf32_operand(c, x, rows, L.in, 0, &lda, st, &pe);
+      if (pe != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("pad_rows_f32: ") + cudaGetErrorString(pe));
+      if (xa != nullptr) {
+        const cudaError_t e = launch_gemm_tf32_tc(false, false, rows, L.out, L.in, xa, lda, c->shadow_f[slot] + L.sb, L.ld_b, y, L.out,
+                                                  params + L.b, GEMM_STORE, 1, st);
+        if (e != cudaErrorNotSupported) { CK(e); return REPPO_OK; }
+      }
     }
     CK(launch_gemm_f32(false, true, rows, L.out, L.in, x, L.in, params + L.w, L.in, y, L.out, params + L.b, GEMM_STORE, 1, st));
   }
@@ -364,9 +402,15 @@ int linear_dgrad(reppo_ctx* c, const Linear& L, const float* params, int slot, c
                            1, nullptr, 0, st));
   } else {
     if (c->tf32) {
-      const cudaError_t e = launch_gemm_tf32_tc(false, true, rows, L.in, L.out, dy, L.out, c->shadow_f[slot] + L.sb, L.ld_b, dx, L.in,
-                                                nullptr, mode, 1, st);
-      if (e != cudaErrorNotSupported) { CK(e); return REPPO_OK; }
+      int lda = L.out;
+      cudaError_t pe;
+      const float* da = tf32_operand(c, dy, rows, L.out, 0, &lda, st, &pe);
+      if (pe != cudaSuccess) return fail(c, REPPO_ERR_CUDA, std::string("pad_rows_f32: ") + cudaGetErrorString(pe));
+      if (da != nullptr) {
+        const cudaError_t e = launch_gemm_tf32_tc(false, true, rows, L.in, L.out, da, lda, c->shadow_f[slot] + L.sb, L.ld_b, dx, L.in,
+                                                  nullptr, mode, 1, st);
+        if (e != cudaErrorNotSupported) { CK(e); return REPPO_OK; }
+      }
     }
     CK(launch_gemm_f32(false, false, rows, L.in, L.out, dy, L.out, params + L.w, L.in, dx, L.in, nullptr, mode, 1, st));
   }
@@ -376,8 +420,15 @@ int linear_dgrad(reppo_ctx* c, const Linear& L, const float* params, int slot, c
 int linear_wgrad(reppo_ctx* c, const Linear& L, const float* dy, const float* x, int rows, float* dw, cudaStream_t st) {
   const int split = wgrad_split(L.out, L.in, rows, c->tc || c->tf32);
   if (c->tf32) {
-    const cudaError_t e = launch_gemm_tf32_tc(true, true, L.out, L.in, rows, dy, L.out, x, L.in, dw, L.in, nullptr, GEMM_ATOMIC, split, st);
-    if (e != cudaErrorNotSupported) { CK(e); return REPPO_OK; }
+    int lda = L.out, ldb = L.in;
+    cudaError_t pe, pe2;
+    const float* da = tf32_operand(c, dy, rows, L.out, 0, &lda, st, &pe);
+    const float* xb = tf32_operand(c, x, rows, L.in, 1, &ldb, st, &pe2);
+    if (pe != cudaSuccess || pe2 != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "pad_rows_f32 failed");
+    if (da != nullptr && xb != nullptr) {
+      const cudaError_t e = launch_gemm_tf32_tc(true, true, L.out, L.in, rows, da, lda, xb, ldb, dw, L.in, nullptr, GEMM_ATOMIC, split, st);
+      if (e != cudaErrorNotSupported) { CK(e); return REPPO_OK; }
+    }
   }
   if (c->tc) {
     const Twin td = c->twin(dy), tx = c->twin(x);
@@ -1069,12 +1120,24 @@ int reppo_linear(reppo_ctx* c, int32_t op, int32_t rows, int32_t in_f, int32_t o
     return fail(c, REPPO_ERR_INVALID, "reppo_linear: bad argument");
   c->launches = 0;
   if (c->tf32) {
-    // fp32 operands read as tf32 straight from the caller's buffers when TMA can address them
-    cudaError_t e;
-    if (op == 0) e = launch_gemm_tf32_tc(false, false, rows, out_f, in_f, a, in_f, b, in_f, out, out_f, bias, GEMM_STORE, 1, st);
-    else if (op == 1) e = launch_gemm_tf32_tc(false, true, rows, in_f, out_f, a, out_f, b, in_f, out, in_f, nullptr, GEMM_STORE, 1, st);
-    else e = launch_gemm_tf32_tc(true, true, out_f, in_f, rows, a, out_f, b, in_f, out, in_f, nullptr, GEMM_ATOMIC,
-                                 wgrad_split(out_f, in_f, rows, true), st);
+    // fp32 operands read as tf32 straight from the caller's buffers when TMA can address them, else from row-padded copies
+    cudaError_t e = cudaErrorNotSupported, p1 = cudaSuccess, p2 = cudaSuccess;
+    int la = 0, lb = 0;
+    if (op == 0) {          // a = x [rows, in], b = w [out, in]
+      const float* xa = tf32_operand(c, a, rows, in_f, 0, &la, st, &p1);
+      const float* wb = tf32_operand(c, b, out_f, in_f, 1, &lb, st, &p2);
+      if (xa && wb) e = launch_gemm_tf32_tc(false, false, rows, out_f, in_f, xa, la, wb, lb, out, out_f, bias, GEMM_STORE, 1, st);
+    } else if (op == 1) {   // a = dy [rows, out], b = w [out, in]
+      const float* da = tf32_operand(c, a, rows, out_f, 0, &la, st, &p1);
+      const float* wb = tf32_operand(c, b, out_f, in_f, 1, &lb, st, &p2);
+      if (da && wb) e = launch_gemm_tf32_tc(false, true, rows, in_f, out_f, da, la, wb, lb, out, in_f, nullptr, GEMM_STORE, 1, st);
+    } else {                // a = dy [rows, out], b = x [rows, in]
+      const float* da = tf32_operand(c, a, rows, out_f, 0, &la, st, &p1);
+      const float* xb = tf32_operand(c, b, rows, in_f, 1, &lb, st, &p2);
+      if (da && xb) e = launch_gemm_tf32_tc(true, true, out_f, in_f, rows, da, la, xb, lb, out, in_f, nullptr, GEMM_ATOMIC,
+                                            wgrad_split(out_f, in_f, rows, true), st);
+    }
+    if (p1 != cudaSuccess || p2 != cudaSuccess) return fail(c, REPPO_ERR_CUDA, "pad_rows_f32 failed");
     if (e != cudaErrorNotSupported) { CK(e); return REPPO_OK; }
   }
   if (!c->tc) {

@@ -70,6 +70,7 @@ struct PackEntry { const float* w; void* wb; int out, in, ld_b; };
 constexpr int kMaxPack = 16;
 struct PackTable { int n; int fp32; PackEntry e[kMaxPack]; };   // fp32: the shadow keeps fp32 (tf32 GEMM operands), else bf16
 cudaError_t launch_pack_weights(const PackTable& t, cudaStream_t st);
+cudaError_t launch_pad_rows_f32(const float* src, int rows, int cols, int ld_src, float* dst, int ld_dst, cudaStream_t st);
 cudaError_t launch_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, cudaStream_t st);
 cudaError_t launch_colsum(const float* X, int M, int N, int ld, float* out, float* out2, float scale2, cudaStream_t st);
 
