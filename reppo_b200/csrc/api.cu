@@ -72,8 +72,6 @@ struct NcclApi {
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
-  int (*GroupStart)() = nullptr;   // optional (grouped data-parallel schedule)
-  int (*GroupEnd)() = nullptr;
 };
 
 struct GraphKey {
@@ -1358,8 +1356,6 @@ static int nccl_load(reppo_ctx* c) {
   c->nccl.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t)>(dlsym(c->nccl.lib, "ncclAllReduce"));
   c->nccl.CommDestroy = reinterpret_cast<int (*)(ncclComm_t)>(dlsym(c->nccl.lib, "ncclCommDestroy"));
   c->nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(c->nccl.lib, "ncclGetErrorString"));
-  c->nccl.GroupStart = reinterpret_cast<int (*)()>(dlsym(c->nccl.lib, "ncclGroupStart"));
-  c->nccl.GroupEnd = reinterpret_cast<int (*)()>(dlsym(c->nccl.lib, "ncclGroupEnd"));
   if (!c->nccl.GetUniqueId || !c->nccl.CommInitRank || !c->nccl.AllReduce || !c->nccl.CommDestroy || !c->nccl.GetErrorString)
     return fail(c, REPPO_ERR_NCCL, "libnccl is missing required symbols");
   return REPPO_OK;

@@ -70,6 +70,10 @@ def _gloo_worker(rank, world, port, out):
         assert abs(red[L.METRIC_NAMES.index("critic_loss")].item() - m_full["loss"].item()) < 1e-5
         assert red[L.METRIC_NAMES.index("target_max")].item() == m_full["target_max"].item()
         assert red[L.METRIC_NAMES.index("target_min")].item() == m_full["target_min"].item()
+        # (4) the multicast exchange needs NCCL + NVSwitch multicast memory: on any other backend the attach declines before it
+        # touches the engine, and the caller stays on the collectives it already has
+        assert D.attach_multicast(object()) is False
+        assert D.RECOMMENDED_NCCL_ENV == {"NCCL_PROTO": "LL"}
         if rank == 0:
             out.put("ok")
     finally:
