@@ -335,6 +335,11 @@ def measure_config(name, semantics, gemm, world, rank, dev, steps, warmup, stron
     step_metrics = torch.empty(E * n_mb, 24, device=dev)
 
     def one_update():
+        # the update's own random draws are part of it (learn_step shuffles and samples inside, src/jaxrl/reppo.py:535-557,645-647)
+        for e in range(E):
+            perms[e].copy_(torch.randperm(S, device=dev, generator=g))
+        eps_pi.normal_(generator=g)
+        eps_kl.normal_(generator=g)
         eng.td_lambda(devb["soft_reward"], devb["value"], devb["done"], devb["truncated"], devb["importance_weight"],
                       h.gamma, h.lmbda, out=target)
         eng.sync_actor_old()
@@ -545,6 +550,12 @@ def main():
     use_graph = not args.no_graph
 
     def one_update():
+        # the update's own random draws are inside the timed region (learn_step shuffles and samples inside,
+        # src/jaxrl/reppo.py:535-557,645-647); same buffers every time, so the captured graph is replayed
+        for e in range(E):
+            perms[e].copy_(torch.randperm(S, device=dev, generator=g))
+        eps_pi.normal_(generator=g)
+        eps_kl.normal_(generator=g)
         eng.td_lambda(devb["soft_reward"], devb["value"], devb["done"], devb["truncated"], devb["importance_weight"],
                       h.gamma, h.lmbda, out=target)
         eng.sync_actor_old()
