@@ -172,10 +172,13 @@ def _scalar(v):
 
 def main(cfg: Optional[DictConfig] = None, overrides: Sequence[str] = (), *, envs=None, eval_envs=None,
          log_fn: Optional[Callable[[dict, int], None]] = None, fused: bool = True, max_updates: Optional[int] = None,
-         return_state: bool = False):
+         return_state: bool = False, checkpoint_path: Optional[str] = None, save_path: Optional[str] = None):
     """Train.  ``cfg``: a composed config (``config.compose``) or None to compose ``overrides`` like the hydra CLI.
     ``envs`` / ``eval_envs``: pre-built environments (else ``make_envs``).  ``log_fn(logs, frame)`` stands where the
-    reference calls ``wandb.log``.  Returns the list of per-update log dicts (and the final TrainState on request)."""
+    reference calls ``wandb.log``.  ``checkpoint_path`` resumes from a file in the reference's checkpoint layout (the branch the
+    reference leaves as a TODO, src/torchrl/reppo.py:579-594), ``save_path`` writes one at the end (``torch_api.save_params`` /
+    ``load_params``, src/torchrl/reppo_util.py:723-753).  Returns the list of per-update log dicts (and the final TrainState on
+    request)."""
     if cfg is None:
         # the Torch entry point does not merge experiment_overrides into hyperparameters (src/torchrl/reppo.py never does)
         cfg = compose(list(overrides), merge_overrides=False)
@@ -225,6 +228,9 @@ def main(cfg: Optional[DictConfig] = None, overrides: Sequence[str] = (), *, env
         update_actor = T.make_actor_update_fn(cfg, train_state)
 
     global_step = 0
+    if checkpoint_path:
+        global_step = int(T.load_params(checkpoint_path, train_state.actor, train_state.critic, train_state.normalizer,
+                                        train_state.critic_normalizer, old_actor=train_state.old_actor))
     total_env_steps = int(h.total_time_steps) // (int(h.num_envs) * int(h.num_steps)) + 1
     if max_updates is not None:
         total_env_steps = min(total_env_steps, int(max_updates))
@@ -281,6 +287,9 @@ def main(cfg: Optional[DictConfig] = None, overrides: Sequence[str] = (), *, env
             if log_fn is not None:
                 log_fn(logs, global_step * frames)
         global_step += 1
+    if save_path:
+        T.save_params(global_step, train_state.actor, train_state.critic, None, train_state.normalizer, train_state.critic_normalizer,
+                      {"env": dict(cfg.env), "hyperparameters": dict(h)}, save_path)
     return (history, train_state) if return_state else history
 
 

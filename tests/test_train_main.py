@@ -103,3 +103,19 @@ def test_main_learns_on_synthetic_env():
     first = sum(x["critic/qf_loss"] for x in h[:3]) / 3
     last = sum(x["critic/qf_loss"] for x in h[-3:]) / 3
     assert last < first
+
+
+@pytest.mark.gpu
+def test_main_checkpoint_resume(tmp_path):
+    """save_path / checkpoint_path: a run that stops after 3 updates and is resumed holds the saved networks and normaliser
+    statistics and continues from the saved step (the loop the reference leaves as a TODO, src/torchrl/reppo.py:579-594)."""
+    from reppo_b200.train import main
+    path = str(tmp_path / "ckpt.pt")
+    h1, ts1 = main(_small_cfg(), max_updates=3, save_path=path, return_state=True)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert ck["global_step"] == 3 and set(ck) >= {"actor_state_dict", "qnet_state_dict", "obs_normalizer_state", "args"}
+    for k, v in ts1.actor.state_dict().items():
+        assert torch.equal(ck["actor_state_dict"][k], v.cpu()), k
+    h2, ts2 = main(_small_cfg(), max_updates=5, checkpoint_path=path, return_state=True)
+    assert len(h1) == 3 and len(h2) == 2 and h2[0]["frame"] == 3 * 64 * 8      # resumed at update 3
+    assert ts2.normalizer.count.item() > ts1.normalizer.count.item()
